@@ -1,0 +1,229 @@
+/*
+ * ssb.h -- C ABI of libsemiseg_b200.so: the sm_100a kernels behind the SemiSegECG
+ * training hot path (1-D ResNet + FCN head + semi-supervised step).
+ *
+ * The reference (bakqui/semi-seg-ecg) has NO FFI/plugin interface: every GPU op on
+ * its hot path is a PyTorch library call.  Each entry point below
+ * therefore names the reference call site whose device work it replaces (file:line
+ * relative to the reference tree).  Host code (Python, semi-seg-ecg_b200/src) binds
+ * these with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, ints, floats; no torch / C++ types.
+ *  - the caller owns every buffer (incl. workspaces); the library never allocates or
+ *    frees device memory and never synchronises: all work is enqueued on `stream`
+ *    and is CUDA-graph capturable.
+ *  - return value: 0 on success, negative ssb_status otherwise; the message is
+ *    available (thread-local) from ssb_last_error().  The library never exits.
+ *  - dtype: SSB_F32 (exact-parity mode, 1e-5) or SSB_BF16 (2e-2 mode) = storage type
+ *    of activations / activation gradients / repacked weights.  Accumulation is fp32,
+ *    BatchNorm statistics fp64, master weights / optimizer state fp32.
+ *
+ * Activation layout ("flat padded NLC"): a tensor with B samples, C channels and
+ * `len` valid positions per sample is stored as rows of C contiguous channels,
+ * `pitch` rows per sample: row(b, t) = b*pitch + 1 + t.  Row b*pitch (front halo)
+ * and rows b*pitch+len+1 .. (b+1)*pitch-1 (back pad, >= 1 row) are ZERO; every kernel
+ * that writes such a tensor writes zeros there.  The halo rows implement the convs'
+ * zero padding, so a k=3 conv is three row-shifted GEMMs over the flat row space and
+ * M-tiles may span samples.  For a stride-2 layer pitch_in == 2*pitch_out, which makes
+ * input row pairs line up with output rows (pair q <-> output row q+1).
+ * C must be a multiple of 8.
+ */
+#ifndef SSB_H_
+#define SSB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSB_VERSION 1
+
+typedef void* ssb_stream_t; /* cudaStream_t */
+
+enum ssb_status {
+  SSB_OK = 0,
+  SSB_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  SSB_ERR_CUDA = -2,      /* CUDA runtime / driver error (launch failed) */
+  SSB_ERR_UNSUPPORTED = -3 /* device is not sm_100 / algo not available for shape */
+};
+
+enum ssb_dtype { SSB_F32 = 0, SSB_BF16 = 1 };
+enum ssb_algo { SSB_ALGO_SIMT = 0, SSB_ALGO_TCGEN05 = 1 };
+enum ssb_loss_mode { SSB_LOSS_SUP = 0, SSB_LOSS_FIXMATCH = 1, SSB_LOSS_SOFT = 2 };
+
+/* geometry of one flat padded NLC tensor */
+typedef struct ssb_geom {
+  int32_t B;      /* samples */
+  int32_t pitch;  /* rows per sample (>= len + 2) */
+  int32_t len;    /* valid positions per sample */
+  int32_t C;      /* channels (multiple of 8) */
+} ssb_geom;
+
+/* one BatchNorm1d layer: parameter, buffer, statistic and gradient pointers
+ * (nn.BatchNorm1d at resnet.py:41,50,254,290 and fcn_head.py:48). */
+typedef struct ssb_bn {
+  const float* gamma;      /* [C] weight */
+  const float* beta;       /* [C] bias */
+  float* running_mean;     /* [C] */
+  float* running_var;      /* [C] */
+  int64_t* num_batches_tracked; /* scalar, may be NULL */
+  double* sums;            /* [2C] batch sum(x), sum(x^2); zeroed by the caller before ssb_bn_stats */
+  float* mean_invstd;      /* [2C] batch mean / invstd saved by the train-mode forward */
+  double* bwd_sums;        /* [2C] sum(g), sum(g*xhat); zeroed by the caller before the reduce */
+  float* dgamma;           /* [C] gradient of weight (written, not accumulated) */
+  float* dbeta;            /* [C] gradient of bias */
+  int32_t count_mul;       /* SyncBN: world size (sums hold the all-reduced totals); 0/1 = local */
+  int32_t pad;
+} ssb_bn;
+
+/* per-step scalars that change between replays of a captured step graph; lives in
+ * device memory and is refreshed by one small H2D copy per step */
+typedef struct ssb_step_params {
+  float lr;            /* utils/lr_sched.py:6-18 */
+  float inv_bias1;     /* 1/(1-beta1^t) */
+  float inv_sqrt_bias2;/* 1/sqrt(1-beta2^t) */
+  float ema_decay;     /* mean_teacher.py:46 */
+  int32_t ema_first;   /* 1 while the teacher still aliases the student (mean_teacher.py:285-290) */
+  int32_t step;        /* optimizer step count t (1-based) */
+  uint32_t rng_seed;   /* dropout RNG key */
+  uint32_t rng_step;   /* dropout RNG counter */
+  float grad_scale;    /* multiplies gradients before the update (1/world_size after all-reduce sum) */
+  float conf_thresh;   /* fixmatch.py:115 */
+  float pad[6];
+} ssb_step_params;
+
+/* descriptor of one conv weight for the multi-tensor repack */
+typedef struct ssb_repack_desc {
+  const float* w;  /* master weight [Cout][Cin][k] fp32 (reference layout) */
+  void* w_kio;     /* [k][Cin][Cout] in `dtype` */
+  void* w_koi;     /* [k][Cout][Cin] in `dtype` */
+  int32_t Cout, Cin, k, pad;
+} ssb_repack_desc;
+
+/* ---- library / device ------------------------------------------------------------ */
+int ssb_version(void);
+const char* ssb_last_error(void);
+/* 0 if the current CUDA device can run these kernels (compute capability 10.x) */
+int ssb_device_check(void);
+/* number of kernels launched by this library since load (all threads); for bench accounting */
+int64_t ssb_launch_count(void);
+
+int ssb_memset_zero(void* p, size_t bytes, ssb_stream_t stream);
+
+/* ---- stem: Conv1d(C_leads -> Cs, k7, s2, p3, bias=False)  (resnet.py:246-253) ------ */
+/* x: [B, Cl, L] fp32 NCL (the reference's input layout); w: [Cs][Cl][7] fp32 master
+ * weight; y: flat padded NLC, geometry g (g.len = floor((L-1)/2)+1, g.C = Cs). */
+int ssb_stem_conv_fwd(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g,
+                      int dtype, ssb_stream_t stream);
+/* dw[Cs][Cl][7] (fp32) += sum_{b,t} dy * x   (conv backward w.r.t. weight; the stem has no dgrad) */
+int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L, ssb_geom g,
+                        int dtype, ssb_stream_t stream);
+
+/* ---- Conv1d k in {1,3}, stride in {1,2}, padding k/2, dilation 1, bias=False --------
+ * (resnet.py:32-49, 283-289; fcn_head.py:40-47).  gin/gout: geometries of the conv
+ * input / output tensors (same B; gin.pitch == stride*gout.pitch).
+ * w_kio / w_koi: repacked weights (ssb_weight_repack).  algo SSB_ALGO_TCGEN05 needs
+ * dtype bf16 and Cin, Cout multiples of 64. */
+int ssb_conv1d_fwd(const void* x, const void* w_kio, const void* w_koi, void* y,
+                   ssb_geom gin, ssb_geom gout, int k, int stride,
+                   int dtype, int algo, ssb_stream_t stream);
+/* dx = conv_transpose(dy, w) (+ dx if accumulate) */
+int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void* dx,
+                     ssb_geom gin, ssb_geom gout, int k, int stride, int accumulate,
+                     int dtype, int algo, ssb_stream_t stream);
+/* dw[Cout][Cin][k] (fp32, reference layout) += x^T dy; the caller zeroes dw once per step */
+int ssb_conv1d_wgrad(const void* x, const void* dy, float* dw,
+                     ssb_geom gin, ssb_geom gout, int k, int stride,
+                     int dtype, int algo, ssb_stream_t stream);
+/* master fp32 [Cout][Cin][k] -> both GEMM layouts in `dtype`, all convs in one launch;
+ * table_dev: device array of n descriptors */
+int ssb_weight_repack(const ssb_repack_desc* table_dev, int n, int max_elems, int dtype,
+                      ssb_stream_t stream);
+
+/* ---- BatchNorm1d (+ReLU, +residual, +MaxPool) -------------------------------------- */
+/* sums[0:C] += sum_rows x, sums[C:2C] += sum_rows x^2 (fp64) */
+int ssb_bn_stats(const void* x, ssb_geom g, double* sums, int dtype, ssb_stream_t stream);
+/* y = [relu]( bn(x) [+ bn_res(res) | + res] ).  train != 0: batch statistics from
+ * bn->sums (count B*len), saves mean/invstd, updates running stats (momentum 0.1,
+ * unbiased var) and num_batches_tracked; train == 0: running statistics.
+ * res may be NULL; bn_res NULL with res != NULL means identity residual.
+ * (resnet.py:58-70: bn1+relu, bn2 + identity/downsample + relu; fcn_head.py:48-49) */
+int ssb_bn_act_fwd(const void* x, const ssb_bn* bn, const void* res, const ssb_bn* bn_res,
+                   void* y, ssb_geom g, int relu, int train, int dtype, ssb_stream_t stream);
+/* stem tail: MaxPool1d(3,2,1)(relu(bn(c0)))  (resnet.py:254-257, 354-355) */
+int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, ssb_geom gin,
+                              ssb_geom gout, int train, int dtype, ssb_stream_t stream);
+/* backward, pass 1: g = (g1 [+ g2]) * (y > 0 if y != NULL);  bn->bwd_sums += (sum g, sum g*xhat);
+ * if x_res/bn_res given the same for the residual-branch BN. */
+int ssb_bn_bwd_reduce(const void* g1, const void* g2, const void* y, const void* x,
+                      const ssb_bn* bn, const void* x_res, const ssb_bn* bn_res,
+                      ssb_geom g, int dtype, ssb_stream_t stream);
+/* backward, pass 2: dx = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); writes dgamma/dbeta;
+ * residual branch: dx_res likewise (bn_res) or, for an identity residual, g itself to g_ident. */
+int ssb_bn_bwd_apply(const void* g1, const void* g2, const void* y, const void* x,
+                     const ssb_bn* bn, void* dx, const void* x_res, const ssb_bn* bn_res,
+                     void* dx_res, void* g_ident, ssb_geom g, int dtype, ssb_stream_t stream);
+/* stem tail backward (max-pool scatter + relu + bn), same two passes; gp: grad w.r.t. pooled output */
+int ssb_stem_bwd_reduce(const void* gp, const void* c0, const ssb_bn* bn, ssb_geom gin,
+                        ssb_geom gout, int dtype, ssb_stream_t stream);
+int ssb_stem_bwd_apply(const void* gp, const void* c0, const ssb_bn* bn, void* dc0, ssb_geom gin,
+                       ssb_geom gout, int dtype, ssb_stream_t stream);
+
+/* ---- FCN head tail: Dropout(p) + Conv1d(C -> ncls, 1, bias=True)  (fcn_head.py:83-97) --- */
+/* a: flat padded NLC [B*pitch, C]; low: [B, len, ncls] fp32 (compact).
+ * drop_mask: optional explicit keep-mask u8 [B, len, C] (tests); else if p > 0 and
+ * sp != NULL a counter-based RNG keyed by (sp->rng_seed, sp->rng_step, element). */
+int ssb_head_cls_fwd(const void* a, const float* w, const float* bias, float* low, ssb_geom g,
+                     int ncls, float p, const uint8_t* drop_mask, const ssb_step_params* sp,
+                     int dtype, ssb_stream_t stream);
+int ssb_head_cls_bwd(const float* dlow, const void* a, const float* w, void* da, float* dw,
+                     float* dbias, ssb_geom g, int ncls, float p, const uint8_t* drop_mask,
+                     const ssb_step_params* sp, int dtype, ssb_stream_t stream);
+
+/* ---- linear upsample (F.interpolate, encoder_decoder.py:102-107) ------------------- */
+/* low [B, Lin, ncls] fp32 -> out [B, ncls, Lout] fp32 (reference NCL logits) */
+int ssb_upsample_fwd(const float* low, float* out, int B, int Lin, int Lout, int ncls,
+                     int align_corners, ssb_stream_t stream);
+/* dlow [B, Lin, ncls] = gather-reduce of dout [B, ncls, Lout] (deterministic) */
+int ssb_upsample_bwd(const float* dout, float* dlow, int B, int Lin, int Lout, int ncls,
+                     int align_corners, ssb_stream_t stream);
+
+/* ---- pseudo-labels (fixmatch.py:89-91,115) ----------------------------------------- */
+/* logits [U, ncls, L] fp32 NCL -> conf f32 [U,L], label i64 [U,L], mask u8 [U,L];
+ * bit-exact with torch softmax(1).max(1)[0] / argmax(1) / (conf >= thr) on CUDA */
+int ssb_pseudo_label(const float* logits, float thr, float* conf, int64_t* label, uint8_t* mask,
+                     int U, int ncls, int L, ssb_stream_t stream);
+
+/* ---- fused upsample + softmax + pseudo-label + loss + gradient -----------------------
+ * (fixmatch.py:87-118, mean_teacher.py:90-117, base.py/encoder_decoder.py:110-111)
+ * low_s: student low-res logits [Bl+Bu, Lin, ncls]; target: int64 [Bl, L];
+ * low_t: teacher / self-eval low-res logits [Bu, Lin, ncls] (NULL for SSB_LOSS_SUP).
+ * dlow: gradient of the total loss w.r.t. low_s (written).  sums (fp64[4], zeroed by the
+ * caller) += { sum CE_x, sum masked CE_u or soft CE_u, sum mask, 0 }.
+ * Total loss = sum_x/(Bl*L) for SUP, else (sum_x/(Bl*L) + sum_u/(Bu*L))/2.
+ * Optional materialised outputs (may be NULL): conf f32 [Bu,L], label i64 [Bu,L], mask u8 [Bu,L].
+ * thr is read from sp->conf_thresh when sp != NULL, else from thr. */
+int ssb_semi_loss(const float* low_s, const int64_t* target, const float* low_t, float* dlow,
+                  double* sums, int Bl, int Bu, int Lin, int L, int ncls, int mode, float thr,
+                  const ssb_step_params* sp, int align_corners, float* conf, int64_t* label,
+                  uint8_t* mask, ssb_stream_t stream);
+
+/* ---- fused multi-tensor AdamW (+ EMA teacher)  (optimizer.py:22-34, mean_teacher.py:139-149) --- */
+/* flat arenas of n floats.  p_ema may be NULL.  Scalars come from sp (device). */
+int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, size_t n,
+                  float beta1, float beta2, float eps, float weight_decay,
+                  const ssb_step_params* sp, ssb_stream_t stream);
+/* dst = dst*d + src*(1-d) (teacher BN buffers); d from sp->ema_decay */
+int ssb_ema(float* dst, const float* src, size_t n, const ssb_step_params* sp, ssb_stream_t stream);
+/* teacher num_batches_tracked quirk: dst_f32[i] = dst_f32[i]*d + (float)src_i64[i]*(1-d) */
+int ssb_ema_i64(float* dst, const int64_t* src, size_t n, const ssb_step_params* sp, ssb_stream_t stream);
+/* out[0] = sqrt(sum g^2) (misc.py:265-278); ws: fp64[1] zeroed by the caller */
+int ssb_grad_norm(const float* g, size_t n, double* ws, float* out, ssb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB_H_ */

@@ -1,0 +1,480 @@
+"""CPU oracle: restatement of the SemiSegECG training hot path (TEST INFRASTRUCTURE ONLY).
+
+Every function cites the reference location (relative to /root/reference) whose
+behaviour it restates.  Nothing here is copied from the reference; the model is
+expressed functionally over a ``state_dict``-shaped mapping (same key names as the
+reference) so that the same tensors can be fed to the
+reference, to this oracle and to the CUDA path.
+
+Arithmetic: plain PyTorch on whatever device/dtype the inputs live on (CPU fp32 /
+fp64 for parity truth; the pseudo-label helpers are also run on CUDA tensors by the
+bit-exactness tests so that the comparison target is torch's own CUDA soft-max).
+Third-party arithmetic: ``torch.nn.functional.conv1d`` (PyTorch; reference pins
+torch==1.11.0+cu113 in requirements.txt:8, this image has torch 2.11.0).
+
+Parity pinning: pinned against outputs of the reference itself, see
+tests/golden/make_golden.py and tests/test_oracle_golden.py.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------------------
+# architecture description
+# --------------------------------------------------------------------------------------
+@dataclass
+class Arch:
+    """Shape parameters of EncoderDecoder(resnet18-style BasicBlock net, FCNHead).
+
+    Mirrors the constructor arguments in src/models/backbones/resnet.py:135-204 and
+    src/models/decode_heads/fcn_head.py:10-24 that the hot path uses.
+    """
+    num_leads: int = 1
+    stem_channels: int = 64
+    base_channels: int = 64
+    strides: Tuple[int, ...] = (1, 2, 2, 2)
+    stage_blocks: Tuple[int, ...] = (2, 2, 2, 2)
+    head_channels: int = 128
+    num_classes: int = 4
+    in_index: int = 3
+    dropout_ratio: float = 0.1
+    align_corners: bool = False
+
+    @staticmethod
+    def from_config(cfg: dict) -> "Arch":
+        """YAML dict -> Arch (algorithms/base.py:32-43 reads the same two sub-dicts)."""
+        bname, bkw = list(cfg["backbone"].items())[0]
+        hname, hkw = list(cfg["decode_head"].items())[0]
+        blocks = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}[bname]
+        ns = bkw.get("num_stages", 4)
+        return Arch(
+            num_leads=bkw["num_leads"],
+            stem_channels=bkw.get("stem_channels", 64),
+            base_channels=bkw.get("base_channels", 64),
+            strides=tuple(bkw.get("strides", (1, 2, 2, 2)))[:ns],
+            stage_blocks=tuple(blocks)[:ns],
+            head_channels=hkw["channels"],
+            num_classes=hkw["num_classes"],
+            in_index=hkw.get("in_index", -1),
+            dropout_ratio=hkw.get("dropout_ratio", 0.1),
+            align_corners=hkw.get("align_corners", False),
+        )
+
+    def planes(self, i: int) -> int:
+        return self.base_channels * 2 ** i
+
+
+def conv_out_len(L: int, k: int, s: int, p: int, d: int = 1) -> int:
+    """L_out = floor((L + 2p - d(k-1) - 1)/s) + 1 (torch Conv1d/MaxPool1d length rule)."""
+    return (L + 2 * p - d * (k - 1) - 1) // s + 1
+
+
+def stage_lengths(arch: Arch, L: int) -> List[int]:
+    """[stem, pooled, stage1..stageN] lengths; resnet.py:246-257 (k7 s2 p3, pool k3 s2 p1)."""
+    out = [conv_out_len(L, 7, 2, 3)]
+    out.append(conv_out_len(out[-1], 3, 2, 1))
+    cur = out[-1]
+    for s in arch.strides:
+        cur = conv_out_len(cur, 3, s, 1)
+        out.append(cur)
+    return out
+
+
+def param_names(arch: Arch) -> List[str]:
+    """Parameter names in ``model.parameters()`` order (registration order of
+    resnet.py:181-199 / BasicBlock 31-51 / fcn_head.py:70-83)."""
+    names = ["backbone.stem.0.weight", "backbone.stem.1.weight", "backbone.stem.1.bias"]
+    inpl = arch.stem_channels
+    for i, nb in enumerate(arch.stage_blocks):
+        pl = arch.planes(i)
+        for j in range(nb):
+            pre = f"backbone.layer{i + 1}.{j}"
+            names += [f"{pre}.conv1.weight", f"{pre}.bn1.weight", f"{pre}.bn1.bias",
+                      f"{pre}.conv2.weight", f"{pre}.bn2.weight", f"{pre}.bn2.bias"]
+            if j == 0 and (arch.strides[i] != 1 or inpl != pl):
+                names += [f"{pre}.downsample.0.weight", f"{pre}.downsample.1.weight",
+                          f"{pre}.downsample.1.bias"]
+        inpl = pl
+    names += ["decode_head.convs.0.0.weight", "decode_head.convs.0.1.weight",
+              "decode_head.convs.0.1.bias", "decode_head.cls_seg.weight", "decode_head.cls_seg.bias"]
+    return names
+
+
+def bn_prefixes(arch: Arch) -> List[str]:
+    """BatchNorm module prefixes in ``model.buffers()`` order."""
+    out = []
+    for n in param_names(arch):
+        if n.endswith(".bias") and not n.endswith("cls_seg.bias"):
+            out.append(n[: -len(".bias")])
+    return out
+
+
+def buffer_names(arch: Arch) -> List[str]:
+    out = []
+    for p in bn_prefixes(arch):
+        out += [p + ".running_mean", p + ".running_var", p + ".num_batches_tracked"]
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# layer restatements
+# --------------------------------------------------------------------------------------
+def batchnorm(x: Tensor, sd: Dict[str, Tensor], pre: str, train: bool,
+              new_buffers: Optional[Dict[str, Tensor]], eps: float = 1e-5, momentum: float = 0.1) -> Tensor:
+    """nn.BatchNorm1d as used at resnet.py:41,50,254,290 and fcn_head.py:48.
+
+    train: biased batch variance for normalisation, unbiased for the running estimate,
+    running <- 0.9*running + 0.1*batch, num_batches_tracked += 1.  eval: running stats.
+    """
+    g, b = sd[pre + ".weight"], sd[pre + ".bias"]
+    if train:
+        n = x.shape[0] * x.shape[2]
+        mean = x.mean(dim=(0, 2))
+        var = ((x - mean[None, :, None]) ** 2).mean(dim=(0, 2))
+        if new_buffers is not None:
+            with torch.no_grad():
+                rm, rv = sd[pre + ".running_mean"], sd[pre + ".running_var"]
+                new_buffers[pre + ".running_mean"] = (1 - momentum) * rm + momentum * mean.detach().to(rm.dtype)
+                new_buffers[pre + ".running_var"] = (1 - momentum) * rv + momentum * (var.detach() * (n / (n - 1))).to(rv.dtype)
+                new_buffers[pre + ".num_batches_tracked"] = sd[pre + ".num_batches_tracked"] + 1
+    else:
+        mean = sd[pre + ".running_mean"].to(x.dtype)
+        var = sd[pre + ".running_var"].to(x.dtype)
+    invstd = 1.0 / torch.sqrt(var + eps)
+    return (x - mean[None, :, None]) * (invstd * g)[None, :, None] + b[None, :, None]
+
+
+def maxpool_k3s2p1(x: Tensor) -> Tensor:
+    """nn.MaxPool1d(3, 2, 1) (resnet.py:257): -inf padding, window {2t-1, 2t, 2t+1}."""
+    xp = F.pad(x, (1, 1), value=float("-inf"))
+    return xp.unfold(2, 3, 2).max(dim=-1).values
+
+
+def linear_upsample(x: Tensor, L_out: int, align_corners: bool = False) -> Tensor:
+    """F.interpolate(mode='linear') as called at encoder_decoder.py:102-107.
+
+    align_corners=False: src = max((t+0.5)*L_in/L_out - 0.5, 0); two-tap lerp.
+    Index arithmetic is done in the tensor's dtype (ATen uses float for float tensors).
+    """
+    L_in = x.shape[-1]
+    t = torch.arange(L_out, dtype=x.dtype, device=x.device)
+    if align_corners:
+        scale = (L_in - 1) / (L_out - 1) if L_out > 1 else 0.0
+        src = t * torch.tensor(scale, dtype=x.dtype, device=x.device)
+    else:
+        scale = torch.tensor(L_in, dtype=x.dtype, device=x.device) / L_out
+        src = torch.clamp((t + 0.5) * scale - 0.5, min=0)
+    i0 = torch.floor(src).long()
+    i1 = torch.clamp(i0 + 1, max=L_in - 1)
+    w1 = src - i0.to(x.dtype)
+    w0 = 1.0 - w1
+    return x[..., i0] * w0 + x[..., i1] * w1
+
+
+def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
+            dropout_mask: Optional[Tensor] = None,
+            new_buffers: Optional[Dict[str, Tensor]] = None,
+            taps: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+    """EncoderDecoder.forward (encoder_decoder.py:78-108) over resnet.py:353-363
+    (stem -> maxpool -> BasicBlocks, resnet.py:55-72) and FCNHead.forward (fcn_head.py:89-97).
+
+    x: [B, C, L].  dropout_mask: [B, head_channels, L_head] of {0,1} (keep mask) applied as
+    ``h * mask / (1-p)`` in train mode; None means no dropout (p=0 or eval).
+    Returns {'seg_logits': [B, ncls, L], 'low_logits': [B, ncls, L_head]}.
+    If ``taps`` is a dict it is filled with named intermediate activations (module-output
+    granularity) for per-layer parity checks.
+    """
+    def tap(name, t):
+        if taps is not None:
+            taps[name] = t
+        return t
+
+    L = x.shape[2]
+    h = F.conv1d(x, sd["backbone.stem.0.weight"], None, stride=2, padding=3)
+    tap("backbone.stem.0", h)
+    h = torch.relu(batchnorm(h, sd, "backbone.stem.1", train, new_buffers))
+    tap("backbone.stem", h)
+    h = maxpool_k3s2p1(h)
+    tap("backbone.maxpool", h)
+    feats = []
+    inpl = arch.stem_channels
+    for i, nb in enumerate(arch.stage_blocks):
+        pl = arch.planes(i)
+        for j in range(nb):
+            pre = f"backbone.layer{i + 1}.{j}"
+            s = arch.strides[i] if j == 0 else 1
+            ident = h
+            o = F.conv1d(h, sd[pre + ".conv1.weight"], None, stride=s, padding=1)
+            tap(pre + ".conv1", o)
+            o = torch.relu(batchnorm(o, sd, pre + ".bn1", train, new_buffers))
+            o = F.conv1d(o, sd[pre + ".conv2.weight"], None, stride=1, padding=1)
+            tap(pre + ".conv2", o)
+            o = batchnorm(o, sd, pre + ".bn2", train, new_buffers)
+            if (pre + ".downsample.0.weight") in sd:
+                ident = F.conv1d(h, sd[pre + ".downsample.0.weight"], None, stride=s, padding=0)
+                tap(pre + ".downsample.0", ident)
+                ident = batchnorm(ident, sd, pre + ".downsample.1", train, new_buffers)
+            h = torch.relu(o + ident)
+            tap(pre, h)
+        inpl = pl
+        feats.append(h)
+    f = feats[arch.in_index]
+    h = F.conv1d(f, sd["decode_head.convs.0.0.weight"], None, stride=1, padding=1)
+    tap("decode_head.convs.0.0", h)
+    h = torch.relu(batchnorm(h, sd, "decode_head.convs.0.1", train, new_buffers))
+    tap("decode_head.convs.0", h)
+    if train and dropout_mask is not None and arch.dropout_ratio > 0:
+        h = h * dropout_mask.to(h.dtype) / (1.0 - arch.dropout_ratio)
+    low = F.conv1d(h, sd["decode_head.cls_seg.weight"], sd["decode_head.cls_seg.bias"])
+    tap("decode_head.cls_seg", low)
+    seg = linear_upsample(low, L, arch.align_corners)
+    return {"seg_logits": seg, "low_logits": low}
+
+
+# --------------------------------------------------------------------------------------
+# pseudo-labels and losses
+# --------------------------------------------------------------------------------------
+def pseudo_label(logits: Tensor, conf_thresh: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """fixmatch.py:89-91,115: conf = softmax(1).max(1)[0]; label = argmax(1); mask = conf >= thr.
+
+    Uses torch's own soft-max/arg-max so that, run on a CUDA tensor, it is the exact
+    comparison target for the bit-exactness tests.
+    """
+    conf = logits.softmax(dim=1).max(dim=1)[0]
+    label = logits.argmax(dim=1)
+    mask = conf >= conf_thresh
+    return conf, label, mask
+
+
+def log_softmax_c(z: Tensor) -> Tensor:
+    m = z.max(dim=1, keepdim=True).values
+    return z - m - torch.log(torch.exp(z - m).sum(dim=1, keepdim=True))
+
+
+def ce_hard(z: Tensor, y: Tensor) -> Tensor:
+    """F.cross_entropy(z, y) mean over all B*L positions (fixmatch.py:105; encoder_decoder.py:110-111)."""
+    return -(log_softmax_c(z).gather(1, y[:, None, :]).squeeze(1)).mean()
+
+
+def ce_masked(z: Tensor, y: Tensor, mask: Tensor) -> Tensor:
+    """(CE(z, y, 'none') * mask).mean(): denominator is ALL positions (fixmatch.py:114-116)."""
+    per = -(log_softmax_c(z).gather(1, y[:, None, :]).squeeze(1))
+    return (per * mask.to(per.dtype)).mean()
+
+
+def ce_soft(z: Tensor, p: Tensor) -> Tensor:
+    """F.cross_entropy(z, probs): mean over B*L of -sum_c p_c log softmax(z)_c (mean_teacher.py:115)."""
+    return -(p * log_softmax_c(z)).sum(dim=1).mean()
+
+
+def lr_at(epoch: float, cfg: dict) -> float:
+    """utils/lr_sched.py:6-18 -- linear warm-up then half-cosine to min_lr."""
+    if epoch < cfg["warmup_epochs"]:
+        return cfg["lr"] * epoch / cfg["warmup_epochs"]
+    return cfg["min_lr"] + (cfg["lr"] - cfg["min_lr"]) * 0.5 * (
+        1.0 + math.cos(math.pi * (epoch - cfg["warmup_epochs"]) / (cfg["epochs"] - cfg["warmup_epochs"])))
+
+
+def adamw_update(p: Tensor, g: Tensor, m: Tensor, v: Tensor, t: int, lr: float,
+                 betas=(0.9, 0.999), eps: float = 1e-8, wd: float = 0.05) -> None:
+    """torch.optim.AdamW single step, in place (utils/optimizer.py:22-34; amsgrad off)."""
+    b1, b2 = betas
+    p.mul_(1.0 - lr * wd)
+    m.mul_(b1).add_(g, alpha=1.0 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+    bc1 = 1.0 - b1 ** t
+    bc2 = 1.0 - b2 ** t
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+# --------------------------------------------------------------------------------------
+# the semi-supervised step
+# --------------------------------------------------------------------------------------
+class OracleTrainer:
+    """Stateful restatement of the train_one_epoch bodies:
+    fixmatch.py:73-138, mean_teacher.py:76-149, base.py:110-150 (use_amp=False path,
+    GradScaler disabled as it is on CPU -- misc.py:239-253)."""
+
+    def __init__(self, sd: Dict[str, Tensor], arch: Arch, train_cfg: dict, dtype=torch.float64):
+        self.arch = arch
+        self.cfg = train_cfg
+        self.dtype = dtype
+        self.pnames = param_names(arch)
+        self.bnames = buffer_names(arch)
+        self.sd: Dict[str, Tensor] = {}
+        for k, v in sd.items():
+            if k in self.pnames or (v.is_floating_point()):
+                self.sd[k] = v.detach().clone().to(dtype)
+            else:
+                self.sd[k] = v.detach().clone()
+        self.m = {k: torch.zeros_like(self.sd[k]) for k in self.pnames}
+        self.v = {k: torch.zeros_like(self.sd[k]) for k in self.pnames}
+        self.t = 0
+        self.grads: Dict[str, Tensor] = {}
+        self.taps: Dict[str, Tensor] = {}
+        # mean-teacher state (mean_teacher.py:281-290): params alias the student until the
+        # first EMA; buffers are the teacher's own fresh-init copies.
+        self.teacher_sd: Optional[Dict[str, Tensor]] = None
+        self.teacher_aliased = True
+
+    # ---- helpers -------------------------------------------------------------------
+    def _leaf_params(self) -> Dict[str, Tensor]:
+        sdg = dict(self.sd)
+        for k in self.pnames:
+            sdg[k] = self.sd[k].detach().clone().requires_grad_(True)
+        return sdg
+
+    def _apply_grads(self, sdg: Dict[str, Tensor], lr: float) -> None:
+        self.t += 1
+        kw = self.cfg.get("optimizer_kwargs", {}) or {}
+        betas = tuple(kw.get("betas", (0.9, 0.999)))
+        eps = kw.get("eps", 1e-8)
+        for k in self.pnames:
+            g = sdg[k].grad
+            self.grads[k] = g.detach().clone()
+            adamw_update(self.sd[k], g, self.m[k], self.v[k], self.t, lr, betas, eps,
+                         self.cfg["weight_decay"])
+
+    def grad_norm(self) -> float:
+        """misc.py:265-278 -- global L2 norm over all parameter gradients."""
+        return math.sqrt(sum(float((g.double() ** 2).sum()) for g in self.grads.values()))
+
+    def init_teacher(self, teacher_buffers: Optional[Dict[str, Tensor]] = None) -> None:
+        self.teacher_sd = {}
+        for k in self.bnames:
+            src = teacher_buffers[k] if teacher_buffers is not None else self.sd[k]
+            self.teacher_sd[k] = src.detach().clone().to(self.dtype) if src.is_floating_point() else src.detach().clone()
+        self.teacher_aliased = True
+
+    def _teacher_view(self) -> Dict[str, Tensor]:
+        tv = dict(self.teacher_sd)
+        if self.teacher_aliased:
+            for k in self.pnames:
+                tv[k] = self.sd[k]
+        return tv
+
+    def _ema(self, d: float) -> None:
+        """mean_teacher.py:139-149: k <- k*d + q*(1-d) over parameters AND buffers (the
+        int64 num_batches_tracked is promoted to float32 exactly as torch does)."""
+        tv = self._teacher_view()
+        for k in self.pnames:
+            self.teacher_sd[k] = tv[k] * d + self.sd[k] * (1.0 - d)
+        for k in self.bnames:
+            self.teacher_sd[k] = self.teacher_sd[k] * d + self.sd[k] * (1.0 - d)
+        self.teacher_aliased = False
+
+    # ---- steps ---------------------------------------------------------------------
+    def supervised_step(self, ecg: Tensor, target: Tensor, lr: float,
+                        dropout_mask: Optional[Tensor] = None, want_taps: bool = False) -> Dict[str, float]:
+        """base.py:110-150: model(x, y, return_loss=True) -> CE -> backward -> AdamW."""
+        sdg = self._leaf_params()
+        nb: Dict[str, Tensor] = {}
+        self.taps = {} if want_taps else None
+        out = forward(sdg, ecg.to(self.dtype), self.arch, True, dropout_mask, nb, self.taps)
+        if want_taps:
+            for t_ in self.taps.values():
+                if t_.requires_grad:
+                    t_.retain_grad()
+        self.low_logits = out["low_logits"]
+        self.low_logits.retain_grad()
+        loss = ce_hard(out["seg_logits"], target)
+        loss.backward()
+        self.sd.update(nb)
+        self._apply_grads(sdg, lr)
+        return {"loss": float(loss.detach())}
+
+    def fixmatch_step(self, ecg_x: Tensor, mask_x: Tensor, ecg_u_w: Tensor, ecg_u_s: Tensor,
+                      lr: float, dropout_mask: Optional[Tensor] = None, want_taps: bool = False) -> Dict[str, float]:
+        """fixmatch.py:79-138."""
+        thr = self.cfg["conf_thresh"]
+        with torch.no_grad():
+            pw = forward(self.sd, ecg_u_w.to(self.dtype), self.arch, False)["seg_logits"]
+            conf = pw.softmax(dim=1).max(dim=1)[0]
+            label = pw.argmax(dim=1)
+            # the reference compares an fp32 conf with the python float threshold
+            mask = conf >= (torch.tensor(thr, dtype=torch.float32).to(conf.dtype) if conf.dtype == torch.float32 else thr)
+        self.pseudo = {"conf": conf, "label": label, "mask": mask, "logits_w": pw}
+        sdg = self._leaf_params()
+        nb: Dict[str, Tensor] = {}
+        self.taps = {} if want_taps else None
+        nl = ecg_x.shape[0]
+        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps)
+        if want_taps:
+            for t_ in self.taps.values():
+                if t_.requires_grad:
+                    t_.retain_grad()
+        self.low_logits = out["low_logits"]
+        self.low_logits.retain_grad()
+        seg = out["seg_logits"]
+        loss_x = ce_hard(seg[:nl], mask_x)
+        loss_u = ce_masked(seg[nl:], label, mask)
+        loss = (loss_x + loss_u) / 2.0
+        loss.backward()
+        self.sd.update(nb)
+        self._apply_grads(sdg, lr)
+        return {"loss_total": float(loss.detach()), "loss_x": float(loss_x.detach()),
+                "loss_u_s": float(loss_u.detach()), "mask_ratio": float(mask.to(torch.float32).mean())}
+
+    def mean_teacher_step(self, ecg_x: Tensor, mask_x: Tensor, ecg_u_w: Tensor, ecg_u_s: Tensor,
+                          lr: float, dropout_mask: Optional[Tensor] = None, want_taps: bool = False) -> Dict[str, float]:
+        """mean_teacher.py:82-149."""
+        if self.teacher_sd is None:
+            self.init_teacher()
+        d = self.cfg.get("ema_decay", 0.999)
+        with torch.no_grad():
+            pw = forward(self._teacher_view(), ecg_u_w.to(self.dtype), self.arch, False)["seg_logits"]
+            prob = pw.softmax(dim=1)
+        self.pseudo = {"prob": prob, "logits_w": pw}
+        sdg = self._leaf_params()
+        nb: Dict[str, Tensor] = {}
+        self.taps = {} if want_taps else None
+        nl = ecg_x.shape[0]
+        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps)
+        self.low_logits = out["low_logits"]
+        self.low_logits.retain_grad()
+        seg = out["seg_logits"]
+        loss_x = ce_hard(seg[:nl], mask_x)
+        loss_u = ce_soft(seg[nl:], prob)
+        loss = (loss_x + loss_u) / 2.0
+        loss.backward()
+        self.sd.update(nb)
+        self._apply_grads(sdg, lr)
+        self._ema(d)
+        return {"loss_total": float(loss.detach()), "loss_x": float(loss_x.detach()),
+                "loss_u_s": float(loss_u.detach())}
+
+    def teacher_state(self) -> Dict[str, Tensor]:
+        return self._teacher_view()
+
+
+# --------------------------------------------------------------------------------------
+# closed-form gradient of the fused loss w.r.t. the LOW-RES logits (used to check the
+# fused CUDA loss kernel without autograd)
+# --------------------------------------------------------------------------------------
+def loss_grad_fullres(z: Tensor, nl: int, mask_x: Tensor, label_u: Optional[Tensor],
+                      mask_u: Optional[Tensor], prob_u: Optional[Tensor]) -> Tensor:
+    """d[(loss_x + loss_u)/2]/dz for z=[B_l+B_u, C, L] (Appendix A of SURVEY.md):
+    (softmax - onehot)/(2*B_l*L) on labeled rows; mask*(softmax - onehot)/(2*B_u*L) or
+    (softmax - p)/(2*B_u*L) on unlabeled rows."""
+    p = z.softmax(dim=1)
+    g = torch.zeros_like(z)
+    L = z.shape[2]
+    nu = z.shape[0] - nl
+    oh = F.one_hot(mask_x, z.shape[1]).permute(0, 2, 1).to(z.dtype)
+    g[:nl] = (p[:nl] - oh) / (2.0 * nl * L)
+    if nu > 0:
+        if prob_u is not None:
+            g[nl:] = (p[nl:] - prob_u.to(z.dtype)) / (2.0 * nu * L)
+        else:
+            ohu = F.one_hot(label_u, z.shape[1]).permute(0, 2, 1).to(z.dtype)
+            g[nl:] = (p[nl:] - ohu) * mask_u.to(z.dtype)[:, None, :] / (2.0 * nu * L)
+    return g

@@ -1,0 +1,54 @@
+// Library-level entry points of libsemiseg_b200: version, error reporting, device check.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+std::atomic<long long> g_ssb_launches{0};
+static thread_local char g_err[512] = "";
+
+void ssb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+int ssb_version(void) { return SSB_VERSION; }
+
+const char* ssb_last_error(void) { return g_err; }
+
+int64_t ssb_launch_count(void) { return (int64_t)g_ssb_launches.load(); }
+
+int ssb_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    ssb_set_error("ssb_device_check: no CUDA device: %s", cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+  }
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10) {
+    ssb_set_error("ssb_device_check: device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                  major, minor);
+    return SSB_ERR_UNSUPPORTED;
+  }
+  return SSB_OK;
+}
+
+int ssb_memset_zero(void* p, size_t bytes, ssb_stream_t stream) {
+  if (bytes == 0) return SSB_OK;
+  SSB_REQUIRE(p != nullptr, "ssb_memset_zero: null pointer");
+  cudaError_t e = cudaMemsetAsync(p, 0, bytes, to_stream(stream));
+  if (e != cudaSuccess) {
+    ssb_set_error("ssb_memset_zero: %s", cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+  }
+  return SSB_OK;
+}
+
+}  // extern "C"

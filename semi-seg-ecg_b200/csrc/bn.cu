@@ -1,0 +1,775 @@
+// BatchNorm1d (+ReLU, +residual, +MaxPool) forward/backward over flat padded NLC tensors.
+// Replaces cuDNN/ATen native_batch_norm + relu_ + add_ + max_pool (+ their backward
+// kernels) at resnet.py:41-70,254-257,354-355 and fcn_head.py:48-49.  HBM-bound: every
+// kernel moves 16-byte vectors, channels fastest (coalesced), one pass per tensor.
+#include "common.cuh"
+
+#define BN_EPS 1e-5
+#define BN_MOMENTUM 0.1f
+#define BN_THREADS 256
+
+// ---------------------------------------------------------------------------------------
+// statistics: sums[c] += sum_r x[r][c]; sums[C+c] += sum_r x[r][c]^2   (fp64 accumulators)
+// halo / pad rows are zero by the layout invariant, so no masking is needed.
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restrict__ x, int rows, int C,
+                                                              double* __restrict__ sums, int rpb) {
+  constexpr int V = Vec<T>::N;
+  const int ncg = C / V;
+  const int cgb = ncg < BN_THREADS ? ncg : BN_THREADS;
+  const int nrl = BN_THREADS / cgb;
+  const int tid = threadIdx.x;
+  const int cgl = tid % cgb, rl = tid / cgb;
+  const int cg = blockIdx.y * cgb + cgl;
+  __shared__ float sS[BN_THREADS * V];
+  __shared__ float sQ[BN_THREADS * V];
+  float s[V], q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] = q[i] = 0.f;
+  if (rl < nrl && cg < ncg) {
+    const int r0 = blockIdx.x * rpb;
+    const int r1 = min(rows, r0 + rpb);
+    for (int r = r0 + rl; r < r1; r += nrl) {
+      Vec<T> v;
+      v.load(x + (size_t)r * C + (size_t)cg * V);
+      float f[V];
+      v.get(f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s[i] += f[i];
+        q[i] += f[i] * f[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sS[tid * V + i] = s[i];
+    sQ[tid * V + i] = q[i];
+  }
+  __syncthreads();
+  // first row-lane reduces over the row lanes in fp64, one thread per (cg, i)
+  for (int o = tid; o < cgb * V; o += BN_THREADS) {
+    const int l = o / V, i = o % V;
+    const int cgo = blockIdx.y * cgb + l;
+    if (cgo >= ncg) continue;
+    double ds = 0.0, dq = 0.0;
+    for (int k = 0; k < nrl; ++k) {
+      ds += (double)sS[(k * cgb + l) * V + i];
+      dq += (double)sQ[(k * cgb + l) * V + i];
+    }
+    const int c = cgo * V + i;
+    atomicAdd(&sums[c], ds);
+    atomicAdd(&sums[C + c], dq);
+  }
+}
+
+// per-channel affine coefficients: y = x*scale + shift
+__device__ __forceinline__ void bn_coeffs(const ssb_bn& bn, int c, int C, int train, double inv_n, double n,
+                                          bool writer, float& scale, float& shift) {
+  float mean, invstd;
+  if (train) {
+    double m = bn.sums[c] * inv_n;
+    double var = bn.sums[C + c] * inv_n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + BN_EPS));
+    if (writer) {
+      bn.mean_invstd[c] = mean;
+      bn.mean_invstd[C + c] = invstd;
+      double unb = n > 1.0 ? var * (n / (n - 1.0)) : var;
+      bn.running_mean[c] = (1.f - BN_MOMENTUM) * bn.running_mean[c] + BN_MOMENTUM * mean;
+      bn.running_var[c] = (1.f - BN_MOMENTUM) * bn.running_var[c] + BN_MOMENTUM * (float)unb;
+      if (c == 0 && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
+    }
+  } else {
+    mean = bn.running_mean[c];
+    invstd = 1.0f / sqrtf(bn.running_var[c] + (float)BN_EPS);
+  }
+  scale = bn.gamma[c] * invstd;
+  shift = bn.beta[c] - mean * scale;
+}
+
+// ---------------------------------------------------------------------------------------
+// y = [relu]( bn(x) [+ bn_res(res) | + res] ), zero on halo/pad rows
+// RES: 0 none, 1 identity residual, 2 residual with its own BN
+// ---------------------------------------------------------------------------------------
+template <typename T, int RES>
+__global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
+                                                                T* __restrict__ y, ssb_bn bn, ssb_bn bnr,
+                                                                ssb_geom g, int relu, int train) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float sm[];
+  const int C = g.C;
+  float* sScale = sm;
+  float* sShift = sm + C;
+  float* sRScale = sm + 2 * C;
+  float* sRShift = sm + 3 * C;
+  const double n = (double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1);
+  const double inv_n = 1.0 / n;
+  const bool writer = blockIdx.x == 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc, sh;
+    bn_coeffs(bn, c, C, train, inv_n, n, writer, sc, sh);
+    sScale[c] = sc;
+    sShift[c] = sh;
+    if (RES == 2) {
+      bn_coeffs(bnr, c, C, train, inv_n, n, writer, sc, sh);
+      sRScale[c] = sc;
+      sRShift[c] = sh;
+    }
+  }
+  __syncthreads();
+  const int ncg = C / V;
+  const long long total = (long long)g.B * g.pitch * ncg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / ncg);
+    const int cg = (int)(idx - (long long)row * ncg);
+    const size_t off = (size_t)row * C + (size_t)cg * V;
+    Vec<T> out;
+    if (row_valid(row, g.pitch, g.len)) {
+      Vec<T> v;
+      v.load(x + off);
+      float f[V];
+      v.get(f);
+      float r[V];
+      if (RES != 0) {
+        Vec<T> rv;
+        rv.load(res + off);
+        rv.get(r);
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = cg * V + i;
+        float o = fmaf(f[i], sScale[c], sShift[c]);
+        if (RES == 1) o += r[i];
+        if (RES == 2) o += fmaf(r[i], sRScale[c], sRShift[c]);
+        if (relu) o = fmaxf(o, 0.f);
+        f[i] = o;
+      }
+      out.set(f);
+    } else {
+      out.zero();
+    }
+    out.store(y + off);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stem tail: y[b, t] = max_{l in {2t-1,2t,2t+1} valid} relu(bn(c0[b, l]))
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS) stem_bn_relu_pool_kernel(const T* __restrict__ c0, T* __restrict__ y,
+                                                                       ssb_bn bn, ssb_geom gi, ssb_geom go, int train) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float sm[];
+  const int C = gi.C;
+  float* sScale = sm;
+  float* sShift = sm + C;
+  const double n = (double)gi.B * (double)gi.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc, sh;
+    bn_coeffs(bn, c, C, train, 1.0 / n, n, blockIdx.x == 0, sc, sh);
+    sScale[c] = sc;
+    sShift[c] = sh;
+  }
+  __syncthreads();
+  const int ncg = C / V;
+  const long long total = (long long)go.B * go.pitch * ncg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / ncg);
+    const int cg = (int)(idx - (long long)row * ncg);
+    const int b = row / go.pitch, pos = row - b * go.pitch;
+    Vec<T> out;
+    if (pos >= 1 && pos <= go.len) {
+      const int t = pos - 1;
+      float m[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) m[i] = -INFINITY;
+#pragma unroll
+      for (int j = -1; j <= 1; ++j) {
+        const int l = 2 * t + j;
+        if (l < 0 || l >= gi.len) continue;
+        Vec<T> v;
+        v.load(c0 + ((size_t)b * gi.pitch + 1 + l) * C + (size_t)cg * V);
+        float f[V];
+        v.get(f);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const int c = cg * V + i;
+          m[i] = fmaxf(m[i], fmaxf(fmaf(f[i], sScale[c], sShift[c]), 0.f));
+        }
+      }
+      out.set(m);
+    } else {
+      out.zero();
+    }
+    out.store(y + (size_t)row * C + (size_t)cg * V);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward pass 1 (reduce): g = (g1 [+g2]) * (y>0);  bwd_sums += (sum g, sum g*xhat)
+// ---------------------------------------------------------------------------------------
+template <typename T, bool HAS_G2, bool HAS_Y, bool HAS_RES>
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __restrict__ g1, const T* __restrict__ g2,
+                                                                   const T* __restrict__ y, const T* __restrict__ x,
+                                                                   const T* __restrict__ xr, ssb_bn bn, ssb_bn bnr,
+                                                                   int rows, int C, int rpb) {
+  constexpr int V = Vec<T>::N;
+  const int ncg = C / V;
+  const int cgb = ncg < BN_THREADS ? ncg : BN_THREADS;
+  const int nrl = BN_THREADS / cgb;
+  const int tid = threadIdx.x;
+  const int cgl = tid % cgb, rl = tid / cgb;
+  const int cg = blockIdx.y * cgb + cgl;
+  __shared__ float sA[BN_THREADS * V];
+  __shared__ float sB[BN_THREADS * V];
+  __shared__ float sC[HAS_RES ? BN_THREADS * V : 1];
+  float a[V], bq[V], cq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) a[i] = bq[i] = cq[i] = 0.f;
+  if (rl < nrl && cg < ncg) {
+    float mean[V], inv[V], meanr[V], invr[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = cg * V + i;
+      mean[i] = bn.mean_invstd[c];
+      inv[i] = bn.mean_invstd[C + c];
+      if (HAS_RES) {
+        meanr[i] = bnr.mean_invstd[c];
+        invr[i] = bnr.mean_invstd[C + c];
+      }
+    }
+    const int r0 = blockIdx.x * rpb;
+    const int r1 = min(rows, r0 + rpb);
+    for (int r = r0 + rl; r < r1; r += nrl) {
+      const size_t off = (size_t)r * C + (size_t)cg * V;
+      Vec<T> vg, vx;
+      vg.load(g1 + off);
+      vx.load(x + off);
+      float fg[V], fx[V];
+      vg.get(fg);
+      vx.get(fx);
+      if (HAS_G2) {
+        Vec<T> v2;
+        v2.load(g2 + off);
+        float f2[V];
+        v2.get(f2);
+#pragma unroll
+        for (int i = 0; i < V; ++i) fg[i] += f2[i];
+      }
+      if (HAS_Y) {
+        Vec<T> vy;
+        vy.load(y + off);
+        float fy[V];
+        vy.get(fy);
+#pragma unroll
+        for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
+      }
+      float fr[V];
+      if (HAS_RES) {
+        Vec<T> vr;
+        vr.load(xr + off);
+        vr.get(fr);
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        a[i] += fg[i];
+        bq[i] += fg[i] * ((fx[i] - mean[i]) * inv[i]);
+        if (HAS_RES) cq[i] += fg[i] * ((fr[i] - meanr[i]) * invr[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sA[tid * V + i] = a[i];
+    sB[tid * V + i] = bq[i];
+    if (HAS_RES) sC[tid * V + i] = cq[i];
+  }
+  __syncthreads();
+  for (int o = tid; o < cgb * V; o += BN_THREADS) {
+    const int l = o / V, i = o % V;
+    const int cgo = blockIdx.y * cgb + l;
+    if (cgo >= ncg) continue;
+    double da = 0.0, db = 0.0, dc = 0.0;
+    for (int k = 0; k < nrl; ++k) {
+      da += (double)sA[(k * cgb + l) * V + i];
+      db += (double)sB[(k * cgb + l) * V + i];
+      if (HAS_RES) dc += (double)sC[(k * cgb + l) * V + i];
+    }
+    const int c = cgo * V + i;
+    atomicAdd(&bn.bwd_sums[c], da);
+    atomicAdd(&bn.bwd_sums[C + c], db);
+    if (HAS_RES) {
+      atomicAdd(&bnr.bwd_sums[c], da);
+      atomicAdd(&bnr.bwd_sums[C + c], dc);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward pass 2 (apply): dx = gamma*invstd*(g - sum_g/n - xhat*sum_gx/n)
+// RES: 0 none; 1 identity residual -> g_ident = g; 2 residual BN -> dx_res
+// ---------------------------------------------------------------------------------------
+template <typename T, bool HAS_G2, bool HAS_Y, int RES>
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __restrict__ g1, const T* __restrict__ g2,
+                                                                  const T* __restrict__ y, const T* __restrict__ x,
+                                                                  const T* __restrict__ xr, T* __restrict__ dx,
+                                                                  T* __restrict__ dxr, T* __restrict__ gid, ssb_bn bn,
+                                                                  ssb_bn bnr, ssb_geom g) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float sm[];
+  const int C = g.C;
+  // per channel: mean, invstd, k0 = gamma*invstd, k1 = sum_g/n, k2 = sum_gx/n
+  float* sMean = sm;
+  float* sInv = sm + C;
+  float* sK0 = sm + 2 * C;
+  float* sK1 = sm + 3 * C;
+  float* sK2 = sm + 4 * C;
+  float* rMean = sm + 5 * C;
+  float* rInv = sm + 6 * C;
+  float* rK0 = sm + 7 * C;
+  float* rK2 = sm + 8 * C;
+  const double inv_n = 1.0 / ((double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = bn.mean_invstd[c], inv = bn.mean_invstd[C + c];
+    const double sg = bn.bwd_sums[c], sgx = bn.bwd_sums[C + c];
+    sMean[c] = mean;
+    sInv[c] = inv;
+    sK0[c] = bn.gamma[c] * inv;
+    sK1[c] = (float)(sg * inv_n);
+    sK2[c] = (float)(sgx * inv_n);
+    if (blockIdx.x == 0) {
+      bn.dgamma[c] = (float)sgx;
+      bn.dbeta[c] = (float)sg;
+    }
+    if (RES == 2) {
+      const float meanr = bnr.mean_invstd[c], invr = bnr.mean_invstd[C + c];
+      const double sgxr = bnr.bwd_sums[C + c];
+      rMean[c] = meanr;
+      rInv[c] = invr;
+      rK0[c] = bnr.gamma[c] * invr;
+      rK2[c] = (float)(sgxr * inv_n);
+      if (blockIdx.x == 0) {
+        bnr.dgamma[c] = (float)sgxr;
+        bnr.dbeta[c] = (float)sg;
+      }
+    }
+  }
+  __syncthreads();
+  const int ncg = C / V;
+  const long long total = (long long)g.B * g.pitch * ncg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / ncg);
+    const int cg = (int)(idx - (long long)row * ncg);
+    const size_t off = (size_t)row * C + (size_t)cg * V;
+    Vec<T> odx, odr, ogi;
+    if (row_valid(row, g.pitch, g.len)) {
+      Vec<T> vg, vx;
+      vg.load(g1 + off);
+      vx.load(x + off);
+      float fg[V], fx[V];
+      vg.get(fg);
+      vx.get(fx);
+      if (HAS_G2) {
+        Vec<T> v2;
+        v2.load(g2 + off);
+        float f2[V];
+        v2.get(f2);
+#pragma unroll
+        for (int i = 0; i < V; ++i) fg[i] += f2[i];
+      }
+      if (HAS_Y) {
+        Vec<T> vy;
+        vy.load(y + off);
+        float fy[V];
+        vy.get(fy);
+#pragma unroll
+        for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
+      }
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = cg * V + i;
+        const float xh = (fx[i] - sMean[c]) * sInv[c];
+        o[i] = sK0[c] * (fg[i] - sK1[c] - xh * sK2[c]);
+      }
+      odx.set(o);
+      if (RES == 1) ogi.set(fg);
+      if (RES == 2) {
+        Vec<T> vr;
+        vr.load(xr + off);
+        float fr[V];
+        vr.get(fr);
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const int c = cg * V + i;
+          const float xh = (fr[i] - rMean[c]) * rInv[c];
+          o[i] = rK0[c] * (fg[i] - sK1[c] - xh * rK2[c]);
+        }
+        odr.set(o);
+      }
+    } else {
+      odx.zero();
+      odr.zero();
+      ogi.zero();
+    }
+    odx.store(dx + off);
+    if (RES == 1) ogi.store(gid + off);
+    if (RES == 2) odr.store(dxr + off);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stem tail backward: gradient of pooled output scattered through max-pool (first max on
+// ties, torch semantics), relu mask, then the two BN-backward passes on c0.
+// ---------------------------------------------------------------------------------------
+template <typename T, int V>
+__device__ __forceinline__ void stem_masked_grad(const T* __restrict__ c0, const T* __restrict__ gp,
+                                                 const float* sScale, const float* sShift, const ssb_geom& gi,
+                                                 const ssb_geom& go, int b, int l, int cg, float* g, float* xc) {
+  const int C = gi.C;
+  float a[5][V];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    const int ll = l - 2 + j;
+    if (ll < 0 || ll >= gi.len) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[j][i] = -INFINITY;
+    } else {
+      Vec<T> v;
+      v.load(c0 + ((size_t)b * gi.pitch + 1 + ll) * C + (size_t)cg * V);
+      float f[V];
+      v.get(f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = cg * V + i;
+        if (j == 2) xc[i] = f[i];
+        a[j][i] = fmaxf(fmaf(f[i], sScale[c], sShift[c]), 0.f);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) g[i] = 0.f;
+  // windows containing l: centre index 2t; l even -> t=l/2 (l-1,l,l+1);
+  // l odd -> t=(l-1)/2 (l-2,l-1,l) and t=(l+1)/2 (l,l+1,l+2)
+  int tw[2], base[2];  // base = array index j of the window's first element
+  int nw = 0;
+  if ((l & 1) == 0) {
+    tw[nw] = l >> 1; base[nw] = 1; ++nw;
+  } else {
+    tw[nw] = (l - 1) >> 1; base[nw] = 0; ++nw;
+    tw[nw] = (l + 1) >> 1; base[nw] = 2; ++nw;
+  }
+  for (int w = 0; w < nw; ++w) {
+    if (tw[w] >= go.len) continue;
+    Vec<T> vg;
+    vg.load(gp + ((size_t)b * go.pitch + 1 + tw[w]) * C + (size_t)cg * V);
+    float fg[V];
+    vg.get(fg);
+    const int bs = base[w];
+    const int me = 2 - bs;  // position of l inside the window (0..2)
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      // first-max arg over the 3 window entries (strict > from the left; -inf = padding)
+      float best = a[bs][i];
+      int arg = 0;
+      if (a[bs + 1][i] > best) { best = a[bs + 1][i]; arg = 1; }
+      if (a[bs + 2][i] > best) { best = a[bs + 2][i]; arg = 2; }
+      if (arg == me) g[i] += fg[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) g[i] = a[2][i] > 0.f ? g[i] : 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS) stem_bwd_reduce_kernel(const T* __restrict__ gp, const T* __restrict__ c0,
+                                                                     ssb_bn bn, ssb_geom gi, ssb_geom go) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float sm[];
+  const int C = gi.C;
+  float* sScale = sm;
+  float* sShift = sm + C;
+  float* sMean = sm + 2 * C;
+  float* sInv = sm + 3 * C;
+  float* sAcc = sm + 4 * C;  // [2C] block-level accumulators
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = bn.mean_invstd[c], inv = bn.mean_invstd[C + c];
+    sMean[c] = mean;
+    sInv[c] = inv;
+    sScale[c] = bn.gamma[c] * inv;
+    sShift[c] = bn.beta[c] - mean * sScale[c];
+    sAcc[c] = 0.f;
+    sAcc[C + c] = 0.f;
+  }
+  __syncthreads();
+  const int ncg = C / V;
+  // a block owns a contiguous chunk of (row, cg) work items so the smem atomics stay cheap
+  const long long total = (long long)gi.B * gi.len * ncg;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long i0 = (long long)blockIdx.x * per;
+  const long long i1 = i0 + per < total ? i0 + per : total;
+  for (long long idx = i0 + threadIdx.x; idx < i1; idx += blockDim.x) {
+    const long long rl = idx / ncg;
+    const int cg = (int)(idx - rl * ncg);
+    const int b = (int)(rl / gi.len), l = (int)(rl - (long long)b * gi.len);
+    float g[V], xc[V];
+    stem_masked_grad<T, V>(c0, gp, sScale, sShift, gi, go, b, l, cg, g, xc);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = cg * V + i;
+      if (g[i] != 0.f) {
+        atomicAdd(&sAcc[c], g[i]);
+        atomicAdd(&sAcc[C + c], g[i] * ((xc[i] - sMean[c]) * sInv[c]));
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) atomicAdd(&bn.bwd_sums[c], (double)sAcc[c]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS) stem_bwd_apply_kernel(const T* __restrict__ gp, const T* __restrict__ c0,
+                                                                    T* __restrict__ dc0, ssb_bn bn, ssb_geom gi,
+                                                                    ssb_geom go) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float sm[];
+  const int C = gi.C;
+  float* sScale = sm;
+  float* sShift = sm + C;
+  float* sMean = sm + 2 * C;
+  float* sInv = sm + 3 * C;
+  float* sK1 = sm + 4 * C;
+  float* sK2 = sm + 5 * C;
+  const double inv_n = 1.0 / ((double)gi.B * (double)gi.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = bn.mean_invstd[c], inv = bn.mean_invstd[C + c];
+    sMean[c] = mean;
+    sInv[c] = inv;
+    sScale[c] = bn.gamma[c] * inv;
+    sShift[c] = bn.beta[c] - mean * sScale[c];
+    sK1[c] = (float)(bn.bwd_sums[c] * inv_n);
+    sK2[c] = (float)(bn.bwd_sums[C + c] * inv_n);
+    if (blockIdx.x == 0) {
+      bn.dgamma[c] = (float)bn.bwd_sums[C + c];
+      bn.dbeta[c] = (float)bn.bwd_sums[c];
+    }
+  }
+  __syncthreads();
+  const int ncg = C / V;
+  const long long total = (long long)gi.B * gi.pitch * ncg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / ncg);
+    const int cg = (int)(idx - (long long)row * ncg);
+    const int b = row / gi.pitch, pos = row - b * gi.pitch;
+    Vec<T> out;
+    if (pos >= 1 && pos <= gi.len) {
+      float g[V], xc[V];
+      stem_masked_grad<T, V>(c0, gp, sScale, sShift, gi, go, b, pos - 1, cg, g, xc);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = cg * V + i;
+        const float xh = (xc[i] - sMean[c]) * sInv[c];
+        g[i] = sScale[c] * (g[i] - sK1[c] - xh * sK2[c]);
+      }
+      out.set(g);
+    } else {
+      out.zero();
+    }
+    out.store(dc0 + (size_t)row * C + (size_t)cg * V);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host wrappers
+// ---------------------------------------------------------------------------------------
+static int check_geom(const char* who, const ssb_geom& g, int vec) {
+  SSB_REQUIRE(g.B > 0 && g.len > 0 && g.C > 0, "%s: empty geometry (B=%d len=%d C=%d)", who, g.B, g.len, g.C);
+  SSB_REQUIRE(g.pitch >= g.len + 2, "%s: pitch %d < len %d + 2", who, g.pitch, g.len);
+  SSB_REQUIRE(g.C % 8 == 0, "%s: C=%d must be a multiple of 8", who, g.C);
+  SSB_REQUIRE((long long)g.B * g.pitch < (1ll << 31), "%s: too many rows", who);
+  (void)vec;
+  return SSB_OK;
+}
+
+static int ew_blocks(long long total_vec) {
+  long long b = ceil_div_ll(total_vec, (long long)BN_THREADS * 4);
+  if (b < 1) b = 1;
+  if (b > 148 * 8) b = 148 * 8;
+  return (int)b;
+}
+
+static const ssb_bn kNoBn = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
+
+#define SSB_RED(G2, Y, R) \
+  bn_bwd_reduce_kernel<T, G2, Y, R><<<grid, BN_THREADS, 0, st>>>((const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, *bn, br, rows, g.C, rpb)
+#define SSB_APP(G2, Y, R) \
+  bn_bwd_apply_kernel<T, G2, Y, R><<<blocks, BN_THREADS, smem, st>>>((const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g)
+
+extern "C" {
+
+int ssb_bn_stats(const void* x, ssb_geom g, double* sums, int dtype, ssb_stream_t stream) {
+  int rc = check_geom("ssb_bn_stats", g, 0);
+  if (rc) return rc;
+  SSB_REQUIRE(x && sums, "ssb_bn_stats: null pointer");
+  const int rows = g.B * g.pitch;
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    constexpr int V = Vec<T>::N;
+    const int ncg = g.C / V;
+    const int cgb = ncg < BN_THREADS ? ncg : BN_THREADS;
+    const int nrl = BN_THREADS / cgb;
+    int rpb = ceil_div(rows, 148 * 4);
+    if (rpb < nrl * 4) rpb = nrl * 4;
+    dim3 grid(ceil_div(rows, rpb), ceil_div(ncg, cgb));
+    bn_stats_kernel<T><<<grid, BN_THREADS, 0, to_stream(stream)>>>((const T*)x, rows, g.C, sums, rpb);
+  })
+  SSB_LAUNCH_CHECK("ssb_bn_stats");
+  return SSB_OK;
+}
+
+int ssb_bn_act_fwd(const void* x, const ssb_bn* bn, const void* res, const ssb_bn* bn_res, void* y, ssb_geom g,
+                   int relu, int train, int dtype, ssb_stream_t stream) {
+  int rc = check_geom("ssb_bn_act_fwd", g, 0);
+  if (rc) return rc;
+  SSB_REQUIRE(x && bn && y, "ssb_bn_act_fwd: null pointer");
+  SSB_REQUIRE(!(bn_res && !res), "ssb_bn_act_fwd: bn_res given without res");
+  const int mode = res ? (bn_res ? 2 : 1) : 0;
+  const size_t smem = (size_t)4 * g.C * sizeof(float);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    const long long total = (long long)g.B * g.pitch * (g.C / Vec<T>::N);
+    const int blocks = ew_blocks(total);
+    cudaStream_t st = to_stream(stream);
+    if (mode == 0)
+      bn_act_fwd_kernel<T, 0><<<blocks, BN_THREADS, smem, st>>>((const T*)x, nullptr, (T*)y, *bn, kNoBn, g, relu, train);
+    else if (mode == 1)
+      bn_act_fwd_kernel<T, 1><<<blocks, BN_THREADS, smem, st>>>((const T*)x, (const T*)res, (T*)y, *bn, kNoBn, g, relu, train);
+    else
+      bn_act_fwd_kernel<T, 2><<<blocks, BN_THREADS, smem, st>>>((const T*)x, (const T*)res, (T*)y, *bn, *bn_res, g, relu, train);
+  })
+  SSB_LAUNCH_CHECK("ssb_bn_act_fwd");
+  return SSB_OK;
+}
+
+int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, ssb_geom gin, ssb_geom gout, int train,
+                              int dtype, ssb_stream_t stream) {
+  int rc = check_geom("ssb_stem_bn_relu_pool_fwd(in)", gin, 0);
+  if (rc) return rc;
+  rc = check_geom("ssb_stem_bn_relu_pool_fwd(out)", gout, 0);
+  if (rc) return rc;
+  SSB_REQUIRE(c0 && bn && y, "ssb_stem_bn_relu_pool_fwd: null pointer");
+  SSB_REQUIRE(gin.C == gout.C && gin.B == gout.B, "ssb_stem_bn_relu_pool_fwd: geometry mismatch");
+  SSB_REQUIRE(gout.len == (gin.len - 1) / 2 + 1, "ssb_stem_bn_relu_pool_fwd: len_out %d != pool(len_in %d)", gout.len, gin.len);
+  const size_t smem = (size_t)2 * gin.C * sizeof(float);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    const long long total = (long long)gout.B * gout.pitch * (gout.C / Vec<T>::N);
+    stem_bn_relu_pool_kernel<T><<<ew_blocks(total), BN_THREADS, smem, to_stream(stream)>>>((const T*)c0, (T*)y, *bn, gin, gout, train);
+  })
+  SSB_LAUNCH_CHECK("ssb_stem_bn_relu_pool_fwd");
+  return SSB_OK;
+}
+
+int ssb_bn_bwd_reduce(const void* g1, const void* g2, const void* y, const void* x, const ssb_bn* bn,
+                      const void* x_res, const ssb_bn* bn_res, ssb_geom g, int dtype, ssb_stream_t stream) {
+  int rc = check_geom("ssb_bn_bwd_reduce", g, 0);
+  if (rc) return rc;
+  SSB_REQUIRE(g1 && x && bn, "ssb_bn_bwd_reduce: null pointer");
+  SSB_REQUIRE((x_res != nullptr) == (bn_res != nullptr), "ssb_bn_bwd_reduce: x_res and bn_res go together");
+  const int rows = g.B * g.pitch;
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    constexpr int V = Vec<T>::N;
+    const int ncg = g.C / V;
+    const int cgb = ncg < BN_THREADS ? ncg : BN_THREADS;
+    const int nrl = BN_THREADS / cgb;
+    int rpb = ceil_div(rows, 148 * 4);
+    if (rpb < nrl * 4) rpb = nrl * 4;
+    dim3 grid(ceil_div(rows, rpb), ceil_div(ncg, cgb));
+    cudaStream_t st = to_stream(stream);
+    const ssb_bn br = bn_res ? *bn_res : kNoBn;
+    const int sel = (g2 ? 4 : 0) | (y ? 2 : 0) | (x_res ? 1 : 0);
+    switch (sel) {
+      case 0: SSB_RED(false, false, false); break;
+      case 1: SSB_RED(false, false, true); break;
+      case 2: SSB_RED(false, true, false); break;
+      case 3: SSB_RED(false, true, true); break;
+      case 4: SSB_RED(true, false, false); break;
+      case 5: SSB_RED(true, false, true); break;
+      case 6: SSB_RED(true, true, false); break;
+      default: SSB_RED(true, true, true); break;
+    }
+  })
+  SSB_LAUNCH_CHECK("ssb_bn_bwd_reduce");
+  return SSB_OK;
+}
+
+int ssb_bn_bwd_apply(const void* g1, const void* g2, const void* y, const void* x, const ssb_bn* bn, void* dx,
+                     const void* x_res, const ssb_bn* bn_res, void* dx_res, void* g_ident, ssb_geom g, int dtype,
+                     ssb_stream_t stream) {
+  int rc = check_geom("ssb_bn_bwd_apply", g, 0);
+  if (rc) return rc;
+  SSB_REQUIRE(g1 && x && bn && dx, "ssb_bn_bwd_apply: null pointer");
+  SSB_REQUIRE(!(bn_res && (!x_res || !dx_res)), "ssb_bn_bwd_apply: residual BN needs x_res and dx_res");
+  SSB_REQUIRE(!(bn_res && g_ident), "ssb_bn_bwd_apply: g_ident and bn_res are exclusive");
+  const int mode = bn_res ? 2 : (g_ident ? 1 : 0);
+  const size_t smem = (size_t)9 * g.C * sizeof(float);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    const long long total = (long long)g.B * g.pitch * (g.C / Vec<T>::N);
+    const int blocks = ew_blocks(total);
+    cudaStream_t st = to_stream(stream);
+    const ssb_bn br = bn_res ? *bn_res : kNoBn;
+    const int sel = (g2 ? 2 : 0) | (y ? 1 : 0);
+    if (mode == 0) {
+      switch (sel) { case 0: SSB_APP(false, false, 0); break; case 1: SSB_APP(false, true, 0); break;
+                     case 2: SSB_APP(true, false, 0); break; default: SSB_APP(true, true, 0); break; }
+    } else if (mode == 1) {
+      switch (sel) { case 0: SSB_APP(false, false, 1); break; case 1: SSB_APP(false, true, 1); break;
+                     case 2: SSB_APP(true, false, 1); break; default: SSB_APP(true, true, 1); break; }
+    } else {
+      switch (sel) { case 0: SSB_APP(false, false, 2); break; case 1: SSB_APP(false, true, 2); break;
+                     case 2: SSB_APP(true, false, 2); break; default: SSB_APP(true, true, 2); break; }
+    }
+  })
+  SSB_LAUNCH_CHECK("ssb_bn_bwd_apply");
+  return SSB_OK;
+}
+
+int ssb_stem_bwd_reduce(const void* gp, const void* c0, const ssb_bn* bn, ssb_geom gin, ssb_geom gout, int dtype,
+                        ssb_stream_t stream) {
+  int rc = check_geom("ssb_stem_bwd_reduce(in)", gin, 0);
+  if (rc) return rc;
+  rc = check_geom("ssb_stem_bwd_reduce(out)", gout, 0);
+  if (rc) return rc;
+  SSB_REQUIRE(gp && c0 && bn, "ssb_stem_bwd_reduce: null pointer");
+  SSB_REQUIRE(gin.C == gout.C && gin.B == gout.B, "ssb_stem_bwd_reduce: geometry mismatch");
+  const size_t smem = (size_t)6 * gin.C * sizeof(float);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    const long long total = (long long)gin.B * gin.len * (gin.C / Vec<T>::N);
+    stem_bwd_reduce_kernel<T><<<ew_blocks(total), BN_THREADS, smem, to_stream(stream)>>>((const T*)gp, (const T*)c0, *bn, gin, gout);
+  })
+  SSB_LAUNCH_CHECK("ssb_stem_bwd_reduce");
+  return SSB_OK;
+}
+
+int ssb_stem_bwd_apply(const void* gp, const void* c0, const ssb_bn* bn, void* dc0, ssb_geom gin, ssb_geom gout,
+                       int dtype, ssb_stream_t stream) {
+  int rc = check_geom("ssb_stem_bwd_apply(in)", gin, 0);
+  if (rc) return rc;
+  rc = check_geom("ssb_stem_bwd_apply(out)", gout, 0);
+  if (rc) return rc;
+  SSB_REQUIRE(gp && c0 && bn && dc0, "ssb_stem_bwd_apply: null pointer");
+  SSB_REQUIRE(gin.C == gout.C && gin.B == gout.B, "ssb_stem_bwd_apply: geometry mismatch");
+  const size_t smem = (size_t)6 * gin.C * sizeof(float);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    const long long total = (long long)gin.B * gin.pitch * (gin.C / Vec<T>::N);
+    stem_bwd_apply_kernel<T><<<ew_blocks(total), BN_THREADS, smem, to_stream(stream)>>>((const T*)gp, (const T*)c0, (T*)dc0, *bn, gin, gout);
+  })
+  SSB_LAUNCH_CHECK("ssb_stem_bwd_apply");
+  return SSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// Shared helpers for the libsemiseg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/ssb.h"
+
+typedef __nv_bfloat16 bf16;
+
+void ssb_set_error(const char* fmt, ...);
+extern std::atomic<long long> g_ssb_launches;
+
+#define SSB_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      ssb_set_error(__VA_ARGS__);     \
+      return SSB_ERR_INVALID;         \
+    }                                 \
+  } while (0)
+
+// call after every kernel launch
+#define SSB_LAUNCH_CHECK(name)                                              \
+  do {                                                                      \
+    g_ssb_launches.fetch_add(1, std::memory_order_relaxed);                 \
+    cudaError_t e__ = cudaGetLastError();                                   \
+    if (e__ != cudaSuccess) {                                               \
+      ssb_set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return SSB_ERR_CUDA;                                                  \
+    }                                                                       \
+  } while (0)
+
+#define SSB_DISPATCH_DTYPE(dtype, T, ...)              \
+  if ((dtype) == SSB_F32) {                            \
+    typedef float T;                                   \
+    __VA_ARGS__                                        \
+  } else if ((dtype) == SSB_BF16) {                    \
+    typedef bf16 T;                                    \
+    __VA_ARGS__                                        \
+  } else {                                             \
+    ssb_set_error("unsupported dtype %d", (int)(dtype)); \
+    return SSB_ERR_INVALID;                            \
+  }
+
+static inline cudaStream_t to_stream(ssb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// ---- element access ------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+// 16-byte vectors: 4 floats or 8 bf16
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  float4 raw;
+  __device__ __forceinline__ void load(const float* p) { raw = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = raw; }
+  __device__ __forceinline__ void get(float* f) const { f[0] = raw.x; f[1] = raw.y; f[2] = raw.z; f[3] = raw.w; }
+  __device__ __forceinline__ void set(const float* f) { raw = make_float4(f[0], f[1], f[2], f[3]); }
+  __device__ __forceinline__ void zero() { raw = make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ void load(const bf16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ void get(float* f) const {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ __forceinline__ void set(const float* f) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  }
+  __device__ __forceinline__ void zero() { raw = make_uint4(0u, 0u, 0u, 0u); }
+};
+
+// row validity in the flat padded layout
+__device__ __forceinline__ bool row_valid(int row, int pitch, int len) {
+  int pos = row % pitch;
+  return pos >= 1 && pos <= len;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// counter-based dropout RNG (keep decision for element idx), shared by fwd and bwd
+__device__ __forceinline__ uint32_t ssb_hash3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t step, uint32_t idx, float p) {
+  uint32_t h = ssb_hash3(seed, step, idx);
+  return (float)(h >> 8) * (1.0f / 16777216.0f) >= p;
+}

@@ -1,0 +1,537 @@
+// Generic (any channel count, fp32 accumulate) Conv1d kernels on CUDA cores:
+//  * stem direct conv k7 s2 p3 from the NCL fp32 input (HBM-bound, resnet.py:246-253)
+//  * tap-GEMM fprop / dgrad for k in {1,3}, stride in {1,2} over flat padded NLC rows
+//  * wgrad (split over rows, fp32 atomics into the reference-layout gradient)
+//  * multi-tensor weight repack (master fp32 [Cout][Cin][k] -> GEMM layouts)
+// These are the exact-parity (fp32) path and the fallback for shapes the tcgen05 kernels
+// (conv_sm100.cu) do not cover.  Replaces cuDNN fprop/dgrad/wgrad (SURVEY.md 2.2 K1,K4).
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// tap-GEMM:  Out[o_mul*m + o_off][n] (+)= sum_tap sum_k A[a_mul*m + a_off[tap]][k] * W[w_tap[tap]][k][n]
+// ---------------------------------------------------------------------------------------
+struct TapSpec {
+  int ntaps;
+  int a_off[3];
+  int w_tap[3];
+};
+
+#define TG_BM 128
+#define TG_BN 64
+#define TG_BK 16
+#define TG_THREADS 256
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float* f);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float* f) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  float4 b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<bf16>(const bf16* p, float* f) {
+  Vec<bf16> v;
+  v.load(p);
+  v.get(f);
+}
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float* f);
+template <>
+__device__ __forceinline__ void load4<float>(const float* p, float* f) {
+  float4 a = *reinterpret_cast<const float4*>(p);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+}
+template <>
+__device__ __forceinline__ void load4<bf16>(const bf16* p, float* f) {
+  uint2 raw = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+template <typename T>
+__device__ __forceinline__ void store4(T* p, const float* f);
+template <>
+__device__ __forceinline__ void store4<float>(float* p, const float* f) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <>
+__device__ __forceinline__ void store4<bf16>(bf16* p, const float* f) {
+  uint2 raw;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&raw);
+  h[0] = __floats2bfloat162_rn(f[0], f[1]);
+  h[1] = __floats2bfloat162_rn(f[2], f[3]);
+  *reinterpret_cast<uint2*>(p) = raw;
+}
+
+template <typename T, bool ACC>
+__global__ void __launch_bounds__(TG_THREADS)
+tap_gemm_kernel(const T* __restrict__ A, const T* __restrict__ W, T* __restrict__ Out, int M, int N, int K,
+                int a_rows, int a_mul, TapSpec taps, int o_mul, int o_off, int o_rows, int o_pitch, int o_len) {
+  __shared__ float As[TG_BK][TG_BM + 4];
+  __shared__ float Bs[TG_BK][TG_BN];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * TG_BM;
+  const int n0 = blockIdx.y * TG_BN;
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int la_row = tid >> 1, la_k = (tid & 1) * 8;  // A loader: row, k offset
+  const int lb_k = tid >> 4, lb_n = (tid & 15) * 4;   // B loader
+  for (int tp = 0; tp < taps.ntaps; ++tp) {
+    const int m = m0 + la_row;
+    const long long arow = (long long)a_mul * m + taps.a_off[tp];
+    const bool arow_ok = m < M && arow >= 0 && arow < a_rows;
+    const T* wt = W + (size_t)taps.w_tap[tp] * K * N;
+    for (int k0 = 0; k0 < K; k0 += TG_BK) {
+      float fa[8];
+      if (arow_ok && k0 + la_k < K) {
+        load8<T>(A + (size_t)arow * K + k0 + la_k, fa);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) fa[i] = 0.f;
+      }
+      float fb[4];
+      if (k0 + lb_k < K && n0 + lb_n < N) {
+        load4<T>(wt + (size_t)(k0 + lb_k) * N + n0 + lb_n, fb);
+      } else {
+        fb[0] = fb[1] = fb[2] = fb[3] = 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[la_k + i][la_row] = fa[i];
+      *reinterpret_cast<float4*>(&Bs[lb_k][lb_n]) = make_float4(fb[0], fb[1], fb[2], fb[3]);
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < TG_BK; ++kk) {
+        float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+        float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+        float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+      }
+    }
+  }
+  const int n = n0 + tx * 4;
+  if (n >= N) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+    const long long orow = (long long)o_mul * m + o_off;
+    if (orow < 0 || orow >= o_rows) continue;
+    T* op = Out + (size_t)orow * N + n;
+    float o[4];
+    if (row_valid((int)orow, o_pitch, o_len)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = acc[i][j];
+      if (ACC) {
+        float prev[4];
+        load4<T>(op, prev);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] += prev[j];
+      }
+      store4<T>(op, o);
+    } else if (!ACC) {
+      o[0] = o[1] = o[2] = o[3] = 0.f;
+      store4<T>(op, o);
+    }
+  }
+}
+
+// zero-fill rows of one parity (used when a stride-2 dgrad has no tap for that parity)
+template <typename T>
+__global__ void zero_parity_rows_kernel(T* out, int rows, int N, int parity) {
+  const long long total = (long long)(rows / 2) * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long q = idx / N;
+    const int n = (int)(idx - q * N);
+    out[(size_t)(2 * q + parity) * N + n] = from_f<T>(0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// wgrad: dW[co][ci][tap] += sum_m X[a_mul*m + a_off[tap]][ci] * dY[m][co]
+// ---------------------------------------------------------------------------------------
+#define WG_T 64
+#define WG_BK 16
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+wgrad_kernel(const T* __restrict__ X, const T* __restrict__ dY, float* __restrict__ dW, int M, int Cin, int Cout,
+             int k, int x_rows, int a_mul, TapSpec taps, int nsplit, int rows_per_split) {
+  __shared__ float Xs[WG_BK][WG_T];
+  __shared__ float Ys[WG_BK][WG_T];
+  const int tid = threadIdx.x;
+  const int ci0 = blockIdx.x * WG_T, co0 = blockIdx.y * WG_T;
+  const int tp = blockIdx.z / nsplit, sp = blockIdx.z % nsplit;
+  const int ty = tid / 16, tx = tid % 16;
+  const int lr = tid >> 4, lc = (tid & 15) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int mbeg = sp * rows_per_split;
+  const int mend = min(M, mbeg + rows_per_split);
+  const int aoff = taps.a_off[tp];
+  for (int mm = mbeg; mm < mend; mm += WG_BK) {
+    const int m = mm + lr;
+    float fx[4] = {0.f, 0.f, 0.f, 0.f}, fy[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < mend) {
+      const long long xr = (long long)a_mul * m + aoff;
+      if (xr >= 0 && xr < x_rows && ci0 + lc < Cin) load4<T>(X + (size_t)xr * Cin + ci0 + lc, fx);
+      if (co0 + lc < Cout) load4<T>(dY + (size_t)m * Cout + co0 + lc, fy);
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&Xs[lr][lc]) = make_float4(fx[0], fx[1], fx[2], fx[3]);
+    *reinterpret_cast<float4*>(&Ys[lr][lc]) = make_float4(fy[0], fy[1], fy[2], fy[3]);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < WG_BK; ++r) {
+      float4 a = *reinterpret_cast<const float4*>(&Xs[r][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Ys[r][tx * 4]);
+      const float aa[4] = {a.x, a.y, a.z, a.w};
+      const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+  const int wt = taps.w_tap[tp];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + ty * 4 + i;
+    if (ci >= Cin) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co >= Cout) continue;
+      atomicAdd(&dW[((size_t)co * Cin + ci) * k + wt], acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// weight repack (all convs, one launch): fp32 [Cout][Cin][k] -> T [k][Cin][Cout], T [k][Cout][Cin]
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void repack_kernel(const ssb_repack_desc* __restrict__ table) {
+  const ssb_repack_desc d = table[blockIdx.y];
+  const int total = d.Cout * d.Cin * d.k;
+  T* kio = (T*)d.w_kio;
+  T* koi = (T*)d.w_koi;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int j = idx % d.k;
+    const int ci = (idx / d.k) % d.Cin;
+    const int co = idx / (d.k * d.Cin);
+    const T v = from_f<T>(d.w[idx]);
+    kio[((size_t)j * d.Cin + ci) * d.Cout + co] = v;
+    koi[((size_t)j * d.Cout + co) * d.Cin + ci] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stem: y[b, t, co] = sum_{c,j} w[co][c][j] * x[b][c][2t + j - 3]
+// ---------------------------------------------------------------------------------------
+#define ST_TT 64
+#define ST_THREADS 256
+
+template <typename T>
+__global__ void __launch_bounds__(ST_THREADS)
+stem_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int Cl, int L,
+                     ssb_geom g) {
+  extern __shared__ float sm[];
+  const int Cs = g.C;
+  float* ws = sm;                  // [Cl*7][Cs]
+  float* xs = sm + Cl * 7 * Cs;    // [Cl][2*TT+5]
+  const int XW = 2 * ST_TT + 5;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * ST_TT;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < Cs * Cl * 7; idx += ST_THREADS) {
+    const int co = idx / (Cl * 7), cj = idx % (Cl * 7);
+    ws[cj * Cs + co] = w[idx];
+  }
+  for (int idx = tid; idx < Cl * XW; idx += ST_THREADS) {
+    const int c = idx / XW, i = idx % XW;
+    const int l = 2 * t0 - 3 + i;
+    xs[idx] = (l >= 0 && l < L) ? x[((size_t)b * Cl + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  const int csb = Cs < ST_THREADS ? Cs : ST_THREADS;
+  const int ntl = ST_THREADS / csb;  // t-lanes
+  const int tl = tid / csb;
+  if (tl < ntl) {
+    for (int co = tid % csb; co < Cs; co += csb) {
+      for (int tb = tl * 4; tb < ST_TT; tb += ntl * 4) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int c = 0; c < Cl; ++c) {
+          float xv[13];
+#pragma unroll
+          for (int i = 0; i < 13; ++i) xv[i] = xs[c * XW + 2 * tb + i];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const float wv = ws[(c * 7 + j) * Cs + co];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmaf(wv, xv[2 * u + j], acc[u]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int t = t0 + tb + u;
+          if (t < g.len) y[((size_t)b * g.pitch + 1 + t) * Cs + co] = from_f<T>(acc[u]);
+        }
+      }
+    }
+  }
+  // halo / pad rows of this sample stay zero
+  if (blockIdx.x == 0)
+    for (int c = tid; c < Cs; c += ST_THREADS) y[(size_t)b * g.pitch * Cs + c] = from_f<T>(0.f);
+  if (blockIdx.x == gridDim.x - 1) {
+    const int npad = g.pitch - g.len - 1;
+    for (int idx = tid; idx < npad * Cs; idx += ST_THREADS)
+      y[((size_t)b * g.pitch + g.len + 1) * Cs + idx] = from_f<T>(0.f);
+  }
+}
+
+// dw[co][c][j] += sum_{b,t} dy[b,t,co] * x[b][c][2t+j-3]
+template <typename T>
+__global__ void __launch_bounds__(ST_THREADS)
+stem_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int Cl, int L,
+                       ssb_geom g) {
+  extern __shared__ float sm[];
+  const int Cs = g.C;
+  const int XW = 2 * ST_TT + 5;
+  float* dys = sm;                 // [TT][Cs]
+  float* xs = sm + ST_TT * Cs;     // [Cl][XW]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * ST_TT;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < ST_TT * Cs; idx += ST_THREADS) {
+    const int t = t0 + idx / Cs;
+    dys[idx] = t < g.len ? to_f(dy[((size_t)b * g.pitch + 1 + t) * Cs + idx % Cs]) : 0.f;
+  }
+  for (int idx = tid; idx < Cl * XW; idx += ST_THREADS) {
+    const int c = idx / XW, i = idx % XW;
+    const int l = 2 * t0 - 3 + i;
+    xs[idx] = (l >= 0 && l < L) ? x[((size_t)b * Cl + c) * L + l] : 0.f;
+  }
+  __syncthreads();
+  const int nout = Cl * 7 * Cs;
+  for (int o = tid; o < nout; o += ST_THREADS) {
+    const int co = o % Cs, cj = o / Cs;
+    const int c = cj / 7, j = cj % 7;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int t = 0; t < ST_TT; ++t) acc = fmaf(dys[t * Cs + co], xs[c * XW + 2 * t + j], acc);
+    atomicAdd(&dw[((size_t)co * Cl + c) * 7 + j], acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static int check_conv_geom(const char* who, const ssb_geom& gi, const ssb_geom& go, int k, int stride) {
+  SSB_REQUIRE(k == 1 || k == 3, "%s: kernel size %d not supported (1 or 3)", who, k);
+  SSB_REQUIRE(stride == 1 || stride == 2, "%s: stride %d not supported (1 or 2)", who, stride);
+  SSB_REQUIRE(gi.B == go.B && gi.B > 0, "%s: batch mismatch", who);
+  SSB_REQUIRE(gi.C % 8 == 0 && go.C % 8 == 0 && gi.C > 0 && go.C > 0, "%s: channels must be multiples of 8 (Cin=%d Cout=%d)", who, gi.C, go.C);
+  SSB_REQUIRE(gi.pitch == stride * go.pitch, "%s: pitch_in %d != stride*pitch_out %d", who, gi.pitch, stride * go.pitch);
+  SSB_REQUIRE(go.len == (gi.len - 1) / stride + 1, "%s: len_out %d inconsistent with len_in %d stride %d", who, go.len, gi.len, stride);
+  SSB_REQUIRE(gi.pitch >= gi.len + 2 && go.pitch >= go.len + 2, "%s: pitch too small", who);
+  SSB_REQUIRE((long long)gi.B * gi.pitch < (1ll << 31), "%s: too many rows", who);
+  return SSB_OK;
+}
+
+// taps of the forward conv in flat-row space: in_row = stride*m + a_off[j], m = output row
+static TapSpec fwd_taps(int k, int stride) {
+  TapSpec t;
+  t.ntaps = k;
+  for (int j = 0; j < 3; ++j) {
+    t.a_off[j] = 0;
+    t.w_tap[j] = j < k ? j : 0;
+  }
+  if (stride == 1) {
+    if (k == 3) { t.a_off[0] = -1; t.a_off[1] = 0; t.a_off[2] = 1; }
+  } else {
+    // in_row = 2*(m-1) + j + (k==1 ? 1 : 0)
+    if (k == 3) { t.a_off[0] = -2; t.a_off[1] = -1; t.a_off[2] = 0; }
+    else t.a_off[0] = -1;
+  }
+  return t;
+}
+
+int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
+                         cudaStream_t st);
+int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
+                           int accumulate, cudaStream_t st);
+int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
+                           cudaStream_t st);
+
+extern "C" {
+
+int ssb_conv1d_fwd(const void* x, const void* w_kio, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k,
+                   int stride, int dtype, int algo, ssb_stream_t stream) {
+  int rc = check_conv_geom("ssb_conv1d_fwd", gin, gout, k, stride);
+  if (rc) return rc;
+  SSB_REQUIRE(x && y && w_kio && w_koi, "ssb_conv1d_fwd: null pointer");
+  if (algo == SSB_ALGO_TCGEN05) {
+    SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_fwd: tcgen05 path needs bf16");
+    return ssb_conv1d_fwd_sm100(x, w_koi, y, gin, gout, k, stride, to_stream(stream));
+  }
+  const int M = gout.B * gout.pitch;
+  const TapSpec taps = fwd_taps(k, stride);
+  dim3 grid(ceil_div(M, TG_BM), ceil_div(gout.C, TG_BN));
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    tap_gemm_kernel<T, false><<<grid, TG_THREADS, 0, to_stream(stream)>>>(
+        (const T*)x, (const T*)w_kio, (T*)y, M, gout.C, gin.C, gin.B * gin.pitch, stride, taps, 1, 0, M, gout.pitch,
+        gout.len);
+  })
+  SSB_LAUNCH_CHECK("ssb_conv1d_fwd");
+  return SSB_OK;
+}
+
+int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void* dx, ssb_geom gin, ssb_geom gout,
+                     int k, int stride, int accumulate, int dtype, int algo, ssb_stream_t stream) {
+  int rc = check_conv_geom("ssb_conv1d_dgrad", gin, gout, k, stride);
+  if (rc) return rc;
+  SSB_REQUIRE(dy && dx && w_kio && w_koi, "ssb_conv1d_dgrad: null pointer");
+  if (algo == SSB_ALGO_TCGEN05) {
+    SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_dgrad: tcgen05 path needs bf16");
+    return ssb_conv1d_dgrad_sm100(dy, w_kio, dx, gin, gout, k, stride, accumulate, to_stream(stream));
+  }
+  cudaStream_t st = to_stream(stream);
+  const int rows_in = gin.B * gin.pitch, rows_out = gout.B * gout.pitch;
+  // GEMM: M over dx rows (or row pairs), N = Cin, K = Cout, weights [k][Cout][Cin] = w_koi
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    if (stride == 1) {
+      TapSpec t;
+      t.ntaps = k;
+      for (int j = 0; j < 3; ++j) { t.a_off[j] = (k == 3) ? 1 - j : 0; t.w_tap[j] = j < k ? j : 0; }
+      dim3 grid(ceil_div(rows_in, TG_BM), ceil_div(gin.C, TG_BN));
+      if (accumulate)
+        tap_gemm_kernel<T, true><<<grid, TG_THREADS, 0, st>>>((const T*)dy, (const T*)w_koi, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
+      else
+        tap_gemm_kernel<T, false><<<grid, TG_THREADS, 0, st>>>((const T*)dy, (const T*)w_koi, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
+      SSB_LAUNCH_CHECK("ssb_conv1d_dgrad");
+    } else {
+      // dx row 2q+p: p=0 <- dy[q+1]*W0 + dy[q]*W2 ; p=1 <- dy[q+1]*W1   (k=1: p=1 <- dy[q+1]*W0)
+      const int Mq = rows_in / 2;
+      dim3 grid(ceil_div(Mq, TG_BM), ceil_div(gin.C, TG_BN));
+      for (int p = 0; p < 2; ++p) {
+        TapSpec t;
+        t.ntaps = 0;
+        for (int j = 0; j < 3; ++j) { t.a_off[j] = 0; t.w_tap[j] = 0; }
+        if (k == 3) {
+          if (p == 0) { t.ntaps = 2; t.a_off[0] = 1; t.w_tap[0] = 0; t.a_off[1] = 0; t.w_tap[1] = 2; }
+          else { t.ntaps = 1; t.a_off[0] = 1; t.w_tap[0] = 1; }
+        } else if (p == 1) {
+          t.ntaps = 1; t.a_off[0] = 1; t.w_tap[0] = 0;
+        }
+        if (t.ntaps == 0) {
+          if (!accumulate) {
+            zero_parity_rows_kernel<T><<<148 * 2, 256, 0, st>>>((T*)dx, rows_in, gin.C, p);
+            SSB_LAUNCH_CHECK("ssb_conv1d_dgrad(zero)");
+          }
+          continue;
+        }
+        if (accumulate)
+          tap_gemm_kernel<T, true><<<grid, TG_THREADS, 0, st>>>((const T*)dy, (const T*)w_koi, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
+        else
+          tap_gemm_kernel<T, false><<<grid, TG_THREADS, 0, st>>>((const T*)dy, (const T*)w_koi, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
+        SSB_LAUNCH_CHECK("ssb_conv1d_dgrad");
+      }
+    }
+  })
+  return SSB_OK;
+}
+
+int ssb_conv1d_wgrad(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
+                     int dtype, int algo, ssb_stream_t stream) {
+  int rc = check_conv_geom("ssb_conv1d_wgrad", gin, gout, k, stride);
+  if (rc) return rc;
+  SSB_REQUIRE(x && dy && dw, "ssb_conv1d_wgrad: null pointer");
+  if (algo == SSB_ALGO_TCGEN05) {
+    SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_wgrad: tcgen05 path needs bf16");
+    return ssb_conv1d_wgrad_sm100(x, dy, dw, gin, gout, k, stride, to_stream(stream));
+  }
+  const int M = gout.B * gout.pitch;
+  const TapSpec taps = fwd_taps(k, stride);
+  const int tiles = ceil_div(gin.C, WG_T) * ceil_div(gout.C, WG_T) * k;
+  int nsplit = ceil_div(148 * 4, tiles);
+  const int max_split = ceil_div(M, 4 * WG_BK);
+  if (nsplit > max_split) nsplit = max_split;
+  if (nsplit < 1) nsplit = 1;
+  int rps = ceil_div(M, nsplit);
+  rps = ceil_div(rps, WG_BK) * WG_BK;
+  nsplit = ceil_div(M, rps);
+  dim3 grid(ceil_div(gin.C, WG_T), ceil_div(gout.C, WG_T), k * nsplit);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    wgrad_kernel<T><<<grid, 256, 0, to_stream(stream)>>>((const T*)x, (const T*)dy, dw, M, gin.C, gout.C, k,
+                                                          gin.B * gin.pitch, stride, taps, nsplit, rps);
+  })
+  SSB_LAUNCH_CHECK("ssb_conv1d_wgrad");
+  return SSB_OK;
+}
+
+int ssb_weight_repack(const ssb_repack_desc* table_dev, int n, int max_elems, int dtype, ssb_stream_t stream) {
+  SSB_REQUIRE(table_dev && n > 0 && max_elems > 0, "ssb_weight_repack: bad arguments");
+  int bx = ceil_div(max_elems, 256 * 8);
+  if (bx > 64) bx = 64;
+  dim3 grid(bx, n);
+  SSB_DISPATCH_DTYPE(dtype, T, { repack_kernel<T><<<grid, 256, 0, to_stream(stream)>>>(table_dev); })
+  SSB_LAUNCH_CHECK("ssb_weight_repack");
+  return SSB_OK;
+}
+
+static int check_stem(const char* who, int Cl, int L, const ssb_geom& g) {
+  SSB_REQUIRE(Cl >= 1 && Cl <= 16, "%s: num_leads %d out of range [1,16]", who, Cl);
+  SSB_REQUIRE(L >= 1 && g.B > 0, "%s: empty input", who);
+  SSB_REQUIRE(g.C % 8 == 0 && g.C > 0 && g.C <= 256, "%s: stem channels %d must be a multiple of 8 and <= 256", who, g.C);
+  SSB_REQUIRE(g.len == (L - 1) / 2 + 1, "%s: len_out %d != floor((L-1)/2)+1 for L=%d", who, g.len, L);
+  SSB_REQUIRE(g.pitch >= g.len + 2, "%s: pitch too small", who);
+  return SSB_OK;
+}
+
+int ssb_stem_conv_fwd(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g, int dtype,
+                      ssb_stream_t stream) {
+  int rc = check_stem("ssb_stem_conv_fwd", Cl, L, g);
+  if (rc) return rc;
+  SSB_REQUIRE(x && w && y, "ssb_stem_conv_fwd: null pointer");
+  const size_t smem = ((size_t)Cl * 7 * g.C + (size_t)Cl * (2 * ST_TT + 5)) * sizeof(float);
+  dim3 grid(ceil_div(g.len, ST_TT), g.B);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(stem_conv_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    stem_conv_fwd_kernel<T><<<grid, ST_THREADS, smem, to_stream(stream)>>>(x, w, (T*)y, Cl, L, g);
+  })
+  SSB_LAUNCH_CHECK("ssb_stem_conv_fwd");
+  return SSB_OK;
+}
+
+int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L, ssb_geom g, int dtype,
+                        ssb_stream_t stream) {
+  int rc = check_stem("ssb_stem_conv_wgrad", Cl, L, g);
+  if (rc) return rc;
+  SSB_REQUIRE(x && dy && dw, "ssb_stem_conv_wgrad: null pointer");
+  const size_t smem = ((size_t)ST_TT * g.C + (size_t)Cl * (2 * ST_TT + 5)) * sizeof(float);
+  dim3 grid(ceil_div(g.len, ST_TT), g.B);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(stem_conv_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    stem_conv_wgrad_kernel<T><<<grid, ST_THREADS, smem, to_stream(stream)>>>(x, (const T*)dy, dw, Cl, L, g);
+  })
+  SSB_LAUNCH_CHECK("ssb_stem_conv_wgrad");
+  return SSB_OK;
+}
+
+}  // extern "C"

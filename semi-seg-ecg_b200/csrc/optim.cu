@@ -1,0 +1,131 @@
+// Fused multi-tensor AdamW (+ EMA teacher) over flat parameter arenas, EMA of teacher BN
+// buffers and the global gradient norm.  Replaces torch.optim.AdamW's per-tensor loop
+// (utils/optimizer.py:22-34), the python EMA loops (mean_teacher.py:139-149; ~384 tiny
+// kernels per step) and get_grad_norm_ (misc.py:265-278).  HBM-bound: 28 B/param
+// (AdamW) or 36 B/param (AdamW+EMA), 128-bit loads/stores.
+#include "common.cuh"
+
+__global__ void __launch_bounds__(256)
+adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 float* __restrict__ pe, size_t n4, float beta1, float beta2, float eps, float wd,
+                 const ssb_step_params* __restrict__ sp) {
+  const float lr = sp->lr;
+  const float step_size = lr * sp->inv_bias1;
+  const float isb2 = sp->inv_sqrt_bias2;
+  const float decay = 1.0f - lr * wd;
+  const float gs = sp->grad_scale;
+  const float d = sp->ema_decay;
+  const int first = sp->ema_first;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  float4* e4 = reinterpret_cast<float4*>(pe);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
+    float P[4] = {pp.x, pp.y, pp.z, pp.w};
+    const float G[4] = {gg.x * gs, gg.y * gs, gg.z * gs, gg.w * gs};
+    float M[4] = {mm.x, mm.y, mm.z, mm.w};
+    float V[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      P[j] *= decay;
+      M[j] = beta1 * M[j] + (1.0f - beta1) * G[j];
+      V[j] = beta2 * V[j] + (1.0f - beta2) * G[j] * G[j];
+      const float denom = sqrtf(V[j]) * isb2 + eps;
+      P[j] -= step_size * (M[j] / denom);
+    }
+    p4[i] = make_float4(P[0], P[1], P[2], P[3]);
+    m4[i] = make_float4(M[0], M[1], M[2], M[3]);
+    v4[i] = make_float4(V[0], V[1], V[2], V[3]);
+    if (pe) {
+      float E[4];
+      if (first) {
+        // teacher still aliases the student: k_old == q_new (mean_teacher.py:285-290)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) E[j] = P[j] * d + P[j] * (1.0f - d);
+      } else {
+        const float4 ee = e4[i];
+        const float EO[4] = {ee.x, ee.y, ee.z, ee.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) E[j] = EO[j] * d + P[j] * (1.0f - d);
+      }
+      e4[i] = make_float4(E[0], E[1], E[2], E[3]);
+    }
+  }
+}
+
+__global__ void ema_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n,
+                           const ssb_step_params* __restrict__ sp) {
+  const float d = sp->ema_decay;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = dst[i] * d + src[i] * (1.0f - d);
+}
+
+__global__ void ema_i64_kernel(float* __restrict__ dst, const int64_t* __restrict__ src, size_t n,
+                               const ssb_step_params* __restrict__ sp) {
+  const float d = sp->ema_decay;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = dst[i] * d + (float)src[i] * (1.0f - d);
+}
+
+__global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ ws) {
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float x = g[i];
+    acc += (double)x * (double)x;
+  }
+  acc = warp_sum_d(acc);
+  __shared__ double s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += s[i];
+    atomicAdd(ws, t);
+  }
+}
+__global__ void grad_norm_final_kernel(const double* ws, float* out) { out[0] = (float)sqrt(ws[0]); }
+
+extern "C" {
+
+int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, size_t n, float beta1, float beta2,
+                  float eps, float weight_decay, const ssb_step_params* sp, ssb_stream_t stream) {
+  SSB_REQUIRE(p && g && m && v && sp, "ssb_adamw_ema: null pointer");
+  SSB_REQUIRE(n > 0 && n % 4 == 0, "ssb_adamw_ema: arena length %zu must be a positive multiple of 4", n);
+  const size_t n4 = n / 4;
+  long long blocks = ceil_div_ll((long long)n4, 256 * 2);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adamw_ema_kernel<<<(int)blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, p_ema, n4, beta1, beta2, eps, weight_decay, sp);
+  SSB_LAUNCH_CHECK("ssb_adamw_ema");
+  return SSB_OK;
+}
+
+int ssb_ema(float* dst, const float* src, size_t n, const ssb_step_params* sp, ssb_stream_t stream) {
+  SSB_REQUIRE(dst && src && sp && n > 0, "ssb_ema: bad arguments");
+  long long blocks = ceil_div_ll((long long)n, 256);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  ema_kernel<<<(int)blocks, 256, 0, to_stream(stream)>>>(dst, src, n, sp);
+  SSB_LAUNCH_CHECK("ssb_ema");
+  return SSB_OK;
+}
+
+int ssb_ema_i64(float* dst, const int64_t* src, size_t n, const ssb_step_params* sp, ssb_stream_t stream) {
+  SSB_REQUIRE(dst && src && sp && n > 0, "ssb_ema_i64: bad arguments");
+  ema_i64_kernel<<<(int)ceil_div_ll((long long)n, 256), 256, 0, to_stream(stream)>>>(dst, src, n, sp);
+  SSB_LAUNCH_CHECK("ssb_ema_i64");
+  return SSB_OK;
+}
+
+int ssb_grad_norm(const float* g, size_t n, double* ws, float* out, ssb_stream_t stream) {
+  SSB_REQUIRE(g && ws && out && n > 0, "ssb_grad_norm: bad arguments");
+  long long blocks = ceil_div_ll((long long)n, 256 * 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  grad_sumsq_kernel<<<(int)blocks, 256, 0, to_stream(stream)>>>(g, n, ws);
+  SSB_LAUNCH_CHECK("ssb_grad_norm");
+  grad_norm_final_kernel<<<1, 1, 0, to_stream(stream)>>>(ws, out);
+  SSB_LAUNCH_CHECK("ssb_grad_norm(final)");
+  return SSB_OK;
+}
+
+}  // extern "C"

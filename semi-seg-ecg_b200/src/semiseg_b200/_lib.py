@@ -1,0 +1,123 @@
+"""ctypes binding of libsemiseg_b200.so (C ABI declared in include/ssb.h).
+
+The product path has no CPU fallback: if the shared library is missing, `load()` raises,
+and every op raises `RuntimeError` with the library's own message on a non-zero status.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+F32, BF16 = 0, 1
+ALGO_SIMT, ALGO_TCGEN05 = 0, 1
+LOSS_SUP, LOSS_FIXMATCH, LOSS_SOFT = 0, 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))          # semi-seg-ecg_b200/
+LIB_PATH = os.path.join(PKG_ROOT, "lib", "libsemiseg_b200.so")
+CSRC_DIR = os.path.join(PKG_ROOT, "csrc")
+
+
+class Geom(C.Structure):
+    _fields_ = [("B", C.c_int32), ("pitch", C.c_int32), ("len", C.c_int32), ("C", C.c_int32)]
+
+    def rows(self) -> int:
+        return self.B * self.pitch
+
+    def __repr__(self):
+        return f"Geom(B={self.B}, pitch={self.pitch}, len={self.len}, C={self.C})"
+
+
+class BN(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p), ("sums", C.c_void_p),
+                ("mean_invstd", C.c_void_p), ("bwd_sums", C.c_void_p), ("dgamma", C.c_void_p),
+                ("dbeta", C.c_void_p), ("count_mul", C.c_int32), ("pad", C.c_int32)]
+
+
+class StepParams(C.Structure):
+    _fields_ = [("lr", C.c_float), ("inv_bias1", C.c_float), ("inv_sqrt_bias2", C.c_float),
+                ("ema_decay", C.c_float), ("ema_first", C.c_int32), ("step", C.c_int32),
+                ("rng_seed", C.c_uint32), ("rng_step", C.c_uint32), ("grad_scale", C.c_float),
+                ("conf_thresh", C.c_float), ("pad", C.c_float * 6)]
+
+
+class RepackDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("w_kio", C.c_void_p), ("w_koi", C.c_void_p), ("Cout", C.c_int32),
+                ("Cin", C.c_int32), ("k", C.c_int32), ("pad", C.c_int32)]
+
+
+assert C.sizeof(StepParams) == 64 and C.sizeof(RepackDesc) == 40 and C.sizeof(Geom) == 16
+
+_P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_BNP = C.POINTER(BN)
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES); this table is also what
+# tests/test_cabi.py checks against include/ssb.h
+SIGNATURES = {
+    "ssb_version": [],
+    "ssb_last_error": [],
+    "ssb_device_check": [],
+    "ssb_launch_count": [],
+    "ssb_memset_zero": [_P, _SZ, _P],
+    "ssb_stem_conv_fwd": [_P, _P, _P, _I, _I, Geom, _I, _P],
+    "ssb_stem_conv_wgrad": [_P, _P, _P, _I, _I, Geom, _I, _P],
+    "ssb_conv1d_fwd": [_P, _P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
+    "ssb_conv1d_dgrad": [_P, _P, _P, _P, Geom, Geom, _I, _I, _I, _I, _I, _P],
+    "ssb_conv1d_wgrad": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
+    "ssb_weight_repack": [_P, _I, _I, _I, _P],
+    "ssb_bn_stats": [_P, Geom, _P, _I, _P],
+    "ssb_bn_act_fwd": [_P, _BNP, _P, _BNP, _P, Geom, _I, _I, _I, _P],
+    "ssb_stem_bn_relu_pool_fwd": [_P, _BNP, _P, Geom, Geom, _I, _I, _P],
+    "ssb_bn_bwd_reduce": [_P, _P, _P, _P, _BNP, _P, _BNP, Geom, _I, _P],
+    "ssb_bn_bwd_apply": [_P, _P, _P, _P, _BNP, _P, _P, _BNP, _P, _P, Geom, _I, _P],
+    "ssb_stem_bwd_reduce": [_P, _P, _BNP, Geom, Geom, _I, _P],
+    "ssb_stem_bwd_apply": [_P, _P, _BNP, _P, Geom, Geom, _I, _P],
+    "ssb_head_cls_fwd": [_P, _P, _P, _P, Geom, _I, _F, _P, _P, _I, _P],
+    "ssb_head_cls_bwd": [_P, _P, _P, _P, _P, _P, Geom, _I, _F, _P, _P, _I, _P],
+    "ssb_upsample_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ssb_upsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
+    "ssb_pseudo_label": [_P, _F, _P, _P, _P, _I, _I, _I, _P],
+    "ssb_semi_loss": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P],
+    "ssb_adamw_ema": [_P, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _P, _P],
+    "ssb_ema": [_P, _P, _SZ, _P, _P],
+    "ssb_ema_i64": [_P, _P, _SZ, _P, _P],
+    "ssb_grad_norm": [_P, _SZ, _P, _P, _P],
+}
+_RESTYPES = {"ssb_last_error": C.c_char_p, "ssb_launch_count": C.c_int64}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load(path: Optional[str] = None) -> C.CDLL:
+    """dlopen the kernel library (no CUDA initialisation happens at load time)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or os.environ.get("SSB_LIB", LIB_PATH)
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"libsemiseg_b200.so not found at {p}: build it with `make -C {CSRC_DIR}` "
+            "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError => symbol missing => fail loudly
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.ssb_version() != 1:
+        raise RuntimeError(f"libsemiseg_b200.so ABI version {lib.ssb_version()} != 1")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().ssb_last_error()
+        raise RuntimeError(f"libsemiseg_b200 {what} failed ({status}): {msg.decode() if msg else '?'}")
+
+
+def call(name: str, *args) -> None:
+    """Invoke an int-returning entry point and raise on error."""
+    check(getattr(load(), name)(*args), name)

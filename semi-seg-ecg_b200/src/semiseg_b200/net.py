@@ -1,0 +1,570 @@
+"""Network description, flat parameter arenas and the hand-scheduled forward/backward plan.
+
+This is the host side of the hot path: it owns the memory layout in HBM (flat padded NLC
+activations, flat fp32 parameter / gradient / optimizer arenas, repacked GEMM weights) and
+issues the C-ABI kernels of libsemiseg_b200 in dependency order on one CUDA stream.  No
+autograd, no ATen compute ops: torch is used for allocation and streams only.
+
+Reference behaviour restated here (file:line relative to the reference tree):
+  stem/maxpool/stages     src/models/backbones/resnet.py:206-257, 259-324, 353-363
+  BasicBlock              src/models/backbones/resnet.py:55-72
+  FCNHead                 src/models/decode_heads/fcn_head.py:36-97
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BN, Geom, RepackDesc, StepParams, call
+
+
+# --------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class SegNetSpec:
+    """Constructor arguments of resnet18-style backbone + FCNHead that the kernels cover."""
+    num_leads: int = 1
+    stem_channels: int = 64
+    base_channels: int = 64
+    strides: Tuple[int, ...] = (1, 2, 2, 2)
+    stage_blocks: Tuple[int, ...] = (2, 2, 2, 2)
+    head_channels: int = 128
+    num_classes: int = 4
+    dropout_ratio: float = 0.1
+    align_corners: bool = False
+
+    def planes(self, i: int) -> int:
+        return self.base_channels * 2 ** i
+
+    @property
+    def feat_dim(self) -> int:
+        return self.planes(len(self.stage_blocks) - 1)
+
+
+def conv_out_len(L: int, k: int, s: int, p: int) -> int:
+    return (L + 2 * p - (k - 1) - 1) // s + 1
+
+
+@dataclass
+class ConvDesc:
+    name: str          # state_dict key of the weight
+    cout: int
+    cin: int
+    k: int
+    stride: int
+    poff: int = 0      # offset (floats) in the parameter arena
+    soff: int = 0      # offset (elements) in each repacked-weight arena
+
+
+@dataclass
+class BNDesc:
+    prefix: str        # state_dict prefix
+    C: int
+    goff: int = 0      # gamma offset in parameter arena
+    boff: int = 0      # beta offset
+    roff: int = 0      # running_mean offset in buffer arena (running_var at roff + C)
+    soff: int = 0      # offset (doubles) in sums arenas; (floats) in mean_invstd arena
+    index: int = 0     # index into num_batches_tracked
+
+
+@dataclass
+class BlockDesc:
+    prefix: str
+    conv1: ConvDesc
+    bn1: BNDesc
+    conv2: ConvDesc
+    bn2: BNDesc
+    convd: Optional[ConvDesc]
+    bnd: Optional[BNDesc]
+    stage: int
+
+
+ALIGN = 64  # floats; every tensor in an arena starts on a 256-byte boundary
+
+
+class ParamLayout:
+    """Names, shapes and arena offsets in the reference's `parameters()` / `buffers()` order
+    (SURVEY.md 8b-viii).  Single source of truth for state_dict <-> arena mapping."""
+
+    def __init__(self, spec: SegNetSpec):
+        self.spec = spec
+        self.params: List[Tuple[str, Tuple[int, ...], int]] = []   # (name, shape, offset)
+        self.convs: List[ConvDesc] = []
+        self.bns: List[BNDesc] = []
+        self.blocks: List[BlockDesc] = []
+        self._poff = 0
+        self._roff = 0
+        self._soff = 0
+        self._woff = 0
+
+        self.stem_conv = self._conv("backbone.stem.0.weight", spec.stem_channels, spec.num_leads, 7, 2, repack=False)
+        self.stem_bn = self._bn("backbone.stem.1", spec.stem_channels)
+        inpl = spec.stem_channels
+        for i, nb in enumerate(spec.stage_blocks):
+            pl = spec.planes(i)
+            for j in range(nb):
+                pre = f"backbone.layer{i + 1}.{j}"
+                s = spec.strides[i] if j == 0 else 1
+                cin = inpl if j == 0 else pl
+                c1 = self._conv(pre + ".conv1.weight", pl, cin, 3, s)
+                b1 = self._bn(pre + ".bn1", pl)
+                c2 = self._conv(pre + ".conv2.weight", pl, pl, 3, 1)
+                b2 = self._bn(pre + ".bn2", pl)
+                cd = bd = None
+                if j == 0 and (s != 1 or inpl != pl):
+                    cd = self._conv(pre + ".downsample.0.weight", pl, inpl, 1, s)
+                    bd = self._bn(pre + ".downsample.1", pl)
+                self.blocks.append(BlockDesc(pre, c1, b1, c2, b2, cd, bd, i))
+            inpl = pl
+        self.head_conv = self._conv("decode_head.convs.0.0.weight", spec.head_channels, spec.feat_dim, 3, 1)
+        self.head_bn = self._bn("decode_head.convs.0.1", spec.head_channels)
+        self.cls_w_off = self._param("decode_head.cls_seg.weight", (spec.num_classes, spec.head_channels, 1))
+        self.cls_b_off = self._param("decode_head.cls_seg.bias", (spec.num_classes,))
+        self.n_params = self._poff
+        self.n_bufs = self._roff
+        self.n_sums = self._soff
+        self.n_shadow = self._woff
+        self.numel = sum(int(torch.Size(s).numel()) for _, s, _ in self.params)
+
+    def _param(self, name, shape) -> int:
+        off = self._poff
+        self.params.append((name, tuple(shape), off))
+        n = 1
+        for d in shape:
+            n *= d
+        self._poff += (n + ALIGN - 1) // ALIGN * ALIGN
+        return off
+
+    def _conv(self, name, cout, cin, k, stride, repack=True) -> ConvDesc:
+        d = ConvDesc(name, cout, cin, k, stride, self._param(name, (cout, cin, k)))
+        if repack:
+            d.soff = self._woff
+            self._woff += (cout * cin * k + ALIGN - 1) // ALIGN * ALIGN
+            self.convs.append(d)
+        return d
+
+    def _bn(self, prefix, Cn) -> BNDesc:
+        d = BNDesc(prefix, Cn)
+        d.goff = self._param(prefix + ".weight", (Cn,))
+        d.boff = self._param(prefix + ".bias", (Cn,))
+        d.roff = self._roff
+        self._roff += (2 * Cn + ALIGN - 1) // ALIGN * ALIGN
+        d.soff = self._soff
+        self._soff += (2 * Cn + ALIGN - 1) // ALIGN * ALIGN
+        d.index = len(self.bns)
+        self.bns.append(d)
+        return d
+
+    def param_names(self) -> List[str]:
+        return [n for n, _, _ in self.params]
+
+    def buffer_names(self) -> List[str]:
+        out = []
+        for b in self.bns:
+            out += [b.prefix + ".running_mean", b.prefix + ".running_var", b.prefix + ".num_batches_tracked"]
+        return out
+
+
+def _torch_dtype(dtype: int):
+    return torch.float32 if dtype == _lib.F32 else torch.bfloat16
+
+
+class Shadow:
+    """Repacked GEMM copies of all conv weights of one WeightSet in one storage dtype."""
+
+    def __init__(self, w: "WeightSet", dtype: int):
+        layout, device = w.layout, w.device
+        self.dtype = dtype
+        self.n = len(layout.convs)
+        tdt = _torch_dtype(dtype)
+        self.kio = torch.zeros(max(layout.n_shadow, 1), dtype=tdt, device=device)
+        self.koi = torch.zeros(max(layout.n_shadow, 1), dtype=tdt, device=device)
+        es = self.kio.element_size()
+        tab = (RepackDesc * self.n)()
+        for i, c in enumerate(layout.convs):
+            tab[i].w = w.params.data_ptr() + 4 * c.poff
+            tab[i].w_kio = self.kio.data_ptr() + es * c.soff
+            tab[i].w_koi = self.koi.data_ptr() + es * c.soff
+            tab[i].Cout, tab[i].Cin, tab[i].k = c.cout, c.cin, c.k
+        raw = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8)
+        self.table = raw.to(device)
+        self.max_elems = max(c.cout * c.cin * c.k for c in layout.convs)
+
+    def repack(self, stream: int) -> None:
+        call("ssb_weight_repack", self.table.data_ptr(), self.n, self.max_elems, self.dtype, stream)
+
+    def kio_ptr(self, c: ConvDesc) -> int:
+        return self.kio.data_ptr() + self.kio.element_size() * c.soff
+
+    def koi_ptr(self, c: ConvDesc) -> int:
+        return self.koi.data_ptr() + self.koi.element_size() * c.soff
+
+
+class WeightSet:
+    """One set of network weights in HBM: fp32 master arena, BN buffers, repacked GEMM copies."""
+
+    def __init__(self, layout: ParamLayout, device, nbt_float: bool = False):
+        self.layout = layout
+        self.device = torch.device(device)
+        self.params = torch.zeros(layout.n_params, dtype=torch.float32, device=device)
+        self.bufs = torch.zeros(layout.n_bufs, dtype=torch.float32, device=device)
+        # student: int64 counters; EMA teacher: float32 (mean_teacher.py:145-149 promotes them)
+        self.nbt = torch.zeros(len(layout.bns), dtype=torch.float32 if nbt_float else torch.int64, device=device)
+        for b in layout.bns:  # fresh BatchNorm: running_var = 1
+            self.bufs[b.roff + b.C: b.roff + 2 * b.C] = 1.0
+        self._shadows: Dict[int, Shadow] = {}
+
+    def shadow(self, dtype: int) -> Shadow:
+        if dtype not in self._shadows:
+            self._shadows[dtype] = Shadow(self, dtype)
+        return self._shadows[dtype]
+
+    # ---- views ---------------------------------------------------------------------
+    def param_view(self, name: str) -> torch.Tensor:
+        for n, shape, off in self.layout.params:
+            if n == name:
+                numel = int(torch.Size(shape).numel())
+                return self.params[off: off + numel].view(shape)
+        raise KeyError(name)
+
+    def param_views(self, arena: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        a = self.params if arena is None else arena
+        return {n: a[off: off + int(torch.Size(s).numel())].view(s) for n, s, off in self.layout.params}
+
+    def buffer_views(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for b in self.layout.bns:
+            out[b.prefix + ".running_mean"] = self.bufs[b.roff: b.roff + b.C]
+            out[b.prefix + ".running_var"] = self.bufs[b.roff + b.C: b.roff + 2 * b.C]
+            out[b.prefix + ".num_batches_tracked"] = self.nbt[b.index]
+        return out
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Reference-ordered state_dict (128 entries for resnet18+FCNHead)."""
+        out: Dict[str, torch.Tensor] = {}
+        pv, bv = self.param_views(), self.buffer_views()
+        bn_by_prefix = {b.prefix: b for b in self.layout.bns}
+        for n, _, _ in self.layout.params:
+            out[n] = pv[n]
+            if n.endswith(".bias") and n[:-5] in bn_by_prefix:
+                p = n[:-5]
+                for suffix in (".running_mean", ".running_var", ".num_batches_tracked"):
+                    out[p + suffix] = bv[p + suffix]
+        return out
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        mine = self.state_dict()
+        missing = [k for k in mine if k not in sd]
+        unexpected = [k for k in sd if k not in mine]
+        if missing or unexpected:
+            raise RuntimeError(f"state_dict mismatch: missing {missing[:4]}..., unexpected {unexpected[:4]}...")
+        with torch.no_grad():
+            for k, v in mine.items():
+                src = sd[k]
+                if tuple(src.shape) != tuple(v.shape):
+                    raise RuntimeError(f"shape mismatch for {k}: {tuple(src.shape)} vs {tuple(v.shape)}")
+                v.copy_(src.to(device=v.device, dtype=v.dtype))
+
+    # ---- pointers ------------------------------------------------------------------
+    def w_ptr(self, c: ConvDesc) -> int:
+        return self.params.data_ptr() + 4 * c.poff
+
+
+class TrainState:
+    """Gradient / optimizer arenas and BN statistic scratch for one trainable WeightSet."""
+
+    def __init__(self, w: WeightSet):
+        lay, dev = w.layout, w.device
+        self.grads = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
+        self.step = 0
+
+
+class NetPlan:
+    """Static buffers + kernel schedule for one (weights, batch, length, dtype, mode)."""
+
+    def __init__(self, weights: WeightSet, dtype: int, B: int, L: int, train: bool, algo: Optional[int] = None,
+                 grads: Optional[torch.Tensor] = None, sp_ptr: int = 0):
+        self.w = weights
+        self.sh = weights.shadow(dtype)
+        self.lay = weights.layout
+        self.spec = self.lay.spec
+        self.B, self.L, self.train = B, L, train
+        self.dtype = dtype
+        self.device = weights.device
+        self.tdt = _torch_dtype(self.dtype)
+        self.grads = grads
+        self.sp_ptr = sp_ptr
+        self.drop_mask_ptr = 0   # tests may inject an explicit keep-mask (u8 [B, Lh, Ch])
+        self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
+        if algo is None:
+            algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
+        self.algo = algo
+        spec = self.spec
+        if train and grads is None:
+            raise ValueError("a training plan needs the gradient arena")
+        for ch in (spec.stem_channels, spec.base_channels, spec.head_channels):
+            if ch % 8:
+                raise ValueError(f"channel counts must be multiples of 8, got {ch}")
+
+        # ---- lengths and pitches (see include/ssb.h for the layout) ----
+        L0 = conv_out_len(L, 7, 2, 3)
+        Lp = conv_out_len(L0, 3, 2, 1)
+        lens = []
+        cur = Lp
+        for s in spec.strides:
+            cur = conv_out_len(cur, 3, s, 1)
+            lens.append(cur)
+        pitches = [0] * len(lens)
+        pitches[-1] = lens[-1] + 2
+        for i in range(len(lens) - 2, -1, -1):
+            pitches[i] = pitches[i + 1] * spec.strides[i + 1]
+            assert pitches[i] >= lens[i] + 2
+        p_pool = pitches[0] * spec.strides[0]
+        assert p_pool >= Lp + 2
+        p_stem = 2 * p_pool
+        assert p_stem >= L0 + 2
+        self.g_stem = Geom(B, p_stem, L0, spec.stem_channels)
+        self.g_pool = Geom(B, p_pool, Lp, spec.stem_channels)
+        self.g_stage = [Geom(B, pitches[i], lens[i], spec.planes(i)) for i in range(len(lens))]
+        self.g_head = Geom(B, pitches[-1], lens[-1], spec.head_channels)
+        self.Lh = lens[-1]
+
+        def act(g: Geom, C_: Optional[int] = None) -> torch.Tensor:
+            return torch.zeros(g.B * g.pitch, C_ or g.C, dtype=self.tdt, device=self.device)
+
+        # ---- BN statistic arenas ----
+        self.sums = torch.zeros(self.lay.n_sums, dtype=torch.float64, device=self.device)
+        self.bwd_sums = torch.zeros(self.lay.n_sums, dtype=torch.float64, device=self.device)
+        self.mean_invstd = torch.zeros(self.lay.n_sums, dtype=torch.float32, device=self.device)
+        self._bn_structs: Dict[str, BN] = {}
+        for b in self.lay.bns:
+            self._bn_structs[b.prefix] = self._make_bn(b)
+
+        # ---- activations ----
+        self.x_in: Optional[torch.Tensor] = None  # [B, C, L] fp32, bound by the caller
+        self.c0 = act(self.g_stem)
+        self.p0 = act(self.g_pool)
+        self.blk_bufs: List[Dict[str, torch.Tensor]] = []
+        gin = self.g_pool
+        for bd in self.lay.blocks:
+            gout = self.g_stage[bd.stage]
+            bufs = {"c1": act(gout), "a1": act(gout), "c2": act(gout), "out": act(gout)}
+            if bd.convd is not None:
+                bufs["cd"] = act(gout)
+            self.blk_bufs.append(bufs)
+            gin = gout
+        self.ch = act(self.g_head)
+        self.ah = act(self.g_head)
+        self.low = torch.zeros(B, self.Lh, spec.num_classes, dtype=torch.float32, device=self.device)
+
+        # ---- gradient scratch (per geometry) ----
+        self._scratch: Dict[Tuple[int, int, int], Dict[str, torch.Tensor]] = {}
+        if train:
+            self.dlow = torch.zeros_like(self.low)
+            self.dc0 = act(self.g_stem)
+            for g in [self.g_pool, self.g_head] + self.g_stage:
+                key = (g.pitch, g.len, g.C)
+                if key not in self._scratch:
+                    self._scratch[key] = {n: act(g) for n in ("gA", "gE", "gB", "gC", "gD")}
+        self.launches_fwd = 0
+
+    # ---- helpers -------------------------------------------------------------------
+    def _make_bn(self, b: BNDesc) -> BN:
+        w = self.w
+        s = BN()
+        s.gamma = w.params.data_ptr() + 4 * b.goff
+        s.beta = w.params.data_ptr() + 4 * b.boff
+        s.running_mean = w.bufs.data_ptr() + 4 * b.roff
+        s.running_var = w.bufs.data_ptr() + 4 * (b.roff + b.C)
+        s.num_batches_tracked = (w.nbt.data_ptr() + 8 * b.index) if w.nbt.dtype == torch.int64 else None
+        s.sums = self.sums.data_ptr() + 8 * b.soff
+        s.mean_invstd = self.mean_invstd.data_ptr() + 4 * b.soff
+        s.bwd_sums = self.bwd_sums.data_ptr() + 8 * b.soff
+        if self.grads is not None:
+            s.dgamma = self.grads.data_ptr() + 4 * b.goff
+            s.dbeta = self.grads.data_ptr() + 4 * b.boff
+        return s
+
+    def bn(self, b: BNDesc):
+        return C.byref(self._bn_structs[b.prefix])
+
+    def _g(self, c: ConvDesc) -> int:
+        return self.grads.data_ptr() + 4 * c.poff
+
+    def _conv_fwd(self, c: ConvDesc, x, y, gin: Geom, gout: Geom, st: int):
+        call("ssb_conv1d_fwd", x.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), y.data_ptr(), gin, gout,
+             c.k, c.stride, self.dtype, self._algo_for(c), st)
+
+    def _algo_for(self, c: ConvDesc) -> int:
+        if self.algo == _lib.ALGO_TCGEN05 and self.dtype == _lib.BF16 and c.cin % 64 == 0 and c.cout % 64 == 0:
+            return _lib.ALGO_TCGEN05
+        return _lib.ALGO_SIMT
+
+    def _stats(self, buf, g: Geom, b: BNDesc, st: int):
+        call("ssb_bn_stats", buf.data_ptr(), g, self._bn_structs[b.prefix].sums, self.dtype, st)
+        if self.sync_hook is not None:
+            self.sync_hook(self.sums[b.soff: b.soff + 2 * b.C])
+
+    def _sync_bwd(self, first: BNDesc, last: Optional[BNDesc] = None):
+        if self.sync_hook is not None:
+            last = last or first
+            self.sync_hook(self.bwd_sums[first.soff: last.soff + 2 * last.C])
+
+    def zero_stats(self, st: int):
+        call("ssb_memset_zero", self.sums.data_ptr(), self.sums.numel() * 8, st)
+        if self.train:
+            call("ssb_memset_zero", self.bwd_sums.data_ptr(), self.bwd_sums.numel() * 8, st)
+
+    # ---- forward -------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, st: int, train_mode: Optional[bool] = None) -> torch.Tensor:
+        """x: [B, C, L] fp32 contiguous CUDA tensor.  Returns low-res logits [B, Lh, ncls] fp32.
+        train_mode: batch statistics + running-stat update + dropout (default: plan's mode)."""
+        tm = self.train if train_mode is None else train_mode
+        if tm and not self.train:
+            raise ValueError("plan was built for eval mode")
+        spec, lay, dt = self.spec, self.lay, self.dtype
+        assert x.dtype == torch.float32 and x.is_contiguous() and tuple(x.shape) == (self.B, spec.num_leads, self.L), \
+            f"input must be contiguous fp32 [{self.B},{spec.num_leads},{self.L}], got {tuple(x.shape)} {x.dtype}"
+        self.x_in = x
+        t = 1 if tm else 0
+        if tm:
+            self.zero_stats(st)
+        call("ssb_stem_conv_fwd", x.data_ptr(), self.w.w_ptr(lay.stem_conv), self.c0.data_ptr(), spec.num_leads,
+             self.L, self.g_stem, dt, st)
+        if tm:
+            self._stats(self.c0, self.g_stem, lay.stem_bn, st)
+        call("ssb_stem_bn_relu_pool_fwd", self.c0.data_ptr(), self.bn(lay.stem_bn), self.p0.data_ptr(), self.g_stem,
+             self.g_pool, t, dt, st)
+        h, gin = self.p0, self.g_pool
+        for bd, bufs in zip(lay.blocks, self.blk_bufs):
+            gout = self.g_stage[bd.stage]
+            self._conv_fwd(bd.conv1, h, bufs["c1"], gin, gout, st)
+            if tm:
+                self._stats(bufs["c1"], gout, bd.bn1, st)
+            call("ssb_bn_act_fwd", bufs["c1"].data_ptr(), self.bn(bd.bn1), None, None, bufs["a1"].data_ptr(), gout, 1, t, dt, st)
+            self._conv_fwd(bd.conv2, bufs["a1"], bufs["c2"], gout, gout, st)
+            if tm:
+                self._stats(bufs["c2"], gout, bd.bn2, st)
+            if bd.convd is not None:
+                self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st)
+                if tm:
+                    self._stats(bufs["cd"], gout, bd.bnd, st)
+                call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), bufs["cd"].data_ptr(), self.bn(bd.bnd),
+                     bufs["out"].data_ptr(), gout, 1, t, dt, st)
+            else:
+                call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), h.data_ptr(), None,
+                     bufs["out"].data_ptr(), gout, 1, t, dt, st)
+            h, gin = bufs["out"], gout
+        self.feat = h
+        gfeat = gin
+        self._conv_fwd(lay.head_conv, h, self.ch, gfeat, self.g_head, st)
+        if tm:
+            self._stats(self.ch, self.g_head, lay.head_bn, st)
+        call("ssb_bn_act_fwd", self.ch.data_ptr(), self.bn(lay.head_bn), None, None, self.ah.data_ptr(), self.g_head, 1, t, dt, st)
+        p = spec.dropout_ratio if tm else 0.0
+        call("ssb_head_cls_fwd", self.ah.data_ptr(), self.w.params.data_ptr() + 4 * lay.cls_w_off,
+             self.w.params.data_ptr() + 4 * lay.cls_b_off, self.low.data_ptr(), self.g_head, spec.num_classes,
+             p, self.drop_mask_ptr or None, self.sp_ptr or None, dt, st)
+        return self.low
+
+    # ---- backward ------------------------------------------------------------------
+    def backward(self, dlow: torch.Tensor, st: int) -> None:
+        """dlow: gradient w.r.t. the low-res logits [B, Lh, ncls] fp32.  Accumulates weight
+        gradients into the gradient arena (the caller zeroes it once per step)."""
+        assert self.train
+        spec, lay, dt = self.spec, self.lay, self.dtype
+        x = self.x_in
+        sc_h = self._scratch[(self.g_head.pitch, self.g_head.len, self.g_head.C)]
+        p = spec.dropout_ratio
+        gw = self.grads.data_ptr()
+        call("ssb_head_cls_bwd", dlow.data_ptr(), self.ah.data_ptr(), self.w.params.data_ptr() + 4 * lay.cls_w_off,
+             sc_h["gA"].data_ptr(), gw + 4 * lay.cls_w_off, gw + 4 * lay.cls_b_off, self.g_head, spec.num_classes, p,
+             self.drop_mask_ptr or None, self.sp_ptr or None, dt, st)
+        # head BN + ReLU backward -> dch (gB)
+        call("ssb_bn_bwd_reduce", sc_h["gA"].data_ptr(), None, self.ah.data_ptr(), self.ch.data_ptr(), self.bn(lay.head_bn),
+             None, None, self.g_head, dt, st)
+        self._sync_bwd(lay.head_bn)
+        call("ssb_bn_bwd_apply", sc_h["gA"].data_ptr(), None, self.ah.data_ptr(), self.ch.data_ptr(), self.bn(lay.head_bn),
+             sc_h["gB"].data_ptr(), None, None, None, None, self.g_head, dt, st)
+        gfeat = self.g_stage[-1]
+        sc_f = self._scratch[(gfeat.pitch, gfeat.len, gfeat.C)]
+        hc = lay.head_conv
+        G = sc_f["gA"]
+        call("ssb_conv1d_dgrad", sc_h["gB"].data_ptr(), self.sh.kio_ptr(hc), self.sh.koi_ptr(hc), G.data_ptr(), gfeat,
+             self.g_head, hc.k, hc.stride, 0, dt, self._algo_for(hc), st)
+        call("ssb_conv1d_wgrad", self.feat.data_ptr(), sc_h["gB"].data_ptr(), self._g(hc), gfeat, self.g_head, hc.k,
+             hc.stride, dt, self._algo_for(hc), st)
+
+        # blocks in reverse
+        nblk = len(lay.blocks)
+        for bi in range(nblk - 1, -1, -1):
+            bd, bufs = lay.blocks[bi], self.blk_bufs[bi]
+            gout = self.g_stage[bd.stage]
+            if bi == 0:
+                xin, gin = self.p0, self.g_pool
+            else:
+                xin, gin = self.blk_bufs[bi - 1]["out"], self.g_stage[lay.blocks[bi - 1].stage]
+            sc = self._scratch[(gout.pitch, gout.len, gout.C)]
+            sci = self._scratch[(gin.pitch, gin.len, gin.C)]
+            # destination for the gradient w.r.t. the block input
+            if sci is sc:
+                Gin = sc["gE"] if G is sc["gA"] else sc["gA"]
+            else:
+                Gin = sci["gA"]
+            dc2, dcd, da1 = sc["gB"], sc["gC"], sc["gD"]
+            out, c2 = bufs["out"], bufs["c2"]
+            if bd.convd is not None:
+                cd = bufs["cd"]
+                call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
+                     cd.data_ptr(), self.bn(bd.bnd), gout, dt, st)
+                self._sync_bwd(bd.bn2, bd.bnd)
+                call("ssb_bn_bwd_apply", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
+                     dc2.data_ptr(), cd.data_ptr(), self.bn(bd.bnd), dcd.data_ptr(), None, gout, dt, st)
+            else:
+                call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
+                     None, None, gout, dt, st)
+                self._sync_bwd(bd.bn2)
+                call("ssb_bn_bwd_apply", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
+                     dc2.data_ptr(), None, None, None, Gin.data_ptr(), gout, dt, st)
+            c = bd.conv2
+            call("ssb_conv1d_dgrad", dc2.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), da1.data_ptr(), gout, gout,
+                 c.k, c.stride, 0, dt, self._algo_for(c), st)
+            call("ssb_conv1d_wgrad", bufs["a1"].data_ptr(), dc2.data_ptr(), self._g(c), gout, gout, c.k, c.stride, dt,
+                 self._algo_for(c), st)
+            # bn1 + relu backward -> dc1 (reuses gB: dc2 is dead)
+            dc1 = dc2
+            call("ssb_bn_bwd_reduce", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
+                 None, None, gout, dt, st)
+            self._sync_bwd(bd.bn1)
+            call("ssb_bn_bwd_apply", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
+                 dc1.data_ptr(), None, None, None, None, gout, dt, st)
+            c = bd.conv1
+            acc = 0 if bd.convd is not None else 1   # identity residual: Gin already holds g
+            call("ssb_conv1d_dgrad", dc1.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), Gin.data_ptr(), gin, gout,
+                 c.k, c.stride, acc, dt, self._algo_for(c), st)
+            call("ssb_conv1d_wgrad", xin.data_ptr(), dc1.data_ptr(), self._g(c), gin, gout, c.k, c.stride, dt,
+                 self._algo_for(c), st)
+            if bd.convd is not None:
+                c = bd.convd
+                call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), Gin.data_ptr(), gin, gout,
+                     c.k, c.stride, 1, dt, self._algo_for(c), st)
+                call("ssb_conv1d_wgrad", xin.data_ptr(), dcd.data_ptr(), self._g(c), gin, gout, c.k, c.stride, dt,
+                     self._algo_for(c), st)
+            G = Gin
+        # stem tail + stem conv weight gradient
+        call("ssb_stem_bwd_reduce", G.data_ptr(), self.c0.data_ptr(), self.bn(lay.stem_bn), self.g_stem, self.g_pool, dt, st)
+        self._sync_bwd(lay.stem_bn)
+        call("ssb_stem_bwd_apply", G.data_ptr(), self.c0.data_ptr(), self.bn(lay.stem_bn), self.dc0.data_ptr(),
+             self.g_stem, self.g_pool, dt, st)
+        call("ssb_stem_conv_wgrad", x.data_ptr(), self.dc0.data_ptr(), self._g(lay.stem_conv), spec.num_leads, self.L,
+             self.g_stem, dt, st)
+
+    # ---- test helpers: NCL fp32 copies of internal tensors ---------------------------
+    def to_ncl(self, buf: torch.Tensor, g: Geom) -> torch.Tensor:
+        v = buf.view(g.B, g.pitch, -1)[:, 1: 1 + g.len, :]
+        return v.permute(0, 2, 1).float().contiguous()

@@ -1,0 +1,171 @@
+"""Shared epoch loop behind algorithms.{base,fixmatch,mean_teacher}.train_one_epoch.
+
+Keeps the reference's observable behaviour (per-iteration LR schedule, returned epoch means,
+non-finite-loss abort, tensorboard scalar names) while replacing the per-step host work:
+no `.item()` per step, no `cuda.synchronize()` per step, no separate logging all-reduces --
+loss sums are read back asynchronously every `print_freq` steps.
+"""
+from __future__ import annotations
+
+import math
+import sys
+import time
+from typing import Dict, Iterable, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .engine import StepEngine
+
+PRINT_FREQ = 20
+
+
+def _unwrap(model):
+    return model.module if hasattr(model, "module") and not hasattr(model, "runtime") else model
+
+
+def _lr_at(epoch: float, cfg: dict) -> float:
+    warm = cfg["warmup_epochs"]
+    if epoch < warm:
+        return cfg["lr"] * epoch / warm
+    return cfg["min_lr"] + (cfg["lr"] - cfg["min_lr"]) * 0.5 * (
+        1.0 + math.cos(math.pi * (epoch - warm) / (cfg["epochs"] - warm)))
+
+
+def get_engine(algorithm: str, model, teacher, Bl: int, Bu: int, L: int, dtype: int, config: dict,
+               optimizer=None, use_graph: bool = True, algo: Optional[int] = None) -> StepEngine:
+    """Engine cache keyed by shapes; engines share the model's arenas."""
+    rt = model.runtime()
+    rt.ensure()
+    rt_t = None
+    if algorithm == "mean_teacher":
+        rt_t = teacher.runtime(nbt_float=True)
+        rt_t.ensure()
+    key = (algorithm, Bl, Bu, L, dtype, use_graph, algo, id(rt_t))
+    eng = rt.engines.get(key)
+    if eng is None:
+        pg = dist.group.WORLD if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        cfg = dict(config)
+        if optimizer is not None:
+            g = optimizer.param_groups[0]
+            cfg["optimizer"] = "adamw"
+            cfg["weight_decay"] = g.get("weight_decay", cfg.get("weight_decay", 0.0))
+            cfg["optimizer_kwargs"] = {"betas": tuple(g.get("betas", (0.9, 0.999))), "eps": g.get("eps", 1e-8)}
+        eng = StepEngine(rt.weights, rt.state, dtype, algorithm, Bl, Bu, L, cfg,
+                         teacher=rt_t.weights if rt_t is not None else None, algo=algo, use_graph=use_graph,
+                         process_group=pg, sync_bn=bool(getattr(model, "sync_bn", False)),
+                         seed=int(getattr(model, "seed", 0)))
+        if rt_t is not None:
+            eng.ema_first = not rt_t.ema_started
+        rt.engines[key] = eng
+    return eng
+
+
+def bind_optimizer_state(optimizer, model) -> None:
+    """Make `optimizer.state` (any torch AdamW-like optimizer over model.parameters()) alias the flat
+    moment arenas, importing existing state first."""
+    rt = model.runtime()
+    rt.ensure()
+    st = rt.state
+    mv, vv = rt.weights.param_views(st.exp_avg), rt.weights.param_views(st.exp_avg_sq)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            s = optimizer.state.get(p, None)
+            if s and "exp_avg" in s and s["exp_avg"].data_ptr() != mv[n].data_ptr():
+                mv[n].copy_(s["exp_avg"])
+                vv[n].copy_(s["exp_avg_sq"])
+                st.step = max(st.step, int(s["step"]))
+            optimizer.state[p] = {"step": torch.tensor(float(st.step)), "exp_avg": mv[n], "exp_avg_sq": vv[n]}
+
+
+def run_epoch(algorithm: str, model, teacher, labeled_loader: Iterable, unlabeled_loader: Optional[Iterable],
+              optimizer, device, epoch: int, loss_scaler=None, log_writer=None, use_amp: bool = True,
+              config: Optional[dict] = None) -> Dict[str, float]:
+    model = _unwrap(model)
+    teacher = _unwrap(teacher) if teacher is not None else None
+    config = config or {}
+    if config.get("accum_iter", 1) != 1:
+        raise NotImplementedError("accum_iter > 1 is not supported by the fused step (all shipped configs use 1)")
+    if config.get("max_norm", None) is not None:
+        raise NotImplementedError("gradient clipping (max_norm) is not supported by the fused step "
+                                  "(max_norm is null in every shipped config)")
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("train_one_epoch: the B200 hot path needs device='cuda' (no CPU fallback)")
+    model.train()
+    if teacher is not None:
+        teacher.eval()
+    precision = getattr(model, "precision", None)
+    dtype = {"fp32": _lib.F32, "bf16": _lib.BF16}[precision] if precision else (_lib.BF16 if use_amp else _lib.F32)
+    num_steps = len(labeled_loader)
+    if unlabeled_loader is not None:
+        assert len(unlabeled_loader) == num_steps, "The number of labeled and unlabeled data should be the same"
+    if log_writer is not None:
+        print("log_dir: {}".format(log_writer.log_dir))
+    bind_optimizer_state(optimizer, model)
+
+    sums: Dict[str, float] = {}
+    count = 0
+    last_lr = 0.0
+    t0 = time.time()
+    eng = None
+    pairs = zip(labeled_loader, unlabeled_loader) if unlabeled_loader is not None else ((b, None) for b in labeled_loader)
+
+    def drain(step_idx):
+        nonlocal count
+        for s in eng.read_stats():
+            total = s.get("loss_total", s.get("loss"))
+            if not math.isfinite(total):
+                print(f"Loss is {total}, stopping training")
+                sys.exit(1)
+            for k, v in s.items():
+                sums[k] = sums.get(k, 0.0) + v
+            count += 1
+            if log_writer is not None:
+                x = int((epoch + (count - 1) / num_steps) * 1000)
+                for k, v in s.items():
+                    log_writer.add_scalar(k, v, x)
+        if log_writer is not None:
+            log_writer.add_scalar("lr", last_lr, int((epoch + step_idx / num_steps) * 1000))
+
+    for it, (lab, unl) in enumerate(pairs):
+        lr = _lr_at(it / num_steps + epoch, config)
+        for g in optimizer.param_groups:
+            g["lr"] = lr * g["lr_scale"] if "lr_scale" in g else lr
+        last_lr = lr
+        ecg_x, mask_x = lab["ecg"], lab["target"]
+        Bl, _, L = ecg_x.shape
+        Bu = unl["ecg"].shape[0] if unl is not None else 0
+        e = get_engine(algorithm, model, teacher, Bl, Bu, L, dtype, config, optimizer)
+        if e is not eng and eng is not None:
+            drain(it)
+        eng = e
+        if unl is not None:
+            eng.load_batch(ecg_x, mask_x, unl["ecg"], unl["ecg_aug"])
+        else:
+            eng.load_batch(ecg_x, mask_x)
+        eng.step(lr)
+        if teacher is not None:
+            teacher.runtime().ema_started = True
+        if (it + 1) % PRINT_FREQ == 0 or it + 1 == num_steps:
+            drain(it)
+            dt = time.time() - t0
+            print(f"Epoch: [{epoch}]  [{it + 1}/{num_steps}]  lr: {lr:.6f}  " +
+                  "  ".join(f"{k}: {v / max(count, 1):.4f}" for k, v in sums.items()) +
+                  f"  time: {dt / (it + 1):.4f}  max mem: {torch.cuda.max_memory_allocated() / 2 ** 20:.0f}")
+    if eng is not None:
+        drain(num_steps - 1)
+    for p in optimizer.state.values():
+        if isinstance(p, dict) and "step" in p:
+            p["step"] = torch.tensor(float(model.runtime().state.step))
+    stats = {k: v / max(count, 1) for k, v in sums.items()}
+    stats["lr"] = last_lr
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        keys = sorted(k for k in stats if k != "lr")
+        t = torch.tensor([stats[k] for k in keys], dtype=torch.float64, device=device)
+        dist.all_reduce(t)
+        t /= dist.get_world_size()
+        for k, v in zip(keys, t.tolist()):
+            stats[k] = v
+    print("Averaged stats:", "  ".join(f"{k}: {v:.6f}" for k, v in stats.items()))
+    return stats

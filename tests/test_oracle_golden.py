@@ -1,0 +1,127 @@
+"""Pins the CPU oracle (oracle/segnet_oracle.py) against outputs of the reference itself
+(tests/golden/reference_vectors.npz, produced by tests/golden/make_golden.py).  The reference
+has no tests / golden vectors of its own."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, TINY_ARCH, TRAIN_CFG, batches, group, rel_err, sd_from
+
+TOL = 2e-5  # fp32 reference vs fp64 oracle, relative L2 per tensor
+
+
+def test_forward_backward_per_layer(golden):
+    g = golden
+    sd = sd_from(g, "A/init")
+    tr = O.OracleTrainer(sd, TINY_ARCH, dict(TRAIN_CFG), dtype=torch.float64)
+    x = torch.from_numpy(g["A/x"])
+    y = torch.from_numpy(g["A/y"])
+    st = tr.supervised_step(x, y, lr=0.0, want_taps=True)
+    assert abs(st["loss"] - float(g["A/loss"])) < 1e-6
+    acts, dacts = group(g, "A/act"), group(g, "A/dact")
+    assert len(acts) == 22
+    for name, ref in acts.items():
+        assert rel_err(tr.taps[name], ref) < TOL, name
+        assert rel_err(tr.taps[name].grad, dacts[name]) < TOL * 5, name
+    for name, ref in group(g, "A/grad").items():
+        assert rel_err(tr.grads[name], ref) < TOL * 5, name
+    for name, ref in group(g, "A/after_train_fwd").items():
+        assert rel_err(tr.sd[name], ref) < TOL, name
+    # the reference's eval forward ran after the train forward: running stats updated once (lr=0: same weights)
+    ev = O.forward(tr.sd, x.double(), TINY_ARCH, False)
+    assert rel_err(ev["seg_logits"], g["A/seg_logits_eval"]) < TOL
+
+
+def _run_fixmatch(g, tag, dropout):
+    arch = dataclasses.replace(TINY_ARCH, dropout_ratio=dropout)
+    cfg = dict(TRAIN_CFG, conf_thresh=float(g[f"{tag}/conf_thresh"]))
+    tr = O.OracleTrainer(sd_from(g, f"{tag}/init"), arch, cfg, dtype=torch.float64)
+    n, epoch = int(g[f"{tag}/nsteps"]), int(g[f"{tag}/epoch"])
+    data = batches(int(g[f"{tag}/data_seed"]), n, 3, 3, 2, 300)
+    masks = g[f"{tag}/dropout_masks"] if dropout > 0 else None
+    stats = []
+    for it, (lab, unl) in enumerate(data):
+        lr = O.lr_at(it / n + epoch, cfg)
+        dm = torch.from_numpy(masks[it]) if masks is not None else None
+        stats.append(tr.fixmatch_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], lr, dropout_mask=dm))
+    return tr, stats
+
+
+@pytest.mark.parametrize("tag,dropout", [("B", 0.0), ("D", 0.1)])
+def test_fixmatch_steps(golden, tag, dropout):
+    g = golden
+    tr, stats = _run_fixmatch(g, tag, dropout)
+    ref = group(g, f"{tag}/stats")
+    for k in ("loss_total", "loss_x", "loss_u_s", "mask_ratio"):
+        mean = float(np.mean([s[k] for s in stats]))
+        assert abs(mean - float(ref[k])) < 2e-5 * max(1.0, abs(float(ref[k]))), (k, mean, float(ref[k]))
+    assert 0.05 < float(ref["mask_ratio"]) < 0.95  # the masked branch is really exercised
+    for name, refv in group(g, f"{tag}/final").items():
+        if "num_batches_tracked" in name:
+            assert int(tr.sd[name]) == int(refv)
+        else:
+            assert rel_err(tr.sd[name], refv) < 1e-4, name
+
+
+def test_mean_teacher_steps(golden):
+    g = golden
+    cfg = dict(TRAIN_CFG, ema_decay=0.99)
+    tr = O.OracleTrainer(sd_from(g, "C/init"), TINY_ARCH, cfg, dtype=torch.float64)
+    tr.init_teacher(sd_from(g, "C/teacher_init_buffers"))
+    n, epoch = int(g["C/nsteps"]), int(g["C/epoch"])
+    stats = []
+    for it, (lab, unl) in enumerate(batches(int(g["C/data_seed"]), n, 3, 3, 2, 300)):
+        stats.append(tr.mean_teacher_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], O.lr_at(it / n + epoch, cfg)))
+    ref = group(g, "C/stats")
+    for k in ("loss_total", "loss_x", "loss_u_s"):
+        assert abs(float(np.mean([s[k] for s in stats])) - float(ref[k])) < 2e-5
+    for name, refv in group(g, "C/final").items():
+        if "num_batches_tracked" not in name:
+            assert rel_err(tr.sd[name], refv) < 1e-4, name
+    teacher = tr.teacher_state()
+    for name, refv in group(g, "C/teacher_final").items():
+        if "num_batches_tracked" in name:
+            # reference quirk: the int64 counter becomes a float32 EMA (0.01 -> 0.0299 -> 0.0596)
+            assert refv.dtype == np.float32 and abs(float(teacher[name]) - float(refv)) < 1e-6, name
+        else:
+            assert rel_err(teacher[name], refv) < 1e-4, name
+
+
+def test_full_size_step_scalars(golden):
+    """resnet18 @ 1x2500, one FixMatch step: losses, mask ratio and all 65 gradient norms."""
+    import models.backbones  # product constructors give the seeded init (checked bit-exact in test_surface)
+    from algorithms.base import init_model_from_cfg
+    from helpers import model_cfg
+    g = golden
+    torch.manual_seed(0)
+    model = init_model_from_cfg(model_cfg(1, 64, 64, 128, 0.0))
+    arch = O.Arch(num_leads=1, dropout_ratio=0.0)
+    cfg = dict(TRAIN_CFG, conf_thresh=float(g["E/conf_thresh"]))
+    tr = O.OracleTrainer({k: v.detach() for k, v in model.state_dict().items()}, arch, cfg, dtype=torch.float32)
+    (lab, unl), = batches(int(g["E/data_seed"]), 1, 2, 2, 1, 2500)
+    s = tr.fixmatch_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], O.lr_at(3.0, cfg))
+    ref = group(g, "E/stats")
+    for k in ("loss_total", "loss_x", "loss_u_s"):
+        assert abs(s[k] - float(ref[k])) < 1e-4, (k, s[k], float(ref[k]))
+    assert abs(s["mask_ratio"] - float(ref["mask_ratio"])) < 2e-3
+    gn = np.array([float(tr.grads[n].double().norm()) for n in tr.pnames])
+    assert np.allclose(gn, g["E/grad_norms"], rtol=2e-3, atol=1e-7)
+
+
+def test_closed_form_loss_gradient():
+    """The closed-form d(loss)/d(logits) used to check the fused CUDA loss kernel equals autograd."""
+    torch.manual_seed(0)
+    z = torch.randn(5, 4, 37, dtype=torch.float64, requires_grad=True)
+    yx = torch.randint(0, 4, (2, 37))
+    lab = torch.randint(0, 4, (3, 37))
+    mask = torch.rand(3, 37) > 0.5
+    loss = (O.ce_hard(z[:2], yx) + O.ce_masked(z[2:], lab, mask)) / 2
+    loss.backward()
+    assert rel_err(O.loss_grad_fullres(z.detach(), 2, yx, lab, mask, None), z.grad) < 1e-12
+    z.grad = None
+    p = torch.softmax(torch.randn(3, 4, 37, dtype=torch.float64), 1)
+    loss = (O.ce_hard(z[:2], yx) + O.ce_soft(z[2:], p)) / 2
+    loss.backward()
+    assert rel_err(O.loss_grad_fullres(z.detach(), 2, yx, None, None, p), z.grad) < 1e-12
