@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the SemiSegECG training hot path on B200 (contract: see the task statement).
+
+metric  : train samples/sec of the FixMatch step (labeled + unlabeled strips per second, whole job)
+workload: BASELINE.json configs[1] -- FixMatch, resnet18 + FCNHead, LUDB 1/16 shape
+          (configs/base/resnet18/fixmatch.yaml + configs/bench/ludb/1over16.yaml): 1 lead x 2500
+          samples, B_l = B_u = 16 per GPU, conf_thresh 0.8, AdamW; synthetic LUDB-shaped data,
+          random-init weights.
+value   : throughput with inputs resident in HBM; e2e: through algorithms-level engine API with
+          pinned-host batches copied H2D and the loss read back D2H inside the timed region.
+--impl reference: the CPU implementation of the same step (oracle port of the reference's
+          fixmatch.train_one_epoch body; the reference is Python and is not present on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(REPO, "semi-seg-ecg_b200", "src")
+for p in (REPO, SRC):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (algorithm, num_leads, L, Bl, Bu, base_channels, stem_channels, head_in)
+    "fixmatch_resnet18_ludb_1x2500_b16+16": ("fixmatch", 1, 2500, 16, 16, 64, 64),
+    "mean_teacher_resnet18_qtdb_2x2500_b16+16": ("mean_teacher", 2, 2500, 16, 16, 64, 64),
+    "fixmatch_resnet18w128_12x5000_b32+32": ("fixmatch", 12, 5000, 32, 32, 128, 128),
+}
+DEFAULT_WORKLOAD = "fixmatch_resnet18_ludb_1x2500_b16+16"
+
+
+def make_host_batch(seed, rank, Bl, Bu, C, L):
+    from semiseg_b200 import synthetic
+    return synthetic.make_batch(seed * 1000 + rank, Bl, Bu, C, L)
+
+
+def load_cfg(workload):
+    from utils.config import load_config
+    algo, C, L, Bl, Bu, base, stem = WORKLOADS[workload]
+    cfgdir = os.path.join(REPO, "semi-seg-ecg_b200", "configs")
+    cfg = load_config(os.path.join(cfgdir, "base", "resnet18", f"{algo}.yaml"),
+                      os.path.join(cfgdir, "bench", "ludb", "1over16.yaml"))
+    bb = cfg["backbone"]["resnet18"]
+    bb["num_leads"] = C
+    if base != 64 or stem != 64:
+        bb["base_channels"], bb["stem_channels"] = base, stem
+        cfg["decode_head"]["FCNHead"]["in_channels"] = base * 8
+    cfg["dataset"]["signal_length"] = L
+    cfg["dataloader"]["batch_size"] = Bl
+    return cfg, algo, C, L, Bl, Bu
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples, self.reasons, self.stop_flag = [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ---- algorithmic cost model (per launch) ------------------------------------------------------
+def launch_cost(name, args, es):
+    """(flops, bytes) of one C-ABI launch from its arguments; es = activation element size."""
+    from semiseg_b200._lib import Geom
+    geoms = [a for a in args if isinstance(a, Geom)]
+    if name in ("ssb_conv1d_fwd", "ssb_conv1d_dgrad", "ssb_conv1d_wgrad"):
+        gi, go = geoms
+        k = args[6] if name != "ssb_conv1d_wgrad" else args[5]
+        flops = 2.0 * go.B * go.len * go.C * gi.C * k
+        w = gi.C * go.C * k
+        if name == "ssb_conv1d_wgrad":
+            byt = (gi.B * gi.len * gi.C + go.B * go.len * go.C) * es + w * 4
+        else:
+            byt = (gi.B * gi.len * gi.C + go.B * go.len * go.C) * es + w * es
+        return flops, byt, f"{name[4:]}[{gi.C}->{go.C},k{k},L{gi.len}->{go.len}]"
+    if geoms:
+        g = geoms[-1]
+        n = g.B * g.len * g.C
+        mult = {"ssb_bn_stats": 1, "ssb_bn_act_fwd": 2.5, "ssb_bn_bwd_reduce": 3, "ssb_bn_bwd_apply": 4,
+                "ssb_stem_bn_relu_pool_fwd": 3, "ssb_stem_bwd_reduce": 3, "ssb_stem_bwd_apply": 3.5}.get(name, 2)
+        return 0.0, n * es * mult, f"{name[4:]}[C{g.C},L{g.len}]"
+    if name == "ssb_adamw_ema":
+        n = args[5]
+        return 0.0, n * (36.0 if args[4] else 28.0), "adamw_ema"
+    return 0.0, 0.0, name[4:]
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from algorithms.base import init_model_from_cfg
+    from algorithms.mean_teacher import init_teacher
+    from semiseg_b200 import _lib
+    from semiseg_b200.trainer import get_engine
+    from utils.lr_sched import lr_at
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1 and args.gpus == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    cfg, algo, C, L, Bl, Bu = load_cfg(args.workload)
+    tcfg = cfg["train"]
+    dtype = _lib.BF16 if args.dtype == "bf16" else _lib.F32
+    torch.manual_seed(cfg["seed"])           # identical initial weights on every rank
+    model = init_model_from_cfg(cfg).to(dev)
+    model.sync_bn = bool(args.sync_bn) and world > 1
+    model.seed = cfg["seed"] + rank
+    teacher = init_teacher(cfg, model, dev) if algo == "mean_teacher" else None
+    eng = get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=not args.no_graph)
+
+    # synthetic batches: a pool of distinct host (pinned) and device copies, shard = seed + rank
+    pool = 4
+    host, devb = [], []
+    for i in range(pool):
+        lab, unl = make_host_batch(cfg["seed"] + 17 * i, rank, Bl, Bu, C, L)
+        h = [torch.from_numpy(lab["ecg"]).pin_memory(), torch.from_numpy(lab["target"]).pin_memory(),
+             torch.from_numpy(unl["ecg"]).pin_memory(), torch.from_numpy(unl["ecg_aug"]).pin_memory()]
+        host.append(h)
+        devb.append([t.to(dev) for t in h])
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    epoch_f = [20.0]  # a post-warm-up point of the LR schedule (lr ~ 9.8e-4)
+
+    def step_from(batch):
+        eng.load_batch(*batch)
+        eng.step(lr_at(epoch_f[0], tcfg))
+        epoch_f[0] += 1e-3
+
+    def timed(batches, steps, read_each_step):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        ev0.record()
+        for i in range(steps):
+            step_from(batches[i % pool])
+            if read_each_step:
+                pass  # eng.step() already enqueues the asynchronous D2H copy of the loss sums
+        ev1.record()
+        sync_all()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        stats = eng.read_stats()
+        return ms, stats
+
+    for i in range(max(args.warmup, 3)):
+        step_from(devb[i % pool])
+    eng.read_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_dev, stats_dev = timed(devb, args.steps, False)
+    ms_e2e, stats_e2e = timed(host, args.steps, True)
+    sampler.stop_flag = True
+    per_step = Bl + Bu
+    value = per_step * world * args.steps / (ms_dev / 1e3)
+    e2e = per_step * world * args.steps / (ms_e2e / 1e3)
+    assert all(np.isfinite(s["loss_total"]) for s in stats_dev + stats_e2e), "non-finite loss in the timed region"
+
+    # ---- per-kernel timing pass (eager, CUDA events around every launch on the launch stream) ----
+    roof, top = None, []
+    if rank == 0 or world > 1:
+        es = 2 if dtype == _lib.BF16 else 4
+        rec = []
+
+        def hook(name, a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.raw_call(name, *a)
+            e1.record()
+            rec.append((name, a, e0, e1))
+        eng_e = get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=False)
+        for i in range(2):
+            eng_e.load_batch(*devb[i % pool]); eng_e.step(lr_at(epoch_f[0], tcfg))
+        torch.cuda.synchronize()
+        _lib._hook = hook
+        nprof = min(args.steps, 10)
+        for i in range(nprof):
+            eng_e.load_batch(*devb[i % pool]); eng_e.step(lr_at(epoch_f[0], tcfg))
+        _lib._hook = None
+        torch.cuda.synchronize()
+        eng_e.read_stats()
+        agg = {}
+        for name, a, e0, e1 in rec:
+            fl, by, label = launch_cost(name, a, es)
+            d = agg.setdefault(label, [0.0, 0, fl, by])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += 1
+        tot = sum(v[0] for v in agg.values())
+        ranked = sorted(agg.items(), key=lambda kv: -kv[1][0])
+        peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback"}
+        pf = os.path.join(REPO, "MEASURED_PEAKS.json")
+        if os.path.exists(pf):
+            mp = json.load(open(pf))
+            peaks = {"hbm_gbs": mp["hbm_gbs"], "bf16_tflops": mp.get("bf16_tflops_sustained", mp["bf16_tflops"]), "src": "measured"}
+        ridge = peaks["bf16_tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        for label, (ms, n, fl, by) in ranked[:8]:
+            us = ms / n * 1e3
+            top.append({"kernel": label, "share": round(ms / tot, 4), "us_per_launch": round(us, 2), "launches_per_step": n / nprof,
+                        "tflops": round(fl / (us * 1e-6) / 1e12, 2) if fl else None, "gbs": round(by / (us * 1e-6) / 1e9, 1) if by else None})
+        label, (ms, n, fl, by) = ranked[0]
+        us = ms / n * 1e3
+        if fl and by and fl / by > ridge:
+            ach = fl / (us * 1e-6) / 1e12
+            roof = {"bound": "tensor", "achieved": round(ach, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": round(ach / peaks["bf16_tflops"], 4), "traffic": None}
+        else:
+            ach = by / (us * 1e-6) / 1e9
+            roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None}
+        roof.update({"kernel": label, "us_per_launch": round(us, 2), "share_of_step": round(ms / tot, 4),
+                     "peak_source": peaks["src"], "timing": "CUDA events around each launch, eager replay of the same step"})
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    # working set, to justify the L2 policy
+    plan = eng.plan_s
+    ws = sum(t.numel() * t.element_size() for bufs in plan.blk_bufs for t in bufs.values())
+    ws += sum(t.numel() * t.element_size() for t in (plan.c0, plan.p0, plan.ch, plan.ah, plan.dc0))
+    ws += 4 * model.runtime().weights.params.numel() * 4
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.workload, budget_s=15.0)
+    line = {
+        "metric": "train samples/sec FixMatch 1D U-Net (resnet18+FCNHead segmentor) step",
+        "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.dtype, "data": "synthetic LUDB-shaped strips (z-scored Gaussian, 4-class piecewise labels), random-init weights",
+        "config": {"workload": args.workload, "algorithm": algo, "per_gpu_batch": f"{Bl}+{Bu}", "leads": C, "length": L,
+                   "parallelism": f"dp{world}", "sync_bn": bool(model.sync_bn), "cuda_graph": not args.no_graph,
+                   "l2_policy": f"no explicit flush: per-step working set {ws / 2**20:.0f} MiB (activations + param/grad/Adam arenas) "
+                                "vs 126 MB L2; inputs rotate over 4 distinct batches"},
+        "e2e": {"value": round(e2e, 1), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes(), "d2h_bytes_per_step": 32,
+                "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": eng.launches_per_step * args.steps,
+        "launches_per_step": eng.launches_per_step,
+        "clocks": sampler.summary(),
+        "roofline": roof, "top_kernels": top,
+        "loss_last": stats_dev[-1] if stats_dev else None,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_step_fn(workload):
+    """One FixMatch/Mean-Teacher step of the oracle port on the host CPU (fp32, all threads)."""
+    from algorithms.base import init_model_from_cfg
+    from oracle import segnet_oracle as O
+    cfg, algo, C, L, Bl, Bu = load_cfg(workload)
+    torch.manual_seed(cfg["seed"])
+    model = init_model_from_cfg(cfg)
+    arch = O.Arch.from_config(cfg)
+    tr = O.OracleTrainer({k: v.detach() for k, v in model.state_dict().items()}, arch, cfg["train"], dtype=torch.float32)
+    lab, unl = make_host_batch(cfg["seed"], 0, Bl, Bu, C, L)
+    lab = {k: torch.from_numpy(v) for k, v in lab.items()}
+    unl = {k: torch.from_numpy(v) for k, v in unl.items()}
+    g = torch.Generator().manual_seed(0)
+    Lh = O.stage_lengths(arch, L)[-1]
+
+    def step():
+        dm = (torch.rand(Bl + Bu, arch.head_channels, Lh, generator=g) >= arch.dropout_ratio)
+        if algo == "mean_teacher":
+            return tr.mean_teacher_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], 1e-3, dropout_mask=dm)
+        return tr.fixmatch_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], 1e-3, dropout_mask=dm)
+    return step, Bl + Bu
+
+
+def cpu_baseline(workload, budget_s=15.0):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, per = cpu_step_fn(workload)
+    step()
+    t0 = time.time()
+    n = 0
+    while time.time() - t0 < budget_s and n < 100:
+        step()
+        n += 1
+    dt = time.time() - t0
+    return {"value": round(per * n / dt, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} steps of the same workload (oracle port of fixmatch.train_one_epoch body, torch CPU fp32, "
+                      f"{dt:.1f} s after 1 warm-up step)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, per = cpu_step_fn(args.workload)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.time()
+    for _ in range(args.steps):
+        step()
+    dt = time.time() - t0
+    v = round(per * args.steps / dt, 2)
+    cfg, algo, C, L, Bl, Bu = load_cfg(args.workload)
+    print(json.dumps({
+        "impl": "reference", "metric": "train samples/sec FixMatch 1D U-Net (resnet18+FCNHead segmentor) step",
+        "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
+        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic LUDB-shaped strips, random-init weights",
+        "config": {"workload": args.workload, "algorithm": algo, "per_gpu_batch": f"{Bl}+{Bu}", "leads": C, "length": L},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{args.steps} steps of the workload on the host CPU (oracle port of the reference step; the "
+                                   "reference is Python and is not shipped to the GPU box)"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--sync-bn", type=int, default=0, help="1: SyncBatchNorm statistic exchange (reference default); "
+                    "0: per-rank BN (ddp.sync_bn: false)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        a.steps = a.steps or 10
+        a.warmup = a.warmup if a.warmup is not None else 1
+        run_reference(a)
+    else:
+        a.steps = a.steps or 200
+        a.warmup = a.warmup if a.warmup is not None else 20
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,6 +118,16 @@ def check(status: int, what: str = "") -> None:
         raise RuntimeError(f"libsemiseg_b200 {what} failed ({status}): {msg.decode() if msg else '?'}")
 
 
+_hook = None  # bench.py installs a per-launch timing hook here
+
+
 def call(name: str, *args) -> None:
     """Invoke an int-returning entry point and raise on error."""
+    if _hook is not None:
+        _hook(name, args)
+        return
+    check(getattr(load(), name)(*args), name)
+
+
+def raw_call(name: str, *args) -> None:
     check(getattr(load(), name)(*args), name)

@@ -13,6 +13,7 @@ Reference behaviour restated here (file:line relative to the reference tree):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -303,6 +304,8 @@ class NetPlan:
         self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
         if algo is None:
             algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
+            if os.environ.get("SSB_FORCE_SIMT"):   # debugging aid: generic CUDA-core conv kernels everywhere
+                algo = _lib.ALGO_SIMT
         self.algo = algo
         spec = self.spec
         if train and grads is None:

@@ -1,0 +1,480 @@
+"""Op-level parity of the CUDA kernels (through the C ABI) against the oracle / plain torch fp64.
+
+FP32 kernels: relative L2 error <= 1e-5 (north_star FP32 tolerance); BF16 kernels: <= 2e-2.
+Pseudo-label outputs: bit-exact against torch's own CUDA softmax/argmax on identical logits.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import O, rel_err
+
+pytestmark = pytest.mark.gpu
+
+from semiseg_b200 import _lib  # noqa: E402
+from semiseg_b200._lib import BN, Geom, StepParams, call  # noqa: E402
+
+DEV = "cuda"
+TOL = {_lib.F32: 1e-5, _lib.BF16: 2e-2}
+TDT = {_lib.F32: torch.float32, _lib.BF16: torch.bfloat16}
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def to_flat(x_ncl, pitch, dtype):
+    B, Cc, L = x_ncl.shape
+    buf = torch.zeros(B * pitch, Cc, dtype=TDT[dtype], device=DEV)
+    buf.view(B, pitch, Cc)[:, 1:1 + L, :] = x_ncl.permute(0, 2, 1).to(TDT[dtype])
+    return buf
+
+
+def from_flat(buf, B, pitch, L):
+    return buf.view(B, pitch, -1)[:, 1:1 + L, :].permute(0, 2, 1).double()
+
+
+def halo_is_zero(buf, B, pitch, L):
+    v = buf.view(B, pitch, -1).float()
+    return float(v[:, 0].abs().max()) == 0.0 and float(v[:, 1 + L:].abs().max()) == 0.0
+
+
+def rq(x, dtype):
+    """round-trip through the storage dtype (so the reference sees the same inputs)"""
+    return x.to(TDT[dtype]).double()
+
+
+def repack(w, dtype):
+    Cout, Cin, k = w.shape
+    kio = w.permute(2, 1, 0).contiguous().to(TDT[dtype])
+    koi = w.permute(2, 0, 1).contiguous().to(TDT[dtype])
+    return kio, koi
+
+
+CONV_CASES = [(8, 16, 3, 1, 37), (16, 16, 3, 2, 37), (8, 16, 1, 2, 38), (16, 8, 1, 1, 20), (64, 64, 3, 1, 157),
+              (64, 128, 3, 2, 313), (64, 128, 1, 2, 313), (128, 128, 3, 1, 79), (256, 512, 3, 2, 157), (512, 128, 3, 1, 79)]
+
+
+def _algos(cin, cout):
+    out = [(_lib.F32, _lib.ALGO_SIMT), (_lib.BF16, _lib.ALGO_SIMT)]
+    if cin % 64 == 0 and cout % 64 == 0:
+        out.append((_lib.BF16, _lib.ALGO_TCGEN05))
+    return out
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,L", CONV_CASES)
+def test_conv_fwd_dgrad_wgrad(cin, cout, k, stride, L):
+    torch.manual_seed(cin * 7 + cout + k + stride)
+    B = 3
+    Lo = (L - 1) // stride + 1
+    po = Lo + 2 + 3
+    pi = stride * po
+    x = torch.randn(B, cin, L, device=DEV, dtype=torch.float64)
+    w = torch.randn(cout, cin, k, device=DEV, dtype=torch.float64) / (cin * k) ** 0.5
+    dy = torch.randn(B, cout, Lo, device=DEV, dtype=torch.float64)
+    gi, go = Geom(B, pi, L, cin), Geom(B, po, Lo, cout)
+    for dtype, algo in _algos(cin, cout):
+        xq, wq, dyq = rq(x, dtype), rq(w, dtype), rq(dy, dtype)
+        xr = xq.clone().requires_grad_(True)
+        wr = wq.clone().requires_grad_(True)
+        yr = F.conv1d(xr, wr, None, stride=stride, padding=k // 2)
+        assert yr.shape[2] == Lo
+        yr.backward(dyq)
+        kio, koi = repack(w.float(), dtype)
+        xb = to_flat(x, pi, dtype)
+        yb = torch.full((B * po, cout), 7.0, dtype=TDT[dtype], device=DEV)
+        call("ssb_conv1d_fwd", xb.data_ptr(), kio.data_ptr(), koi.data_ptr(), yb.data_ptr(), gi, go, k, stride, dtype, algo, st())
+        tag = f"dtype={dtype} algo={algo}"
+        assert rel_err(from_flat(yb, B, po, Lo), yr.detach()) < TOL[dtype], "fwd " + tag
+        assert halo_is_zero(yb, B, po, Lo), "fwd halo " + tag
+        # dgrad (plain, then accumulate)
+        dyb = to_flat(dy, po, dtype)
+        dxb = torch.full((B * pi, cin), 3.0, dtype=TDT[dtype], device=DEV)
+        call("ssb_conv1d_dgrad", dyb.data_ptr(), kio.data_ptr(), koi.data_ptr(), dxb.data_ptr(), gi, go, k, stride, 0, dtype, algo, st())
+        assert rel_err(from_flat(dxb, B, pi, L), xr.grad) < TOL[dtype], "dgrad " + tag
+        assert halo_is_zero(dxb, B, pi, L), "dgrad halo " + tag
+        base = torch.randn(B, cin, L, device=DEV, dtype=torch.float64)
+        dxb2 = to_flat(base, pi, dtype)
+        call("ssb_conv1d_dgrad", dyb.data_ptr(), kio.data_ptr(), koi.data_ptr(), dxb2.data_ptr(), gi, go, k, stride, 1, dtype, algo, st())
+        assert rel_err(from_flat(dxb2, B, pi, L), xr.grad + rq(base, dtype)) < TOL[dtype] * 2, "dgrad acc " + tag
+        assert halo_is_zero(dxb2, B, pi, L)
+        # wgrad (accumulates into fp32 [Cout][Cin][k])
+        dw = torch.zeros(cout, cin, k, dtype=torch.float32, device=DEV)
+        call("ssb_conv1d_wgrad", xb.data_ptr(), dyb.data_ptr(), dw.data_ptr(), gi, go, k, stride, dtype, algo, st())
+        assert rel_err(dw, wr.grad) < TOL[dtype], "wgrad " + tag
+
+
+def test_weight_repack():
+    from semiseg_b200._lib import RepackDesc
+    torch.manual_seed(0)
+    ws = [torch.randn(16, 8, 3, device=DEV), torch.randn(64, 64, 1, device=DEV)]
+    for dtype in (_lib.F32, _lib.BF16):
+        tab = (RepackDesc * len(ws))()
+        outs = []
+        for i, w in enumerate(ws):
+            kio = torch.zeros(w.numel(), dtype=TDT[dtype], device=DEV)
+            koi = torch.zeros(w.numel(), dtype=TDT[dtype], device=DEV)
+            outs.append((kio, koi))
+            tab[i].w, tab[i].w_kio, tab[i].w_koi = w.data_ptr(), kio.data_ptr(), koi.data_ptr()
+            tab[i].Cout, tab[i].Cin, tab[i].k = w.shape
+        tdev = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(DEV)
+        call("ssb_weight_repack", tdev.data_ptr(), len(ws), max(w.numel() for w in ws), dtype, st())
+        for w, (kio, koi) in zip(ws, outs):
+            rk, ro = repack(w, dtype)
+            assert torch.equal(kio.view_as(rk), rk) and torch.equal(koi.view_as(ro), ro)
+
+
+def make_bn(Cn, train_count_mul=0):
+    t = {"gamma": torch.rand(Cn, device=DEV) + 0.5, "beta": torch.randn(Cn, device=DEV) * 0.1,
+         "rm": torch.randn(Cn, device=DEV) * 0.1, "rv": torch.rand(Cn, device=DEV) + 0.5,
+         "nbt": torch.zeros(1, dtype=torch.int64, device=DEV), "sums": torch.zeros(2 * Cn, dtype=torch.float64, device=DEV),
+         "mi": torch.zeros(2 * Cn, device=DEV), "bsums": torch.zeros(2 * Cn, dtype=torch.float64, device=DEV),
+         "dgamma": torch.zeros(Cn, device=DEV), "dbeta": torch.zeros(Cn, device=DEV)}
+    s = BN()
+    s.gamma, s.beta, s.running_mean, s.running_var = t["gamma"].data_ptr(), t["beta"].data_ptr(), t["rm"].data_ptr(), t["rv"].data_ptr()
+    s.num_batches_tracked, s.sums, s.mean_invstd, s.bwd_sums = t["nbt"].data_ptr(), t["sums"].data_ptr(), t["mi"].data_ptr(), t["bsums"].data_ptr()
+    s.dgamma, s.dbeta, s.count_mul = t["dgamma"].data_ptr(), t["dbeta"].data_ptr(), train_count_mul
+    return s, t
+
+
+def ref_bn(x, t, train):
+    sd = {"p.weight": t["gamma"].double(), "p.bias": t["beta"].double(), "p.running_mean": t["rm"].double(),
+          "p.running_var": t["rv"].double(), "p.num_batches_tracked": t["nbt"][0].clone()}
+    nb = {}
+    y = O.batchnorm(x, sd, "p", train, nb)
+    return y, nb
+
+
+@pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
+@pytest.mark.parametrize("Cn,res_mode", [(8, 0), (64, 1), (128, 2), (24, 0)])
+def test_bn_forward_backward(dtype, Cn, res_mode):
+    torch.manual_seed(Cn + res_mode)
+    B, L, pitch = 4, 53, 60
+    g = Geom(B, pitch, L, Cn)
+    x = torch.randn(B, Cn, L, device=DEV, dtype=torch.float64) * 1.5 + 0.3
+    r = torch.randn(B, Cn, L, device=DEV, dtype=torch.float64)
+    gout = torch.randn(B, Cn, L, device=DEV, dtype=torch.float64)
+    xq, rq_, gq = rq(x, dtype), rq(r, dtype), rq(gout, dtype)
+    bn, t = make_bn(Cn)
+    bnr, tr_ = make_bn(Cn)
+    # ---- reference (train mode) ----
+    xr = xq.clone().requires_grad_(True)
+    rr = rq_.clone().requires_grad_(True)
+    rm0, rv0 = t["rm"].clone(), t["rv"].clone()
+    y_ref, nb = ref_bn(xr, t, True)
+    if res_mode == 1:
+        y_ref = y_ref + rr
+    elif res_mode == 2:
+        yr2, nbr = ref_bn(rr, tr_, True)
+        y_ref = y_ref + yr2
+    y_ref = torch.relu(y_ref)
+    y_ref.backward(gq)
+    # ---- CUDA ----
+    xb, rb = to_flat(x, pitch, dtype), to_flat(r, pitch, dtype)
+    yb = torch.full((B * pitch, Cn), 5.0, dtype=TDT[dtype], device=DEV)
+    call("ssb_bn_stats", xb.data_ptr(), g, t["sums"].data_ptr(), dtype, st())
+    if res_mode == 2:
+        call("ssb_bn_stats", rb.data_ptr(), g, tr_["sums"].data_ptr(), dtype, st())
+    call("ssb_bn_act_fwd", xb.data_ptr(), C.byref(bn), rb.data_ptr() if res_mode else None,
+         C.byref(bnr) if res_mode == 2 else None, yb.data_ptr(), g, 1, 1, dtype, st())
+    tol = TOL[dtype]
+    assert rel_err(from_flat(yb, B, pitch, L), y_ref.detach()) < tol
+    assert halo_is_zero(yb, B, pitch, L)
+    assert rel_err(t["rm"], nb["p.running_mean"]) < 1e-5 and rel_err(t["rv"], nb["p.running_var"]) < 1e-5
+    assert int(t["nbt"][0]) == 1
+    # backward: reduce + apply
+    gb = to_flat(gout, pitch, dtype)
+    dxb = torch.full((B * pitch, Cn), 5.0, dtype=TDT[dtype], device=DEV)
+    dxr = torch.full((B * pitch, Cn), 5.0, dtype=TDT[dtype], device=DEV)
+    gid = torch.full((B * pitch, Cn), 5.0, dtype=TDT[dtype], device=DEV)
+    call("ssb_bn_bwd_reduce", gb.data_ptr(), None, yb.data_ptr(), xb.data_ptr(), C.byref(bn),
+         rb.data_ptr() if res_mode == 2 else None, C.byref(bnr) if res_mode == 2 else None, g, dtype, st())
+    call("ssb_bn_bwd_apply", gb.data_ptr(), None, yb.data_ptr(), xb.data_ptr(), C.byref(bn), dxb.data_ptr(),
+         rb.data_ptr() if res_mode == 2 else None, C.byref(bnr) if res_mode == 2 else None,
+         dxr.data_ptr() if res_mode == 2 else None, gid.data_ptr() if res_mode == 1 else None, g, dtype, st())
+    # the CUDA relu mask comes from the stored (rounded) output; compare against the same rule
+    btol = tol * 3
+    assert rel_err(from_flat(dxb, B, pitch, L), xr.grad) < btol
+    assert halo_is_zero(dxb, B, pitch, L)
+    if res_mode == 1:
+        assert rel_err(from_flat(gid, B, pitch, L), rr.grad) < btol
+    if res_mode == 2:
+        assert rel_err(from_flat(dxr, B, pitch, L), rr.grad) < btol
+    # dgamma / dbeta
+    xhat = (xq - xq.mean(dim=(0, 2), keepdim=True)) / torch.sqrt(xq.var(dim=(0, 2), unbiased=False, keepdim=True) + 1e-5)
+    gm = gq * (y_ref.detach() > 0)
+    assert rel_err(t["dgamma"], (gm * xhat).sum(dim=(0, 2))) < btol
+    assert rel_err(t["dbeta"], gm.sum(dim=(0, 2))) < btol
+    # ---- eval mode uses running statistics ----
+    t["rm"].copy_(rm0)
+    t["rv"].copy_(rv0)
+    y_eval, _ = ref_bn(xq, t, False)
+    call("ssb_bn_act_fwd", xb.data_ptr(), C.byref(bn), None, None, yb.data_ptr(), g, 0, 0, dtype, st())
+    assert rel_err(from_flat(yb, B, pitch, L), y_eval) < tol
+
+
+@pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
+@pytest.mark.parametrize("Cl,Cs,L", [(1, 64, 250), (2, 8, 301), (12, 128, 200)])
+def test_stem(dtype, Cl, Cs, L):
+    torch.manual_seed(Cl + Cs)
+    B = 3
+    L0 = (L - 1) // 2 + 1
+    Lp = (L0 - 1) // 2 + 1
+    pp = Lp + 2 + 1
+    p0 = 2 * pp
+    g0, gp = Geom(B, p0, L0, Cs), Geom(B, pp, Lp, Cs)
+    x = torch.randn(B, Cl, L, device=DEV)
+    w = torch.randn(Cs, Cl, 7, device=DEV) / (7 * Cl) ** 0.5
+    gpool = torch.randn(B, Cs, Lp, device=DEV, dtype=torch.float64)
+    bn, t = make_bn(Cs)
+    # reference
+    wr = w.double().clone().requires_grad_(True)
+    c0r = F.conv1d(x.double(), wr, None, stride=2, padding=3)
+    c0q = c0r if dtype == _lib.F32 else (c0r + (rq(c0r.detach(), dtype) - c0r.detach()))  # see stored rounding
+    a0, nb = ref_bn(c0q, t, True)
+    pr = O.maxpool_k3s2p1(torch.relu(a0))
+    pr.backward(rq(gpool, dtype))
+    # CUDA
+    c0 = torch.full((B * p0, Cs), 9.0, dtype=TDT[dtype], device=DEV)
+    call("ssb_stem_conv_fwd", x.data_ptr(), w.data_ptr(), c0.data_ptr(), Cl, L, g0, dtype, st())
+    assert rel_err(from_flat(c0, B, p0, L0), c0r.detach()) < TOL[dtype]
+    assert halo_is_zero(c0, B, p0, L0)
+    call("ssb_bn_stats", c0.data_ptr(), g0, t["sums"].data_ptr(), dtype, st())
+    pb = torch.full((B * pp, Cs), 9.0, dtype=TDT[dtype], device=DEV)
+    call("ssb_stem_bn_relu_pool_fwd", c0.data_ptr(), C.byref(bn), pb.data_ptr(), g0, gp, 1, dtype, st())
+    assert rel_err(from_flat(pb, B, pp, Lp), pr.detach()) < TOL[dtype]
+    assert halo_is_zero(pb, B, pp, Lp)
+    gpb = to_flat(gpool, pp, dtype)
+    dc0 = torch.full((B * p0, Cs), 9.0, dtype=TDT[dtype], device=DEV)
+    call("ssb_stem_bwd_reduce", gpb.data_ptr(), c0.data_ptr(), C.byref(bn), g0, gp, dtype, st())
+    call("ssb_stem_bwd_apply", gpb.data_ptr(), c0.data_ptr(), C.byref(bn), dc0.data_ptr(), g0, gp, dtype, st())
+    assert halo_is_zero(dc0, B, p0, L0)
+    dw = torch.zeros(Cs, Cl, 7, device=DEV)
+    call("ssb_stem_conv_wgrad", x.data_ptr(), dc0.data_ptr(), dw.data_ptr(), Cl, L, g0, dtype, st())
+    assert rel_err(dw, wr.grad) < TOL[dtype] * 3
+
+
+@pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_head_cls(dtype, p):
+    torch.manual_seed(5)
+    B, L, Cn, ncls, pitch = 3, 19, 128, 4, 23
+    g = Geom(B, pitch, L, Cn)
+    a = torch.relu(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64))
+    w = torch.randn(ncls, Cn, device=DEV) * 0.1
+    bias = torch.randn(ncls, device=DEV) * 0.1
+    mask = (torch.rand(B, L, Cn, device=DEV) >= p).to(torch.uint8)
+    dlow = torch.randn(B, L, ncls, device=DEV)
+    ar = rq(a, dtype).clone().requires_grad_(True)
+    wr = w.double().clone().requires_grad_(True)
+    br = bias.double().clone().requires_grad_(True)
+    h = ar * mask.permute(0, 2, 1).double() / (1.0 - p) if p > 0 else ar
+    low_r = F.conv1d(h, wr[:, :, None], br)
+    low_r.backward(dlow.permute(0, 2, 1).double())
+    ab = to_flat(a, pitch, dtype)
+    low = torch.zeros(B, L, ncls, device=DEV)
+    mp = mask.data_ptr() if p > 0 else None
+    call("ssb_head_cls_fwd", ab.data_ptr(), w.data_ptr(), bias.data_ptr(), low.data_ptr(), g, ncls, p, mp, None, dtype, st())
+    assert rel_err(low.permute(0, 2, 1), low_r.detach()) < 1e-5
+    da = torch.full((B * pitch, Cn), 2.0, dtype=TDT[dtype], device=DEV)
+    dw = torch.zeros(ncls, Cn, device=DEV)
+    db = torch.zeros(ncls, device=DEV)
+    call("ssb_head_cls_bwd", dlow.data_ptr(), ab.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(), db.data_ptr(), g,
+         ncls, p, mp, None, dtype, st())
+    assert rel_err(from_flat(da, B, pitch, L), ar.grad) < TOL[dtype]
+    assert halo_is_zero(da, B, pitch, L)
+    assert rel_err(dw, wr.grad) < 1e-5 and rel_err(db, br.grad) < 1e-5
+
+
+def test_dropout_rng_statistics():
+    """Counter-based dropout: keep-rate ~ 1-p, fwd and bwd use the same mask, masks differ per step."""
+    B, L, Cn, ncls, pitch, p = 8, 79, 128, 4, 81, 0.1
+    g = Geom(B, pitch, L, Cn)
+    ab = to_flat(torch.ones(B, Cn, L, device=DEV, dtype=torch.float64), pitch, _lib.F32)
+    w = torch.ones(ncls, Cn, device=DEV)
+    bias = torch.zeros(ncls, device=DEV)
+    lows = []
+    for step in (0, 1):
+        sp = StepParams()
+        sp.rng_seed, sp.rng_step = 123, step
+        spd = torch.frombuffer(bytearray(bytes(sp)), dtype=torch.uint8).to(DEV)
+        low = torch.zeros(B, L, ncls, device=DEV)
+        call("ssb_head_cls_fwd", ab.data_ptr(), w.data_ptr(), bias.data_ptr(), low.data_ptr(), g, ncls, p, None, spd.data_ptr(), _lib.F32, st())
+        kept = low[..., 0] * (1 - p)     # number of kept channels per row
+        assert abs(float(kept.mean()) / Cn - (1 - p)) < 0.01
+        da = torch.zeros(B * pitch, Cn, device=DEV)
+        dw = torch.zeros(ncls, Cn, device=DEV)
+        db = torch.zeros(ncls, device=DEV)
+        dl = torch.zeros(B, L, ncls, device=DEV)
+        dl[..., 0] = 1.0
+        call("ssb_head_cls_bwd", dl.data_ptr(), ab.data_ptr(), w.data_ptr(), da.data_ptr(), dw.data_ptr(), db.data_ptr(), g, ncls, p,
+             None, spd.data_ptr(), _lib.F32, st())
+        kept_b = (from_flat(da, B, pitch, L) > 0).sum(dim=1).float()
+        assert torch.equal(kept_b, torch.round(kept).float())
+        lows.append(low)
+    assert not torch.equal(lows[0], lows[1])
+
+
+@pytest.mark.parametrize("Lin,Lout", [(79, 2500), (157, 5000), (10, 300), (5, 5)])
+def test_upsample(Lin, Lout):
+    torch.manual_seed(1)
+    B, ncls = 3, 4
+    low = torch.randn(B, Lin, ncls, device=DEV)
+    out = torch.zeros(B, ncls, Lout, device=DEV)
+    call("ssb_upsample_fwd", low.data_ptr(), out.data_ptr(), B, Lin, Lout, ncls, 0, st())
+    lr = low.permute(0, 2, 1).contiguous().requires_grad_(True)
+    ref = F.interpolate(lr, size=Lout, mode="linear", align_corners=False)
+    assert float((out - ref).abs().max()) < 2e-6
+    assert rel_err(out, O.linear_upsample(low.permute(0, 2, 1).double(), Lout)) < 1e-6
+    dout = torch.randn(B, ncls, Lout, device=DEV)
+    ref.backward(dout)
+    dlow = torch.zeros(B, Lin, ncls, device=DEV)
+    call("ssb_upsample_bwd", dout.data_ptr(), dlow.data_ptr(), B, Lin, Lout, ncls, 0, st())
+    assert rel_err(dlow.permute(0, 2, 1), lr.grad) < 1e-5
+
+
+def _adversarial_logits(U, L):
+    torch.manual_seed(3)
+    z = torch.randn(U, 4, L, device=DEV)
+    z[0] *= 5
+    z[1] *= 20
+    z[2, :, :50] = 0.0                       # exact ties -> first index
+    z[2, 1, 50:100] = z[2, 3, 50:100]        # pairwise ties
+    # confidences within a few ulp of fp32(0.8): logits (a, 0, 0, 0) with softmax max = 0.8 -> a = ln(12)
+    a = float(np.log(12.0))
+    z[3, :, :] = 0.0
+    z[3, 0, :] = a + (torch.arange(L, device=DEV) - L // 2).float() * 1e-7
+    return z
+
+
+def test_pseudo_label_bit_exact():
+    U, L = 6, 2500
+    z = _adversarial_logits(U, L)
+    thr = 0.8
+    conf = torch.zeros(U, L, device=DEV)
+    label = torch.zeros(U, L, dtype=torch.int64, device=DEV)
+    mask = torch.zeros(U, L, dtype=torch.uint8, device=DEV)
+    call("ssb_pseudo_label", z.data_ptr(), thr, conf.data_ptr(), label.data_ptr(), mask.data_ptr(), U, 4, L, st())
+    rc, rl, rm = O.pseudo_label(z, thr)      # torch's own CUDA softmax / argmax / compare
+    assert torch.equal(label, rl)
+    assert torch.equal(conf.view(torch.int32), rc.view(torch.int32))      # bit pattern
+    assert torch.equal(mask.bool(), rm)
+    assert 0 < int(rm[3].sum()) < L           # the 1-ulp band straddles the threshold
+    # special values
+    z2 = torch.randn(2, 4, 64, device=DEV)
+    z2[0, 1, 3] = float("inf")
+    z2[0, 2, 5] = float("-inf")
+    z2[1, 0, 7] = float("nan")
+    c2 = torch.zeros(2, 64, device=DEV)
+    l2 = torch.zeros(2, 64, dtype=torch.int64, device=DEV)
+    m2 = torch.zeros(2, 64, dtype=torch.uint8, device=DEV)
+    call("ssb_pseudo_label", z2.data_ptr(), thr, c2.data_ptr(), l2.data_ptr(), m2.data_ptr(), 2, 4, 64, st())
+    rc, rl, rm = O.pseudo_label(z2, thr)
+    assert torch.equal(l2, rl) and torch.equal(m2.bool(), rm)
+    assert torch.equal(torch.isnan(c2), torch.isnan(rc))
+
+
+@pytest.mark.parametrize("mode", [_lib.LOSS_SUP, _lib.LOSS_FIXMATCH, _lib.LOSS_SOFT])
+@pytest.mark.parametrize("Lin,L", [(79, 2500), (10, 300), (157, 5000)])
+def test_semi_loss(mode, Lin, L):
+    torch.manual_seed(Lin + mode)
+    Bl, Bu, ncls = 3, (0 if mode == _lib.LOSS_SUP else 4), 4
+    S = Bl + Bu
+    low_s = torch.randn(S, Lin, ncls, device=DEV) * 2
+    low_t = torch.randn(max(Bu, 1), Lin, ncls, device=DEV) * 3
+    y = torch.randint(0, ncls, (Bl, L), device=DEV)
+    thr = 0.6
+    # oracle (fp64) on the upsampled logits, autograd back to the low-res logits
+    ls = low_s.double().permute(0, 2, 1).contiguous().requires_grad_(True)
+    zs = O.linear_upsample(ls, L)
+    loss_x = O.ce_hard(zs[:Bl], y)
+    if mode == _lib.LOSS_SUP:
+        loss, loss_u, mratio = loss_x, None, None
+    else:
+        zt = O.linear_upsample(low_t.permute(0, 2, 1).contiguous(), L)   # fp32, like the CUDA path
+        if mode == _lib.LOSS_FIXMATCH:
+            conf_r, lab_r, mask_r = O.pseudo_label(zt, thr)
+            loss_u = O.ce_masked(zs[Bl:], lab_r, mask_r)
+            mratio = float(mask_r.float().mean())
+        else:
+            loss_u = O.ce_soft(zs[Bl:], zt.double().softmax(1))
+        loss = (loss_x + loss_u) / 2
+    loss.backward()
+    dlow = torch.full((S, Lin, ncls), 9.0, device=DEV)
+    sums = torch.zeros(4, dtype=torch.float64, device=DEV)
+    conf = torch.zeros(max(Bu, 1), L, device=DEV)
+    label = torch.zeros(max(Bu, 1), L, dtype=torch.int64, device=DEV)
+    mask = torch.zeros(max(Bu, 1), L, dtype=torch.uint8, device=DEV)
+    mat = mode == _lib.LOSS_FIXMATCH
+    call("ssb_semi_loss", low_s.data_ptr(), y.data_ptr(), low_t.data_ptr() if Bu else None, dlow.data_ptr(), sums.data_ptr(),
+         Bl, Bu, Lin, L, ncls, mode, thr, None, 0, conf.data_ptr() if mat else None, label.data_ptr() if mat else None,
+         mask.data_ptr() if mat else None, st())
+    s = sums.cpu()
+    assert abs(float(s[0]) / (Bl * L) - float(loss_x)) < 2e-6 * max(1, abs(float(loss_x)))
+    if mode != _lib.LOSS_SUP:
+        assert abs(float(s[1]) / (Bu * L) - float(loss_u)) < 5e-6 * max(1, abs(float(loss_u)))
+    if mode == _lib.LOSS_FIXMATCH:
+        # masks computed from kernel-internal fp32 lerp may differ from the torch path at exact threshold ties only
+        assert abs(float(s[2]) / (Bu * L) - mratio) < 1e-4
+        assert float((label != lab_r).float().mean()) < 1e-4
+        assert float((mask.bool() != mask_r).float().mean()) < 1e-4
+        assert float((conf - conf_r).abs().max()) < 1e-5
+    assert rel_err(dlow.permute(0, 2, 1), ls.grad) < 2e-5
+
+
+def test_semi_loss_deterministic():
+    torch.manual_seed(0)
+    Bl, Bu, Lin, L, ncls = 4, 4, 79, 2500, 4
+    low_s = torch.randn(Bl + Bu, Lin, ncls, device=DEV)
+    low_t = torch.randn(Bu, Lin, ncls, device=DEV) * 4
+    y = torch.randint(0, ncls, (Bl, L), device=DEV)
+    outs = []
+    for _ in range(3):
+        dlow = torch.zeros(Bl + Bu, Lin, ncls, device=DEV)
+        sums = torch.zeros(4, dtype=torch.float64, device=DEV)
+        call("ssb_semi_loss", low_s.data_ptr(), y.data_ptr(), low_t.data_ptr(), dlow.data_ptr(), sums.data_ptr(), Bl, Bu, Lin, L,
+             ncls, _lib.LOSS_FIXMATCH, 0.7, None, 0, None, None, None, st())
+        outs.append(dlow)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_adamw_ema_matches_oracle():
+    torch.manual_seed(0)
+    n = 64 * 1024 + 64
+    p = torch.randn(n, device=DEV)
+    m = torch.randn(n, device=DEV) * 0.01
+    v = torch.rand(n, device=DEV) * 1e-4
+    e = torch.randn(n, device=DEV)
+    g = torch.randn(n, device=DEV) * 0.1
+    pr, mr, vr, er = p.double().clone(), m.double().clone(), v.double().clone(), e.double().clone()
+    lr, b1, b2, eps, wd, t, d = 3e-4, 0.9, 0.999, 1e-8, 0.05, 7, 0.99
+    O.adamw_update(pr, g.double(), mr, vr, t, lr, (b1, b2), eps, wd)
+    er = er * d + pr * (1 - d)
+    sp = StepParams()
+    sp.lr, sp.inv_bias1, sp.inv_sqrt_bias2 = lr, 1 / (1 - b1 ** t), 1 / (1 - b2 ** t) ** 0.5
+    sp.ema_decay, sp.ema_first, sp.step, sp.grad_scale = d, 0, t, 1.0
+    spd = torch.frombuffer(bytearray(bytes(sp)), dtype=torch.uint8).to(DEV)
+    call("ssb_adamw_ema", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), e.data_ptr(), n, b1, b2, eps, wd, spd.data_ptr(), st())
+    assert rel_err(p, pr) < 1e-6 and rel_err(m, mr) < 1e-6 and rel_err(v, vr) < 1e-6 and rel_err(e, er) < 1e-6
+    # teacher-aliasing first step: EMA result == new student weights (up to one rounding)
+    sp.ema_first = 1
+    spd = torch.frombuffer(bytearray(bytes(sp)), dtype=torch.uint8).to(DEV)
+    call("ssb_adamw_ema", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), e.data_ptr(), n, b1, b2, eps, wd, spd.data_ptr(), st())
+    assert rel_err(e, p) < 1e-6
+    # grad norm
+    ws = torch.zeros(1, dtype=torch.float64, device=DEV)
+    out = torch.zeros(1, device=DEV)
+    call("ssb_grad_norm", g.data_ptr(), n, ws.data_ptr(), out.data_ptr(), st())
+    assert abs(float(out) - float(g.double().norm())) < 1e-4 * float(g.double().norm())
+
+
+def test_errors_are_reported():
+    lib = _lib.load()
+    g = Geom(1, 4, 8, 8)   # pitch < len + 2
+    rc = lib.ssb_bn_stats(None, g, None, 0, None)
+    assert rc != 0 and b"ssb_bn_stats" in lib.ssb_last_error()
+    with pytest.raises(RuntimeError):
+        call("ssb_conv1d_fwd", None, None, None, None, Geom(1, 10, 8, 8), Geom(1, 10, 8, 8), 5, 1, 0, 0, None)

@@ -1,0 +1,125 @@
+"""Drop-in surface: configs parse through init_model_from_cfg, state_dict keys /
+shapes / dtypes equal the reference's 128 entries, seeded init is bit-identical to the
+reference's, LR schedule, optimizer facade, loud failure without CUDA."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+from helpers import O, REPO, TRAIN_CFG, group, model_cfg
+
+CONFIGS = os.path.join(REPO, "semi-seg-ecg_b200", "configs")
+
+
+def test_every_base_config_builds_a_model():
+    from algorithms.base import init_model_from_cfg
+    from utils.config import load_config
+    files = sorted(glob.glob(os.path.join(CONFIGS, "base", "**", "*.yaml"), recursive=True))
+    assert len(files) >= 6
+    for f in files:
+        cfg = load_config(f, os.path.join(CONFIGS, "bench", "ludb", "1over16.yaml"))
+        assert cfg["exp_name"] == "ludb/1over16" and cfg["dataset"]["signal_length"] == 2500
+        m = init_model_from_cfg(cfg)
+        assert sum(p.numel() for p in m.parameters()) == 4041284
+        assert len(m.state_dict()) == 128
+    assert len(glob.glob(os.path.join(CONFIGS, "bench", "**", "*.yaml"), recursive=True)) >= 17
+
+
+def test_algorithm_registry():
+    import algorithms
+    for name in ("base", "fixmatch", "mean_teacher"):
+        mod = algorithms.__dict__[name]
+        assert callable(mod.train) and callable(mod.test) and callable(mod.train_one_epoch)
+
+
+def test_state_dict_matches_reference_golden(golden):
+    from algorithms.base import init_model_from_cfg
+    ref = group(golden, "A/init")
+    torch.manual_seed(0)
+    m = init_model_from_cfg(model_cfg(2, 8, 8, 16, 0.0))
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(ref[k].shape) and str(v.dtype).replace("torch.", "") == str(ref[k].dtype), k
+        assert np.array_equal(v.numpy(), ref[k]), f"seeded init differs from the reference for {k}"
+    # full-size model: per-tensor checksums of the reference init
+    torch.manual_seed(0)
+    m = init_model_from_cfg(model_cfg(1, 64, 64, 128, 0.0))
+    cs = np.array([float(v.double().sum()) for v in m.state_dict().values()])
+    assert np.array_equal(cs, golden["E/init_checksum"])
+
+
+def test_layout_matches_oracle_names():
+    from semiseg_b200.net import ParamLayout, SegNetSpec
+    lay = ParamLayout(SegNetSpec())
+    arch = O.Arch()
+    assert lay.param_names() == O.param_names(arch)
+    assert lay.buffer_names() == O.buffer_names(arch)
+    assert lay.numel == 4041284 and len(lay.params) == 65 and len(lay.bns) == 21 and len(lay.convs) == 20
+    for _, _, off in lay.params:
+        assert off % 64 == 0
+
+
+def test_plan_geometry():
+    """Stage lengths and pitches: 2500 -> 1250 -> 625 -> 625 -> 313 -> 157 -> 79."""
+    assert O.stage_lengths(O.Arch(), 2500) == [1250, 625, 625, 313, 157, 79]
+    assert O.stage_lengths(O.Arch(), 5000) == [2500, 1250, 1250, 625, 313, 157]
+
+
+def test_lr_schedule_matches_oracle():
+    from utils.lr_sched import adjust_learning_rate
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+    for e in (0.0, 0.5, 3.2, 10.0, 55.5, 99.9):
+        lr = adjust_learning_rate(opt, e, TRAIN_CFG)
+        assert lr == pytest.approx(O.lr_at(e, TRAIN_CFG), rel=0, abs=1e-15)
+        assert opt.param_groups[0]["lr"] == lr
+    assert adjust_learning_rate(opt, 0.0, TRAIN_CFG) == 0.0       # step 0 has lr = 0
+
+
+def test_unsupported_variants_fail_loudly():
+    import models.backbones as bb
+    import models.decode_heads as dh
+    from utils.optimizer import get_optimizer_from_config
+    with pytest.raises(NotImplementedError):
+        bb.resnet50(num_leads=1)
+    with pytest.raises(NotImplementedError):
+        bb.resnet18(num_leads=1, deep_stem=True)
+    with pytest.raises(NotImplementedError):
+        bb.vit_tiny()
+    with pytest.raises(NotImplementedError):
+        dh.FCNHead(512, 128, 4, num_convs=2, concat_input=False)
+    with pytest.raises(NotImplementedError):
+        get_optimizer_from_config(dict(TRAIN_CFG, optimizer="sgd"), [torch.nn.Parameter(torch.zeros(1))])
+
+
+def test_cpu_forward_fails_loudly():
+    from algorithms.base import init_model_from_cfg
+    m = init_model_from_cfg(model_cfg(1, 8, 8, 16, 0.0))
+    with pytest.raises(RuntimeError, match="no CPU fallback|CUDA"):
+        m(torch.zeros(1, 1, 64))
+
+
+def test_config_merge_and_cli_override(tmp_path):
+    from utils.config import deep_merge, load_config
+    a = {"x": {"y": 1, "z": 2}, "k": [1, 2]}
+    b = {"x": {"y": 5}, "k": [3]}
+    assert deep_merge(a, b) == {"x": {"y": 5, "z": 2}, "k": [3]} and a["x"]["y"] == 1
+    p = tmp_path / "c.yaml"
+    p.write_text(yaml.safe_dump({"exp_name": "a", "resume": None, "start_epoch": 0}))
+    cfg = load_config(str(p), None, {"exp_name": "cli", "resume": "", "start_epoch": 0})
+    assert cfg["exp_name"] == "cli" and cfg["resume"] is None      # only truthy CLI values overwrite
+
+
+def test_synthetic_batches_follow_the_dataset_contract():
+    from semiseg_b200 import synthetic
+    lab, unl = synthetic.make_batch(0, 4, 6, 12, 5000, fs=500)
+    assert lab["ecg"].shape == (4, 12, 5000) and lab["ecg"].dtype == np.float32
+    assert lab["target"].shape == (4, 5000) and lab["target"].dtype == np.int64
+    assert set(np.unique(lab["target"])) == {0, 1, 2, 3}
+    assert unl["ecg"].shape == unl["ecg_aug"].shape == (6, 12, 5000)
+    assert abs(float(lab["ecg"][0].mean())) < 1e-5 and abs(float(lab["ecg"][0].std()) - 1) < 1e-4
+    lab2, _ = synthetic.make_batch(0, 4, 6, 12, 5000, fs=500)
+    assert np.array_equal(lab["ecg"], lab2["ecg"])
