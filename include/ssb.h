@@ -111,6 +111,10 @@ int ssb_device_check(void);
 /* number of kernels launched by this library since load (all threads); for bench accounting */
 int64_t ssb_launch_count(void);
 
+/* one-time per-device setup (opt-in shared-memory sizes of the large kernels); call once before
+ * the first launch / before capturing a CUDA graph */
+int ssb_prepare(void);
+
 int ssb_memset_zero(void* p, size_t bytes, ssb_stream_t stream);
 
 /* ---- stem: Conv1d(C_leads -> Cs, k7, s2, p3, bias=False)  (resnet.py:246-253) ------ */
@@ -214,7 +218,7 @@ int ssb_semi_loss(const float* low_s, const int64_t* target, const float* low_t,
 /* ---- fused multi-tensor AdamW (+ EMA teacher)  (optimizer.py:22-34, mean_teacher.py:139-149) --- */
 /* flat arenas of n floats.  p_ema may be NULL.  Scalars come from sp (device). */
 int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, size_t n,
-                  float beta1, float beta2, float eps, float weight_decay,
+                  double beta1, double beta2, double eps, double weight_decay,
                   const ssb_step_params* sp, ssb_stream_t stream);
 /* dst = dst*d + src*(1-d) (teacher BN buffers); d from sp->ema_decay */
 int ssb_ema(float* dst, const float* src, size_t n, const ssb_step_params* sp, ssb_stream_t stream);

@@ -179,10 +179,15 @@ def linear_upsample(x: Tensor, L_out: int, align_corners: bool = False) -> Tenso
     return x[..., i0] * w0 + x[..., i1] * w1
 
 
+def bf16_round(t: Tensor) -> Tensor:
+    """Round to bf16 and back (straight-through for autograd): emulates bf16 STORAGE of a tensor."""
+    return t + (t.detach().to(torch.bfloat16).to(t.dtype) - t.detach())
+
+
 def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
             dropout_mask: Optional[Tensor] = None,
             new_buffers: Optional[Dict[str, Tensor]] = None,
-            taps: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
+            taps: Optional[Dict[str, Tensor]] = None, quant=None) -> Dict[str, Tensor]:
     """EncoderDecoder.forward (encoder_decoder.py:78-108) over resnet.py:353-363
     (stem -> maxpool -> BasicBlocks, resnet.py:55-72) and FCNHead.forward (fcn_head.py:89-97).
 
@@ -191,18 +196,26 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
     Returns {'seg_logits': [B, ncls, L], 'low_logits': [B, ncls, L_head]}.
     If ``taps`` is a dict it is filled with named intermediate activations (module-output
     granularity) for per-layer parity checks.
+    ``quant`` (e.g. ``bf16_round``) is applied to every conv weight, conv output and stored
+    activation: it emulates the BF16 path's storage roundings on top of exact arithmetic, so that
+    the BF16 kernels can be checked tightly (kernel correctness) separately from the precision
+    loss that bf16 storage itself causes.
     """
+    q = quant if quant is not None else (lambda t: t)
+    if quant is not None:
+        sd = {k: (q(v) if (k.endswith("conv1.weight") or k.endswith("conv2.weight") or k.endswith("downsample.0.weight")
+                           or k == "decode_head.convs.0.0.weight") else v) for k, v in sd.items()}
     def tap(name, t):
         if taps is not None:
             taps[name] = t
         return t
 
     L = x.shape[2]
-    h = F.conv1d(x, sd["backbone.stem.0.weight"], None, stride=2, padding=3)
+    h = q(F.conv1d(x, sd["backbone.stem.0.weight"], None, stride=2, padding=3))
     tap("backbone.stem.0", h)
     h = torch.relu(batchnorm(h, sd, "backbone.stem.1", train, new_buffers))
     tap("backbone.stem", h)
-    h = maxpool_k3s2p1(h)
+    h = q(maxpool_k3s2p1(h))
     tap("backbone.maxpool", h)
     feats = []
     inpl = arch.stem_channels
@@ -212,24 +225,24 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
             pre = f"backbone.layer{i + 1}.{j}"
             s = arch.strides[i] if j == 0 else 1
             ident = h
-            o = F.conv1d(h, sd[pre + ".conv1.weight"], None, stride=s, padding=1)
+            o = q(F.conv1d(h, sd[pre + ".conv1.weight"], None, stride=s, padding=1))
             tap(pre + ".conv1", o)
-            o = torch.relu(batchnorm(o, sd, pre + ".bn1", train, new_buffers))
-            o = F.conv1d(o, sd[pre + ".conv2.weight"], None, stride=1, padding=1)
+            o = q(torch.relu(batchnorm(o, sd, pre + ".bn1", train, new_buffers)))
+            o = q(F.conv1d(o, sd[pre + ".conv2.weight"], None, stride=1, padding=1))
             tap(pre + ".conv2", o)
             o = batchnorm(o, sd, pre + ".bn2", train, new_buffers)
             if (pre + ".downsample.0.weight") in sd:
-                ident = F.conv1d(h, sd[pre + ".downsample.0.weight"], None, stride=s, padding=0)
+                ident = q(F.conv1d(h, sd[pre + ".downsample.0.weight"], None, stride=s, padding=0))
                 tap(pre + ".downsample.0", ident)
                 ident = batchnorm(ident, sd, pre + ".downsample.1", train, new_buffers)
-            h = torch.relu(o + ident)
+            h = q(torch.relu(o + ident))
             tap(pre, h)
         inpl = pl
         feats.append(h)
     f = feats[arch.in_index]
-    h = F.conv1d(f, sd["decode_head.convs.0.0.weight"], None, stride=1, padding=1)
+    h = q(F.conv1d(f, sd["decode_head.convs.0.0.weight"], None, stride=1, padding=1))
     tap("decode_head.convs.0.0", h)
-    h = torch.relu(batchnorm(h, sd, "decode_head.convs.0.1", train, new_buffers))
+    h = q(torch.relu(batchnorm(h, sd, "decode_head.convs.0.1", train, new_buffers)))
     tap("decode_head.convs.0", h)
     if train and dropout_mask is not None and arch.dropout_ratio > 0:
         h = h * dropout_mask.to(h.dtype) / (1.0 - arch.dropout_ratio)
@@ -325,6 +338,7 @@ class OracleTrainer:
         # first EMA; buffers are the teacher's own fresh-init copies.
         self.teacher_sd: Optional[Dict[str, Tensor]] = None
         self.teacher_aliased = True
+        self.quant = None   # set to bf16_round to emulate the BF16 path's storage roundings
 
     # ---- helpers -------------------------------------------------------------------
     def _leaf_params(self) -> Dict[str, Tensor]:
@@ -379,7 +393,7 @@ class OracleTrainer:
         sdg = self._leaf_params()
         nb: Dict[str, Tensor] = {}
         self.taps = {} if want_taps else None
-        out = forward(sdg, ecg.to(self.dtype), self.arch, True, dropout_mask, nb, self.taps)
+        out = forward(sdg, ecg.to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant)
         if want_taps:
             for t_ in self.taps.values():
                 if t_.requires_grad:
@@ -397,7 +411,7 @@ class OracleTrainer:
         """fixmatch.py:79-138."""
         thr = self.cfg["conf_thresh"]
         with torch.no_grad():
-            pw = forward(self.sd, ecg_u_w.to(self.dtype), self.arch, False)["seg_logits"]
+            pw = forward(self.sd, ecg_u_w.to(self.dtype), self.arch, False, quant=self.quant)["seg_logits"]
             conf = pw.softmax(dim=1).max(dim=1)[0]
             label = pw.argmax(dim=1)
             # the reference compares an fp32 conf with the python float threshold
@@ -407,7 +421,7 @@ class OracleTrainer:
         nb: Dict[str, Tensor] = {}
         self.taps = {} if want_taps else None
         nl = ecg_x.shape[0]
-        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps)
+        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant)
         if want_taps:
             for t_ in self.taps.values():
                 if t_.requires_grad:
@@ -431,14 +445,14 @@ class OracleTrainer:
             self.init_teacher()
         d = self.cfg.get("ema_decay", 0.999)
         with torch.no_grad():
-            pw = forward(self._teacher_view(), ecg_u_w.to(self.dtype), self.arch, False)["seg_logits"]
+            pw = forward(self._teacher_view(), ecg_u_w.to(self.dtype), self.arch, False, quant=self.quant)["seg_logits"]
             prob = pw.softmax(dim=1)
         self.pseudo = {"prob": prob, "logits_w": pw}
         sdg = self._leaf_params()
         nb: Dict[str, Tensor] = {}
         self.taps = {} if want_taps else None
         nl = ecg_x.shape[0]
-        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps)
+        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant)
         self.low_logits = out["low_logits"]
         self.low_logits.retain_grad()
         seg = out["seg_logits"]

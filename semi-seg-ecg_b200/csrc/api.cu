@@ -14,7 +14,19 @@ void ssb_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int ssb_sm100_prepare();
+int ssb_simt_prepare();
+int ssb_loss_prepare();
+
 extern "C" {
+
+int ssb_prepare(void) {
+  int rc = ssb_device_check();
+  if (rc) return rc;
+  if ((rc = ssb_simt_prepare())) return rc;
+  if ((rc = ssb_loss_prepare())) return rc;
+  return ssb_sm100_prepare();
+}
 
 int ssb_version(void) { return SSB_VERSION; }
 

@@ -379,6 +379,19 @@ int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom
 int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
                            cudaStream_t st);
 
+int ssb_simt_prepare() {
+  const int big = 96 * 1024;
+  cudaError_t e = cudaFuncSetAttribute(stem_conv_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_conv_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_conv_wgrad_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_conv_wgrad_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+  if (e != cudaSuccess) {
+    ssb_set_error("ssb_simt_prepare: %s", cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+  }
+  return SSB_OK;
+}
+
 extern "C" {
 
 int ssb_conv1d_fwd(const void* x, const void* w_kio, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k,
@@ -510,9 +523,9 @@ int ssb_stem_conv_fwd(const float* x, const float* w, void* y, int Cl, int L, ss
   if (rc) return rc;
   SSB_REQUIRE(x && w && y, "ssb_stem_conv_fwd: null pointer");
   const size_t smem = ((size_t)Cl * 7 * g.C + (size_t)Cl * (2 * ST_TT + 5)) * sizeof(float);
+  SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_fwd: num_leads x stem_channels too large (%zu B of shared memory)", smem);
   dim3 grid(ceil_div(g.len, ST_TT), g.B);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(stem_conv_fwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     stem_conv_fwd_kernel<T><<<grid, ST_THREADS, smem, to_stream(stream)>>>(x, w, (T*)y, Cl, L, g);
   })
   SSB_LAUNCH_CHECK("ssb_stem_conv_fwd");
@@ -525,9 +538,9 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
   if (rc) return rc;
   SSB_REQUIRE(x && dy && dw, "ssb_stem_conv_wgrad: null pointer");
   const size_t smem = ((size_t)ST_TT * g.C + (size_t)Cl * (2 * ST_TT + 5)) * sizeof(float);
+  SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_wgrad: stem_channels too large (%zu B of shared memory)", smem);
   dim3 grid(ceil_div(g.len, ST_TT), g.B);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(stem_conv_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     stem_conv_wgrad_kernel<T><<<grid, ST_THREADS, smem, to_stream(stream)>>>(x, (const T*)dy, dw, Cl, L, g);
   })
   SSB_LAUNCH_CHECK("ssb_stem_conv_wgrad");

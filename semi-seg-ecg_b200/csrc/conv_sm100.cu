@@ -1,5 +1,602 @@
-// placeholder, replaced below
+// Blackwell-native Conv1d for the wide-channel stages: implicit GEMM on the 5th-generation
+// tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA into 128B-swizzled
+// shared memory, mbarrier producer/consumer pipeline, warp-specialised roles.
+//
+//   fprop / dgrad  (conv_tn_kernel):  D[rows, N] = sum_taps A_tap[rows, K] * W_tap[N, K]^T
+//       both operands K-major; a k=3 conv is three row-shifted TMA boxes over the flat padded
+//       NLC activation (halo rows / TMA out-of-bounds zero fill implement the padding); a
+//       stride-2 conv reads the input through a [rows/2, 2C] "row pair" view.
+//   wgrad          (conv_wgrad_kernel): dW_tap[ci, co] = sum_rows X_tap[rows, ci] * dY[rows, co]
+//       both operands MN-major (the reduction runs over rows), split over rows across CTAs.
+//
+// Replaces cuDNN fprop/dgrad/wgrad for resnet.py:32-49,283-289 and fcn_head.py:40-47 (K4, K6 in
+// SURVEY.md 2.2).  bf16 operands, fp32 accumulation.  One CTA = one 128 x BN output tile;
+// warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
+#include <cuda.h>
+
 #include "common.cuh"
-int ssb_conv1d_fwd_sm100(const void*, const void*, void*, ssb_geom, ssb_geom, int, int, cudaStream_t) { ssb_set_error("tcgen05 conv not built"); return SSB_ERR_UNSUPPORTED; }
-int ssb_conv1d_dgrad_sm100(const void*, const void*, void*, ssb_geom, ssb_geom, int, int, int, cudaStream_t) { ssb_set_error("tcgen05 conv not built"); return SSB_ERR_UNSUPPORTED; }
-int ssb_conv1d_wgrad_sm100(const void*, const void*, float*, ssb_geom, ssb_geom, int, int, cudaStream_t) { ssb_set_error("tcgen05 conv not built"); return SSB_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BM = 128;          // UMMA_M
+constexpr int BK = 64;           // bf16 elements per 128-byte swizzle row
+constexpr int A_BYTES = BM * BK * 2;
+constexpr int NTHREADS = 192;
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (lane i of the warp <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, 128-byte swizzle, Blackwell version bit
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: bf16 x bf16 -> f32, M = 128, N = n
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TnParams {
+  int M, N, K, ntaps;
+  int a_row_off[3], a_col_off[3], w_tap[3];
+  int w_rows_per_tap;
+  int o_mul, o_off, o_rows, o_pitch, o_len;
+  int accumulate;
+};
+
+struct SmemLayout {
+  uint8_t* a;
+  uint8_t* b;
+  uint64_t* full;
+  uint64_t* empty;
+  uint64_t* done;
+  uint32_t* tmem_slot;
+};
+
+template <int B_BYTES, int STAGES>
+__device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
+  const uint32_t base = smem_u32(raw);
+  uint8_t* al = raw + (((base + 1023u) & ~1023u) - base);
+  SmemLayout s;
+  s.a = al;
+  s.b = al + STAGES * A_BYTES;
+  s.full = reinterpret_cast<uint64_t*>(s.b + STAGES * B_BYTES);
+  s.empty = s.full + STAGES;
+  s.done = s.empty + STAGES;
+  s.tmem_slot = reinterpret_cast<uint32_t*>(s.done + 1);
+  return s;
+}
+template <int B_BYTES, int STAGES>
+constexpr int smem_bytes() {
+  return STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fprop / dgrad
+// ---------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
+               const TnParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout s = carve<B_BYTES, STAGES>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(s.done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+  const int KC = p.K / BK;
+  const int iters = p.ntaps * KC;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&s.empty[st], ph ^ 1u);
+        mbar_expect_tx(&s.full[st], A_BYTES + B_BYTES);
+        const int tap = it / KC, kc = it - tap * KC;
+        tma_load_2d(s.a + st * A_BYTES, &tmA, &s.full[st], kc * BK + p.a_col_off[tap], m0 + p.a_row_off[tap]);
+        tma_load_2d(s.b + st * B_BYTES, &tmB, &s.full[st], kc * BK, p.w_tap[tap] * p.w_rows_per_tap + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, false);
+      for (int it = 0; it < iters; ++it) {
+        const int st = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(&s.full[st], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(s.a + st * A_BYTES), b0 = smem_u32(s.b + st * B_BYTES);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 16; ++k4) {
+          // K-major, 128B swizzle: 8-row groups are 1024 B apart; advance 16 elements = 32 B along K
+          umma_bf16(tmem_base, make_smem_desc(a0 + k4 * 32, 0, 1024), make_smem_desc(b0 + k4 * 32, 0, 1024), idesc,
+                    (uint32_t)((it | k4) != 0));
+        }
+        umma_commit(&s.empty[st]);   // frees the smem stage when these MMAs retire
+      }
+      umma_commit(s.done);           // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
+    const int q = warp & 3;
+    mbar_wait(s.done, 0);
+    tc_fence_after();
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const long long orow = (long long)p.o_mul * m + p.o_off;
+    const bool in_range = m < p.M && orow >= 0 && orow < p.o_rows;
+    const bool valid = in_range && row_valid((int)orow, p.o_pitch, p.o_len);
+    bf16* optr = out + (size_t)(in_range ? orow : 0) * p.N + n0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      if (!in_range) continue;
+      if (!valid && p.accumulate) continue;
+      uint4* dst = reinterpret_cast<uint4*>(optr + c);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(r[v * 8 + i]) : 0.f;
+        if (p.accumulate) {
+          Vec<bf16> prev;
+          prev.raw = dst[v];
+          float g[8];
+          prev.get(g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += g[i];
+        }
+        Vec<bf16> o;
+        o.set(f);
+        dst[v] = o.raw;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: dW[co][ci][tap] += sum_rows X[rows + shift(tap)][ci] * dY[rows][co]
+// GEMM rows (TMEM lanes) = ci tile of 128, columns = co tile of BN, reduction over rows.
+// grid = (ci tiles * co tiles, taps, splits)
+// ---------------------------------------------------------------------------------------------
+struct WgParams {
+  int M;            // output rows of the conv (reduction length)
+  int Cin, Cout, k;
+  int n_ci_tiles;
+  int a_row_off[3], a_col_off[3], w_tap[3];
+  int blocks_per_split;   // reduction blocks (of BK rows) per split
+  int nsplit;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  float* __restrict__ dw, const WgParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  SmemLayout s = carve<B_BYTES, STAGES>(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci0 = (blockIdx.x % p.n_ci_tiles) * BM;
+  const int co0 = (blockIdx.x / p.n_ci_tiles) * BN;
+  const int tap = blockIdx.y;
+  const int nblk_total = (p.M + BK - 1) / BK;
+  const int blk0 = blockIdx.z * p.blocks_per_split;
+  const int blk1 = min(nblk_total, blk0 + p.blocks_per_split);
+  const int iters = blk1 - blk0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&s.full[i], 1);
+      mbar_init(&s.empty[i], 1);
+    }
+    mbar_init(s.done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(s.tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s.tmem_slot;
+
+  if (iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < iters; ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&s.empty[st], ph ^ 1u);
+          mbar_expect_tx(&s.full[st], A_BYTES + B_BYTES);
+          const int r0 = (blk0 + it) * BK;
+          // MN-major operand tiles: [64-channel atom][BK rows][128 B]
+#pragma unroll
+          for (int a = 0; a < BM / 64; ++a)
+            tma_load_2d(s.a + st * A_BYTES + a * (BK * 128), &tmX, &s.full[st], p.a_col_off[tap] + ci0 + a * 64,
+                        r0 + p.a_row_off[tap]);
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_2d(s.b + st * B_BYTES + b * (BK * 128), &tmDY, &s.full[st], co0 + b * 64, r0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(BN, true);
+        for (int it = 0; it < iters; ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&s.full[st], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(s.a + st * A_BYTES), b0 = smem_u32(s.b + st * B_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            // MN-major, 128B swizzle: 64-element MN atoms are BK*128 B apart (LBO), 8-row K groups
+            // 1024 B apart (SBO); advancing 16 reduction rows = 2048 B
+            umma_bf16(tmem_base, make_smem_desc(a0 + k4 * 2048, BK * 128, 1024),
+                      make_smem_desc(b0 + k4 * 2048, BK * 128, 1024), idesc, (uint32_t)((it | k4) != 0));
+          }
+          umma_commit(&s.empty[st]);
+        }
+        umma_commit(s.done);
+      }
+    } else {
+      const int q = warp & 3;
+      mbar_wait(s.done, 0);
+      tc_fence_after();
+      const int ci = ci0 + q * 32 + lane;
+      const int wt = p.w_tap[tap];
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        tmem_ld_wait();
+        if (ci >= p.Cin) continue;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int co = co0 + c + j;
+          if (co < p.Cout) {
+            float* dst = dw + ((size_t)co * p.Cin + ci) * p.k + wt;
+            const float v = __uint_as_float(r[j]);
+            if (p.nsplit > 1) atomicAdd(dst, v);
+            else *dst += v;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `outer` rows of `pitch_elems` elements,
+// box = box_inner x box_outer, 128-byte swizzle, out-of-bounds elements read as zero
+int make_map(CUtensorMap* map, const void* base, long long inner, long long outer, long long pitch_elems, int box_inner,
+             int box_outer) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    ssb_set_error("cuTensorMapEncodeTiled entry point not available");
+    return SSB_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch_elems * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ssb_set_error("cuTensorMapEncodeTiled failed (%d): inner=%lld outer=%lld pitch=%lld box=%dx%d base=%p", (int)r, inner,
+                  outer, pitch_elems, box_inner, box_outer, base);
+    return SSB_ERR_CUDA;
+  }
+  return SSB_OK;
+}
+
+constexpr int TN_STAGES = 4;
+constexpr int WG_STAGES = 4;
+
+template <int BN>
+int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
+  constexpr int smem = smem_bytes<BN * BK * 2, TN_STAGES>();
+  dim3 grid(ceil_div(p.M, BM), p.N / BN);
+  conv_tn_kernel<BN, TN_STAGES><<<grid, NTHREADS, smem, st>>>(tmA, tmB, out, p);
+  SSB_LAUNCH_CHECK("conv_tn_kernel");
+  return SSB_OK;
+}
+
+int run_tn(const void* a_base, long long a_inner, long long a_outer, long long a_pitch, const void* w_base, int w_rows,
+           bf16* out, const TnParams& p, cudaStream_t st) {
+  const int BN = (p.N % 128 == 0) ? 128 : 64;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, a_base, a_inner, a_outer, a_pitch, BK, BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, w_base, p.K, w_rows, p.K, BK, BN);
+  if (rc) return rc;
+  return BN == 128 ? launch_tn<128>(tmA, tmB, out, p, st) : launch_tn<64>(tmA, tmB, out, p, st);
+}
+
+int check_sm100_shape(const char* who, const ssb_geom& gi, const ssb_geom& go) {
+  SSB_REQUIRE(gi.C % 64 == 0 && go.C % 64 == 0, "%s: tcgen05 path needs Cin, Cout multiples of 64 (got %d, %d)", who, gi.C, go.C);
+  return SSB_OK;
+}
+
+}  // namespace
+
+template <typename T>
+__global__ void zero_parity_rows_sm100(T* out, int rows, int N, int parity) {
+  const long long total = (long long)(rows / 2) * N;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long q = idx / N;
+    const int n = (int)(idx - q * N);
+    out[(size_t)(2 * q + parity) * N + n] = from_f<T>(0.f);
+  }
+}
+
+int ssb_sm100_prepare() {
+  cudaError_t e = cudaSuccess;
+  e = cudaFuncSetAttribute(conv_tn_kernel<128, TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           smem_bytes<128 * BK * 2, TN_STAGES>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tn_kernel<64, TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes<64 * BK * 2, TN_STAGES>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_wgrad_kernel<128, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes<128 * BK * 2, WG_STAGES>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_wgrad_kernel<64, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes<64 * BK * 2, WG_STAGES>());
+  if (e != cudaSuccess) {
+    ssb_set_error("ssb_sm100_prepare: %s", cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+  }
+  return SSB_OK;
+}
+
+int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
+                         cudaStream_t st) {
+  int rc = check_sm100_shape("ssb_conv1d_fwd", gin, gout);
+  if (rc) return rc;
+  TnParams p = {};
+  p.M = gout.B * gout.pitch;
+  p.N = gout.C;
+  p.K = gin.C;
+  p.ntaps = k;
+  p.w_rows_per_tap = gout.C;
+  p.o_mul = 1;
+  p.o_off = 0;
+  p.o_rows = p.M;
+  p.o_pitch = gout.pitch;
+  p.o_len = gout.len;
+  p.accumulate = 0;
+  const long long rows_in = (long long)gin.B * gin.pitch;
+  long long a_inner, a_outer, a_pitch;
+  if (stride == 1) {
+    a_inner = gin.C; a_outer = rows_in; a_pitch = gin.C;
+    for (int j = 0; j < k; ++j) { p.a_row_off[j] = (k == 3) ? j - 1 : 0; p.a_col_off[j] = 0; p.w_tap[j] = j; }
+  } else {
+    // row-pair view [rows/2, 2C]: input row 2q+par <-> (q, par*C); output row R <-> q = R-1
+    a_inner = 2LL * gin.C; a_outer = rows_in / 2; a_pitch = 2LL * gin.C;
+    if (k == 3) {
+      p.a_row_off[0] = -1; p.a_col_off[0] = 0;     p.w_tap[0] = 0;
+      p.a_row_off[1] = -1; p.a_col_off[1] = gin.C; p.w_tap[1] = 1;
+      p.a_row_off[2] = 0;  p.a_col_off[2] = 0;     p.w_tap[2] = 2;
+    } else {
+      p.a_row_off[0] = -1; p.a_col_off[0] = gin.C; p.w_tap[0] = 0;
+    }
+  }
+  return run_tn(x, a_inner, a_outer, a_pitch, w_koi, k * gout.C, (bf16*)y, p, st);
+}
+
+int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
+                           int accumulate, cudaStream_t st) {
+  int rc = check_sm100_shape("ssb_conv1d_dgrad", gin, gout);
+  if (rc) return rc;
+  const int rows_in = gin.B * gin.pitch, rows_out = gout.B * gout.pitch;
+  TnParams p = {};
+  p.N = gin.C;
+  p.K = gout.C;
+  p.w_rows_per_tap = gin.C;
+  p.o_rows = rows_in;
+  p.o_pitch = gin.pitch;
+  p.o_len = gin.len;
+  p.accumulate = accumulate;
+  if (stride == 1) {
+    p.M = rows_in;
+    p.ntaps = k;
+    p.o_mul = 1;
+    p.o_off = 0;
+    for (int j = 0; j < k; ++j) { p.a_row_off[j] = (k == 3) ? 1 - j : 0; p.a_col_off[j] = 0; p.w_tap[j] = j; }
+    return run_tn(dy, gout.C, rows_out, gout.C, w_kio, k * gin.C, (bf16*)dx, p, st);
+  }
+  // stride 2: dx row 2q+par; par 0 <- dy[q+1]*W0 + dy[q]*W2; par 1 <- dy[q+1]*W1 (k=1: par 1 <- dy[q+1]*W0)
+  p.M = rows_in / 2;
+  p.o_mul = 2;
+  for (int par = 0; par < 2; ++par) {
+    p.o_off = par;
+    p.ntaps = 0;
+    if (k == 3) {
+      if (par == 0) { p.ntaps = 2; p.a_row_off[0] = 1; p.w_tap[0] = 0; p.a_row_off[1] = 0; p.w_tap[1] = 2; }
+      else { p.ntaps = 1; p.a_row_off[0] = 1; p.w_tap[0] = 1; }
+    } else if (par == 1) {
+      p.ntaps = 1; p.a_row_off[0] = 1; p.w_tap[0] = 0;
+    }
+    p.a_col_off[0] = p.a_col_off[1] = p.a_col_off[2] = 0;
+    if (p.ntaps == 0) {
+      if (!accumulate) {
+        zero_parity_rows_sm100<bf16><<<148 * 2, 256, 0, st>>>((bf16*)dx, rows_in, gin.C, par);
+        SSB_LAUNCH_CHECK("zero_parity_rows_sm100");
+      }
+      continue;
+    }
+    rc = run_tn(dy, gout.C, rows_out, gout.C, w_kio, k * gin.C, (bf16*)dx, p, st);
+    if (rc) return rc;
+  }
+  return SSB_OK;
+}
+
+int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
+                           cudaStream_t st) {
+  int rc = check_sm100_shape("ssb_conv1d_wgrad", gin, gout);
+  if (rc) return rc;
+  WgParams p = {};
+  p.M = gout.B * gout.pitch;
+  p.Cin = gin.C;
+  p.Cout = gout.C;
+  p.k = k;
+  p.n_ci_tiles = ceil_div(gin.C, BM);
+  const long long rows_in = (long long)gin.B * gin.pitch;
+  long long x_inner, x_outer, x_pitch;
+  if (stride == 1) {
+    x_inner = gin.C; x_outer = rows_in; x_pitch = gin.C;
+    for (int j = 0; j < k; ++j) { p.a_row_off[j] = (k == 3) ? j - 1 : 0; p.a_col_off[j] = 0; p.w_tap[j] = j; }
+  } else {
+    x_inner = 2LL * gin.C; x_outer = rows_in / 2; x_pitch = 2LL * gin.C;
+    if (k == 3) {
+      p.a_row_off[0] = -1; p.a_col_off[0] = 0;     p.w_tap[0] = 0;
+      p.a_row_off[1] = -1; p.a_col_off[1] = gin.C; p.w_tap[1] = 1;
+      p.a_row_off[2] = 0;  p.a_col_off[2] = 0;     p.w_tap[2] = 2;
+    } else {
+      p.a_row_off[0] = -1; p.a_col_off[0] = gin.C; p.w_tap[0] = 0;
+    }
+  }
+  const int BN = (gout.C % 128 == 0) ? 128 : 64;
+  const int tiles = p.n_ci_tiles * (gout.C / BN) * k;
+  const int nblk = ceil_div(p.M, BK);
+  int nsplit = ceil_div(148, tiles);
+  if (nsplit > nblk / 4) nsplit = nblk / 4;
+  if (nsplit < 1) nsplit = 1;
+  p.blocks_per_split = ceil_div(nblk, nsplit);
+  p.nsplit = ceil_div(nblk, p.blocks_per_split);
+  CUtensorMap tmX, tmDY;
+  // a 128-wide ci tile may run past Cin (into the other parity's columns of the pair view or out of
+  // bounds = zeros); those accumulator rows are skipped by the epilogue (ci >= Cin)
+  rc = make_map(&tmX, x, x_inner, x_outer, x_pitch, 64, BK);
+  if (rc) return rc;
+  rc = make_map(&tmDY, dy, gout.C, p.M, gout.C, 64, BK);
+  if (rc) return rc;
+  dim3 grid(p.n_ci_tiles * (gout.C / BN), k, p.nsplit);
+  if (BN == 128) {
+    conv_wgrad_kernel<128, WG_STAGES><<<grid, NTHREADS, smem_bytes<128 * BK * 2, WG_STAGES>(), st>>>(tmX, tmDY, dw, p);
+  } else {
+    conv_wgrad_kernel<64, WG_STAGES><<<grid, NTHREADS, smem_bytes<64 * BK * 2, WG_STAGES>(), st>>>(tmX, tmDY, dw, p);
+  }
+  SSB_LAUNCH_CHECK("conv_wgrad_kernel");
+  return SSB_OK;
+}

@@ -367,6 +367,15 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
   }
 }
 
+int ssb_loss_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(semi_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  if (e != cudaSuccess) {
+    ssb_set_error("ssb_loss_prepare: %s", cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+  }
+  return SSB_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 extern "C" {
 
@@ -453,7 +462,6 @@ int ssb_semi_loss(const float* low_s, const int64_t* target, const float* low_t,
   if (tcap > L) tcap = L;
   const size_t smem = (size_t)tcap * (ncls + 2) * sizeof(float);
   SSB_REQUIRE(smem <= 160 * 1024, "ssb_semi_loss: upsample ratio too large for the staging buffer (%zu bytes)", smem);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(semi_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(ceil_div(Lin, SL_NI), Bl + Bu);
   semi_loss_kernel<<<grid, SL_THREADS, smem, to_stream(stream)>>>(low_s, target, low_t, dlow, sums, Bl, Bu, Lin, L, ncls, mode, thr, sp, scale, align_corners, conf, label, mask, tcap);
   SSB_LAUNCH_CHECK("ssb_semi_loss");

@@ -7,8 +7,8 @@
 
 __global__ void __launch_bounds__(256)
 adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 float* __restrict__ pe, size_t n4, float beta1, float beta2, float eps, float wd,
-                 const ssb_step_params* __restrict__ sp) {
+                 float* __restrict__ pe, size_t n4, float beta1, float omb1, float beta2, float omb2, float eps,
+                 float wd, const ssb_step_params* __restrict__ sp) {
   const float lr = sp->lr;
   const float step_size = lr * sp->inv_bias1;
   const float isb2 = sp->inv_sqrt_bias2;
@@ -30,8 +30,8 @@ adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       P[j] *= decay;
-      M[j] = beta1 * M[j] + (1.0f - beta1) * G[j];
-      V[j] = beta2 * V[j] + (1.0f - beta2) * G[j] * G[j];
+      M[j] = beta1 * M[j] + omb1 * G[j];
+      V[j] = beta2 * V[j] + omb2 * G[j] * G[j];
       const float denom = sqrtf(V[j]) * isb2 + eps;
       P[j] -= step_size * (M[j] / denom);
     }
@@ -89,14 +89,15 @@ __global__ void grad_norm_final_kernel(const double* ws, float* out) { out[0] = 
 
 extern "C" {
 
-int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, size_t n, float beta1, float beta2,
-                  float eps, float weight_decay, const ssb_step_params* sp, ssb_stream_t stream) {
+int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, size_t n, double beta1, double beta2,
+                  double eps, double weight_decay, const ssb_step_params* sp, ssb_stream_t stream) {
   SSB_REQUIRE(p && g && m && v && sp, "ssb_adamw_ema: null pointer");
   SSB_REQUIRE(n > 0 && n % 4 == 0, "ssb_adamw_ema: arena length %zu must be a positive multiple of 4", n);
   const size_t n4 = n / 4;
   long long blocks = ceil_div_ll((long long)n4, 256 * 2);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adamw_ema_kernel<<<(int)blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, p_ema, n4, beta1, beta2, eps, weight_decay, sp);
+  adamw_ema_kernel<<<(int)blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, p_ema, n4, (float)beta1, (float)(1.0 - beta1), (float)beta2,
+                                                                (float)(1.0 - beta2), (float)eps, (float)weight_decay, sp);
   SSB_LAUNCH_CHECK("ssb_adamw_ema");
   return SSB_OK;
 }

@@ -50,7 +50,7 @@ class RepackDesc(C.Structure):
 
 assert C.sizeof(StepParams) == 64 and C.sizeof(RepackDesc) == 40 and C.sizeof(Geom) == 16
 
-_P, _I, _F, _SZ = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+_P, _I, _F, _SZ, _D = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_double
 _BNP = C.POINTER(BN)
 
 # name -> argtypes (restype is always int unless listed in _RESTYPES); this table is also what
@@ -60,6 +60,7 @@ SIGNATURES = {
     "ssb_last_error": [],
     "ssb_device_check": [],
     "ssb_launch_count": [],
+    "ssb_prepare": [],
     "ssb_memset_zero": [_P, _SZ, _P],
     "ssb_stem_conv_fwd": [_P, _P, _P, _I, _I, Geom, _I, _P],
     "ssb_stem_conv_wgrad": [_P, _P, _P, _I, _I, Geom, _I, _P],
@@ -80,7 +81,7 @@ SIGNATURES = {
     "ssb_upsample_bwd": [_P, _P, _I, _I, _I, _I, _I, _P],
     "ssb_pseudo_label": [_P, _F, _P, _P, _P, _I, _I, _I, _P],
     "ssb_semi_loss": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P],
-    "ssb_adamw_ema": [_P, _P, _P, _P, _P, _SZ, _F, _F, _F, _F, _P, _P],
+    "ssb_adamw_ema": [_P, _P, _P, _P, _P, _SZ, _D, _D, _D, _D, _P, _P],
     "ssb_ema": [_P, _P, _SZ, _P, _P],
     "ssb_ema_i64": [_P, _P, _SZ, _P, _P],
     "ssb_grad_norm": [_P, _SZ, _P, _P, _P],
@@ -110,6 +111,17 @@ def load(path: Optional[str] = None) -> C.CDLL:
     if path is None:
         _lib = lib
     return lib
+
+
+_prepared = False
+
+
+def prepare() -> None:
+    """One-time device setup (ssb_prepare); also verifies the device is sm_100."""
+    global _prepared
+    if not _prepared:
+        check(load().ssb_prepare(), "ssb_prepare")
+        _prepared = True
 
 
 def check(status: int, what: str = "") -> None:

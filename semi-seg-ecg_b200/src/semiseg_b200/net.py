@@ -290,6 +290,7 @@ class NetPlan:
 
     def __init__(self, weights: WeightSet, dtype: int, B: int, L: int, train: bool, algo: Optional[int] = None,
                  grads: Optional[torch.Tensor] = None, sp_ptr: int = 0):
+        _lib.prepare()
         self.w = weights
         self.sh = weights.shadow(dtype)
         self.lay = weights.layout

@@ -36,8 +36,8 @@ def batches(seed0, n, Bl, Bu, C, L):
 
 
 def rel_err(a, b):
-    a = torch.as_tensor(a).double().flatten()
-    b = torch.as_tensor(b).double().flatten()
+    a = torch.as_tensor(a).detach().double().flatten().cpu()
+    b = torch.as_tensor(b).detach().double().flatten().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
