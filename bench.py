@@ -184,6 +184,14 @@ def run_b200(args):
     for i in range(max(args.warmup, 3)):
         step_from(devb[i % pool])
     eng.read_stats()
+    if args.profile_mode:      # plain launch sequence for ncu: K more steps, nothing else
+        torch.cuda.synchronize()
+        for i in range(args.steps):
+            step_from(devb[i % pool])
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(json.dumps({"profile_mode": True, "steps": args.steps, "launches_per_step": eng.launches_per_step}))
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -366,6 +374,7 @@ def main():
                     "0: per-rank BN (ddp.sync_bn: false)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true", help="warm-up + K plain steps only (for ncu)")
     a = ap.parse_args()
     if a.impl == "reference":
         a.steps = a.steps or 10

@@ -228,6 +228,7 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
             o = q(F.conv1d(h, sd[pre + ".conv1.weight"], None, stride=s, padding=1))
             tap(pre + ".conv1", o)
             o = q(torch.relu(batchnorm(o, sd, pre + ".bn1", train, new_buffers)))
+            tap(pre + ".relu1", o)
             o = q(F.conv1d(o, sd[pre + ".conv2.weight"], None, stride=1, padding=1))
             tap(pre + ".conv2", o)
             o = batchnorm(o, sd, pre + ".bn2", train, new_buffers)

@@ -450,6 +450,10 @@ __global__ void zero_parity_rows_sm100(T* out, int rows, int N, int parity) {
 }
 
 int ssb_sm100_prepare() {
+  if (!get_encode()) {   // resolve the driver entry point outside of any stream capture
+    ssb_set_error("ssb_sm100_prepare: cuTensorMapEncodeTiled entry point not available");
+    return SSB_ERR_CUDA;
+  }
   cudaError_t e = cudaSuccess;
   e = cudaFuncSetAttribute(conv_tn_kernel<128, TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            smem_bytes<128 * BK * 2, TN_STAGES>());

@@ -302,6 +302,7 @@ class NetPlan:
         self.grads = grads
         self.sp_ptr = sp_ptr
         self.drop_mask_ptr = 0   # tests may inject an explicit keep-mask (u8 [B, Lh, Ch])
+        self.debug = None        # tests: dict that receives clones of the block-output gradients
         self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
         if algo is None:
             algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
@@ -515,6 +516,8 @@ class NetPlan:
                 xin, gin = self.blk_bufs[bi - 1]["out"], self.g_stage[lay.blocks[bi - 1].stage]
             sc = self._scratch[(gout.pitch, gout.len, gout.C)]
             sci = self._scratch[(gin.pitch, gin.len, gin.C)]
+            if self.debug is not None:
+                self.debug[bd.prefix] = self.to_ncl(G, gout)
             # destination for the gradient w.r.t. the block input
             if sci is sc:
                 Gin = sc["gE"] if G is sc["gA"] else sc["gA"]
@@ -535,6 +538,10 @@ class NetPlan:
                 self._sync_bwd(bd.bn2)
                 call("ssb_bn_bwd_apply", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
                      dc2.data_ptr(), None, None, None, Gin.data_ptr(), gout, dt, st)
+            if self.debug is not None:
+                self.debug[bd.prefix + ".conv2"] = self.to_ncl(dc2, gout)
+                if bd.convd is not None:
+                    self.debug[bd.prefix + ".downsample.0"] = self.to_ncl(dcd, gout)
             c = bd.conv2
             call("ssb_conv1d_dgrad", dc2.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), da1.data_ptr(), gout, gout,
                  c.k, c.stride, 0, dt, self._algo_for(c), st)
@@ -547,6 +554,8 @@ class NetPlan:
             self._sync_bwd(bd.bn1)
             call("ssb_bn_bwd_apply", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
                  dc1.data_ptr(), None, None, None, None, gout, dt, st)
+            if self.debug is not None:
+                self.debug[bd.prefix + ".conv1"] = self.to_ncl(dc1, gout)
             c = bd.conv1
             acc = 0 if bd.convd is not None else 1   # identity residual: Gin already holds g
             call("ssb_conv1d_dgrad", dc1.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), Gin.data_ptr(), gin, gout,

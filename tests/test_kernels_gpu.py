@@ -22,6 +22,11 @@ TOL = {_lib.F32: 1e-5, _lib.BF16: 2e-2}
 TDT = {_lib.F32: torch.float32, _lib.BF16: torch.bfloat16}
 
 
+@pytest.fixture(autouse=True, scope="module")
+def _prepare_device():
+    _lib.prepare()      # ssb_prepare(): device check + opt-in shared-memory sizes
+
+
 def st():
     return torch.cuda.current_stream().cuda_stream
 
