@@ -73,7 +73,8 @@ __device__ __forceinline__ void bn_coeffs(const ssb_bn& bn, int c, int C, int tr
     double var = bn.sums[C + c] * inv_n - m * m;
     if (var < 0.0) var = 0.0;
     mean = (float)m;
-    invstd = (float)(1.0 / sqrt(var + BN_EPS));
+    invstd = rsqrtf((float)var + (float)BN_EPS);
+    invstd = invstd * (1.5f - 0.5f * ((float)var + (float)BN_EPS) * invstd * invstd);   // one Newton step: full fp32 accuracy
     if (writer) {
       bn.mean_invstd[c] = mean;
       bn.mean_invstd[C + c] = invstd;
@@ -599,7 +600,7 @@ static int check_geom(const char* who, const ssb_geom& g, int vec) {
 }
 
 static int ew_blocks(long long total_vec) {
-  long long b = ceil_div_ll(total_vec, (long long)BN_THREADS * 4);
+  long long b = ceil_div_ll(total_vec, (long long)BN_THREADS * 2);
   if (b < 1) b = 1;
   if (b > 148 * 8) b = 148 * 8;
   return (int)b;

@@ -224,20 +224,35 @@ wgrad_kernel(const T* __restrict__ X, const T* __restrict__ dY, float* __restric
 
 // ---------------------------------------------------------------------------------------
 // weight repack (all convs, one launch): fp32 [Cout][Cin][k] -> T [k][Cin][Cout], T [k][Cout][Cin]
+// one block = 32 co x 32 ci tile of one conv, transposed through shared memory so that both
+// outputs are written in 64-byte runs
 // ---------------------------------------------------------------------------------------
 template <typename T>
-__global__ void repack_kernel(const ssb_repack_desc* __restrict__ table) {
+__global__ void __launch_bounds__(256) repack_kernel(const ssb_repack_desc* __restrict__ table, int max_tiles) {
   const ssb_repack_desc d = table[blockIdx.y];
-  const int total = d.Cout * d.Cin * d.k;
+  const int tco = (d.Cout + 31) / 32, tci = (d.Cin + 31) / 32;
+  __shared__ float sw[32][32 * 3 + 1];
   T* kio = (T*)d.w_kio;
   T* koi = (T*)d.w_koi;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int j = idx % d.k;
-    const int ci = (idx / d.k) % d.Cin;
-    const int co = idx / (d.k * d.Cin);
-    const T v = from_f<T>(d.w[idx]);
-    kio[((size_t)j * d.Cin + ci) * d.Cout + co] = v;
-    koi[((size_t)j * d.Cout + co) * d.Cin + ci] = v;
+  for (int tile = blockIdx.x; tile < tco * tci; tile += gridDim.x) {
+    const int co0 = (tile / tci) * 32, ci0 = (tile % tci) * 32;
+    const int nci = min(32, d.Cin - ci0), nco = min(32, d.Cout - co0);
+    const int rowlen = nci * d.k;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * rowlen; idx += 256) {
+      const int r = idx / rowlen, c = idx - r * rowlen;
+      if (r < nco) sw[r][c] = d.w[((size_t)(co0 + r) * d.Cin + ci0) * d.k + c];
+    }
+    __syncthreads();
+    for (int j = 0; j < d.k; ++j) {
+      for (int idx = threadIdx.x; idx < 32 * 32; idx += 256) {
+        const int a = idx >> 5, b = idx & 31;
+        // koi[j][co0+a][ci0+b]
+        if (a < nco && b < nci) koi[((size_t)j * d.Cout + co0 + a) * d.Cin + ci0 + b] = from_f<T>(sw[a][b * d.k + j]);
+        // kio[j][ci0+a][co0+b]
+        if (a < nci && b < nco) kio[((size_t)j * d.Cin + ci0 + a) * d.Cout + co0 + b] = from_f<T>(sw[b][a * d.k + j]);
+      }
+    }
   }
 }
 
@@ -500,10 +515,11 @@ int ssb_conv1d_wgrad(const void* x, const void* dy, float* dw, ssb_geom gin, ssb
 
 int ssb_weight_repack(const ssb_repack_desc* table_dev, int n, int max_elems, int dtype, ssb_stream_t stream) {
   SSB_REQUIRE(table_dev && n > 0 && max_elems > 0, "ssb_weight_repack: bad arguments");
-  int bx = ceil_div(max_elems, 256 * 8);
-  if (bx > 64) bx = 64;
+  int bx = ceil_div(max_elems, 32 * 32 * 3);
+  if (bx > 128) bx = 128;
+  if (bx < 1) bx = 1;
   dim3 grid(bx, n);
-  SSB_DISPATCH_DTYPE(dtype, T, { repack_kernel<T><<<grid, 256, 0, to_stream(stream)>>>(table_dev); })
+  SSB_DISPATCH_DTYPE(dtype, T, { repack_kernel<T><<<grid, 256, 0, to_stream(stream)>>>(table_dev, bx); })
   SSB_LAUNCH_CHECK("ssb_weight_repack");
   return SSB_OK;
 }

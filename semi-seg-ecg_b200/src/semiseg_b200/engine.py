@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -80,11 +81,21 @@ class StepEngine:
         self.ema_first = True
         # plans
         self.dtype = dtype
-        self.plan_s = NetPlan(weights, dtype, S, L, True, algo, grads=state.grads, sp_ptr=self.sp_dev.data_ptr())
+        # concurrency inside the step: weight-gradient GEMMs and the pseudo-label forward are off the
+        # critical path -> own streams, forked/joined with events (captured as graph branches)
+        self.multi_stream = bool(int(os.environ.get("SSB_MULTI_STREAM", "1")))
+        self.wgrad_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
+        self.teacher_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
+        self.plan_s = NetPlan(weights, dtype, S, L, True, algo, grads=state.grads, sp_ptr=self.sp_dev.data_ptr(),
+                              wgrad_stream=self.wgrad_stream)
         self.plan_t: Optional[NetPlan] = None
+        self.bufs_snap: Optional[torch.Tensor] = None
         if self.mode != _lib.LOSS_SUP:
             tw = teacher if algorithm == "mean_teacher" else weights
-            self.plan_t = NetPlan(tw, dtype, self.Bu, L, False, algo)
+            if algorithm == "fixmatch" and self.multi_stream:
+                # self-eval pass must see the running stats from BEFORE this step's update (fixmatch.py:87-93)
+                self.bufs_snap = torch.empty_like(weights.bufs)
+            self.plan_t = NetPlan(tw, dtype, self.Bu, L, False, algo, bufs=self.bufs_snap)
         if self.sync_bn:
             # SyncBatchNorm (fixmatch.py:290-291): statistic arenas are all-reduced layer by layer
             for s in self.plan_s._bn_structs.values():
@@ -157,8 +168,18 @@ class StepEngine:
         if self.plan_t is not None:
             if self.algorithm == "mean_teacher":
                 self.plan_t.sh.repack(st)
-            low_t = self.plan_t.forward(self.x_uw, st, train_mode=False)
+            if self.teacher_stream is not None:
+                if self.bufs_snap is not None:
+                    self.bufs_snap.copy_(w.bufs, non_blocking=True)
+                fork = torch.cuda.Event()
+                fork.record()
+                self.teacher_stream.wait_event(fork)
+                low_t = self.plan_t.forward(self.x_uw, self.teacher_stream.cuda_stream, train_mode=False)
+            else:
+                low_t = self.plan_t.forward(self.x_uw, st, train_mode=False)
         self.plan_s.forward(self.x_s, st, train_mode=True)
+        if self.plan_t is not None and self.teacher_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.teacher_stream)
         low_s = self.plan_s.low
         m = self.mat
         call("ssb_semi_loss", low_s.data_ptr(), self.y_l.data_ptr(), low_t.data_ptr() if low_t is not None else None,

@@ -289,7 +289,8 @@ class NetPlan:
     """Static buffers + kernel schedule for one (weights, batch, length, dtype, mode)."""
 
     def __init__(self, weights: WeightSet, dtype: int, B: int, L: int, train: bool, algo: Optional[int] = None,
-                 grads: Optional[torch.Tensor] = None, sp_ptr: int = 0):
+                 grads: Optional[torch.Tensor] = None, sp_ptr: int = 0, bufs: Optional[torch.Tensor] = None,
+                 wgrad_stream: Optional[torch.cuda.Stream] = None):
         _lib.prepare()
         self.w = weights
         self.sh = weights.shadow(dtype)
@@ -301,6 +302,11 @@ class NetPlan:
         self.tdt = _torch_dtype(self.dtype)
         self.grads = grads
         self.sp_ptr = sp_ptr
+        # BN running-stat arena this plan reads/updates (an eval plan may be pointed at a snapshot)
+        self.bufs = bufs if bufs is not None else weights.bufs
+        # weight-gradient GEMMs are off the critical path of backward: issue them on a second stream
+        self.wgrad_stream = wgrad_stream
+        self._pending_reads: Dict[int, torch.cuda.Event] = {}
         self.drop_mask_ptr = 0   # tests may inject an explicit keep-mask (u8 [B, Lh, Ch])
         self.debug = None        # tests: dict that receives clones of the block-output gradients
         self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
@@ -384,8 +390,8 @@ class NetPlan:
         s = BN()
         s.gamma = w.params.data_ptr() + 4 * b.goff
         s.beta = w.params.data_ptr() + 4 * b.boff
-        s.running_mean = w.bufs.data_ptr() + 4 * b.roff
-        s.running_var = w.bufs.data_ptr() + 4 * (b.roff + b.C)
+        s.running_mean = self.bufs.data_ptr() + 4 * b.roff
+        s.running_var = self.bufs.data_ptr() + 4 * (b.roff + b.C)
         s.num_batches_tracked = (w.nbt.data_ptr() + 8 * b.index) if w.nbt.dtype == torch.int64 else None
         s.sums = self.sums.data_ptr() + 8 * b.soff
         s.mean_invstd = self.mean_invstd.data_ptr() + 4 * b.soff
@@ -419,6 +425,35 @@ class NetPlan:
         if self.sync_hook is not None:
             last = last or first
             self.sync_hook(self.bwd_sums[first.soff: last.soff + 2 * last.C])
+
+    def _wgrad(self, c: ConvDesc, x, dy, gin: Geom, gout: Geom, st: int):
+        """dW += x^T dy.  With a wgrad stream: fork after dy is produced, remember that dy is still
+        being read so that the next writer of that scratch buffer waits (WAR)."""
+        if self.wgrad_stream is None:
+            call("ssb_conv1d_wgrad", x.data_ptr(), dy.data_ptr(), self._g(c), gin, gout, c.k, c.stride, self.dtype,
+                 self._algo_for(c), st)
+            return
+        ready = torch.cuda.Event()
+        ready.record()
+        self.wgrad_stream.wait_event(ready)
+        call("ssb_conv1d_wgrad", x.data_ptr(), dy.data_ptr(), self._g(c), gin, gout, c.k, c.stride, self.dtype,
+             self._algo_for(c), self.wgrad_stream.cuda_stream)
+        done = torch.cuda.Event()
+        done.record(self.wgrad_stream)
+        self._pending_reads[dy.data_ptr()] = done
+
+    def _before_write(self, *bufs):
+        for b in bufs:
+            if b is None:
+                continue
+            ev = self._pending_reads.pop(b.data_ptr(), None)
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+
+    def _join_wgrad(self):
+        if self.wgrad_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.wgrad_stream)
+            self._pending_reads.clear()
 
     def zero_stats(self, st: int):
         call("ssb_memset_zero", self.sums.data_ptr(), self.sums.numel() * 8, st)
@@ -502,8 +537,7 @@ class NetPlan:
         G = sc_f["gA"]
         call("ssb_conv1d_dgrad", sc_h["gB"].data_ptr(), self.sh.kio_ptr(hc), self.sh.koi_ptr(hc), G.data_ptr(), gfeat,
              self.g_head, hc.k, hc.stride, 0, dt, self._algo_for(hc), st)
-        call("ssb_conv1d_wgrad", self.feat.data_ptr(), sc_h["gB"].data_ptr(), self._g(hc), gfeat, self.g_head, hc.k,
-             hc.stride, dt, self._algo_for(hc), st)
+        self._wgrad(hc, self.feat, sc_h["gB"], gfeat, self.g_head, st)
 
         # blocks in reverse
         nblk = len(lay.blocks)
@@ -525,6 +559,7 @@ class NetPlan:
                 Gin = sci["gA"]
             dc2, dcd, da1 = sc["gB"], sc["gC"], sc["gD"]
             out, c2 = bufs["out"], bufs["c2"]
+            self._before_write(dc2, dcd)
             if bd.convd is not None:
                 cd = bufs["cd"]
                 call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
@@ -545,10 +580,10 @@ class NetPlan:
             c = bd.conv2
             call("ssb_conv1d_dgrad", dc2.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), da1.data_ptr(), gout, gout,
                  c.k, c.stride, 0, dt, self._algo_for(c), st)
-            call("ssb_conv1d_wgrad", bufs["a1"].data_ptr(), dc2.data_ptr(), self._g(c), gout, gout, c.k, c.stride, dt,
-                 self._algo_for(c), st)
+            self._wgrad(c, bufs["a1"], dc2, gout, gout, st)
             # bn1 + relu backward -> dc1 (reuses gB: dc2 is dead)
             dc1 = dc2
+            self._before_write(dc1)
             call("ssb_bn_bwd_reduce", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
                  None, None, gout, dt, st)
             self._sync_bwd(bd.bn1)
@@ -560,15 +595,14 @@ class NetPlan:
             acc = 0 if bd.convd is not None else 1   # identity residual: Gin already holds g
             call("ssb_conv1d_dgrad", dc1.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), Gin.data_ptr(), gin, gout,
                  c.k, c.stride, acc, dt, self._algo_for(c), st)
-            call("ssb_conv1d_wgrad", xin.data_ptr(), dc1.data_ptr(), self._g(c), gin, gout, c.k, c.stride, dt,
-                 self._algo_for(c), st)
+            self._wgrad(c, xin, dc1, gin, gout, st)
             if bd.convd is not None:
                 c = bd.convd
                 call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), Gin.data_ptr(), gin, gout,
                      c.k, c.stride, 1, dt, self._algo_for(c), st)
-                call("ssb_conv1d_wgrad", xin.data_ptr(), dcd.data_ptr(), self._g(c), gin, gout, c.k, c.stride, dt,
-                     self._algo_for(c), st)
+                self._wgrad(c, xin, dcd, gin, gout, st)
             G = Gin
+        self._join_wgrad()
         # stem tail + stem conv weight gradient
         call("ssb_stem_bwd_reduce", G.data_ptr(), self.c0.data_ptr(), self.bn(lay.stem_bn), self.g_stem, self.g_pool, dt, st)
         self._sync_bwd(lay.stem_bn)

@@ -280,9 +280,11 @@ def test_full_size_fp32_vs_oracle(golden):
     assert rel_err(gflat, rflat) < 1e-5
     for k in ("loss_total", "loss_x", "loss_u_s", "mask_ratio"):
         assert abs(s[k] - s64[k]) < 1e-5 * max(1.0, abs(s64[k])), (k, s[k], s64[k])
+    # updated weights: the first Adam step is g/(|g|+eps) -- elements whose gradient is a near-cancelling sum
+    # of magnitude ~eps are amplified, hence 5e-5 rather than 1e-5
     sd = model.state_dict()
     for n in t64.pnames:
-        assert rel_err(sd[n], t64.sd[n]) < 1e-5, n
+        assert rel_err(sd[n], t64.sd[n]) < 5e-5, n
 
 
 def test_full_size_fp32_golden_scalars(golden):
