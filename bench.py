@@ -114,6 +114,19 @@ def launch_cost(name, args, es):
     return 0.0, 0.0, name[4:]
 
 
+def _finish(world):
+    """Multi-rank teardown: destroying an NCCL communicator while CUDA graphs that captured collectives
+    on it are still alive can hang, so synchronise, barrier and leave without the destructor."""
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_b200(args):
     import torch.distributed as dist
     from algorithms.base import init_model_from_cfg
@@ -190,7 +203,8 @@ def run_b200(args):
             step_from(devb[i % pool])
         torch.cuda.synchronize()
         if rank == 0:
-            print(json.dumps({"profile_mode": True, "steps": args.steps, "launches_per_step": eng.launches_per_step}))
+            print(json.dumps({"profile_mode": True, "steps": args.steps, "launches_per_step": eng.launches_per_step}), flush=True)
+        _finish(world)
         return
     sampler = ClockSampler(local)
     if rank == 0:
@@ -259,9 +273,7 @@ def run_b200(args):
                      "peak_source": peaks["src"], "timing": "CUDA events around each launch, eager replay of the same step"})
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        _finish(world)
         return
     # working set, to justify the L2 policy
     plan = eng.plan_s
@@ -290,10 +302,8 @@ def run_b200(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    _finish(world)
 
 
 def cpu_step_fn(workload):

@@ -53,7 +53,16 @@ class StepEngine:
         self.use_graph = use_graph
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
-        self.sync_bn = sync_bn and self.world > 1
+        # SSB_FORCE_COLLECTIVES=1: issue the collectives even at world size 1 (exercises the capture path on one GPU)
+        self.collectives = process_group is not None and (self.world > 1 or bool(os.environ.get("SSB_FORCE_COLLECTIVES")))
+        self.sync_bn = sync_bn and self.collectives
+        if self.collectives:
+            # create the NCCL communicator OUTSIDE of any stream capture (lazy init inside a capture deadlocks)
+            warm = torch.zeros(8, device=weights.device)
+            torch.distributed.all_reduce(warm, group=process_group)
+            warm64 = torch.zeros(8, dtype=torch.float64, device=weights.device)
+            torch.distributed.all_reduce(warm64, group=process_group)
+            torch.cuda.synchronize()
         self.seed = seed
         dev = self.device
         S = self.Bl + self.Bu
@@ -188,7 +197,7 @@ class StepEngine:
              m["conf"].data_ptr() if m else None, m["label"].data_ptr() if m else None,
              m["mask"].data_ptr() if m else None, st)
         self.plan_s.backward(self.plan_s.dlow, st)
-        if self.world > 1:
+        if self.collectives:
             torch.distributed.all_reduce(state.grads, group=self.pg)
         if self.cfg.get("grad_norm", False):
             call("ssb_memset_zero", self.gnorm_ws.data_ptr(), 8, st)

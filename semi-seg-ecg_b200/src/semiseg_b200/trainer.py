@@ -8,6 +8,7 @@ loss sums are read back asynchronously every `print_freq` steps.
 from __future__ import annotations
 
 import math
+import os
 import sys
 import time
 from typing import Dict, Iterable, Optional
@@ -45,7 +46,8 @@ def get_engine(algorithm: str, model, teacher, Bl: int, Bu: int, L: int, dtype: 
     key = (algorithm, Bl, Bu, L, dtype, use_graph, algo, id(rt_t))
     eng = rt.engines.get(key)
     if eng is None:
-        pg = dist.group.WORLD if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        pg = dist.group.WORLD if (dist.is_available() and dist.is_initialized() and
+                                  (dist.get_world_size() > 1 or os.environ.get("SSB_FORCE_COLLECTIVES"))) else None
         cfg = dict(config)
         if optimizer is not None:
             g = optimizer.param_groups[0]

@@ -1,0 +1,57 @@
+"""torchrun --nproc-per-node 2 tools/dp_check.py : k-rank FixMatch steps (SyncBN on, gradient all-reduce)
+== single-process steps on the concatenated batch.  fp32 path."""
+import os, sys
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, REPO); sys.path.insert(0, os.path.join(REPO, "semi-seg-ecg_b200", "src")); sys.path.insert(0, os.path.join(REPO, "tests"))
+import numpy as np, torch, torch.distributed as dist
+from helpers import TRAIN_CFG, batches, model_cfg, rel_err
+from algorithms.base import init_model_from_cfg
+from semiseg_b200 import _lib
+from semiseg_b200.engine import StepEngine
+from semiseg_b200.trainer import get_engine
+
+import traceback
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+cfg = dict(TRAIN_CFG, conf_thresh=0.3)
+per = 2
+data = batches(900, 3, per * world, per * world, 1, 2500)      # global batches
+use_graph = bool(int(os.environ.get("DP_GRAPH", "1")))
+
+def run(sync_bn, sharded):
+    torch.manual_seed(0)
+    model = init_model_from_cfg(model_cfg(1, 64, 64, 128, 0.0)).to("cuda")
+    model.sync_bn = sync_bn
+    rt = model.runtime(); rt.ensure()
+    B = per if sharded else per * world
+    eng = StepEngine(rt.weights, rt.state, _lib.F32, "fixmatch", B, B, 2500, cfg, use_graph=use_graph,
+                     process_group=dist.group.WORLD if sharded else None, sync_bn=sync_bn)
+    sl = slice(rank * per, (rank + 1) * per) if sharded else slice(None)
+    for lab, unl in data:
+        eng.load_batch(lab["ecg"][sl], lab["target"][sl], unl["ecg"][sl], unl["ecg_aug"][sl])
+        eng.step(5e-4)
+    stats = eng.read_stats()
+    return {k: v.clone() for k, v in model.state_dict().items()}, stats
+
+try:
+    sd_dp, st_dp = run(True, True)
+    sd_1, st_1 = run(False, False)
+except Exception:
+    traceback.print_exc()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(3)
+worst = max(rel_err(sd_dp[k].double(), sd_1[k].double()) for k in sd_1 if "tracked" not in k)
+# mean over ranks of the per-rank losses == global loss (equal shards)
+t = torch.tensor([st_dp[-1]["loss_total"], st_dp[-1]["mask_ratio"]], device="cuda", dtype=torch.float64)
+dist.all_reduce(t); t /= world
+if rank == 0:
+    print(f"DP{world} (SyncBN, graph={use_graph}) vs single process on the concatenated batch: worst state_dict rel err {worst:.2e}; "
+          f"loss {float(t[0]):.6f} vs {st_1[-1]['loss_total']:.6f}; mask_ratio {float(t[1]):.4f} vs {st_1[-1]['mask_ratio']:.4f}")
+    assert worst < 2e-3, worst   # 3 Adam steps amplify summation-order differences (sign-like first updates)
+    assert abs(float(t[0]) - st_1[-1]["loss_total"]) < 1e-4
+    print("DP equivalence OK")
+torch.cuda.synchronize()
+dist.barrier()
+sys.stdout.flush()
+os._exit(0)
