@@ -1,10 +1,12 @@
 // Library-level entry points of libsemiseg_b200: version, error reporting, device check.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 
 std::atomic<long long> g_ssb_launches{0};
+int g_ssb_pdl = 0;   // env SSB_PDL: see common.cuh
 static thread_local char g_err[512] = "";
 
 void ssb_set_error(const char* fmt, ...) {
@@ -21,6 +23,8 @@ int ssb_loss_prepare();
 extern "C" {
 
 int ssb_prepare(void) {
+  const char* pdl = getenv("SSB_PDL");
+  if (pdl) g_ssb_pdl = atoi(pdl);
   int rc = ssb_device_check();
   if (rc) return rc;
   if ((rc = ssb_simt_prepare())) return rc;

@@ -15,6 +15,8 @@
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restrict__ x, int rows, int C,
                                                               double* __restrict__ sums, int rpb) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   const int ncg = C / V;
   const int cgb = ncg < BN_THREADS ? ncg : BN_THREADS;
@@ -99,6 +101,8 @@ template <typename T, int RES>
 __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
                                                                 T* __restrict__ y, ssb_bn bn, ssb_bn bnr,
                                                                 ssb_geom g, int relu, int train) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   extern __shared__ float sm[];
   const int C = g.C;
@@ -163,6 +167,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restr
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) stem_bn_relu_pool_kernel(const T* __restrict__ c0, T* __restrict__ y,
                                                                        ssb_bn bn, ssb_geom gi, ssb_geom go, int train) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   extern __shared__ float sm[];
   const int C = gi.C;
@@ -219,6 +225,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
                                                                    const T* __restrict__ y, const T* __restrict__ x,
                                                                    const T* __restrict__ xr, ssb_bn bn, ssb_bn bnr,
                                                                    int rows, int C, int rpb) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   const int ncg = C / V;
   const int cgb = ncg < BN_THREADS ? ncg : BN_THREADS;
@@ -321,6 +329,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
                                                                   const T* __restrict__ xr, T* __restrict__ dx,
                                                                   T* __restrict__ dxr, T* __restrict__ gid, ssb_bn bn,
                                                                   ssb_bn bnr, ssb_geom g) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   extern __shared__ float sm[];
   const int C = g.C;
@@ -344,8 +354,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
     sK1[c] = (float)(sg * inv_n);
     sK2[c] = (float)(sgx * inv_n);
     if (blockIdx.x == 0) {
-      bn.dgamma[c] = (float)sgx;
-      bn.dbeta[c] = (float)sg;
+      // SyncBN: the sums are global totals and the gradient arena is averaged over ranks afterwards,
+      // so each rank contributes total / world
+      const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
+      bn.dgamma[c] = (float)(sgx * gsc);
+      bn.dbeta[c] = (float)(sg * gsc);
     }
     if (RES == 2) {
       const float meanr = bnr.mean_invstd[c], invr = bnr.mean_invstd[C + c];
@@ -355,8 +368,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
       rK0[c] = bnr.gamma[c] * invr;
       rK2[c] = (float)(sgxr * inv_n);
       if (blockIdx.x == 0) {
-        bnr.dgamma[c] = (float)sgxr;
-        bnr.dbeta[c] = (float)sg;
+        const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
+        bnr.dgamma[c] = (float)(sgxr * gsc);
+        bnr.dbeta[c] = (float)(sg * gsc);
       }
     }
   }
@@ -491,6 +505,8 @@ __device__ __forceinline__ void stem_masked_grad(const T* __restrict__ c0, const
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) stem_bwd_reduce_kernel(const T* __restrict__ gp, const T* __restrict__ c0,
                                                                      ssb_bn bn, ssb_geom gi, ssb_geom go) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   extern __shared__ float sm[];
   const int C = gi.C;
@@ -538,6 +554,8 @@ template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) stem_bwd_apply_kernel(const T* __restrict__ gp, const T* __restrict__ c0,
                                                                     T* __restrict__ dc0, ssb_bn bn, ssb_geom gi,
                                                                     ssb_geom go) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Vec<T>::N;
   extern __shared__ float sm[];
   const int C = gi.C;
@@ -557,8 +575,9 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bwd_apply_kernel(const T* __r
     sK1[c] = (float)(bn.bwd_sums[c] * inv_n);
     sK2[c] = (float)(bn.bwd_sums[C + c] * inv_n);
     if (blockIdx.x == 0) {
-      bn.dgamma[c] = (float)bn.bwd_sums[C + c];
-      bn.dbeta[c] = (float)bn.bwd_sums[c];
+      const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
+      bn.dgamma[c] = (float)(bn.bwd_sums[C + c] * gsc);
+      bn.dbeta[c] = (float)(bn.bwd_sums[c] * gsc);
     }
   }
   __syncthreads();
@@ -609,9 +628,9 @@ static int ew_blocks(long long total_vec) {
 static const ssb_bn kNoBn = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
 
 #define SSB_RED(G2, Y, R) \
-  bn_bwd_reduce_kernel<T, G2, Y, R><<<grid, BN_THREADS, 0, st>>>((const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, *bn, br, rows, g.C, rpb)
+  ssb_launch(bn_bwd_reduce_kernel<T, G2, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, *bn, br, rows, g.C, rpb)
 #define SSB_APP(G2, Y, R) \
-  bn_bwd_apply_kernel<T, G2, Y, R><<<blocks, BN_THREADS, smem, st>>>((const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g)
+  ssb_launch(bn_bwd_apply_kernel<T, G2, Y, R>, dim3(blocks), dim3(BN_THREADS), smem, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g)
 
 extern "C" {
 
@@ -628,7 +647,7 @@ int ssb_bn_stats(const void* x, ssb_geom g, double* sums, int dtype, ssb_stream_
     int rpb = ceil_div(rows, 148 * 4);
     if (rpb < nrl * 4) rpb = nrl * 4;
     dim3 grid(ceil_div(rows, rpb), ceil_div(ncg, cgb));
-    bn_stats_kernel<T><<<grid, BN_THREADS, 0, to_stream(stream)>>>((const T*)x, rows, g.C, sums, rpb);
+    ssb_launch(bn_stats_kernel<T>, dim3(grid), dim3(BN_THREADS), 0, to_stream(stream), (const T*)x, rows, g.C, sums, rpb);
   })
   SSB_LAUNCH_CHECK("ssb_bn_stats");
   return SSB_OK;
@@ -647,11 +666,11 @@ int ssb_bn_act_fwd(const void* x, const ssb_bn* bn, const void* res, const ssb_b
     const int blocks = ew_blocks(total);
     cudaStream_t st = to_stream(stream);
     if (mode == 0)
-      bn_act_fwd_kernel<T, 0><<<blocks, BN_THREADS, smem, st>>>((const T*)x, nullptr, (T*)y, *bn, kNoBn, g, relu, train);
+      ssb_launch(bn_act_fwd_kernel<T, 0>, dim3(blocks), dim3(BN_THREADS), smem, st, (const T*)x, nullptr, (T*)y, *bn, kNoBn, g, relu, train);
     else if (mode == 1)
-      bn_act_fwd_kernel<T, 1><<<blocks, BN_THREADS, smem, st>>>((const T*)x, (const T*)res, (T*)y, *bn, kNoBn, g, relu, train);
+      ssb_launch(bn_act_fwd_kernel<T, 1>, dim3(blocks), dim3(BN_THREADS), smem, st, (const T*)x, (const T*)res, (T*)y, *bn, kNoBn, g, relu, train);
     else
-      bn_act_fwd_kernel<T, 2><<<blocks, BN_THREADS, smem, st>>>((const T*)x, (const T*)res, (T*)y, *bn, *bn_res, g, relu, train);
+      ssb_launch(bn_act_fwd_kernel<T, 2>, dim3(blocks), dim3(BN_THREADS), smem, st, (const T*)x, (const T*)res, (T*)y, *bn, *bn_res, g, relu, train);
   })
   SSB_LAUNCH_CHECK("ssb_bn_act_fwd");
   return SSB_OK;
@@ -669,7 +688,7 @@ int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, ssb_geo
   const size_t smem = (size_t)2 * gin.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
     const long long total = (long long)gout.B * gout.pitch * (gout.C / Vec<T>::N);
-    stem_bn_relu_pool_kernel<T><<<ew_blocks(total), BN_THREADS, smem, to_stream(stream)>>>((const T*)c0, (T*)y, *bn, gin, gout, train);
+    ssb_launch(stem_bn_relu_pool_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)c0, (T*)y, *bn, gin, gout, train);
   })
   SSB_LAUNCH_CHECK("ssb_stem_bn_relu_pool_fwd");
   return SSB_OK;
@@ -750,7 +769,7 @@ int ssb_stem_bwd_reduce(const void* gp, const void* c0, const ssb_bn* bn, ssb_ge
   const size_t smem = (size_t)6 * gin.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
     const long long total = (long long)gin.B * gin.len * (gin.C / Vec<T>::N);
-    stem_bwd_reduce_kernel<T><<<ew_blocks(total), BN_THREADS, smem, to_stream(stream)>>>((const T*)gp, (const T*)c0, *bn, gin, gout);
+    ssb_launch(stem_bwd_reduce_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)gp, (const T*)c0, *bn, gin, gout);
   })
   SSB_LAUNCH_CHECK("ssb_stem_bwd_reduce");
   return SSB_OK;
@@ -767,7 +786,7 @@ int ssb_stem_bwd_apply(const void* gp, const void* c0, const ssb_bn* bn, void* d
   const size_t smem = (size_t)6 * gin.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
     const long long total = (long long)gin.B * gin.pitch * (gin.C / Vec<T>::N);
-    stem_bwd_apply_kernel<T><<<ew_blocks(total), BN_THREADS, smem, to_stream(stream)>>>((const T*)gp, (const T*)c0, (T*)dc0, *bn, gin, gout);
+    ssb_launch(stem_bwd_apply_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)gp, (const T*)c0, (T*)dc0, *bn, gin, gout);
   })
   SSB_LAUNCH_CHECK("ssb_stem_bwd_apply");
   return SSB_OK;

@@ -45,6 +45,42 @@ extern std::atomic<long long> g_ssb_launches;
     return SSB_ERR_INVALID;                            \
   }
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------
+// Every kernel is launched with the programmatic-stream-serialization attribute: the next
+// kernel in the stream may be scheduled while this one is still running, and blocks at
+// pdl_wait() until all of this kernel's memory operations are visible.  Kernels call
+// pdl_trigger() first thing and pdl_wait() before their first global-memory access, so launch
+// latency / CTA scheduling / on-chip prologues overlap with the predecessor's tail.
+extern int g_ssb_pdl;
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// g_ssb_pdl (env SSB_PDL): 0 = plain launches, 1 = every launch carries the attribute, 2 = only the
+// kernels with an on-chip prologue worth overlapping (the tcgen05 convs: barrier init, TMEM alloc,
+// tensor-map prefetch), launched through ssb_launch_pro.
+template <int LEVEL, typename... KArgs, typename... Args>
+static inline void ssb_launch_impl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (g_ssb_pdl == 1 || (g_ssb_pdl == 2 && LEVEL == 2)) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline void ssb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  ssb_launch_impl<1>(kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline void ssb_launch_pro(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  ssb_launch_impl<2>(kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+
 static inline cudaStream_t to_stream(ssb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -68,6 +68,8 @@ template <typename T, bool ACC>
 __global__ void __launch_bounds__(TG_THREADS)
 tap_gemm_kernel(const T* __restrict__ A, const T* __restrict__ W, T* __restrict__ Out, int M, int N, int K,
                 int a_rows, int a_mul, TapSpec taps, int o_mul, int o_off, int o_rows, int o_pitch, int o_len) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float As[TG_BK][TG_BM + 4];
   __shared__ float Bs[TG_BK][TG_BN];
   const int tid = threadIdx.x;
@@ -150,6 +152,8 @@ tap_gemm_kernel(const T* __restrict__ A, const T* __restrict__ W, T* __restrict_
 // zero-fill rows of one parity (used when a stride-2 dgrad has no tap for that parity)
 template <typename T>
 __global__ void zero_parity_rows_kernel(T* out, int rows, int N, int parity) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)(rows / 2) * N;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -169,6 +173,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 wgrad_kernel(const T* __restrict__ X, const T* __restrict__ dY, float* __restrict__ dW, int M, int Cin, int Cout,
              int k, int x_rows, int a_mul, TapSpec taps, int nsplit, int rows_per_split) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float Xs[WG_BK][WG_T];
   __shared__ float Ys[WG_BK][WG_T];
   const int tid = threadIdx.x;
@@ -229,6 +235,8 @@ wgrad_kernel(const T* __restrict__ X, const T* __restrict__ dY, float* __restric
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) repack_kernel(const ssb_repack_desc* __restrict__ table, int max_tiles) {
+  pdl_trigger();
+  pdl_wait();
   const ssb_repack_desc d = table[blockIdx.y];
   const int tco = (d.Cout + 31) / 32, tci = (d.Cin + 31) / 32;
   __shared__ float sw[32][32 * 3 + 1];
@@ -266,6 +274,8 @@ template <typename T>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int Cl, int L,
                      ssb_geom g) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int Cs = g.C;
   float* ws = sm;                  // [Cl*7][Cs]
@@ -325,6 +335,8 @@ template <typename T>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int Cl, int L,
                        ssb_geom g) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   const int Cs = g.C;
   const int XW = 2 * ST_TT + 5;
@@ -422,7 +434,7 @@ int ssb_conv1d_fwd(const void* x, const void* w_kio, const void* w_koi, void* y,
   const TapSpec taps = fwd_taps(k, stride);
   dim3 grid(ceil_div(M, TG_BM), ceil_div(gout.C, TG_BN));
   SSB_DISPATCH_DTYPE(dtype, T, {
-    tap_gemm_kernel<T, false><<<grid, TG_THREADS, 0, to_stream(stream)>>>(
+    ssb_launch(tap_gemm_kernel<T, false>, dim3(grid), dim3(TG_THREADS), 0, to_stream(stream), 
         (const T*)x, (const T*)w_kio, (T*)y, M, gout.C, gin.C, gin.B * gin.pitch, stride, taps, 1, 0, M, gout.pitch,
         gout.len);
   })
@@ -449,9 +461,9 @@ int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void*
       for (int j = 0; j < 3; ++j) { t.a_off[j] = (k == 3) ? 1 - j : 0; t.w_tap[j] = j < k ? j : 0; }
       dim3 grid(ceil_div(rows_in, TG_BM), ceil_div(gin.C, TG_BN));
       if (accumulate)
-        tap_gemm_kernel<T, true><<<grid, TG_THREADS, 0, st>>>((const T*)dy, (const T*)w_koi, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
+        ssb_launch(tap_gemm_kernel<T, true>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w_koi, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
       else
-        tap_gemm_kernel<T, false><<<grid, TG_THREADS, 0, st>>>((const T*)dy, (const T*)w_koi, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
+        ssb_launch(tap_gemm_kernel<T, false>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w_koi, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
       SSB_LAUNCH_CHECK("ssb_conv1d_dgrad");
     } else {
       // dx row 2q+p: p=0 <- dy[q+1]*W0 + dy[q]*W2 ; p=1 <- dy[q+1]*W1   (k=1: p=1 <- dy[q+1]*W0)
@@ -469,15 +481,15 @@ int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void*
         }
         if (t.ntaps == 0) {
           if (!accumulate) {
-            zero_parity_rows_kernel<T><<<148 * 2, 256, 0, st>>>((T*)dx, rows_in, gin.C, p);
+            ssb_launch(zero_parity_rows_kernel<T>, dim3(148 * 2), dim3(256), 0, st, (T*)dx, rows_in, gin.C, p);
             SSB_LAUNCH_CHECK("ssb_conv1d_dgrad(zero)");
           }
           continue;
         }
         if (accumulate)
-          tap_gemm_kernel<T, true><<<grid, TG_THREADS, 0, st>>>((const T*)dy, (const T*)w_koi, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
+          ssb_launch(tap_gemm_kernel<T, true>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w_koi, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
         else
-          tap_gemm_kernel<T, false><<<grid, TG_THREADS, 0, st>>>((const T*)dy, (const T*)w_koi, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
+          ssb_launch(tap_gemm_kernel<T, false>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w_koi, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
         SSB_LAUNCH_CHECK("ssb_conv1d_dgrad");
       }
     }
@@ -506,7 +518,7 @@ int ssb_conv1d_wgrad(const void* x, const void* dy, float* dw, ssb_geom gin, ssb
   nsplit = ceil_div(M, rps);
   dim3 grid(ceil_div(gin.C, WG_T), ceil_div(gout.C, WG_T), k * nsplit);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    wgrad_kernel<T><<<grid, 256, 0, to_stream(stream)>>>((const T*)x, (const T*)dy, dw, M, gin.C, gout.C, k,
+    ssb_launch(wgrad_kernel<T>, dim3(grid), dim3(256), 0, to_stream(stream), (const T*)x, (const T*)dy, dw, M, gin.C, gout.C, k,
                                                           gin.B * gin.pitch, stride, taps, nsplit, rps);
   })
   SSB_LAUNCH_CHECK("ssb_conv1d_wgrad");
@@ -519,7 +531,7 @@ int ssb_weight_repack(const ssb_repack_desc* table_dev, int n, int max_elems, in
   if (bx > 128) bx = 128;
   if (bx < 1) bx = 1;
   dim3 grid(bx, n);
-  SSB_DISPATCH_DTYPE(dtype, T, { repack_kernel<T><<<grid, 256, 0, to_stream(stream)>>>(table_dev, bx); })
+  SSB_DISPATCH_DTYPE(dtype, T, { ssb_launch(repack_kernel<T>, dim3(grid), dim3(256), 0, to_stream(stream), table_dev, bx); })
   SSB_LAUNCH_CHECK("ssb_weight_repack");
   return SSB_OK;
 }
@@ -542,7 +554,7 @@ int ssb_stem_conv_fwd(const float* x, const float* w, void* y, int Cl, int L, ss
   SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_fwd: num_leads x stem_channels too large (%zu B of shared memory)", smem);
   dim3 grid(ceil_div(g.len, ST_TT), g.B);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    stem_conv_fwd_kernel<T><<<grid, ST_THREADS, smem, to_stream(stream)>>>(x, w, (T*)y, Cl, L, g);
+    ssb_launch(stem_conv_fwd_kernel<T>, dim3(grid), dim3(ST_THREADS), smem, to_stream(stream), x, w, (T*)y, Cl, L, g);
   })
   SSB_LAUNCH_CHECK("ssb_stem_conv_fwd");
   return SSB_OK;
@@ -557,7 +569,7 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
   SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_wgrad: stem_channels too large (%zu B of shared memory)", smem);
   dim3 grid(ceil_div(g.len, ST_TT), g.B);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    stem_conv_wgrad_kernel<T><<<grid, ST_THREADS, smem, to_stream(stream)>>>(x, (const T*)dy, dw, Cl, L, g);
+    ssb_launch(stem_conv_wgrad_kernel<T>, dim3(grid), dim3(ST_THREADS), smem, to_stream(stream), x, (const T*)dy, dw, Cl, L, g);
   })
   SSB_LAUNCH_CHECK("ssb_stem_conv_wgrad");
   return SSB_OK;

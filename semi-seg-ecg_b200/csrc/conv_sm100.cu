@@ -156,6 +156,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const TnParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   SmemLayout s = carve<B_BYTES, STAGES>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -174,6 +175,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
+  pdl_wait();   // everything above is on-chip setup; global memory is first touched below
   const int KC = p.K / BK;
   const int iters = p.ntaps * KC;
 
@@ -271,6 +273,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                   float* __restrict__ dw, const WgParams p) {
   constexpr int B_BYTES = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   SmemLayout s = carve<B_BYTES, STAGES>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci0 = (blockIdx.x % p.n_ci_tiles) * BM;
@@ -295,6 +298,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s.tmem_slot;
+  pdl_wait();   // everything above is on-chip setup; global memory is first touched below
 
   if (iters > 0) {
     if (warp == 0) {
@@ -415,7 +419,7 @@ template <int BN>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem_bytes<BN * BK * 2, TN_STAGES>();
   dim3 grid(ceil_div(p.M, BM), p.N / BN);
-  conv_tn_kernel<BN, TN_STAGES><<<grid, NTHREADS, smem, st>>>(tmA, tmB, out, p);
+  ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   SSB_LAUNCH_CHECK("conv_tn_kernel");
   return SSB_OK;
 }
@@ -440,6 +444,8 @@ int check_sm100_shape(const char* who, const ssb_geom& gi, const ssb_geom& go) {
 
 template <typename T>
 __global__ void zero_parity_rows_sm100(T* out, int rows, int N, int parity) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)(rows / 2) * N;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -544,7 +550,7 @@ int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom
     p.a_col_off[0] = p.a_col_off[1] = p.a_col_off[2] = 0;
     if (p.ntaps == 0) {
       if (!accumulate) {
-        zero_parity_rows_sm100<bf16><<<148 * 2, 256, 0, st>>>((bf16*)dx, rows_in, gin.C, par);
+        ssb_launch(zero_parity_rows_sm100<bf16>, dim3(148 * 2), dim3(256), 0, st, (bf16*)dx, rows_in, gin.C, par);
         SSB_LAUNCH_CHECK("zero_parity_rows_sm100");
       }
       continue;
@@ -597,9 +603,9 @@ int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gi
   if (rc) return rc;
   dim3 grid(p.n_ci_tiles * (gout.C / BN), k, p.nsplit);
   if (BN == 128) {
-    conv_wgrad_kernel<128, WG_STAGES><<<grid, NTHREADS, smem_bytes<128 * BK * 2, WG_STAGES>(), st>>>(tmX, tmDY, dw, p);
+    ssb_launch_pro(conv_wgrad_kernel<128, WG_STAGES>, dim3(grid), dim3(NTHREADS), smem_bytes<128 * BK * 2, WG_STAGES>(), st, tmX, tmDY, dw, p);
   } else {
-    conv_wgrad_kernel<64, WG_STAGES><<<grid, NTHREADS, smem_bytes<64 * BK * 2, WG_STAGES>(), st>>>(tmX, tmDY, dw, p);
+    ssb_launch_pro(conv_wgrad_kernel<64, WG_STAGES>, dim3(grid), dim3(NTHREADS), smem_bytes<64 * BK * 2, WG_STAGES>(), st, tmX, tmDY, dw, p);
   }
   SSB_LAUNCH_CHECK("conv_wgrad_kernel");
   return SSB_OK;

@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(256)
 head_cls_fwd_kernel(const T* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ low, ssb_geom g, int ncls, float p, const uint8_t* __restrict__ dmask,
                     const ssb_step_params* __restrict__ sp) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int nrows = g.B * g.len;
@@ -71,6 +73,8 @@ __global__ void __launch_bounds__(256)
 head_cls_bwd_kernel(const float* __restrict__ dlow, const T* __restrict__ a, const float* __restrict__ w,
                     T* __restrict__ da, float* __restrict__ dw, float* __restrict__ dbias, ssb_geom g, int ncls,
                     float p, const uint8_t* __restrict__ dmask, const ssb_step_params* __restrict__ sp, int rpb) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // [ncls][C] dW partials + [ncls] dbias partials
   const int C = g.C;
   float* sW = sm;
@@ -136,6 +140,8 @@ head_cls_bwd_kernel(const float* __restrict__ dlow, const T* __restrict__ a, con
 // ---------------------------------------------------------------------------------------
 __global__ void upsample_fwd_kernel(const float* __restrict__ low, float* __restrict__ out, int B, int Lin, int Lout,
                                     int ncls, float scale, int align_corners) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)B * Lout;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -151,6 +157,8 @@ __global__ void upsample_fwd_kernel(const float* __restrict__ low, float* __rest
 
 __global__ void upsample_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dlow, int B, int Lin, int Lout,
                                     int ncls, float scale, int align_corners) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)B * Lin * ncls;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -212,6 +220,8 @@ __device__ __forceinline__ void softmax_conf_label(const float* z, int ncls, flo
 
 __global__ void pseudo_label_kernel(const float* __restrict__ logits, float thr, float* __restrict__ conf,
                                     int64_t* __restrict__ label, uint8_t* __restrict__ mask, int U, int ncls, int L) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)U * L;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -242,6 +252,8 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
                  float thr_arg, const ssb_step_params* __restrict__ sp, float scale, int align_corners,
                  float* __restrict__ conf_out, int64_t* __restrict__ label_out, uint8_t* __restrict__ mask_out,
                  int tcap) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* sG = sm;                                  // [tcap][ncls]
   float* sW1 = sm + (size_t)tcap * ncls;           // [tcap]
@@ -387,7 +399,7 @@ int ssb_head_cls_fwd(const void* a, const float* w, const float* bias, float* lo
   SSB_REQUIRE(p >= 0.f && p < 1.f, "ssb_head_cls_fwd: dropout p=%f out of [0,1)", p);
   const int nrows = g.B * g.len;
   SSB_DISPATCH_DTYPE(dtype, T, {
-    head_cls_fwd_kernel<T><<<ceil_div(nrows, 8), 256, 0, to_stream(stream)>>>((const T*)a, w, bias, low, g, ncls, p, drop_mask, sp);
+    ssb_launch(head_cls_fwd_kernel<T>, dim3(ceil_div(nrows, 8)), dim3(256), 0, to_stream(stream), (const T*)a, w, bias, low, g, ncls, p, drop_mask, sp);
   })
   SSB_LAUNCH_CHECK("ssb_head_cls_fwd");
   return SSB_OK;
@@ -407,7 +419,7 @@ int ssb_head_cls_bwd(const float* dlow, const void* a, const float* w, void* da,
   const size_t smem = ((size_t)ncls * g.C + ncls) * sizeof(float);
   SSB_REQUIRE(smem <= 48 * 1024, "ssb_head_cls_bwd: head channels %d too large", g.C);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    head_cls_bwd_kernel<T><<<ceil_div(rows, rpb), 256, smem, to_stream(stream)>>>(dlow, (const T*)a, w, (T*)da, dw, dbias, g, ncls, p, drop_mask, sp, rpb);
+    ssb_launch(head_cls_bwd_kernel<T>, dim3(ceil_div(rows, rpb)), dim3(256), smem, to_stream(stream), dlow, (const T*)a, w, (T*)da, dw, dbias, g, ncls, p, drop_mask, sp, rpb);
   })
   SSB_LAUNCH_CHECK("ssb_head_cls_bwd");
   return SSB_OK;
@@ -419,7 +431,7 @@ int ssb_upsample_fwd(const float* low, float* out, int B, int Lin, int Lout, int
   const long long total = (long long)B * Lout;
   int blocks = (int)ceil_div_ll(total, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  upsample_fwd_kernel<<<blocks, 256, 0, to_stream(stream)>>>(low, out, B, Lin, Lout, ncls, lerp_scale(Lin, Lout, align_corners), align_corners);
+  ssb_launch(upsample_fwd_kernel, dim3(blocks), dim3(256), 0, to_stream(stream), low, out, B, Lin, Lout, ncls, lerp_scale(Lin, Lout, align_corners), align_corners);
   SSB_LAUNCH_CHECK("ssb_upsample_fwd");
   return SSB_OK;
 }
@@ -430,7 +442,7 @@ int ssb_upsample_bwd(const float* dout, float* dlow, int B, int Lin, int Lout, i
   const long long total = (long long)B * Lin * ncls;
   int blocks = (int)ceil_div_ll(total, 128);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  upsample_bwd_kernel<<<blocks, 128, 0, to_stream(stream)>>>(dout, dlow, B, Lin, Lout, ncls, lerp_scale(Lin, Lout, align_corners), align_corners);
+  ssb_launch(upsample_bwd_kernel, dim3(blocks), dim3(128), 0, to_stream(stream), dout, dlow, B, Lin, Lout, ncls, lerp_scale(Lin, Lout, align_corners), align_corners);
   SSB_LAUNCH_CHECK("ssb_upsample_bwd");
   return SSB_OK;
 }
@@ -442,7 +454,7 @@ int ssb_pseudo_label(const float* logits, float thr, float* conf, int64_t* label
   const long long total = (long long)U * L;
   int blocks = (int)ceil_div_ll(total, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  pseudo_label_kernel<<<blocks, 256, 0, to_stream(stream)>>>(logits, thr, conf, label, mask, U, ncls, L);
+  ssb_launch(pseudo_label_kernel, dim3(blocks), dim3(256), 0, to_stream(stream), logits, thr, conf, label, mask, U, ncls, L);
   SSB_LAUNCH_CHECK("ssb_pseudo_label");
   return SSB_OK;
 }
@@ -463,7 +475,7 @@ int ssb_semi_loss(const float* low_s, const int64_t* target, const float* low_t,
   const size_t smem = (size_t)tcap * (ncls + 2) * sizeof(float);
   SSB_REQUIRE(smem <= 160 * 1024, "ssb_semi_loss: upsample ratio too large for the staging buffer (%zu bytes)", smem);
   dim3 grid(ceil_div(Lin, SL_NI), Bl + Bu);
-  semi_loss_kernel<<<grid, SL_THREADS, smem, to_stream(stream)>>>(low_s, target, low_t, dlow, sums, Bl, Bu, Lin, L, ncls, mode, thr, sp, scale, align_corners, conf, label, mask, tcap);
+  ssb_launch(semi_loss_kernel, dim3(grid), dim3(SL_THREADS), smem, to_stream(stream), low_s, target, low_t, dlow, sums, Bl, Bu, Lin, L, ncls, mode, thr, sp, scale, align_corners, conf, label, mask, tcap);
   SSB_LAUNCH_CHECK("ssb_semi_loss");
   return SSB_OK;
 }

@@ -9,6 +9,8 @@ __global__ void __launch_bounds__(256)
 adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  float* __restrict__ pe, size_t n4, float beta1, float omb1, float beta2, float omb2, float eps,
                  float wd, const ssb_step_params* __restrict__ sp) {
+  pdl_trigger();
+  pdl_wait();
   const float lr = sp->lr;
   const float step_size = lr * sp->inv_bias1;
   const float isb2 = sp->inv_sqrt_bias2;
@@ -57,6 +59,8 @@ adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 __global__ void ema_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n,
                            const ssb_step_params* __restrict__ sp) {
+  pdl_trigger();
+  pdl_wait();
   const float d = sp->ema_decay;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = dst[i] * d + src[i] * (1.0f - d);
@@ -64,12 +68,16 @@ __global__ void ema_kernel(float* __restrict__ dst, const float* __restrict__ sr
 
 __global__ void ema_i64_kernel(float* __restrict__ dst, const int64_t* __restrict__ src, size_t n,
                                const ssb_step_params* __restrict__ sp) {
+  pdl_trigger();
+  pdl_wait();
   const float d = sp->ema_decay;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = dst[i] * d + (float)src[i] * (1.0f - d);
 }
 
 __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict__ g, size_t n, double* __restrict__ ws) {
+  pdl_trigger();
+  pdl_wait();
   double acc = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const float x = g[i];
@@ -85,7 +93,9 @@ __global__ void __launch_bounds__(256) grad_sumsq_kernel(const float* __restrict
     atomicAdd(ws, t);
   }
 }
-__global__ void grad_norm_final_kernel(const double* ws, float* out) { out[0] = (float)sqrt(ws[0]); }
+__global__ void grad_norm_final_kernel(const double* ws, float* out) {
+  pdl_trigger();
+  pdl_wait(); out[0] = (float)sqrt(ws[0]); }
 
 extern "C" {
 
@@ -96,7 +106,7 @@ int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, si
   const size_t n4 = n / 4;
   long long blocks = ceil_div_ll((long long)n4, 256 * 2);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  adamw_ema_kernel<<<(int)blocks, 256, 0, to_stream(stream)>>>(p, g, m, v, p_ema, n4, (float)beta1, (float)(1.0 - beta1), (float)beta2,
+  ssb_launch(adamw_ema_kernel, dim3((int)blocks), dim3(256), 0, to_stream(stream), p, g, m, v, p_ema, n4, (float)beta1, (float)(1.0 - beta1), (float)beta2,
                                                                 (float)(1.0 - beta2), (float)eps, (float)weight_decay, sp);
   SSB_LAUNCH_CHECK("ssb_adamw_ema");
   return SSB_OK;
@@ -106,14 +116,14 @@ int ssb_ema(float* dst, const float* src, size_t n, const ssb_step_params* sp, s
   SSB_REQUIRE(dst && src && sp && n > 0, "ssb_ema: bad arguments");
   long long blocks = ceil_div_ll((long long)n, 256);
   if (blocks > 148 * 4) blocks = 148 * 4;
-  ema_kernel<<<(int)blocks, 256, 0, to_stream(stream)>>>(dst, src, n, sp);
+  ssb_launch(ema_kernel, dim3((int)blocks), dim3(256), 0, to_stream(stream), dst, src, n, sp);
   SSB_LAUNCH_CHECK("ssb_ema");
   return SSB_OK;
 }
 
 int ssb_ema_i64(float* dst, const int64_t* src, size_t n, const ssb_step_params* sp, ssb_stream_t stream) {
   SSB_REQUIRE(dst && src && sp && n > 0, "ssb_ema_i64: bad arguments");
-  ema_i64_kernel<<<(int)ceil_div_ll((long long)n, 256), 256, 0, to_stream(stream)>>>(dst, src, n, sp);
+  ssb_launch(ema_i64_kernel, dim3((int)ceil_div_ll((long long)n, 256)), dim3(256), 0, to_stream(stream), dst, src, n, sp);
   SSB_LAUNCH_CHECK("ssb_ema_i64");
   return SSB_OK;
 }
@@ -122,9 +132,9 @@ int ssb_grad_norm(const float* g, size_t n, double* ws, float* out, ssb_stream_t
   SSB_REQUIRE(g && ws && out && n > 0, "ssb_grad_norm: bad arguments");
   long long blocks = ceil_div_ll((long long)n, 256 * 8);
   if (blocks > 148 * 4) blocks = 148 * 4;
-  grad_sumsq_kernel<<<(int)blocks, 256, 0, to_stream(stream)>>>(g, n, ws);
+  ssb_launch(grad_sumsq_kernel, dim3((int)blocks), dim3(256), 0, to_stream(stream), g, n, ws);
   SSB_LAUNCH_CHECK("ssb_grad_norm");
-  grad_norm_final_kernel<<<1, 1, 0, to_stream(stream)>>>(ws, out);
+  ssb_launch(grad_norm_final_kernel, dim3(1), dim3(1), 0, to_stream(stream), ws, out);
   SSB_LAUNCH_CHECK("ssb_grad_norm(final)");
   return SSB_OK;
 }
