@@ -134,6 +134,13 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
 int ssb_conv1d_fwd(const void* x, const void* w_kio, const void* w_koi, void* y,
                    ssb_geom gin, ssb_geom gout, int k, int stride,
                    int dtype, int algo, ssb_stream_t stream);
+/* same conv with the BatchNorm statistics of its output fused into the epilogue:
+ * sums[0:Cout] += sum_rows y, sums[Cout:2Cout] += sum_rows y^2 (fp64, of the values as stored);
+ * sums == NULL: plain conv.  Replaces the separate statistics pass of native_batch_norm
+ * (resnet.py:41,50; fcn_head.py:48) after the conv. */
+int ssb_conv1d_fwd_stats(const void* x, const void* w_kio, const void* w_koi, void* y,
+                         ssb_geom gin, ssb_geom gout, int k, int stride, double* sums,
+                         int dtype, int algo, ssb_stream_t stream);
 /* dx = conv_transpose(dy, w) (+ dx if accumulate) */
 int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void* dx,
                      ssb_geom gin, ssb_geom gout, int k, int stride, int accumulate,
@@ -157,8 +164,11 @@ int ssb_bn_stats(const void* x, ssb_geom g, double* sums, int dtype, ssb_stream_
  * (resnet.py:58-70: bn1+relu, bn2 + identity/downsample + relu; fcn_head.py:48-49) */
 int ssb_bn_act_fwd(const void* x, const ssb_bn* bn, const void* res, const ssb_bn* bn_res,
                    void* y, ssb_geom g, int relu, int train, int dtype, ssb_stream_t stream);
-/* stem tail: MaxPool1d(3,2,1)(relu(bn(c0)))  (resnet.py:254-257, 354-355) */
-int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, ssb_geom gin,
+/* stem tail: MaxPool1d(3,2,1)(relu(bn(c0)))  (resnet.py:254-257, 354-355).
+ * arg (may be NULL): u8 [B*gout.pitch, C], per pooled element the window slot 0..2 of the first
+ * maximum (torch's max_pool1d index rule) or 3 where the maximum is <= 0 (ReLU-dead); it is what
+ * the backward pass routes gradients by (replaces max_pool1d's int64 indices + the ReLU mask). */
+int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, uint8_t* arg, ssb_geom gin,
                               ssb_geom gout, int train, int dtype, ssb_stream_t stream);
 /* backward, pass 1: g = (g1 [+ g2]) * (y > 0 if y != NULL);  bn->bwd_sums += (sum g, sum g*xhat);
  * if x_res/bn_res given the same for the residual-branch BN. */
@@ -171,10 +181,10 @@ int ssb_bn_bwd_apply(const void* g1, const void* g2, const void* y, const void* 
                      const ssb_bn* bn, void* dx, const void* x_res, const ssb_bn* bn_res,
                      void* dx_res, void* g_ident, ssb_geom g, int dtype, ssb_stream_t stream);
 /* stem tail backward (max-pool scatter + relu + bn), same two passes; gp: grad w.r.t. pooled output */
-int ssb_stem_bwd_reduce(const void* gp, const void* c0, const ssb_bn* bn, ssb_geom gin,
+int ssb_stem_bwd_reduce(const void* gp, const void* c0, const uint8_t* arg, const ssb_bn* bn, ssb_geom gin,
                         ssb_geom gout, int dtype, ssb_stream_t stream);
-int ssb_stem_bwd_apply(const void* gp, const void* c0, const ssb_bn* bn, void* dc0, ssb_geom gin,
-                       ssb_geom gout, int dtype, ssb_stream_t stream);
+int ssb_stem_bwd_apply(const void* gp, const void* c0, const uint8_t* arg, const ssb_bn* bn, void* dc0,
+                       ssb_geom gin, ssb_geom gout, int dtype, ssb_stream_t stream);
 
 /* ---- FCN head tail: Dropout(p) + Conv1d(C -> ncls, 1, bias=True)  (fcn_head.py:83-97) --- */
 /* a: flat padded NLC [B*pitch, C]; low: [B, len, ncls] fp32 (compact).

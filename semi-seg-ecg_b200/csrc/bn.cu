@@ -163,10 +163,14 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restr
 
 // ---------------------------------------------------------------------------------------
 // stem tail: y[b, t] = max_{l in {2t-1,2t,2t+1} valid} relu(bn(c0[b, l]))
+// arg (optional, train): per pooled element the window slot 0..2 of the first maximum (torch's
+// max-pool tie rule), or 3 when the maximum is <= 0 (the ReLU kills the gradient there), so the
+// backward pass routes gradients without recomputing the windows.
 // ---------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) stem_bn_relu_pool_kernel(const T* __restrict__ c0, T* __restrict__ y,
-                                                                       ssb_bn bn, ssb_geom gi, ssb_geom go, int train) {
+                                                                       uint8_t* __restrict__ arg, ssb_bn bn,
+                                                                       ssb_geom gi, ssb_geom go, int train) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
@@ -190,11 +194,12 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bn_relu_pool_kernel(const T* 
     const int cg = (int)(idx - (long long)row * ncg);
     const int b = row / go.pitch, pos = row - b * go.pitch;
     Vec<T> out;
+    uint8_t am[V];
     if (pos >= 1 && pos <= go.len) {
       const int t = pos - 1;
       float m[V];
 #pragma unroll
-      for (int i = 0; i < V; ++i) m[i] = -INFINITY;
+      for (int i = 0; i < V; ++i) { m[i] = 0.f; am[i] = 3; }
 #pragma unroll
       for (int j = -1; j <= 1; ++j) {
         const int l = 2 * t + j;
@@ -206,14 +211,23 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bn_relu_pool_kernel(const T* 
 #pragma unroll
         for (int i = 0; i < V; ++i) {
           const int c = cg * V + i;
-          m[i] = fmaxf(m[i], fmaxf(fmaf(f[i], sScale[c], sShift[c]), 0.f));
+          const float a = fmaf(f[i], sScale[c], sShift[c]);
+          if (a > m[i]) { m[i] = a; am[i] = (uint8_t)(j + 1); }   // strict >: first maximum wins
         }
       }
       out.set(m);
     } else {
       out.zero();
+#pragma unroll
+      for (int i = 0; i < V; ++i) am[i] = 3;
     }
     out.store(y + (size_t)row * C + (size_t)cg * V);
+    if (arg) {
+      uint8_t* ap = arg + (size_t)row * C + (size_t)cg * V;
+#pragma unroll
+      for (int i = 0; i < V; i += 4)
+        *reinterpret_cast<uint32_t*>(ap + i) = (uint32_t)am[i] | ((uint32_t)am[i + 1] << 8) | ((uint32_t)am[i + 2] << 16) | ((uint32_t)am[i + 3] << 24);
+    }
   }
 }
 
@@ -440,138 +454,122 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
 }
 
 // ---------------------------------------------------------------------------------------
-// stem tail backward: gradient of pooled output scattered through max-pool (first max on
-// ties, torch semantics), relu mask, then the two BN-backward passes on c0.
+// stem tail backward: the pooled gradient is routed through the max-pool by the slot index the
+// forward saved (slot 3 = ReLU-dead), then the two BN-backward passes on c0.
 // ---------------------------------------------------------------------------------------
 template <typename T, int V>
-__device__ __forceinline__ void stem_masked_grad(const T* __restrict__ c0, const T* __restrict__ gp,
-                                                 const float* sScale, const float* sShift, const ssb_geom& gi,
-                                                 const ssb_geom& go, int b, int l, int cg, float* g, float* xc) {
+__device__ __forceinline__ void stem_routed_grad(const T* __restrict__ gp, const uint8_t* __restrict__ arg,
+                                                 const ssb_geom& gi, const ssb_geom& go, int b, int l, int cg, float* g) {
   const int C = gi.C;
-  float a[5][V];
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    const int ll = l - 2 + j;
-    if (ll < 0 || ll >= gi.len) {
-#pragma unroll
-      for (int i = 0; i < V; ++i) a[j][i] = -INFINITY;
-    } else {
-      Vec<T> v;
-      v.load(c0 + ((size_t)b * gi.pitch + 1 + ll) * C + (size_t)cg * V);
-      float f[V];
-      v.get(f);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const int c = cg * V + i;
-        if (j == 2) xc[i] = f[i];
-        a[j][i] = fmaxf(fmaf(f[i], sScale[c], sShift[c]), 0.f);
-      }
-    }
-  }
 #pragma unroll
   for (int i = 0; i < V; ++i) g[i] = 0.f;
-  // windows containing l: centre index 2t; l even -> t=l/2 (l-1,l,l+1);
-  // l odd -> t=(l-1)/2 (l-2,l-1,l) and t=(l+1)/2 (l,l+1,l+2)
-  int tw[2], base[2];  // base = array index j of the window's first element
-  int nw = 0;
-  if ((l & 1) == 0) {
-    tw[nw] = l >> 1; base[nw] = 1; ++nw;
-  } else {
-    tw[nw] = (l - 1) >> 1; base[nw] = 0; ++nw;
-    tw[nw] = (l + 1) >> 1; base[nw] = 2; ++nw;
-  }
+  // windows containing l (centre 2t): l even -> t = l/2, slot 1; l odd -> t = (l-1)/2 slot 2 and t = (l+1)/2 slot 0
+  int tw[2], slot[2], nw;
+  if ((l & 1) == 0) { tw[0] = l >> 1; slot[0] = 1; nw = 1; }
+  else { tw[0] = (l - 1) >> 1; slot[0] = 2; tw[1] = (l + 1) >> 1; slot[1] = 0; nw = 2; }
   for (int w = 0; w < nw; ++w) {
     if (tw[w] >= go.len) continue;
+    const size_t off = ((size_t)b * go.pitch + 1 + tw[w]) * C + (size_t)cg * V;
     Vec<T> vg;
-    vg.load(gp + ((size_t)b * go.pitch + 1 + tw[w]) * C + (size_t)cg * V);
+    vg.load(gp + off);
     float fg[V];
     vg.get(fg);
-    const int bs = base[w];
-    const int me = 2 - bs;  // position of l inside the window (0..2)
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      // first-max arg over the 3 window entries (strict > from the left; -inf = padding)
-      float best = a[bs][i];
-      int arg = 0;
-      if (a[bs + 1][i] > best) { best = a[bs + 1][i]; arg = 1; }
-      if (a[bs + 2][i] > best) { best = a[bs + 2][i]; arg = 2; }
-      if (arg == me) g[i] += fg[i];
+    for (int i = 0; i < V; i += 4) {
+      const uint32_t a4 = *reinterpret_cast<const uint32_t*>(arg + off + i);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (((a4 >> (8 * u)) & 0xffu) == (uint32_t)slot[w]) g[i + u] += fg[i + u];
     }
   }
-#pragma unroll
-  for (int i = 0; i < V; ++i) g[i] = a[2][i] > 0.f ? g[i] : 0.f;
 }
 
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) stem_bwd_reduce_kernel(const T* __restrict__ gp, const T* __restrict__ c0,
-                                                                     ssb_bn bn, ssb_geom gi, ssb_geom go) {
+                                                                     const uint8_t* __restrict__ arg, ssb_bn bn,
+                                                                     ssb_geom gi, ssb_geom go, int rpb) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
-  extern __shared__ float sm[];
   const int C = gi.C;
-  float* sScale = sm;
-  float* sShift = sm + C;
-  float* sMean = sm + 2 * C;
-  float* sInv = sm + 3 * C;
-  float* sAcc = sm + 4 * C;  // [2C] block-level accumulators
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mean = bn.mean_invstd[c], inv = bn.mean_invstd[C + c];
-    sMean[c] = mean;
-    sInv[c] = inv;
-    sScale[c] = bn.gamma[c] * inv;
-    sShift[c] = bn.beta[c] - mean * sScale[c];
-    sAcc[c] = 0.f;
-    sAcc[C + c] = 0.f;
-  }
-  __syncthreads();
   const int ncg = C / V;
-  // a block owns a contiguous chunk of (row, cg) work items so the smem atomics stay cheap
-  const long long total = (long long)gi.B * gi.len * ncg;
-  const long long per = (total + gridDim.x - 1) / gridDim.x;
-  const long long i0 = (long long)blockIdx.x * per;
-  const long long i1 = i0 + per < total ? i0 + per : total;
-  for (long long idx = i0 + threadIdx.x; idx < i1; idx += blockDim.x) {
-    const long long rl = idx / ncg;
-    const int cg = (int)(idx - rl * ncg);
-    const int b = (int)(rl / gi.len), l = (int)(rl - (long long)b * gi.len);
-    float g[V], xc[V];
-    stem_masked_grad<T, V>(c0, gp, sScale, sShift, gi, go, b, l, cg, g, xc);
+  const int cgb = ncg < BN_THREADS ? ncg : BN_THREADS;
+  const int nrl = BN_THREADS / cgb;
+  const int tid = threadIdx.x;
+  const int cgl = tid % cgb, rl = tid / cgb;
+  const int cg = blockIdx.y * cgb + cgl;
+  __shared__ float sA[BN_THREADS * V];
+  __shared__ float sB[BN_THREADS * V];
+  float a[V], bq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) a[i] = bq[i] = 0.f;
+  if (rl < nrl && cg < ncg) {
+    float mean[V], inv[V];
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      const int c = cg * V + i;
-      if (g[i] != 0.f) {
-        atomicAdd(&sAcc[c], g[i]);
-        atomicAdd(&sAcc[C + c], g[i] * ((xc[i] - sMean[c]) * sInv[c]));
+      mean[i] = bn.mean_invstd[cg * V + i];
+      inv[i] = bn.mean_invstd[C + cg * V + i];
+    }
+    const int rows = gi.B * gi.pitch;
+    const int r0 = blockIdx.x * rpb;
+    const int r1 = min(rows, r0 + rpb);
+    for (int r = r0 + rl; r < r1; r += nrl) {
+      const int b = r / gi.pitch, pos = r - b * gi.pitch;
+      if (pos < 1 || pos > gi.len) continue;
+      float g[V];
+      stem_routed_grad<T, V>(gp, arg, gi, go, b, pos - 1, cg, g);
+      Vec<T> vx;
+      vx.load(c0 + (size_t)r * C + (size_t)cg * V);
+      float fx[V];
+      vx.get(fx);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        a[i] += g[i];
+        bq[i] += g[i] * ((fx[i] - mean[i]) * inv[i]);
       }
     }
   }
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sA[tid * V + i] = a[i];
+    sB[tid * V + i] = bq[i];
+  }
   __syncthreads();
-  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) atomicAdd(&bn.bwd_sums[c], (double)sAcc[c]);
+  for (int o = tid; o < cgb * V; o += BN_THREADS) {
+    const int l = o / V, i = o % V;
+    const int cgo = blockIdx.y * cgb + l;
+    if (cgo >= ncg) continue;
+    double da = 0.0, db = 0.0;
+    for (int k = 0; k < nrl; ++k) {
+      da += (double)sA[(k * cgb + l) * V + i];
+      db += (double)sB[(k * cgb + l) * V + i];
+    }
+    const int c = cgo * V + i;
+    atomicAdd(&bn.bwd_sums[c], da);
+    atomicAdd(&bn.bwd_sums[C + c], db);
+  }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) stem_bwd_apply_kernel(const T* __restrict__ gp, const T* __restrict__ c0,
-                                                                    T* __restrict__ dc0, ssb_bn bn, ssb_geom gi,
-                                                                    ssb_geom go) {
+                                                                    const uint8_t* __restrict__ arg, T* __restrict__ dc0,
+                                                                    ssb_bn bn, ssb_geom gi, ssb_geom go) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
   extern __shared__ float sm[];
   const int C = gi.C;
   float* sScale = sm;
-  float* sShift = sm + C;
-  float* sMean = sm + 2 * C;
-  float* sInv = sm + 3 * C;
-  float* sK1 = sm + 4 * C;
-  float* sK2 = sm + 5 * C;
+  float* sMean = sm + C;
+  float* sInv = sm + 2 * C;
+  float* sK1 = sm + 3 * C;
+  float* sK2 = sm + 4 * C;
   const double inv_n = 1.0 / ((double)gi.B * (double)gi.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1));
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float mean = bn.mean_invstd[c], inv = bn.mean_invstd[C + c];
     sMean[c] = mean;
     sInv[c] = inv;
     sScale[c] = bn.gamma[c] * inv;
-    sShift[c] = bn.beta[c] - mean * sScale[c];
     sK1[c] = (float)(bn.bwd_sums[c] * inv_n);
     sK2[c] = (float)(bn.bwd_sums[C + c] * inv_n);
     if (blockIdx.x == 0) {
@@ -590,12 +588,16 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bwd_apply_kernel(const T* __r
     const int b = row / gi.pitch, pos = row - b * gi.pitch;
     Vec<T> out;
     if (pos >= 1 && pos <= gi.len) {
-      float g[V], xc[V];
-      stem_masked_grad<T, V>(c0, gp, sScale, sShift, gi, go, b, pos - 1, cg, g, xc);
+      float g[V];
+      stem_routed_grad<T, V>(gp, arg, gi, go, b, pos - 1, cg, g);
+      Vec<T> vx;
+      vx.load(c0 + (size_t)row * C + (size_t)cg * V);
+      float fx[V];
+      vx.get(fx);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         const int c = cg * V + i;
-        const float xh = (xc[i] - sMean[c]) * sInv[c];
+        const float xh = (fx[i] - sMean[c]) * sInv[c];
         g[i] = sScale[c] * (g[i] - sK1[c] - xh * sK2[c]);
       }
       out.set(g);
@@ -676,8 +678,8 @@ int ssb_bn_act_fwd(const void* x, const ssb_bn* bn, const void* res, const ssb_b
   return SSB_OK;
 }
 
-int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, ssb_geom gin, ssb_geom gout, int train,
-                              int dtype, ssb_stream_t stream) {
+int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, uint8_t* arg, ssb_geom gin, ssb_geom gout,
+                              int train, int dtype, ssb_stream_t stream) {
   int rc = check_geom("ssb_stem_bn_relu_pool_fwd(in)", gin, 0);
   if (rc) return rc;
   rc = check_geom("ssb_stem_bn_relu_pool_fwd(out)", gout, 0);
@@ -688,7 +690,7 @@ int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, ssb_geo
   const size_t smem = (size_t)2 * gin.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
     const long long total = (long long)gout.B * gout.pitch * (gout.C / Vec<T>::N);
-    ssb_launch(stem_bn_relu_pool_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)c0, (T*)y, *bn, gin, gout, train);
+    ssb_launch(stem_bn_relu_pool_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)c0, (T*)y, arg, *bn, gin, gout, train);
   })
   SSB_LAUNCH_CHECK("ssb_stem_bn_relu_pool_fwd");
   return SSB_OK;
@@ -758,35 +760,41 @@ int ssb_bn_bwd_apply(const void* g1, const void* g2, const void* y, const void* 
   return SSB_OK;
 }
 
-int ssb_stem_bwd_reduce(const void* gp, const void* c0, const ssb_bn* bn, ssb_geom gin, ssb_geom gout, int dtype,
-                        ssb_stream_t stream) {
+int ssb_stem_bwd_reduce(const void* gp, const void* c0, const uint8_t* arg, const ssb_bn* bn, ssb_geom gin,
+                        ssb_geom gout, int dtype, ssb_stream_t stream) {
   int rc = check_geom("ssb_stem_bwd_reduce(in)", gin, 0);
   if (rc) return rc;
   rc = check_geom("ssb_stem_bwd_reduce(out)", gout, 0);
   if (rc) return rc;
-  SSB_REQUIRE(gp && c0 && bn, "ssb_stem_bwd_reduce: null pointer");
+  SSB_REQUIRE(gp && c0 && bn && arg, "ssb_stem_bwd_reduce: null pointer");
   SSB_REQUIRE(gin.C == gout.C && gin.B == gout.B, "ssb_stem_bwd_reduce: geometry mismatch");
-  const size_t smem = (size_t)6 * gin.C * sizeof(float);
+  const int rows = gin.B * gin.pitch;
   SSB_DISPATCH_DTYPE(dtype, T, {
-    const long long total = (long long)gin.B * gin.len * (gin.C / Vec<T>::N);
-    ssb_launch(stem_bwd_reduce_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)gp, (const T*)c0, *bn, gin, gout);
+    constexpr int V = Vec<T>::N;
+    const int ncg = gin.C / V;
+    const int cgb = ncg < BN_THREADS ? ncg : BN_THREADS;
+    const int nrl = BN_THREADS / cgb;
+    int rpb = ceil_div(rows, 148 * 4);
+    if (rpb < nrl * 4) rpb = nrl * 4;
+    dim3 grid(ceil_div(rows, rpb), ceil_div(ncg, cgb));
+    ssb_launch(stem_bwd_reduce_kernel<T>, dim3(grid), dim3(BN_THREADS), 0, to_stream(stream), (const T*)gp, (const T*)c0, arg, *bn, gin, gout, rpb);
   })
   SSB_LAUNCH_CHECK("ssb_stem_bwd_reduce");
   return SSB_OK;
 }
 
-int ssb_stem_bwd_apply(const void* gp, const void* c0, const ssb_bn* bn, void* dc0, ssb_geom gin, ssb_geom gout,
-                       int dtype, ssb_stream_t stream) {
+int ssb_stem_bwd_apply(const void* gp, const void* c0, const uint8_t* arg, const ssb_bn* bn, void* dc0, ssb_geom gin,
+                       ssb_geom gout, int dtype, ssb_stream_t stream) {
   int rc = check_geom("ssb_stem_bwd_apply(in)", gin, 0);
   if (rc) return rc;
   rc = check_geom("ssb_stem_bwd_apply(out)", gout, 0);
   if (rc) return rc;
-  SSB_REQUIRE(gp && c0 && bn && dc0, "ssb_stem_bwd_apply: null pointer");
+  SSB_REQUIRE(gp && c0 && bn && dc0 && arg, "ssb_stem_bwd_apply: null pointer");
   SSB_REQUIRE(gin.C == gout.C && gin.B == gout.B, "ssb_stem_bwd_apply: geometry mismatch");
   const size_t smem = (size_t)6 * gin.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
     const long long total = (long long)gin.B * gin.pitch * (gin.C / Vec<T>::N);
-    ssb_launch(stem_bwd_apply_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)gp, (const T*)c0, (T*)dc0, *bn, gin, gout);
+    ssb_launch(stem_bwd_apply_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)gp, (const T*)c0, arg, (T*)dc0, *bn, gin, gout);
   })
   SSB_LAUNCH_CHECK("ssb_stem_bwd_apply");
   return SSB_OK;

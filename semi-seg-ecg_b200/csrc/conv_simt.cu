@@ -331,38 +331,65 @@ stem_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T
 }
 
 // dw[co][c][j] += sum_{b,t} dy[b,t,co] * x[b][c][2t+j-3]
+// One CTA per SM walks over (sample, 64-position tile) work items and keeps its partial dw in shared
+// memory (thread o owns outputs o, o+blockDim, ...: no conflicts), so the fp32 atomics into dw are
+// one per output per CTA instead of one per output per tile.
+#define SW_THREADS 512
 template <typename T>
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(SW_THREADS)
 stem_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int Cl, int L,
-                       ssb_geom g) {
+                       ssb_geom g, int ntt) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
   const int Cs = g.C;
   const int XW = 2 * ST_TT + 5;
+  const int nout = Cl * 7 * Cs;
   float* dys = sm;                 // [TT][Cs]
   float* xs = sm + ST_TT * Cs;     // [Cl][XW]
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * ST_TT;
+  float* acc_s = xs + Cl * XW;     // [nout]
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < ST_TT * Cs; idx += ST_THREADS) {
-    const int t = t0 + idx / Cs;
-    dys[idx] = t < g.len ? to_f(dy[((size_t)b * g.pitch + 1 + t) * Cs + idx % Cs]) : 0.f;
-  }
-  for (int idx = tid; idx < Cl * XW; idx += ST_THREADS) {
-    const int c = idx / XW, i = idx % XW;
-    const int l = 2 * t0 - 3 + i;
-    xs[idx] = (l >= 0 && l < L) ? x[((size_t)b * Cl + c) * L + l] : 0.f;
-  }
-  __syncthreads();
-  const int nout = Cl * 7 * Cs;
-  for (int o = tid; o < nout; o += ST_THREADS) {
-    const int co = o % Cs, cj = o / Cs;
-    const int c = cj / 7, j = cj % 7;
-    float acc = 0.f;
+  for (int o = tid; o < nout; o += SW_THREADS) acc_s[o] = 0.f;
+  const int ntiles = ntt * g.B;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int b = tile / ntt;
+    const int t0 = (tile - b * ntt) * ST_TT;
+    __syncthreads();   // previous tile's readers are done with dys / xs
+    constexpr int V = Vec<T>::N;
+    for (int idx = tid; idx < ST_TT * Cs / V; idx += SW_THREADS) {   // 16-byte loads (Cs is a multiple of 8)
+      const int e = idx * V;
+      const int t = t0 + e / Cs;
+      float f[V];
+      if (t < g.len) {
+        Vec<T> v;
+        v.load(dy + ((size_t)b * g.pitch + 1 + t) * Cs + e % Cs);
+        v.get(f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < V; ++i) f[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < V; ++i) dys[e + i] = f[i];
+    }
+    for (int idx = tid; idx < Cl * XW; idx += SW_THREADS) {
+      const int c = idx / XW, i = idx % XW;
+      const int l = 2 * t0 - 3 + i;
+      xs[idx] = (l >= 0 && l < L) ? x[((size_t)b * Cl + c) * L + l] : 0.f;
+    }
+    __syncthreads();
+    for (int o = tid; o < nout; o += SW_THREADS) {
+      const int co = o % Cs, cj = o / Cs;
+      const int c = cj / 7, j = cj % 7;
+      const float* xr = xs + c * XW + j;
+      float acc = 0.f;
 #pragma unroll 8
-    for (int t = 0; t < ST_TT; ++t) acc = fmaf(dys[t * Cs + co], xs[c * XW + 2 * t + j], acc);
-    atomicAdd(&dw[((size_t)co * Cl + c) * 7 + j], acc);
+      for (int t = 0; t < ST_TT; ++t) acc = fmaf(dys[t * Cs + co], xr[2 * t], acc);
+      acc_s[o] += acc;
+    }
+  }
+  for (int o = tid; o < nout; o += SW_THREADS) {
+    const int co = o % Cs, cj = o / Cs;
+    atomicAdd(&dw[(size_t)co * Cl * 7 + cj], acc_s[o]);
   }
 }
 
@@ -400,7 +427,7 @@ static TapSpec fwd_taps(int k, int stride) {
 }
 
 int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
-                         cudaStream_t st);
+                         double* stats, cudaStream_t st);
 int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
                            int accumulate, cudaStream_t st);
 int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
@@ -423,12 +450,22 @@ extern "C" {
 
 int ssb_conv1d_fwd(const void* x, const void* w_kio, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k,
                    int stride, int dtype, int algo, ssb_stream_t stream) {
+  return ssb_conv1d_fwd_stats(x, w_kio, w_koi, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
+}
+
+int ssb_conv1d_fwd_stats(const void* x, const void* w_kio, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k,
+                         int stride, double* sums, int dtype, int algo, ssb_stream_t stream) {
   int rc = check_conv_geom("ssb_conv1d_fwd", gin, gout, k, stride);
   if (rc) return rc;
   SSB_REQUIRE(x && y && w_kio && w_koi, "ssb_conv1d_fwd: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_fwd: tcgen05 path needs bf16");
-    return ssb_conv1d_fwd_sm100(x, w_koi, y, gin, gout, k, stride, to_stream(stream));
+    return ssb_conv1d_fwd_sm100(x, w_koi, y, gin, gout, k, stride, sums, to_stream(stream));
+  }
+  if (sums) {   // generic CUDA-core path: conv, then the statistics pass as its own launch
+    rc = ssb_conv1d_fwd_stats(x, w_kio, w_koi, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
+    if (rc) return rc;
+    return ssb_bn_stats(y, gout, sums, dtype, stream);
   }
   const int M = gout.B * gout.pitch;
   const TapSpec taps = fwd_taps(k, stride);
@@ -565,11 +602,13 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
   int rc = check_stem("ssb_stem_conv_wgrad", Cl, L, g);
   if (rc) return rc;
   SSB_REQUIRE(x && dy && dw, "ssb_stem_conv_wgrad: null pointer");
-  const size_t smem = ((size_t)ST_TT * g.C + (size_t)Cl * (2 * ST_TT + 5)) * sizeof(float);
-  SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_wgrad: stem_channels too large (%zu B of shared memory)", smem);
-  dim3 grid(ceil_div(g.len, ST_TT), g.B);
+  const size_t smem = ((size_t)ST_TT * g.C + (size_t)Cl * (2 * ST_TT + 5) + (size_t)Cl * 7 * g.C) * sizeof(float);
+  SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_wgrad: num_leads x stem_channels too large (%zu B of shared memory)", smem);
+  const int ntt = ceil_div(g.len, ST_TT);
+  const int ntiles = ntt * g.B;
+  dim3 grid(ntiles < 148 ? ntiles : 148);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    ssb_launch(stem_conv_wgrad_kernel<T>, dim3(grid), dim3(ST_THREADS), smem, to_stream(stream), x, (const T*)dy, dw, Cl, L, g);
+    ssb_launch(stem_conv_wgrad_kernel<T>, dim3(grid), dim3(SW_THREADS), smem, to_stream(stream), x, (const T*)dy, dw, Cl, L, g, ntt);
   })
   SSB_LAUNCH_CHECK("ssb_stem_conv_wgrad");
   return SSB_OK;

@@ -118,7 +118,23 @@ struct TnParams {
   int w_rows_per_tap;
   int o_mul, o_off, o_rows, o_pitch, o_len;
   int accumulate;
+  double* stats;   // STATS epilogue: [2N] per-channel sum / sum of squares of the stored (rounded) output
 };
+
+// Column sums across the 32 lanes of a warp: every lane holds 32 column values x[0..31] of its own row;
+// on return x[0] of lane l is the sum over all lanes of column l (31 shuffles instead of 160).
+__device__ __forceinline__ void warp_transpose_sum(float (&x)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = upper ? x[i] : x[i + o];
+      const float keep = upper ? x[i + o] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
 
 struct SmemLayout {
   uint8_t* a;
@@ -150,7 +166,7 @@ constexpr int smem_bytes() {
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool STATS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
                const TnParams p) {
@@ -221,30 +237,60 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool in_range = m < p.M && orow >= 0 && orow < p.o_rows;
     const bool valid = in_range && row_valid((int)orow, p.o_pitch, p.o_len);
     bf16* optr = out + (size_t)(in_range ? orow : 0) * p.N + n0;
+    // all MMAs have retired: the operand stages are free, stage 0 of A is reused as reduction scratch
+    float* red = reinterpret_cast<float*>(s.a);   // [4 warps][2][BN]
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
       tmem_ld_wait();
-      if (!in_range) continue;
-      if (!valid && p.accumulate) continue;
-      uint4* dst = reinterpret_cast<uint4*>(optr + c);
+      float sv[32];
+      if (in_range && !(!valid && p.accumulate)) {
+        uint4* dst = reinterpret_cast<uint4*>(optr + c);
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
-        float f[8];
+        for (int v = 0; v < 4; ++v) {
+          float f[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(r[v * 8 + i]) : 0.f;
-        if (p.accumulate) {
-          Vec<bf16> prev;
-          prev.raw = dst[v];
-          float g[8];
-          prev.get(g);
+          for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(r[v * 8 + i]) : 0.f;
+          if (p.accumulate) {
+            Vec<bf16> prev;
+            prev.raw = dst[v];
+            float g[8];
+            prev.get(g);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] += g[i];
+            for (int i = 0; i < 8; ++i) f[i] += g[i];
+          }
+          Vec<bf16> o;
+          o.set(f);
+          dst[v] = o.raw;
+          if (STATS) o.get(&sv[v * 8]);   // statistics of the values as stored
         }
-        Vec<bf16> o;
-        o.set(f);
-        dst[v] = o.raw;
+      } else if (STATS) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sv[i] = 0.f;
+      }
+      if (STATS) {
+        float sq[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sq[i] = sv[i] * sv[i];
+        warp_transpose_sum(sv, lane);
+        warp_transpose_sum(sq, lane);
+        red[(q * 2 + 0) * BN + c + lane] = sv[0];
+        red[(q * 2 + 1) * BN + c + lane] = sq[0];
+      }
+    }
+    if (STATS) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+      const int e = q * 32 + lane;
+      for (int col = e; col < BN; col += 128) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          a += red[(w * 2 + 0) * BN + col];
+          b += red[(w * 2 + 1) * BN + col];
+        }
+        atomicAdd(&p.stats[n0 + col], (double)a);
+        atomicAdd(&p.stats[p.N + n0 + col], (double)b);
       }
     }
   }
@@ -419,7 +465,10 @@ template <int BN>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem_bytes<BN * BK * 2, TN_STAGES>();
   dim3 grid(ceil_div(p.M, BM), p.N / BN);
-  ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  if (p.stats)
+    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  else
+    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   SSB_LAUNCH_CHECK("conv_tn_kernel");
   return SSB_OK;
 }
@@ -461,10 +510,16 @@ int ssb_sm100_prepare() {
     return SSB_ERR_CUDA;
   }
   cudaError_t e = cudaSuccess;
-  e = cudaFuncSetAttribute(conv_tn_kernel<128, TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = cudaFuncSetAttribute(conv_tn_kernel<128, TN_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            smem_bytes<128 * BK * 2, TN_STAGES>());
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_tn_kernel<64, TN_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(conv_tn_kernel<64, TN_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes<64 * BK * 2, TN_STAGES>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tn_kernel<128, TN_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes<128 * BK * 2, TN_STAGES>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tn_kernel<64, TN_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_bytes<64 * BK * 2, TN_STAGES>());
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_wgrad_kernel<128, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -480,7 +535,7 @@ int ssb_sm100_prepare() {
 }
 
 int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
-                         cudaStream_t st) {
+                         double* stats, cudaStream_t st) {
   int rc = check_sm100_shape("ssb_conv1d_fwd", gin, gout);
   if (rc) return rc;
   TnParams p = {};
@@ -495,6 +550,7 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin
   p.o_pitch = gout.pitch;
   p.o_len = gout.len;
   p.accumulate = 0;
+  p.stats = stats;
   const long long rows_in = (long long)gin.B * gin.pitch;
   long long a_inner, a_outer, a_pitch;
   if (stride == 1) {

@@ -65,16 +65,17 @@ SIGNATURES = {
     "ssb_stem_conv_fwd": [_P, _P, _P, _I, _I, Geom, _I, _P],
     "ssb_stem_conv_wgrad": [_P, _P, _P, _I, _I, Geom, _I, _P],
     "ssb_conv1d_fwd": [_P, _P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
+    "ssb_conv1d_fwd_stats": [_P, _P, _P, _P, Geom, Geom, _I, _I, _P, _I, _I, _P],
     "ssb_conv1d_dgrad": [_P, _P, _P, _P, Geom, Geom, _I, _I, _I, _I, _I, _P],
     "ssb_conv1d_wgrad": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
     "ssb_weight_repack": [_P, _I, _I, _I, _P],
     "ssb_bn_stats": [_P, Geom, _P, _I, _P],
     "ssb_bn_act_fwd": [_P, _BNP, _P, _BNP, _P, Geom, _I, _I, _I, _P],
-    "ssb_stem_bn_relu_pool_fwd": [_P, _BNP, _P, Geom, Geom, _I, _I, _P],
+    "ssb_stem_bn_relu_pool_fwd": [_P, _BNP, _P, _P, Geom, Geom, _I, _I, _P],
     "ssb_bn_bwd_reduce": [_P, _P, _P, _P, _BNP, _P, _BNP, Geom, _I, _P],
     "ssb_bn_bwd_apply": [_P, _P, _P, _P, _BNP, _P, _P, _BNP, _P, _P, Geom, _I, _P],
-    "ssb_stem_bwd_reduce": [_P, _P, _BNP, Geom, Geom, _I, _P],
-    "ssb_stem_bwd_apply": [_P, _P, _BNP, _P, Geom, Geom, _I, _P],
+    "ssb_stem_bwd_reduce": [_P, _P, _P, _BNP, Geom, Geom, _I, _P],
+    "ssb_stem_bwd_apply": [_P, _P, _P, _BNP, _P, Geom, Geom, _I, _P],
     "ssb_head_cls_fwd": [_P, _P, _P, _P, Geom, _I, _F, _P, _P, _I, _P],
     "ssb_head_cls_bwd": [_P, _P, _P, _P, _P, _P, Geom, _I, _F, _P, _P, _I, _P],
     "ssb_upsample_fwd": [_P, _P, _I, _I, _I, _I, _I, _P],

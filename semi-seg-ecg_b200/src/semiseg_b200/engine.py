@@ -76,7 +76,7 @@ class StepEngine:
         self.sp_events = [torch.cuda.Event() for _ in range(8)]
         self.sp_used = [False] * 8
         self.sp_dev = torch.zeros(64, dtype=torch.uint8, device=dev)
-        self.loss_sums = torch.zeros(4, dtype=torch.float64, device=dev)
+        self.loss_sums = state.loss_sums   # inside the step's zero arena
         self.stats_host = [torch.zeros(4, dtype=torch.float64).pin_memory() for _ in range(8)]
         self.stats_events = [torch.cuda.Event() for _ in range(8)]
         self._pending: List[int] = []
@@ -95,8 +95,9 @@ class StepEngine:
         self.multi_stream = bool(int(os.environ.get("SSB_MULTI_STREAM", "1")))
         self.wgrad_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.teacher_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
+        self.repack_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.plan_s = NetPlan(weights, dtype, S, L, True, algo, grads=state.grads, sp_ptr=self.sp_dev.data_ptr(),
-                              wgrad_stream=self.wgrad_stream)
+                              wgrad_stream=self.wgrad_stream, state=state)
         self.plan_t: Optional[NetPlan] = None
         self.bufs_snap: Optional[torch.Tensor] = None
         if self.mode != _lib.LOSS_SUP:
@@ -170,23 +171,38 @@ class StepEngine:
         st = _stream()
         w, state = self.w, self.state
         n0 = _lib.load().ssb_launch_count()
-        call("ssb_memset_zero", state.grads.data_ptr(), state.grads.numel() * 4, st)
-        call("ssb_memset_zero", self.loss_sums.data_ptr(), 32, st)
-        self.plan_s.sh.repack(st)
+        call("ssb_memset_zero", state.zero_arena.data_ptr(), state.zero_arena.numel() * 4, st)   # grads, BN sums, loss sums
+        cur = torch.cuda.current_stream()
+        repacked = None
+        if self.repack_stream is not None:
+            # the weight repack overlaps the stem (which reads the fp32 master weights): own graph branch
+            fork0 = torch.cuda.Event()
+            fork0.record()
+            self.repack_stream.wait_event(fork0)
+            self.plan_s.sh.repack(self.repack_stream.cuda_stream)
+            if self.plan_t is not None and self.algorithm == "mean_teacher":
+                self.plan_t.sh.repack(self.repack_stream.cuda_stream)
+            repacked = torch.cuda.Event()
+            repacked.record(self.repack_stream)
+        else:
+            self.plan_s.sh.repack(st)
+            if self.plan_t is not None and self.algorithm == "mean_teacher":
+                self.plan_t.sh.repack(st)
+        self.plan_s.pre_block_event = repacked
         low_t = None
         if self.plan_t is not None:
-            if self.algorithm == "mean_teacher":
-                self.plan_t.sh.repack(st)
+            self.plan_t.pre_block_event = repacked
             if self.teacher_stream is not None:
                 if self.bufs_snap is not None:
                     self.bufs_snap.copy_(w.bufs, non_blocking=True)
                 fork = torch.cuda.Event()
                 fork.record()
                 self.teacher_stream.wait_event(fork)
-                low_t = self.plan_t.forward(self.x_uw, self.teacher_stream.cuda_stream, train_mode=False)
+                low_t = self.plan_t.forward(self.x_uw, self.teacher_stream.cuda_stream, train_mode=False,
+                                            stream=self.teacher_stream)
             else:
                 low_t = self.plan_t.forward(self.x_uw, st, train_mode=False)
-        self.plan_s.forward(self.x_s, st, train_mode=True)
+        self.plan_s.forward(self.x_s, st, train_mode=True, zero=False, stream=cur)
         if self.plan_t is not None and self.teacher_stream is not None:
             torch.cuda.current_stream().wait_stream(self.teacher_stream)
         low_s = self.plan_s.low

@@ -279,7 +279,15 @@ class TrainState:
 
     def __init__(self, w: WeightSet):
         lay, dev = w.layout, w.device
-        self.grads = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
+        # everything a step zeroes before it starts lives in ONE arena (one memset node per step):
+        # [gradients | BN forward sums | BN backward sums | loss sums] -- the tail is fp64
+        n_tail = 2 * lay.n_sums + 64
+        self.zero_arena = torch.zeros(lay.n_params + 2 * n_tail, dtype=torch.float32, device=dev)
+        self.grads = self.zero_arena[: lay.n_params]
+        tail = self.zero_arena[lay.n_params:].view(torch.float64)
+        self.sums = tail[: lay.n_sums]
+        self.bwd_sums = tail[lay.n_sums: 2 * lay.n_sums]
+        self.loss_sums = tail[2 * lay.n_sums: 2 * lay.n_sums + 4]
         self.exp_avg = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
         self.step = 0
@@ -290,7 +298,7 @@ class NetPlan:
 
     def __init__(self, weights: WeightSet, dtype: int, B: int, L: int, train: bool, algo: Optional[int] = None,
                  grads: Optional[torch.Tensor] = None, sp_ptr: int = 0, bufs: Optional[torch.Tensor] = None,
-                 wgrad_stream: Optional[torch.cuda.Stream] = None):
+                 wgrad_stream: Optional[torch.cuda.Stream] = None, state: Optional["TrainState"] = None):
         _lib.prepare()
         self.w = weights
         self.sh = weights.shadow(dtype)
@@ -310,6 +318,7 @@ class NetPlan:
         self.drop_mask_ptr = 0   # tests may inject an explicit keep-mask (u8 [B, Lh, Ch])
         self.debug = None        # tests: dict that receives clones of the block-output gradients
         self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
+        self.pre_block_event = None   # event the stream waits on after the stem (repacked weights ready)
         if algo is None:
             algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
             if os.environ.get("SSB_FORCE_SIMT"):   # debugging aid: generic CUDA-core conv kernels everywhere
@@ -349,8 +358,11 @@ class NetPlan:
             return torch.zeros(g.B * g.pitch, C_ or g.C, dtype=self.tdt, device=self.device)
 
         # ---- BN statistic arenas ----
-        self.sums = torch.zeros(self.lay.n_sums, dtype=torch.float64, device=self.device)
-        self.bwd_sums = torch.zeros(self.lay.n_sums, dtype=torch.float64, device=self.device)
+        if state is not None:   # statistic arenas inside the step's zero arena (TrainState)
+            self.sums, self.bwd_sums = state.sums, state.bwd_sums
+        else:
+            self.sums = torch.zeros(self.lay.n_sums, dtype=torch.float64, device=self.device)
+            self.bwd_sums = torch.zeros(self.lay.n_sums, dtype=torch.float64, device=self.device)
         self.mean_invstd = torch.zeros(self.lay.n_sums, dtype=torch.float32, device=self.device)
         self._bn_structs: Dict[str, BN] = {}
         for b in self.lay.bns:
@@ -360,6 +372,8 @@ class NetPlan:
         self.x_in: Optional[torch.Tensor] = None  # [B, C, L] fp32, bound by the caller
         self.c0 = act(self.g_stem)
         self.p0 = act(self.g_pool)
+        # max-pool routing slots saved by the train-mode stem tail for its backward pass
+        self.pool_arg = torch.zeros(B * p_pool, spec.stem_channels, dtype=torch.uint8, device=self.device) if train else None
         self.blk_bufs: List[Dict[str, torch.Tensor]] = []
         gin = self.g_pool
         for bd in self.lay.blocks:
@@ -407,9 +421,17 @@ class NetPlan:
     def _g(self, c: ConvDesc) -> int:
         return self.grads.data_ptr() + 4 * c.poff
 
-    def _conv_fwd(self, c: ConvDesc, x, y, gin: Geom, gout: Geom, st: int):
-        call("ssb_conv1d_fwd", x.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), y.data_ptr(), gin, gout,
-             c.k, c.stride, self.dtype, self._algo_for(c), st)
+    def _conv_fwd(self, c: ConvDesc, x, y, gin: Geom, gout: Geom, st: int, stats: Optional[BNDesc] = None):
+        """Conv1d; with `stats` the train-mode BatchNorm statistics of the output come out of the same
+        launch (epilogue of the tcgen05 kernel; the generic path issues the statistics pass itself)."""
+        if stats is None:
+            call("ssb_conv1d_fwd", x.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), y.data_ptr(), gin, gout,
+                 c.k, c.stride, self.dtype, self._algo_for(c), st)
+            return
+        call("ssb_conv1d_fwd_stats", x.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), y.data_ptr(), gin, gout,
+             c.k, c.stride, self._bn_structs[stats.prefix].sums, self.dtype, self._algo_for(c), st)
+        if self.sync_hook is not None:
+            self.sync_hook(self.sums[stats.soff: stats.soff + 2 * stats.C])
 
     def _algo_for(self, c: ConvDesc) -> int:
         if self.algo == _lib.ALGO_TCGEN05 and self.dtype == _lib.BF16 and c.cin % 64 == 0 and c.cout % 64 == 0:
@@ -461,9 +483,11 @@ class NetPlan:
             call("ssb_memset_zero", self.bwd_sums.data_ptr(), self.bwd_sums.numel() * 8, st)
 
     # ---- forward -------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, st: int, train_mode: Optional[bool] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, st: int, train_mode: Optional[bool] = None, zero: bool = True,
+                stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """x: [B, C, L] fp32 contiguous CUDA tensor.  Returns low-res logits [B, Lh, ncls] fp32.
-        train_mode: batch statistics + running-stat update + dropout (default: plan's mode)."""
+        train_mode: batch statistics + running-stat update + dropout (default: plan's mode).
+        zero=False: the caller has already zeroed the statistic arenas (step engine: one memset)."""
         tm = self.train if train_mode is None else train_mode
         if tm and not self.train:
             raise ValueError("plan was built for eval mode")
@@ -472,28 +496,24 @@ class NetPlan:
             f"input must be contiguous fp32 [{self.B},{spec.num_leads},{self.L}], got {tuple(x.shape)} {x.dtype}"
         self.x_in = x
         t = 1 if tm else 0
-        if tm:
+        if tm and zero:
             self.zero_stats(st)
         call("ssb_stem_conv_fwd", x.data_ptr(), self.w.w_ptr(lay.stem_conv), self.c0.data_ptr(), spec.num_leads,
              self.L, self.g_stem, dt, st)
         if tm:
             self._stats(self.c0, self.g_stem, lay.stem_bn, st)
-        call("ssb_stem_bn_relu_pool_fwd", self.c0.data_ptr(), self.bn(lay.stem_bn), self.p0.data_ptr(), self.g_stem,
-             self.g_pool, t, dt, st)
+        call("ssb_stem_bn_relu_pool_fwd", self.c0.data_ptr(), self.bn(lay.stem_bn), self.p0.data_ptr(),
+             self.pool_arg.data_ptr() if tm else None, self.g_stem, self.g_pool, t, dt, st)
         h, gin = self.p0, self.g_pool
+        if self.pre_block_event is not None:   # the stem reads the master weights; everything after it the repacked copies
+            (stream or torch.cuda.current_stream()).wait_event(self.pre_block_event)
         for bd, bufs in zip(lay.blocks, self.blk_bufs):
             gout = self.g_stage[bd.stage]
-            self._conv_fwd(bd.conv1, h, bufs["c1"], gin, gout, st)
-            if tm:
-                self._stats(bufs["c1"], gout, bd.bn1, st)
+            self._conv_fwd(bd.conv1, h, bufs["c1"], gin, gout, st, bd.bn1 if tm else None)
             call("ssb_bn_act_fwd", bufs["c1"].data_ptr(), self.bn(bd.bn1), None, None, bufs["a1"].data_ptr(), gout, 1, t, dt, st)
-            self._conv_fwd(bd.conv2, bufs["a1"], bufs["c2"], gout, gout, st)
-            if tm:
-                self._stats(bufs["c2"], gout, bd.bn2, st)
+            self._conv_fwd(bd.conv2, bufs["a1"], bufs["c2"], gout, gout, st, bd.bn2 if tm else None)
             if bd.convd is not None:
-                self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st)
-                if tm:
-                    self._stats(bufs["cd"], gout, bd.bnd, st)
+                self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st, bd.bnd if tm else None)
                 call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), bufs["cd"].data_ptr(), self.bn(bd.bnd),
                      bufs["out"].data_ptr(), gout, 1, t, dt, st)
             else:
@@ -502,9 +522,7 @@ class NetPlan:
             h, gin = bufs["out"], gout
         self.feat = h
         gfeat = gin
-        self._conv_fwd(lay.head_conv, h, self.ch, gfeat, self.g_head, st)
-        if tm:
-            self._stats(self.ch, self.g_head, lay.head_bn, st)
+        self._conv_fwd(lay.head_conv, h, self.ch, gfeat, self.g_head, st, lay.head_bn if tm else None)
         call("ssb_bn_act_fwd", self.ch.data_ptr(), self.bn(lay.head_bn), None, None, self.ah.data_ptr(), self.g_head, 1, t, dt, st)
         p = spec.dropout_ratio if tm else 0.0
         call("ssb_head_cls_fwd", self.ah.data_ptr(), self.w.params.data_ptr() + 4 * lay.cls_w_off,
@@ -604,10 +622,11 @@ class NetPlan:
             G = Gin
         self._join_wgrad()
         # stem tail + stem conv weight gradient
-        call("ssb_stem_bwd_reduce", G.data_ptr(), self.c0.data_ptr(), self.bn(lay.stem_bn), self.g_stem, self.g_pool, dt, st)
-        self._sync_bwd(lay.stem_bn)
-        call("ssb_stem_bwd_apply", G.data_ptr(), self.c0.data_ptr(), self.bn(lay.stem_bn), self.dc0.data_ptr(),
+        call("ssb_stem_bwd_reduce", G.data_ptr(), self.c0.data_ptr(), self.pool_arg.data_ptr(), self.bn(lay.stem_bn),
              self.g_stem, self.g_pool, dt, st)
+        self._sync_bwd(lay.stem_bn)
+        call("ssb_stem_bwd_apply", G.data_ptr(), self.c0.data_ptr(), self.pool_arg.data_ptr(), self.bn(lay.stem_bn),
+             self.dc0.data_ptr(), self.g_stem, self.g_pool, dt, st)
         call("ssb_stem_conv_wgrad", x.data_ptr(), self.dc0.data_ptr(), self._g(lay.stem_conv), spec.num_leads, self.L,
              self.g_stem, dt, st)
 

@@ -116,7 +116,7 @@ class ModelRuntime:
                 self._plans.pop(next(iter(self._plans)))
             self._plans[key] = NetPlan(self.weights, dtype, B, L, train, None,
                                        grads=self.state.grads if train else None,
-                                       sp_ptr=self._sp_dev.data_ptr())
+                                       sp_ptr=self._sp_dev.data_ptr(), state=self.state if train else None)
             self._plans[key].generation = 0
         return self._plans[key]
 

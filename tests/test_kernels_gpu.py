@@ -102,6 +102,15 @@ def test_conv_fwd_dgrad_wgrad(cin, cout, k, stride, L, dtype, algo):
         tag = f"dtype={dtype} algo={algo}"
         assert rel_err(from_flat(yb, B, po, Lo), yr.detach()) < TOL[dtype], "fwd " + tag
         assert halo_is_zero(yb, B, po, Lo), "fwd halo " + tag
+        # same conv with the BatchNorm statistics fused into the epilogue: identical output, and the sums
+        # are those of the stored values (what the separate ssb_bn_stats pass computes)
+        yb2 = torch.full((B * po, cout), 5.0, dtype=TDT[dtype], device=DEV)
+        sums = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+        call("ssb_conv1d_fwd_stats", xb.data_ptr(), kio.data_ptr(), koi.data_ptr(), yb2.data_ptr(), gi, go, k, stride,
+             sums.data_ptr(), dtype, algo, st())
+        assert torch.equal(yb2, yb), "fwd+stats output " + tag
+        ys = yb2.double()
+        assert rel_err(sums[:cout], ys.sum(0)) < 5e-6 and rel_err(sums[cout:], (ys * ys).sum(0)) < 5e-6, "fused stats " + tag
         # dgrad (plain, then accumulate)
         dyb = to_flat(dy, po, dtype)
         dxb = torch.full((B * pi, cin), 3.0, dtype=TDT[dtype], device=DEV)
@@ -256,13 +265,14 @@ def test_stem(dtype, Cl, Cs, L):
     assert halo_is_zero(c0, B, p0, L0)
     call("ssb_bn_stats", c0.data_ptr(), g0, t["sums"].data_ptr(), dtype, st())
     pb = torch.full((B * pp, Cs), 9.0, dtype=TDT[dtype], device=DEV)
-    call("ssb_stem_bn_relu_pool_fwd", c0.data_ptr(), C.byref(bn), pb.data_ptr(), g0, gp, 1, dtype, st())
+    arg = torch.full((B * pp, Cs), 9, dtype=torch.uint8, device=DEV)
+    call("ssb_stem_bn_relu_pool_fwd", c0.data_ptr(), C.byref(bn), pb.data_ptr(), arg.data_ptr(), g0, gp, 1, dtype, st())
     assert rel_err(from_flat(pb, B, pp, Lp), pr.detach()) < TOL[dtype]
     assert halo_is_zero(pb, B, pp, Lp)
     gpb = to_flat(gpool, pp, dtype)
     dc0 = torch.full((B * p0, Cs), 9.0, dtype=TDT[dtype], device=DEV)
-    call("ssb_stem_bwd_reduce", gpb.data_ptr(), c0.data_ptr(), C.byref(bn), g0, gp, dtype, st())
-    call("ssb_stem_bwd_apply", gpb.data_ptr(), c0.data_ptr(), C.byref(bn), dc0.data_ptr(), g0, gp, dtype, st())
+    call("ssb_stem_bwd_reduce", gpb.data_ptr(), c0.data_ptr(), arg.data_ptr(), C.byref(bn), g0, gp, dtype, st())
+    call("ssb_stem_bwd_apply", gpb.data_ptr(), c0.data_ptr(), arg.data_ptr(), C.byref(bn), dc0.data_ptr(), g0, gp, dtype, st())
     assert halo_is_zero(dc0, B, p0, L0)
     dw = torch.zeros(Cs, Cl, 7, device=DEV)
     call("ssb_stem_conv_wgrad", x.data_ptr(), dc0.data_ptr(), dw.data_ptr(), Cl, L, g0, dtype, st())
