@@ -94,7 +94,7 @@ def launch_cost(name, args, es):
     geoms = [a for a in args if isinstance(a, Geom)]
     if name in ("ssb_conv1d_fwd", "ssb_conv1d_fwd_stats", "ssb_conv1d_dgrad", "ssb_conv1d_wgrad"):
         gi, go = geoms
-        k = args[6] if name != "ssb_conv1d_wgrad" else args[5]
+        k = args[5]
         flops = 2.0 * go.B * go.len * go.C * gi.C * k
         w = gi.C * go.C * k
         if name == "ssb_conv1d_wgrad":

@@ -16,7 +16,7 @@
  *  - return value: 0 on success, negative ssb_status otherwise; the message is
  *    available (thread-local) from ssb_last_error().  The library never exits.
  *  - dtype: SSB_F32 (exact-parity mode, 1e-5) or SSB_BF16 (2e-2 mode) = storage type
- *    of activations / activation gradients / repacked weights.  Accumulation is fp32,
+ *    of activations / activation gradients / the weight copy the convs read.  Accumulation is fp32,
  *    BatchNorm statistics fp64, master weights / optimizer state fp32.
  *
  * Activation layout ("flat padded NLC"): a tensor with B samples, C channels and
@@ -95,14 +95,6 @@ typedef struct ssb_step_params {
   float pad[6];
 } ssb_step_params;
 
-/* descriptor of one conv weight for the multi-tensor repack */
-typedef struct ssb_repack_desc {
-  const float* w;  /* master weight [Cout][Cin][k] fp32 (reference layout) */
-  void* w_kio;     /* [k][Cin][Cout] in `dtype` */
-  void* w_koi;     /* [k][Cout][Cin] in `dtype` */
-  int32_t Cout, Cin, k, pad;
-} ssb_repack_desc;
-
 /* ---- library / device ------------------------------------------------------------ */
 int ssb_version(void);
 const char* ssb_last_error(void);
@@ -129,30 +121,30 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
 /* ---- Conv1d k in {1,3}, stride in {1,2}, padding k/2, dilation 1, bias=False --------
  * (resnet.py:32-49, 283-289; fcn_head.py:40-47).  gin/gout: geometries of the conv
  * input / output tensors (same B; gin.pitch == stride*gout.pitch).
- * w_kio / w_koi: repacked weights (ssb_weight_repack).  algo SSB_ALGO_TCGEN05 needs
- * dtype bf16 and Cin, Cout multiples of 64. */
-int ssb_conv1d_fwd(const void* x, const void* w_kio, const void* w_koi, void* y,
-                   ssb_geom gin, ssb_geom gout, int k, int stride,
-                   int dtype, int algo, ssb_stream_t stream);
+ * w: the weight in TAP-MAJOR layout [k][Cin][Cout] (element (co, ci, t) of the reference's
+ * [Cout][Cin][k] tensor at ((t*Cin + ci)*Cout + co)), in `dtype`.  This is the ONE weight
+ * layout of the library: fprop reads it as an N-contiguous B operand, dgrad as a K-contiguous
+ * one, wgrad writes it with 16-byte vector reductions; the host side exposes the reference
+ * shape as a strided view.  algo SSB_ALGO_TCGEN05 needs dtype bf16 and Cin, Cout multiples of 64. */
+int ssb_conv1d_fwd(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k,
+                   int stride, int dtype, int algo, ssb_stream_t stream);
 /* same conv with the BatchNorm statistics of its output fused into the epilogue:
  * sums[0:Cout] += sum_rows y, sums[Cout:2Cout] += sum_rows y^2 (fp64, of the values as stored);
  * sums == NULL: plain conv.  Replaces the separate statistics pass of native_batch_norm
  * (resnet.py:41,50; fcn_head.py:48) after the conv. */
-int ssb_conv1d_fwd_stats(const void* x, const void* w_kio, const void* w_koi, void* y,
-                         ssb_geom gin, ssb_geom gout, int k, int stride, double* sums,
-                         int dtype, int algo, ssb_stream_t stream);
+int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout,
+                         int k, int stride, double* sums, int dtype, int algo,
+                         ssb_stream_t stream);
 /* dx = conv_transpose(dy, w) (+ dx if accumulate) */
-int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void* dx,
-                     ssb_geom gin, ssb_geom gout, int k, int stride, int accumulate,
-                     int dtype, int algo, ssb_stream_t stream);
-/* dw[Cout][Cin][k] (fp32, reference layout) += x^T dy; the caller zeroes dw once per step */
+int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout,
+                     int k, int stride, int accumulate, int dtype, int algo, ssb_stream_t stream);
+/* dw[k][Cin][Cout] (fp32, tap-major like w) += x^T dy; the caller zeroes dw once per step */
 int ssb_conv1d_wgrad(const void* x, const void* dy, float* dw,
                      ssb_geom gin, ssb_geom gout, int k, int stride,
                      int dtype, int algo, ssb_stream_t stream);
-/* master fp32 [Cout][Cin][k] -> both GEMM layouts in `dtype`, all convs in one launch;
- * table_dev: device array of n descriptors */
-int ssb_weight_repack(const ssb_repack_desc* table_dev, int n, int max_elems, int dtype,
-                      ssb_stream_t stream);
+/* bf16 copy of a flat fp32 parameter arena (same element offsets; n multiple of 8): the
+ * storage-dtype weights the bf16 kernels read.  Replaces autocast's per-op weight casts. */
+int ssb_weight_shadow(const float* src, void* dst, size_t n, int dtype, ssb_stream_t stream);
 
 /* ---- BatchNorm1d (+ReLU, +residual, +MaxPool) -------------------------------------- */
 /* sums[0:C] += sum_rows x, sums[C:2C] += sum_rows x^2 (fp64) */

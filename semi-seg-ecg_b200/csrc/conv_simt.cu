@@ -2,13 +2,14 @@
 //  * stem direct conv k7 s2 p3 from the NCL fp32 input (HBM-bound, resnet.py:246-253)
 //  * tap-GEMM fprop / dgrad for k in {1,3}, stride in {1,2} over flat padded NLC rows
 //  * wgrad (split over rows, fp32 atomics into the reference-layout gradient)
-//  * multi-tensor weight repack (master fp32 [Cout][Cin][k] -> GEMM layouts)
+//  * flat storage-dtype copy of the parameter arena (conv weights are kept tap-major, [k][Cin][Cout])
 // These are the exact-parity (fp32) path and the fallback for shapes the tcgen05 kernels
 // (conv_sm100.cu) do not cover.  Replaces cuDNN fprop/dgrad/wgrad (SURVEY.md 2.2 K1,K4).
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------
 // tap-GEMM:  Out[o_mul*m + o_off][n] (+)= sum_tap sum_k A[a_mul*m + a_off[tap]][k] * W[w_tap[tap]][k][n]
+// (WT: the tap matrices are stored transposed, W[tap][n][k] -- dgrad reading the [k][Cin][Cout] weights)
 // ---------------------------------------------------------------------------------------
 struct TapSpec {
   int ntaps;
@@ -64,7 +65,7 @@ __device__ __forceinline__ void store4<bf16>(bf16* p, const float* f) {
   *reinterpret_cast<uint2*>(p) = raw;
 }
 
-template <typename T, bool ACC>
+template <typename T, bool ACC, bool WT>
 __global__ void __launch_bounds__(TG_THREADS)
 tap_gemm_kernel(const T* __restrict__ A, const T* __restrict__ W, T* __restrict__ Out, int M, int N, int K,
                 int a_rows, int a_mul, TapSpec taps, int o_mul, int o_off, int o_rows, int o_pitch, int o_len) {
@@ -84,6 +85,7 @@ tap_gemm_kernel(const T* __restrict__ A, const T* __restrict__ W, T* __restrict_
 
   const int la_row = tid >> 1, la_k = (tid & 1) * 8;  // A loader: row, k offset
   const int lb_k = tid >> 4, lb_n = (tid & 15) * 4;   // B loader
+  const int lt_n = tid >> 2, lt_k = (tid & 3) * 4;    // B loader, transposed storage: 4 consecutive k of one n
   for (int tp = 0; tp < taps.ntaps; ++tp) {
     const int m = m0 + la_row;
     const long long arow = (long long)a_mul * m + taps.a_off[tp];
@@ -98,7 +100,13 @@ tap_gemm_kernel(const T* __restrict__ A, const T* __restrict__ W, T* __restrict_
         for (int i = 0; i < 8; ++i) fa[i] = 0.f;
       }
       float fb[4];
-      if (k0 + lb_k < K && n0 + lb_n < N) {
+      if (WT) {
+        if (k0 + lt_k < K && n0 + lt_n < N) {
+          load4<T>(wt + (size_t)(n0 + lt_n) * K + k0 + lt_k, fb);
+        } else {
+          fb[0] = fb[1] = fb[2] = fb[3] = 0.f;
+        }
+      } else if (k0 + lb_k < K && n0 + lb_n < N) {
         load4<T>(wt + (size_t)(k0 + lb_k) * N + n0 + lb_n, fb);
       } else {
         fb[0] = fb[1] = fb[2] = fb[3] = 0.f;
@@ -106,7 +114,12 @@ tap_gemm_kernel(const T* __restrict__ A, const T* __restrict__ W, T* __restrict_
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < 8; ++i) As[la_k + i][la_row] = fa[i];
-      *reinterpret_cast<float4*>(&Bs[lb_k][lb_n]) = make_float4(fb[0], fb[1], fb[2], fb[3]);
+      if (WT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Bs[lt_k + i][lt_n] = fb[i];
+      } else {
+        *reinterpret_cast<float4*>(&Bs[lb_k][lb_n]) = make_float4(fb[0], fb[1], fb[2], fb[3]);
+      }
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < TG_BK; ++kk) {
@@ -164,7 +177,7 @@ __global__ void zero_parity_rows_kernel(T* out, int rows, int N, int parity) {
 }
 
 // ---------------------------------------------------------------------------------------
-// wgrad: dW[co][ci][tap] += sum_m X[a_mul*m + a_off[tap]][ci] * dY[m][co]
+// wgrad: dW[tap][ci][co] += sum_m X[a_mul*m + a_off[tap]][ci] * dY[m][co]
 // ---------------------------------------------------------------------------------------
 #define WG_T 64
 #define WG_BK 16
@@ -223,44 +236,25 @@ wgrad_kernel(const T* __restrict__ X, const T* __restrict__ dY, float* __restric
     for (int j = 0; j < 4; ++j) {
       const int co = co0 + tx * 4 + j;
       if (co >= Cout) continue;
-      atomicAdd(&dW[((size_t)co * Cin + ci) * k + wt], acc[i][j]);
+      atomicAdd(&dW[((size_t)wt * Cin + ci) * Cout + co], acc[i][j]);
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------
-// weight repack (all convs, one launch): fp32 [Cout][Cin][k] -> T [k][Cin][Cout], T [k][Cout][Cin]
-// one block = 32 co x 32 ci tile of one conv, transposed through shared memory so that both
-// outputs are written in 64-byte runs
+// storage-dtype copy of the whole parameter arena (same offsets): what the bf16 convs read.
+// The weights of the GEMM convs are kept in [k][Cin][Cout] in the master arena itself, so this
+// is a flat conversion (no per-tensor repack, no transposed copy).
 // ---------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) repack_kernel(const ssb_repack_desc* __restrict__ table, int max_tiles) {
+__global__ void __launch_bounds__(256) weight_shadow_kernel(const float* __restrict__ src, bf16* __restrict__ dst, size_t n8) {
   pdl_trigger();
   pdl_wait();
-  const ssb_repack_desc d = table[blockIdx.y];
-  const int tco = (d.Cout + 31) / 32, tci = (d.Cin + 31) / 32;
-  __shared__ float sw[32][32 * 3 + 1];
-  T* kio = (T*)d.w_kio;
-  T* koi = (T*)d.w_koi;
-  for (int tile = blockIdx.x; tile < tco * tci; tile += gridDim.x) {
-    const int co0 = (tile / tci) * 32, ci0 = (tile % tci) * 32;
-    const int nci = min(32, d.Cin - ci0), nco = min(32, d.Cout - co0);
-    const int rowlen = nci * d.k;
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < 32 * rowlen; idx += 256) {
-      const int r = idx / rowlen, c = idx - r * rowlen;
-      if (r < nco) sw[r][c] = d.w[((size_t)(co0 + r) * d.Cin + ci0) * d.k + c];
-    }
-    __syncthreads();
-    for (int j = 0; j < d.k; ++j) {
-      for (int idx = threadIdx.x; idx < 32 * 32; idx += 256) {
-        const int a = idx >> 5, b = idx & 31;
-        // koi[j][co0+a][ci0+b]
-        if (a < nco && b < nci) koi[((size_t)j * d.Cout + co0 + a) * d.Cin + ci0 + b] = from_f<T>(sw[a][b * d.k + j]);
-        // kio[j][ci0+a][co0+b]
-        if (a < nci && b < nco) kio[((size_t)j * d.Cin + ci0 + a) * d.Cout + co0 + b] = from_f<T>(sw[b][a * d.k + j]);
-      }
-    }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    Vec<bf16> o;
+    o.set(f);
+    o.store(dst + 8 * i);
   }
 }
 
@@ -426,9 +420,9 @@ static TapSpec fwd_taps(int k, int stride) {
   return t;
 }
 
-int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
+int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
                          double* stats, cudaStream_t st);
-int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
+int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
                            int accumulate, cudaStream_t st);
 int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
                            cudaStream_t st);
@@ -448,22 +442,22 @@ int ssb_simt_prepare() {
 
 extern "C" {
 
-int ssb_conv1d_fwd(const void* x, const void* w_kio, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k,
-                   int stride, int dtype, int algo, ssb_stream_t stream) {
-  return ssb_conv1d_fwd_stats(x, w_kio, w_koi, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
+int ssb_conv1d_fwd(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride, int dtype,
+                   int algo, ssb_stream_t stream) {
+  return ssb_conv1d_fwd_stats(x, w, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
 }
 
-int ssb_conv1d_fwd_stats(const void* x, const void* w_kio, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k,
-                         int stride, double* sums, int dtype, int algo, ssb_stream_t stream) {
+int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
+                         double* sums, int dtype, int algo, ssb_stream_t stream) {
   int rc = check_conv_geom("ssb_conv1d_fwd", gin, gout, k, stride);
   if (rc) return rc;
-  SSB_REQUIRE(x && y && w_kio && w_koi, "ssb_conv1d_fwd: null pointer");
+  SSB_REQUIRE(x && y && w, "ssb_conv1d_fwd: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_fwd: tcgen05 path needs bf16");
-    return ssb_conv1d_fwd_sm100(x, w_koi, y, gin, gout, k, stride, sums, to_stream(stream));
+    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, sums, to_stream(stream));
   }
   if (sums) {   // generic CUDA-core path: conv, then the statistics pass as its own launch
-    rc = ssb_conv1d_fwd_stats(x, w_kio, w_koi, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
+    rc = ssb_conv1d_fwd_stats(x, w, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
     if (rc) return rc;
     return ssb_bn_stats(y, gout, sums, dtype, stream);
   }
@@ -471,26 +465,26 @@ int ssb_conv1d_fwd_stats(const void* x, const void* w_kio, const void* w_koi, vo
   const TapSpec taps = fwd_taps(k, stride);
   dim3 grid(ceil_div(M, TG_BM), ceil_div(gout.C, TG_BN));
   SSB_DISPATCH_DTYPE(dtype, T, {
-    ssb_launch(tap_gemm_kernel<T, false>, dim3(grid), dim3(TG_THREADS), 0, to_stream(stream), 
-        (const T*)x, (const T*)w_kio, (T*)y, M, gout.C, gin.C, gin.B * gin.pitch, stride, taps, 1, 0, M, gout.pitch,
+    ssb_launch(tap_gemm_kernel<T, false, false>, dim3(grid), dim3(TG_THREADS), 0, to_stream(stream),
+        (const T*)x, (const T*)w, (T*)y, M, gout.C, gin.C, gin.B * gin.pitch, stride, taps, 1, 0, M, gout.pitch,
         gout.len);
   })
   SSB_LAUNCH_CHECK("ssb_conv1d_fwd");
   return SSB_OK;
 }
 
-int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void* dx, ssb_geom gin, ssb_geom gout,
-                     int k, int stride, int accumulate, int dtype, int algo, ssb_stream_t stream) {
+int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
+                     int accumulate, int dtype, int algo, ssb_stream_t stream) {
   int rc = check_conv_geom("ssb_conv1d_dgrad", gin, gout, k, stride);
   if (rc) return rc;
-  SSB_REQUIRE(dy && dx && w_kio && w_koi, "ssb_conv1d_dgrad: null pointer");
+  SSB_REQUIRE(dy && dx && w, "ssb_conv1d_dgrad: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_dgrad: tcgen05 path needs bf16");
-    return ssb_conv1d_dgrad_sm100(dy, w_kio, dx, gin, gout, k, stride, accumulate, to_stream(stream));
+    return ssb_conv1d_dgrad_sm100(dy, w, dx, gin, gout, k, stride, accumulate, to_stream(stream));
   }
   cudaStream_t st = to_stream(stream);
   const int rows_in = gin.B * gin.pitch, rows_out = gout.B * gout.pitch;
-  // GEMM: M over dx rows (or row pairs), N = Cin, K = Cout, weights [k][Cout][Cin] = w_koi
+  // GEMM: M over dx rows (or row pairs), N = Cin, K = Cout; the tap matrices of w are [Cin][Cout] = [N][K] (WT)
   SSB_DISPATCH_DTYPE(dtype, T, {
     if (stride == 1) {
       TapSpec t;
@@ -498,9 +492,9 @@ int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void*
       for (int j = 0; j < 3; ++j) { t.a_off[j] = (k == 3) ? 1 - j : 0; t.w_tap[j] = j < k ? j : 0; }
       dim3 grid(ceil_div(rows_in, TG_BM), ceil_div(gin.C, TG_BN));
       if (accumulate)
-        ssb_launch(tap_gemm_kernel<T, true>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w_koi, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
+        ssb_launch(tap_gemm_kernel<T, true, true>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
       else
-        ssb_launch(tap_gemm_kernel<T, false>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w_koi, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
+        ssb_launch(tap_gemm_kernel<T, false, true>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w, (T*)dx, rows_in, gin.C, gout.C, rows_out, 1, t, 1, 0, rows_in, gin.pitch, gin.len);
       SSB_LAUNCH_CHECK("ssb_conv1d_dgrad");
     } else {
       // dx row 2q+p: p=0 <- dy[q+1]*W0 + dy[q]*W2 ; p=1 <- dy[q+1]*W1   (k=1: p=1 <- dy[q+1]*W0)
@@ -524,9 +518,9 @@ int ssb_conv1d_dgrad(const void* dy, const void* w_kio, const void* w_koi, void*
           continue;
         }
         if (accumulate)
-          ssb_launch(tap_gemm_kernel<T, true>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w_koi, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
+          ssb_launch(tap_gemm_kernel<T, true, true>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
         else
-          ssb_launch(tap_gemm_kernel<T, false>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w_koi, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
+          ssb_launch(tap_gemm_kernel<T, false, true>, dim3(grid), dim3(TG_THREADS), 0, st, (const T*)dy, (const T*)w, (T*)dx, Mq, gin.C, gout.C, rows_out, 1, t, 2, p, rows_in, gin.pitch, gin.len);
         SSB_LAUNCH_CHECK("ssb_conv1d_dgrad");
       }
     }
@@ -562,14 +556,14 @@ int ssb_conv1d_wgrad(const void* x, const void* dy, float* dw, ssb_geom gin, ssb
   return SSB_OK;
 }
 
-int ssb_weight_repack(const ssb_repack_desc* table_dev, int n, int max_elems, int dtype, ssb_stream_t stream) {
-  SSB_REQUIRE(table_dev && n > 0 && max_elems > 0, "ssb_weight_repack: bad arguments");
-  int bx = ceil_div(max_elems, 32 * 32 * 3);
-  if (bx > 128) bx = 128;
-  if (bx < 1) bx = 1;
-  dim3 grid(bx, n);
-  SSB_DISPATCH_DTYPE(dtype, T, { ssb_launch(repack_kernel<T>, dim3(grid), dim3(256), 0, to_stream(stream), table_dev, bx); })
-  SSB_LAUNCH_CHECK("ssb_weight_repack");
+int ssb_weight_shadow(const float* src, void* dst, size_t n, int dtype, ssb_stream_t stream) {
+  SSB_REQUIRE(src && dst && n > 0 && n % 8 == 0, "ssb_weight_shadow: bad arguments (n=%zu must be a positive multiple of 8)", n);
+  SSB_REQUIRE(dtype == SSB_BF16, "ssb_weight_shadow: only the bf16 storage type needs a copy (fp32 kernels read the master arena)");
+  const size_t n8 = n / 8;
+  long long blocks = ceil_div_ll((long long)n8, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ssb_launch(weight_shadow_kernel, dim3((int)blocks), dim3(256), 0, to_stream(stream), src, (bf16*)dst, n8);
+  SSB_LAUNCH_CHECK("ssb_weight_shadow");
   return SSB_OK;
 }
 

@@ -2,8 +2,11 @@
 // tensor cores (tcgen05.mma, accumulators in TMEM), operands staged by TMA into 128B-swizzled
 // shared memory, mbarrier producer/consumer pipeline, warp-specialised roles.
 //
-//   fprop / dgrad  (conv_tn_kernel):  D[rows, N] = sum_taps A_tap[rows, K] * W_tap[N, K]^T
-//       both operands K-major; a k=3 conv is three row-shifted TMA boxes over the flat padded
+//   fprop / dgrad  (conv_tn_kernel):  D[rows, N] = sum_taps A_tap[rows, K] * B_tap[K, N]
+//       A (activations) K-major.  The weights live in ONE layout, [k][Cin][Cout]: for dgrad
+//       (N = Cin, K = Cout) that is a K-major B operand, for fprop (N = Cout, K = Cin) an
+//       MN-major one (template B_MN) -- no transposed weight copy exists.
+//       A k=3 conv is three row-shifted TMA boxes over the flat padded
 //       NLC activation (halo rows / TMA out-of-bounds zero fill implement the padding); a
 //       stride-2 conv reads the input through a [rows/2, 2C] "row pair" view.
 //   wgrad          (conv_wgrad_kernel): dW_tap[ci, co] = sum_rows X_tap[rows, ci] * dY[rows, co]
@@ -107,9 +110,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 // instruction descriptor: bf16 x bf16 -> f32, M = 128, N = n
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (mn_major ? ((1u << 15) | (1u << 16)) : 0u) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
 struct TnParams {
@@ -166,7 +169,7 @@ constexpr int smem_bytes() {
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool STATS>
+template <int BN, int STAGES, bool STATS, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
                const TnParams p) {
@@ -204,12 +207,20 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(&s.full[st], A_BYTES + B_BYTES);
         const int tap = it / KC, kc = it - tap * KC;
         tma_load_2d(s.a + st * A_BYTES, &tmA, &s.full[st], kc * BK + p.a_col_off[tap], m0 + p.a_row_off[tap]);
-        tma_load_2d(s.b + st * B_BYTES, &tmB, &s.full[st], kc * BK, p.w_tap[tap] * p.w_rows_per_tap + n0);
+        if (B_MN) {
+          // weights [tap][K][N], N contiguous: one [BK rows x 64 columns] box per 64-column atom
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_2d(s.b + st * B_BYTES + b * (BK * 128), &tmB, &s.full[st], n0 + b * 64,
+                        p.w_tap[tap] * p.w_rows_per_tap + kc * BK);
+        } else {
+          tma_load_2d(s.b + st * B_BYTES, &tmB, &s.full[st], kc * BK, p.w_tap[tap] * p.w_rows_per_tap + n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, false);
+      constexpr uint32_t idesc = make_idesc(BN, false, B_MN);
       for (int it = 0; it < iters; ++it) {
         const int st = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -218,9 +229,10 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t a0 = smem_u32(s.a + st * A_BYTES), b0 = smem_u32(s.b + st * B_BYTES);
 #pragma unroll
         for (int k4 = 0; k4 < BK / 16; ++k4) {
-          // K-major, 128B swizzle: 8-row groups are 1024 B apart; advance 16 elements = 32 B along K
-          umma_bf16(tmem_base, make_smem_desc(a0 + k4 * 32, 0, 1024), make_smem_desc(b0 + k4 * 32, 0, 1024), idesc,
-                    (uint32_t)((it | k4) != 0));
+          // K-major, 128B swizzle: 8-row groups are 1024 B apart; advance 16 elements = 32 B along K.
+          // MN-major B: 64-column atoms BK*128 B apart (LBO), 8-row K groups 1024 B apart (SBO); 16 K rows = 2048 B
+          const uint64_t bdesc = B_MN ? make_smem_desc(b0 + k4 * 2048, BK * 128, 1024) : make_smem_desc(b0 + k4 * 32, 0, 1024);
+          umma_bf16(tmem_base, make_smem_desc(a0 + k4 * 32, 0, 1024), bdesc, idesc, (uint32_t)((it | k4) != 0));
         }
         umma_commit(&s.empty[st]);   // frees the smem stage when these MMAs retire
       }
@@ -300,7 +312,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// wgrad: dW[co][ci][tap] += sum_rows X[rows + shift(tap)][ci] * dY[rows][co]
+// wgrad: dW[tap][ci][co] += sum_rows X[rows + shift(tap)][ci] * dY[rows][co]
 // GEMM rows (TMEM lanes) = ci tile of 128, columns = co tile of BN, reduction over rows.
 // grid = (ci tiles * co tiles, taps, splits)
 // ---------------------------------------------------------------------------------------------
@@ -367,7 +379,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc(BN, true);
+        constexpr uint32_t idesc = make_idesc(BN, true, true);
         for (int it = 0; it < iters; ++it) {
           const int st = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -397,14 +409,21 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
         tmem_ld_wait();
         if (ci >= p.Cin) continue;
+        // dw is [tap][Cin][Cout]: this thread's 32 columns are 128 contiguous bytes
+        float* dst = dw + ((size_t)wt * p.Cin + ci) * p.Cout + co0 + c;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int co = co0 + c + j;
-          if (co < p.Cout) {
-            float* dst = dw + ((size_t)co * p.Cin + ci) * p.k + wt;
-            const float v = __uint_as_float(r[j]);
-            if (p.nsplit > 1) atomicAdd(dst, v);
-            else *dst += v;
+        for (int j = 0; j < 32; j += 4) {
+          if (p.nsplit > 1) {
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                         : "memory");
+          } else {
+            float4 o = *reinterpret_cast<float4*>(dst + j);
+            o.x += __uint_as_float(r[j]);
+            o.y += __uint_as_float(r[j + 1]);
+            o.z += __uint_as_float(r[j + 2]);
+            o.w += __uint_as_float(r[j + 3]);
+            *reinterpret_cast<float4*>(dst + j) = o;
           }
         }
       }
@@ -461,27 +480,33 @@ int make_map(CUtensorMap* map, const void* base, long long inner, long long oute
 constexpr int TN_STAGES = 4;
 constexpr int WG_STAGES = 4;
 
-template <int BN>
+template <int BN, bool B_MN>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem_bytes<BN * BK * 2, TN_STAGES>();
   dim3 grid(ceil_div(p.M, BM), p.N / BN);
   if (p.stats)
-    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, B_MN>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   else
-    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, B_MN>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   SSB_LAUNCH_CHECK("conv_tn_kernel");
   return SSB_OK;
 }
 
+// b_mn: the weight matrix of one tap is [K rows][N contiguous] (fprop) instead of [N rows][K contiguous] (dgrad)
 int run_tn(const void* a_base, long long a_inner, long long a_outer, long long a_pitch, const void* w_base, int w_rows,
-           bf16* out, const TnParams& p, cudaStream_t st) {
+           bool b_mn, bf16* out, const TnParams& p, cudaStream_t st) {
   const int BN = (p.N % 128 == 0) ? 128 : 64;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, a_base, a_inner, a_outer, a_pitch, BK, BM);
   if (rc) return rc;
+  if (b_mn) {
+    rc = make_map(&tmB, w_base, p.N, w_rows, p.N, 64, BK);
+    if (rc) return rc;
+    return BN == 128 ? launch_tn<128, true>(tmA, tmB, out, p, st) : launch_tn<64, true>(tmA, tmB, out, p, st);
+  }
   rc = make_map(&tmB, w_base, p.K, w_rows, p.K, BK, BN);
   if (rc) return rc;
-  return BN == 128 ? launch_tn<128>(tmA, tmB, out, p, st) : launch_tn<64>(tmA, tmB, out, p, st);
+  return BN == 128 ? launch_tn<128, false>(tmA, tmB, out, p, st) : launch_tn<64, false>(tmA, tmB, out, p, st);
 }
 
 int check_sm100_shape(const char* who, const ssb_geom& gi, const ssb_geom& go) {
@@ -510,17 +535,13 @@ int ssb_sm100_prepare() {
     return SSB_ERR_CUDA;
   }
   cudaError_t e = cudaSuccess;
-  e = cudaFuncSetAttribute(conv_tn_kernel<128, TN_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           smem_bytes<128 * BK * 2, TN_STAGES>());
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_tn_kernel<64, TN_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_bytes<64 * BK * 2, TN_STAGES>());
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_tn_kernel<128, TN_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_bytes<128 * BK * 2, TN_STAGES>());
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(conv_tn_kernel<64, TN_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_bytes<64 * BK * 2, TN_STAGES>());
+#define SSB_TN_ATTR(BN_, ST_, MN_)                                                                                    \
+  if (e == cudaSuccess)                                                                                                 \
+    e = cudaFuncSetAttribute(conv_tn_kernel<BN_, TN_STAGES, ST_, MN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             smem_bytes<BN_ * BK * 2, TN_STAGES>());
+  SSB_TN_ATTR(128, false, false) SSB_TN_ATTR(64, false, false) SSB_TN_ATTR(128, true, false) SSB_TN_ATTR(64, true, false)
+  SSB_TN_ATTR(128, false, true) SSB_TN_ATTR(64, false, true) SSB_TN_ATTR(128, true, true) SSB_TN_ATTR(64, true, true)
+#undef SSB_TN_ATTR
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_wgrad_kernel<128, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_bytes<128 * BK * 2, WG_STAGES>());
@@ -534,7 +555,7 @@ int ssb_sm100_prepare() {
   return SSB_OK;
 }
 
-int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
+int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
                          double* stats, cudaStream_t st) {
   int rc = check_sm100_shape("ssb_conv1d_fwd", gin, gout);
   if (rc) return rc;
@@ -543,7 +564,7 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin
   p.N = gout.C;
   p.K = gin.C;
   p.ntaps = k;
-  p.w_rows_per_tap = gout.C;
+  p.w_rows_per_tap = gin.C;   // weight rows of one tap in [k][Cin][Cout]
   p.o_mul = 1;
   p.o_off = 0;
   p.o_rows = p.M;
@@ -567,10 +588,10 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w_koi, void* y, ssb_geom gin
       p.a_row_off[0] = -1; p.a_col_off[0] = gin.C; p.w_tap[0] = 0;
     }
   }
-  return run_tn(x, a_inner, a_outer, a_pitch, w_koi, k * gout.C, (bf16*)y, p, st);
+  return run_tn(x, a_inner, a_outer, a_pitch, w, k * gin.C, true, (bf16*)y, p, st);
 }
 
-int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
+int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
                            int accumulate, cudaStream_t st) {
   int rc = check_sm100_shape("ssb_conv1d_dgrad", gin, gout);
   if (rc) return rc;
@@ -589,7 +610,7 @@ int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom
     p.o_mul = 1;
     p.o_off = 0;
     for (int j = 0; j < k; ++j) { p.a_row_off[j] = (k == 3) ? 1 - j : 0; p.a_col_off[j] = 0; p.w_tap[j] = j; }
-    return run_tn(dy, gout.C, rows_out, gout.C, w_kio, k * gin.C, (bf16*)dx, p, st);
+    return run_tn(dy, gout.C, rows_out, gout.C, w, k * gin.C, false, (bf16*)dx, p, st);
   }
   // stride 2: dx row 2q+par; par 0 <- dy[q+1]*W0 + dy[q]*W2; par 1 <- dy[q+1]*W1 (k=1: par 1 <- dy[q+1]*W0)
   p.M = rows_in / 2;
@@ -611,7 +632,7 @@ int ssb_conv1d_dgrad_sm100(const void* dy, const void* w_kio, void* dx, ssb_geom
       }
       continue;
     }
-    rc = run_tn(dy, gout.C, rows_out, gout.C, w_kio, k * gin.C, (bf16*)dx, p, st);
+    rc = run_tn(dy, gout.C, rows_out, gout.C, w, k * gin.C, false, (bf16*)dx, p, st);
     if (rc) return rc;
   }
   return SSB_OK;

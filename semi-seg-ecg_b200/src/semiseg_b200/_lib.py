@@ -43,12 +43,7 @@ class StepParams(C.Structure):
                 ("conf_thresh", C.c_float), ("pad", C.c_float * 6)]
 
 
-class RepackDesc(C.Structure):
-    _fields_ = [("w", C.c_void_p), ("w_kio", C.c_void_p), ("w_koi", C.c_void_p), ("Cout", C.c_int32),
-                ("Cin", C.c_int32), ("k", C.c_int32), ("pad", C.c_int32)]
-
-
-assert C.sizeof(StepParams) == 64 and C.sizeof(RepackDesc) == 40 and C.sizeof(Geom) == 16
+assert C.sizeof(StepParams) == 64 and C.sizeof(Geom) == 16
 
 _P, _I, _F, _SZ, _D = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_double
 _BNP = C.POINTER(BN)
@@ -64,11 +59,11 @@ SIGNATURES = {
     "ssb_memset_zero": [_P, _SZ, _P],
     "ssb_stem_conv_fwd": [_P, _P, _P, _I, _I, Geom, _I, _P],
     "ssb_stem_conv_wgrad": [_P, _P, _P, _I, _I, Geom, _I, _P],
-    "ssb_conv1d_fwd": [_P, _P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
-    "ssb_conv1d_fwd_stats": [_P, _P, _P, _P, Geom, Geom, _I, _I, _P, _I, _I, _P],
-    "ssb_conv1d_dgrad": [_P, _P, _P, _P, Geom, Geom, _I, _I, _I, _I, _I, _P],
+    "ssb_conv1d_fwd": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
+    "ssb_conv1d_fwd_stats": [_P, _P, _P, Geom, Geom, _I, _I, _P, _I, _I, _P],
+    "ssb_conv1d_dgrad": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _I, _P],
     "ssb_conv1d_wgrad": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
-    "ssb_weight_repack": [_P, _I, _I, _I, _P],
+    "ssb_weight_shadow": [_P, _P, _SZ, _I, _P],
     "ssb_bn_stats": [_P, Geom, _P, _I, _P],
     "ssb_bn_act_fwd": [_P, _BNP, _P, _BNP, _P, Geom, _I, _I, _I, _P],
     "ssb_stem_bn_relu_pool_fwd": [_P, _BNP, _P, _P, Geom, Geom, _I, _I, _P],

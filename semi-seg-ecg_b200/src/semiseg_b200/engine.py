@@ -7,7 +7,7 @@ Replaces the bodies of the reference's hot loops (file:line relative to the refe
   NativeScaler / AdamW / EMA    src/utils/misc.py:242-256, src/utils/optimizer.py:22-34,
                                 src/algorithms/mean_teacher.py:139-149
 
-One step = [zero grads] -> repack weights -> pseudo-label forward (self-eval or EMA teacher)
+One step = [zero grads] -> bf16 weight copy -> pseudo-label forward (self-eval or EMA teacher)
 -> student forward (batch statistics, dropout) -> fused upsample+softmax+threshold+argmax+
 loss+gradient -> backward -> [NCCL gradient all-reduce] -> fused AdamW(+EMA).  All buffers are
 static; scalars that change per step (lr, bias corrections, RNG counter) live in a 64-byte
@@ -175,19 +175,19 @@ class StepEngine:
         cur = torch.cuda.current_stream()
         repacked = None
         if self.repack_stream is not None:
-            # the weight repack overlaps the stem (which reads the fp32 master weights): own graph branch
+            # the storage-dtype weight copy overlaps the stem (which reads the fp32 master weights): own graph branch
             fork0 = torch.cuda.Event()
             fork0.record()
             self.repack_stream.wait_event(fork0)
-            self.plan_s.sh.repack(self.repack_stream.cuda_stream)
+            self.plan_s.sh.refresh(self.repack_stream.cuda_stream)
             if self.plan_t is not None and self.algorithm == "mean_teacher":
-                self.plan_t.sh.repack(self.repack_stream.cuda_stream)
+                self.plan_t.sh.refresh(self.repack_stream.cuda_stream)
             repacked = torch.cuda.Event()
             repacked.record(self.repack_stream)
         else:
-            self.plan_s.sh.repack(st)
+            self.plan_s.sh.refresh(st)
             if self.plan_t is not None and self.algorithm == "mean_teacher":
-                self.plan_t.sh.repack(st)
+                self.plan_t.sh.refresh(st)
         self.plan_s.pre_block_event = repacked
         low_t = None
         if self.plan_t is not None:

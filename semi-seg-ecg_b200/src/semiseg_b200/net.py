@@ -1,7 +1,7 @@
 """Network description, flat parameter arenas and the hand-scheduled forward/backward plan.
 
 This is the host side of the hot path: it owns the memory layout in HBM (flat padded NLC
-activations, flat fp32 parameter / gradient / optimizer arenas, repacked GEMM weights) and
+activations, flat fp32 parameter / gradient / optimizer arenas, storage-dtype weight copy) and
 issues the C-ABI kernels of libsemiseg_b200 in dependency order on one CUDA stream.  No
 autograd, no ATen compute ops: torch is used for allocation and streams only.
 
@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import BN, Geom, RepackDesc, StepParams, call
+from ._lib import BN, Geom, StepParams, call
 
 
 # --------------------------------------------------------------------------------------
@@ -57,7 +57,7 @@ class ConvDesc:
     k: int
     stride: int
     poff: int = 0      # offset (floats) in the parameter arena
-    soff: int = 0      # offset (elements) in each repacked-weight arena
+    tap_major: bool = True   # stored [k][Cin][Cout] (GEMM convs); the stem keeps the reference layout
 
 
 @dataclass
@@ -93,15 +93,15 @@ class ParamLayout:
     def __init__(self, spec: SegNetSpec):
         self.spec = spec
         self.params: List[Tuple[str, Tuple[int, ...], int]] = []   # (name, shape, offset)
+        self.tap_major: Dict[str, bool] = {}
         self.convs: List[ConvDesc] = []
         self.bns: List[BNDesc] = []
         self.blocks: List[BlockDesc] = []
         self._poff = 0
         self._roff = 0
         self._soff = 0
-        self._woff = 0
 
-        self.stem_conv = self._conv("backbone.stem.0.weight", spec.stem_channels, spec.num_leads, 7, 2, repack=False)
+        self.stem_conv = self._conv("backbone.stem.0.weight", spec.stem_channels, spec.num_leads, 7, 2, tap_major=False)
         self.stem_bn = self._bn("backbone.stem.1", spec.stem_channels)
         inpl = spec.stem_channels
         for i, nb in enumerate(spec.stage_blocks):
@@ -127,7 +127,6 @@ class ParamLayout:
         self.n_params = self._poff
         self.n_bufs = self._roff
         self.n_sums = self._soff
-        self.n_shadow = self._woff
         self.numel = sum(int(torch.Size(s).numel()) for _, s, _ in self.params)
 
     def _param(self, name, shape) -> int:
@@ -139,13 +138,25 @@ class ParamLayout:
         self._poff += (n + ALIGN - 1) // ALIGN * ALIGN
         return off
 
-    def _conv(self, name, cout, cin, k, stride, repack=True) -> ConvDesc:
-        d = ConvDesc(name, cout, cin, k, stride, self._param(name, (cout, cin, k)))
-        if repack:
-            d.soff = self._woff
-            self._woff += (cout * cin * k + ALIGN - 1) // ALIGN * ALIGN
+    def _conv(self, name, cout, cin, k, stride, tap_major=True) -> ConvDesc:
+        d = ConvDesc(name, cout, cin, k, stride, self._param(name, (cout, cin, k)), tap_major)
+        self.tap_major[name] = tap_major
+        if tap_major:
             self.convs.append(d)
         return d
+
+    def view(self, arena: torch.Tensor, name: str, shape, off: int) -> torch.Tensor:
+        """The tensor `name` inside a flat arena, in the reference's shape.  GEMM-conv weights are stored
+        tap-major ([k][Cin][Cout]) and come back as a strided [Cout, Cin, k] view: values and indexing are
+        the reference's, only the memory order differs."""
+        n = 1
+        for d in shape:
+            n *= d
+        flat = arena[off: off + n]
+        if self.tap_major.get(name, False):
+            cout, cin, k = shape
+            return flat.view(k, cin, cout).permute(2, 1, 0)
+        return flat.view(shape)
 
     def _bn(self, prefix, Cn) -> BNDesc:
         d = BNDesc(prefix, Cn)
@@ -174,38 +185,27 @@ def _torch_dtype(dtype: int):
 
 
 class Shadow:
-    """Repacked GEMM copies of all conv weights of one WeightSet in one storage dtype."""
+    """Storage-dtype copy of a WeightSet's parameter arena (same element offsets).  fp32 kernels read the
+    master arena itself; the bf16 copy is one flat conversion launch (ssb_weight_shadow)."""
 
     def __init__(self, w: "WeightSet", dtype: int):
-        layout, device = w.layout, w.device
+        self.w = w
         self.dtype = dtype
-        self.n = len(layout.convs)
-        tdt = _torch_dtype(dtype)
-        self.kio = torch.zeros(max(layout.n_shadow, 1), dtype=tdt, device=device)
-        self.koi = torch.zeros(max(layout.n_shadow, 1), dtype=tdt, device=device)
-        es = self.kio.element_size()
-        tab = (RepackDesc * self.n)()
-        for i, c in enumerate(layout.convs):
-            tab[i].w = w.params.data_ptr() + 4 * c.poff
-            tab[i].w_kio = self.kio.data_ptr() + es * c.soff
-            tab[i].w_koi = self.koi.data_ptr() + es * c.soff
-            tab[i].Cout, tab[i].Cin, tab[i].k = c.cout, c.cin, c.k
-        raw = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8)
-        self.table = raw.to(device)
-        self.max_elems = max(c.cout * c.cin * c.k for c in layout.convs)
+        self.buf = torch.zeros(w.layout.n_params, dtype=torch.bfloat16, device=w.device) if dtype == _lib.BF16 else None
 
-    def repack(self, stream: int) -> None:
-        call("ssb_weight_repack", self.table.data_ptr(), self.n, self.max_elems, self.dtype, stream)
+    def refresh(self, stream: int) -> None:
+        if self.buf is not None:
+            call("ssb_weight_shadow", self.w.params.data_ptr(), self.buf.data_ptr(), self.w.params.numel(), self.dtype, stream)
 
-    def kio_ptr(self, c: ConvDesc) -> int:
-        return self.kio.data_ptr() + self.kio.element_size() * c.soff
-
-    def koi_ptr(self, c: ConvDesc) -> int:
-        return self.koi.data_ptr() + self.koi.element_size() * c.soff
+    def ptr(self, c: ConvDesc) -> int:
+        if self.buf is None:
+            return self.w.params.data_ptr() + 4 * c.poff
+        return self.buf.data_ptr() + 2 * c.poff
 
 
 class WeightSet:
-    """One set of network weights in HBM: fp32 master arena, BN buffers, repacked GEMM copies."""
+    """One set of network weights in HBM: fp32 master arena (GEMM-conv weights tap-major), BN buffers,
+    storage-dtype shadow copies."""
 
     def __init__(self, layout: ParamLayout, device, nbt_float: bool = False):
         self.layout = layout
@@ -227,13 +227,12 @@ class WeightSet:
     def param_view(self, name: str) -> torch.Tensor:
         for n, shape, off in self.layout.params:
             if n == name:
-                numel = int(torch.Size(shape).numel())
-                return self.params[off: off + numel].view(shape)
+                return self.layout.view(self.params, n, shape, off)
         raise KeyError(name)
 
     def param_views(self, arena: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         a = self.params if arena is None else arena
-        return {n: a[off: off + int(torch.Size(s).numel())].view(s) for n, s, off in self.layout.params}
+        return {n: self.layout.view(a, n, s, off) for n, s, off in self.layout.params}
 
     def buffer_views(self) -> Dict[str, torch.Tensor]:
         out = {}
@@ -318,7 +317,7 @@ class NetPlan:
         self.drop_mask_ptr = 0   # tests may inject an explicit keep-mask (u8 [B, Lh, Ch])
         self.debug = None        # tests: dict that receives clones of the block-output gradients
         self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
-        self.pre_block_event = None   # event the stream waits on after the stem (repacked weights ready)
+        self.pre_block_event = None   # event the stream waits on after the stem (storage-dtype weight copy ready)
         if algo is None:
             algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
             if os.environ.get("SSB_FORCE_SIMT"):   # debugging aid: generic CUDA-core conv kernels everywhere
@@ -425,10 +424,10 @@ class NetPlan:
         """Conv1d; with `stats` the train-mode BatchNorm statistics of the output come out of the same
         launch (epilogue of the tcgen05 kernel; the generic path issues the statistics pass itself)."""
         if stats is None:
-            call("ssb_conv1d_fwd", x.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), y.data_ptr(), gin, gout,
+            call("ssb_conv1d_fwd", x.data_ptr(), self.sh.ptr(c), y.data_ptr(), gin, gout,
                  c.k, c.stride, self.dtype, self._algo_for(c), st)
             return
-        call("ssb_conv1d_fwd_stats", x.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), y.data_ptr(), gin, gout,
+        call("ssb_conv1d_fwd_stats", x.data_ptr(), self.sh.ptr(c), y.data_ptr(), gin, gout,
              c.k, c.stride, self._bn_structs[stats.prefix].sums, self.dtype, self._algo_for(c), st)
         if self.sync_hook is not None:
             self.sync_hook(self.sums[stats.soff: stats.soff + 2 * stats.C])
@@ -505,7 +504,7 @@ class NetPlan:
         call("ssb_stem_bn_relu_pool_fwd", self.c0.data_ptr(), self.bn(lay.stem_bn), self.p0.data_ptr(),
              self.pool_arg.data_ptr() if tm else None, self.g_stem, self.g_pool, t, dt, st)
         h, gin = self.p0, self.g_pool
-        if self.pre_block_event is not None:   # the stem reads the master weights; everything after it the repacked copies
+        if self.pre_block_event is not None:   # the stem reads the master weights; everything after it the storage-dtype copy
             (stream or torch.cuda.current_stream()).wait_event(self.pre_block_event)
         for bd, bufs in zip(lay.blocks, self.blk_bufs):
             gout = self.g_stage[bd.stage]
@@ -553,7 +552,7 @@ class NetPlan:
         sc_f = self._scratch[(gfeat.pitch, gfeat.len, gfeat.C)]
         hc = lay.head_conv
         G = sc_f["gA"]
-        call("ssb_conv1d_dgrad", sc_h["gB"].data_ptr(), self.sh.kio_ptr(hc), self.sh.koi_ptr(hc), G.data_ptr(), gfeat,
+        call("ssb_conv1d_dgrad", sc_h["gB"].data_ptr(), self.sh.ptr(hc), G.data_ptr(), gfeat,
              self.g_head, hc.k, hc.stride, 0, dt, self._algo_for(hc), st)
         self._wgrad(hc, self.feat, sc_h["gB"], gfeat, self.g_head, st)
 
@@ -596,7 +595,7 @@ class NetPlan:
                 if bd.convd is not None:
                     self.debug[bd.prefix + ".downsample.0"] = self.to_ncl(dcd, gout)
             c = bd.conv2
-            call("ssb_conv1d_dgrad", dc2.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), da1.data_ptr(), gout, gout,
+            call("ssb_conv1d_dgrad", dc2.data_ptr(), self.sh.ptr(c), da1.data_ptr(), gout, gout,
                  c.k, c.stride, 0, dt, self._algo_for(c), st)
             self._wgrad(c, bufs["a1"], dc2, gout, gout, st)
             # bn1 + relu backward -> dc1 (reuses gB: dc2 is dead)
@@ -611,12 +610,12 @@ class NetPlan:
                 self.debug[bd.prefix + ".conv1"] = self.to_ncl(dc1, gout)
             c = bd.conv1
             acc = 0 if bd.convd is not None else 1   # identity residual: Gin already holds g
-            call("ssb_conv1d_dgrad", dc1.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), Gin.data_ptr(), gin, gout,
+            call("ssb_conv1d_dgrad", dc1.data_ptr(), self.sh.ptr(c), Gin.data_ptr(), gin, gout,
                  c.k, c.stride, acc, dt, self._algo_for(c), st)
             self._wgrad(c, xin, dc1, gin, gout, st)
             if bd.convd is not None:
                 c = bd.convd
-                call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.kio_ptr(c), self.sh.koi_ptr(c), Gin.data_ptr(), gin, gout,
+                call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.ptr(c), Gin.data_ptr(), gin, gout,
                      c.k, c.stride, 1, dt, self._algo_for(c), st)
                 self._wgrad(c, xin, dcd, gin, gout, st)
             G = Gin

@@ -135,7 +135,7 @@ class _SegNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, rt: ModelRuntime, plan: NetPlan, train_mode: bool, *params):
         st = torch.cuda.current_stream().cuda_stream
-        plan.sh.repack(st)
+        plan.sh.refresh(st)
         if train_mode and rt.spec.dropout_ratio > 0:
             rt.bump_rng()
         xin = x.detach().to(torch.float32).contiguous()

@@ -39,7 +39,6 @@ def test_library_loads_and_exports_all_symbols():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.Geom) == 16
     assert ctypes.sizeof(_lib.StepParams) == 64
-    assert ctypes.sizeof(_lib.RepackDesc) == 40
     assert ctypes.sizeof(_lib.BN) == 88
     assert _lib.StepParams.conf_thresh.offset == 36 and _lib.StepParams.grad_scale.offset == 32
 

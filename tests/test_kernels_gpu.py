@@ -52,11 +52,9 @@ def rq(x, dtype):
     return x.to(TDT[dtype]).double()
 
 
-def repack(w, dtype):
-    Cout, Cin, k = w.shape
-    kio = w.permute(2, 1, 0).contiguous().to(TDT[dtype])
-    koi = w.permute(2, 0, 1).contiguous().to(TDT[dtype])
-    return kio, koi
+def tap_major(w, dtype):
+    """reference [Cout, Cin, k] -> the library's weight layout [k][Cin][Cout] in the storage dtype"""
+    return w.permute(2, 1, 0).contiguous().to(TDT[dtype])
 
 
 CONV_CASES = [(8, 16, 3, 1, 37), (16, 16, 3, 2, 37), (8, 16, 1, 2, 38), (16, 8, 1, 1, 20), (64, 64, 3, 1, 157),
@@ -95,10 +93,10 @@ def test_conv_fwd_dgrad_wgrad(cin, cout, k, stride, L, dtype, algo):
         yr = F.conv1d(xr, wr, None, stride=stride, padding=k // 2)
         assert yr.shape[2] == Lo
         yr.backward(dyq)
-        kio, koi = repack(w.float(), dtype)
+        wt = tap_major(w.float(), dtype)
         xb = to_flat(x, pi, dtype)
         yb = torch.full((B * po, cout), 7.0, dtype=TDT[dtype], device=DEV)
-        call("ssb_conv1d_fwd", xb.data_ptr(), kio.data_ptr(), koi.data_ptr(), yb.data_ptr(), gi, go, k, stride, dtype, algo, st())
+        call("ssb_conv1d_fwd", xb.data_ptr(), wt.data_ptr(), yb.data_ptr(), gi, go, k, stride, dtype, algo, st())
         tag = f"dtype={dtype} algo={algo}"
         assert rel_err(from_flat(yb, B, po, Lo), yr.detach()) < TOL[dtype], "fwd " + tag
         assert halo_is_zero(yb, B, po, Lo), "fwd halo " + tag
@@ -106,7 +104,7 @@ def test_conv_fwd_dgrad_wgrad(cin, cout, k, stride, L, dtype, algo):
         # are those of the stored values (what the separate ssb_bn_stats pass computes)
         yb2 = torch.full((B * po, cout), 5.0, dtype=TDT[dtype], device=DEV)
         sums = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
-        call("ssb_conv1d_fwd_stats", xb.data_ptr(), kio.data_ptr(), koi.data_ptr(), yb2.data_ptr(), gi, go, k, stride,
+        call("ssb_conv1d_fwd_stats", xb.data_ptr(), wt.data_ptr(), yb2.data_ptr(), gi, go, k, stride,
              sums.data_ptr(), dtype, algo, st())
         assert torch.equal(yb2, yb), "fwd+stats output " + tag
         ys = yb2.double()
@@ -114,38 +112,30 @@ def test_conv_fwd_dgrad_wgrad(cin, cout, k, stride, L, dtype, algo):
         # dgrad (plain, then accumulate)
         dyb = to_flat(dy, po, dtype)
         dxb = torch.full((B * pi, cin), 3.0, dtype=TDT[dtype], device=DEV)
-        call("ssb_conv1d_dgrad", dyb.data_ptr(), kio.data_ptr(), koi.data_ptr(), dxb.data_ptr(), gi, go, k, stride, 0, dtype, algo, st())
+        call("ssb_conv1d_dgrad", dyb.data_ptr(), wt.data_ptr(), dxb.data_ptr(), gi, go, k, stride, 0, dtype, algo, st())
         assert rel_err(from_flat(dxb, B, pi, L), xr.grad) < TOL[dtype], "dgrad " + tag
         assert halo_is_zero(dxb, B, pi, L), "dgrad halo " + tag
         base = torch.randn(B, cin, L, device=DEV, dtype=torch.float64)
         dxb2 = to_flat(base, pi, dtype)
-        call("ssb_conv1d_dgrad", dyb.data_ptr(), kio.data_ptr(), koi.data_ptr(), dxb2.data_ptr(), gi, go, k, stride, 1, dtype, algo, st())
+        call("ssb_conv1d_dgrad", dyb.data_ptr(), wt.data_ptr(), dxb2.data_ptr(), gi, go, k, stride, 1, dtype, algo, st())
         assert rel_err(from_flat(dxb2, B, pi, L), xr.grad + rq(base, dtype)) < TOL[dtype] * 2, "dgrad acc " + tag
         assert halo_is_zero(dxb2, B, pi, L)
-        # wgrad (accumulates into fp32 [Cout][Cin][k])
-        dw = torch.zeros(cout, cin, k, dtype=torch.float32, device=DEV)
+        # wgrad (accumulates into fp32 [k][Cin][Cout], the weight layout)
+        dw = torch.zeros(k, cin, cout, dtype=torch.float32, device=DEV)
         call("ssb_conv1d_wgrad", xb.data_ptr(), dyb.data_ptr(), dw.data_ptr(), gi, go, k, stride, dtype, algo, st())
-        assert rel_err(dw, wr.grad) < TOL[dtype], "wgrad " + tag
+        assert rel_err(dw.permute(2, 1, 0), wr.grad) < TOL[dtype], "wgrad " + tag
+        call("ssb_conv1d_wgrad", xb.data_ptr(), dyb.data_ptr(), dw.data_ptr(), gi, go, k, stride, dtype, algo, st())
+        assert rel_err(dw.permute(2, 1, 0), 2 * wr.grad) < TOL[dtype], "wgrad accumulate " + tag
 
 
-def test_weight_repack():
-    from semiseg_b200._lib import RepackDesc
+def test_weight_shadow():
     torch.manual_seed(0)
-    ws = [torch.randn(16, 8, 3, device=DEV), torch.randn(64, 64, 1, device=DEV)]
-    for dtype in (_lib.F32, _lib.BF16):
-        tab = (RepackDesc * len(ws))()
-        outs = []
-        for i, w in enumerate(ws):
-            kio = torch.zeros(w.numel(), dtype=TDT[dtype], device=DEV)
-            koi = torch.zeros(w.numel(), dtype=TDT[dtype], device=DEV)
-            outs.append((kio, koi))
-            tab[i].w, tab[i].w_kio, tab[i].w_koi = w.data_ptr(), kio.data_ptr(), koi.data_ptr()
-            tab[i].Cout, tab[i].Cin, tab[i].k = w.shape
-        tdev = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(DEV)
-        call("ssb_weight_repack", tdev.data_ptr(), len(ws), max(w.numel() for w in ws), dtype, st())
-        for w, (kio, koi) in zip(ws, outs):
-            rk, ro = repack(w, dtype)
-            assert torch.equal(kio.view_as(rk), rk) and torch.equal(koi.view_as(ro), ro)
+    src = torch.randn(4096 + 64, device=DEV)
+    dst = torch.zeros(src.numel(), dtype=torch.bfloat16, device=DEV)
+    call("ssb_weight_shadow", src.data_ptr(), dst.data_ptr(), src.numel(), _lib.BF16, st())
+    assert torch.equal(dst, src.to(torch.bfloat16))
+    with pytest.raises(RuntimeError):
+        call("ssb_weight_shadow", src.data_ptr(), dst.data_ptr(), 12, _lib.BF16, st())
 
 
 def make_bn(Cn, train_count_mul=0):
@@ -499,4 +489,4 @@ def test_errors_are_reported():
     rc = lib.ssb_bn_stats(None, g, None, 0, None)
     assert rc != 0 and b"ssb_bn_stats" in lib.ssb_last_error()
     with pytest.raises(RuntimeError):
-        call("ssb_conv1d_fwd", None, None, None, None, Geom(1, 10, 8, 8), Geom(1, 10, 8, 8), 5, 1, 0, 0, None)
+        call("ssb_conv1d_fwd", None, None, None, Geom(1, 10, 8, 8), Geom(1, 10, 8, 8), 5, 1, 0, 0, None)
