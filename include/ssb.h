@@ -135,6 +135,13 @@ int ssb_conv1d_fwd(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom
 int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout,
                          int k, int stride, double* sums, int dtype, int algo,
                          ssb_stream_t stream);
+/* eval-mode conv + BatchNorm (running statistics) [+ residual] [+ ReLU] in one launch:
+ * y = [relu]( bn(conv(x, w)) [+ res] ); res: tensor in the output geometry or NULL.  This is the
+ * forward of the pseudo-label / teacher / inference passes (fixmatch.py:87-93, mean_teacher.py:90-92:
+ * model.eval() => BatchNorm is a fixed per-channel affine map folded into the conv epilogue). */
+int ssb_conv1d_bn_act_fwd(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout,
+                          int k, int stride, const ssb_bn* bn, const void* res, int relu,
+                          int dtype, int algo, ssb_stream_t stream);
 /* dx = conv_transpose(dy, w) (+ dx if accumulate) */
 int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout,
                      int k, int stride, int accumulate, int dtype, int algo, ssb_stream_t stream);

@@ -6,7 +6,7 @@
 #include "common.cuh"
 
 std::atomic<long long> g_ssb_launches{0};
-int g_ssb_pdl = 0;   // env SSB_PDL: see common.cuh
+int g_ssb_pdl = 2;   // env SSB_PDL: see common.cuh
 static thread_local char g_err[512] = "";
 
 void ssb_set_error(const char* fmt, ...) {

@@ -46,14 +46,16 @@ extern std::atomic<long long> g_ssb_launches;
   }
 
 // ---- programmatic dependent launch (PDL) -------------------------------------------------
-// Every kernel is launched with the programmatic-stream-serialization attribute: the next
-// kernel in the stream may be scheduled while this one is still running, and blocks at
-// pdl_wait() until all of this kernel's memory operations are visible.  Kernels call
-// pdl_trigger() first thing and pdl_wait() before their first global-memory access, so launch
-// latency / CTA scheduling / on-chip prologues overlap with the predecessor's tail.
+// A kernel launched with the programmatic-stream-serialization attribute may be scheduled while
+// its predecessor in the stream is still running; it blocks at pdl_wait() until all of the
+// predecessor's memory operations are visible.  Kernels call pdl_wait() before their first
+// global-memory access, so launch latency / CTA scheduling / on-chip prologues (barrier init,
+// TMEM allocation, tensor-map prefetch) overlap with the predecessor's tail.
 extern int g_ssb_pdl;
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// The dependent grid is released only once this one is past its own wait (measured: releasing at kernel
+// entry lets a whole chain of parked grids pile up and is slower; profiles/r1b_pdl.md).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {}
 
 // g_ssb_pdl (env SSB_PDL): 0 = plain launches, 1 = every launch carries the attribute, 2 = only the
 // kernels with an on-chip prologue worth overlapping (the tcgen05 convs: barrier init, TMEM alloc,

@@ -421,7 +421,7 @@ static TapSpec fwd_taps(int k, int stride) {
 }
 
 int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
-                         double* stats, cudaStream_t st);
+                         double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, cudaStream_t st);
 int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
                            int accumulate, cudaStream_t st);
 int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
@@ -454,7 +454,7 @@ int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ss
   SSB_REQUIRE(x && y && w, "ssb_conv1d_fwd: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_fwd: tcgen05 path needs bf16");
-    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, sums, to_stream(stream));
+    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, sums, nullptr, nullptr, 0, to_stream(stream));
   }
   if (sums) {   // generic CUDA-core path: conv, then the statistics pass as its own launch
     rc = ssb_conv1d_fwd_stats(x, w, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
@@ -471,6 +471,21 @@ int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ss
   })
   SSB_LAUNCH_CHECK("ssb_conv1d_fwd");
   return SSB_OK;
+}
+
+int ssb_conv1d_bn_act_fwd(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
+                          const ssb_bn* bn, const void* res, int relu, int dtype, int algo, ssb_stream_t stream) {
+  int rc = check_conv_geom("ssb_conv1d_bn_act_fwd", gin, gout, k, stride);
+  if (rc) return rc;
+  SSB_REQUIRE(x && y && w && bn, "ssb_conv1d_bn_act_fwd: null pointer");
+  if (algo == SSB_ALGO_TCGEN05) {
+    SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_bn_act_fwd: tcgen05 path needs bf16");
+    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, nullptr, bn, res, relu, to_stream(stream));
+  }
+  // generic CUDA-core path: conv, then the eval-mode BN(+residual)(+ReLU) pass in place
+  rc = ssb_conv1d_fwd(x, w, y, gin, gout, k, stride, dtype, algo, stream);
+  if (rc) return rc;
+  return ssb_bn_act_fwd(y, bn, res, nullptr, y, gout, relu, 0, dtype, stream);
 }
 
 int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,

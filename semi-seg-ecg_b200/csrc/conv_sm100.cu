@@ -122,6 +122,13 @@ struct TnParams {
   int o_mul, o_off, o_rows, o_pitch, o_len;
   int accumulate;
   double* stats;   // STATS epilogue: [2N] per-channel sum / sum of squares of the stored (rounded) output
+  // EPI epilogue (eval-mode BatchNorm folded into the conv): y = [relu](acc*scale + shift [+ res])
+  const float* ep_gamma;
+  const float* ep_beta;
+  const float* ep_mean;
+  const float* ep_var;
+  const bf16* ep_res;   // residual in the output geometry, may be NULL
+  int ep_relu;
 };
 
 // Column sums across the 32 lanes of a warp: every lane holds 32 column values x[0..31] of its own row;
@@ -163,13 +170,13 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
 }
 template <int B_BYTES, int STAGES>
 constexpr int smem_bytes() {
-  return STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  return STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024 + 2 * 128 * 4;   // + per-column scale/shift (EPI)
 }
 
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool STATS, bool B_MN>
+template <int BN, int STAGES, bool STATS, bool B_MN, bool EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
                const TnParams p) {
@@ -241,6 +248,16 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
     const int q = warp & 3;
+    float* ep_scale = reinterpret_cast<float*>(s.tmem_slot + 4);   // [BN] scale, [BN] shift
+    float* ep_shift = ep_scale + BN;
+    if (EPI) {   // eval-mode BN coefficients of this CTA's columns, computed while the main loop runs
+      for (int col = q * 32 + lane; col < BN; col += 128) {
+        const float sc = p.ep_gamma[n0 + col] * (1.0f / sqrtf(p.ep_var[n0 + col] + 1e-5f));
+        ep_scale[col] = sc;
+        ep_shift[col] = p.ep_beta[n0 + col] - p.ep_mean[n0 + col] * sc;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     mbar_wait(s.done, 0);
     tc_fence_after();
     const int row = q * 32 + lane;
@@ -264,7 +281,22 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float f[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(r[v * 8 + i]) : 0.f;
-          if (p.accumulate) {
+          if (EPI) {
+            if (valid) {
+              float rs[8];
+              if (p.ep_res) {
+                Vec<bf16> rv;
+                rv.raw = *reinterpret_cast<const uint4*>(p.ep_res + (size_t)orow * p.N + n0 + c + v * 8);
+                rv.get(rs);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float o = fmaf(f[i], ep_scale[c + v * 8 + i], ep_shift[c + v * 8 + i]);
+                if (p.ep_res) o += rs[i];
+                f[i] = p.ep_relu ? fmaxf(o, 0.f) : o;
+              }
+            }
+          } else if (p.accumulate) {
             Vec<bf16> prev;
             prev.raw = dst[v];
             float g[8];
@@ -484,10 +516,15 @@ template <int BN, bool B_MN>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem_bytes<BN * BK * 2, TN_STAGES>();
   dim3 grid(ceil_div(p.M, BM), p.N / BN);
-  if (p.stats)
-    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, B_MN>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
-  else
-    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, B_MN>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  if (p.ep_gamma) {
+    if constexpr (B_MN)
+      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  } else if (p.stats) {
+    if constexpr (B_MN)
+      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  } else {
+    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, B_MN, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  }
   SSB_LAUNCH_CHECK("conv_tn_kernel");
   return SSB_OK;
 }
@@ -535,12 +572,13 @@ int ssb_sm100_prepare() {
     return SSB_ERR_CUDA;
   }
   cudaError_t e = cudaSuccess;
-#define SSB_TN_ATTR(BN_, ST_, MN_)                                                                                    \
-  if (e == cudaSuccess)                                                                                                 \
-    e = cudaFuncSetAttribute(conv_tn_kernel<BN_, TN_STAGES, ST_, MN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+#define SSB_TN_ATTR(BN_, ST_, MN_, EP_)                                                                                    \
+  if (e == cudaSuccess)                                                                                                      \
+    e = cudaFuncSetAttribute(conv_tn_kernel<BN_, TN_STAGES, ST_, MN_, EP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              smem_bytes<BN_ * BK * 2, TN_STAGES>());
-  SSB_TN_ATTR(128, false, false) SSB_TN_ATTR(64, false, false) SSB_TN_ATTR(128, true, false) SSB_TN_ATTR(64, true, false)
-  SSB_TN_ATTR(128, false, true) SSB_TN_ATTR(64, false, true) SSB_TN_ATTR(128, true, true) SSB_TN_ATTR(64, true, true)
+  SSB_TN_ATTR(128, false, false, false) SSB_TN_ATTR(64, false, false, false) SSB_TN_ATTR(128, false, true, false)
+  SSB_TN_ATTR(64, false, true, false) SSB_TN_ATTR(128, true, true, false) SSB_TN_ATTR(64, true, true, false)
+  SSB_TN_ATTR(128, false, true, true) SSB_TN_ATTR(64, false, true, true)
 #undef SSB_TN_ATTR
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_wgrad_kernel<128, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -556,7 +594,7 @@ int ssb_sm100_prepare() {
 }
 
 int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
-                         double* stats, cudaStream_t st) {
+                         double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, cudaStream_t st) {
   int rc = check_sm100_shape("ssb_conv1d_fwd", gin, gout);
   if (rc) return rc;
   TnParams p = {};
@@ -572,6 +610,15 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ss
   p.o_len = gout.len;
   p.accumulate = 0;
   p.stats = stats;
+  if (ep_bn) {
+    SSB_REQUIRE(!stats, "ssb_conv1d_fwd: the statistics epilogue and the eval-mode BN epilogue are exclusive");
+    p.ep_gamma = ep_bn->gamma;
+    p.ep_beta = ep_bn->beta;
+    p.ep_mean = ep_bn->running_mean;
+    p.ep_var = ep_bn->running_var;
+    p.ep_res = (const bf16*)ep_res;
+    p.ep_relu = ep_relu;
+  }
   const long long rows_in = (long long)gin.B * gin.pitch;
   long long a_inner, a_outer, a_pitch;
   if (stride == 1) {

@@ -432,6 +432,11 @@ class NetPlan:
         if self.sync_hook is not None:
             self.sync_hook(self.sums[stats.soff: stats.soff + 2 * stats.C])
 
+    def _conv_bn_act(self, c: ConvDesc, b: BNDesc, x, y, gin: Geom, gout: Geom, res, relu: int, st: int):
+        """eval mode: y = [relu](bn_running(conv(x)) [+ res]) in one launch."""
+        call("ssb_conv1d_bn_act_fwd", x.data_ptr(), self.sh.ptr(c), y.data_ptr(), gin, gout, c.k, c.stride, self.bn(b),
+             res.data_ptr() if res is not None else None, relu, self.dtype, self._algo_for(c), st)
+
     def _algo_for(self, c: ConvDesc) -> int:
         if self.algo == _lib.ALGO_TCGEN05 and self.dtype == _lib.BF16 and c.cin % 64 == 0 and c.cout % 64 == 0:
             return _lib.ALGO_TCGEN05
@@ -506,23 +511,37 @@ class NetPlan:
         h, gin = self.p0, self.g_pool
         if self.pre_block_event is not None:   # the stem reads the master weights; everything after it the storage-dtype copy
             (stream or torch.cuda.current_stream()).wait_event(self.pre_block_event)
-        for bd, bufs in zip(lay.blocks, self.blk_bufs):
-            gout = self.g_stage[bd.stage]
-            self._conv_fwd(bd.conv1, h, bufs["c1"], gin, gout, st, bd.bn1 if tm else None)
-            call("ssb_bn_act_fwd", bufs["c1"].data_ptr(), self.bn(bd.bn1), None, None, bufs["a1"].data_ptr(), gout, 1, t, dt, st)
-            self._conv_fwd(bd.conv2, bufs["a1"], bufs["c2"], gout, gout, st, bd.bn2 if tm else None)
-            if bd.convd is not None:
-                self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st, bd.bnd if tm else None)
-                call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), bufs["cd"].data_ptr(), self.bn(bd.bnd),
-                     bufs["out"].data_ptr(), gout, 1, t, dt, st)
-            else:
-                call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), h.data_ptr(), None,
-                     bufs["out"].data_ptr(), gout, 1, t, dt, st)
-            h, gin = bufs["out"], gout
-        self.feat = h
-        gfeat = gin
-        self._conv_fwd(lay.head_conv, h, self.ch, gfeat, self.g_head, st, lay.head_bn if tm else None)
-        call("ssb_bn_act_fwd", self.ch.data_ptr(), self.bn(lay.head_bn), None, None, self.ah.data_ptr(), self.g_head, 1, t, dt, st)
+        if not tm:
+            # eval mode: BatchNorm is a fixed affine map -> folded, with the residual add and the ReLU, into
+            # the conv epilogue (one launch per conv, no pre-activation tensors)
+            for bd, bufs in zip(lay.blocks, self.blk_bufs):
+                gout = self.g_stage[bd.stage]
+                self._conv_bn_act(bd.conv1, bd.bn1, h, bufs["a1"], gin, gout, None, 1, st)
+                res = h
+                if bd.convd is not None:
+                    self._conv_bn_act(bd.convd, bd.bnd, h, bufs["cd"], gin, gout, None, 0, st)
+                    res = bufs["cd"]
+                self._conv_bn_act(bd.conv2, bd.bn2, bufs["a1"], bufs["out"], gout, gout, res, 1, st)
+                h, gin = bufs["out"], gout
+            self.feat = h
+            self._conv_bn_act(lay.head_conv, lay.head_bn, h, self.ah, gin, self.g_head, None, 1, st)
+        else:
+            for bd, bufs in zip(lay.blocks, self.blk_bufs):
+                gout = self.g_stage[bd.stage]
+                self._conv_fwd(bd.conv1, h, bufs["c1"], gin, gout, st, bd.bn1)
+                call("ssb_bn_act_fwd", bufs["c1"].data_ptr(), self.bn(bd.bn1), None, None, bufs["a1"].data_ptr(), gout, 1, t, dt, st)
+                self._conv_fwd(bd.conv2, bufs["a1"], bufs["c2"], gout, gout, st, bd.bn2)
+                if bd.convd is not None:
+                    self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st, bd.bnd)
+                    call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), bufs["cd"].data_ptr(), self.bn(bd.bnd),
+                         bufs["out"].data_ptr(), gout, 1, t, dt, st)
+                else:
+                    call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), h.data_ptr(), None,
+                         bufs["out"].data_ptr(), gout, 1, t, dt, st)
+                h, gin = bufs["out"], gout
+            self.feat = h
+            self._conv_fwd(lay.head_conv, h, self.ch, gin, self.g_head, st, lay.head_bn)
+            call("ssb_bn_act_fwd", self.ch.data_ptr(), self.bn(lay.head_bn), None, None, self.ah.data_ptr(), self.g_head, 1, t, dt, st)
         p = spec.dropout_ratio if tm else 0.0
         call("ssb_head_cls_fwd", self.ah.data_ptr(), self.w.params.data_ptr() + 4 * lay.cls_w_off,
              self.w.params.data_ptr() + 4 * lay.cls_b_off, self.low.data_ptr(), self.g_head, spec.num_classes,

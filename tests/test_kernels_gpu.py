@@ -159,6 +159,39 @@ def ref_bn(x, t, train):
     return y, nb
 
 
+@pytest.mark.parametrize("dtype,algo", ALGO_CASES)
+@pytest.mark.parametrize("cin,cout,k,stride,L,with_res,relu", [(64, 64, 3, 1, 157, True, 1), (64, 128, 1, 2, 313, False, 0),
+                                                              (128, 256, 3, 2, 157, False, 1), (512, 128, 3, 1, 79, False, 1),
+                                                              (16, 8, 3, 1, 37, True, 1)])
+def test_conv_bn_act_eval(cin, cout, k, stride, L, with_res, relu, dtype, algo):
+    """eval-mode conv + BatchNorm(running stats) [+ residual] [+ ReLU] in one launch vs the composed reference"""
+    if algo == _lib.ALGO_TCGEN05 and (cin % 64 or cout % 64):
+        pytest.skip("tcgen05 path needs channel counts that are multiples of 64")
+    torch.manual_seed(cin + cout + k)
+    B = 3
+    Lo = (L - 1) // stride + 1
+    po = Lo + 2 + 2
+    pi = stride * po
+    x = torch.randn(B, cin, L, device=DEV, dtype=torch.float64)
+    w = torch.randn(cout, cin, k, device=DEV, dtype=torch.float64) / (cin * k) ** 0.5
+    r = torch.randn(B, cout, Lo, device=DEV, dtype=torch.float64)
+    bn, t = make_bn(cout)
+    rm0, rv0 = t["rm"].clone(), t["rv"].clone()
+    y_ref, _ = ref_bn(F.conv1d(rq(x, dtype), rq(w, dtype), None, stride=stride, padding=k // 2), t, False)
+    if with_res:
+        y_ref = y_ref + rq(r, dtype)
+    if relu:
+        y_ref = torch.relu(y_ref)
+    gi, go = Geom(B, pi, L, cin), Geom(B, po, Lo, cout)
+    xb, rb, wt = to_flat(x, pi, dtype), to_flat(r, po, dtype), tap_major(w.float(), dtype)
+    yb = torch.full((B * po, cout), 7.0, dtype=TDT[dtype], device=DEV)
+    call("ssb_conv1d_bn_act_fwd", xb.data_ptr(), wt.data_ptr(), yb.data_ptr(), gi, go, k, stride, C.byref(bn),
+         rb.data_ptr() if with_res else None, relu, dtype, algo, st())
+    assert rel_err(from_flat(yb, B, po, Lo), y_ref) < TOL[dtype]
+    assert halo_is_zero(yb, B, po, Lo)
+    assert torch.equal(t["rm"], rm0) and torch.equal(t["rv"], rv0) and int(t["nbt"][0]) == 0   # eval mode: buffers untouched
+
+
 @pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
 @pytest.mark.parametrize("Cn,res_mode", [(8, 0), (64, 1), (128, 2), (24, 0)])
 def test_bn_forward_backward(dtype, Cn, res_mode):
