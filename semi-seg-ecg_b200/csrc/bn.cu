@@ -96,41 +96,59 @@ __device__ __forceinline__ void bn_coeffs(const ssb_bn& bn, int c, int C, int tr
 // ---------------------------------------------------------------------------------------
 // y = [relu]( bn(x) [+ bn_res(res) | + res] ), zero on halo/pad rows
 // RES: 0 none, 1 identity residual, 2 residual with its own BN
+// grid = (row blocks, channel chunks of <= 64 channels).  A thread keeps ONE 16-byte channel
+// group for all its rows, so the per-channel coefficients live in registers: no shared memory,
+// no barrier, and the data loads are in flight while the coefficients are being computed.
 // ---------------------------------------------------------------------------------------
 template <typename T, int RES>
 __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
                                                                 T* __restrict__ y, ssb_bn bn, ssb_bn bnr,
-                                                                ssb_geom g, int relu, int train) {
+                                                                ssb_geom g, int relu, int train, int cgpc, int rpb) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
-  extern __shared__ float sm[];
   const int C = g.C;
-  float* sScale = sm;
-  float* sShift = sm + C;
-  float* sRScale = sm + 2 * C;
-  float* sRShift = sm + 3 * C;
-  const double n = (double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1);
-  const double inv_n = 1.0 / n;
-  const bool writer = blockIdx.x == 0;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float sc, sh;
-    bn_coeffs(bn, c, C, train, inv_n, n, writer, sc, sh);
-    sScale[c] = sc;
-    sShift[c] = sh;
-    if (RES == 2) {
-      bn_coeffs(bnr, c, C, train, inv_n, n, writer, sc, sh);
-      sRScale[c] = sc;
-      sRShift[c] = sh;
+  const int ncg = C / V;
+  const int rpp = BN_THREADS / cgpc;            // rows per pass
+  const int cgl = threadIdx.x % cgpc, rl = threadIdx.x / cgpc;
+  const int cg = blockIdx.y * cgpc + cgl;
+  const int rows = g.B * g.pitch;
+  const int r0 = blockIdx.x * rpb;
+  const int r1 = min(rows, r0 + rpb);
+  // per-channel coefficients of this block's <= 64 channels: ONE thread per channel does the fp64
+  // statistics arithmetic (fp64 issue rate is low: never replicate it across row lanes)
+  __shared__ float sCo[4][64];
+  const int nch = cgpc * V;
+  if (threadIdx.x < nch) {
+    const int c = blockIdx.y * nch + threadIdx.x;
+    if (c < C) {
+      const double n = (double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1);
+      const double inv_n = 1.0 / n;
+      const bool writer = blockIdx.x == 0;
+      float a, b;
+      bn_coeffs(bn, c, C, train, inv_n, n, writer, a, b);
+      sCo[0][threadIdx.x] = a;
+      sCo[1][threadIdx.x] = b;
+      if (RES == 2) {
+        bn_coeffs(bnr, c, C, train, inv_n, n, writer, a, b);
+        sCo[2][threadIdx.x] = a;
+        sCo[3][threadIdx.x] = b;
+      }
     }
   }
   __syncthreads();
-  const int ncg = C / V;
-  const long long total = (long long)g.B * g.pitch * ncg;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(idx / ncg);
-    const int cg = (int)(idx - (long long)row * ncg);
+  if (rl >= rpp || cg >= ncg) return;
+  float sc[V], sh[V], rsc[V], rsh[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = sCo[0][cgl * V + i];
+    sh[i] = sCo[1][cgl * V + i];
+    if (RES == 2) {
+      rsc[i] = sCo[2][cgl * V + i];
+      rsh[i] = sCo[3][cgl * V + i];
+    }
+  }
+  for (int row = r0 + rl; row < r1; row += rpp) {
     const size_t off = (size_t)row * C + (size_t)cg * V;
     Vec<T> out;
     if (row_valid(row, g.pitch, g.len)) {
@@ -146,10 +164,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restr
       }
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const int c = cg * V + i;
-        float o = fmaf(f[i], sScale[c], sShift[c]);
+        float o = fmaf(f[i], sc[i], sh[i]);
         if (RES == 1) o += r[i];
-        if (RES == 2) o += fmaf(r[i], sRScale[c], sRShift[c]);
+        if (RES == 2) o += fmaf(r[i], rsc[i], rsh[i]);
         if (relu) o = fmaxf(o, 0.f);
         f[i] = o;
       }
@@ -336,65 +353,72 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
 // ---------------------------------------------------------------------------------------
 // backward pass 2 (apply): dx = gamma*invstd*(g - sum_g/n - xhat*sum_gx/n)
 // RES: 0 none; 1 identity residual -> g_ident = g; 2 residual BN -> dx_res
+// same decomposition as bn_act_fwd_kernel: per-channel constants in registers.
 // ---------------------------------------------------------------------------------------
 template <typename T, bool HAS_G2, bool HAS_Y, int RES>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __restrict__ g1, const T* __restrict__ g2,
                                                                   const T* __restrict__ y, const T* __restrict__ x,
                                                                   const T* __restrict__ xr, T* __restrict__ dx,
                                                                   T* __restrict__ dxr, T* __restrict__ gid, ssb_bn bn,
-                                                                  ssb_bn bnr, ssb_geom g) {
+                                                                  ssb_bn bnr, ssb_geom g, int cgpc, int rpb) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
-  extern __shared__ float sm[];
   const int C = g.C;
-  // per channel: mean, invstd, k0 = gamma*invstd, k1 = sum_g/n, k2 = sum_gx/n
-  float* sMean = sm;
-  float* sInv = sm + C;
-  float* sK0 = sm + 2 * C;
-  float* sK1 = sm + 3 * C;
-  float* sK2 = sm + 4 * C;
-  float* rMean = sm + 5 * C;
-  float* rInv = sm + 6 * C;
-  float* rK0 = sm + 7 * C;
-  float* rK2 = sm + 8 * C;
-  const double inv_n = 1.0 / ((double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1));
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float mean = bn.mean_invstd[c], inv = bn.mean_invstd[C + c];
-    const double sg = bn.bwd_sums[c], sgx = bn.bwd_sums[C + c];
-    sMean[c] = mean;
-    sInv[c] = inv;
-    sK0[c] = bn.gamma[c] * inv;
-    sK1[c] = (float)(sg * inv_n);
-    sK2[c] = (float)(sgx * inv_n);
-    if (blockIdx.x == 0) {
+  const int ncg = C / V;
+  const int rpp = BN_THREADS / cgpc;
+  const int cgl = threadIdx.x % cgpc, rl = threadIdx.x / cgpc;
+  const int cg = blockIdx.y * cgpc + cgl;
+  const int rows = g.B * g.pitch;
+  const int r0 = blockIdx.x * rpb;
+  const int r1 = min(rows, r0 + rpb);
+  // per channel: mean, invstd, k0 = gamma*invstd, k1 = sum_g/n, k2 = sum_gx/n (+ residual-BN mean, invstd, k0, k2);
+  // one thread per channel does the fp64 part
+  __shared__ float sCo[9][64];
+  const int nch = cgpc * V;
+  if (threadIdx.x < nch) {
+    const int c = blockIdx.y * nch + threadIdx.x;
+    if (c < C) {
+      const double inv_n = 1.0 / ((double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1));
       // SyncBN: the sums are global totals and the gradient arena is averaged over ranks afterwards,
       // so each rank contributes total / world
       const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
-      bn.dgamma[c] = (float)(sgx * gsc);
-      bn.dbeta[c] = (float)(sg * gsc);
-    }
-    if (RES == 2) {
-      const float meanr = bnr.mean_invstd[c], invr = bnr.mean_invstd[C + c];
-      const double sgxr = bnr.bwd_sums[C + c];
-      rMean[c] = meanr;
-      rInv[c] = invr;
-      rK0[c] = bnr.gamma[c] * invr;
-      rK2[c] = (float)(sgxr * inv_n);
-      if (blockIdx.x == 0) {
-        const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
-        bnr.dgamma[c] = (float)(sgxr * gsc);
-        bnr.dbeta[c] = (float)(sg * gsc);
+      const bool writer = blockIdx.x == 0;
+      const float mean_ = bn.mean_invstd[c], inv_ = bn.mean_invstd[C + c];
+      const double sg = bn.bwd_sums[c], sgx = bn.bwd_sums[C + c];
+      sCo[0][threadIdx.x] = mean_;
+      sCo[1][threadIdx.x] = inv_;
+      sCo[2][threadIdx.x] = bn.gamma[c] * inv_;
+      sCo[3][threadIdx.x] = (float)(sg * inv_n);
+      sCo[4][threadIdx.x] = (float)(sgx * inv_n);
+      if (writer) {
+        bn.dgamma[c] = (float)(sgx * gsc);
+        bn.dbeta[c] = (float)(sg * gsc);
+      }
+      if (RES == 2) {
+        const float meanr = bnr.mean_invstd[c], invr = bnr.mean_invstd[C + c];
+        const double sgxr = bnr.bwd_sums[C + c];
+        sCo[5][threadIdx.x] = meanr;
+        sCo[6][threadIdx.x] = invr;
+        sCo[7][threadIdx.x] = bnr.gamma[c] * invr;
+        sCo[8][threadIdx.x] = (float)(sgxr * inv_n);
+        if (writer) {
+          bnr.dgamma[c] = (float)(sgxr * gsc);
+          bnr.dbeta[c] = (float)(sg * gsc);
+        }
       }
     }
   }
   __syncthreads();
-  const int ncg = C / V;
-  const long long total = (long long)g.B * g.pitch * ncg;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(idx / ncg);
-    const int cg = (int)(idx - (long long)row * ncg);
+  if (rl >= rpp || cg >= ncg) return;
+  float mean[V], inv[V], k0[V], k1[V], k2[V], rmean[V], rinv[V], rk0[V], rk2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = cgl * V + i;
+    mean[i] = sCo[0][j]; inv[i] = sCo[1][j]; k0[i] = sCo[2][j]; k1[i] = sCo[3][j]; k2[i] = sCo[4][j];
+    if (RES == 2) { rmean[i] = sCo[5][j]; rinv[i] = sCo[6][j]; rk0[i] = sCo[7][j]; rk2[i] = sCo[8][j]; }
+  }
+  for (int row = r0 + rl; row < r1; row += rpp) {
     const size_t off = (size_t)row * C + (size_t)cg * V;
     Vec<T> odx, odr, ogi;
     if (row_valid(row, g.pitch, g.len)) {
@@ -423,9 +447,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
       float o[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) {
-        const int c = cg * V + i;
-        const float xh = (fx[i] - sMean[c]) * sInv[c];
-        o[i] = sK0[c] * (fg[i] - sK1[c] - xh * sK2[c]);
+        const float xh = (fx[i] - mean[i]) * inv[i];
+        o[i] = k0[i] * (fg[i] - k1[i] - xh * k2[i]);
       }
       odx.set(o);
       if (RES == 1) ogi.set(fg);
@@ -436,9 +459,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
         vr.get(fr);
 #pragma unroll
         for (int i = 0; i < V; ++i) {
-          const int c = cg * V + i;
-          const float xh = (fr[i] - rMean[c]) * rInv[c];
-          o[i] = rK0[c] * (fg[i] - sK1[c] - xh * rK2[c]);
+          const float xh = (fr[i] - rmean[i]) * rinv[i];
+          o[i] = rk0[i] * (fg[i] - k1[i] - xh * rk2[i]);
         }
         odr.set(o);
       }
@@ -627,12 +649,33 @@ static int ew_blocks(long long total_vec) {
   return (int)b;
 }
 
+// 2-D launch geometry of the per-row elementwise BN kernels: channel chunks of <= 64 channels
+// (cgpc 16-byte groups), rpb rows per block chosen so that the grid has a few blocks per SM
+struct EwGeom {
+  int cgpc, rpb;
+  dim3 grid;
+};
+static EwGeom ew_geom(int rows, int ncg, int vec) {
+  EwGeom e;
+  const int per_chunk = 64 / vec;
+  e.cgpc = ncg < per_chunk ? ncg : per_chunk;
+  const int ny = ceil_div(ncg, e.cgpc);
+  const int rpp = BN_THREADS / e.cgpc;
+  int nx = ceil_div(148 * 6, ny);
+  int rpb = ceil_div(rows, nx);
+  rpb = ceil_div(rpb, rpp) * rpp;
+  if (rpb < rpp) rpb = rpp;
+  e.rpb = rpb;
+  e.grid = dim3(ceil_div(rows, rpb), ny);
+  return e;
+}
+
 static const ssb_bn kNoBn = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
 
 #define SSB_RED(G2, Y, R) \
   ssb_launch(bn_bwd_reduce_kernel<T, G2, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, *bn, br, rows, g.C, rpb)
 #define SSB_APP(G2, Y, R) \
-  ssb_launch(bn_bwd_apply_kernel<T, G2, Y, R>, dim3(blocks), dim3(BN_THREADS), smem, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g)
+  ssb_launch(bn_bwd_apply_kernel<T, G2, Y, R>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, eg.cgpc, eg.rpb)
 
 extern "C" {
 
@@ -662,17 +705,15 @@ int ssb_bn_act_fwd(const void* x, const ssb_bn* bn, const void* res, const ssb_b
   SSB_REQUIRE(x && bn && y, "ssb_bn_act_fwd: null pointer");
   SSB_REQUIRE(!(bn_res && !res), "ssb_bn_act_fwd: bn_res given without res");
   const int mode = res ? (bn_res ? 2 : 1) : 0;
-  const size_t smem = (size_t)4 * g.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    const long long total = (long long)g.B * g.pitch * (g.C / Vec<T>::N);
-    const int blocks = ew_blocks(total);
+    const EwGeom eg = ew_geom(g.B * g.pitch, g.C / Vec<T>::N, Vec<T>::N);
     cudaStream_t st = to_stream(stream);
     if (mode == 0)
-      ssb_launch(bn_act_fwd_kernel<T, 0>, dim3(blocks), dim3(BN_THREADS), smem, st, (const T*)x, nullptr, (T*)y, *bn, kNoBn, g, relu, train);
+      ssb_launch(bn_act_fwd_kernel<T, 0>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, nullptr, (T*)y, *bn, kNoBn, g, relu, train, eg.cgpc, eg.rpb);
     else if (mode == 1)
-      ssb_launch(bn_act_fwd_kernel<T, 1>, dim3(blocks), dim3(BN_THREADS), smem, st, (const T*)x, (const T*)res, (T*)y, *bn, kNoBn, g, relu, train);
+      ssb_launch(bn_act_fwd_kernel<T, 1>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, (const T*)res, (T*)y, *bn, kNoBn, g, relu, train, eg.cgpc, eg.rpb);
     else
-      ssb_launch(bn_act_fwd_kernel<T, 2>, dim3(blocks), dim3(BN_THREADS), smem, st, (const T*)x, (const T*)res, (T*)y, *bn, *bn_res, g, relu, train);
+      ssb_launch(bn_act_fwd_kernel<T, 2>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, (const T*)res, (T*)y, *bn, *bn_res, g, relu, train, eg.cgpc, eg.rpb);
   })
   SSB_LAUNCH_CHECK("ssb_bn_act_fwd");
   return SSB_OK;
@@ -738,10 +779,8 @@ int ssb_bn_bwd_apply(const void* g1, const void* g2, const void* y, const void* 
   SSB_REQUIRE(!(bn_res && (!x_res || !dx_res)), "ssb_bn_bwd_apply: residual BN needs x_res and dx_res");
   SSB_REQUIRE(!(bn_res && g_ident), "ssb_bn_bwd_apply: g_ident and bn_res are exclusive");
   const int mode = bn_res ? 2 : (g_ident ? 1 : 0);
-  const size_t smem = (size_t)9 * g.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    const long long total = (long long)g.B * g.pitch * (g.C / Vec<T>::N);
-    const int blocks = ew_blocks(total);
+    const EwGeom eg = ew_geom(g.B * g.pitch, g.C / Vec<T>::N, Vec<T>::N);
     cudaStream_t st = to_stream(stream);
     const ssb_bn br = bn_res ? *bn_res : kNoBn;
     const int sel = (g2 ? 2 : 0) | (y ? 1 : 0);
