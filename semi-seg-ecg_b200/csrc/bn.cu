@@ -55,14 +55,16 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restric
     const int l = o / V, i = o % V;
     const int cgo = blockIdx.y * cgb + l;
     if (cgo >= ncg) continue;
-    double ds = 0.0, dq = 0.0;
+    // block-level partials in fp32 (<= 32 terms each already summed over a few rows); only the
+    // cross-block accumulation is fp64 -- the fp64 pipe is slow and this loop is on every block's tail
+    float ds = 0.f, dq = 0.f;
     for (int k = 0; k < nrl; ++k) {
-      ds += (double)sS[(k * cgb + l) * V + i];
-      dq += (double)sQ[(k * cgb + l) * V + i];
+      ds += sS[(k * cgb + l) * V + i];
+      dq += sQ[(k * cgb + l) * V + i];
     }
     const int c = cgo * V + i;
-    atomicAdd(&sums[c], ds);
-    atomicAdd(&sums[C + c], dq);
+    atomicAdd(&sums[c], (double)ds);
+    atomicAdd(&sums[C + c], (double)dq);
   }
 }
 
@@ -334,18 +336,18 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
     const int l = o / V, i = o % V;
     const int cgo = blockIdx.y * cgb + l;
     if (cgo >= ncg) continue;
-    double da = 0.0, db = 0.0, dc = 0.0;
+    float da = 0.f, db = 0.f, dc = 0.f;
     for (int k = 0; k < nrl; ++k) {
-      da += (double)sA[(k * cgb + l) * V + i];
-      db += (double)sB[(k * cgb + l) * V + i];
-      if (HAS_RES) dc += (double)sC[(k * cgb + l) * V + i];
+      da += sA[(k * cgb + l) * V + i];
+      db += sB[(k * cgb + l) * V + i];
+      if (HAS_RES) dc += sC[(k * cgb + l) * V + i];
     }
     const int c = cgo * V + i;
-    atomicAdd(&bn.bwd_sums[c], da);
-    atomicAdd(&bn.bwd_sums[C + c], db);
+    atomicAdd(&bn.bwd_sums[c], (double)da);
+    atomicAdd(&bn.bwd_sums[C + c], (double)db);
     if (HAS_RES) {
-      atomicAdd(&bnr.bwd_sums[c], da);
-      atomicAdd(&bnr.bwd_sums[C + c], dc);
+      atomicAdd(&bnr.bwd_sums[c], (double)da);
+      atomicAdd(&bnr.bwd_sums[C + c], (double)dc);
     }
   }
 }
@@ -561,14 +563,14 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bwd_reduce_kernel(const T* __
     const int l = o / V, i = o % V;
     const int cgo = blockIdx.y * cgb + l;
     if (cgo >= ncg) continue;
-    double da = 0.0, db = 0.0;
+    float da = 0.f, db = 0.f;
     for (int k = 0; k < nrl; ++k) {
-      da += (double)sA[(k * cgb + l) * V + i];
-      db += (double)sB[(k * cgb + l) * V + i];
+      da += sA[(k * cgb + l) * V + i];
+      db += sB[(k * cgb + l) * V + i];
     }
     const int c = cgo * V + i;
-    atomicAdd(&bn.bwd_sums[c], da);
-    atomicAdd(&bn.bwd_sums[C + c], db);
+    atomicAdd(&bn.bwd_sums[c], (double)da);
+    atomicAdd(&bn.bwd_sums[C + c], (double)db);
   }
 }
 

@@ -16,6 +16,7 @@
 // SURVEY.md 2.2).  bf16 operands, fp32 accumulation.  One CTA = one 128 x BN output tile;
 // warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -109,6 +110,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)2 << 61;
   return d;
 }
+// NOTE (measured on B200, tests/test_kernels_gpu.py): a start address that is offset by whole 128-byte
+// rows inside an 8-row swizzle group needs NO matrix-base-offset field -- the 128B swizzle is applied on
+// absolute shared-memory address bits, exactly as TMA wrote the tile; setting (addr >> 7) & 7 in bits
+// 49-51 gives wrong products.  The tap-reuse kernel below relies on this.
 // instruction descriptor: bf16 x bf16 -> f32, M = 128, N = n
 __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major ? (1u << 15) : 0u) | (b_mn_major ? (1u << 16) : 0u) |
@@ -172,6 +177,107 @@ template <int B_BYTES, int STAGES>
 constexpr int smem_bytes() {
   return STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024 + 2 * 128 * 4;   // + per-column scale/shift (EPI)
 }
+
+// ---------------------------------------------------------------------------------------------
+// epilogue shared by the conv kernels: TMEM -> registers -> (BN affine / residual / ReLU | accumulate)
+// -> bf16 rows in global memory, plus the optional per-channel statistics of the stored values.
+// Called by the four epilogue warps (threads 64..191); `scratch` is operand smem that is free once
+// `done` has fired, `ep_scale` a dedicated [2*BN] float area.
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool STATS, bool EPI>
+__device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict__ out, uint32_t tmem_base, uint64_t* done,
+                                          float* ep_scale, float* scratch, int m0, int n0, int warp, int lane) {
+  // epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
+  const int q = warp & 3;
+  float* ep_shift = ep_scale + BN;
+  if (EPI) {   // eval-mode BN coefficients of this CTA's columns, computed while the main loop runs
+    for (int col = q * 32 + lane; col < BN; col += 128) {
+      const float sc = p.ep_gamma[n0 + col] * (1.0f / sqrtf(p.ep_var[n0 + col] + 1e-5f));
+      ep_scale[col] = sc;
+      ep_shift[col] = p.ep_beta[n0 + col] - p.ep_mean[n0 + col] * sc;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  mbar_wait(done, 0);
+  tc_fence_after();
+  const int row = q * 32 + lane;
+  const int m = m0 + row;
+  const long long orow = (long long)p.o_mul * m + p.o_off;
+  const bool in_range = m < p.M && orow >= 0 && orow < p.o_rows;
+  const bool valid = in_range && row_valid((int)orow, p.o_pitch, p.o_len);
+  bf16* optr = out + (size_t)(in_range ? orow : 0) * p.N + n0;
+  // all MMAs have retired: the operand stages are free, stage 0 of A is reused as reduction scratch
+  float* red = scratch;   // [4 warps][2][BN]
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+    tmem_ld_wait();
+    float sv[32];
+    if (in_range && !(!valid && p.accumulate)) {
+      uint4* dst = reinterpret_cast<uint4*>(optr + c);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(r[v * 8 + i]) : 0.f;
+        if (EPI) {
+          if (valid) {
+            float rs[8];
+            if (p.ep_res) {
+              Vec<bf16> rv;
+              rv.raw = *reinterpret_cast<const uint4*>(p.ep_res + (size_t)orow * p.N + n0 + c + v * 8);
+              rv.get(rs);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float o = fmaf(f[i], ep_scale[c + v * 8 + i], ep_shift[c + v * 8 + i]);
+              if (p.ep_res) o += rs[i];
+              f[i] = p.ep_relu ? fmaxf(o, 0.f) : o;
+            }
+          }
+        } else if (p.accumulate) {
+          Vec<bf16> prev;
+          prev.raw = dst[v];
+          float g[8];
+          prev.get(g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] += g[i];
+        }
+        Vec<bf16> o;
+        o.set(f);
+        dst[v] = o.raw;
+        if (STATS) o.get(&sv[v * 8]);   // statistics of the values as stored
+      }
+    } else if (STATS) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sv[i] = 0.f;
+    }
+    if (STATS) {
+      float sq[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sq[i] = sv[i] * sv[i];
+      warp_transpose_sum(sv, lane);
+      warp_transpose_sum(sq, lane);
+      red[(q * 2 + 0) * BN + c + lane] = sv[0];
+      red[(q * 2 + 1) * BN + c + lane] = sq[0];
+    }
+  }
+  if (STATS) {
+    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+    const int e = q * 32 + lane;
+    for (int col = e; col < BN; col += 128) {
+      float a = 0.f, b = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        a += red[(w * 2 + 0) * BN + col];
+        b += red[(w * 2 + 1) * BN + col];
+      }
+      atomicAdd(&p.stats[n0 + col], (double)a);
+      atomicAdd(&p.stats[p.N + n0 + col], (double)b);
+    }
+  }
+  }
 
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad
@@ -246,97 +352,114 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(s.done);           // accumulator complete
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
-    const int q = warp & 3;
-    float* ep_scale = reinterpret_cast<float*>(s.tmem_slot + 4);   // [BN] scale, [BN] shift
-    float* ep_shift = ep_scale + BN;
-    if (EPI) {   // eval-mode BN coefficients of this CTA's columns, computed while the main loop runs
-      for (int col = q * 32 + lane; col < BN; col += 128) {
-        const float sc = p.ep_gamma[n0 + col] * (1.0f / sqrtf(p.ep_var[n0 + col] + 1e-5f));
-        ep_scale[col] = sc;
-        ep_shift[col] = p.ep_beta[n0 + col] - p.ep_mean[n0 + col] * sc;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-    }
-    mbar_wait(s.done, 0);
-    tc_fence_after();
-    const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const long long orow = (long long)p.o_mul * m + p.o_off;
-    const bool in_range = m < p.M && orow >= 0 && orow < p.o_rows;
-    const bool valid = in_range && row_valid((int)orow, p.o_pitch, p.o_len);
-    bf16* optr = out + (size_t)(in_range ? orow : 0) * p.N + n0;
-    // all MMAs have retired: the operand stages are free, stage 0 of A is reused as reduction scratch
-    float* red = reinterpret_cast<float*>(s.a);   // [4 warps][2][BN]
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      float sv[32];
-      if (in_range && !(!valid && p.accumulate)) {
-        uint4* dst = reinterpret_cast<uint4*>(optr + c);
+    tn_epilogue<BN, STATS, EPI>(p, out, tmem_base, s.done, reinterpret_cast<float*>(s.tmem_slot + 4),
+                                reinterpret_cast<float*>(s.a), m0, n0, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fprop / dgrad of the stride-1 k=3 convs with TAP REUSE: the three taps read the same activation
+// rows shifted by one, so the A tile (BM + 2 halo rows, padded to 136) is loaded ONCE per 64-channel
+// K chunk and the three MMAs address it at row offsets 0/1/2 through the smem descriptor start address
+// (128 B per row; the swizzle follows the absolute address).  A traffic from L2 drops 3x; the B (weight) tiles
+// have their own, deeper ring.  Tiles up to 128 x 256.
+// ---------------------------------------------------------------------------------------------
+constexpr int A3_ROWS = 136;
+constexpr int A3_BYTES = A3_ROWS * 128;   // 17408 = 17 * 1024
+constexpr int A3_SLOTS = 3;
+template <int BN> __host__ __device__ constexpr int b3_slots() { return BN == 256 ? 5 : (BN == 128 ? 8 : 9); }
+template <int BN> constexpr int smem3_bytes() {
+  return A3_SLOTS * A3_BYTES + b3_slots<BN>() * BN * 128 + (2 * A3_SLOTS + 2 * b3_slots<BN>() + 1) * 8 + 16 + 2 * BN * 4 + 1024;
+}
+
+template <int BN, bool STATS, bool B_MN, bool EPI>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
+                const TnParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int NB = b3_slots<BN>();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* sa = smem_raw + (((base + 1023u) & ~1023u) - base);
+  uint8_t* sb = sa + A3_SLOTS * A3_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sb + NB * B_BYTES);
+  uint64_t* a_empty = a_full + A3_SLOTS;
+  uint64_t* b_full = a_empty + A3_SLOTS;
+  uint64_t* b_empty = b_full + NB;
+  uint64_t* done = b_empty + NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  float* ep_scale = reinterpret_cast<float*>(tmem_slot + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < A3_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int KC = p.K / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int bi = 0;
+      for (int kc = 0; kc < KC; ++kc) {
+        const int sl = kc % A3_SLOTS;
+        mbar_wait(&a_empty[sl], (((uint32_t)(kc / A3_SLOTS)) & 1u) ^ 1u);
+        mbar_expect_tx(&a_full[sl], A3_BYTES);
+        tma_load_2d(sa + sl * A3_BYTES, &tmA, &a_full[sl], kc * BK, m0 - 1);   // rows m0-1 .. m0+134 (zero fill outside)
+        for (int tap = 0; tap < 3; ++tap, ++bi) {
+          const int bs = bi % NB;
+          mbar_wait(&b_empty[bs], (((uint32_t)(bi / NB)) & 1u) ^ 1u);
+          mbar_expect_tx(&b_full[bs], B_BYTES);
+          if (B_MN) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(r[v * 8 + i]) : 0.f;
-          if (EPI) {
-            if (valid) {
-              float rs[8];
-              if (p.ep_res) {
-                Vec<bf16> rv;
-                rv.raw = *reinterpret_cast<const uint4*>(p.ep_res + (size_t)orow * p.N + n0 + c + v * 8);
-                rv.get(rs);
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float o = fmaf(f[i], ep_scale[c + v * 8 + i], ep_shift[c + v * 8 + i]);
-                if (p.ep_res) o += rs[i];
-                f[i] = p.ep_relu ? fmaxf(o, 0.f) : o;
-              }
-            }
-          } else if (p.accumulate) {
-            Vec<bf16> prev;
-            prev.raw = dst[v];
-            float g[8];
-            prev.get(g);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] += g[i];
+            for (int b = 0; b < BN / 64; ++b)
+              tma_load_2d(sb + bs * B_BYTES + b * (BK * 128), &tmB, &b_full[bs], n0 + b * 64,
+                          p.w_tap[tap] * p.w_rows_per_tap + kc * BK);
+          } else {
+            tma_load_2d(sb + bs * B_BYTES, &tmB, &b_full[bs], kc * BK, p.w_tap[tap] * p.w_rows_per_tap + n0);
           }
-          Vec<bf16> o;
-          o.set(f);
-          dst[v] = o.raw;
-          if (STATS) o.get(&sv[v * 8]);   // statistics of the values as stored
         }
-      } else if (STATS) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sv[i] = 0.f;
-      }
-      if (STATS) {
-        float sq[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) sq[i] = sv[i] * sv[i];
-        warp_transpose_sum(sv, lane);
-        warp_transpose_sum(sq, lane);
-        red[(q * 2 + 0) * BN + c + lane] = sv[0];
-        red[(q * 2 + 1) * BN + c + lane] = sq[0];
       }
     }
-    if (STATS) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-      const int e = q * 32 + lane;
-      for (int col = e; col < BN; col += 128) {
-        float a = 0.f, b = 0.f;
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, false, B_MN);
+      int bi = 0;
+      for (int kc = 0; kc < KC; ++kc) {
+        const int sl = kc % A3_SLOTS;
+        mbar_wait(&a_full[sl], ((uint32_t)(kc / A3_SLOTS)) & 1u);
+        const uint32_t a0 = smem_u32(sa + sl * A3_BYTES);
+        for (int tap = 0; tap < 3; ++tap, ++bi) {
+          const int bs = bi % NB;
+          mbar_wait(&b_full[bs], ((uint32_t)(bi / NB)) & 1u);
+          tc_fence_after();
+          const uint32_t b0 = smem_u32(sb + bs * B_BYTES);
+          const uint32_t at = a0 + (uint32_t)(p.a_row_off[tap] + 1) * 128u;   // tap's row shift inside the haloed tile
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          a += red[(w * 2 + 0) * BN + col];
-          b += red[(w * 2 + 1) * BN + col];
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            const uint64_t bdesc = B_MN ? make_smem_desc(b0 + k4 * 2048, BK * 128, 1024) : make_smem_desc(b0 + k4 * 32, 0, 1024);
+            umma_bf16(tmem_base, make_smem_desc(at + k4 * 32, 0, 1024), bdesc, idesc, (uint32_t)((kc | tap | k4) != 0));
+          }
+          umma_commit(&b_empty[bs]);
         }
-        atomicAdd(&p.stats[n0 + col], (double)a);
-        atomicAdd(&p.stats[p.N + n0 + col], (double)b);
+        umma_commit(&a_empty[sl]);
       }
+      umma_commit(done);
     }
+  } else {
+    tn_epilogue<BN, STATS, EPI>(p, out, tmem_base, done, ep_scale, reinterpret_cast<float*>(sa), m0, n0, warp, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -529,12 +652,52 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
   return SSB_OK;
 }
 
+template <int BN, bool B_MN>
+int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
+  constexpr int smem = smem3_bytes<BN>();
+  dim3 grid(ceil_div(p.M, BM), p.N / BN);
+  if (p.ep_gamma) {
+    if constexpr (B_MN)
+      ssb_launch_pro(conv_tn3_kernel<BN, false, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  } else if (p.stats) {
+    if constexpr (B_MN)
+      ssb_launch_pro(conv_tn3_kernel<BN, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  } else {
+    ssb_launch_pro(conv_tn3_kernel<BN, false, B_MN, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  }
+  SSB_LAUNCH_CHECK("conv_tn3_kernel");
+  return SSB_OK;
+}
+
+int g_tn3 = 1;   // env SSB_TN3=0 disables the tap-reuse kernel (A/B comparison)
+
 // b_mn: the weight matrix of one tap is [K rows][N contiguous] (fprop) instead of [N rows][K contiguous] (dgrad)
+// tap3: stride-1 k=3 conv whose taps are the row shifts -1/0/+1 of the same operand -> tap-reuse kernel
 int run_tn(const void* a_base, long long a_inner, long long a_outer, long long a_pitch, const void* w_base, int w_rows,
-           bool b_mn, bf16* out, const TnParams& p, cudaStream_t st) {
-  const int BN = (p.N % 128 == 0) ? 128 : 64;
+           bool b_mn, bool tap3, bf16* out, const TnParams& p, cudaStream_t st) {
   CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, a_base, a_inner, a_outer, a_pitch, BK, BM);
+  int rc;
+  if (tap3 && g_tn3) {
+    // widest tile that still gives every SM a CTA
+    const int mt = ceil_div(p.M, BM);
+    int BN = 64;
+    if (p.N % 256 == 0 && (long long)mt * (p.N / 256) >= 148) BN = 256;
+    else if (p.N % 128 == 0) BN = 128;
+    rc = make_map(&tmA, a_base, a_inner, a_outer, a_pitch, BK, A3_ROWS);
+    if (rc) return rc;
+    if (b_mn) {
+      rc = make_map(&tmB, w_base, p.N, w_rows, p.N, 64, BK);
+      if (rc) return rc;
+      return BN == 256 ? launch_tn3<256, true>(tmA, tmB, out, p, st)
+                       : (BN == 128 ? launch_tn3<128, true>(tmA, tmB, out, p, st) : launch_tn3<64, true>(tmA, tmB, out, p, st));
+    }
+    rc = make_map(&tmB, w_base, p.K, w_rows, p.K, BK, BN);
+    if (rc) return rc;
+    return BN == 256 ? launch_tn3<256, false>(tmA, tmB, out, p, st)
+                     : (BN == 128 ? launch_tn3<128, false>(tmA, tmB, out, p, st) : launch_tn3<64, false>(tmA, tmB, out, p, st));
+  }
+  const int BN = (p.N % 128 == 0) ? 128 : 64;
+  rc = make_map(&tmA, a_base, a_inner, a_outer, a_pitch, BK, BM);
   if (rc) return rc;
   if (b_mn) {
     rc = make_map(&tmB, w_base, p.N, w_rows, p.N, 64, BK);
@@ -580,6 +743,15 @@ int ssb_sm100_prepare() {
   SSB_TN_ATTR(64, false, true, false) SSB_TN_ATTR(128, true, true, false) SSB_TN_ATTR(64, true, true, false)
   SSB_TN_ATTR(128, false, true, true) SSB_TN_ATTR(64, false, true, true)
 #undef SSB_TN_ATTR
+#define SSB_TN3_ATTR(BN_, ST_, MN_, EP_)                                                                               \
+  if (e == cudaSuccess)                                                                                              \
+    e = cudaFuncSetAttribute(conv_tn3_kernel<BN_, ST_, MN_, EP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3_bytes<BN_>());
+  SSB_TN3_ATTR(64, false, false, false) SSB_TN3_ATTR(128, false, false, false) SSB_TN3_ATTR(256, false, false, false)
+  SSB_TN3_ATTR(64, false, true, false) SSB_TN3_ATTR(128, false, true, false) SSB_TN3_ATTR(256, false, true, false)
+  SSB_TN3_ATTR(64, true, true, false) SSB_TN3_ATTR(128, true, true, false) SSB_TN3_ATTR(256, true, true, false)
+  SSB_TN3_ATTR(64, false, true, true) SSB_TN3_ATTR(128, false, true, true) SSB_TN3_ATTR(256, false, true, true)
+#undef SSB_TN3_ATTR
+  if (const char* t3 = getenv("SSB_TN3")) g_tn3 = atoi(t3);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_wgrad_kernel<128, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_bytes<128 * BK * 2, WG_STAGES>());
@@ -635,7 +807,7 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ss
       p.a_row_off[0] = -1; p.a_col_off[0] = gin.C; p.w_tap[0] = 0;
     }
   }
-  return run_tn(x, a_inner, a_outer, a_pitch, w, k * gin.C, true, (bf16*)y, p, st);
+  return run_tn(x, a_inner, a_outer, a_pitch, w, k * gin.C, true, stride == 1 && k == 3, (bf16*)y, p, st);
 }
 
 int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
@@ -657,7 +829,7 @@ int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin
     p.o_mul = 1;
     p.o_off = 0;
     for (int j = 0; j < k; ++j) { p.a_row_off[j] = (k == 3) ? 1 - j : 0; p.a_col_off[j] = 0; p.w_tap[j] = j; }
-    return run_tn(dy, gout.C, rows_out, gout.C, w, k * gin.C, false, (bf16*)dx, p, st);
+    return run_tn(dy, gout.C, rows_out, gout.C, w, k * gin.C, false, k == 3, (bf16*)dx, p, st);
   }
   // stride 2: dx row 2q+par; par 0 <- dy[q+1]*W0 + dy[q]*W2; par 1 <- dy[q+1]*W1 (k=1: par 1 <- dy[q+1]*W0)
   p.M = rows_in / 2;
@@ -679,7 +851,7 @@ int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin
       }
       continue;
     }
-    rc = run_tn(dy, gout.C, rows_out, gout.C, w, k * gin.C, false, (bf16*)dx, p, st);
+    rc = run_tn(dy, gout.C, rows_out, gout.C, w, k * gin.C, false, false, (bf16*)dx, p, st);
     if (rc) return rc;
   }
   return SSB_OK;

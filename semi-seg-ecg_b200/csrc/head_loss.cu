@@ -258,7 +258,7 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
   float* sG = sm;                                  // [tcap][ncls]
   float* sW1 = sm + (size_t)tcap * ncls;           // [tcap]
   int* sI0 = (int*)(sW1 + tcap);                   // [tcap]
-  __shared__ double sRed[3][SL_THREADS / 32];
+  __shared__ float sRed[3][SL_THREADS / 32];
   const int b = blockIdx.y;
   const int ia = blockIdx.x * SL_NI;
   const int ib = min(Lin, ia + SL_NI);
@@ -277,7 +277,8 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
   const bool labeled = b < Bl;
   const float cx = (mode == SSB_LOSS_SUP ? 1.0f : 0.5f) / ((float)Bl * (float)L);
   const float cu = Bu > 0 ? 0.5f / ((float)Bu * (float)L) : 0.f;
-  double acc_x = 0.0, acc_u = 0.0, acc_m = 0.0;
+  // per-block partial sums in fp32 (a few hundred O(1) terms); only the cross-block accumulation is fp64
+  float acc_x = 0.f, acc_u = 0.f, acc_m = 0.f;
   for (int tt = threadIdx.x; tt < nt; tt += SL_THREADS) {
     const int t = tlo + tt;
     int i0, i1;
@@ -309,7 +310,7 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
       if (labeled) {
         const int y = (int)target[(size_t)b * L + t];
         if (y >= 0 && y < ncls) {
-          if (owner) acc_x += (double)(lse - z[y]);
+          if (owner) acc_x += lse - z[y];
           for (int k = 0; k < ncls; ++k) g[k] = (pr[k] * inv - (k == y ? 1.f : 0.f)) * cx;
         }
       } else if (mode != SSB_LOSS_SUP) {
@@ -324,7 +325,7 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
           softmax_conf_label(zt, ncls, c, lab);
           const bool mk = c >= thr;
           if (owner) {
-            if (mk) { acc_u += (double)(lse - z[lab]); acc_m += 1.0; }
+            if (mk) { acc_u += lse - z[lab]; acc_m += 1.0f; }
             const size_t o = (size_t)u * L + t;
             if (conf_out) conf_out[o] = c;
             if (label_out) label_out[o] = (int64_t)lab;
@@ -344,7 +345,7 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
             l += q[k] * (lse - z[k]);
             g[k] = (pr[k] * inv - q[k]) * cu;
           }
-          if (owner) acc_u += (double)l;
+          if (owner) acc_u += l;
         }
       }
     }
@@ -355,7 +356,13 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
   for (int o = threadIdx.x; o < (ib - ia) * ncls; o += SL_THREADS) {
     const int i = ia + o / ncls, k = o % ncls;
     float acc = 0.f;
-    for (int tt = 0; tt < nt; ++tt) {
+    // only positions whose source coordinate lies in (i-1, i+1) can touch low-res index i
+    int ta = 0, tb = nt;
+    if (scale > 0.f && !align_corners) {
+      ta = max(0, (int)floorf(((float)i - 0.5f) / scale - 0.5f) - 2 - tlo);
+      tb = min(nt, (int)ceilf(((float)i + 1.5f) / scale - 0.5f) + 3 - tlo);
+    }
+    for (int tt = ta; tt < tb; ++tt) {
       const int i0 = sI0[tt];
       const int i1 = i0 + (i0 < Lin - 1 ? 1 : 0);
       const float w1 = sW1[tt];
@@ -366,16 +373,16 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
     dlow[((size_t)b * Lin + i) * ncls + k] = acc;
   }
   // loss partial sums
-  acc_x = warp_sum_d(acc_x);
-  acc_u = warp_sum_d(acc_u);
-  acc_m = warp_sum_d(acc_m);
+  acc_x = warp_sum(acc_x);
+  acc_u = warp_sum(acc_u);
+  acc_m = warp_sum(acc_m);
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) { sRed[0][wid] = acc_x; sRed[1][wid] = acc_u; sRed[2][wid] = acc_m; }
   __syncthreads();
   if (threadIdx.x < 3) {
-    double s = 0.0;
+    float s = 0.f;
     for (int i = 0; i < SL_THREADS / 32; ++i) s += sRed[threadIdx.x][i];
-    if (s != 0.0) atomicAdd(&sums[threadIdx.x], s);
+    if (s != 0.f) atomicAdd(&sums[threadIdx.x], (double)s);
   }
 }
 
