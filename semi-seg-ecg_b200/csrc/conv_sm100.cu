@@ -677,7 +677,8 @@ int run_tn(const void* a_base, long long a_inner, long long a_outer, long long a
            bool b_mn, bool tap3, bf16* out, const TnParams& p, cudaStream_t st) {
   CUtensorMap tmA, tmB;
   int rc;
-  if (tap3 && g_tn3) {
+  // (K = 64: a single K chunk -- nothing to reuse, and the smaller v1 footprint lets two CTAs share an SM)
+  if (tap3 && g_tn3 && p.K >= 128) {
     // widest tile that still gives every SM a CTA
     const int mt = ceil_div(p.M, BM);
     int BN = 64;
