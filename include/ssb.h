@@ -95,6 +95,20 @@ typedef struct ssb_step_params {
   float pad[6];
 } ssb_step_params;
 
+/* one (possibly skipped) RandAugment op of one strip; the draws are made on the host in the
+ * reference's np.random call order (utils/transforms.py:574-583, 647-657) */
+enum ssb_aug_kind {
+  SSB_AUG_AMPLITUDE = 0,     /* AmplitudeScaling: x *= N(1, level*0.5) elementwise          (:340-351) */
+  SSB_AUG_POWERLINE = 1,     /* AdaptivePowerlineNoise: a = frequency in Hz (50 | 60)       (:480-502) */
+  SSB_AUG_PARTIAL_WHITE = 2, /* RandomPartialWhiteNoise: a = count, b = start               (:521-546) */
+  SSB_AUG_PARTIAL_SINE = 3   /* RandomPartialSineNoise:  a = count, b = start               (:504-509, 529-546) */
+};
+typedef struct ssb_aug_op {
+  int32_t kind;   /* ssb_aug_kind */
+  int32_t apply;  /* RandomApply's coin (0: op skipped) */
+  int32_t a, b;
+} ssb_aug_op;
+
 /* ---- library / device ------------------------------------------------------------ */
 int ssb_version(void);
 const char* ssb_last_error(void);
@@ -235,6 +249,28 @@ int ssb_ema(float* dst, const float* src, size_t n, const ssb_step_params* sp, s
 int ssb_ema_i64(float* dst, const int64_t* src, size_t n, const ssb_step_params* sp, ssb_stream_t stream);
 /* out[0] = sqrt(sum g^2) (misc.py:265-278); ws: fp64[1] zeroed by the caller */
 int ssb_grad_norm(const float* g, size_t n, double* ws, float* out, ssb_stream_t stream);
+
+/* ---- GPU-resident augmentation (utils/semi_dataset.py:193-197, 235-242) ---------
+ * Strips are [B, C, L] fp32 (the reference's item layout, batched); per-strip draws live in small
+ * device arrays filled by the host. */
+/* spec[B*C][L/2+1] (complex64) = rfft(x) bins 0 .. min(size[b], L)/2 (the others are not written) */
+int ssb_aug_spectrum(const float* x, float* spec, const int32_t* size, int B, int C, int L,
+                     ssb_stream_t stream);
+/* RandomResizeCrop (utils/transforms.py:93-127) from the spectrum: Fourier resize to size[b]
+ * (scipy.signal.resample semantics), centre zero-pad to >= L, crop [start[b], start[b]+L).
+ * lab_in/lab_out: optional int64 [B, L] labels, nearest-neighbour resized (interp1d kind='nearest'),
+ * padded with 0 and cropped with the same indices.  max_size >= max_b size[b] (<= 2L). */
+int ssb_aug_resize_crop(const float* spec, const int64_t* lab_in, float* y, int64_t* lab_out,
+                        const int32_t* size, const int32_t* start, int B, int C, int L, int max_size,
+                        ssb_stream_t stream);
+/* RandAugment ops (ops[B][n_ops], in drawn order) followed by Standardize over (C, L)
+ * (utils/transforms.py:301-310); n_ops = 0 is the plain standardise of the weak view.
+ * scales / white: optional explicit [B, C, L] draws of AmplitudeScaling's N(1, sigma) factors and
+ * of the white noise (injected-draw parity); NULL: counter-based RNG keyed by (seed, strip, element).
+ * level = RandAugment level / 10; fs = sampling rate of the powerline op.  y may alias x. */
+int ssb_aug_strong_standardize(const float* x, float* y, const ssb_aug_op* ops, int n_ops,
+                               const float* scales, const float* white, uint32_t seed, int B, int C,
+                               int L, int fs, float level, ssb_stream_t stream);
 
 #ifdef __cplusplus
 }

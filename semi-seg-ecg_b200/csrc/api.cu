@@ -19,6 +19,7 @@ void ssb_set_error(const char* fmt, ...) {
 int ssb_sm100_prepare();
 int ssb_simt_prepare();
 int ssb_loss_prepare();
+int ssb_aug_prepare();
 
 extern "C" {
 
@@ -29,6 +30,7 @@ int ssb_prepare(void) {
   if (rc) return rc;
   if ((rc = ssb_simt_prepare())) return rc;
   if ((rc = ssb_loss_prepare())) return rc;
+  if ((rc = ssb_aug_prepare())) return rc;
   return ssb_sm100_prepare();
 }
 

@@ -1,0 +1,312 @@
+// GPU-resident augmentation of ECG strips: the per-item numpy/scipy pipeline of the
+// reference's DataLoader workers, batched on the device and written straight into the step's input arena.
+//   weak   RandomResizeCrop: Fourier resize (scipy.signal.resample) + centre zero-pad + random crop,
+//          labels by nearest-neighbour resize                       (utils/transforms.py:93-127)
+//   strong RandAugment over AmplitudeScaling / AdaptivePowerlineNoise / RandomPartialWhiteNoise /
+//          RandomPartialSineNoise                                    (utils/transforms.py:340-351, 480-546, 647-657)
+//   Standardize over (leads, time)                                   (utils/transforms.py:301-310)
+// All random DRAWS come from the host (a few scalars per strip, same np.random call order as the
+// reference); the bulk noise arrays are either passed in (parity tests: injected draws) or generated
+// by a counter-based RNG on the device.
+//
+// The Fourier resize is evaluated directly (two dense DFT passes with exact integer phase indices into a
+// shared-memory twiddle table): sizes are arbitrary integers in [L/2, 2L] (no FFT-friendly factorisation),
+// only the L cropped output positions are needed, and at L = 2500 the whole batch is ~1 GFLOP.
+#include "common.cuh"
+
+#define AUG_THREADS 256
+
+// ---------------------------------------------------------------------------------------------
+// forward real DFT of every (strip, lead): spec[bc][k] = sum_n x[n] * exp(-2*pi*i*k*n/L), k <= min(size,L)/2
+// grid = (ceil(K1 / AUG_THREADS), B*C); one frequency per thread
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AUG_THREADS)
+aug_spectrum_kernel(const float* __restrict__ x, float2* __restrict__ spec, const int32_t* __restrict__ size, int C, int L,
+                    int K1) {
+  pdl_wait();
+  extern __shared__ float sm[];
+  float* xs = sm;                                        // [L]
+  float2* tw = reinterpret_cast<float2*>(sm + ((L + 1) & ~1));   // [L] (cos, sin)(2*pi*m/L)
+  const int bc = blockIdx.y;
+  const int b = bc / C;
+  const int N = min(size[b], L);
+  const int kmax = N / 2;
+  if ((int)(blockIdx.x * AUG_THREADS) > kmax) return;
+  for (int n = threadIdx.x; n < L; n += AUG_THREADS) {
+    xs[n] = x[(size_t)bc * L + n];
+    float s, c;
+    sincospif(2.0f * (float)n / (float)L, &s, &c);
+    tw[n] = make_float2(c, s);
+  }
+  __syncthreads();
+  const int k = blockIdx.x * AUG_THREADS + threadIdx.x;
+  if (k > kmax) return;
+  float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
+  int idx = 0;
+  int n = 0;
+  for (; n + 1 < L; n += 2) {
+    const float2 w0 = tw[idx];
+    idx += k; if (idx >= L) idx -= L;
+    const float2 w1 = tw[idx];
+    idx += k; if (idx >= L) idx -= L;
+    const float a0 = xs[n], a1 = xs[n + 1];
+    re0 = fmaf(a0, w0.x, re0); im0 = fmaf(-a0, w0.y, im0);
+    re1 = fmaf(a1, w1.x, re1); im1 = fmaf(-a1, w1.y, im1);
+  }
+  if (n < L) {
+    const float2 w0 = tw[idx];
+    re0 = fmaf(xs[n], w0.x, re0); im0 = fmaf(-xs[n], w0.y, im0);
+  }
+  spec[(size_t)bc * K1 + k] = make_float2(re0 + re1, im0 + im1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// inverse real DFT of length `size` evaluated only at the cropped positions, + pad + crop, + labels
+// grid = (ceil(L / AUG_THREADS), B*C); one output position per thread
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AUG_THREADS)
+aug_resize_crop_kernel(const float2* __restrict__ spec, const int64_t* __restrict__ lab_in, float* __restrict__ y,
+                       int64_t* __restrict__ lab_out, const int32_t* __restrict__ size_arr,
+                       const int32_t* __restrict__ start_arr, int C, int L, int K1) {
+  pdl_wait();
+  extern __shared__ float sm[];
+  const int bc = blockIdx.y;
+  const int b = bc / C, c = bc - b * C;
+  const int size = size_arr[b], start = start_arr[b];
+  const int N = min(size, L);
+  const int kmax = N / 2;
+  float2* Xs = reinterpret_cast<float2*>(sm);            // [kmax + 1]
+  float2* tw = Xs + (K1 + 1);                            // [size] (cos, sin)(2*pi*m/size)
+  for (int k = threadIdx.x; k <= kmax; k += AUG_THREADS) {
+    float2 v = spec[(size_t)bc * K1 + k];
+    // irfft weights: 1 for DC, 2 for interior bins; the shared Nyquist bin of an even N keeps
+    // scipy.signal.resample's fix-up (x2 when shrinking, x0.5 when growing, untouched when equal)
+    float w = (k == 0) ? 1.f : 2.f;
+    if ((N & 1) == 0 && k == kmax) w = (size < L) ? 2.f : 1.f;
+    Xs[k] = make_float2(v.x * w, v.y * w);
+  }
+  for (int m = threadIdx.x; m < size; m += AUG_THREADS) {
+    float s, co;
+    sincospif(2.0f * (float)m / (float)size, &s, &co);
+    tw[m] = make_float2(co, s);
+  }
+  __syncthreads();
+  const int j = blockIdx.x * AUG_THREADS + threadIdx.x;
+  if (j >= L) return;
+  const int pad = L - size;
+  const int left = pad > 0 ? pad / 2 : 0;
+  const int p = start + j - left;                        // position in the resized strip
+  float out = 0.f;
+  if (p >= 0 && p < size) {
+    float a0 = 0.f, a1 = 0.f;
+    int idx = 0;
+    int k = 0;
+    for (; k + 1 <= kmax; k += 2) {
+      const float2 w0 = tw[idx];
+      idx += p; if (idx >= size) idx -= size;
+      const float2 w1 = tw[idx];
+      idx += p; if (idx >= size) idx -= size;
+      const float2 x0 = Xs[k], x1 = Xs[k + 1];
+      a0 = fmaf(x0.x, w0.x, a0); a0 = fmaf(-x0.y, w0.y, a0);
+      a1 = fmaf(x1.x, w1.x, a1); a1 = fmaf(-x1.y, w1.y, a1);
+    }
+    if (k <= kmax) {
+      const float2 w0 = tw[idx];
+      const float2 x0 = Xs[k];
+      a0 = fmaf(x0.x, w0.x, a0); a0 = fmaf(-x0.y, w0.y, a0);
+    }
+    out = (a0 + a1) / (float)L;
+  }
+  y[(size_t)bc * L + j] = out;
+  if (lab_in && c == 0) {
+    int64_t lab = 0;
+    if (p >= 0 && p < size) {
+      // np.linspace(0, L-1, size)[p] in float64, then interp1d(kind='nearest'): half-way points round DOWN
+      int src;
+      if (size == 1) src = 0;
+      else if (p == size - 1) src = L - 1;
+      else {
+        const double step = (double)(L - 1) / (double)(size - 1);
+        const double pos = (double)p * step;
+        src = (int)ceil(pos - 0.5);
+        src = src < 0 ? 0 : (src > L - 1 ? L - 1 : src);
+      }
+      lab = lab_in[(size_t)b * L + src];
+    }
+    lab_out[(size_t)b * L + j] = lab;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// strong augmentation + standardise, one block per strip
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float aug_uniform(uint32_t seed, uint32_t stream, uint32_t idx) {
+  return ((float)(ssb_hash3(seed, stream, idx) >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+}
+__device__ __forceinline__ float aug_normal(uint32_t seed, uint32_t stream, uint32_t idx) {
+  const float u1 = aug_uniform(seed, stream, 2 * idx), u2 = aug_uniform(seed, stream, 2 * idx + 1);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+// block-wide sum (all threads get the result)
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) red[wid] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < AUG_THREADS / 32; ++i) t += red[i];
+  return t;
+}
+
+// numpy.percentile(..., method='linear') on an ascending array
+__device__ __forceinline__ float percentile_sorted(const float* s, int n, double q) {
+  const double h = (double)(n - 1) * q / 100.0;
+  const int lo = (int)floor(h);
+  const int hi = lo + 1 < n ? lo + 1 : n - 1;
+  const float t = (float)(h - (double)lo);
+  const float a = s[lo], b = s[hi];
+  return t >= 0.5f ? b - (b - a) * (1.0f - t) : a + (b - a) * t;
+}
+
+__global__ void __launch_bounds__(AUG_THREADS)
+aug_strong_standardize_kernel(const float* __restrict__ x, float* __restrict__ y, const ssb_aug_op* __restrict__ ops,
+                              int n_ops, const float* __restrict__ scales, const float* __restrict__ white, uint32_t seed,
+                              int C, int L, int fs, float level, int npow2) {
+  pdl_wait();
+  extern __shared__ float sm[];
+  float* sortbuf = sm;                 // [npow2] (only used by the powerline op)
+  __shared__ float red[AUG_THREADS / 32];
+  __shared__ float s_amp;
+  const int b = blockIdx.x;
+  const size_t base = (size_t)b * C * L;
+  const int n = C * L;
+  float* yb = y + base;
+  for (int i = threadIdx.x; i < n; i += AUG_THREADS) yb[i] = x[base + i];
+  __syncthreads();
+  for (int oi = 0; oi < n_ops; ++oi) {
+    const ssb_aug_op op = ops[(size_t)b * n_ops + oi];
+    if (!op.apply) continue;
+    if (op.kind == SSB_AUG_AMPLITUDE) {
+      const float sigma = level * 0.5f;
+      for (int i = threadIdx.x; i < n; i += AUG_THREADS) {
+        const float sc = scales ? scales[base + i] : 1.0f + sigma * aug_normal(seed, (uint32_t)(b * 8 + oi), (uint32_t)i);
+        yb[i] *= sc;
+      }
+    } else if (op.kind == SSB_AUG_POWERLINE) {
+      for (int c = 0; c < C; ++c) {
+        float* row = yb + (size_t)c * L;
+        for (int i = threadIdx.x; i < npow2; i += AUG_THREADS) sortbuf[i] = i < L ? row[i] : INFINITY;
+        __syncthreads();
+        for (int k = 2; k <= npow2; k <<= 1) {          // bitonic sort, ascending
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < npow2; i += AUG_THREADS) {
+              const int ixj = i ^ j;
+              if (ixj > i) {
+                const float a = sortbuf[i], bb = sortbuf[ixj];
+                const bool up = (i & k) == 0;
+                if ((a > bb) == up) { sortbuf[i] = bb; sortbuf[ixj] = a; }
+              }
+            }
+            __syncthreads();
+          }
+        }
+        if (threadIdx.x == 0) s_amp = (percentile_sorted(sortbuf, L, 95.0) - percentile_sorted(sortbuf, L, 5.0)) * 0.5f;
+        __syncthreads();
+        const float amp = s_amp;
+        const int f2 = 2 * op.a;                          // phase in half-turns: 2*f*t/fs, reduced exactly
+        for (int t = threadIdx.x; t < L; t += AUG_THREADS) {
+          const int r = (int)(((long long)f2 * t) % (2 * fs));
+          row[t] += amp * sinpif((float)r / (float)fs);
+        }
+        __syncthreads();
+      }
+    } else if (op.kind == SSB_AUG_PARTIAL_WHITE) {
+      const int cnt = op.a, st = op.b;
+      for (int i = threadIdx.x; i < C * cnt; i += AUG_THREADS) {
+        const int c = i / cnt, t = i - c * cnt;
+        const float nz = white ? white[base + (size_t)c * L + t] : aug_normal(seed, (uint32_t)(b * 8 + oi), (uint32_t)(c * L + t));
+        yb[(size_t)c * L + st + t] += level * nz;
+      }
+    } else if (op.kind == SSB_AUG_PARTIAL_SINE) {
+      const int cnt = op.a, st = op.b;
+      // amplitude = level, freq = 0.5/level: sin(2*pi*(t/L)/freq) = sinpi(4*level*t/L)
+      for (int i = threadIdx.x; i < C * cnt; i += AUG_THREADS) {
+        const int c = i / cnt, t = i - c * cnt;
+        yb[(size_t)c * L + st + t] += level * sinpif(4.0f * level * (float)t / (float)L);
+      }
+    }
+    __syncthreads();
+  }
+  // standardise over (C, L): two passes for the variance
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += AUG_THREADS) s += yb[i];
+  const float mean = block_sum(s, red) / (float)n;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < n; i += AUG_THREADS) {
+    const float d = yb[i] - mean;
+    q = fmaf(d, d, q);
+  }
+  const float var = block_sum(q, red) / (float)n;
+  const float sd = sqrtf(var);
+  const float inv = sd != 0.f ? 1.0f / sd : 0.f;
+  for (int i = threadIdx.x; i < n; i += AUG_THREADS) yb[i] = (yb[i] - mean) * inv;
+}
+
+int ssb_aug_prepare() {
+  cudaError_t e = cudaFuncSetAttribute(aug_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(aug_resize_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(aug_strong_standardize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (e != cudaSuccess) {
+    ssb_set_error("ssb_aug_prepare: %s", cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+  }
+  return SSB_OK;
+}
+
+extern "C" {
+
+int ssb_aug_spectrum(const float* x, float* spec, const int32_t* size, int B, int C, int L, ssb_stream_t stream) {
+  SSB_REQUIRE(x && spec && size, "ssb_aug_spectrum: null pointer");
+  SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_spectrum: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
+  const int K1 = L / 2 + 1;
+  const size_t smem = ((size_t)((L + 1) & ~1) + 2 * (size_t)L) * sizeof(float);
+  ssb_launch(aug_spectrum_kernel, dim3(ceil_div(K1, AUG_THREADS), B * C), dim3(AUG_THREADS), smem, to_stream(stream), x,
+             reinterpret_cast<float2*>(spec), size, C, L, K1);
+  SSB_LAUNCH_CHECK("ssb_aug_spectrum");
+  return SSB_OK;
+}
+
+int ssb_aug_resize_crop(const float* spec, const int64_t* lab_in, float* y, int64_t* lab_out, const int32_t* size,
+                        const int32_t* start, int B, int C, int L, int max_size, ssb_stream_t stream) {
+  SSB_REQUIRE(spec && y && size && start, "ssb_aug_resize_crop: null pointer");
+  SSB_REQUIRE((lab_in == nullptr) == (lab_out == nullptr), "ssb_aug_resize_crop: lab_in and lab_out go together");
+  SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_resize_crop: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
+  SSB_REQUIRE(max_size >= 1 && max_size <= 2 * L, "ssb_aug_resize_crop: max_size %d out of [1, 2L]", max_size);
+  const int K1 = L / 2 + 1;
+  const size_t smem = ((size_t)(K1 + 1) + (size_t)max_size) * sizeof(float2);
+  SSB_REQUIRE(smem <= 200 * 1024, "ssb_aug_resize_crop: strip too long for the shared-memory tables (%zu B)", smem);
+  ssb_launch(aug_resize_crop_kernel, dim3(ceil_div(L, AUG_THREADS), B * C), dim3(AUG_THREADS), smem, to_stream(stream),
+             reinterpret_cast<const float2*>(spec), lab_in, y, lab_out, size, start, C, L, K1);
+  SSB_LAUNCH_CHECK("ssb_aug_resize_crop");
+  return SSB_OK;
+}
+
+int ssb_aug_strong_standardize(const float* x, float* y, const ssb_aug_op* ops, int n_ops, const float* scales,
+                               const float* white, uint32_t seed, int B, int C, int L, int fs, float level,
+                               ssb_stream_t stream) {
+  SSB_REQUIRE(x && y, "ssb_aug_strong_standardize: null pointer");
+  SSB_REQUIRE(n_ops == 0 || ops, "ssb_aug_strong_standardize: ops table missing");
+  SSB_REQUIRE(B > 0 && C > 0 && L >= 2 && L <= 8192 && fs > 0 && n_ops >= 0 && n_ops <= 8,
+              "ssb_aug_strong_standardize: bad arguments (B=%d C=%d L=%d fs=%d n_ops=%d)", B, C, L, fs, n_ops);
+  int npow2 = 1;
+  while (npow2 < L) npow2 <<= 1;
+  ssb_launch(aug_strong_standardize_kernel, dim3(B), dim3(AUG_THREADS), (size_t)npow2 * sizeof(float), to_stream(stream), x, y,
+             ops, n_ops, scales, white, seed, C, L, fs, level, npow2);
+  SSB_LAUNCH_CHECK("ssb_aug_strong_standardize");
+  return SSB_OK;
+}
+
+}  // extern "C"

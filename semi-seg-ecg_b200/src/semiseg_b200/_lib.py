@@ -43,7 +43,13 @@ class StepParams(C.Structure):
                 ("conf_thresh", C.c_float), ("pad", C.c_float * 6)]
 
 
-assert C.sizeof(StepParams) == 64 and C.sizeof(Geom) == 16
+class AugOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("apply", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
+
+
+AUG_AMPLITUDE, AUG_POWERLINE, AUG_PARTIAL_WHITE, AUG_PARTIAL_SINE = 0, 1, 2, 3
+
+assert C.sizeof(StepParams) == 64 and C.sizeof(Geom) == 16 and C.sizeof(AugOp) == 16
 
 _P, _I, _F, _SZ, _D = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_double
 _BNP = C.POINTER(BN)
@@ -82,6 +88,9 @@ SIGNATURES = {
     "ssb_ema": [_P, _P, _SZ, _P, _P],
     "ssb_ema_i64": [_P, _P, _SZ, _P, _P],
     "ssb_grad_norm": [_P, _SZ, _P, _P, _P],
+    "ssb_aug_spectrum": [_P, _P, _P, _I, _I, _I, _P],
+    "ssb_aug_resize_crop": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "ssb_aug_strong_standardize": [_P, _P, _P, _I, _P, _P, C.c_uint32, _I, _I, _I, _I, _F, _P],
 }
 _RESTYPES = {"ssb_last_error": C.c_char_p, "ssb_launch_count": C.c_int64}
 

@@ -2,6 +2,7 @@
 (tests/golden/reference_vectors.npz, produced by tests/golden/make_golden.py).  The reference
 has no tests / golden vectors of its own."""
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -125,3 +126,55 @@ def test_closed_form_loss_gradient():
     loss = (O.ce_hard(z[:2], yx) + O.ce_soft(z[2:], p)) / 2
     loss.backward()
     assert rel_err(O.loss_grad_fullres(z.detach(), 2, yx, None, None, p), z.grad) < 1e-12
+
+
+# ---- augmentation row: oracle pinned against the unmodified reference transforms ----
+AUG_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "augment_vectors.npz")
+
+
+def test_augment_oracle_matches_reference_transforms():
+    """Seeding numpy like tests/golden/make_golden_aug.py did, the oracle must consume the same random
+    stream and produce the reference's outputs (float32 items and int64 labels) exactly."""
+    from oracle import augment_oracle as A
+    g = np.load(AUG_GOLDEN)
+    for seed, C, L in g["cases"]:
+        pre = f"s{seed}"
+        x, y = g[pre + "/x"], g[pre + "/y"]
+        np.random.seed(int(seed))
+        ecg, tgt, _ = A.labeled_item(x.copy(), y.copy(), int(L))
+        assert np.array_equal(tgt, g[pre + "/lab_target"]), (seed, "labels")
+        assert np.abs(ecg - g[pre + "/lab_ecg"]).max() <= 1e-6, (seed, "labeled ecg")
+        np.random.seed(int(seed) + 1000)
+        uw, us, _ = A.unlabeled_item(x.copy(), int(L))
+        assert np.abs(uw - g[pre + "/unl_ecg"]).max() <= 1e-6, (seed, "weak view")
+        assert np.abs(us - g[pre + "/unl_ecg_aug"]).max() <= 1e-6, (seed, "strong view")
+
+
+def test_fourier_resample_is_scipy_resample():
+    from scipy.signal import resample
+    from oracle import augment_oracle as A
+    rng = np.random.default_rng(0)
+    for L, num in [(2500, 1250), (2500, 1251), (2500, 2500), (2500, 3708), (2500, 4999), (601, 433), (601, 900), (600, 600)]:
+        x = rng.standard_normal((2, L))
+        assert np.abs(A.fourier_resample(x, num) - resample(x, num, axis=1)).max() < 1e-10, (L, num)
+
+
+def test_host_draws_follow_the_reference_order():
+    """semiseg_b200.augment's draw functions (product side) consume numpy's stream exactly like the oracle's."""
+    from oracle import augment_oracle as A
+    from semiseg_b200 import augment as G
+    cfg = G.AugConfig(target_length=600)
+    np.random.seed(5)
+    a = [A.draw_weak(600, 600), A.draw_strong(2, 600), A.draw_weak(600, 600)]
+    np.random.seed(5)
+    b = [G.draw_weak(600, cfg), G.draw_strong(2, 600, cfg, bulk=True), G.draw_weak(600, cfg)]
+    assert (a[0]["size"], a[0]["start"]) == (b[0]["size"], b[0]["start"])
+    assert (a[2]["size"], a[2]["start"]) == (b[2]["size"], b[2]["start"])
+    for oa, ob in zip(a[1]["ops"], b[1]["ops"]):
+        assert oa["op"] == ob["op"] and oa["apply"] == ob["apply"]
+        if oa["apply"] and oa["op"] == "powerline":
+            assert oa["freq"] == ob["a"]
+        if oa["apply"] and oa["op"] in ("partial_white", "partial_sine"):
+            assert (oa["count"], oa["start"]) == (ob["a"], ob["b"])
+        if oa["apply"] and oa["op"] == "amplitude_scaling":
+            assert np.array_equal(oa["scales"], ob["scales"])
