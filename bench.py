@@ -336,6 +336,52 @@ def run_b200(args):
                         "tflops": round(fl / (us * 1e-6) / 1e12, 2) if fl else None, "gbs": round(by / (us * 1e-6) / 1e9, 1) if by else None})
         if world == 1 and not args.no_large:
             large = large_batch_roofline(peaks)
+    # ---- augmentation row (8a-15): raw strips resident on the device -> GPU weak/strong/standardise -> step ----
+    aug = None
+    if world == 1 and not args.no_aug:
+        from semiseg_b200.augment import AugConfig, FixMatchBatcher
+        acfg = AugConfig.from_config(cfg)
+        acfg.target_length = L
+        bat = FixMatchBatcher(eng, acfg, seed=cfg["seed"])
+        raw = [(torch.randn(Bl, C, L, device=dev) * 0.4 + 0.1, devb[i][1], torch.randn(Bu, C, L, device=dev) * 0.4) for i in range(pool)]
+        np.random.seed(cfg["seed"])
+        for i in range(3):
+            bat.load(*raw[i % pool]); eng.step(lr_at(epoch_f[0], tcfg))
+        torch.cuda.synchronize()
+        ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        nrep = min(args.steps, 100)
+        t0 = time.time()
+        ev0.record()
+        for i in range(nrep):
+            bat.load(*raw[i % pool])
+        ev1.record()
+        for i in range(nrep):
+            bat.load(*raw[i % pool]); eng.step(lr_at(epoch_f[0], tcfg))
+        ev2.record()
+        # overlapped: batch i+1 is augmented on a side stream (one captured graph launch) while step i runs
+        ev4 = torch.cuda.Event(enable_timing=True)
+        bat2 = FixMatchBatcher(eng, acfg, seed=cfg["seed"] + 1)
+        bat2.prefetch_captured(*raw[0])
+        bat2.commit(); eng.step(lr_at(epoch_f[0], tcfg)); bat2.prefetch_captured(*raw[1])
+        torch.cuda.synchronize()
+        ev3b = torch.cuda.Event(enable_timing=True)
+        ev3b.record()
+        for i in range(nrep):
+            bat2.commit(); eng.step(lr_at(epoch_f[0], tcfg))
+            bat2.prefetch_captured(*raw[(i + 1) % pool])
+        bat2.commit()
+        ev4.record()
+        torch.cuda.synchronize()
+        eng.read_stats()
+        aug = {"augment_only_ms_per_batch": round(ev0.elapsed_time(ev1) / nrep, 4),
+               "augment_only_samples_per_s": round(per_step * nrep / (ev0.elapsed_time(ev1) / 1e3), 1),
+               "step_with_augment_ms": round(ev1.elapsed_time(ev2) / nrep, 4),
+               "step_with_augment_samples_per_s": round(per_step * nrep / (ev1.elapsed_time(ev2) / 1e3), 1),
+               "step_with_overlapped_augment_ms": round(ev3b.elapsed_time(ev4) / nrep, 4),
+               "step_with_overlapped_augment_samples_per_s": round(per_step * nrep / (ev3b.elapsed_time(ev4) / 1e3), 1),
+               "cpu_oracle_samples_per_s": cpu_augment_rate(C, L),
+               "what": "FixMatchBatcher.load (weak Fourier resize-crop + labels, RandAugment 3 of 4 ops, standardise x3) from raw "
+                       "strips resident in HBM into the engine's input arena; host makes only the scalar draws"}
     if rank != 0:
         _finish(world)
         return
@@ -368,6 +414,8 @@ def run_b200(args):
         line["cpu_baseline"] = cpu
     if large is not None:
         line["large_batch_roofline"] = large
+    if aug is not None:
+        line["gpu_augmentation"] = aug
     print(json.dumps(line), flush=True)
     _finish(world)
 
@@ -404,6 +452,21 @@ def large_batch_roofline(peaks, workload="fixmatch_resnet18w128_12x5000_b32+32")
     del eng, model
     torch.cuda.empty_cache()
     return out
+
+
+def cpu_augment_rate(C, L, budget_s=2.0):
+    """The reference's per-item augmentation (oracle port: numpy/scipy float64, one core) on this host."""
+    from oracle import augment_oracle as A
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((C, L))
+    y = rng.integers(0, 4, (1, L))
+    np.random.seed(0)
+    t0, n = time.time(), 0
+    while time.time() - t0 < budget_s:
+        A.labeled_item(x, y, L)
+        A.unlabeled_item(x, L)
+        n += 2
+    return round(n / (time.time() - t0), 1)
 
 
 def cpu_step_fn(workload):
@@ -484,6 +547,7 @@ def main():
                     "0: per-rank BN (ddp.sync_bn: false)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aug", action="store_true", help="skip the supplementary GPU-augmentation measurement")
     ap.add_argument("--no-large", action="store_true", help="skip the supplementary large-batch roofline block")
     ap.add_argument("--profile-mode", action="store_true", help="warm-up + K plain steps only (for ncu)")
     a = ap.parse_args()

@@ -267,10 +267,13 @@ int ssb_aug_resize_crop(const float* spec, const int64_t* lab_in, float* y, int6
  * (utils/transforms.py:301-310); n_ops = 0 is the plain standardise of the weak view.
  * scales / white: optional explicit [B, C, L] draws of AmplitudeScaling's N(1, sigma) factors and
  * of the white noise (injected-draw parity); NULL: counter-based RNG keyed by (seed, strip, element).
- * level = RandAugment level / 10; fs = sampling rate of the powerline op.  y may alias x. */
+ * seed_dev (may be NULL): device word added to `seed` at run time, so a launch captured in a CUDA graph
+ * gets a fresh key on every replay.  level = RandAugment level / 10; fs = sampling rate of the powerline
+ * op.  y may alias x. */
 int ssb_aug_strong_standardize(const float* x, float* y, const ssb_aug_op* ops, int n_ops,
-                               const float* scales, const float* white, uint32_t seed, int B, int C,
-                               int L, int fs, float level, ssb_stream_t stream);
+                               const float* scales, const float* white, uint32_t seed,
+                               const uint32_t* seed_dev, int B, int C, int L, int fs, float level,
+                               ssb_stream_t stream);
 
 #ifdef __cplusplus
 }

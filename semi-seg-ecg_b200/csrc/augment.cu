@@ -16,53 +16,67 @@
 
 #define AUG_THREADS 256
 
+// Both DFT passes walk the phase with a complex rotation (4 FMAs per term) and re-anchor it every
+// AUG_RESYNC terms from the EXACT integer phase (k*n mod L) through sincospi, so there is no twiddle table,
+// no data-dependent shared-memory traffic, and the rounding drift stays below ~1e-6.
+#define AUG_RESYNC 32
+#define AUG_FPB 64        // frequencies (or output positions) per block; x 4 segments of the summation range
+
+__device__ __forceinline__ float2 unit_phase(long long num, int den) {   // exp(2*pi*i * (num mod den) / den)
+  const int r = (int)(num % den);
+  float s, c;
+  sincospif(2.0f * (float)r / (float)den, &s, &c);
+  return make_float2(c, s);
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward real DFT of every (strip, lead): spec[bc][k] = sum_n x[n] * exp(-2*pi*i*k*n/L), k <= min(size,L)/2
-// grid = (ceil(K1 / AUG_THREADS), B*C); one frequency per thread
+// grid = (ceil(K1 / 64), B*C); block = 64 frequencies x 4 segments of n
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(AUG_THREADS)
 aug_spectrum_kernel(const float* __restrict__ x, float2* __restrict__ spec, const int32_t* __restrict__ size, int C, int L,
                     int K1) {
   pdl_wait();
   extern __shared__ float sm[];
-  float* xs = sm;                                        // [L]
-  float2* tw = reinterpret_cast<float2*>(sm + ((L + 1) & ~1));   // [L] (cos, sin)(2*pi*m/L)
+  float* xs = sm;                                                   // [L]
+  float2* part = reinterpret_cast<float2*>(sm + ((L + 3) & ~3));    // [4][64]
   const int bc = blockIdx.y;
   const int b = bc / C;
-  const int N = min(size[b], L);
-  const int kmax = N / 2;
-  if ((int)(blockIdx.x * AUG_THREADS) > kmax) return;
-  for (int n = threadIdx.x; n < L; n += AUG_THREADS) {
-    xs[n] = x[(size_t)bc * L + n];
-    float s, c;
-    sincospif(2.0f * (float)n / (float)L, &s, &c);
-    tw[n] = make_float2(c, s);
-  }
+  const int kmax = min(size[b], L) / 2;
+  if ((int)(blockIdx.x * AUG_FPB) > kmax) return;
+  for (int n = threadIdx.x; n < L; n += AUG_THREADS) xs[n] = x[(size_t)bc * L + n];
   __syncthreads();
-  const int k = blockIdx.x * AUG_THREADS + threadIdx.x;
-  if (k > kmax) return;
-  float re0 = 0.f, im0 = 0.f, re1 = 0.f, im1 = 0.f;
-  int idx = 0;
-  int n = 0;
-  for (; n + 1 < L; n += 2) {
-    const float2 w0 = tw[idx];
-    idx += k; if (idx >= L) idx -= L;
-    const float2 w1 = tw[idx];
-    idx += k; if (idx >= L) idx -= L;
-    const float a0 = xs[n], a1 = xs[n + 1];
-    re0 = fmaf(a0, w0.x, re0); im0 = fmaf(-a0, w0.y, im0);
-    re1 = fmaf(a1, w1.x, re1); im1 = fmaf(-a1, w1.y, im1);
+  const int kl = threadIdx.x & (AUG_FPB - 1), seg = threadIdx.x / AUG_FPB;
+  const int k = blockIdx.x * AUG_FPB + kl;
+  const int seglen = (L + 3) / 4;
+  const int n0 = seg * seglen, n1 = min(L, n0 + seglen);
+  float re = 0.f, im = 0.f;
+  if (k <= kmax) {
+    const float2 w = unit_phase(k, L);            // one step of the rotation (conjugated below)
+    for (int nb = n0; nb < n1; nb += AUG_RESYNC) {
+      float2 ph = unit_phase((long long)k * nb, L);
+      const int ne = min(n1, nb + AUG_RESYNC);
+      for (int n = nb; n < ne; ++n) {
+        const float a = xs[n];
+        re = fmaf(a, ph.x, re);
+        im = fmaf(-a, ph.y, im);
+        const float c = ph.x * w.x - ph.y * w.y;
+        ph.y = fmaf(ph.x, w.y, ph.y * w.x);
+        ph.x = c;
+      }
+    }
   }
-  if (n < L) {
-    const float2 w0 = tw[idx];
-    re0 = fmaf(xs[n], w0.x, re0); im0 = fmaf(-xs[n], w0.y, im0);
+  part[seg * AUG_FPB + kl] = make_float2(re, im);
+  __syncthreads();
+  if (seg == 0 && k <= kmax) {
+    const float2 p0 = part[kl], p1 = part[AUG_FPB + kl], p2 = part[2 * AUG_FPB + kl], p3 = part[3 * AUG_FPB + kl];
+    spec[(size_t)bc * K1 + k] = make_float2((p0.x + p1.x) + (p2.x + p3.x), (p0.y + p1.y) + (p2.y + p3.y));
   }
-  spec[(size_t)bc * K1 + k] = make_float2(re0 + re1, im0 + im1);
 }
 
 // ---------------------------------------------------------------------------------------------
 // inverse real DFT of length `size` evaluated only at the cropped positions, + pad + crop, + labels
-// grid = (ceil(L / AUG_THREADS), B*C); one output position per thread
+// grid = (ceil(L / 64), B*C); block = 64 output positions x 4 segments of k
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(AUG_THREADS)
 aug_resize_crop_kernel(const float2* __restrict__ spec, const int64_t* __restrict__ lab_in, float* __restrict__ y,
@@ -75,8 +89,8 @@ aug_resize_crop_kernel(const float2* __restrict__ spec, const int64_t* __restric
   const int size = size_arr[b], start = start_arr[b];
   const int N = min(size, L);
   const int kmax = N / 2;
-  float2* Xs = reinterpret_cast<float2*>(sm);            // [kmax + 1]
-  float2* tw = Xs + (K1 + 1);                            // [size] (cos, sin)(2*pi*m/size)
+  float2* Xs = reinterpret_cast<float2*>(sm);            // [K1]
+  float* part = sm + 2 * (size_t)(K1 + 1);               // [4][64]
   for (int k = threadIdx.x; k <= kmax; k += AUG_THREADS) {
     float2 v = spec[(size_t)bc * K1 + k];
     // irfft weights: 1 for DC, 2 for interior bins; the shared Nyquist bin of an even N keeps
@@ -85,42 +99,40 @@ aug_resize_crop_kernel(const float2* __restrict__ spec, const int64_t* __restric
     if ((N & 1) == 0 && k == kmax) w = (size < L) ? 2.f : 1.f;
     Xs[k] = make_float2(v.x * w, v.y * w);
   }
-  for (int m = threadIdx.x; m < size; m += AUG_THREADS) {
-    float s, co;
-    sincospif(2.0f * (float)m / (float)size, &s, &co);
-    tw[m] = make_float2(co, s);
-  }
   __syncthreads();
-  const int j = blockIdx.x * AUG_THREADS + threadIdx.x;
-  if (j >= L) return;
+  const int jl = threadIdx.x & (AUG_FPB - 1), seg = threadIdx.x / AUG_FPB;
+  const int j = blockIdx.x * AUG_FPB + jl;
   const int pad = L - size;
   const int left = pad > 0 ? pad / 2 : 0;
   const int p = start + j - left;                        // position in the resized strip
-  float out = 0.f;
-  if (p >= 0 && p < size) {
-    float a0 = 0.f, a1 = 0.f;
-    int idx = 0;
-    int k = 0;
-    for (; k + 1 <= kmax; k += 2) {
-      const float2 w0 = tw[idx];
-      idx += p; if (idx >= size) idx -= size;
-      const float2 w1 = tw[idx];
-      idx += p; if (idx >= size) idx -= size;
-      const float2 x0 = Xs[k], x1 = Xs[k + 1];
-      a0 = fmaf(x0.x, w0.x, a0); a0 = fmaf(-x0.y, w0.y, a0);
-      a1 = fmaf(x1.x, w1.x, a1); a1 = fmaf(-x1.y, w1.y, a1);
+  const bool inside = j < L && p >= 0 && p < size;
+  float acc = 0.f;
+  if (inside) {
+    const int nk = kmax + 1;
+    const int seglen = (nk + 3) / 4;
+    const int k0 = seg * seglen, k1 = min(nk, k0 + seglen);
+    const float2 w = unit_phase(p, size);
+    for (int kb = k0; kb < k1; kb += AUG_RESYNC) {
+      float2 ph = unit_phase((long long)kb * p, size);
+      const int ke = min(k1, kb + AUG_RESYNC);
+      for (int k = kb; k < ke; ++k) {
+        const float2 X = Xs[k];
+        acc = fmaf(X.x, ph.x, acc);
+        acc = fmaf(-X.y, ph.y, acc);
+        const float cc = ph.x * w.x - ph.y * w.y;
+        ph.y = fmaf(ph.x, w.y, ph.y * w.x);
+        ph.x = cc;
+      }
     }
-    if (k <= kmax) {
-      const float2 w0 = tw[idx];
-      const float2 x0 = Xs[k];
-      a0 = fmaf(x0.x, w0.x, a0); a0 = fmaf(-x0.y, w0.y, a0);
-    }
-    out = (a0 + a1) / (float)L;
   }
+  part[seg * AUG_FPB + jl] = acc;
+  __syncthreads();
+  if (seg != 0 || j >= L) return;
+  const float out = inside ? ((part[jl] + part[AUG_FPB + jl]) + (part[2 * AUG_FPB + jl] + part[3 * AUG_FPB + jl])) / (float)L : 0.f;
   y[(size_t)bc * L + j] = out;
   if (lab_in && c == 0) {
     int64_t lab = 0;
-    if (p >= 0 && p < size) {
+    if (inside) {
       // np.linspace(0, L-1, size)[p] in float64, then interp1d(kind='nearest'): half-way points round DOWN
       int src;
       if (size == 1) src = 0;
@@ -173,8 +185,9 @@ __device__ __forceinline__ float percentile_sorted(const float* s, int n, double
 __global__ void __launch_bounds__(AUG_THREADS)
 aug_strong_standardize_kernel(const float* __restrict__ x, float* __restrict__ y, const ssb_aug_op* __restrict__ ops,
                               int n_ops, const float* __restrict__ scales, const float* __restrict__ white, uint32_t seed,
-                              int C, int L, int fs, float level, int npow2) {
+                              const uint32_t* __restrict__ seed_dev, int C, int L, int fs, float level, int npow2) {
   pdl_wait();
+  if (seed_dev) seed += *seed_dev;   // per-replay seed of a captured launch
   extern __shared__ float sm[];
   float* sortbuf = sm;                 // [npow2] (only used by the powerline op)
   __shared__ float red[AUG_THREADS / 32];
@@ -272,8 +285,8 @@ int ssb_aug_spectrum(const float* x, float* spec, const int32_t* size, int B, in
   SSB_REQUIRE(x && spec && size, "ssb_aug_spectrum: null pointer");
   SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_spectrum: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
   const int K1 = L / 2 + 1;
-  const size_t smem = ((size_t)((L + 1) & ~1) + 2 * (size_t)L) * sizeof(float);
-  ssb_launch(aug_spectrum_kernel, dim3(ceil_div(K1, AUG_THREADS), B * C), dim3(AUG_THREADS), smem, to_stream(stream), x,
+  const size_t smem = ((size_t)((L + 3) & ~3) + 2 * 4 * AUG_FPB) * sizeof(float);
+  ssb_launch(aug_spectrum_kernel, dim3(ceil_div(K1, AUG_FPB), B * C), dim3(AUG_THREADS), smem, to_stream(stream), x,
              reinterpret_cast<float2*>(spec), size, C, L, K1);
   SSB_LAUNCH_CHECK("ssb_aug_spectrum");
   return SSB_OK;
@@ -286,17 +299,16 @@ int ssb_aug_resize_crop(const float* spec, const int64_t* lab_in, float* y, int6
   SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_resize_crop: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
   SSB_REQUIRE(max_size >= 1 && max_size <= 2 * L, "ssb_aug_resize_crop: max_size %d out of [1, 2L]", max_size);
   const int K1 = L / 2 + 1;
-  const size_t smem = ((size_t)(K1 + 1) + (size_t)max_size) * sizeof(float2);
-  SSB_REQUIRE(smem <= 200 * 1024, "ssb_aug_resize_crop: strip too long for the shared-memory tables (%zu B)", smem);
-  ssb_launch(aug_resize_crop_kernel, dim3(ceil_div(L, AUG_THREADS), B * C), dim3(AUG_THREADS), smem, to_stream(stream),
+  const size_t smem = (2 * (size_t)(K1 + 1) + 4 * AUG_FPB) * sizeof(float);
+  ssb_launch(aug_resize_crop_kernel, dim3(ceil_div(L, AUG_FPB), B * C), dim3(AUG_THREADS), smem, to_stream(stream),
              reinterpret_cast<const float2*>(spec), lab_in, y, lab_out, size, start, C, L, K1);
   SSB_LAUNCH_CHECK("ssb_aug_resize_crop");
   return SSB_OK;
 }
 
 int ssb_aug_strong_standardize(const float* x, float* y, const ssb_aug_op* ops, int n_ops, const float* scales,
-                               const float* white, uint32_t seed, int B, int C, int L, int fs, float level,
-                               ssb_stream_t stream) {
+                               const float* white, uint32_t seed, const uint32_t* seed_dev, int B, int C, int L, int fs,
+                               float level, ssb_stream_t stream) {
   SSB_REQUIRE(x && y, "ssb_aug_strong_standardize: null pointer");
   SSB_REQUIRE(n_ops == 0 || ops, "ssb_aug_strong_standardize: ops table missing");
   SSB_REQUIRE(B > 0 && C > 0 && L >= 2 && L <= 8192 && fs > 0 && n_ops >= 0 && n_ops <= 8,
@@ -304,7 +316,7 @@ int ssb_aug_strong_standardize(const float* x, float* y, const ssb_aug_op* ops, 
   int npow2 = 1;
   while (npow2 < L) npow2 <<= 1;
   ssb_launch(aug_strong_standardize_kernel, dim3(B), dim3(AUG_THREADS), (size_t)npow2 * sizeof(float), to_stream(stream), x, y,
-             ops, n_ops, scales, white, seed, C, L, fs, level, npow2);
+             ops, n_ops, scales, white, seed, seed_dev, C, L, fs, level, npow2);
   SSB_LAUNCH_CHECK("ssb_aug_strong_standardize");
   return SSB_OK;
 }

@@ -90,7 +90,7 @@ SIGNATURES = {
     "ssb_grad_norm": [_P, _SZ, _P, _P, _P],
     "ssb_aug_spectrum": [_P, _P, _P, _I, _I, _I, _P],
     "ssb_aug_resize_crop": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
-    "ssb_aug_strong_standardize": [_P, _P, _P, _I, _P, _P, C.c_uint32, _I, _I, _I, _I, _F, _P],
+    "ssb_aug_strong_standardize": [_P, _P, _P, _I, _P, _P, C.c_uint32, _P, _I, _I, _I, _I, _F, _P],
 }
 _RESTYPES = {"ssb_last_error": C.c_char_p, "ssb_launch_count": C.c_int64}
 

@@ -60,7 +60,8 @@ def test_weak_resize_crop(C, L, B):
     x_d = torch.from_numpy(np.stack(xs).astype(np.float32)).to(DEV)
     y_d = torch.from_numpy(np.stack(ys)[:, 0]).to(DEV)
     y_out = torch.full((B, L), -7, dtype=torch.int64, device=DEV)
-    out = aug.weak_resize_crop(x_d, y_d, draws, labels_out=y_out)
+    sz, st_ = G.weak_table(draws)
+    out = aug.weak_resize_crop(x_d, y_d, sz, st_, labels_out=y_out)
     torch.cuda.synchronize()
     got = out.cpu().numpy().astype(np.float64)
     for b in range(B):
@@ -68,8 +69,10 @@ def test_weak_resize_crop(C, L, B):
         assert np.abs(got[b] - ref_x[b]).max() / scale < TOL, (b, draws[b])
         assert np.array_equal(y_out[b].cpu().numpy(), ref_y[b][0].astype(np.int64)), (b, draws[b])
     # unlabeled call: no label pointers
-    out2 = aug.weak_resize_crop(x_d, None, draws, out=torch.empty_like(out))
+    out2 = aug.weak_resize_crop(x_d, None, sz, st_, out=torch.empty_like(out))
     assert torch.equal(out2, out)
+    with pytest.raises(ValueError):
+        aug.weak_resize_crop(x_d, None, sz * 0 + 3 * L, st_)
 
 
 @pytest.mark.parametrize("C,L,B", [(1, 2500, 8), (2, 1000, 6), (12, 500, 4)])
@@ -109,6 +112,7 @@ def test_strong_and_standardize(C, L, B):
     aug = G.GpuAugmenter(cfg, B, C, L, DEV)
     x_d = torch.from_numpy(np.stack(xs).astype(np.float32)).to(DEV)
     out_s, out_w = torch.empty_like(x_d), torch.empty_like(x_d)
+    gd = G.ops_table(gd)
     aug.strong_standardize(x_d, out_s, gd, scales=torch.from_numpy(scales).to(DEV), white=torch.from_numpy(white).to(DEV))
     aug.strong_standardize(x_d, out_w)
     torch.cuda.synchronize()
@@ -125,7 +129,7 @@ def test_strong_and_standardize(C, L, B):
     assert float(m) < 1e-4 and float(s) < 1e-3
     # statistics of the device RNG: AmplitudeScaling factors ~ N(1, 0.5)
     ones = torch.ones(B, C, L, device=DEV)
-    only_amp = [{"ops": [{"op": "amplitude_scaling", "apply": True, "a": 0, "b": 0}]} for _ in range(B)]
+    only_amp = G.ops_table([{"ops": [{"op": "amplitude_scaling", "apply": True, "a": 0, "b": 0}]} for _ in range(B)])
     raw = torch.empty_like(ones)
     aug.strong_standardize(ones, raw, only_amp)          # standardised N(1, .5) draws -> unit normal
     torch.cuda.synchronize()
@@ -150,7 +154,7 @@ def test_fixmatch_batcher_fills_engine_arena():
     raw_l = torch.from_numpy(np.stack(xs[:Bl]).astype(np.float32)).to(DEV)
     lab_l = torch.from_numpy(np.stack(ys[:Bl])[:, 0]).to(DEV)
     raw_u = torch.from_numpy(np.stack(xs[Bl:]).astype(np.float32)).to(DEV)
-    bat = G.FixMatchBatcher(eng, cfg, seed=1)
+    bat = G.FixMatchBatcher(eng, cfg, seed=1, exact_stream=True)
     bat.load(raw_l, lab_l, raw_u)
     torch.cuda.synchronize()
     # replay the same numpy stream through the oracle (scalar draws only: bulk arrays are device-side)
@@ -169,3 +173,44 @@ def test_fixmatch_batcher_fills_engine_arena():
     eng.step(1e-3)
     s, = eng.read_stats()
     assert np.isfinite(s["loss_total"])
+    # production mode: vectorised draws -- every draw inside its range, outputs standardised
+    fast = G.FixMatchBatcher(eng, cfg, seed=2)
+    for _ in range(20):
+        sz, st_, ops = G.draw_batch(fast.rng, 64, L, cfg, True)
+        assert sz.min() >= L // 2 and sz.max() <= 2 * L - 1 and (st_ <= np.maximum(sz, L) - L).all() and st_.min() >= 0
+        part = (ops[..., 0] >= 2)
+        assert ((ops[..., 2] + ops[..., 3])[part] <= L).all() and set(np.unique(ops[..., 2][ops[..., 0] == 1])) <= {50, 60}
+        assert all(len(set(r)) == cfg.num_layers for r in ops[..., 0])       # ops drawn without replacement
+    fast.load(raw_l, lab_l, raw_u)
+    torch.cuda.synchronize()
+    # overlapped mode delivers the same batches as the in-line mode (same draws: same private generator state)
+    a1, a2 = G.FixMatchBatcher(eng, cfg, seed=9), G.FixMatchBatcher(eng, cfg, seed=9)
+    ref = []
+    for _ in range(3):
+        a1.load(raw_l, lab_l, raw_u)
+        torch.cuda.synchronize()
+        ref.append((eng.x_s.clone(), eng.y_l.clone(), eng.x_uw.clone()))
+    a2.aug_l.calls = a2.aug_u.calls = 0
+    a1.aug_l.calls = a1.aug_u.calls = 0
+    a2.prefetch(raw_l, lab_l, raw_u)
+    for i in range(3):
+        a2.commit()
+        if i < 2:
+            a2.prefetch(raw_l, lab_l, raw_u)
+        torch.cuda.synchronize()
+        assert torch.equal(eng.y_l, ref[i][1]) and torch.equal(eng.x_uw, ref[i][2])
+        assert torch.equal(eng.x_s[:Bl], ref[i][0][:Bl])
+    # captured mode (one graph launch per batch): same weak views / labels as the in-line mode for the same draws
+    a3 = G.FixMatchBatcher(eng, cfg, seed=9)
+    a3.prefetch_captured(raw_l, lab_l, raw_u)
+    for i in range(3):
+        a3.commit()
+        if i < 2:
+            a3.prefetch_captured(raw_l, lab_l, raw_u)
+        torch.cuda.synchronize()
+        assert torch.equal(eng.y_l, ref[i][1]) and torch.equal(eng.x_uw, ref[i][2]) and torch.equal(eng.x_s[:Bl], ref[i][0][:Bl])
+        v = eng.x_s[Bl:].reshape(Bu, -1)
+        assert float(v.mean(1).abs().max()) < 1e-4 and float((v.std(1, unbiased=False) - 1).abs().max()) < 1e-3
+    for t in (eng.x_s, eng.x_uw):
+        v = t.view(t.shape[0], -1)
+        assert float(v.mean(1).abs().max()) < 1e-4 and float((v.std(1, unbiased=False) - 1).abs().max()) < 1e-3
