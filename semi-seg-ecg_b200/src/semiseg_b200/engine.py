@@ -96,6 +96,10 @@ class StepEngine:
         self.wgrad_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.teacher_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.repack_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
+        # gradient all-reduce in two buckets: the tail of the arena (last stage + head, ~3/4 of the bytes) is
+        # exchanged on its own stream as soon as those gradients exist, under the backward of the earlier stages
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.multi_stream and self.collectives and
+                                                              int(os.environ.get("SSB_BUCKETS", "1"))) else None
         self.plan_s = NetPlan(weights, dtype, S, L, True, algo, grads=state.grads, sp_ptr=self.sp_dev.data_ptr(),
                               wgrad_stream=self.wgrad_stream, state=state)
         self.plan_t: Optional[NetPlan] = None
@@ -212,9 +216,31 @@ class StepEngine:
              self.spec.num_classes, self.mode, 0.0, self.sp_dev.data_ptr(), 1 if self.spec.align_corners else 0,
              m["conf"].data_ptr() if m else None, m["label"].data_ptr() if m else None,
              m["mask"].data_ptr() if m else None, st)
+        split = None
+        if self.comm_stream is not None:
+            lay = self.plan_s.lay
+            last_stage = len(self.spec.stage_blocks) - 1
+            first = next(i for i, b in enumerate(lay.blocks) if b.stage == last_stage)
+            split = lay.blocks[first].conv1.poff
+
+            def bucket(bi, first=first, split=split):
+                if bi != first:
+                    return
+                cur_ = torch.cuda.current_stream()
+                self.comm_stream.wait_stream(cur_)                       # BN / head gradients of the tail (main stream)
+                if self.wgrad_stream is not None:
+                    self.comm_stream.wait_stream(self.wgrad_stream)      # conv weight gradients of the tail
+                with torch.cuda.stream(self.comm_stream):
+                    torch.distributed.all_reduce(state.grads[split:], group=self.pg)
+            self.plan_s.block_done_hook = bucket
         self.plan_s.backward(self.plan_s.dlow, st)
+        self.plan_s.block_done_hook = None
         if self.collectives:
-            torch.distributed.all_reduce(state.grads, group=self.pg)
+            if split is not None:
+                torch.distributed.all_reduce(state.grads[:split], group=self.pg)
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+            else:
+                torch.distributed.all_reduce(state.grads, group=self.pg)
         if self.cfg.get("grad_norm", False):
             call("ssb_memset_zero", self.gnorm_ws.data_ptr(), 8, st)
             call("ssb_grad_norm", state.grads.data_ptr(), state.grads.numel(), self.gnorm_ws.data_ptr(),

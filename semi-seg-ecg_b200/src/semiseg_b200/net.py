@@ -318,6 +318,7 @@ class NetPlan:
         self.debug = None        # tests: dict that receives clones of the block-output gradients
         self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
         self.pre_block_event = None   # event the stream waits on after the stem (storage-dtype weight copy ready)
+        self.block_done_hook = None   # callable(block_index) after a block's backward has been enqueued (bucketed all-reduce)
         if algo is None:
             algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
             if os.environ.get("SSB_FORCE_SIMT"):   # debugging aid: generic CUDA-core conv kernels everywhere
@@ -638,6 +639,8 @@ class NetPlan:
                      c.k, c.stride, 1, dt, self._algo_for(c), st)
                 self._wgrad(c, xin, dcd, gin, gout, st)
             G = Gin
+            if self.block_done_hook is not None:
+                self.block_done_hook(bi)
         self._join_wgrad()
         # stem tail + stem conv weight gradient
         call("ssb_stem_bwd_reduce", G.data_ptr(), self.c0.data_ptr(), self.pool_arg.data_ptr(), self.bn(lay.stem_bn),

@@ -19,6 +19,9 @@ per = 2
 data = batches(900, 3, per * world, per * world, 1, 2500)      # global batches
 use_graph = bool(int(os.environ.get("DP_GRAPH", "1")))
 
+nsteps = int(os.environ.get("DP_STEPS", "3"))
+
+
 def run(sync_bn, sharded):
     torch.manual_seed(0)
     model = init_model_from_cfg(model_cfg(1, 64, 64, 128, 0.0)).to("cuda")
@@ -28,7 +31,7 @@ def run(sync_bn, sharded):
     eng = StepEngine(rt.weights, rt.state, _lib.F32, "fixmatch", B, B, 2500, cfg, use_graph=use_graph,
                      process_group=dist.group.WORLD if sharded else None, sync_bn=sync_bn)
     sl = slice(rank * per, (rank + 1) * per) if sharded else slice(None)
-    for lab, unl in data:
+    for lab, unl in data[:nsteps]:
         eng.load_batch(lab["ecg"][sl], lab["target"][sl], unl["ecg"][sl], unl["ecg_aug"][sl])
         eng.step(5e-4)
     stats = eng.read_stats()
@@ -41,14 +44,24 @@ except Exception:
     traceback.print_exc()
     sys.stdout.flush(); sys.stderr.flush()
     os._exit(3)
-worst = max(rel_err(sd_dp[k].double(), sd_1[k].double()) for k in sd_1 if "tracked" not in k)
+errs = sorted(((rel_err(sd_dp[k].double(), sd_1[k].double()), float((sd_dp[k].double() - sd_1[k].double()).abs().max()), k)
+               for k in sd_1 if "tracked" not in k), reverse=True)
+worst = errs[0][0]
+if rank == 0:
+    for e, a, k in errs[:5]:
+        print(f"  {k:50s} rel {e:.2e}  max abs {a:.2e}")
 # mean over ranks of the per-rank losses == global loss (equal shards)
 t = torch.tensor([st_dp[-1]["loss_total"], st_dp[-1]["mask_ratio"]], device="cuda", dtype=torch.float64)
 dist.all_reduce(t); t /= world
 if rank == 0:
     print(f"DP{world} (SyncBN, graph={use_graph}) vs single process on the concatenated batch: worst state_dict rel err {worst:.2e}; "
           f"loss {float(t[0]):.6f} vs {st_1[-1]['loss_total']:.6f}; mask_ratio {float(t[1]):.4f} vs {st_1[-1]['mask_ratio']:.4f}")
-    assert worst < 2e-3, worst   # 3 Adam steps amplify summation-order differences (sign-like first updates)
+    # one step: the sharded run IS the single-process run up to summation order.  More steps: Adam's early updates are
+    # sign-like (m/sqrt(v) = +-1), so 1e-6 gradient differences move near-zero tensors (BN biases, |beta| ~ lr) by a
+    # fraction of lr -- bound the ABSOLUTE drift by one learning-rate step instead
+    if nsteps == 1:
+        assert worst < 1e-4, worst
+    assert errs[0][1] < 5e-4 and max(a for _, a, _ in errs) < 5e-4, errs[:3]
     assert abs(float(t[0]) - st_1[-1]["loss_total"]) < 1e-4
     print("DP equivalence OK")
 torch.cuda.synchronize()
