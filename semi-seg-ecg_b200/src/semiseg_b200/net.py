@@ -396,6 +396,16 @@ class NetPlan:
                 key = (g.pitch, g.len, g.C)
                 if key not in self._scratch:
                     self._scratch[key] = {n: act(g) for n in ("gA", "gE", "gB", "gC", "gD")}
+            # the conv-output gradients (dc2, dc1, downsample) are ALSO read by the weight-gradient GEMMs on the
+            # second stream: one buffer each per block, so that the main chain never waits for a wgrad to
+            # release a buffer it wants to overwrite
+            self.blk_grads: List[Dict[str, torch.Tensor]] = []
+            for bd in self.lay.blocks:
+                gout = self.g_stage[bd.stage]
+                bg = {"dc2": act(gout), "dc1": act(gout)}
+                if bd.convd is not None:
+                    bg["dcd"] = act(gout)
+                self.blk_grads.append(bg)
         self.launches_fwd = 0
 
     # ---- helpers -------------------------------------------------------------------
@@ -572,9 +582,10 @@ class NetPlan:
         sc_f = self._scratch[(gfeat.pitch, gfeat.len, gfeat.C)]
         hc = lay.head_conv
         G = sc_f["gA"]
+        # (the weight-gradient GEMM only needs dy: fork it BEFORE the dgrad so that the two run side by side)
+        self._wgrad(hc, self.feat, sc_h["gB"], gfeat, self.g_head, st)
         call("ssb_conv1d_dgrad", sc_h["gB"].data_ptr(), self.sh.ptr(hc), G.data_ptr(), gfeat,
              self.g_head, hc.k, hc.stride, 0, dt, self._algo_for(hc), st)
-        self._wgrad(hc, self.feat, sc_h["gB"], gfeat, self.g_head, st)
 
         # blocks in reverse
         nblk = len(lay.blocks)
@@ -594,7 +605,8 @@ class NetPlan:
                 Gin = sc["gE"] if G is sc["gA"] else sc["gA"]
             else:
                 Gin = sci["gA"]
-            dc2, dcd, da1 = sc["gB"], sc["gC"], sc["gD"]
+            bg = self.blk_grads[bi]
+            dc2, dcd, da1 = bg["dc2"], bg.get("dcd"), sc["gD"]
             out, c2 = bufs["out"], bufs["c2"]
             self._before_write(dc2, dcd)
             if bd.convd is not None:
@@ -615,11 +627,11 @@ class NetPlan:
                 if bd.convd is not None:
                     self.debug[bd.prefix + ".downsample.0"] = self.to_ncl(dcd, gout)
             c = bd.conv2
+            self._wgrad(c, bufs["a1"], dc2, gout, gout, st)
             call("ssb_conv1d_dgrad", dc2.data_ptr(), self.sh.ptr(c), da1.data_ptr(), gout, gout,
                  c.k, c.stride, 0, dt, self._algo_for(c), st)
-            self._wgrad(c, bufs["a1"], dc2, gout, gout, st)
-            # bn1 + relu backward -> dc1 (reuses gB: dc2 is dead)
-            dc1 = dc2
+            # bn1 + relu backward -> dc1
+            dc1 = bg["dc1"]
             self._before_write(dc1)
             call("ssb_bn_bwd_reduce", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
                  None, None, gout, dt, st)
@@ -630,19 +642,19 @@ class NetPlan:
                 self.debug[bd.prefix + ".conv1"] = self.to_ncl(dc1, gout)
             c = bd.conv1
             acc = 0 if bd.convd is not None else 1   # identity residual: Gin already holds g
+            self._wgrad(c, xin, dc1, gin, gout, st)
+            if bd.convd is not None:
+                self._wgrad(bd.convd, xin, dcd, gin, gout, st)
             call("ssb_conv1d_dgrad", dc1.data_ptr(), self.sh.ptr(c), Gin.data_ptr(), gin, gout,
                  c.k, c.stride, acc, dt, self._algo_for(c), st)
-            self._wgrad(c, xin, dc1, gin, gout, st)
             if bd.convd is not None:
                 c = bd.convd
                 call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.ptr(c), Gin.data_ptr(), gin, gout,
                      c.k, c.stride, 1, dt, self._algo_for(c), st)
-                self._wgrad(c, xin, dcd, gin, gout, st)
             G = Gin
             if self.block_done_hook is not None:
                 self.block_done_hook(bi)
-        self._join_wgrad()
-        # stem tail + stem conv weight gradient
+        # stem tail + stem conv weight gradient (independent of the conv weight gradients still in flight)
         call("ssb_stem_bwd_reduce", G.data_ptr(), self.c0.data_ptr(), self.pool_arg.data_ptr(), self.bn(lay.stem_bn),
              self.g_stem, self.g_pool, dt, st)
         self._sync_bwd(lay.stem_bn)
@@ -650,6 +662,7 @@ class NetPlan:
              self.dc0.data_ptr(), self.g_stem, self.g_pool, dt, st)
         call("ssb_stem_conv_wgrad", x.data_ptr(), self.dc0.data_ptr(), self._g(lay.stem_conv), spec.num_leads, self.L,
              self.g_stem, dt, st)
+        self._join_wgrad()
 
     # ---- test helpers: NCL fp32 copies of internal tensors ---------------------------
     def to_ncl(self, buf: torch.Tensor, g: Geom) -> torch.Tensor:
