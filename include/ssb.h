@@ -156,6 +156,16 @@ int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ss
 int ssb_conv1d_bn_act_fwd(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout,
                           int k, int stride, const ssb_bn* bn, const void* res, int relu,
                           int dtype, int algo, ssb_stream_t stream);
+/* train rows and eval rows of the SAME conv in one launch (FixMatch: the pseudo-label forward uses the
+ * student's weights, fixmatch.py:87-102): the first `train_samples` samples of x are train-mode rows
+ * (raw output to y_train + statistics into sums, as ssb_conv1d_fwd_stats), the remaining samples are
+ * eval-mode rows (y_eval = [relu](bn_eval(conv) [+ res_eval]), as ssb_conv1d_bn_act_fwd).  y_train,
+ * y_eval and res_eval are bases of full [B*pitch, Cout] tensors (same row indexing; each launch only
+ * touches its own row range of each). */
+int ssb_conv1d_fwd_dual(const void* x, const void* w, void* y_train, void* y_eval, ssb_geom gin,
+                        ssb_geom gout, int k, int stride, int train_samples, double* sums,
+                        const ssb_bn* bn_eval, const void* res_eval, int relu, int dtype, int algo,
+                        ssb_stream_t stream);
 /* dx = conv_transpose(dy, w) (+ dx if accumulate) */
 int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout,
                      int k, int stride, int accumulate, int dtype, int algo, ssb_stream_t stream);

@@ -421,7 +421,8 @@ static TapSpec fwd_taps(int k, int stride) {
 }
 
 int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
-                         double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, cudaStream_t st);
+                         double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, int train_samples,
+                         void* y_eval, cudaStream_t st);
 int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
                            int accumulate, cudaStream_t st);
 int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
@@ -454,7 +455,7 @@ int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ss
   SSB_REQUIRE(x && y && w, "ssb_conv1d_fwd: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_fwd: tcgen05 path needs bf16");
-    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, sums, nullptr, nullptr, 0, to_stream(stream));
+    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, sums, nullptr, nullptr, 0, 0, nullptr, to_stream(stream));
   }
   if (sums) {   // generic CUDA-core path: conv, then the statistics pass as its own launch
     rc = ssb_conv1d_fwd_stats(x, w, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
@@ -480,12 +481,36 @@ int ssb_conv1d_bn_act_fwd(const void* x, const void* w, void* y, ssb_geom gin, s
   SSB_REQUIRE(x && y && w && bn, "ssb_conv1d_bn_act_fwd: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_bn_act_fwd: tcgen05 path needs bf16");
-    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, nullptr, bn, res, relu, to_stream(stream));
+    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, nullptr, bn, res, relu, 0, nullptr, to_stream(stream));
   }
   // generic CUDA-core path: conv, then the eval-mode BN(+residual)(+ReLU) pass in place
   rc = ssb_conv1d_fwd(x, w, y, gin, gout, k, stride, dtype, algo, stream);
   if (rc) return rc;
   return ssb_bn_act_fwd(y, bn, res, nullptr, y, gout, relu, 0, dtype, stream);
+}
+
+int ssb_conv1d_fwd_dual(const void* x, const void* w, void* y_train, void* y_eval, ssb_geom gin, ssb_geom gout, int k,
+                        int stride, int train_samples, double* sums, const ssb_bn* bn_eval, const void* res_eval, int relu,
+                        int dtype, int algo, ssb_stream_t stream) {
+  int rc = check_conv_geom("ssb_conv1d_fwd_dual", gin, gout, k, stride);
+  if (rc) return rc;
+  SSB_REQUIRE(x && w && y_train && y_eval && sums && bn_eval, "ssb_conv1d_fwd_dual: null pointer");
+  SSB_REQUIRE(train_samples > 0 && train_samples < gout.B, "ssb_conv1d_fwd_dual: train_samples %d not inside (0, B=%d)", train_samples, gout.B);
+  if (algo == SSB_ALGO_TCGEN05) {
+    SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_fwd_dual: tcgen05 path needs bf16");
+    return ssb_conv1d_fwd_sm100(x, w, y_train, gin, gout, k, stride, sums, bn_eval, res_eval, relu, train_samples, y_eval,
+                                to_stream(stream));
+  }
+  // generic CUDA-core path: the two row ranges as separate launches (train rows + statistics, eval rows + BN pass)
+  const size_t es = dtype == SSB_BF16 ? 2 : 4;
+  ssb_geom gi_t = gin, go_t = gout, gi_e = gin, go_e = gout;
+  gi_t.B = go_t.B = train_samples;
+  gi_e.B = go_e.B = gout.B - train_samples;
+  const size_t in_off = (size_t)train_samples * gin.pitch * gin.C * es, out_off = (size_t)train_samples * gout.pitch * gout.C * es;
+  rc = ssb_conv1d_fwd_stats(x, w, y_train, gi_t, go_t, k, stride, sums, dtype, algo, stream);
+  if (rc) return rc;
+  return ssb_conv1d_bn_act_fwd((const char*)x + in_off, w, (char*)y_eval + out_off, gi_e, go_e, k, stride, bn_eval,
+                               res_eval ? (const char*)res_eval + out_off : nullptr, relu, dtype, algo, stream);
 }
 
 int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,

@@ -134,6 +134,11 @@ struct TnParams {
   const float* ep_var;
   const bf16* ep_res;   // residual in the output geometry, may be NULL
   int ep_relu;
+  // DUAL (STATS and EPI together): rows < split_row are TRAIN rows (raw output to `out`, statistics), rows >=
+  // split_row are EVAL rows of the same conv (EPI transform, written to out2 with the same row indexing) --
+  // FixMatch's pseudo-label forward rides in the student's launches (same weights, more rows)
+  int split_row;
+  bf16* out2;
 };
 
 // Column sums across the 32 lanes of a warp: every lane holds 32 column values x[0..31] of its own row;
@@ -205,7 +210,9 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
   const long long orow = (long long)p.o_mul * m + p.o_off;
   const bool in_range = m < p.M && orow >= 0 && orow < p.o_rows;
   const bool valid = in_range && row_valid((int)orow, p.o_pitch, p.o_len);
-  bf16* optr = out + (size_t)(in_range ? orow : 0) * p.N + n0;
+  constexpr bool DUAL = STATS && EPI;
+  const bool eval_row = !DUAL || m >= p.split_row;    // this thread's row takes the EPI transform
+  bf16* optr = ((DUAL && eval_row) ? p.out2 : out) + (size_t)(in_range ? orow : 0) * p.N + n0;
   // all MMAs have retired: the operand stages are free, stage 0 of A is reused as reduction scratch
   float* red = scratch;   // [4 warps][2][BN]
 #pragma unroll 1
@@ -221,7 +228,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
         float f[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(r[v * 8 + i]) : 0.f;
-        if (EPI) {
+        if (EPI && eval_row) {
           if (valid) {
             float rs[8];
             if (p.ep_res) {
@@ -236,7 +243,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
               f[i] = p.ep_relu ? fmaxf(o, 0.f) : o;
             }
           }
-        } else if (p.accumulate) {
+        } else if (!EPI && p.accumulate) {
           Vec<bf16> prev;
           prev.raw = dst[v];
           float g[8];
@@ -247,7 +254,14 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
         Vec<bf16> o;
         o.set(f);
         dst[v] = o.raw;
-        if (STATS) o.get(&sv[v * 8]);   // statistics of the values as stored
+        if (STATS) {   // statistics of the values as stored (train rows only)
+          if (DUAL && eval_row) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sv[v * 8 + i] = 0.f;
+          } else {
+            o.get(&sv[v * 8]);
+          }
+        }
       }
     } else if (STATS) {
 #pragma unroll
@@ -639,7 +653,10 @@ template <int BN, bool B_MN>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem_bytes<BN * BK * 2, TN_STAGES>();
   dim3 grid(ceil_div(p.M, BM), p.N / BN);
-  if (p.ep_gamma) {
+  if (p.ep_gamma && p.stats) {
+    if constexpr (B_MN)
+      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  } else if (p.ep_gamma) {
     if constexpr (B_MN)
       ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   } else if (p.stats) {
@@ -656,7 +673,10 @@ template <int BN, bool B_MN>
 int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem3_bytes<BN>();
   dim3 grid(ceil_div(p.M, BM), p.N / BN);
-  if (p.ep_gamma) {
+  if (p.ep_gamma && p.stats) {
+    if constexpr (B_MN)
+      ssb_launch_pro(conv_tn3_kernel<BN, true, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  } else if (p.ep_gamma) {
     if constexpr (B_MN)
       ssb_launch_pro(conv_tn3_kernel<BN, false, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   } else if (p.stats) {
@@ -743,6 +763,7 @@ int ssb_sm100_prepare() {
   SSB_TN_ATTR(128, false, false, false) SSB_TN_ATTR(64, false, false, false) SSB_TN_ATTR(128, false, true, false)
   SSB_TN_ATTR(64, false, true, false) SSB_TN_ATTR(128, true, true, false) SSB_TN_ATTR(64, true, true, false)
   SSB_TN_ATTR(128, false, true, true) SSB_TN_ATTR(64, false, true, true)
+  SSB_TN_ATTR(128, true, true, true) SSB_TN_ATTR(64, true, true, true)
 #undef SSB_TN_ATTR
 #define SSB_TN3_ATTR(BN_, ST_, MN_, EP_)                                                                               \
   if (e == cudaSuccess)                                                                                              \
@@ -751,6 +772,7 @@ int ssb_sm100_prepare() {
   SSB_TN3_ATTR(64, false, true, false) SSB_TN3_ATTR(128, false, true, false) SSB_TN3_ATTR(256, false, true, false)
   SSB_TN3_ATTR(64, true, true, false) SSB_TN3_ATTR(128, true, true, false) SSB_TN3_ATTR(256, true, true, false)
   SSB_TN3_ATTR(64, false, true, true) SSB_TN3_ATTR(128, false, true, true) SSB_TN3_ATTR(256, false, true, true)
+  SSB_TN3_ATTR(64, true, true, true) SSB_TN3_ATTR(128, true, true, true) SSB_TN3_ATTR(256, true, true, true)
 #undef SSB_TN3_ATTR
   if (const char* t3 = getenv("SSB_TN3")) g_tn3 = atoi(t3);
   if (e == cudaSuccess)
@@ -767,7 +789,8 @@ int ssb_sm100_prepare() {
 }
 
 int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
-                         double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, cudaStream_t st) {
+                         double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, int train_samples,
+                         void* y_eval, cudaStream_t st) {
   int rc = check_sm100_shape("ssb_conv1d_fwd", gin, gout);
   if (rc) return rc;
   TnParams p = {};
@@ -784,7 +807,11 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ss
   p.accumulate = 0;
   p.stats = stats;
   if (ep_bn) {
-    SSB_REQUIRE(!stats, "ssb_conv1d_fwd: the statistics epilogue and the eval-mode BN epilogue are exclusive");
+    if (stats) {   // dual mode: the first train_samples samples are train rows, the rest eval rows
+      SSB_REQUIRE(train_samples > 0 && train_samples < gout.B && y_eval, "ssb_conv1d_fwd: dual mode needs 0 < train_samples < B and y_eval");
+      p.split_row = train_samples * gout.pitch;
+      p.out2 = (bf16*)y_eval;
+    }
     p.ep_gamma = ep_bn->gamma;
     p.ep_beta = ep_bn->beta;
     p.ep_mean = ep_bn->running_mean;

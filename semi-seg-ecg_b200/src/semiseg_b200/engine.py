@@ -68,9 +68,16 @@ class StepEngine:
         S = self.Bl + self.Bu
         Cl = self.spec.num_leads
         # static input arena: labeled rows first, strong-aug rows after (replaces torch.cat, fixmatch.py:99)
-        self.x_s = torch.zeros(S, Cl, L, dtype=torch.float32, device=dev)
+        # FixMatch: the weak views sit right behind the student batch, so that the pseudo-label forward is the
+        # tail rows of the student's own conv launches (NetPlan.forward_merged)
+        # (measured: with the multi-branch graph the separate pseudo-label branch overlaps the student forward and
+        # wins, 0.76 vs 0.80 ms; in single-stream mode the merged launches win, 0.89 vs 1.00 ms)
+        self.merged = algorithm == "fixmatch" and bool(int(os.environ.get(
+            "SSB_MERGED_EVAL", "0" if int(os.environ.get("SSB_MULTI_STREAM", "1")) else "1")))
+        self.x_all = torch.zeros(S + max(self.Bu, 1), Cl, L, dtype=torch.float32, device=dev)
+        self.x_s = self.x_all[:S]
         self.y_l = torch.zeros(Bl, L, dtype=torch.int64, device=dev)
-        self.x_uw = torch.zeros(max(self.Bu, 1), Cl, L, dtype=torch.float32, device=dev)
+        self.x_uw = self.x_all[S:]
         # per-step scalars
         self.sp_host = [torch.zeros(64, dtype=torch.uint8).pin_memory() for _ in range(8)]
         self.sp_events = [torch.cuda.Event() for _ in range(8)]
@@ -100,11 +107,16 @@ class StepEngine:
         # exchanged on its own stream as soon as those gradients exist, under the backward of the earlier stages
         self.comm_stream = torch.cuda.Stream(device=dev) if (self.multi_stream and self.collectives and
                                                               int(os.environ.get("SSB_BUCKETS", "1"))) else None
-        self.plan_s = NetPlan(weights, dtype, S, L, True, algo, grads=state.grads, sp_ptr=self.sp_dev.data_ptr(),
-                              wgrad_stream=self.wgrad_stream, state=state)
-        self.plan_t: Optional[NetPlan] = None
+        self.dgrad_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.bufs_snap: Optional[torch.Tensor] = None
-        if self.mode != _lib.LOSS_SUP:
+        if self.merged:
+            # the eval rows must see the running stats from BEFORE this step's update (fixmatch.py:87-93)
+            self.bufs_snap = torch.empty_like(weights.bufs)
+        self.plan_s = NetPlan(weights, dtype, S, L, True, algo, grads=state.grads, sp_ptr=self.sp_dev.data_ptr(),
+                              wgrad_stream=self.wgrad_stream, state=state, dgrad_stream=self.dgrad_stream,
+                              eval_rows=self.Bu if self.merged else 0, eval_bufs=self.bufs_snap)
+        self.plan_t: Optional[NetPlan] = None
+        if self.mode != _lib.LOSS_SUP and not self.merged:
             tw = teacher if algorithm == "mean_teacher" else weights
             if algorithm == "fixmatch" and self.multi_stream:
                 # self-eval pass must see the running stats from BEFORE this step's update (fixmatch.py:87-93)
@@ -194,6 +206,9 @@ class StepEngine:
                 self.plan_t.sh.refresh(st)
         self.plan_s.pre_block_event = repacked
         low_t = None
+        if self.merged:
+            self.bufs_snap.copy_(w.bufs, non_blocking=True)
+            _, low_t = self.plan_s.forward_merged(self.x_all, st)
         if self.plan_t is not None:
             self.plan_t.pre_block_event = repacked
             if self.teacher_stream is not None:
@@ -206,7 +221,8 @@ class StepEngine:
                                             stream=self.teacher_stream)
             else:
                 low_t = self.plan_t.forward(self.x_uw, st, train_mode=False)
-        self.plan_s.forward(self.x_s, st, train_mode=True, zero=False, stream=cur)
+        if not self.merged:
+            self.plan_s.forward(self.x_s, st, train_mode=True, zero=False, stream=cur)
         if self.plan_t is not None and self.teacher_stream is not None:
             torch.cuda.current_stream().wait_stream(self.teacher_stream)
         low_s = self.plan_s.low

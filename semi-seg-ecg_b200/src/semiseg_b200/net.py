@@ -297,13 +297,21 @@ class NetPlan:
 
     def __init__(self, weights: WeightSet, dtype: int, B: int, L: int, train: bool, algo: Optional[int] = None,
                  grads: Optional[torch.Tensor] = None, sp_ptr: int = 0, bufs: Optional[torch.Tensor] = None,
-                 wgrad_stream: Optional[torch.cuda.Stream] = None, state: Optional["TrainState"] = None):
+                 wgrad_stream: Optional[torch.cuda.Stream] = None, state: Optional["TrainState"] = None,
+                 dgrad_stream: Optional[torch.cuda.Stream] = None, eval_rows: int = 0,
+                 eval_bufs: Optional[torch.Tensor] = None):
         _lib.prepare()
         self.w = weights
         self.sh = weights.shadow(dtype)
         self.lay = weights.layout
         self.spec = self.lay.spec
         self.B, self.L, self.train = B, L, train
+        # FixMatch: `eval_rows` extra samples ride behind the B train samples in every activation tensor; they
+        # take the eval-mode (running statistics `eval_bufs`) path of the SAME convs in the same launches
+        self.eval_rows = eval_rows
+        self.Ball = B + eval_rows
+        if eval_rows and (not train or eval_bufs is None):
+            raise ValueError("eval rows ride in a TRAINING plan and need the running-statistics arena they read")
         self.dtype = dtype
         self.device = weights.device
         self.tdt = _torch_dtype(self.dtype)
@@ -313,6 +321,7 @@ class NetPlan:
         self.bufs = bufs if bufs is not None else weights.bufs
         # weight-gradient GEMMs are off the critical path of backward: issue them on a second stream
         self.wgrad_stream = wgrad_stream
+        self.dgrad_stream = dgrad_stream   # branch for the shortcut convs' dgrad (off the main backward chain)
         self._pending_reads: Dict[int, torch.cuda.Event] = {}
         self.drop_mask_ptr = 0   # tests may inject an explicit keep-mask (u8 [B, Lh, Ch])
         self.debug = None        # tests: dict that receives clones of the block-output gradients
@@ -355,7 +364,11 @@ class NetPlan:
         self.Lh = lens[-1]
 
         def act(g: Geom, C_: Optional[int] = None) -> torch.Tensor:
-            return torch.zeros(g.B * g.pitch, C_ or g.C, dtype=self.tdt, device=self.device)
+            return torch.zeros(self.Ball * g.pitch, C_ or g.C, dtype=self.tdt, device=self.device)
+
+        def with_b(g: Geom, b: int) -> Geom:
+            return Geom(b, g.pitch, g.len, g.C)
+        self._with_b = with_b
 
         # ---- BN statistic arenas ----
         if state is not None:   # statistic arenas inside the step's zero arena (TrainState)
@@ -385,12 +398,20 @@ class NetPlan:
             gin = gout
         self.ch = act(self.g_head)
         self.ah = act(self.g_head)
-        self.low = torch.zeros(B, self.Lh, spec.num_classes, dtype=torch.float32, device=self.device)
+        self.low_all = torch.zeros(self.Ball, self.Lh, spec.num_classes, dtype=torch.float32, device=self.device)
+        self.low = self.low_all[:B]
+        self._bn_eval: Dict[str, BN] = {}
+        if eval_rows:
+            for b in self.lay.bns:   # same affine parameters, running statistics from the snapshot arena
+                e = self._make_bn(b)
+                e.running_mean = eval_bufs.data_ptr() + 4 * b.roff
+                e.running_var = eval_bufs.data_ptr() + 4 * (b.roff + b.C)
+                self._bn_eval[b.prefix] = e
 
         # ---- gradient scratch (per geometry) ----
         self._scratch: Dict[Tuple[int, int, int], Dict[str, torch.Tensor]] = {}
         if train:
-            self.dlow = torch.zeros_like(self.low)
+            self.dlow = torch.zeros(B, self.Lh, spec.num_classes, dtype=torch.float32, device=self.device)
             self.dc0 = act(self.g_stem)
             for g in [self.g_pool, self.g_head] + self.g_stage:
                 key = (g.pitch, g.len, g.C)
@@ -537,13 +558,26 @@ class NetPlan:
             self.feat = h
             self._conv_bn_act(lay.head_conv, lay.head_bn, h, self.ah, gin, self.g_head, None, 1, st)
         else:
+            aux = self.wgrad_stream if self.sync_hook is None else None   # idle during the forward
             for bd, bufs in zip(lay.blocks, self.blk_bufs):
                 gout = self.g_stage[bd.stage]
+                side_done = None
+                if bd.convd is not None and aux is not None:
+                    # the 1x1 shortcut conv only needs the block input: own branch, joined before the residual add
+                    fork = torch.cuda.Event()
+                    fork.record()
+                    aux.wait_event(fork)
+                    self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, aux.cuda_stream, bd.bnd)
+                    side_done = torch.cuda.Event()
+                    side_done.record(aux)
                 self._conv_fwd(bd.conv1, h, bufs["c1"], gin, gout, st, bd.bn1)
                 call("ssb_bn_act_fwd", bufs["c1"].data_ptr(), self.bn(bd.bn1), None, None, bufs["a1"].data_ptr(), gout, 1, t, dt, st)
                 self._conv_fwd(bd.conv2, bufs["a1"], bufs["c2"], gout, gout, st, bd.bn2)
                 if bd.convd is not None:
-                    self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st, bd.bnd)
+                    if side_done is not None:
+                        torch.cuda.current_stream().wait_event(side_done)
+                    else:
+                        self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st, bd.bnd)
                     call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), bufs["cd"].data_ptr(), self.bn(bd.bnd),
                          bufs["out"].data_ptr(), gout, 1, t, dt, st)
                 else:
@@ -558,6 +592,63 @@ class NetPlan:
              self.w.params.data_ptr() + 4 * lay.cls_b_off, self.low.data_ptr(), self.g_head, spec.num_classes,
              p, self.drop_mask_ptr or None, self.sp_ptr or None, dt, st)
         return self.low
+
+    def forward_merged(self, x_all: torch.Tensor, st: int):
+        """Train-mode forward of the first B samples and eval-mode forward (running statistics of the snapshot
+        arena) of the remaining `eval_rows` samples of x_all in ONE launch per conv (ssb_conv1d_fwd_dual): the
+        pseudo-label pass of FixMatch (fixmatch.py:87-93) shares the student's weights, so it is just more rows.
+        Returns (low_train [B, Lh, ncls], low_eval [eval_rows, Lh, ncls])."""
+        spec, lay, dt, B, E = self.spec, self.lay, self.dtype, self.B, self.eval_rows
+        assert E > 0 and x_all.dtype == torch.float32 and x_all.is_contiguous() and \
+            tuple(x_all.shape) == (self.Ball, spec.num_leads, self.L)
+        self.x_in = x_all[:B]
+        es = 2 if dt == _lib.BF16 else 4
+        wb = self._with_b
+
+        def tail(buf: torch.Tensor, g: Geom) -> int:      # first eval row of a flat padded tensor
+            return buf.data_ptr() + B * g.pitch * g.C * es
+
+        def dual(c: ConvDesc, b: BNDesc, x, y_train, y_eval, gin, gout, res, relu):
+            call("ssb_conv1d_fwd_dual", x.data_ptr(), self.sh.ptr(c), y_train.data_ptr(), y_eval.data_ptr(), wb(gin, self.Ball),
+                 wb(gout, self.Ball), c.k, c.stride, B, self._bn_structs[b.prefix].sums, C.byref(self._bn_eval[b.prefix]),
+                 res.data_ptr() if res is not None else None, relu, dt, self._algo_for(c), st)
+            if self.sync_hook is not None:
+                self.sync_hook(self.sums[b.soff: b.soff + 2 * b.C])
+
+        call("ssb_stem_conv_fwd", x_all.data_ptr(), self.w.w_ptr(lay.stem_conv), self.c0.data_ptr(), spec.num_leads,
+             self.L, wb(self.g_stem, self.Ball), dt, st)
+        self._stats(self.c0, self.g_stem, lay.stem_bn, st)
+        call("ssb_stem_bn_relu_pool_fwd", self.c0.data_ptr(), self.bn(lay.stem_bn), self.p0.data_ptr(),
+             self.pool_arg.data_ptr(), self.g_stem, self.g_pool, 1, dt, st)
+        call("ssb_stem_bn_relu_pool_fwd", tail(self.c0, self.g_stem), C.byref(self._bn_eval[lay.stem_bn.prefix]),
+             tail(self.p0, self.g_pool), None, wb(self.g_stem, E), wb(self.g_pool, E), 0, dt, st)
+        h, gin = self.p0, self.g_pool
+        if self.pre_block_event is not None:
+            torch.cuda.current_stream().wait_event(self.pre_block_event)
+        for bd, bufs in zip(lay.blocks, self.blk_bufs):
+            gout = self.g_stage[bd.stage]
+            dual(bd.conv1, bd.bn1, h, bufs["c1"], bufs["a1"], gin, gout, None, 1)          # eval rows: a1 = relu(bn1(conv1))
+            if bd.convd is not None:
+                dual(bd.convd, bd.bnd, h, bufs["cd"], bufs["cd"], gin, gout, None, 0)      # eval rows: bnd(convd)
+            call("ssb_bn_act_fwd", bufs["c1"].data_ptr(), self.bn(bd.bn1), None, None, bufs["a1"].data_ptr(), gout, 1, 1, dt, st)
+            res = bufs["cd"] if bd.convd is not None else h
+            dual(bd.conv2, bd.bn2, bufs["a1"], bufs["c2"], bufs["out"], gout, gout, res, 1)  # eval rows: relu(bn2(conv2) + res)
+            if bd.convd is not None:
+                call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), bufs["cd"].data_ptr(), self.bn(bd.bnd),
+                     bufs["out"].data_ptr(), gout, 1, 1, dt, st)
+            else:
+                call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), h.data_ptr(), None,
+                     bufs["out"].data_ptr(), gout, 1, 1, dt, st)
+            h, gin = bufs["out"], gout
+        self.feat = h
+        dual(lay.head_conv, lay.head_bn, h, self.ch, self.ah, gin, self.g_head, None, 1)
+        call("ssb_bn_act_fwd", self.ch.data_ptr(), self.bn(lay.head_bn), None, None, self.ah.data_ptr(), self.g_head, 1, 1, dt, st)
+        wp = self.w.params.data_ptr()
+        call("ssb_head_cls_fwd", self.ah.data_ptr(), wp + 4 * lay.cls_w_off, wp + 4 * lay.cls_b_off, self.low_all.data_ptr(),
+             self.g_head, spec.num_classes, spec.dropout_ratio, self.drop_mask_ptr or None, self.sp_ptr or None, dt, st)
+        call("ssb_head_cls_fwd", tail(self.ah, self.g_head), wp + 4 * lay.cls_w_off, wp + 4 * lay.cls_b_off,
+             self.low_all[B:].data_ptr(), wb(self.g_head, E), spec.num_classes, 0.0, None, None, dt, st)
+        return self.low, self.low_all[B:]
 
     # ---- backward ------------------------------------------------------------------
     def backward(self, dlow: torch.Tensor, st: int) -> None:
@@ -626,6 +717,17 @@ class NetPlan:
                 self.debug[bd.prefix + ".conv2"] = self.to_ncl(dc2, gout)
                 if bd.convd is not None:
                     self.debug[bd.prefix + ".downsample.0"] = self.to_ncl(dcd, gout)
+            side_dgrad = None
+            if bd.convd is not None and self.dgrad_stream is not None:
+                # shortcut dgrad (dcd -> Gin, plain store) on its own branch, under the conv2-dgrad / bn1 chain
+                fork = torch.cuda.Event()
+                fork.record()
+                self.dgrad_stream.wait_event(fork)
+                cdn = bd.convd
+                call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.ptr(cdn), Gin.data_ptr(), gin, gout,
+                     cdn.k, cdn.stride, 0, dt, self._algo_for(cdn), self.dgrad_stream.cuda_stream)
+                side_dgrad = torch.cuda.Event()
+                side_dgrad.record(self.dgrad_stream)
             c = bd.conv2
             self._wgrad(c, bufs["a1"], dc2, gout, gout, st)
             call("ssb_conv1d_dgrad", dc2.data_ptr(), self.sh.ptr(c), da1.data_ptr(), gout, gout,
@@ -645,9 +747,12 @@ class NetPlan:
             self._wgrad(c, xin, dc1, gin, gout, st)
             if bd.convd is not None:
                 self._wgrad(bd.convd, xin, dcd, gin, gout, st)
+            if side_dgrad is not None:
+                torch.cuda.current_stream().wait_event(side_dgrad)   # Gin already holds the shortcut's gradient
+                acc = 1
             call("ssb_conv1d_dgrad", dc1.data_ptr(), self.sh.ptr(c), Gin.data_ptr(), gin, gout,
                  c.k, c.stride, acc, dt, self._algo_for(c), st)
-            if bd.convd is not None:
+            if bd.convd is not None and side_dgrad is None:
                 c = bd.convd
                 call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.ptr(c), Gin.data_ptr(), gin, gout,
                      c.k, c.stride, 1, dt, self._algo_for(c), st)
@@ -666,5 +771,5 @@ class NetPlan:
 
     # ---- test helpers: NCL fp32 copies of internal tensors ---------------------------
     def to_ncl(self, buf: torch.Tensor, g: Geom) -> torch.Tensor:
-        v = buf.view(g.B, g.pitch, -1)[:, 1: 1 + g.len, :]
+        v = buf[: g.B * g.pitch].view(g.B, g.pitch, -1)[:, 1: 1 + g.len, :]
         return v.permute(0, 2, 1).float().contiguous()

@@ -192,6 +192,45 @@ def test_conv_bn_act_eval(cin, cout, k, stride, L, with_res, relu, dtype, algo):
     assert torch.equal(t["rm"], rm0) and torch.equal(t["rv"], rv0) and int(t["nbt"][0]) == 0   # eval mode: buffers untouched
 
 
+@pytest.mark.parametrize("dtype,algo", ALGO_CASES)
+@pytest.mark.parametrize("cin,cout,k,stride,L,with_res", [(64, 64, 3, 1, 157, True), (64, 128, 3, 2, 313, False),
+                                                         (128, 256, 1, 2, 157, False), (256, 256, 3, 1, 79, True),
+                                                         (16, 8, 3, 1, 37, True)])
+def test_conv_fwd_dual(cin, cout, k, stride, L, with_res, dtype, algo):
+    """train rows (raw output + statistics) and eval rows (BN running stats [+ residual] + ReLU) of one conv in one launch"""
+    if algo == _lib.ALGO_TCGEN05 and (cin % 64 or cout % 64):
+        pytest.skip("tcgen05 path needs channel counts that are multiples of 64")
+    torch.manual_seed(cin + cout + k + 1)
+    B, Bt = 5, 3
+    Lo = (L - 1) // stride + 1
+    po = Lo + 2 + 1
+    pi = stride * po
+    x = torch.randn(B, cin, L, device=DEV, dtype=torch.float64)
+    w = torch.randn(cout, cin, k, device=DEV, dtype=torch.float64) / (cin * k) ** 0.5
+    r = torch.randn(B, cout, Lo, device=DEV, dtype=torch.float64)
+    bn, t = make_bn(cout)
+    conv = F.conv1d(rq(x, dtype), rq(w, dtype), None, stride=stride, padding=k // 2)
+    y_eval_ref, _ = ref_bn(conv[Bt:], t, False)
+    if with_res:
+        y_eval_ref = y_eval_ref + rq(r, dtype)[Bt:]
+    y_eval_ref = torch.relu(y_eval_ref)
+    gi, go = Geom(B, pi, L, cin), Geom(B, po, Lo, cout)
+    xb, rb, wt = to_flat(x, pi, dtype), to_flat(r, po, dtype), tap_major(w.float(), dtype)
+    y_tr = torch.full((B * po, cout), 7.0, dtype=TDT[dtype], device=DEV)
+    y_ev = torch.full((B * po, cout), 9.0, dtype=TDT[dtype], device=DEV)
+    sums = torch.zeros(2 * cout, dtype=torch.float64, device=DEV)
+    call("ssb_conv1d_fwd_dual", xb.data_ptr(), wt.data_ptr(), y_tr.data_ptr(), y_ev.data_ptr(), gi, go, k, stride, Bt,
+         sums.data_ptr(), C.byref(bn), rb.data_ptr() if with_res else None, 1, dtype, algo, st())
+    tr = y_tr.view(B, po, cout)
+    ev = y_ev.view(B, po, cout)
+    assert rel_err(from_flat(y_tr, B, po, Lo)[:Bt], conv[:Bt]) < TOL[dtype]
+    assert rel_err(from_flat(y_ev, B, po, Lo)[Bt:], y_eval_ref) < TOL[dtype]
+    assert halo_is_zero(tr[:Bt].reshape(-1, cout), Bt, po, Lo) and halo_is_zero(ev[Bt:].reshape(-1, cout), B - Bt, po, Lo)
+    assert float((tr[Bt:].float() - 7.0).abs().max()) == 0.0 and float((ev[:Bt].float() - 9.0).abs().max()) == 0.0   # other range untouched
+    ys = tr[:Bt].reshape(-1, cout).double()
+    assert rel_err(sums[:cout], ys.sum(0)) < 5e-6 and rel_err(sums[cout:], (ys * ys).sum(0)) < 5e-6
+
+
 @pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
 @pytest.mark.parametrize("Cn,res_mode", [(8, 0), (64, 1), (128, 2), (24, 0)])
 def test_bn_forward_backward(dtype, Cn, res_mode):
