@@ -34,6 +34,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -191,7 +194,8 @@ constexpr int smem_bytes() {
 // ---------------------------------------------------------------------------------------------
 template <int BN, bool STATS, bool EPI>
 __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict__ out, uint32_t tmem_base, uint64_t* done,
-                                          float* ep_scale, float* scratch, int m0, int n0, int warp, int lane) {
+                                          uint32_t done_parity, uint64_t* release, float* ep_scale, float* scratch, int m0,
+                                          int n0, int warp, int lane) {
   // epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
   const int q = warp & 3;
   float* ep_shift = ep_scale + BN;
@@ -203,7 +207,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
-  mbar_wait(done, 0);
+  mbar_wait(done, done_parity);
   tc_fence_after();
   const int row = q * 32 + lane;
   const int m = m0 + row;
@@ -276,6 +280,10 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
       red[(q * 2 + 0) * BN + c + lane] = sv[0];
       red[(q * 2 + 1) * BN + c + lane] = sq[0];
     }
+  }
+  if (release) {   // persistent kernel: this thread is done reading the accumulator buffer
+    tc_fence_before();
+    mbar_arrive(release);
   }
   if (STATS) {
     asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
@@ -366,7 +374,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(s.done);           // accumulator complete
     }
   } else {
-    tn_epilogue<BN, STATS, EPI>(p, out, tmem_base, s.done, reinterpret_cast<float*>(s.tmem_slot + 4),
+    tn_epilogue<BN, STATS, EPI>(p, out, tmem_base, s.done, 0u, nullptr, reinterpret_cast<float*>(s.tmem_slot + 4),
                                 reinterpret_cast<float*>(s.a), m0, n0, warp, lane);
   }
   tc_fence_before();
@@ -386,9 +394,13 @@ constexpr int A3_BYTES = A3_ROWS * 128;   // 17408 = 17 * 1024
 constexpr int A3_SLOTS = 3;
 template <int BN> __host__ __device__ constexpr int b3_slots() { return BN == 256 ? 5 : (BN == 128 ? 8 : 9); }
 template <int BN> constexpr int smem3_bytes() {
-  return A3_SLOTS * A3_BYTES + b3_slots<BN>() * BN * 128 + (2 * A3_SLOTS + 2 * b3_slots<BN>() + 1) * 8 + 16 + 2 * BN * 4 + 1024;
+  return A3_SLOTS * A3_BYTES + b3_slots<BN>() * BN * 128 + (2 * A3_SLOTS + 2 * b3_slots<BN>() + 4) * 8 + 16 + 2 * BN * 4 +
+         8 * BN * 4 + 1024;
 }
 
+// PERSISTENT: gridDim.x CTAs walk the tile list (m fastest, so that CTAs running together share the weight
+// tiles in L2); the accumulator is double-buffered in TMEM (2 x BN columns), so the MMAs of tile i+1 run under
+// the epilogue of tile i; the TMA producer runs ahead across tile boundaries through the same rings.
 template <int BN, bool STATS, bool B_MN, bool EPI>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
@@ -403,46 +415,52 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* a_empty = a_full + A3_SLOTS;
   uint64_t* b_full = a_empty + A3_SLOTS;
   uint64_t* b_empty = b_full + NB;
-  uint64_t* done = b_empty + NB;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-  float* ep_scale = reinterpret_cast<float*>(tmem_slot + 4);
+  uint64_t* t_full = b_empty + NB;      // [2] accumulator buffer complete (MMA -> epilogue)
+  uint64_t* t_empty = t_full + 2;       // [2] accumulator buffer drained (epilogue -> MMA), 128 arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  float* ep_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [2 * BN]
+  float* red = ep_scale + 2 * BN;                               // [4][2][BN] statistics scratch
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < A3_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    mbar_init(done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   const int KC = p.K / BK;
+  const int MT = (p.M + BM - 1) / BM;
+  const int ntiles = MT * (p.N / BN);
 
   if (warp == 0) {
     if (lane == 0) {
-      int bi = 0;
-      for (int kc = 0; kc < KC; ++kc) {
-        const int sl = kc % A3_SLOTS;
-        mbar_wait(&a_empty[sl], (((uint32_t)(kc / A3_SLOTS)) & 1u) ^ 1u);
-        mbar_expect_tx(&a_full[sl], A3_BYTES);
-        tma_load_2d(sa + sl * A3_BYTES, &tmA, &a_full[sl], kc * BK, m0 - 1);   // rows m0-1 .. m0+134 (zero fill outside)
-        for (int tap = 0; tap < 3; ++tap, ++bi) {
-          const int bs = bi % NB;
-          mbar_wait(&b_empty[bs], (((uint32_t)(bi / NB)) & 1u) ^ 1u);
-          mbar_expect_tx(&b_full[bs], B_BYTES);
-          if (B_MN) {
+      int ai = 0, bi = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t % MT) * BM, n0 = (t / MT) * BN;
+        for (int kc = 0; kc < KC; ++kc, ++ai) {
+          const int sl = ai % A3_SLOTS;
+          mbar_wait(&a_empty[sl], (((uint32_t)(ai / A3_SLOTS)) & 1u) ^ 1u);
+          mbar_expect_tx(&a_full[sl], A3_BYTES);
+          tma_load_2d(sa + sl * A3_BYTES, &tmA, &a_full[sl], kc * BK, m0 - 1);   // rows m0-1 .. m0+134 (zero fill outside)
+          for (int tap = 0; tap < 3; ++tap, ++bi) {
+            const int bs = bi % NB;
+            mbar_wait(&b_empty[bs], (((uint32_t)(bi / NB)) & 1u) ^ 1u);
+            mbar_expect_tx(&b_full[bs], B_BYTES);
+            if (B_MN) {
 #pragma unroll
-            for (int b = 0; b < BN / 64; ++b)
-              tma_load_2d(sb + bs * B_BYTES + b * (BK * 128), &tmB, &b_full[bs], n0 + b * 64,
-                          p.w_tap[tap] * p.w_rows_per_tap + kc * BK);
-          } else {
-            tma_load_2d(sb + bs * B_BYTES, &tmB, &b_full[bs], kc * BK, p.w_tap[tap] * p.w_rows_per_tap + n0);
+              for (int b = 0; b < BN / 64; ++b)
+                tma_load_2d(sb + bs * B_BYTES + b * (BK * 128), &tmB, &b_full[bs], n0 + b * 64,
+                            p.w_tap[tap] * p.w_rows_per_tap + kc * BK);
+            } else {
+              tma_load_2d(sb + bs * B_BYTES, &tmB, &b_full[bs], kc * BK, p.w_tap[tap] * p.w_rows_per_tap + n0);
+            }
           }
         }
       }
@@ -450,34 +468,47 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN, false, B_MN);
-      int bi = 0;
-      for (int kc = 0; kc < KC; ++kc) {
-        const int sl = kc % A3_SLOTS;
-        mbar_wait(&a_full[sl], ((uint32_t)(kc / A3_SLOTS)) & 1u);
-        const uint32_t a0 = smem_u32(sa + sl * A3_BYTES);
-        for (int tap = 0; tap < 3; ++tap, ++bi) {
-          const int bs = bi % NB;
-          mbar_wait(&b_full[bs], ((uint32_t)(bi / NB)) & 1u);
-          tc_fence_after();
-          const uint32_t b0 = smem_u32(sb + bs * B_BYTES);
-          const uint32_t at = a0 + (uint32_t)(p.a_row_off[tap] + 1) * 128u;   // tap's row shift inside the haloed tile
+      int ai = 0, bi = 0, it = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&t_empty[buf], (((uint32_t)(it >> 1)) & 1u) ^ 1u);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * BN);
+        for (int kc = 0; kc < KC; ++kc, ++ai) {
+          const int sl = ai % A3_SLOTS;
+          mbar_wait(&a_full[sl], ((uint32_t)(ai / A3_SLOTS)) & 1u);
+          const uint32_t a0 = smem_u32(sa + sl * A3_BYTES);
+          for (int tap = 0; tap < 3; ++tap, ++bi) {
+            const int bs = bi % NB;
+            mbar_wait(&b_full[bs], ((uint32_t)(bi / NB)) & 1u);
+            tc_fence_after();
+            const uint32_t b0 = smem_u32(sb + bs * B_BYTES);
+            const uint32_t at = a0 + (uint32_t)(p.a_row_off[tap] + 1) * 128u;   // tap's row shift inside the haloed tile
 #pragma unroll
-          for (int k4 = 0; k4 < BK / 16; ++k4) {
-            const uint64_t bdesc = B_MN ? make_smem_desc(b0 + k4 * 2048, BK * 128, 1024) : make_smem_desc(b0 + k4 * 32, 0, 1024);
-            umma_bf16(tmem_base, make_smem_desc(at + k4 * 32, 0, 1024), bdesc, idesc, (uint32_t)((kc | tap | k4) != 0));
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              const uint64_t bdesc = B_MN ? make_smem_desc(b0 + k4 * 2048, BK * 128, 1024) : make_smem_desc(b0 + k4 * 32, 0, 1024);
+              umma_bf16(acc, make_smem_desc(at + k4 * 32, 0, 1024), bdesc, idesc, (uint32_t)((kc | tap | k4) != 0));
+            }
+            umma_commit(&b_empty[bs]);
           }
-          umma_commit(&b_empty[bs]);
+          umma_commit(&a_empty[sl]);
         }
-        umma_commit(&a_empty[sl]);
+        umma_commit(&t_full[buf]);
       }
-      umma_commit(done);
     }
   } else {
-    tn_epilogue<BN, STATS, EPI>(p, out, tmem_base, done, ep_scale, reinterpret_cast<float*>(sa), m0, n0, warp, lane);
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int m0 = (t % MT) * BM, n0 = (t / MT) * BN;
+      if (it > 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's scratch / coefficient readers are done
+      tn_epilogue<BN, STATS, EPI>(p, out, tmem_base + (uint32_t)(buf * BN), &t_full[buf], ((uint32_t)(it >> 1)) & 1u,
+                                  &t_empty[buf], ep_scale, red, m0, n0, warp, lane);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+  if (warp == 1) tmem_dealloc<2 * BN>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -669,10 +700,13 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
   return SSB_OK;
 }
 
+int g_num_sms = 148;
+
 template <int BN, bool B_MN>
 int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem3_bytes<BN>();
-  dim3 grid(ceil_div(p.M, BM), p.N / BN);
+  const int ntiles = ceil_div(p.M, BM) * (p.N / BN);
+  dim3 grid(ntiles < g_num_sms ? ntiles : g_num_sms);
   if (p.ep_gamma && p.stats) {
     if constexpr (B_MN)
       ssb_launch_pro(conv_tn3_kernel<BN, true, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
@@ -775,6 +809,11 @@ int ssb_sm100_prepare() {
   SSB_TN3_ATTR(64, true, true, true) SSB_TN3_ATTR(128, true, true, true) SSB_TN3_ATTR(256, true, true, true)
 #undef SSB_TN3_ATTR
   if (const char* t3 = getenv("SSB_TN3")) g_tn3 = atoi(t3);
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      g_num_sms = sms;
+  }
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_wgrad_kernel<128, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_bytes<128 * BK * 2, WG_STAGES>());
