@@ -635,6 +635,139 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
+// wgrad of the stride-1 k=3 convs with TAP FUSION: the three taps' weight gradients are
+//   dW_tap[ci, co] = sum_r X[r + tap - 1][ci] * dY[r][co]
+// i.e. the SAME dY tile against the X tile shifted by one row.  One CTA keeps three accumulators
+// (3 x BN TMEM columns), loads dY once and X once (BK + 2 halo rows, padded to 72) per reduction block
+// and issues the three taps' MMAs with the A descriptor offset by 0/1/2 rows of 128 B (MN-major, the
+// swizzle follows the absolute address as in conv_tn3_kernel).  Operand traffic per FLOP drops ~2.5x.
+// grid = (ci tiles * co tiles, 1, splits)
+// ---------------------------------------------------------------------------------------------
+constexpr int XW_ROWS = BK + 8;                 // 72-row TMA box: rows r0-1 .. r0+70
+constexpr int XW_ATOM = XW_ROWS * 128;          // bytes of one 64-channel atom of the X tile (9 * 1024)
+constexpr int XW_BYTES = 2 * XW_ATOM;           // 128 ci
+constexpr int WG3_STAGES = 4;
+template <int BN> constexpr int smem_wg3_bytes() {
+  return WG3_STAGES * (XW_BYTES + BN * BK * 2) + (2 * WG3_STAGES + 1) * 8 + 16 + 1024;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                   float* __restrict__ dw, const WgParams p) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int STAGES = WG3_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* sa = smem_raw + (((base + 1023u) & ~1023u) - base);
+  uint8_t* sb = sa + STAGES * XW_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sb + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* done = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci0 = (blockIdx.x % p.n_ci_tiles) * BM;
+  const int co0 = (blockIdx.x / p.n_ci_tiles) * BN;
+  const int nblk_total = (p.M + BK - 1) / BK;
+  const int blk0 = blockIdx.z * p.blocks_per_split;
+  const int blk1 = min(nblk_total, blk0 + p.blocks_per_split);
+  const int iters = blk1 - blk0;
+  constexpr int TCOLS = (3 * BN <= 256) ? 256 : 512;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TCOLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int it = 0; it < iters; ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty[st], ph ^ 1u);
+          mbar_expect_tx(&full[st], XW_BYTES + B_BYTES);
+          const int r0 = (blk0 + it) * BK;
+#pragma unroll
+          for (int a = 0; a < BM / 64; ++a)     // X rows r0-1 .. r0+70 of a 64-channel atom (zero fill outside)
+            tma_load_2d(sa + st * XW_BYTES + a * XW_ATOM, &tmX, &full[st], ci0 + a * 64, r0 - 1);
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b)
+            tma_load_2d(sb + st * B_BYTES + b * (BK * 128), &tmDY, &full[st], co0 + b * 64, r0);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc(BN, true, true);
+        for (int it = 0; it < iters; ++it) {
+          const int st = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sa + st * XW_BYTES), b0 = smem_u32(sb + st * B_BYTES);
+#pragma unroll
+          for (int tap = 0; tap < 3; ++tap) {
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              // tap t pairs dY row r with X row r + t - 1 = box row (r - r0) + t
+              umma_bf16(tmem_base + (uint32_t)(tap * BN), make_smem_desc(a0 + tap * 128 + k4 * 2048, XW_ATOM, 1024),
+                        make_smem_desc(b0 + k4 * 2048, BK * 128, 1024), idesc, (uint32_t)((it | k4) != 0));
+            }
+          }
+          umma_commit(&empty[st]);
+        }
+        umma_commit(done);
+      }
+    } else {
+      const int q = warp & 3;
+      mbar_wait(done, 0);
+      tc_fence_after();
+      const int ci = ci0 + q * 32 + lane;
+#pragma unroll 1
+      for (int tap = 0; tap < 3; ++tap) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * BN + c), r);
+          tmem_ld_wait();
+          if (ci >= p.Cin) continue;
+          float* dst = dw + ((size_t)tap * p.Cin + ci) * p.Cout + co0 + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (p.nsplit > 1) {
+              asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j), "f"(__uint_as_float(r[j])),
+                           "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                           : "memory");
+            } else {
+              float4 o = *reinterpret_cast<float4*>(dst + j);
+              o.x += __uint_as_float(r[j]);
+              o.y += __uint_as_float(r[j + 1]);
+              o.z += __uint_as_float(r[j + 2]);
+              o.w += __uint_as_float(r[j + 3]);
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -724,6 +857,7 @@ int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const 
 }
 
 int g_tn3 = 1;   // env SSB_TN3=0 disables the tap-reuse kernel (A/B comparison)
+int g_wg3 = 1;   // env SSB_WG3=0 disables the tap-fused wgrad kernel
 
 // b_mn: the weight matrix of one tap is [K rows][N contiguous] (fprop) instead of [N rows][K contiguous] (dgrad)
 // tap3: stride-1 k=3 conv whose taps are the row shifts -1/0/+1 of the same operand -> tap-reuse kernel
@@ -820,6 +954,11 @@ int ssb_sm100_prepare() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_wgrad_kernel<64, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_bytes<64 * BK * 2, WG_STAGES>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_wgrad3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wg3_bytes<128>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_wgrad3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wg3_bytes<64>());
+  if (const char* w3 = getenv("SSB_WG3")) g_wg3 = atoi(w3);
   if (e != cudaSuccess) {
     ssb_set_error("ssb_sm100_prepare: %s", cudaGetErrorString(e));
     return SSB_ERR_CUDA;
@@ -950,8 +1089,31 @@ int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gi
     }
   }
   const int BN = (gout.C % 128 == 0) ? 128 : 64;
-  const int tiles = p.n_ci_tiles * (gout.C / BN) * k;
   const int nblk = ceil_div(p.M, BK);
+  const int tiles3 = p.n_ci_tiles * (gout.C / BN);
+  // tap-fused kernel: one CTA = (ci tile, co tile), all three taps.  Worth it when, after splitting the reduction
+  // to fill the GPU, a CTA still owns >= 16 reduction blocks (else the extra splits' REDs cost more than the
+  // operand traffic saved: measured at the 16+16 x 2500 shapes, 147 -> 189 us per step)
+  if (stride == 1 && k == 3 && g_wg3 && nblk / ceil_div(g_num_sms, tiles3) >= 16) {
+    int ns = ceil_div(g_num_sms, tiles3);
+    if (ns > nblk / 4) ns = nblk / 4;
+    if (ns < 1) ns = 1;
+    p.blocks_per_split = ceil_div(nblk, ns);
+    p.nsplit = ceil_div(nblk, p.blocks_per_split);
+    CUtensorMap tmX3, tmDY3;
+    rc = make_map(&tmX3, x, x_inner, x_outer, x_pitch, 64, XW_ROWS);
+    if (rc) return rc;
+    rc = make_map(&tmDY3, dy, gout.C, p.M, gout.C, 64, BK);
+    if (rc) return rc;
+    dim3 grid3(tiles3, 1, p.nsplit);
+    if (BN == 128)
+      ssb_launch_pro(conv_wgrad3_kernel<128>, dim3(grid3), dim3(NTHREADS), smem_wg3_bytes<128>(), st, tmX3, tmDY3, dw, p);
+    else
+      ssb_launch_pro(conv_wgrad3_kernel<64>, dim3(grid3), dim3(NTHREADS), smem_wg3_bytes<64>(), st, tmX3, tmDY3, dw, p);
+    SSB_LAUNCH_CHECK("conv_wgrad3_kernel");
+    return SSB_OK;
+  }
+  const int tiles = p.n_ci_tiles * (gout.C / BN) * k;
   int nsplit = ceil_div(148, tiles);
   if (nsplit > nblk / 4) nsplit = nblk / 4;
   if (nsplit < 1) nsplit = 1;
