@@ -260,23 +260,26 @@ __global__ void __launch_bounds__(256) weight_shadow_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------------
 // stem: y[b, t, co] = sum_{c,j} w[co][c][j] * x[b][c][2t + j - 3]
+// Register tiles: a thread owns 8 consecutive positions x 4 output channels (32 accumulators); per (lead, tap) it
+// needs one 16-byte weight load and a sliding 21-sample window of the input that is loaded once per lead.
 // ---------------------------------------------------------------------------------------
-#define ST_TT 64
 #define ST_THREADS 256
+#define ST_PT 8      // positions per thread
 
 template <typename T>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, int Cl, int L,
-                     ssb_geom g) {
+                     ssb_geom g, int tt) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
   const int Cs = g.C;
-  float* ws = sm;                  // [Cl*7][Cs]
-  float* xs = sm + Cl * 7 * Cs;    // [Cl][2*TT+5]
-  const int XW = 2 * ST_TT + 5;
+  const int cog = Cs / 4;                 // channel groups of 4
+  const int XW = 2 * tt + 5;
+  float* ws = sm;                         // [Cl*7][Cs]
+  float* xs = sm + Cl * 7 * Cs;           // [Cl][XW]
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * ST_TT;
+  const int t0 = blockIdx.x * tt;
   const int tid = threadIdx.x;
   for (int idx = tid; idx < Cs * Cl * 7; idx += ST_THREADS) {
     const int co = idx / (Cl * 7), cj = idx % (Cl * 7);
@@ -288,30 +291,33 @@ stem_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T
     xs[idx] = (l >= 0 && l < L) ? x[((size_t)b * Cl + c) * L + l] : 0.f;
   }
   __syncthreads();
-  const int csb = Cs < ST_THREADS ? Cs : ST_THREADS;
-  const int ntl = ST_THREADS / csb;  // t-lanes
-  const int tl = tid / csb;
-  if (tl < ntl) {
-    for (int co = tid % csb; co < Cs; co += csb) {
-      for (int tb = tl * 4; tb < ST_TT; tb += ntl * 4) {
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c = 0; c < Cl; ++c) {
-          float xv[13];
+  const int cg = tid % cog, tg = tid / cog;
+  const int tb = tg * ST_PT;              // first position of this thread inside the tile
+  if (tb < tt) {
+    float acc[ST_PT][4];
 #pragma unroll
-          for (int i = 0; i < 13; ++i) xv[i] = xs[c * XW + 2 * tb + i];
+    for (int u = 0; u < ST_PT; ++u) acc[u][0] = acc[u][1] = acc[u][2] = acc[u][3] = 0.f;
+    for (int c = 0; c < Cl; ++c) {
+      float xv[2 * ST_PT + 5];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            const float wv = ws[(c * 7 + j) * Cs + co];
+      for (int i = 0; i < 2 * ST_PT + 5; ++i) xv[i] = xs[c * XW + 2 * tb + i];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u] = fmaf(wv, xv[2 * u + j], acc[u]);
-          }
-        }
+      for (int j = 0; j < 7; ++j) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[(c * 7 + j) * Cs + cg * 4]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int t = t0 + tb + u;
-          if (t < g.len) y[((size_t)b * g.pitch + 1 + t) * Cs + co] = from_f<T>(acc[u]);
+        for (int u = 0; u < ST_PT; ++u) {
+          const float xx = xv[2 * u + j];
+          acc[u][0] = fmaf(wv.x, xx, acc[u][0]);
+          acc[u][1] = fmaf(wv.y, xx, acc[u][1]);
+          acc[u][2] = fmaf(wv.z, xx, acc[u][2]);
+          acc[u][3] = fmaf(wv.w, xx, acc[u][3]);
         }
       }
+    }
+#pragma unroll
+    for (int u = 0; u < ST_PT; ++u) {
+      const int t = t0 + tb + u;
+      if (t < g.len) store4<T>(y + ((size_t)b * g.pitch + 1 + t) * Cs + cg * 4, acc[u]);
     }
   }
   // halo / pad rows of this sample stay zero
@@ -325,32 +331,41 @@ stem_conv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, T
 }
 
 // dw[co][c][j] += sum_{b,t} dy[b,t,co] * x[b][c][2t+j-3]
-// One CTA per SM walks over (sample, 64-position tile) work items and keeps its partial dw in shared
-// memory (thread o owns outputs o, o+blockDim, ...: no conflicts), so the fp32 atomics into dw are
-// one per output per CTA instead of one per output per tile.
+// One CTA per SM walks over (sample, 64-position tile) work items.  A thread owns 4 output channels x the 7 taps
+// of one lead (28 accumulators, kept in registers across all the tiles the CTA walks) for a slice of the tile's
+// positions; the slices are combined through shared memory at the end: one fp32 atomic per output per CTA.
 #define SW_THREADS 512
+#define SW_TT 64
 template <typename T>
 __global__ void __launch_bounds__(SW_THREADS)
 stem_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int Cl, int L,
-                       ssb_geom g, int ntt) {
+                       ssb_geom g, int ntt, int ts) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];
   const int Cs = g.C;
-  const int XW = 2 * ST_TT + 5;
+  const int cog = Cs / 4;
+  const int XW = 2 * SW_TT + 5;
   const int nout = Cl * 7 * Cs;
-  float* dys = sm;                 // [TT][Cs]
-  float* xs = sm + ST_TT * Cs;     // [Cl][XW]
-  float* acc_s = xs + Cl * XW;     // [nout]
+  float* dys = sm;                   // [TT][Cs]
+  float* xs = sm + SW_TT * Cs;       // [Cl][XW]
+  float* acc_s = xs + Cl * XW;       // [nout]
   const int tid = threadIdx.x;
+  const int nown = cog * Cl;         // (channel group, lead) owners per position slice
+  const int own = tid % nown, sl = tid / nown;
+  const bool active = sl < ts;
+  const int cg = own % cog, c = own / cog;
+  float acc[7][4];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
   for (int o = tid; o < nout; o += SW_THREADS) acc_s[o] = 0.f;
   const int ntiles = ntt * g.B;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int b = tile / ntt;
-    const int t0 = (tile - b * ntt) * ST_TT;
+    const int t0 = (tile - b * ntt) * SW_TT;
     __syncthreads();   // previous tile's readers are done with dys / xs
     constexpr int V = Vec<T>::N;
-    for (int idx = tid; idx < ST_TT * Cs / V; idx += SW_THREADS) {   // 16-byte loads (Cs is a multiple of 8)
+    for (int idx = tid; idx < SW_TT * Cs / V; idx += SW_THREADS) {   // 16-byte loads (Cs is a multiple of 8)
       const int e = idx * V;
       const int t = t0 + e / Cs;
       float f[V];
@@ -366,21 +381,34 @@ stem_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, fl
       for (int i = 0; i < V; ++i) dys[e + i] = f[i];
     }
     for (int idx = tid; idx < Cl * XW; idx += SW_THREADS) {
-      const int c = idx / XW, i = idx % XW;
+      const int cc = idx / XW, i = idx % XW;
       const int l = 2 * t0 - 3 + i;
-      xs[idx] = (l >= 0 && l < L) ? x[((size_t)b * Cl + c) * L + l] : 0.f;
+      xs[idx] = (l >= 0 && l < L) ? x[((size_t)b * Cl + cc) * L + l] : 0.f;
     }
     __syncthreads();
-    for (int o = tid; o < nout; o += SW_THREADS) {
-      const int co = o % Cs, cj = o / Cs;
-      const int c = cj / 7, j = cj % 7;
-      const float* xr = xs + c * XW + j;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int t = 0; t < ST_TT; ++t) acc = fmaf(dys[t * Cs + co], xr[2 * t], acc);
-      acc_s[o] += acc;
+    if (active) {
+      const float* xr = xs + c * XW;
+      for (int t = sl; t < SW_TT; t += ts) {
+        const float4 d = *reinterpret_cast<const float4*>(&dys[t * Cs + cg * 4]);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const float xx = xr[2 * t + j];
+          acc[j][0] = fmaf(d.x, xx, acc[j][0]);
+          acc[j][1] = fmaf(d.y, xx, acc[j][1]);
+          acc[j][2] = fmaf(d.z, xx, acc[j][2]);
+          acc[j][3] = fmaf(d.w, xx, acc[j][3]);
+        }
+      }
     }
   }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(&acc_s[(c * 7 + j) * Cs + cg * 4 + i], acc[j][i]);   // shared-memory combine of the slices
+  }
+  __syncthreads();
   for (int o = tid; o < nout; o += SW_THREADS) {
     const int co = o % Cs, cj = o / Cs;
     atomicAdd(&dw[(size_t)co * Cl * 7 + cj], acc_s[o]);
@@ -621,11 +649,16 @@ int ssb_stem_conv_fwd(const float* x, const float* w, void* y, int Cl, int L, ss
   int rc = check_stem("ssb_stem_conv_fwd", Cl, L, g);
   if (rc) return rc;
   SSB_REQUIRE(x && w && y, "ssb_stem_conv_fwd: null pointer");
-  const size_t smem = ((size_t)Cl * 7 * g.C + (size_t)Cl * (2 * ST_TT + 5)) * sizeof(float);
+  // tile of positions per block: every thread owns ST_PT positions x 4 channels
+  const int cog = g.C / 4;
+  int tt = (ST_THREADS / cog) * ST_PT;
+  if (tt < ST_PT) tt = ST_PT;
+  const size_t smem = ((size_t)Cl * 7 * g.C + (size_t)Cl * (2 * tt + 5)) * sizeof(float);
+  SSB_REQUIRE(cog <= ST_THREADS, "ssb_stem_conv_fwd: stem channels %d too wide", g.C);
   SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_fwd: num_leads x stem_channels too large (%zu B of shared memory)", smem);
-  dim3 grid(ceil_div(g.len, ST_TT), g.B);
+  dim3 grid(ceil_div(g.len, tt), g.B);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    ssb_launch(stem_conv_fwd_kernel<T>, dim3(grid), dim3(ST_THREADS), smem, to_stream(stream), x, w, (T*)y, Cl, L, g);
+    ssb_launch(stem_conv_fwd_kernel<T>, dim3(grid), dim3(ST_THREADS), smem, to_stream(stream), x, w, (T*)y, Cl, L, g, tt);
   })
   SSB_LAUNCH_CHECK("ssb_stem_conv_fwd");
   return SSB_OK;
@@ -636,13 +669,17 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
   int rc = check_stem("ssb_stem_conv_wgrad", Cl, L, g);
   if (rc) return rc;
   SSB_REQUIRE(x && dy && dw, "ssb_stem_conv_wgrad: null pointer");
-  const size_t smem = ((size_t)ST_TT * g.C + (size_t)Cl * (2 * ST_TT + 5) + (size_t)Cl * 7 * g.C) * sizeof(float);
+  const size_t smem = ((size_t)SW_TT * g.C + (size_t)Cl * (2 * SW_TT + 5) + (size_t)Cl * 7 * g.C) * sizeof(float);
   SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_wgrad: num_leads x stem_channels too large (%zu B of shared memory)", smem);
-  const int ntt = ceil_div(g.len, ST_TT);
+  const int nown = (g.C / 4) * Cl;    // (4-channel group, lead) owners; the rest of the block slices the positions
+  SSB_REQUIRE(nown <= SW_THREADS, "ssb_stem_conv_wgrad: num_leads x stem_channels / 4 = %d exceeds the block", nown);
+  int ts = SW_THREADS / nown;
+  if (ts > SW_TT) ts = SW_TT;
+  const int ntt = ceil_div(g.len, SW_TT);
   const int ntiles = ntt * g.B;
   dim3 grid(ntiles < 148 ? ntiles : 148);
   SSB_DISPATCH_DTYPE(dtype, T, {
-    ssb_launch(stem_conv_wgrad_kernel<T>, dim3(grid), dim3(SW_THREADS), smem, to_stream(stream), x, (const T*)dy, dw, Cl, L, g, ntt);
+    ssb_launch(stem_conv_wgrad_kernel<T>, dim3(grid), dim3(SW_THREADS), smem, to_stream(stream), x, (const T*)dy, dw, Cl, L, g, ntt, ts);
   })
   SSB_LAUNCH_CHECK("ssb_stem_conv_wgrad");
   return SSB_OK;
