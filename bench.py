@@ -92,9 +92,10 @@ def launch_cost(name, args, es):
     """(flops, bytes) of one C-ABI launch from its arguments; es = activation element size."""
     from semiseg_b200._lib import Geom
     geoms = [a for a in args if isinstance(a, Geom)]
-    if name in ("ssb_conv1d_fwd", "ssb_conv1d_fwd_stats", "ssb_conv1d_bn_act_fwd", "ssb_conv1d_dgrad", "ssb_conv1d_wgrad"):
+    if name in ("ssb_conv1d_fwd", "ssb_conv1d_fwd_stats", "ssb_conv1d_bn_act_fwd", "ssb_conv1d_dgrad", "ssb_conv1d_wgrad",
+                "ssb_conv1d_dgrad_bnred", "ssb_conv1d_fwd_dual"):
         gi, go = geoms
-        k = args[5]
+        k = args[6] if name == "ssb_conv1d_fwd_dual" else args[5]
         flops = 2.0 * go.B * go.len * go.C * gi.C * k
         w = gi.C * go.C * k
         if name == "ssb_conv1d_wgrad":

@@ -169,6 +169,15 @@ int ssb_conv1d_fwd_dual(const void* x, const void* w, void* y_train, void* y_eva
 /* dx = conv_transpose(dy, w) (+ dx if accumulate) */
 int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout,
                      int k, int stride, int accumulate, int dtype, int algo, ssb_stream_t stream);
+/* dgrad with the BatchNorm-backward REDUCE pass of the gradient it produces fused into the epilogue
+ * (stride-1 convs): with g = dx * (y_act > 0) (dx as stored, after the optional accumulate),
+ * bn->bwd_sums += (sum g, sum g*xhat(x_pre)); x_res/bn_res: the same for the residual-branch BN.
+ * y_act / x_pre / x_res are tensors in the geometry of dx (gin).  Equivalent to ssb_conv1d_dgrad followed
+ * by ssb_bn_bwd_reduce(dx, NULL, y_act, x_pre, bn, x_res, bn_res, gin). */
+int ssb_conv1d_dgrad_bnred(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout,
+                           int k, int stride, int accumulate, const void* y_act, const void* x_pre,
+                           const ssb_bn* bn, const void* x_res, const ssb_bn* bn_res, int dtype,
+                           int algo, ssb_stream_t stream);
 /* dw[k][Cin][Cout] (fp32, tap-major like w) += x^T dy; the caller zeroes dw once per step */
 int ssb_conv1d_wgrad(const void* x, const void* dy, float* dw,
                      ssb_geom gin, ssb_geom gout, int k, int stride,

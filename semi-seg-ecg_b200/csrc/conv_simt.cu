@@ -452,7 +452,8 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ss
                          double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, int train_samples,
                          void* y_eval, cudaStream_t st);
 int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
-                           int accumulate, cudaStream_t st);
+                           int accumulate, const void* red_y, const void* red_x, const ssb_bn* red_bn, const void* red_xr,
+                           const ssb_bn* red_bn_r, cudaStream_t st);
 int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
                            cudaStream_t st);
 
@@ -548,7 +549,8 @@ int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_
   SSB_REQUIRE(dy && dx && w, "ssb_conv1d_dgrad: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_dgrad: tcgen05 path needs bf16");
-    return ssb_conv1d_dgrad_sm100(dy, w, dx, gin, gout, k, stride, accumulate, to_stream(stream));
+    return ssb_conv1d_dgrad_sm100(dy, w, dx, gin, gout, k, stride, accumulate, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                  to_stream(stream));
   }
   cudaStream_t st = to_stream(stream);
   const int rows_in = gin.B * gin.pitch, rows_out = gout.B * gout.pitch;
@@ -594,6 +596,24 @@ int ssb_conv1d_dgrad(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_
     }
   })
   return SSB_OK;
+}
+
+int ssb_conv1d_dgrad_bnred(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
+                           int accumulate, const void* y_act, const void* x_pre, const ssb_bn* bn, const void* x_res,
+                           const ssb_bn* bn_res, int dtype, int algo, ssb_stream_t stream) {
+  int rc = check_conv_geom("ssb_conv1d_dgrad_bnred", gin, gout, k, stride);
+  if (rc) return rc;
+  SSB_REQUIRE(dy && dx && w && y_act && x_pre && bn, "ssb_conv1d_dgrad_bnred: null pointer");
+  SSB_REQUIRE((x_res != nullptr) == (bn_res != nullptr), "ssb_conv1d_dgrad_bnred: x_res and bn_res go together");
+  SSB_REQUIRE(stride == 1, "ssb_conv1d_dgrad_bnred: stride-1 convs only (a stride-2 dgrad writes dx in two launches)");
+  if (algo == SSB_ALGO_TCGEN05) {
+    SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_dgrad_bnred: tcgen05 path needs bf16");
+    return ssb_conv1d_dgrad_sm100(dy, w, dx, gin, gout, k, stride, accumulate, y_act, x_pre, bn, x_res, bn_res, to_stream(stream));
+  }
+  // generic CUDA-core path: dgrad, then the reduce pass as its own launch
+  rc = ssb_conv1d_dgrad(dy, w, dx, gin, gout, k, stride, accumulate, dtype, algo, stream);
+  if (rc) return rc;
+  return ssb_bn_bwd_reduce(dx, nullptr, y_act, x_pre, bn, x_res, bn_res, gin, dtype, stream);
 }
 
 int ssb_conv1d_wgrad(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,

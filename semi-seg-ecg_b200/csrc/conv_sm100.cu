@@ -142,6 +142,15 @@ struct TnParams {
   // FixMatch's pseudo-label forward rides in the student's launches (same weights, more rows)
   int split_row;
   bf16* out2;
+  // RED epilogue (dgrad): BatchNorm-backward reduce of the gradient this launch produces, g = dx * (red_y > 0):
+  // red_sums[0:N] += sum g, red_sums[N:2N] += sum g * xhat(red_x); RED == 2 also the residual-branch BN (red_xr)
+  const bf16* red_y;
+  const bf16* red_x;
+  const bf16* red_xr;
+  const float* red_mi;      // [2N] mean / invstd saved by the forward
+  const float* red_mi_r;
+  double* red_sums;
+  double* red_sums_r;
 };
 
 // Column sums across the 32 lanes of a warp: every lane holds 32 column values x[0..31] of its own row;
@@ -183,7 +192,7 @@ __device__ __forceinline__ SmemLayout carve(uint8_t* raw) {
 }
 template <int B_BYTES, int STAGES>
 constexpr int smem_bytes() {
-  return STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024 + 2 * 128 * 4;   // + per-column scale/shift (EPI)
+  return STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024 + 4 * 128 * 4;   // + per-column coefficients (EPI / RED)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -192,7 +201,7 @@ constexpr int smem_bytes() {
 // Called by the four epilogue warps (threads 64..191); `scratch` is operand smem that is free once
 // `done` has fired, `ep_scale` a dedicated [2*BN] float area.
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool STATS, bool EPI>
+template <int BN, bool STATS, bool EPI, int RED = 0>
 __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict__ out, uint32_t tmem_base, uint64_t* done,
                                           uint32_t done_parity, uint64_t* release, float* ep_scale, float* scratch, int m0,
                                           int n0, int warp, int lane) {
@@ -204,6 +213,17 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
       const float sc = p.ep_gamma[n0 + col] * (1.0f / sqrtf(p.ep_var[n0 + col] + 1e-5f));
       ep_scale[col] = sc;
       ep_shift[col] = p.ep_beta[n0 + col] - p.ep_mean[n0 + col] * sc;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
+  if (RED) {   // saved mean / invstd of this CTA's columns (ep_scale area: mean, inv, [mean_r, inv_r])
+    for (int col = q * 32 + lane; col < BN; col += 128) {
+      ep_scale[col] = p.red_mi[n0 + col];
+      ep_scale[BN + col] = p.red_mi[p.N + n0 + col];
+      if (RED == 2) {
+        ep_scale[2 * BN + col] = p.red_mi_r[n0 + col];
+        ep_scale[3 * BN + col] = p.red_mi_r[p.N + n0 + col];
+      }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
   }
@@ -258,6 +278,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
         Vec<bf16> o;
         o.set(f);
         dst[v] = o.raw;
+        if (RED) o.get(&sv[v * 8]);   // the gradient as stored
         if (STATS) {   // statistics of the values as stored (train rows only)
           if (DUAL && eval_row) {
 #pragma unroll
@@ -267,9 +288,78 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
           }
         }
       }
-    } else if (STATS) {
+    } else if (STATS || RED) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) sv[i] = 0.f;
+    }
+    if (RED) {
+      // g = dx * (y > 0); per-column sums of g and g * xhat over this tile's rows, 32 columns at a time:
+      // warp transpose-reduce -> 4 warps combined through a small scratch -> fp64 atomics
+      const size_t roff = (size_t)(in_range ? orow : 0) * p.N + n0 + c;
+      float t[32];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float fy[8];
+        if (valid) {
+          Vec<bf16> vy;
+          vy.raw = *reinterpret_cast<const uint4*>(p.red_y + roff + v * 8);
+          vy.get(fy);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sv[v * 8 + i] = (valid && fy[i] > 0.f) ? sv[v * 8 + i] : 0.f;
+          t[v * 8 + i] = sv[v * 8 + i];
+        }
+      }
+      warp_transpose_sum(t, lane);
+      red[(q * 3 + 0) * 32 + lane] = t[0];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float fx[8];
+        if (valid) {
+          Vec<bf16> vx;
+          vx.raw = *reinterpret_cast<const uint4*>(p.red_x + roff + v * 8);
+          vx.get(fx);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          t[v * 8 + i] = valid ? sv[v * 8 + i] * ((fx[i] - ep_scale[c + v * 8 + i]) * ep_scale[BN + c + v * 8 + i]) : 0.f;
+      }
+      warp_transpose_sum(t, lane);
+      red[(q * 3 + 1) * 32 + lane] = t[0];
+      if (RED == 2) {
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float fx[8];
+          if (valid) {
+            Vec<bf16> vx;
+            vx.raw = *reinterpret_cast<const uint4*>(p.red_xr + roff + v * 8);
+            vx.get(fx);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            t[v * 8 + i] = valid ? sv[v * 8 + i] * ((fx[i] - ep_scale[2 * BN + c + v * 8 + i]) * ep_scale[3 * BN + c + v * 8 + i]) : 0.f;
+        }
+        warp_transpose_sum(t, lane);
+        red[(q * 3 + 2) * 32 + lane] = t[0];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = q * 32 + lane;
+      if (e < 32 * (RED == 2 ? 3 : 2)) {
+        const int which = e >> 5, col = e & 31;
+        const float a = (red[(0 * 3 + which) * 32 + col] + red[(1 * 3 + which) * 32 + col]) +
+                        (red[(2 * 3 + which) * 32 + col] + red[(3 * 3 + which) * 32 + col]);
+        const int gc = n0 + c + col;
+        if (which == 0) {
+          atomicAdd(&p.red_sums[gc], (double)a);
+          if (RED == 2) atomicAdd(&p.red_sums_r[gc], (double)a);
+        } else if (which == 1) {
+          atomicAdd(&p.red_sums[p.N + gc], (double)a);
+        } else {
+          atomicAdd(&p.red_sums_r[p.N + gc], (double)a);
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     if (STATS) {
       float sq[32];
@@ -304,7 +394,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
 // ---------------------------------------------------------------------------------------------
 // fprop / dgrad
 // ---------------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool STATS, bool B_MN, bool EPI>
+template <int BN, int STAGES, bool STATS, bool B_MN, bool EPI, int RED = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
                const TnParams p) {
@@ -374,7 +464,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(s.done);           // accumulator complete
     }
   } else {
-    tn_epilogue<BN, STATS, EPI>(p, out, tmem_base, s.done, 0u, nullptr, reinterpret_cast<float*>(s.tmem_slot + 4),
+    tn_epilogue<BN, STATS, EPI, RED>(p, out, tmem_base, s.done, 0u, nullptr, reinterpret_cast<float*>(s.tmem_slot + 4),
                                 reinterpret_cast<float*>(s.a), m0, n0, warp, lane);
   }
   tc_fence_before();
@@ -394,14 +484,14 @@ constexpr int A3_BYTES = A3_ROWS * 128;   // 17408 = 17 * 1024
 constexpr int A3_SLOTS = 3;
 template <int BN> __host__ __device__ constexpr int b3_slots() { return BN == 256 ? 5 : (BN == 128 ? 8 : 9); }
 template <int BN> constexpr int smem3_bytes() {
-  return A3_SLOTS * A3_BYTES + b3_slots<BN>() * BN * 128 + (2 * A3_SLOTS + 2 * b3_slots<BN>() + 4) * 8 + 16 + 2 * BN * 4 +
+  return A3_SLOTS * A3_BYTES + b3_slots<BN>() * BN * 128 + (2 * A3_SLOTS + 2 * b3_slots<BN>() + 4) * 8 + 16 + 4 * BN * 4 +
          8 * BN * 4 + 1024;
 }
 
 // PERSISTENT: gridDim.x CTAs walk the tile list (m fastest, so that CTAs running together share the weight
 // tiles in L2); the accumulator is double-buffered in TMEM (2 x BN columns), so the MMAs of tile i+1 run under
 // the epilogue of tile i; the TMA producer runs ahead across tile boundaries through the same rings.
-template <int BN, bool STATS, bool B_MN, bool EPI>
+template <int BN, bool STATS, bool B_MN, bool EPI, int RED = 0>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
                 const TnParams p) {
@@ -418,8 +508,8 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* t_full = b_empty + NB;      // [2] accumulator buffer complete (MMA -> epilogue)
   uint64_t* t_empty = t_full + 2;       // [2] accumulator buffer drained (epilogue -> MMA), 128 arrivals
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
-  float* ep_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [2 * BN]
-  float* red = ep_scale + 2 * BN;                               // [4][2][BN] statistics scratch
+  float* ep_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [4 * BN] per-column coefficients
+  float* red = ep_scale + 4 * BN;                               // [4][2][BN] statistics scratch
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -502,7 +592,7 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int buf = it & 1;
       const int m0 = (t % MT) * BM, n0 = (t / MT) * BN;
       if (it > 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's scratch / coefficient readers are done
-      tn_epilogue<BN, STATS, EPI>(p, out, tmem_base + (uint32_t)(buf * BN), &t_full[buf], ((uint32_t)(it >> 1)) & 1u,
+      tn_epilogue<BN, STATS, EPI, RED>(p, out, tmem_base + (uint32_t)(buf * BN), &t_full[buf], ((uint32_t)(it >> 1)) & 1u,
                                   &t_empty[buf], ep_scale, red, m0, n0, warp, lane);
     }
   }
@@ -826,6 +916,13 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
   } else if (p.stats) {
     if constexpr (B_MN)
       ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  } else if (p.red_sums) {
+    if constexpr (!B_MN) {
+      if (p.red_xr)
+        ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, false, false, 2>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+      else
+        ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, false, false, 1>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+    }
   } else {
     ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, B_MN, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   }
@@ -849,6 +946,13 @@ int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const 
   } else if (p.stats) {
     if constexpr (B_MN)
       ssb_launch_pro(conv_tn3_kernel<BN, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+  } else if (p.red_sums) {
+    if constexpr (!B_MN) {
+      if (p.red_xr)
+        ssb_launch_pro(conv_tn3_kernel<BN, false, false, false, 2>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+      else
+        ssb_launch_pro(conv_tn3_kernel<BN, false, false, false, 1>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+    }
   } else {
     ssb_launch_pro(conv_tn3_kernel<BN, false, B_MN, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   }
@@ -933,6 +1037,12 @@ int ssb_sm100_prepare() {
   SSB_TN_ATTR(128, false, true, true) SSB_TN_ATTR(64, false, true, true)
   SSB_TN_ATTR(128, true, true, true) SSB_TN_ATTR(64, true, true, true)
 #undef SSB_TN_ATTR
+#define SSB_TNR_ATTR(BN_, R_)                                                                                               \
+  if (e == cudaSuccess)                                                                                                     \
+    e = cudaFuncSetAttribute(conv_tn_kernel<BN_, TN_STAGES, false, false, false, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             smem_bytes<BN_ * BK * 2, TN_STAGES>());
+  SSB_TNR_ATTR(128, 1) SSB_TNR_ATTR(64, 1) SSB_TNR_ATTR(128, 2) SSB_TNR_ATTR(64, 2)
+#undef SSB_TNR_ATTR
 #define SSB_TN3_ATTR(BN_, ST_, MN_, EP_)                                                                               \
   if (e == cudaSuccess)                                                                                              \
     e = cudaFuncSetAttribute(conv_tn3_kernel<BN_, ST_, MN_, EP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3_bytes<BN_>());
@@ -942,6 +1052,11 @@ int ssb_sm100_prepare() {
   SSB_TN3_ATTR(64, false, true, true) SSB_TN3_ATTR(128, false, true, true) SSB_TN3_ATTR(256, false, true, true)
   SSB_TN3_ATTR(64, true, true, true) SSB_TN3_ATTR(128, true, true, true) SSB_TN3_ATTR(256, true, true, true)
 #undef SSB_TN3_ATTR
+#define SSB_TN3R_ATTR(BN_, R_)                                                                                        \
+  if (e == cudaSuccess)                                                                                               \
+    e = cudaFuncSetAttribute(conv_tn3_kernel<BN_, false, false, false, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3_bytes<BN_>());
+  SSB_TN3R_ATTR(64, 1) SSB_TN3R_ATTR(128, 1) SSB_TN3R_ATTR(256, 1) SSB_TN3R_ATTR(64, 2) SSB_TN3R_ATTR(128, 2) SSB_TN3R_ATTR(256, 2)
+#undef SSB_TN3R_ATTR
   if (const char* t3 = getenv("SSB_TN3")) g_tn3 = atoi(t3);
   {
     int dev = 0, sms = 0;
@@ -1017,7 +1132,8 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ss
 }
 
 int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
-                           int accumulate, cudaStream_t st) {
+                           int accumulate, const void* red_y, const void* red_x, const ssb_bn* red_bn, const void* red_xr,
+                           const ssb_bn* red_bn_r, cudaStream_t st) {
   int rc = check_sm100_shape("ssb_conv1d_dgrad", gin, gout);
   if (rc) return rc;
   const int rows_in = gin.B * gin.pitch, rows_out = gout.B * gout.pitch;
@@ -1029,6 +1145,18 @@ int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin
   p.o_pitch = gin.pitch;
   p.o_len = gin.len;
   p.accumulate = accumulate;
+  if (red_bn) {
+    SSB_REQUIRE(stride == 1, "ssb_conv1d_dgrad: the fused BN-backward reduce needs a stride-1 conv (one launch writes dx)");
+    p.red_y = (const bf16*)red_y;
+    p.red_x = (const bf16*)red_x;
+    p.red_mi = red_bn->mean_invstd;
+    p.red_sums = red_bn->bwd_sums;
+    if (red_bn_r) {
+      p.red_xr = (const bf16*)red_xr;
+      p.red_mi_r = red_bn_r->mean_invstd;
+      p.red_sums_r = red_bn_r->bwd_sums;
+    }
+  }
   if (stride == 1) {
     p.M = rows_in;
     p.ntaps = k;

@@ -70,6 +70,7 @@ SIGNATURES = {
     "ssb_conv1d_bn_act_fwd": [_P, _P, _P, Geom, Geom, _I, _I, _BNP, _P, _I, _I, _I, _P],
     "ssb_conv1d_fwd_dual": [_P, _P, _P, _P, Geom, Geom, _I, _I, _I, _P, _BNP, _P, _I, _I, _I, _P],
     "ssb_conv1d_dgrad": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _I, _P],
+    "ssb_conv1d_dgrad_bnred": [_P, _P, _P, Geom, Geom, _I, _I, _I, _P, _P, _BNP, _P, _BNP, _I, _I, _P],
     "ssb_conv1d_wgrad": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
     "ssb_weight_shadow": [_P, _P, _SZ, _I, _P],
     "ssb_bn_stats": [_P, Geom, _P, _I, _P],

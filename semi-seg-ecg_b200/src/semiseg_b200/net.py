@@ -327,6 +327,10 @@ class NetPlan:
         self.debug = None        # tests: dict that receives clones of the block-output gradients
         self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
         self.pre_block_event = None   # event the stream waits on after the stem (storage-dtype weight copy ready)
+        # BN-backward reduce in the dgrad epilogue (ssb_conv1d_dgrad_bnred): 13 launches fewer per step, but measured
+        # SLOWER (0.779 vs 0.765 ms at 16+16 x 2500; conv family +37 % at width 128): the extra loads, transposes and
+        # per-chunk barriers sit on the epilogue, which is already the long pole of these tiles.  Off by default.
+        self.fuse_reduce = bool(int(os.environ.get("SSB_FUSE_REDUCE", "0")))
         self.block_done_hook = None   # callable(block_index) after a block's backward has been enqueued (bucketed all-reduce)
         if algo is None:
             algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
@@ -650,6 +654,28 @@ class NetPlan:
              self.low_all[B:].data_ptr(), wb(self.g_head, E), spec.num_classes, 0.0, None, None, dt, st)
         return self.low, self.low_all[B:]
 
+    def _dgrad(self, c: ConvDesc, dy, dx, gin: Geom, gout: Geom, acc: int, st: int, red=None):
+        """dx (+)= conv_transpose(dy, w).  red = (y_act, x_pre, bn[, x_res, bn_res]): the BatchNorm-backward reduce of the
+        gradient being produced rides in the epilogue (stride-1 convs), replacing a separate reduce launch."""
+        if red is None or c.stride != 1:
+            call("ssb_conv1d_dgrad", dy.data_ptr(), self.sh.ptr(c), dx.data_ptr(), gin, gout, c.k, c.stride, acc, self.dtype,
+                 self._algo_for(c), st)
+            return False
+        y_act, x_pre, b = red[0], red[1], red[2]
+        x_res = red[3] if len(red) > 3 else None
+        b_res = red[4] if len(red) > 3 else None
+        call("ssb_conv1d_dgrad_bnred", dy.data_ptr(), self.sh.ptr(c), dx.data_ptr(), gin, gout, c.k, c.stride, acc,
+             y_act.data_ptr(), x_pre.data_ptr(), self.bn(b), x_res.data_ptr() if x_res is not None else None,
+             self.bn(b_res) if b_res is not None else None, self.dtype, self._algo_for(c), st)
+        return True
+
+    def _bn2_red(self, bi: int):
+        """reduce arguments of block bi's output BN (bn2 [+ downsample BN]) for the dgrad that produces its gradient"""
+        bd, bufs = self.lay.blocks[bi], self.blk_bufs[bi]
+        if bd.convd is not None:
+            return (bufs["out"], bufs["c2"], bd.bn2, bufs["cd"], bd.bnd)
+        return (bufs["out"], bufs["c2"], bd.bn2)
+
     # ---- backward ------------------------------------------------------------------
     def backward(self, dlow: torch.Tensor, st: int) -> None:
         """dlow: gradient w.r.t. the low-res logits [B, Lh, ncls] fp32.  Accumulates weight
@@ -675,8 +701,8 @@ class NetPlan:
         G = sc_f["gA"]
         # (the weight-gradient GEMM only needs dy: fork it BEFORE the dgrad so that the two run side by side)
         self._wgrad(hc, self.feat, sc_h["gB"], gfeat, self.g_head, st)
-        call("ssb_conv1d_dgrad", sc_h["gB"].data_ptr(), self.sh.ptr(hc), G.data_ptr(), gfeat,
-             self.g_head, hc.k, hc.stride, 0, dt, self._algo_for(hc), st)
+        fuse = self.fuse_reduce
+        pre_reduced = self._dgrad(hc, sc_h["gB"], G, gfeat, self.g_head, 0, st, self._bn2_red(len(lay.blocks) - 1) if fuse else None)
 
         # blocks in reverse
         nblk = len(lay.blocks)
@@ -702,14 +728,16 @@ class NetPlan:
             self._before_write(dc2, dcd)
             if bd.convd is not None:
                 cd = bufs["cd"]
-                call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
-                     cd.data_ptr(), self.bn(bd.bnd), gout, dt, st)
+                if not pre_reduced:
+                    call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
+                         cd.data_ptr(), self.bn(bd.bnd), gout, dt, st)
                 self._sync_bwd(bd.bn2, bd.bnd)
                 call("ssb_bn_bwd_apply", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
                      dc2.data_ptr(), cd.data_ptr(), self.bn(bd.bnd), dcd.data_ptr(), None, gout, dt, st)
             else:
-                call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
-                     None, None, gout, dt, st)
+                if not pre_reduced:
+                    call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
+                         None, None, gout, dt, st)
                 self._sync_bwd(bd.bn2)
                 call("ssb_bn_bwd_apply", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
                      dc2.data_ptr(), None, None, None, Gin.data_ptr(), gout, dt, st)
@@ -730,13 +758,13 @@ class NetPlan:
                 side_dgrad.record(self.dgrad_stream)
             c = bd.conv2
             self._wgrad(c, bufs["a1"], dc2, gout, gout, st)
-            call("ssb_conv1d_dgrad", dc2.data_ptr(), self.sh.ptr(c), da1.data_ptr(), gout, gout,
-                 c.k, c.stride, 0, dt, self._algo_for(c), st)
+            red1 = self._dgrad(c, dc2, da1, gout, gout, 0, st, (bufs["a1"], bufs["c1"], bd.bn1) if fuse else None)
             # bn1 + relu backward -> dc1
             dc1 = bg["dc1"]
             self._before_write(dc1)
-            call("ssb_bn_bwd_reduce", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
-                 None, None, gout, dt, st)
+            if not red1:
+                call("ssb_bn_bwd_reduce", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
+                     None, None, gout, dt, st)
             self._sync_bwd(bd.bn1)
             call("ssb_bn_bwd_apply", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
                  dc1.data_ptr(), None, None, None, None, gout, dt, st)
@@ -750,8 +778,9 @@ class NetPlan:
             if side_dgrad is not None:
                 torch.cuda.current_stream().wait_event(side_dgrad)   # Gin already holds the shortcut's gradient
                 acc = 1
-            call("ssb_conv1d_dgrad", dc1.data_ptr(), self.sh.ptr(c), Gin.data_ptr(), gin, gout,
-                 c.k, c.stride, acc, dt, self._algo_for(c), st)
+            # this launch finalises the gradient of the previous block's output when the block has no shortcut conv
+            nxt = self._bn2_red(bi - 1) if (fuse and bi > 0 and bd.convd is None) else None
+            pre_reduced = self._dgrad(c, dc1, Gin, gin, gout, acc, st, nxt)
             if bd.convd is not None and side_dgrad is None:
                 c = bd.convd
                 call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.ptr(c), Gin.data_ptr(), gin, gout,

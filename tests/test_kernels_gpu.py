@@ -231,6 +231,51 @@ def test_conv_fwd_dual(cin, cout, k, stride, L, with_res, dtype, algo):
     assert rel_err(sums[:cout], ys.sum(0)) < 5e-6 and rel_err(sums[cout:], (ys * ys).sum(0)) < 5e-6
 
 
+@pytest.mark.parametrize("dtype,algo", ALGO_CASES)
+@pytest.mark.parametrize("cin,cout,k,L,acc,with_res", [(64, 64, 3, 157, 0, False), (128, 128, 3, 79, 1, True),
+                                                       (256, 128, 3, 79, 1, False), (512, 512, 3, 40, 0, True),
+                                                       (16, 8, 3, 37, 1, True)])
+def test_conv_dgrad_bnred(cin, cout, k, L, acc, with_res, dtype, algo):
+    """dgrad with the BN-backward reduce of the produced gradient fused in == dgrad followed by ssb_bn_bwd_reduce"""
+    if algo == _lib.ALGO_TCGEN05 and (cin % 64 or cout % 64):
+        pytest.skip("tcgen05 path needs channel counts that are multiples of 64")
+    torch.manual_seed(cin + cout + L)
+    B, pitch = 3, L + 2 + 2
+    g = Geom(B, pitch, L, cin)
+    go = Geom(B, pitch, L, cout)
+    w = torch.randn(cout, cin, k, device=DEV, dtype=torch.float64) / (cout * k) ** 0.5
+    dy = to_flat(torch.randn(B, cout, L, device=DEV, dtype=torch.float64), pitch, dtype)
+    y_act = to_flat(torch.relu(torch.randn(B, cin, L, device=DEV, dtype=torch.float64)), pitch, dtype)
+    x_pre = to_flat(torch.randn(B, cin, L, device=DEV, dtype=torch.float64) * 1.3 + 0.2, pitch, dtype)
+    x_res = to_flat(torch.randn(B, cin, L, device=DEV, dtype=torch.float64), pitch, dtype)
+    base = to_flat(torch.randn(B, cin, L, device=DEV, dtype=torch.float64), pitch, dtype)
+    wt = tap_major(w.float(), dtype)
+    outs = []
+    for fused in (False, True):
+        bn, t = make_bn(cin)
+        bnr, tr_ = make_bn(cin)
+        t["mi"][:cin] = 0.2
+        t["mi"][cin:] = 0.8
+        tr_["mi"][:cin] = -0.1
+        tr_["mi"][cin:] = 1.1
+        dx = base.clone()
+        if fused:
+            call("ssb_conv1d_dgrad_bnred", dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), g, go, k, 1, acc, y_act.data_ptr(),
+                 x_pre.data_ptr(), C.byref(bn), x_res.data_ptr() if with_res else None, C.byref(bnr) if with_res else None,
+                 dtype, algo, st())
+        else:
+            call("ssb_conv1d_dgrad", dy.data_ptr(), wt.data_ptr(), dx.data_ptr(), g, go, k, 1, acc, dtype, algo, st())
+            call("ssb_bn_bwd_reduce", dx.data_ptr(), None, y_act.data_ptr(), x_pre.data_ptr(), C.byref(bn),
+                 x_res.data_ptr() if with_res else None, C.byref(bnr) if with_res else None, g, dtype, st())
+        torch.cuda.synchronize()
+        outs.append((dx, t["bsums"].clone(), tr_["bsums"].clone()))
+    (dx0, s0, r0), (dx1, s1, r1) = outs
+    assert torch.equal(dx0, dx1)
+    assert rel_err(s1, s0) < 5e-6
+    if with_res:
+        assert rel_err(r1, r0) < 5e-6
+
+
 @pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
 @pytest.mark.parametrize("Cn,res_mode", [(8, 0), (64, 1), (128, 2), (24, 0)])
 def test_bn_forward_backward(dtype, Cn, res_mode):
