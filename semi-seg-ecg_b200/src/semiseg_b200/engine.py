@@ -103,10 +103,10 @@ class StepEngine:
         self.wgrad_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.teacher_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.repack_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
-        # gradient all-reduce in two buckets: the tail of the arena (last stage + head, ~3/4 of the bytes) is
-        # exchanged on its own stream as soon as those gradients exist, under the backward of the earlier stages
+        # gradient all-reduce in buckets: the ranges of the last stages (+ head) are exchanged on their own stream as
+        # soon as those gradients exist, under the backward of the earlier stages (SSB_BUCKETS = how many, 0 = off)
         self.comm_stream = torch.cuda.Stream(device=dev) if (self.multi_stream and self.collectives and
-                                                              int(os.environ.get("SSB_BUCKETS", "1"))) else None
+                                                              int(os.environ.get("SSB_BUCKETS", "2"))) else None
         self.dgrad_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.bufs_snap: Optional[torch.Tensor] = None
         if self.merged:
@@ -234,20 +234,29 @@ class StepEngine:
              m["mask"].data_ptr() if m else None, st)
         split = None
         if self.comm_stream is not None:
+            # buckets = the parameter ranges of the last stages (arena order = forward order): each is all-reduced
+            # on the communication stream as soon as its gradients exist; only the early layers' small range is
+            # exchanged after the backward has finished
             lay = self.plan_s.lay
-            last_stage = len(self.spec.stage_blocks) - 1
-            first = next(i for i, b in enumerate(lay.blocks) if b.stage == last_stage)
-            split = lay.blocks[first].conv1.poff
+            nst = len(self.spec.stage_blocks)
+            firsts = {}
+            for st_i in range(nst - 1, max(nst - 1 - int(os.environ.get("SSB_BUCKETS", "2")), 0) - 1, -1):
+                firsts[next(i for i, b in enumerate(lay.blocks) if b.stage == st_i)] = st_i
+            bounds = {bi: lay.blocks[bi].conv1.poff for bi in firsts}
+            upper = {"v": state.grads.numel()}
+            split = min(bounds.values())
 
-            def bucket(bi, first=first, split=split):
-                if bi != first:
+            def bucket(bi):
+                if bi not in bounds:
                     return
+                lo, hi = bounds[bi], upper["v"]
+                upper["v"] = lo
                 cur_ = torch.cuda.current_stream()
-                self.comm_stream.wait_stream(cur_)                       # BN / head gradients of the tail (main stream)
+                self.comm_stream.wait_stream(cur_)                       # BN / head gradients of the range (main stream)
                 if self.wgrad_stream is not None:
-                    self.comm_stream.wait_stream(self.wgrad_stream)      # conv weight gradients of the tail
+                    self.comm_stream.wait_stream(self.wgrad_stream)      # conv weight gradients of the range
                 with torch.cuda.stream(self.comm_stream):
-                    torch.distributed.all_reduce(state.grads[split:], group=self.pg)
+                    torch.distributed.all_reduce(state.grads[lo:hi], group=self.pg)
             self.plan_s.block_done_hook = bucket
         self.plan_s.backward(self.plan_s.dlow, st)
         self.plan_s.block_done_hook = None
