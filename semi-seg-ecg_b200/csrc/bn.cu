@@ -478,6 +478,203 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
 }
 
 // ---------------------------------------------------------------------------------------
+// backward, both passes in ONE launch: reduce -> grid-wide barrier -> apply.  The grid is sized to the kernel's
+// co-resident capacity (host check with the occupancy API) and walks its rows twice (the second read hits L2 / L1);
+// the barrier is a counter in the step's zero arena (one per BN layer, zeroed by the step's memset).
+// RES: 0 none; 1 identity residual -> g_ident = g; 2 residual BN -> dx_res
+// ---------------------------------------------------------------------------------------
+#define BWF_ROWS 2
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < expected);
+  }
+  __syncthreads();
+}
+
+template <typename T, bool HAS_Y, int RES>
+__global__ void __launch_bounds__(BN_THREADS) bn_bwd_fused_kernel(const T* __restrict__ g1, const T* __restrict__ y,
+                                                                  const T* __restrict__ x, const T* __restrict__ xr,
+                                                                  T* __restrict__ dx, T* __restrict__ dxr, T* __restrict__ gid,
+                                                                  ssb_bn bn, ssb_bn bnr, ssb_geom g, int cgpc, int rpb,
+                                                                  unsigned int* __restrict__ barrier) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int V = Vec<T>::N;
+  const int C = g.C;
+  const int ncg = C / V;
+  const int rpp = BN_THREADS / cgpc;
+  const int cgl = threadIdx.x % cgpc, rl = threadIdx.x / cgpc;
+  const int cg = blockIdx.y * cgpc + cgl;
+  const bool owner = rl < rpp && cg < ncg;
+  const int rows = g.B * g.pitch;
+  const int r0 = blockIdx.x * rpb;
+  const int r1 = min(rows, r0 + rpb);
+  __shared__ float sA[BN_THREADS * V];
+  __shared__ float sB[BN_THREADS * V];
+  __shared__ float sC[RES == 2 ? BN_THREADS * V : 1];
+  __shared__ float sCo[5][64];
+  float mean[V], inv[V], meanr[V], invr[V];
+  // ---- pass 1: reduce ----
+  {
+    float a[V], bq[V], cq[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) a[i] = bq[i] = cq[i] = 0.f;
+    if (owner) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const int c = cg * V + i;
+        mean[i] = bn.mean_invstd[c];
+        inv[i] = bn.mean_invstd[C + c];
+        if (RES == 2) {
+          meanr[i] = bnr.mean_invstd[c];
+          invr[i] = bnr.mean_invstd[C + c];
+        }
+      }
+      for (int row = r0 + rl; row < r1; row += rpp) {
+        if (!row_valid(row, g.pitch, g.len)) continue;     // halo / pad rows carry zero gradient
+        const size_t off = (size_t)row * C + (size_t)cg * V;
+        Vec<T> vg, vx;
+        vg.load(g1 + off);
+        vx.load(x + off);
+        float fg[V], fx[V];
+        vg.get(fg);
+        vx.get(fx);
+        if (HAS_Y) {
+          Vec<T> vy;
+          vy.load(y + off);
+          float fy[V];
+          vy.get(fy);
+#pragma unroll
+          for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
+        }
+        float fr[V];
+        if (RES == 2) {
+          Vec<T> vr;
+          vr.load(xr + off);
+          vr.get(fr);
+        }
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          a[i] += fg[i];
+          bq[i] += fg[i] * ((fx[i] - mean[i]) * inv[i]);
+          if (RES == 2) cq[i] += fg[i] * ((fr[i] - meanr[i]) * invr[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      sA[threadIdx.x * V + i] = a[i];
+      sB[threadIdx.x * V + i] = bq[i];
+      if (RES == 2) sC[threadIdx.x * V + i] = cq[i];
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < cgpc * V; o += BN_THREADS) {
+    const int l = o / V, i = o % V;
+    const int cgo = blockIdx.y * cgpc + l;
+    if (cgo >= ncg) continue;
+    float da = 0.f, db = 0.f, dc = 0.f;
+    for (int k = 0; k < rpp; ++k) {
+      da += sA[(k * cgpc + l) * V + i];
+      db += sB[(k * cgpc + l) * V + i];
+      if (RES == 2) dc += sC[(k * cgpc + l) * V + i];
+    }
+    const int c = cgo * V + i;
+    atomicAdd(&bn.bwd_sums[c], (double)da);
+    atomicAdd(&bn.bwd_sums[C + c], (double)db);
+    if (RES == 2) {
+      atomicAdd(&bnr.bwd_sums[c], (double)da);
+      atomicAdd(&bnr.bwd_sums[C + c], (double)dc);
+    }
+    __threadfence();   // this thread's reductions are performed before the block signals the barrier
+  }
+  grid_barrier(barrier, gridDim.x * gridDim.y);
+  // ---- pass 2: apply; per-channel constants from the now complete sums (one thread per channel) ----
+  const int nch = cgpc * V;
+  if (threadIdx.x < nch) {
+    const int c = blockIdx.y * nch + threadIdx.x;
+    if (c < C) {
+      const double inv_n = 1.0 / ((double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1));
+      const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
+      const bool writer = blockIdx.x == 0;
+      const double sg = __ldcg(&bn.bwd_sums[c]), sgx = __ldcg(&bn.bwd_sums[C + c]);
+      sCo[0][threadIdx.x] = bn.gamma[c] * bn.mean_invstd[C + c];
+      sCo[1][threadIdx.x] = (float)(sg * inv_n);
+      sCo[2][threadIdx.x] = (float)(sgx * inv_n);
+      if (writer) {
+        bn.dgamma[c] = (float)(sgx * gsc);
+        bn.dbeta[c] = (float)(sg * gsc);
+      }
+      if (RES == 2) {
+        const double sgxr = __ldcg(&bnr.bwd_sums[C + c]);
+        sCo[3][threadIdx.x] = bnr.gamma[c] * bnr.mean_invstd[C + c];
+        sCo[4][threadIdx.x] = (float)(sgxr * inv_n);
+        if (writer) {
+          bnr.dgamma[c] = (float)(sgxr * gsc);
+          bnr.dbeta[c] = (float)(sg * gsc);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (!owner) return;
+  float k0[V], k1[V], k2[V], rk0[V], rk2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = cgl * V + i;
+    k0[i] = sCo[0][j]; k1[i] = sCo[1][j]; k2[i] = sCo[2][j];
+    if (RES == 2) { rk0[i] = sCo[3][j]; rk2[i] = sCo[4][j]; }
+  }
+  for (int row = r0 + rl; row < r1; row += rpp) {     // the block's rows are still in L2 (and mostly in L1)
+    const size_t off = (size_t)row * C + (size_t)cg * V;
+    Vec<T> odx, odr, ogi;
+    if (row_valid(row, g.pitch, g.len)) {
+      Vec<T> vg, vx;
+      vg.load(g1 + off);
+      vx.load(x + off);
+      float fg[V], fx[V];
+      vg.get(fg);
+      vx.get(fx);
+      if (HAS_Y) {
+        Vec<T> vy;
+        vy.load(y + off);
+        float fy[V];
+        vy.get(fy);
+#pragma unroll
+        for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
+      }
+      float o[V];
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = k0[i] * (fg[i] - k1[i] - ((fx[i] - mean[i]) * inv[i]) * k2[i]);
+      odx.set(o);
+      if (RES == 1) ogi.set(fg);
+      if (RES == 2) {
+        Vec<T> vr;
+        vr.load(xr + off);
+        float fr[V];
+        vr.get(fr);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = rk0[i] * (fg[i] - k1[i] - ((fr[i] - meanr[i]) * invr[i]) * rk2[i]);
+        odr.set(o);
+      }
+    } else {
+      odx.zero();
+      odr.zero();
+      ogi.zero();
+    }
+    odx.store(dx + off);
+    if (RES == 1) ogi.store(gid + off);
+    if (RES == 2) odr.store(dxr + off);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // stem tail backward: the pooled gradient is routed through the max-pool by the slot index the
 // forward saved (slot 3 = ReLU-dead), then the two BN-backward passes on c0.
 // ---------------------------------------------------------------------------------------
@@ -674,6 +871,42 @@ static EwGeom ew_geom(int rows, int ncg, int vec) {
 
 static const ssb_bn kNoBn = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0};
 
+// grid of the fused backward kernel and whether all of it can be resident at once (the blocks meet at a grid-wide
+// barrier): bounded by the measured occupancy of the instantiation, one block per SM left as slack
+template <typename T>
+static bool bwd_fused_plan(const ssb_geom& g, int mode, bool has_y, int* cgpc_o, int* rpb_o, dim3* grid_o) {
+  constexpr int V = Vec<T>::N;
+  const int rows = g.B * g.pitch;
+  const int ncg = g.C / V;
+  const int per_chunk = 64 / V;
+  const int cgpc = ncg < per_chunk ? ncg : per_chunk;
+  const int ny = ceil_div(ncg, cgpc);
+  const int rpp = BN_THREADS / cgpc;
+  int occ = 0;
+  cudaError_t oe = cudaSuccess;
+  if (mode == 0) oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 0>, BN_THREADS, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 0>, BN_THREADS, 0);
+  else if (mode == 1) oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 1>, BN_THREADS, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 1>, BN_THREADS, 0);
+  else oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 2>, BN_THREADS, 0)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 2>, BN_THREADS, 0);
+  if (oe != cudaSuccess) occ = 0;
+  // co-resident capacity with one block per SM left as slack; the rows are spread over at most that many blocks
+  const long long cap = occ >= 2 ? 148LL * (occ - 1) : 0;
+  int nx = cap / ny > 0 ? (int)(cap / ny) : 0;
+  const int want = ceil_div(rows, rpp * BWF_ROWS);
+  if (nx > want) nx = want;
+  int rpb = nx > 0 ? ceil_div(ceil_div(rows, nx), rpp) * rpp : rows;
+  if (nx > 0) nx = ceil_div(rows, rpb);
+  *cgpc_o = cgpc;
+  *rpb_o = rpb;
+  *grid_o = dim3(nx, ny);
+  return nx > 0 && (long long)nx * ny <= cap;
+}
+
+#define SSB_BWF(Y, R)                                                                                                          \
+  ssb_launch(bn_bwd_fused_kernel<T, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)y, (const T*)x,       \
+             (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, cgpc, rpb, barrier)
 #define SSB_RED(G2, Y, R) \
   ssb_launch(bn_bwd_reduce_kernel<T, G2, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, *bn, br, rows, g.C, rpb)
 #define SSB_APP(G2, Y, R) \
@@ -798,6 +1031,42 @@ int ssb_bn_bwd_apply(const void* g1, const void* g2, const void* y, const void* 
     }
   })
   SSB_LAUNCH_CHECK("ssb_bn_bwd_apply");
+  return SSB_OK;
+}
+
+int ssb_bn_bwd_fused_fits(ssb_geom g, int res_mode, int has_y, int dtype) {
+  if (check_geom("ssb_bn_bwd_fused_fits", g, 0)) return 0;
+  int cgpc, rpb;
+  dim3 grid;
+  if (dtype == SSB_F32) return bwd_fused_plan<float>(g, res_mode, has_y != 0, &cgpc, &rpb, &grid) ? 1 : 0;
+  if (dtype == SSB_BF16) return bwd_fused_plan<bf16>(g, res_mode, has_y != 0, &cgpc, &rpb, &grid) ? 1 : 0;
+  return 0;
+}
+
+int ssb_bn_bwd_fused(const void* g1, const void* y, const void* x, const ssb_bn* bn, void* dx, const void* x_res,
+                     const ssb_bn* bn_res, void* dx_res, void* g_ident, ssb_geom g, uint32_t* barrier, int dtype,
+                     ssb_stream_t stream) {
+  int rc = check_geom("ssb_bn_bwd_fused", g, 0);
+  if (rc) return rc;
+  SSB_REQUIRE(g1 && x && bn && dx && barrier, "ssb_bn_bwd_fused: null pointer");
+  SSB_REQUIRE(!(bn_res && (!x_res || !dx_res)), "ssb_bn_bwd_fused: residual BN needs x_res and dx_res");
+  SSB_REQUIRE(!(bn_res && g_ident), "ssb_bn_bwd_fused: g_ident and bn_res are exclusive");
+  const int mode = bn_res ? 2 : (g_ident ? 1 : 0);
+  SSB_DISPATCH_DTYPE(dtype, T, {
+    int cgpc, rpb;
+    dim3 grid;
+    if (!bwd_fused_plan<T>(g, mode, y != nullptr, &cgpc, &rpb, &grid)) {
+      ssb_set_error("ssb_bn_bwd_fused: %u x %u blocks exceed the co-resident capacity; use ssb_bn_bwd_reduce + ssb_bn_bwd_apply",
+                    grid.x, grid.y);
+      return SSB_ERR_UNSUPPORTED;
+    }
+    cudaStream_t st = to_stream(stream);
+    const ssb_bn br = bn_res ? *bn_res : kNoBn;
+    if (mode == 0) { if (y) SSB_BWF(true, 0); else SSB_BWF(false, 0); }
+    else if (mode == 1) { if (y) SSB_BWF(true, 1); else SSB_BWF(false, 1); }
+    else { if (y) SSB_BWF(true, 2); else SSB_BWF(false, 2); }
+  })
+  SSB_LAUNCH_CHECK("ssb_bn_bwd_fused");
   return SSB_OK;
 }
 

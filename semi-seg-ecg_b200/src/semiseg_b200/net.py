@@ -280,13 +280,15 @@ class TrainState:
         lay, dev = w.layout, w.device
         # everything a step zeroes before it starts lives in ONE arena (one memset node per step):
         # [gradients | BN forward sums | BN backward sums | loss sums] -- the tail is fp64
-        n_tail = 2 * lay.n_sums + 64
+        n_tail = 2 * lay.n_sums + 64 + len(lay.bns)
         self.zero_arena = torch.zeros(lay.n_params + 2 * n_tail, dtype=torch.float32, device=dev)
         self.grads = self.zero_arena[: lay.n_params]
         tail = self.zero_arena[lay.n_params:].view(torch.float64)
         self.sums = tail[: lay.n_sums]
         self.bwd_sums = tail[lay.n_sums: 2 * lay.n_sums]
         self.loss_sums = tail[2 * lay.n_sums: 2 * lay.n_sums + 4]
+        # one grid-barrier counter per BN layer (fused BN backward), zeroed with everything else
+        self.barriers = tail[2 * lay.n_sums + 8: 2 * lay.n_sums + 8 + len(lay.bns)].view(torch.int32)
         self.exp_avg = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
         self.step = 0
@@ -331,6 +333,8 @@ class NetPlan:
         # SLOWER (0.779 vs 0.765 ms at 16+16 x 2500; conv family +37 % at width 128): the extra loads, transposes and
         # per-chunk barriers sit on the epilogue, which is already the long pole of these tiles.  Off by default.
         self.fuse_reduce = bool(int(os.environ.get("SSB_FUSE_REDUCE", "0")))
+        self.fuse_bn_bwd = bool(int(os.environ.get("SSB_FUSE_BN_BWD", "1")))   # reduce + apply in one launch (grid barrier)
+        self._fused_ok: Dict[Tuple, bool] = {}
         self.block_done_hook = None   # callable(block_index) after a block's backward has been enqueued (bucketed all-reduce)
         if algo is None:
             algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
@@ -375,6 +379,7 @@ class NetPlan:
         self._with_b = with_b
 
         # ---- BN statistic arenas ----
+        self.barriers = state.barriers if state is not None else None
         if state is not None:   # statistic arenas inside the step's zero arena (TrainState)
             self.sums, self.bwd_sums = state.sums, state.bwd_sums
         else:
@@ -521,6 +526,8 @@ class NetPlan:
         call("ssb_memset_zero", self.sums.data_ptr(), self.sums.numel() * 8, st)
         if self.train:
             call("ssb_memset_zero", self.bwd_sums.data_ptr(), self.bwd_sums.numel() * 8, st)
+            if self.barriers is not None:
+                call("ssb_memset_zero", self.barriers.data_ptr(), self.barriers.numel() * 4, st)
 
     # ---- forward -------------------------------------------------------------------
     def forward(self, x: torch.Tensor, st: int, train_mode: Optional[bool] = None, zero: bool = True,
@@ -669,6 +676,28 @@ class NetPlan:
              self.bn(b_res) if b_res is not None else None, self.dtype, self._algo_for(c), st)
         return True
 
+    def _bn_bwd(self, g1, y, x, b: BNDesc, dx, geom: Geom, st: int, x_res=None, b_res: Optional[BNDesc] = None, dx_res=None,
+                g_ident=None, pre_reduced: bool = False):
+        """BatchNorm(+ReLU) backward of one layer: both passes in one launch (grid barrier) when the tensor is small
+        enough for the whole grid to be co-resident and no statistics exchange sits between them, else two launches."""
+        ptr = lambda t: t.data_ptr() if t is not None else None   # noqa: E731
+        if self.fuse_bn_bwd and not pre_reduced and self.sync_hook is None and self.barriers is not None:
+            mode = 2 if b_res is not None else (1 if g_ident is not None else 0)
+            key = (geom.B, geom.pitch, geom.len, geom.C, mode, y is not None)
+            if key not in self._fused_ok:
+                self._fused_ok[key] = bool(_lib.load().ssb_bn_bwd_fused_fits(geom, mode, 1 if y is not None else 0, self.dtype))
+            if self._fused_ok[key]:
+                call("ssb_bn_bwd_fused", g1.data_ptr(), ptr(y), x.data_ptr(), self.bn(b), dx.data_ptr(), ptr(x_res),
+                     self.bn(b_res) if b_res is not None else None, ptr(dx_res), ptr(g_ident), geom,
+                     self.barriers.data_ptr() + 4 * b.index, self.dtype, st)
+                return
+        if not pre_reduced:
+            call("ssb_bn_bwd_reduce", g1.data_ptr(), None, ptr(y), x.data_ptr(), self.bn(b), ptr(x_res),
+                 self.bn(b_res) if b_res is not None else None, geom, self.dtype, st)
+        self._sync_bwd(b, b_res)
+        call("ssb_bn_bwd_apply", g1.data_ptr(), None, ptr(y), x.data_ptr(), self.bn(b), dx.data_ptr(), ptr(x_res),
+             self.bn(b_res) if b_res is not None else None, ptr(dx_res), ptr(g_ident), geom, self.dtype, st)
+
     def _bn2_red(self, bi: int):
         """reduce arguments of block bi's output BN (bn2 [+ downsample BN]) for the dgrad that produces its gradient"""
         bd, bufs = self.lay.blocks[bi], self.blk_bufs[bi]
@@ -690,11 +719,7 @@ class NetPlan:
              sc_h["gA"].data_ptr(), gw + 4 * lay.cls_w_off, gw + 4 * lay.cls_b_off, self.g_head, spec.num_classes, p,
              self.drop_mask_ptr or None, self.sp_ptr or None, dt, st)
         # head BN + ReLU backward -> dch (gB)
-        call("ssb_bn_bwd_reduce", sc_h["gA"].data_ptr(), None, self.ah.data_ptr(), self.ch.data_ptr(), self.bn(lay.head_bn),
-             None, None, self.g_head, dt, st)
-        self._sync_bwd(lay.head_bn)
-        call("ssb_bn_bwd_apply", sc_h["gA"].data_ptr(), None, self.ah.data_ptr(), self.ch.data_ptr(), self.bn(lay.head_bn),
-             sc_h["gB"].data_ptr(), None, None, None, None, self.g_head, dt, st)
+        self._bn_bwd(sc_h["gA"], self.ah, self.ch, lay.head_bn, sc_h["gB"], self.g_head, st)
         gfeat = self.g_stage[-1]
         sc_f = self._scratch[(gfeat.pitch, gfeat.len, gfeat.C)]
         hc = lay.head_conv
@@ -727,20 +752,9 @@ class NetPlan:
             out, c2 = bufs["out"], bufs["c2"]
             self._before_write(dc2, dcd)
             if bd.convd is not None:
-                cd = bufs["cd"]
-                if not pre_reduced:
-                    call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
-                         cd.data_ptr(), self.bn(bd.bnd), gout, dt, st)
-                self._sync_bwd(bd.bn2, bd.bnd)
-                call("ssb_bn_bwd_apply", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
-                     dc2.data_ptr(), cd.data_ptr(), self.bn(bd.bnd), dcd.data_ptr(), None, gout, dt, st)
+                self._bn_bwd(G, out, c2, bd.bn2, dc2, gout, st, x_res=bufs["cd"], b_res=bd.bnd, dx_res=dcd, pre_reduced=pre_reduced)
             else:
-                if not pre_reduced:
-                    call("ssb_bn_bwd_reduce", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
-                         None, None, gout, dt, st)
-                self._sync_bwd(bd.bn2)
-                call("ssb_bn_bwd_apply", G.data_ptr(), None, out.data_ptr(), c2.data_ptr(), self.bn(bd.bn2),
-                     dc2.data_ptr(), None, None, None, Gin.data_ptr(), gout, dt, st)
+                self._bn_bwd(G, out, c2, bd.bn2, dc2, gout, st, g_ident=Gin, pre_reduced=pre_reduced)
             if self.debug is not None:
                 self.debug[bd.prefix + ".conv2"] = self.to_ncl(dc2, gout)
                 if bd.convd is not None:
@@ -762,12 +776,7 @@ class NetPlan:
             # bn1 + relu backward -> dc1
             dc1 = bg["dc1"]
             self._before_write(dc1)
-            if not red1:
-                call("ssb_bn_bwd_reduce", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
-                     None, None, gout, dt, st)
-            self._sync_bwd(bd.bn1)
-            call("ssb_bn_bwd_apply", da1.data_ptr(), None, bufs["a1"].data_ptr(), bufs["c1"].data_ptr(), self.bn(bd.bn1),
-                 dc1.data_ptr(), None, None, None, None, gout, dt, st)
+            self._bn_bwd(da1, bufs["a1"], bufs["c1"], bd.bn1, dc1, gout, st, pre_reduced=red1)
             if self.debug is not None:
                 self.debug[bd.prefix + ".conv1"] = self.to_ncl(dc1, gout)
             c = bd.conv1

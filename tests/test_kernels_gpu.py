@@ -277,6 +277,49 @@ def test_conv_dgrad_bnred(cin, cout, k, L, acc, with_res, dtype, algo):
 
 
 @pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
+@pytest.mark.parametrize("Cn,res_mode,L", [(64, 0, 625), (128, 1, 313), (512, 2, 79), (24, 1, 50), (8, 2, 33)])
+def test_bn_bwd_fused(dtype, Cn, res_mode, L):
+    """reduce + grid barrier + apply in one launch == ssb_bn_bwd_reduce followed by ssb_bn_bwd_apply"""
+    torch.manual_seed(Cn + L)
+    B, pitch = 16, L + 3
+    g = Geom(B, pitch, L, Cn)
+    gr = to_flat(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64), pitch, dtype)
+    yy = to_flat(torch.relu(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64)), pitch, dtype)
+    xx = to_flat(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64) + 0.3, pitch, dtype)
+    xr = to_flat(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64), pitch, dtype)
+    res = []
+    for fused in (False, True):
+        torch.manual_seed(1234)          # same gamma / beta in both runs
+        bn, t = make_bn(Cn)
+        bnr, tr_ = make_bn(Cn)
+        for d in (t, tr_):
+            d["mi"][:Cn] = 0.1
+            d["mi"][Cn:] = 0.9
+        dx = torch.full((B * pitch, Cn), 3.0, dtype=TDT[dtype], device=DEV)
+        dxr = torch.full((B * pitch, Cn), 3.0, dtype=TDT[dtype], device=DEV)
+        gid = torch.full((B * pitch, Cn), 3.0, dtype=TDT[dtype], device=DEV)
+        a_res = (xr.data_ptr(), C.byref(bnr), dxr.data_ptr(), None) if res_mode == 2 else (None, None, None, gid.data_ptr() if res_mode == 1 else None)
+        if fused:
+            bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+            call("ssb_bn_bwd_fused", gr.data_ptr(), yy.data_ptr(), xx.data_ptr(), C.byref(bn), dx.data_ptr(), a_res[0], a_res[1],
+                 a_res[2], a_res[3], g, bar.data_ptr(), dtype, st())
+        else:
+            call("ssb_bn_bwd_reduce", gr.data_ptr(), None, yy.data_ptr(), xx.data_ptr(), C.byref(bn), a_res[0], a_res[1], g, dtype, st())
+            call("ssb_bn_bwd_apply", gr.data_ptr(), None, yy.data_ptr(), xx.data_ptr(), C.byref(bn), dx.data_ptr(), a_res[0], a_res[1],
+                 a_res[2], a_res[3], g, dtype, st())
+        torch.cuda.synchronize()
+        res.append((dx.float(), dxr.float(), gid.float(), t["dgamma"].clone(), t["dbeta"].clone(), tr_["dgamma"].clone()))
+    tol = 1e-5 if dtype == _lib.F32 else 1e-2
+    assert rel_err(res[1][0], res[0][0]) < tol and halo_is_zero(res[1][0], B, pitch, L)
+    assert rel_err(res[1][3], res[0][3]) < 1e-5 and rel_err(res[1][4], res[0][4]) < 1e-5
+    if res_mode == 2:
+        assert rel_err(res[1][1], res[0][1]) < tol and rel_err(res[1][5], res[0][5]) < 1e-5
+    if res_mode == 1:
+        assert torch.equal(res[1][2], res[0][2])
+    assert _lib.load().ssb_bn_bwd_fused_fits(Geom(64, 1300, 1250, 64), res_mode, 1, dtype) == 1   # any size: the grid is capped
+
+
+@pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
 @pytest.mark.parametrize("Cn,res_mode", [(8, 0), (64, 1), (128, 2), (24, 0)])
 def test_bn_forward_backward(dtype, Cn, res_mode):
     torch.manual_seed(Cn + res_mode)
