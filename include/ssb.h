@@ -156,6 +156,18 @@ int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ss
 int ssb_conv1d_bn_act_fwd(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout,
                           int k, int stride, const ssb_bn* bn, const void* res, int relu,
                           int dtype, int algo, ssb_stream_t stream);
+/* TRAIN-mode conv + BatchNorm(batch statistics) [+ residual | + bn_res(residual)] [+ ReLU] in one launch: the conv
+ * epilogue adds the statistics of its tile to bn->sums, all tiles meet at a grid-wide barrier, then a second pass
+ * over the accumulator (still in tensor memory) writes y_act, while y_raw keeps the conv output the backward needs.
+ * Also does what ssb_bn_act_fwd(train) does to the BN state (running statistics, saved mean / invstd, counter).
+ * Needs every CTA of the launch co-resident: returns SSB_ERR_UNSUPPORTED for shapes with more tiles than that (and
+ * for the generic path / SyncBN); callers then use ssb_conv1d_fwd_stats + ssb_bn_act_fwd.  barrier: zeroed uint32. */
+/* 1 if ssb_conv1d_fwd_bn_train can run this conv (call after ssb_prepare), else 0 */
+int ssb_conv1d_fwd_bn_train_fits(ssb_geom gin, ssb_geom gout, int k, int stride, int dtype, int algo);
+int ssb_conv1d_fwd_bn_train(const void* x, const void* w, void* y_raw, void* y_act, ssb_geom gin,
+                            ssb_geom gout, int k, int stride, const ssb_bn* bn, const void* res,
+                            const ssb_bn* bn_res, int relu, uint32_t* barrier, int dtype, int algo,
+                            ssb_stream_t stream);
 /* train rows and eval rows of the SAME conv in one launch (FixMatch: the pseudo-label forward uses the
  * student's weights, fixmatch.py:87-102): the first `train_samples` samples of x are train-mode rows
  * (raw output to y_train + statistics into sums, as ssb_conv1d_fwd_stats), the remaining samples are

@@ -4,8 +4,6 @@
 // kernel moves 16-byte vectors, channels fastest (coalesced), one pass per tensor.
 #include "common.cuh"
 
-#define BN_EPS 1e-5
-#define BN_MOMENTUM 0.1f
 #define BN_THREADS 256
 
 // ---------------------------------------------------------------------------------------
@@ -66,33 +64,6 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restric
     atomicAdd(&sums[c], (double)ds);
     atomicAdd(&sums[C + c], (double)dq);
   }
-}
-
-// per-channel affine coefficients: y = x*scale + shift
-__device__ __forceinline__ void bn_coeffs(const ssb_bn& bn, int c, int C, int train, double inv_n, double n,
-                                          bool writer, float& scale, float& shift) {
-  float mean, invstd;
-  if (train) {
-    double m = bn.sums[c] * inv_n;
-    double var = bn.sums[C + c] * inv_n - m * m;
-    if (var < 0.0) var = 0.0;
-    mean = (float)m;
-    invstd = rsqrtf((float)var + (float)BN_EPS);
-    invstd = invstd * (1.5f - 0.5f * ((float)var + (float)BN_EPS) * invstd * invstd);   // one Newton step: full fp32 accuracy
-    if (writer) {
-      bn.mean_invstd[c] = mean;
-      bn.mean_invstd[C + c] = invstd;
-      double unb = n > 1.0 ? var * (n / (n - 1.0)) : var;
-      bn.running_mean[c] = (1.f - BN_MOMENTUM) * bn.running_mean[c] + BN_MOMENTUM * mean;
-      bn.running_var[c] = (1.f - BN_MOMENTUM) * bn.running_var[c] + BN_MOMENTUM * (float)unb;
-      if (c == 0 && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
-    }
-  } else {
-    mean = bn.running_mean[c];
-    invstd = 1.0f / sqrtf(bn.running_var[c] + (float)BN_EPS);
-  }
-  scale = bn.gamma[c] * invstd;
-  shift = bn.beta[c] - mean * scale;
 }
 
 // ---------------------------------------------------------------------------------------

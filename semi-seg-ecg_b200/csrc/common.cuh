@@ -144,6 +144,46 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
+// arguments of the train-mode conv + BatchNorm(+residual)(+ReLU) fusion (conv_sm100.cu, BNF epilogue pass)
+struct ssb_bnf_args {
+  const ssb_bn* bn;       // BN of the conv output (batch statistics from bn->sums, filled by this launch)
+  const ssb_bn* bn_res;   // BN of the residual tensor (its sums are already complete) or NULL
+  const void* res;        // residual tensor in the output geometry or NULL
+  void* y_act;            // normalised output
+  int relu;
+  unsigned int* barrier;  // zeroed grid-barrier counter owned by this launch
+};
+
+#define BN_EPS 1e-5
+#define BN_MOMENTUM 0.1f
+
+// per-channel affine coefficients: y = x*scale + shift
+__device__ __forceinline__ void bn_coeffs(const ssb_bn& bn, int c, int C, int train, double inv_n, double n,
+                                          bool writer, float& scale, float& shift) {
+  float mean, invstd;
+  if (train) {
+    double m = __ldcg(&bn.sums[c]) * inv_n;   // (L2 read: the sums may have been completed by other blocks of this launch)
+    double var = __ldcg(&bn.sums[C + c]) * inv_n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = rsqrtf((float)var + (float)BN_EPS);
+    invstd = invstd * (1.5f - 0.5f * ((float)var + (float)BN_EPS) * invstd * invstd);   // one Newton step: full fp32 accuracy
+    if (writer) {
+      bn.mean_invstd[c] = mean;
+      bn.mean_invstd[C + c] = invstd;
+      double unb = n > 1.0 ? var * (n / (n - 1.0)) : var;
+      bn.running_mean[c] = (1.f - BN_MOMENTUM) * bn.running_mean[c] + BN_MOMENTUM * mean;
+      bn.running_var[c] = (1.f - BN_MOMENTUM) * bn.running_var[c] + BN_MOMENTUM * (float)unb;
+      if (c == 0 && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
+    }
+  } else {
+    mean = bn.running_mean[c];
+    invstd = 1.0f / sqrtf(bn.running_var[c] + (float)BN_EPS);
+  }
+  scale = bn.gamma[c] * invstd;
+  shift = bn.beta[c] - mean * scale;
+}
+
 // counter-based dropout RNG (keep decision for element idx), shared by fwd and bwd
 __device__ __forceinline__ uint32_t ssb_hash3(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;

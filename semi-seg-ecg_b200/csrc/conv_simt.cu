@@ -450,12 +450,14 @@ static TapSpec fwd_taps(int k, int stride) {
 
 int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
                          double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, int train_samples,
-                         void* y_eval, cudaStream_t st);
+                         void* y_eval, const ssb_bnf_args* bnf, cudaStream_t st);
 int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,
                            int accumulate, const void* red_y, const void* red_x, const ssb_bn* red_bn, const void* red_xr,
                            const ssb_bn* red_bn_r, cudaStream_t st);
 int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gin, ssb_geom gout, int k, int stride,
                            cudaStream_t st);
+
+int ssb_conv1d_fwd_bnf_fits_sm100(ssb_geom gin, ssb_geom gout, int k, int stride);
 
 int ssb_simt_prepare() {
   const int big = 96 * 1024;
@@ -484,7 +486,7 @@ int ssb_conv1d_fwd_stats(const void* x, const void* w, void* y, ssb_geom gin, ss
   SSB_REQUIRE(x && y && w, "ssb_conv1d_fwd: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_fwd: tcgen05 path needs bf16");
-    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, sums, nullptr, nullptr, 0, 0, nullptr, to_stream(stream));
+    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, sums, nullptr, nullptr, 0, 0, nullptr, nullptr, to_stream(stream));
   }
   if (sums) {   // generic CUDA-core path: conv, then the statistics pass as its own launch
     rc = ssb_conv1d_fwd_stats(x, w, y, gin, gout, k, stride, nullptr, dtype, algo, stream);
@@ -510,12 +512,34 @@ int ssb_conv1d_bn_act_fwd(const void* x, const void* w, void* y, ssb_geom gin, s
   SSB_REQUIRE(x && y && w && bn, "ssb_conv1d_bn_act_fwd: null pointer");
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_bn_act_fwd: tcgen05 path needs bf16");
-    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, nullptr, bn, res, relu, 0, nullptr, to_stream(stream));
+    return ssb_conv1d_fwd_sm100(x, w, y, gin, gout, k, stride, nullptr, bn, res, relu, 0, nullptr, nullptr, to_stream(stream));
   }
   // generic CUDA-core path: conv, then the eval-mode BN(+residual)(+ReLU) pass in place
   rc = ssb_conv1d_fwd(x, w, y, gin, gout, k, stride, dtype, algo, stream);
   if (rc) return rc;
   return ssb_bn_act_fwd(y, bn, res, nullptr, y, gout, relu, 0, dtype, stream);
+}
+
+int ssb_conv1d_fwd_bn_train_fits(ssb_geom gin, ssb_geom gout, int k, int stride, int dtype, int algo) {
+  if (algo != SSB_ALGO_TCGEN05 || dtype != SSB_BF16) return 0;
+  if (check_conv_geom("ssb_conv1d_fwd_bn_train_fits", gin, gout, k, stride)) return 0;
+  return ssb_conv1d_fwd_bnf_fits_sm100(gin, gout, k, stride);
+}
+
+int ssb_conv1d_fwd_bn_train(const void* x, const void* w, void* y_raw, void* y_act, ssb_geom gin, ssb_geom gout, int k,
+                            int stride, const ssb_bn* bn, const void* res, const ssb_bn* bn_res, int relu, uint32_t* barrier,
+                            int dtype, int algo, ssb_stream_t stream) {
+  int rc = check_conv_geom("ssb_conv1d_fwd_bn_train", gin, gout, k, stride);
+  if (rc) return rc;
+  SSB_REQUIRE(x && w && y_raw && y_act && bn && barrier, "ssb_conv1d_fwd_bn_train: null pointer");
+  SSB_REQUIRE(!(bn_res && !res), "ssb_conv1d_fwd_bn_train: bn_res given without res");
+  SSB_REQUIRE(bn->count_mul <= 1, "ssb_conv1d_fwd_bn_train: not for SyncBN (the statistics exchange sits between the passes)");
+  if (algo != SSB_ALGO_TCGEN05 || dtype != SSB_BF16) {
+    ssb_set_error("ssb_conv1d_fwd_bn_train: only the bf16 tcgen05 path fuses the BatchNorm pass; use ssb_conv1d_fwd_stats + ssb_bn_act_fwd");
+    return SSB_ERR_UNSUPPORTED;
+  }
+  ssb_bnf_args a = {bn, bn_res, res, y_act, relu, barrier};
+  return ssb_conv1d_fwd_sm100(x, w, y_raw, gin, gout, k, stride, nullptr, nullptr, nullptr, 0, 0, nullptr, &a, to_stream(stream));
 }
 
 int ssb_conv1d_fwd_dual(const void* x, const void* w, void* y_train, void* y_eval, ssb_geom gin, ssb_geom gout, int k,
@@ -528,7 +552,7 @@ int ssb_conv1d_fwd_dual(const void* x, const void* w, void* y_train, void* y_eva
   if (algo == SSB_ALGO_TCGEN05) {
     SSB_REQUIRE(dtype == SSB_BF16, "ssb_conv1d_fwd_dual: tcgen05 path needs bf16");
     return ssb_conv1d_fwd_sm100(x, w, y_train, gin, gout, k, stride, sums, bn_eval, res_eval, relu, train_samples, y_eval,
-                                to_stream(stream));
+                                nullptr, to_stream(stream));
   }
   // generic CUDA-core path: the two row ranges as separate launches (train rows + statistics, eval rows + BN pass)
   const size_t es = dtype == SSB_BF16 ? 2 : 4;

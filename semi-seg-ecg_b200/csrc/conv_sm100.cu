@@ -151,6 +151,17 @@ struct TnParams {
   const float* red_mi_r;
   double* red_sums;
   double* red_sums_r;
+  // BNF (with STATS, train mode): after the statistics are complete ACROSS the launch (grid-wide barrier on
+  // bnf_barrier), a second pass over the TMEM accumulator writes out2 = [relu](bn(y) [+ res | + bn_r(res)]) --
+  // the BatchNorm apply pass without its own launch and without re-reading y.  bnf / bnf_r: the BN layers
+  // (batch statistics from their sums; the block row 0 tiles update running stats and save mean / invstd).
+  unsigned int* bnf_barrier;
+  unsigned int bnf_expected;
+  ssb_bn bnf, bnf_r;
+  const bf16* bnf_res;
+  int bnf_res_mode;   // 0 none, 1 identity residual, 2 residual with its own BN
+  int bnf_relu;
+  double bnf_n;       // elements per channel (B * len * world)
 };
 
 // Column sums across the 32 lanes of a warp: every lane holds 32 column values x[0..31] of its own row;
@@ -371,7 +382,8 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
       red[(q * 2 + 1) * BN + c + lane] = sq[0];
     }
   }
-  if (release) {   // persistent kernel: this thread is done reading the accumulator buffer
+  const bool bnf = STATS && !EPI && p.bnf_barrier != nullptr;
+  if (release && !bnf) {   // persistent kernel: this thread is done reading the accumulator buffer
     tc_fence_before();
     mbar_arrive(release);
   }
@@ -387,6 +399,76 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
       }
       atomicAdd(&p.stats[n0 + col], (double)a);
       atomicAdd(&p.stats[p.N + n0 + col], (double)b);
+    }
+    if (bnf) {
+      // ---- train-mode BatchNorm apply fused in: wait until every tile of this launch has added its statistics ----
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (e == 0) {
+        atomicAdd(p.bnf_barrier, 1u);
+        unsigned int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.bnf_barrier) : "memory");
+        } while (v < p.bnf_expected);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // per-column coefficients (one thread per column does the fp64 part); the first row tile of each column
+      // tile updates the running statistics and saves mean / invstd for the backward
+      const bool writer = m0 == 0;
+      for (int col = e; col < BN; col += 128) {
+        float sc, sh;
+        bn_coeffs(p.bnf, n0 + col, p.N, 1, 1.0 / p.bnf_n, p.bnf_n, writer, sc, sh);
+        ep_scale[col] = sc;
+        ep_scale[BN + col] = sh;
+        if (p.bnf_res_mode == 2) {
+          bn_coeffs(p.bnf_r, n0 + col, p.N, 1, 1.0 / p.bnf_n, p.bnf_n, writer, sc, sh);
+          ep_scale[2 * BN + col] = sc;
+          ep_scale[3 * BN + col] = sh;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      bf16* optr2 = p.out2 + (size_t)(in_range ? orow : 0) * p.N + n0;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        tmem_ld_wait();
+        if (!in_range) continue;
+        uint4* dst = reinterpret_cast<uint4*>(optr2 + c);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          float f[8];
+          Vec<bf16> o;
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[v * 8 + i]);
+            o.set(f);
+            o.get(f);   // the normalisation sees the value as stored (bf16), like the separate pass did
+            float rs[8];
+            if (p.bnf_res_mode) {
+              Vec<bf16> rv;
+              rv.raw = *reinterpret_cast<const uint4*>(p.bnf_res + (size_t)orow * p.N + n0 + c + v * 8);
+              rv.get(rs);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int cc = c + v * 8 + i;
+              float y = fmaf(f[i], ep_scale[cc], ep_scale[BN + cc]);
+              if (p.bnf_res_mode == 1) y += rs[i];
+              if (p.bnf_res_mode == 2) y += fmaf(rs[i], ep_scale[2 * BN + cc], ep_scale[3 * BN + cc]);
+              f[i] = p.bnf_relu ? fmaxf(y, 0.f) : y;
+            }
+            o.set(f);
+          } else {
+            o.zero();
+          }
+          dst[v] = o.raw;
+        }
+      }
+      if (release) {
+        tc_fence_before();
+        mbar_arrive(release);
+      }
     }
   }
   }
@@ -903,6 +985,8 @@ int make_map(CUtensorMap* map, const void* base, long long inner, long long oute
 constexpr int TN_STAGES = 4;
 constexpr int WG_STAGES = 4;
 
+int g_num_sms = 148;
+
 template <int BN, bool B_MN>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem_bytes<BN * BK * 2, TN_STAGES>();
@@ -914,8 +998,20 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
     if constexpr (B_MN)
       ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   } else if (p.stats) {
-    if constexpr (B_MN)
-      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+    if constexpr (B_MN) {
+      TnParams q = p;
+      if (p.bnf_barrier) {   // grid-wide barrier inside: every CTA of the launch must be resident at once
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<BN, TN_STAGES, true, true, false>, NTHREADS, smem) != cudaSuccess)
+          occ = 0;
+        q.bnf_expected = grid.x * grid.y;
+        if ((long long)q.bnf_expected > (long long)occ * g_num_sms) {
+          ssb_set_error("conv + BN fusion: %u CTAs exceed the co-resident capacity (%d per SM)", q.bnf_expected, occ);
+          return SSB_ERR_UNSUPPORTED;
+        }
+      }
+      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, q);
+    }
   } else if (p.red_sums) {
     if constexpr (!B_MN) {
       if (p.red_xr)
@@ -930,8 +1026,6 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
   return SSB_OK;
 }
 
-int g_num_sms = 148;
-
 template <int BN, bool B_MN>
 int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
   constexpr int smem = smem3_bytes<BN>();
@@ -944,8 +1038,17 @@ int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const 
     if constexpr (B_MN)
       ssb_launch_pro(conv_tn3_kernel<BN, false, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
   } else if (p.stats) {
-    if constexpr (B_MN)
-      ssb_launch_pro(conv_tn3_kernel<BN, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+    if constexpr (B_MN) {
+      TnParams q = p;
+      if (p.bnf_barrier) {   // grid-wide barrier inside: one tile per CTA, every CTA resident (1 per SM)
+        q.bnf_expected = (unsigned int)ntiles;
+        if (ntiles > g_num_sms) {
+          ssb_set_error("conv + BN fusion: %d tiles exceed the %d co-resident CTAs of the persistent kernel", ntiles, g_num_sms);
+          return SSB_ERR_UNSUPPORTED;
+        }
+      }
+      ssb_launch_pro(conv_tn3_kernel<BN, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, q);
+    }
   } else if (p.red_sums) {
     if constexpr (!B_MN) {
       if (p.red_xr)
@@ -1083,7 +1186,7 @@ int ssb_sm100_prepare() {
 
 int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ssb_geom gout, int k, int stride,
                          double* stats, const ssb_bn* ep_bn, const void* ep_res, int ep_relu, int train_samples,
-                         void* y_eval, cudaStream_t st) {
+                         void* y_eval, const ssb_bnf_args* bnf, cudaStream_t st) {
   int rc = check_sm100_shape("ssb_conv1d_fwd", gin, gout);
   if (rc) return rc;
   TnParams p = {};
@@ -1112,6 +1215,17 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ss
     p.ep_res = (const bf16*)ep_res;
     p.ep_relu = ep_relu;
   }
+  if (bnf) {
+    p.bnf_barrier = bnf->barrier;
+    p.bnf = *bnf->bn;
+    if (bnf->bn_res) p.bnf_r = *bnf->bn_res;
+    p.bnf_res = (const bf16*)bnf->res;
+    p.bnf_res_mode = bnf->res ? (bnf->bn_res ? 2 : 1) : 0;
+    p.bnf_relu = bnf->relu;
+    p.bnf_n = (double)gout.B * (double)gout.len * (double)(bnf->bn->count_mul > 1 ? bnf->bn->count_mul : 1);
+    p.out2 = (bf16*)bnf->y_act;
+    p.stats = bnf->bn->sums;
+  }
   const long long rows_in = (long long)gin.B * gin.pitch;
   long long a_inner, a_outer, a_pitch;
   if (stride == 1) {
@@ -1129,6 +1243,28 @@ int ssb_conv1d_fwd_sm100(const void* x, const void* w, void* y, ssb_geom gin, ss
     }
   }
   return run_tn(x, a_inner, a_outer, a_pitch, w, k * gin.C, true, stride == 1 && k == 3, (bf16*)y, p, st);
+}
+
+// same kernel / tile selection as run_tn: can the conv + BN fusion keep every CTA of this conv resident?
+int ssb_conv1d_fwd_bnf_fits_sm100(ssb_geom gin, ssb_geom gout, int k, int stride) {
+  if (gin.C % 64 || gout.C % 64) return 0;
+  const int M = gout.B * gout.pitch, N = gout.C, K = gin.C;
+  const int mt = ceil_div(M, BM);
+  if (stride == 1 && k == 3 && g_tn3 && K >= 128) {
+    int BN = 64;
+    if (N % 256 == 0 && (long long)mt * (N / 256) >= 148) BN = 256;
+    else if (N % 128 == 0) BN = 128;
+    return mt * (N / BN) <= g_num_sms ? 1 : 0;
+  }
+  int occ = 0;
+  if (N % 128 == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<128, TN_STAGES, true, true, false>, NTHREADS,
+                                                      smem_bytes<128 * BK * 2, TN_STAGES>()) != cudaSuccess) return 0;
+    return (long long)mt * (N / 128) <= (long long)occ * g_num_sms ? 1 : 0;
+  }
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<64, TN_STAGES, true, true, false>, NTHREADS,
+                                                    smem_bytes<64 * BK * 2, TN_STAGES>()) != cudaSuccess) return 0;
+  return (long long)mt * (N / 64) <= (long long)occ * g_num_sms ? 1 : 0;
 }
 
 int ssb_conv1d_dgrad_sm100(const void* dy, const void* w, void* dx, ssb_geom gin, ssb_geom gout, int k, int stride,

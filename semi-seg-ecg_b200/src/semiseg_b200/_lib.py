@@ -68,6 +68,8 @@ SIGNATURES = {
     "ssb_conv1d_fwd": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
     "ssb_conv1d_fwd_stats": [_P, _P, _P, Geom, Geom, _I, _I, _P, _I, _I, _P],
     "ssb_conv1d_bn_act_fwd": [_P, _P, _P, Geom, Geom, _I, _I, _BNP, _P, _I, _I, _I, _P],
+    "ssb_conv1d_fwd_bn_train_fits": [Geom, Geom, _I, _I, _I, _I],
+    "ssb_conv1d_fwd_bn_train": [_P, _P, _P, _P, Geom, Geom, _I, _I, _BNP, _P, _BNP, _I, _P, _I, _I, _P],
     "ssb_conv1d_fwd_dual": [_P, _P, _P, _P, Geom, Geom, _I, _I, _I, _P, _BNP, _P, _I, _I, _I, _P],
     "ssb_conv1d_dgrad": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _I, _P],
     "ssb_conv1d_dgrad_bnred": [_P, _P, _P, Geom, Geom, _I, _I, _I, _P, _P, _BNP, _P, _BNP, _I, _I, _P],

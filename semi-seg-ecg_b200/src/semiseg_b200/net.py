@@ -288,7 +288,9 @@ class TrainState:
         self.bwd_sums = tail[lay.n_sums: 2 * lay.n_sums]
         self.loss_sums = tail[2 * lay.n_sums: 2 * lay.n_sums + 4]
         # one grid-barrier counter per BN layer (fused BN backward), zeroed with everything else
-        self.barriers = tail[2 * lay.n_sums + 8: 2 * lay.n_sums + 8 + len(lay.bns)].view(torch.int32)
+        nb = (len(lay.bns) + 1) // 2
+        self.barriers = tail[2 * lay.n_sums + 8: 2 * lay.n_sums + 8 + nb].view(torch.int32)
+        self.fwd_barriers = tail[2 * lay.n_sums + 8 + nb: 2 * lay.n_sums + 8 + 2 * nb].view(torch.int32)
         self.exp_avg = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
         self.step = 0
@@ -335,6 +337,11 @@ class NetPlan:
         self.fuse_reduce = bool(int(os.environ.get("SSB_FUSE_REDUCE", "0")))
         self.fuse_bn_bwd = bool(int(os.environ.get("SSB_FUSE_BN_BWD", "1")))   # reduce + apply in one launch (grid barrier)
         self._fused_ok: Dict[Tuple, bool] = {}
+        # train-mode BN apply inside the conv launch (ssb_conv1d_fwd_bn_train: statistics -> grid barrier -> second pass
+        # over the TMEM accumulator): 21 launches fewer, but measured SLOWER (0.781 vs 0.742 ms/step) -- the barrier plus
+        # the second pass cost what the separate, PDL-overlapped BatchNorm launch cost, on the critical path.  Off.
+        self.fuse_bn_fwd = bool(int(os.environ.get("SSB_FUSE_BN_FWD", "0")))
+        self._bnf_ok: Dict[Tuple, bool] = {}
         self.block_done_hook = None   # callable(block_index) after a block's backward has been enqueued (bucketed all-reduce)
         if algo is None:
             algo = _lib.ALGO_TCGEN05 if self.dtype == _lib.BF16 else _lib.ALGO_SIMT
@@ -380,6 +387,7 @@ class NetPlan:
 
         # ---- BN statistic arenas ----
         self.barriers = state.barriers if state is not None else None
+        self.fwd_barriers = state.fwd_barriers if state is not None else None
         if state is not None:   # statistic arenas inside the step's zero arena (TrainState)
             self.sums, self.bwd_sums = state.sums, state.bwd_sums
         else:
@@ -473,6 +481,25 @@ class NetPlan:
         if self.sync_hook is not None:
             self.sync_hook(self.sums[stats.soff: stats.soff + 2 * stats.C])
 
+    def _conv_bn_train(self, c: ConvDesc, b: BNDesc, x, y_raw, y_act, gin: Geom, gout: Geom, st: int, res=None,
+                       b_res: Optional[BNDesc] = None) -> None:
+        """train mode: y_raw = conv(x) (+ batch statistics), y_act = relu(bn(y_raw) [+ res | + bn_res(res)]).
+        One launch when the conv's tiles are all co-resident (grid barrier + second pass over the TMEM accumulator),
+        else conv(+statistics) followed by the BatchNorm pass."""
+        key = (c.name, gout.B)
+        if key not in self._bnf_ok:
+            self._bnf_ok[key] = bool(self.fuse_bn_fwd and self.sync_hook is None and self.barriers is not None and
+                                     _lib.load().ssb_conv1d_fwd_bn_train_fits(gin, gout, c.k, c.stride, self.dtype, self._algo_for(c)))
+        if self._bnf_ok[key]:
+            call("ssb_conv1d_fwd_bn_train", x.data_ptr(), self.sh.ptr(c), y_raw.data_ptr(), y_act.data_ptr(), gin, gout, c.k,
+                 c.stride, self.bn(b), res.data_ptr() if res is not None else None,
+                 self.bn(b_res) if b_res is not None else None, 1, self.fwd_barriers.data_ptr() + 4 * b.index, self.dtype,
+                 self._algo_for(c), st)
+            return
+        self._conv_fwd(c, x, y_raw, gin, gout, st, b)
+        call("ssb_bn_act_fwd", y_raw.data_ptr(), self.bn(b), res.data_ptr() if res is not None else None,
+             self.bn(b_res) if b_res is not None else None, y_act.data_ptr(), gout, 1, 1, self.dtype, st)
+
     def _conv_bn_act(self, c: ConvDesc, b: BNDesc, x, y, gin: Geom, gout: Geom, res, relu: int, st: int):
         """eval mode: y = [relu](bn_running(conv(x)) [+ res]) in one launch."""
         call("ssb_conv1d_bn_act_fwd", x.data_ptr(), self.sh.ptr(c), y.data_ptr(), gin, gout, c.k, c.stride, self.bn(b),
@@ -526,8 +553,8 @@ class NetPlan:
         call("ssb_memset_zero", self.sums.data_ptr(), self.sums.numel() * 8, st)
         if self.train:
             call("ssb_memset_zero", self.bwd_sums.data_ptr(), self.bwd_sums.numel() * 8, st)
-            if self.barriers is not None:
-                call("ssb_memset_zero", self.barriers.data_ptr(), self.barriers.numel() * 4, st)
+            if self.barriers is not None:   # (the backward and forward barrier counters are adjacent)
+                call("ssb_memset_zero", self.barriers.data_ptr(), (self.barriers.numel() + self.fwd_barriers.numel()) * 4, st)
 
     # ---- forward -------------------------------------------------------------------
     def forward(self, x: torch.Tensor, st: int, train_mode: Optional[bool] = None, zero: bool = True,
@@ -581,23 +608,18 @@ class NetPlan:
                     self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, aux.cuda_stream, bd.bnd)
                     side_done = torch.cuda.Event()
                     side_done.record(aux)
-                self._conv_fwd(bd.conv1, h, bufs["c1"], gin, gout, st, bd.bn1)
-                call("ssb_bn_act_fwd", bufs["c1"].data_ptr(), self.bn(bd.bn1), None, None, bufs["a1"].data_ptr(), gout, 1, t, dt, st)
-                self._conv_fwd(bd.conv2, bufs["a1"], bufs["c2"], gout, gout, st, bd.bn2)
+                self._conv_bn_train(bd.conv1, bd.bn1, h, bufs["c1"], bufs["a1"], gin, gout, st)
                 if bd.convd is not None:
                     if side_done is not None:
                         torch.cuda.current_stream().wait_event(side_done)
                     else:
                         self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st, bd.bnd)
-                    call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), bufs["cd"].data_ptr(), self.bn(bd.bnd),
-                         bufs["out"].data_ptr(), gout, 1, t, dt, st)
+                    self._conv_bn_train(bd.conv2, bd.bn2, bufs["a1"], bufs["c2"], bufs["out"], gout, gout, st, res=bufs["cd"], b_res=bd.bnd)
                 else:
-                    call("ssb_bn_act_fwd", bufs["c2"].data_ptr(), self.bn(bd.bn2), h.data_ptr(), None,
-                         bufs["out"].data_ptr(), gout, 1, t, dt, st)
+                    self._conv_bn_train(bd.conv2, bd.bn2, bufs["a1"], bufs["c2"], bufs["out"], gout, gout, st, res=h)
                 h, gin = bufs["out"], gout
             self.feat = h
-            self._conv_fwd(lay.head_conv, h, self.ch, gin, self.g_head, st, lay.head_bn)
-            call("ssb_bn_act_fwd", self.ch.data_ptr(), self.bn(lay.head_bn), None, None, self.ah.data_ptr(), self.g_head, 1, t, dt, st)
+            self._conv_bn_train(lay.head_conv, lay.head_bn, h, self.ch, self.ah, gin, self.g_head, st)
         p = spec.dropout_ratio if tm else 0.0
         call("ssb_head_cls_fwd", self.ah.data_ptr(), self.w.params.data_ptr() + 4 * lay.cls_w_off,
              self.w.params.data_ptr() + 4 * lay.cls_b_off, self.low.data_ptr(), self.g_head, spec.num_classes,

@@ -276,6 +276,54 @@ def test_conv_dgrad_bnred(cin, cout, k, L, acc, with_res, dtype, algo):
         assert rel_err(r1, r0) < 5e-6
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,L,res_mode", [(64, 64, 3, 1, 625, 1), (64, 128, 3, 2, 625, 0), (128, 128, 3, 1, 313, 2),
+                                                          (256, 256, 3, 1, 157, 1), (512, 128, 3, 1, 79, 0), (128, 256, 1, 2, 313, 0)])
+def test_conv_fwd_bn_train(cin, cout, k, stride, L, res_mode):
+    """train-mode conv + BN(batch stats) [+ residual | + BN(residual)] + ReLU in one launch (grid barrier, second pass over
+    the accumulator) == ssb_conv1d_fwd_stats followed by ssb_bn_act_fwd, including the BatchNorm state it leaves behind"""
+    dtype, algo = _lib.BF16, _lib.ALGO_TCGEN05
+    torch.manual_seed(cin + cout + L)
+    B = 16
+    Lo = (L - 1) // stride + 1
+    po = Lo + 2 + 1
+    pi = stride * po
+    gi, go = Geom(B, pi, L, cin), Geom(B, po, Lo, cout)
+    assert _lib.load().ssb_conv1d_fwd_bn_train_fits(gi, go, k, stride, dtype, algo) == 1
+    x = to_flat(torch.randn(B, cin, L, device=DEV, dtype=torch.float64), pi, dtype)
+    w = tap_major((torch.randn(cout, cin, k, device=DEV) / (cin * k) ** 0.5), dtype)
+    r = to_flat(torch.randn(B, cout, Lo, device=DEV, dtype=torch.float64), po, dtype)
+    res = []
+    for fused in (False, True):
+        torch.manual_seed(99)
+        bn, t = make_bn(cout)
+        bnr, tr_ = make_bn(cout)
+        if res_mode == 2:
+            call("ssb_bn_stats", r.data_ptr(), go, tr_["sums"].data_ptr(), dtype, st())
+        y_raw = torch.full((B * po, cout), 7.0, dtype=TDT[dtype], device=DEV)
+        y_act = torch.full((B * po, cout), 9.0, dtype=TDT[dtype], device=DEV)
+        rp = r.data_ptr() if res_mode else None
+        rb = C.byref(bnr) if res_mode == 2 else None
+        if fused:
+            bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+            call("ssb_conv1d_fwd_bn_train", x.data_ptr(), w.data_ptr(), y_raw.data_ptr(), y_act.data_ptr(), gi, go, k, stride,
+                 C.byref(bn), rp, rb, 1, bar.data_ptr(), dtype, algo, st())
+        else:
+            call("ssb_conv1d_fwd_stats", x.data_ptr(), w.data_ptr(), y_raw.data_ptr(), gi, go, k, stride, t["sums"].data_ptr(),
+                 dtype, algo, st())
+            call("ssb_bn_act_fwd", y_raw.data_ptr(), C.byref(bn), rp, rb, y_act.data_ptr(), go, 1, 1, dtype, st())
+        torch.cuda.synchronize()
+        res.append((y_raw.clone(), y_act.float(), t["rm"].clone(), t["rv"].clone(), t["mi"].clone(), int(t["nbt"][0]),
+                    tr_["rm"].clone(), tr_["mi"].clone()))
+    a_, b_ = res
+    assert torch.equal(a_[0], b_[0])
+    assert rel_err(b_[1], a_[1]) < 1e-2 and float((b_[1] - a_[1]).abs().max()) < 0.05 and halo_is_zero(b_[1], B, po, Lo)
+    assert rel_err(b_[2], a_[2]) < 1e-5 and rel_err(b_[3], a_[3]) < 1e-5 and rel_err(b_[4], a_[4]) < 1e-5 and a_[5] == b_[5] == 1
+    if res_mode == 2:
+        assert rel_err(b_[6], a_[6]) < 1e-5 and rel_err(b_[7], a_[7]) < 1e-5
+    # a conv with more tiles than co-resident CTAs is refused by the query
+    assert _lib.load().ssb_conv1d_fwd_bn_train_fits(Geom(512, 1296, 1250, 128), Geom(512, 1296, 1250, 128), 3, 1, dtype, algo) == 0
+
+
 @pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
 @pytest.mark.parametrize("Cn,res_mode,L", [(64, 0, 625), (128, 1, 313), (512, 2, 79), (24, 1, 50), (8, 2, 33)])
 def test_bn_bwd_fused(dtype, Cn, res_mode, L):
