@@ -287,7 +287,11 @@ class StepEngine:
                 # warm-up run outside capture is NOT done (it would apply an update);
                 # all kernels are capture-safe (no sync, no allocation).
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                # the main chain is captured on a HIGH-priority stream (kernel nodes inherit it): when its kernels
+                # compete for SMs with the wgrad / pseudo-label / shortcut branches, the critical path goes first
+                prio = int(os.environ.get("SSB_MAIN_PRIORITY", "-1"))
+                cap = torch.cuda.Stream(device=self.device, priority=prio) if prio else None
+                with torch.cuda.graph(g, stream=cap, capture_error_mode="thread_local"):
                     self._enqueue()
                 self.graph = g
             self.graph.replay()
