@@ -400,7 +400,9 @@ def run_b200(args):
         "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic LUDB-shaped strips (z-scored Gaussian, 4-class piecewise labels), random-init weights",
         "config": {"workload": args.workload, "algorithm": algo, "per_gpu_batch": f"{Bl}+{Bu}", "leads": C, "length": L,
-                   "parallelism": f"dp{world}", "sync_bn": bool(model.sync_bn), "cuda_graph": not args.no_graph,
+                   "parallelism": f"dp{world}", "sync_bn": bool(model.sync_bn),
+                   "sync_bn_exchange": ("peer-memory kernel" if getattr(eng, "syncbn_p2p", False) else "nccl") if model.sync_bn else None,
+                   "cuda_graph": not args.no_graph,
                    "l2_policy": f"no explicit flush: per-step working set {ws / 2**20:.0f} MiB (activations + param/grad/Adam arenas) "
                                 "vs 126 MB L2; inputs rotate over 4 distinct batches"},
         "e2e": {"value": round(e2e, 1), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes(), "d2h_bytes_per_step": 32,

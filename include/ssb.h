@@ -290,6 +290,18 @@ int ssb_ema_i64(float* dst, const int64_t* src, size_t n, const ssb_step_params*
 /* out[0] = sqrt(sum g^2) (misc.py:265-278); ws: fp64[1] zeroed by the caller */
 int ssb_grad_norm(const float* g, size_t n, double* ws, float* out, ssb_stream_t stream);
 
+/* ---- SyncBatchNorm statistics exchange over NVLink peer memory (fixmatch.py:290-291) ----------------
+ * Replaces the per-layer NCCL collectives of torch's SyncBatchNorm by one small kernel per exchange: every rank
+ * stores its slice of the statistic arena into a slot of every peer's mailbox as self-validating 8-byte words
+ * {32 payload bits, exchange number}, polls the words arriving in its own mailbox and sums the ranks' slices in
+ * rank order (bitwise identical on all ranks): one NVLink hop, no fence, no flag round trip.
+ * peers_dev: device array of `world` base addresses of the ranks' mailboxes (a symmetric allocation of
+ * ssb_syncbn_mailbox_bytes(slot_doubles) bytes, zero-initialised; mapped into this process, e.g. with
+ * torch.distributed._symmetric_memory or CUDA IPC).  All ranks must issue the same sequence of exchanges. */
+size_t ssb_syncbn_mailbox_bytes(int slot_doubles);
+int ssb_syncbn_exchange(double* slice, int n, const uint64_t* peers_dev, int world, int rank,
+                        int slot_doubles, ssb_stream_t stream);
+
 /* ---- GPU-resident augmentation (utils/semi_dataset.py:193-197, 235-242) ---------
  * Strips are [B, C, L] fp32 (the reference's item layout, batched); per-strip draws live in small
  * device arrays filled by the host. */

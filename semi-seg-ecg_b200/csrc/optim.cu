@@ -140,3 +140,90 @@ int ssb_grad_norm(const float* g, size_t n, double* ws, float* out, ssb_stream_t
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------
+// SyncBatchNorm statistics exchange over NVLink peer memory (replaces one small NCCL all-reduce per BN
+// layer and direction: torch SyncBatchNorm's all_gather of (mean, invstd, count) / all_reduce of the
+// backward sums, fixmatch.py:290-291).  Every rank owns a symmetric mailbox; one block per rank
+//   1. stores its slice into slot [parity][rank] of every peer's mailbox as self-validating 8-byte words
+//      {32 payload bits, exchange number} (two per double) -- no fence, no separate flag round trip,
+//   2. polls the words arriving in ITS OWN mailbox until they carry this exchange's number, and
+//   3. replaces its slice by the sum of all ranks' slices in rank order (bitwise identical on every rank).
+// Two parities: a rank can be at most one exchange ahead of a peer (it cannot finish exchange k+1 before the peer
+// has sent k+1, which the peer does only after it has finished reading k), so slot reuse never races.
+// ---------------------------------------------------------------------------------------
+#define SBX_MAX_WORLD 16
+#define SBX_HDR_BYTES 4096          // [0] exchange counter, [64] error word
+
+__device__ __forceinline__ void sbx_store(uint2* p, uint32_t payload, uint32_t epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 sbx_load(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) syncbn_exchange_kernel(double* __restrict__ slice, int n, const unsigned long long* __restrict__ peers,
+                                                              int world, int rank, int slot_doubles) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ unsigned int s_epoch;
+  char* mine = reinterpret_cast<char*>(peers[rank]);
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(mine);
+    s_epoch = *counter + 1;
+    *counter = s_epoch;
+  }
+  __syncthreads();
+  const unsigned int epoch = s_epoch;
+  const size_t slot_words = (size_t)slot_doubles * 2;                       // 8-byte words per slot
+  const size_t par_off = (size_t)(epoch & 1u) * SBX_MAX_WORLD * slot_words;
+  const uint2* mail = reinterpret_cast<const uint2*>(mine + SBX_HDR_BYTES) + par_off;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double mineval = slice[i];
+    const uint32_t lo = (uint32_t)__double2loint(mineval), hi = (uint32_t)__double2hiint(mineval);
+    for (int r = 0; r < world; ++r) {                                       // 1. my value into every peer's slot [rank]
+      if (r == rank) continue;
+      uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<char*>(peers[r]) + SBX_HDR_BYTES) + par_off + (size_t)rank * slot_words + 2 * i;
+      sbx_store(dst, lo, epoch);
+      sbx_store(dst + 1, hi, epoch);
+    }
+    double t = 0.0;
+    const long long t0 = clock64();
+    for (int r = 0; r < world; ++r) {                                       // 2./3. the peers' values, summed in rank order
+      if (r == rank) { t += mineval; continue; }
+      const uint2* src = mail + (size_t)r * slot_words + 2 * i;
+      uint2 a, b;
+      do {
+        a = sbx_load(src);
+        b = sbx_load(src + 1);
+        if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer is gone -- record it and go on rather than hang the GPU
+          *reinterpret_cast<unsigned int*>(mine + 64) = epoch;
+          break;
+        }
+      } while (a.y != epoch || b.y != epoch);
+      t += __hiloint2double((int)b.x, (int)a.x);
+    }
+    slice[i] = t;
+  }
+}
+
+extern "C" {
+
+size_t ssb_syncbn_mailbox_bytes(int slot_doubles) {
+  return (size_t)SBX_HDR_BYTES + (size_t)2 * SBX_MAX_WORLD * (size_t)slot_doubles * 16;   // two {payload, number} words per double
+}
+
+int ssb_syncbn_exchange(double* slice, int n, const uint64_t* peers_dev, int world, int rank, int slot_doubles,
+                        ssb_stream_t stream) {
+  SSB_REQUIRE(slice && peers_dev, "ssb_syncbn_exchange: null pointer");
+  SSB_REQUIRE(world >= 2 && world <= SBX_MAX_WORLD && rank >= 0 && rank < world, "ssb_syncbn_exchange: bad world %d / rank %d", world, rank);
+  SSB_REQUIRE(n > 0 && n <= slot_doubles, "ssb_syncbn_exchange: slice of %d doubles does not fit the %d-double slots", n, slot_doubles);
+  ssb_launch_pro(syncbn_exchange_kernel, dim3(1), dim3(256), 0, to_stream(stream), slice, n,
+             reinterpret_cast<const unsigned long long*>(peers_dev), world, rank, slot_doubles);
+  SSB_LAUNCH_CHECK("ssb_syncbn_exchange");
+  return SSB_OK;
+}
+
+}  // extern "C"

@@ -94,11 +94,13 @@ SIGNATURES = {
     "ssb_ema": [_P, _P, _SZ, _P, _P],
     "ssb_ema_i64": [_P, _P, _SZ, _P, _P],
     "ssb_grad_norm": [_P, _SZ, _P, _P, _P],
+    "ssb_syncbn_mailbox_bytes": [_I],
+    "ssb_syncbn_exchange": [_P, _I, _P, _I, _I, _I, _P],
     "ssb_aug_spectrum": [_P, _P, _P, _I, _I, _I, _P],
     "ssb_aug_resize_crop": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ssb_aug_strong_standardize": [_P, _P, _P, _I, _P, _P, C.c_uint32, _P, _I, _I, _I, _I, _F, _P],
 }
-_RESTYPES = {"ssb_last_error": C.c_char_p, "ssb_launch_count": C.c_int64}
+_RESTYPES = {"ssb_last_error": C.c_char_p, "ssb_launch_count": C.c_int64, "ssb_syncbn_mailbox_bytes": C.c_size_t}
 
 _lib: Optional[C.CDLL] = None
 

@@ -123,10 +123,10 @@ class StepEngine:
                 self.bufs_snap = torch.empty_like(weights.bufs)
             self.plan_t = NetPlan(tw, dtype, self.Bu, L, False, algo, bufs=self.bufs_snap)
         if self.sync_bn:
-            # SyncBatchNorm (fixmatch.py:290-291): statistic arenas are all-reduced layer by layer
+            # SyncBatchNorm (fixmatch.py:290-291): statistic arenas are exchanged layer by layer
             for s in self.plan_s._bn_structs.values():
                 s.count_mul = self.world
-            self.plan_s.sync_hook = lambda t: torch.distributed.all_reduce(t, group=self.pg)
+            self.plan_s.sync_hook = self._make_sync_hook()
         self.mat = None
         if materialize and self.mode == _lib.LOSS_FIXMATCH:
             self.mat = {"conf": torch.zeros(self.Bu, L, dtype=torch.float32, device=dev),
@@ -142,6 +142,41 @@ class StepEngine:
         self.wd = float(train_cfg.get("weight_decay", 0.0))
         if train_cfg.get("optimizer", "adamw") != "adamw":
             raise NotImplementedError("the fused optimizer kernel implements AdamW (all shipped configs)")
+
+    def _make_sync_hook(self):
+        """Statistics exchange of one SyncBN slice.  Preferred: our own kernel over NVLink peer memory (a symmetric
+        mailbox mapped with torch's symmetric-memory allocator) -- one ~5 us launch instead of an ~11 us NCCL
+        all-reduce, 42 times per step.  If the peer mapping cannot be set up: NCCL (SSB_SYNCBN_P2P=0 forces it)."""
+        nccl = lambda t: torch.distributed.all_reduce(t, group=self.pg)   # noqa: E731
+        self.syncbn_p2p = False
+        if not int(os.environ.get("SSB_SYNCBN_P2P", "1")) or self.world < 2 or self.world > 16:
+            return nccl
+        lay = self.plan_s.lay
+        slot = max(2 * b.C for b in lay.bns) * 2 + 2 * 64    # two adjacent BN slices (block output BN + shortcut BN)
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = int(_lib.load().ssb_syncbn_mailbox_bytes(slot))
+            box = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            box.zero_()
+            hdl = symm_mem.rendezvous(box, self.pg if self.pg is not None else torch.distributed.group.WORLD)
+            ptrs = [int(p_) for p_ in hdl.buffer_ptrs]
+            assert len(ptrs) == self.world and ptrs[hdl.rank] == box.data_ptr()
+            torch.cuda.synchronize()
+            torch.distributed.barrier(group=self.pg)
+        except Exception as e:   # no peer access / allocator not available: keep the NCCL path
+            import warnings
+            warnings.warn(f"SyncBN peer-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+            return nccl
+        self._mailbox, self._mail_hdl = box, hdl
+        self._peers_dev = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        rank = hdl.rank
+        self.syncbn_p2p = True
+
+        def hook(t: torch.Tensor):
+            assert t.dtype == torch.float64 and t.numel() <= slot
+            call("ssb_syncbn_exchange", t.data_ptr(), t.numel(), self._peers_dev.data_ptr(), self.world, rank, slot,
+                 torch.cuda.current_stream().cuda_stream)
+        return hook
 
     # ---- data ----------------------------------------------------------------------
     def load_batch(self, ecg_x: torch.Tensor, mask_x: torch.Tensor, ecg_u_w: Optional[torch.Tensor] = None,
