@@ -691,6 +691,35 @@ def test_adamw_ema_matches_oracle():
     assert abs(float(out) - float(g.double().norm())) < 1e-4 * float(g.double().norm())
 
 
+def test_syncbn_exchange_single_gpu():
+    """ssb_syncbn_exchange with two mailboxes on ONE GPU: the peer's words are pre-filled (nothing waits on another
+    kernel), so the launch must (a) deposit this rank's slice in the peer's mailbox in the wire format and (b) replace
+    its slice by the rank-ordered sum."""
+    lib = _lib.load()
+    n, slot, world = 200, 256, 2
+    nbytes = int(lib.ssb_syncbn_mailbox_bytes(slot))
+    box = [torch.zeros(nbytes, dtype=torch.uint8, device=DEV) for _ in range(world)]
+    peers = torch.tensor([b.data_ptr() for b in box], dtype=torch.int64, device=DEV)
+    torch.manual_seed(3)
+    mine = torch.randn(n, dtype=torch.float64, device=DEV)
+    theirs = torch.randn(n, dtype=torch.float64, device=DEV)
+    epoch = 1
+    # wire format: per double two 8-byte words {lo32, epoch}, {hi32, epoch}; parity = epoch & 1; slot of the sender rank
+    words = torch.zeros(n, 4, dtype=torch.int32, device=DEV)
+    raw = theirs.view(torch.int32).view(n, 2)
+    words[:, 0], words[:, 1], words[:, 2], words[:, 3] = raw[:, 0], epoch, raw[:, 1], epoch
+    off = 4096 + ((epoch & 1) * 16 + 1) * slot * 16          # rank 0's mailbox, slot of rank 1
+    box[0][off: off + n * 16] = words.view(torch.uint8).flatten()
+    sl = mine.clone()
+    call("ssb_syncbn_exchange", sl.data_ptr(), n, peers.data_ptr(), world, 0, slot, st())
+    torch.cuda.synchronize()
+    assert torch.equal(sl, mine + theirs)
+    off1 = 4096 + ((epoch & 1) * 16 + 0) * slot * 16         # rank 1's mailbox, slot of rank 0
+    got = box[1][off1: off1 + n * 16].view(torch.int32).view(n, 4)
+    assert torch.equal(got[:, [0, 2]].contiguous().view(torch.float64).flatten(), mine) and bool((got[:, [1, 3]] == epoch).all())
+    assert int(box[0][:4].view(torch.int32)[0]) == 1 and int(box[0][64:68].view(torch.int32)[0]) == 0   # counter, no timeout
+
+
 def test_errors_are_reported():
     lib = _lib.load()
     g = Geom(1, 4, 8, 8)   # pitch < len + 2
