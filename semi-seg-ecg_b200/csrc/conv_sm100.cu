@@ -25,7 +25,10 @@ namespace {
 constexpr int BM = 128;          // UMMA_M
 constexpr int BK = 64;           // bf16 elements per 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 2;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 192;      // wgrad kernels: TMA warp, MMA warp, 4 epilogue warps
+constexpr int TN_THREADS = 320;    // fprop / dgrad kernels: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant,
+                                   // each owning one half of the tile's columns)
+constexpr int EPI_THREADS = 256;
 
 // ---- PTX wrappers ------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -216,19 +219,25 @@ template <int BN, bool STATS, bool EPI, int RED = 0>
 __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict__ out, uint32_t tmem_base, uint64_t* done,
                                           uint32_t done_parity, uint64_t* release, float* ep_scale, float* scratch, int m0,
                                           int n0, int warp, int lane) {
-  // epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
+  // epilogue warps 2..9: warp w may only touch TMEM lanes 32*(w%4) .. +31; the two warps of a lane quadrant split the
+  // tile's columns in halves
   const int q = warp & 3;
+  const int wq = warp - 2;                 // 0..7
+  const int half = wq >> 2;
+  constexpr int CH = BN / 2;               // columns per half (a multiple of 32)
+  const int cbeg = half * CH, cend = cbeg + CH;
+  const int e = wq * 32 + lane;            // 0..255
   float* ep_shift = ep_scale + BN;
   if (EPI) {   // eval-mode BN coefficients of this CTA's columns, computed while the main loop runs
-    for (int col = q * 32 + lane; col < BN; col += 128) {
+    for (int col = e; col < BN; col += EPI_THREADS) {
       const float sc = p.ep_gamma[n0 + col] * (1.0f / sqrtf(p.ep_var[n0 + col] + 1e-5f));
       ep_scale[col] = sc;
       ep_shift[col] = p.ep_beta[n0 + col] - p.ep_mean[n0 + col] * sc;
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   }
   if (RED) {   // saved mean / invstd of this CTA's columns (ep_scale area: mean, inv, [mean_r, inv_r])
-    for (int col = q * 32 + lane; col < BN; col += 128) {
+    for (int col = e; col < BN; col += EPI_THREADS) {
       ep_scale[col] = p.red_mi[n0 + col];
       ep_scale[BN + col] = p.red_mi[p.N + n0 + col];
       if (RED == 2) {
@@ -236,7 +245,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
         ep_scale[3 * BN + col] = p.red_mi_r[p.N + n0 + col];
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
   }
   mbar_wait(done, done_parity);
   tc_fence_after();
@@ -251,7 +260,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
   // all MMAs have retired: the operand stages are free, stage 0 of A is reused as reduction scratch
   float* red = scratch;   // [4 warps][2][BN]
 #pragma unroll 1
-  for (int c = 0; c < BN; c += 32) {
+  for (int c = cbeg; c < cend; c += 32) {
     uint32_t r[32];
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
     tmem_ld_wait();
@@ -323,7 +332,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
         }
       }
       warp_transpose_sum(t, lane);
-      red[(q * 3 + 0) * 32 + lane] = t[0];
+      red[half * 384 + (q * 3 + 0) * 32 + lane] = t[0];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         float fx[8];
@@ -337,7 +346,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
           t[v * 8 + i] = valid ? sv[v * 8 + i] * ((fx[i] - ep_scale[c + v * 8 + i]) * ep_scale[BN + c + v * 8 + i]) : 0.f;
       }
       warp_transpose_sum(t, lane);
-      red[(q * 3 + 1) * 32 + lane] = t[0];
+      red[half * 384 + (q * 3 + 1) * 32 + lane] = t[0];
       if (RED == 2) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
@@ -352,14 +361,15 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
             t[v * 8 + i] = valid ? sv[v * 8 + i] * ((fx[i] - ep_scale[2 * BN + c + v * 8 + i]) * ep_scale[3 * BN + c + v * 8 + i]) : 0.f;
         }
         warp_transpose_sum(t, lane);
-        red[(q * 3 + 2) * 32 + lane] = t[0];
+        red[half * 384 + (q * 3 + 2) * 32 + lane] = t[0];
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = q * 32 + lane;
-      if (e < 32 * (RED == 2 ? 3 : 2)) {
-        const int which = e >> 5, col = e & 31;
-        const float a = (red[(0 * 3 + which) * 32 + col] + red[(1 * 3 + which) * 32 + col]) +
-                        (red[(2 * 3 + which) * 32 + col] + red[(3 * 3 + which) * 32 + col]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int eh = q * 32 + lane;   // 0..127 inside this column half
+      if (eh < 32 * (RED == 2 ? 3 : 2)) {
+        const int which = eh >> 5, col = eh & 31;
+        const float* rh = red + half * 384;
+        const float a = (rh[(0 * 3 + which) * 32 + col] + rh[(1 * 3 + which) * 32 + col]) +
+                        (rh[(2 * 3 + which) * 32 + col] + rh[(3 * 3 + which) * 32 + col]);
         const int gc = n0 + c + col;
         if (which == 0) {
           atomicAdd(&p.red_sums[gc], (double)a);
@@ -370,7 +380,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
           atomicAdd(&p.red_sums_r[p.N + gc], (double)a);
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (STATS) {
       float sq[32];
@@ -388,9 +398,8 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
     mbar_arrive(release);
   }
   if (STATS) {
-    asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
-    const int e = q * 32 + lane;
-    for (int col = e; col < BN; col += 128) {
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
+    for (int col = e; col < BN; col += EPI_THREADS) {
       float a = 0.f, b = 0.f;
 #pragma unroll
       for (int w = 0; w < 4; ++w) {
@@ -403,7 +412,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
     if (bnf) {
       // ---- train-mode BatchNorm apply fused in: wait until every tile of this launch has added its statistics ----
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (e == 0) {
         atomicAdd(p.bnf_barrier, 1u);
         unsigned int v;
@@ -411,11 +420,11 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.bnf_barrier) : "memory");
         } while (v < p.bnf_expected);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       // per-column coefficients (one thread per column does the fp64 part); the first row tile of each column
       // tile updates the running statistics and saves mean / invstd for the backward
       const bool writer = m0 == 0;
-      for (int col = e; col < BN; col += 128) {
+      for (int col = e; col < BN; col += EPI_THREADS) {
         float sc, sh;
         bn_coeffs(p.bnf, n0 + col, p.N, 1, 1.0 / p.bnf_n, p.bnf_n, writer, sc, sh);
         ep_scale[col] = sc;
@@ -426,10 +435,10 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
           ep_scale[3 * BN + col] = sh;
         }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       bf16* optr2 = p.out2 + (size_t)(in_range ? orow : 0) * p.N + n0;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = cbeg; c < cend; c += 32) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
         tmem_ld_wait();
@@ -477,7 +486,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
 // fprop / dgrad
 // ---------------------------------------------------------------------------------------------
 template <int BN, int STAGES, bool STATS, bool B_MN, bool EPI, int RED = 0>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(TN_THREADS, 1)
 conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
                const TnParams p) {
   constexpr int B_BYTES = BN * BK * 2;
@@ -567,14 +576,14 @@ constexpr int A3_SLOTS = 3;
 template <int BN> __host__ __device__ constexpr int b3_slots() { return BN == 256 ? 5 : (BN == 128 ? 8 : 9); }
 template <int BN> constexpr int smem3_bytes() {
   return A3_SLOTS * A3_BYTES + b3_slots<BN>() * BN * 128 + (2 * A3_SLOTS + 2 * b3_slots<BN>() + 4) * 8 + 16 + 4 * BN * 4 +
-         8 * BN * 4 + 1024;
+         (8 * BN < 768 ? 768 : 8 * BN) * 4 + 1024;
 }
 
 // PERSISTENT: gridDim.x CTAs walk the tile list (m fastest, so that CTAs running together share the weight
 // tiles in L2); the accumulator is double-buffered in TMEM (2 x BN columns), so the MMAs of tile i+1 run under
 // the epilogue of tile i; the TMA producer runs ahead across tile boundaries through the same rings.
 template <int BN, bool STATS, bool B_MN, bool EPI, int RED = 0>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(TN_THREADS, 1)
 conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, bf16* __restrict__ out,
                 const TnParams p) {
   constexpr int B_BYTES = BN * BK * 2;
@@ -588,7 +597,7 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* b_full = a_empty + A3_SLOTS;
   uint64_t* b_empty = b_full + NB;
   uint64_t* t_full = b_empty + NB;      // [2] accumulator buffer complete (MMA -> epilogue)
-  uint64_t* t_empty = t_full + 2;       // [2] accumulator buffer drained (epilogue -> MMA), 128 arrivals
+  uint64_t* t_empty = t_full + 2;       // [2] accumulator buffer drained (epilogue -> MMA), one arrival per epilogue thread
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
   float* ep_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [4 * BN] per-column coefficients
   float* red = ep_scale + 4 * BN;                               // [4][2][BN] statistics scratch
@@ -598,7 +607,7 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < A3_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], EPI_THREADS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<2 * BN>(tmem_slot);
@@ -673,7 +682,7 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int buf = it & 1;
       const int m0 = (t % MT) * BM, n0 = (t / MT) * BN;
-      if (it > 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's scratch / coefficient readers are done
+      if (it > 0) asm volatile("bar.sync 1, 256;" ::: "memory");   // previous tile's scratch / coefficient readers are done
       tn_epilogue<BN, STATS, EPI, RED>(p, out, tmem_base + (uint32_t)(buf * BN), &t_full[buf], ((uint32_t)(it >> 1)) & 1u,
                                   &t_empty[buf], ep_scale, red, m0, n0, warp, lane);
     }
@@ -993,16 +1002,16 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
   dim3 grid(ceil_div(p.M, BM), p.N / BN);
   if (p.ep_gamma && p.stats) {
     if constexpr (B_MN)
-      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, true>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
   } else if (p.ep_gamma) {
     if constexpr (B_MN)
-      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, true, true>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
   } else if (p.stats) {
     if constexpr (B_MN) {
       TnParams q = p;
       if (p.bnf_barrier) {   // grid-wide barrier inside: every CTA of the launch must be resident at once
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<BN, TN_STAGES, true, true, false>, NTHREADS, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<BN, TN_STAGES, true, true, false>, TN_THREADS, smem) != cudaSuccess)
           occ = 0;
         q.bnf_expected = grid.x * grid.y;
         if ((long long)q.bnf_expected > (long long)occ * g_num_sms) {
@@ -1010,17 +1019,17 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
           return SSB_ERR_UNSUPPORTED;
         }
       }
-      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, q);
+      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, q);
     }
   } else if (p.red_sums) {
     if constexpr (!B_MN) {
       if (p.red_xr)
-        ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, false, false, 2>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+        ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, false, false, 2>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
       else
-        ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, false, false, 1>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+        ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, false, false, 1>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
     }
   } else {
-    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, B_MN, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+    ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, false, B_MN, false>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
   }
   SSB_LAUNCH_CHECK("conv_tn_kernel");
   return SSB_OK;
@@ -1033,10 +1042,10 @@ int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const 
   dim3 grid(ntiles < g_num_sms ? ntiles : g_num_sms);
   if (p.ep_gamma && p.stats) {
     if constexpr (B_MN)
-      ssb_launch_pro(conv_tn3_kernel<BN, true, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+      ssb_launch_pro(conv_tn3_kernel<BN, true, true, true>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
   } else if (p.ep_gamma) {
     if constexpr (B_MN)
-      ssb_launch_pro(conv_tn3_kernel<BN, false, true, true>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+      ssb_launch_pro(conv_tn3_kernel<BN, false, true, true>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
   } else if (p.stats) {
     if constexpr (B_MN) {
       TnParams q = p;
@@ -1047,17 +1056,17 @@ int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const 
           return SSB_ERR_UNSUPPORTED;
         }
       }
-      ssb_launch_pro(conv_tn3_kernel<BN, true, true, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, q);
+      ssb_launch_pro(conv_tn3_kernel<BN, true, true, false>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, q);
     }
   } else if (p.red_sums) {
     if constexpr (!B_MN) {
       if (p.red_xr)
-        ssb_launch_pro(conv_tn3_kernel<BN, false, false, false, 2>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+        ssb_launch_pro(conv_tn3_kernel<BN, false, false, false, 2>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
       else
-        ssb_launch_pro(conv_tn3_kernel<BN, false, false, false, 1>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+        ssb_launch_pro(conv_tn3_kernel<BN, false, false, false, 1>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
     }
   } else {
-    ssb_launch_pro(conv_tn3_kernel<BN, false, B_MN, false>, dim3(grid), dim3(NTHREADS), smem, st, tmA, tmB, out, p);
+    ssb_launch_pro(conv_tn3_kernel<BN, false, B_MN, false>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, p);
   }
   SSB_LAUNCH_CHECK("conv_tn3_kernel");
   return SSB_OK;
@@ -1258,11 +1267,11 @@ int ssb_conv1d_fwd_bnf_fits_sm100(ssb_geom gin, ssb_geom gout, int k, int stride
   }
   int occ = 0;
   if (N % 128 == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<128, TN_STAGES, true, true, false>, NTHREADS,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<128, TN_STAGES, true, true, false>, TN_THREADS,
                                                       smem_bytes<128 * BK * 2, TN_STAGES>()) != cudaSuccess) return 0;
     return (long long)mt * (N / 128) <= (long long)occ * g_num_sms ? 1 : 0;
   }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<64, TN_STAGES, true, true, false>, NTHREADS,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<64, TN_STAGES, true, true, false>, TN_THREADS,
                                                     smem_bytes<64 * BK * 2, TN_STAGES>()) != cudaSuccess) return 0;
   return (long long)mt * (N / 64) <= (long long)occ * g_num_sms ? 1 : 0;
 }
