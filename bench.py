@@ -322,6 +322,23 @@ def run_b200(args):
     e2e = per_step * world * args.steps / (ms_e2e / 1e3)
     assert all(np.isfinite(s["loss_total"]) for s in stats_dev + stats_e2e), "non-finite loss in the timed region"
 
+    # ---- SyncBN on (the reference YAML's default, ddp.sync_bn: true): same timed loop, reported next to the headline ----
+    syncbn_on = None
+    if world > 1 and not model.sync_bn and not args.no_syncbn_extra:
+        model.sync_bn = True
+        eng_sb = get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=not args.no_graph)
+        model.sync_bn = False
+        eng_main, eng = eng, eng_sb
+        for i in range(max(args.warmup, 3)):
+            step_from(devb[i % pool])
+        eng.read_stats()
+        ms_sb, stats_sb = timed(devb, args.steps, False)
+        eng = eng_main
+        syncbn_on = {"value": round(per_step * world * args.steps / (ms_sb / 1e3), 1), "unit": "samples/s",
+                     "ms_per_step": round(ms_sb / args.steps, 4),
+                     "exchange": "peer-memory kernel" if getattr(eng_sb, "syncbn_p2p", False) else "nccl",
+                     "finite": bool(all(np.isfinite(s_["loss_total"]) for s_ in stats_sb))}
+
     # ---- per-kernel timing pass: every distinct launch of the step, steady state, on its launch stream ----
     roof, top, fams, large = None, [], [], None
     if rank == 0 or world > 1:   # (every rank takes part when the step contains collectives)
@@ -419,6 +436,8 @@ def run_b200(args):
         line["large_batch_roofline"] = large
     if aug is not None:
         line["gpu_augmentation"] = aug
+    if syncbn_on is not None:
+        line["sync_bn_on"] = syncbn_on
     print(json.dumps(line), flush=True)
     _finish(world)
 
@@ -550,6 +569,7 @@ def main():
                     "0: per-rank BN (ddp.sync_bn: false)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-syncbn-extra", action="store_true", help="N>1: skip the extra timed pass with SyncBN on")
     ap.add_argument("--no-aug", action="store_true", help="skip the supplementary GPU-augmentation measurement")
     ap.add_argument("--no-large", action="store_true", help="skip the supplementary large-batch roofline block")
     ap.add_argument("--profile-mode", action="store_true", help="warm-up + K plain steps only (for ncu)")

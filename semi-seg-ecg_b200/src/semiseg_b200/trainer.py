@@ -43,7 +43,7 @@ def get_engine(algorithm: str, model, teacher, Bl: int, Bu: int, L: int, dtype: 
     if algorithm == "mean_teacher":
         rt_t = teacher.runtime(nbt_float=True)
         rt_t.ensure()
-    key = (algorithm, Bl, Bu, L, dtype, use_graph, algo, id(rt_t))
+    key = (algorithm, Bl, Bu, L, dtype, use_graph, algo, id(rt_t), bool(getattr(model, "sync_bn", False)))
     eng = rt.engines.get(key)
     if eng is None:
         pg = dist.group.WORLD if (dist.is_available() and dist.is_initialized() and
