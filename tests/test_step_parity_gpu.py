@@ -404,3 +404,40 @@ def test_train_one_epoch_surface(golden):
         assert set(stats) == {"lr", "loss_total", "loss_x", "loss_u_s", "mask_ratio"}
         assert all(np.isfinite(v) for v in stats.values())
     assert int(model.state_dict()["backbone.stem.1.num_batches_tracked"]) == 8
+
+
+@pytest.mark.parametrize("env", [{"SSB_MULTI_STREAM": "0"},                       # single stream -> merged train+eval conv launches
+                                 {"SSB_MERGED_EVAL": "1"},                         # merged launches inside the multi-branch graph
+                                 {"SSB_FUSE_REDUCE": "1"},                         # BN-backward reduce in the dgrad epilogue
+                                 {"SSB_FUSE_BN_FWD": "1"},                         # train-mode BN apply inside the conv launch
+                                 {"SSB_FUSE_BN_BWD": "0"},                         # two-launch BN backward
+                                 {"SSB_MAIN_PRIORITY": "0", "SSB_BUCKETS": "0"}])
+def test_step_variants_agree(golden, env, monkeypatch):
+    """Every optional schedule / fusion of the step (defaults and the measured-slower alternatives) computes the same
+    FixMatch update: full-size resnet18, bf16 tcgen05 path, one graph-replayed step from the same seeded state (one step:
+    train-mode-BN gradients at B=4 amplify any rounding difference of the first update by tens of percent)."""
+    from algorithms.base import init_model_from_cfg
+    cfg = dict(TRAIN_CFG, conf_thresh=0.3)
+    data = batches(500, 1, 2, 2, 1, 2500)
+
+    def run():
+        torch.manual_seed(0)
+        model = init_model_from_cfg(model_cfg(1, 64, 64, 128, 0.0)).to(DEV)
+        eng = get_engine("fixmatch", model, None, 2, 2, 2500, _lib.BF16, cfg, use_graph=True)
+        for lab, unl in data:
+            eng.load_batch(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"])
+            eng.step(5e-4)
+        stats = eng.read_stats()
+        grads = {n: v.clone() for n, v in model.runtime().weights.param_views(model.runtime().state.grads).items()}
+        return stats, grads, {k: v.clone() for k, v in model.state_dict().items()}
+
+    base_stats, base_grads, base_sd = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    stats, grads, sd = run()
+    for a, b in zip(stats, base_stats):
+        assert abs(a["loss_total"] - b["loss_total"]) < 2e-3 and abs(a["mask_ratio"] - b["mask_ratio"]) < 5e-3, (a, b)
+    # same arithmetic up to summation order / one bf16 rounding less: gradients of the last step agree closely
+    errs = sorted(((rel_err(grads[n], base_grads[n]), n) for n in base_grads), reverse=True)
+    assert errs[0][0] < 2e-2, errs[:3]
+    assert all(torch.isfinite(v.float()).all() for v in sd.values())
