@@ -324,7 +324,7 @@ def run_b200(args):
 
     # ---- SyncBN on (the reference YAML's default, ddp.sync_bn: true): same timed loop, reported next to the headline ----
     syncbn_on = None
-    if world > 1 and not model.sync_bn and not args.no_syncbn_extra:
+    if world > 1 and not model.sync_bn and args.syncbn_extra:
         model.sync_bn = True
         eng_sb = get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=not args.no_graph)
         model.sync_bn = False
@@ -569,7 +569,8 @@ def main():
                     "0: per-rank BN (ddp.sync_bn: false)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-syncbn-extra", action="store_true", help="N>1: skip the extra timed pass with SyncBN on")
+    ap.add_argument("--syncbn-extra", action="store_true", help="N>1: also time the step with SyncBN on (reference YAML "
+                    "default) after the headline measurement and report it as sync_bn_on")
     ap.add_argument("--no-aug", action="store_true", help="skip the supplementary GPU-augmentation measurement")
     ap.add_argument("--no-large", action="store_true", help="skip the supplementary large-batch roofline block")
     ap.add_argument("--profile-mode", action="store_true", help="warm-up + K plain steps only (for ncu)")

@@ -219,6 +219,11 @@ template <int BN, bool STATS, bool EPI, int RED = 0>
 __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict__ out, uint32_t tmem_base, uint64_t* done,
                                           uint32_t done_parity, uint64_t* release, float* ep_scale, float* scratch, int m0,
                                           int n0, int warp, int lane) {
+  // RED template parameter: 0 none, 1 / 2 = BN-backward reduce of the produced gradient (2: + residual BN), 3 = BNF, the
+  // train-mode BatchNorm apply pass fused behind the statistics (compiled only into the variants that use it, so that
+  // the default kernels stay small)
+  constexpr bool REDC = RED == 1 || RED == 2;
+  constexpr bool BNFC = RED == 3;
   // epilogue warps 2..9: warp w may only touch TMEM lanes 32*(w%4) .. +31; the two warps of a lane quadrant split the
   // tile's columns in halves
   const int q = warp & 3;
@@ -236,7 +241,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
   }
-  if (RED) {   // saved mean / invstd of this CTA's columns (ep_scale area: mean, inv, [mean_r, inv_r])
+  if (REDC) {   // saved mean / invstd of this CTA's columns (ep_scale area: mean, inv, [mean_r, inv_r])
     for (int col = e; col < BN; col += EPI_THREADS) {
       ep_scale[col] = p.red_mi[n0 + col];
       ep_scale[BN + col] = p.red_mi[p.N + n0 + col];
@@ -298,7 +303,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
         Vec<bf16> o;
         o.set(f);
         dst[v] = o.raw;
-        if (RED) o.get(&sv[v * 8]);   // the gradient as stored
+        if (REDC) o.get(&sv[v * 8]);   // the gradient as stored
         if (STATS) {   // statistics of the values as stored (train rows only)
           if (DUAL && eval_row) {
 #pragma unroll
@@ -308,11 +313,11 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
           }
         }
       }
-    } else if (STATS || RED) {
+    } else if (STATS || REDC) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) sv[i] = 0.f;
     }
-    if (RED) {
+    if (REDC) {
       // g = dx * (y > 0); per-column sums of g and g * xhat over this tile's rows, 32 columns at a time:
       // warp transpose-reduce -> 4 warps combined through a small scratch -> fp64 atomics
       const size_t roff = (size_t)(in_range ? orow : 0) * p.N + n0 + c;
@@ -392,7 +397,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
       red[(q * 2 + 1) * BN + c + lane] = sq[0];
     }
   }
-  const bool bnf = STATS && !EPI && p.bnf_barrier != nullptr;
+  const bool bnf = STATS && !EPI && BNFC && p.bnf_barrier != nullptr;
   if (release && !bnf) {   // persistent kernel: this thread is done reading the accumulator buffer
     tc_fence_before();
     mbar_arrive(release);
@@ -1011,7 +1016,7 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
       TnParams q = p;
       if (p.bnf_barrier) {   // grid-wide barrier inside: every CTA of the launch must be resident at once
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<BN, TN_STAGES, true, true, false>, TN_THREADS, smem) != cudaSuccess)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<BN, TN_STAGES, true, true, false, 3>, TN_THREADS, smem) != cudaSuccess)
           occ = 0;
         q.bnf_expected = grid.x * grid.y;
         if ((long long)q.bnf_expected > (long long)occ * g_num_sms) {
@@ -1019,7 +1024,10 @@ int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const T
           return SSB_ERR_UNSUPPORTED;
         }
       }
-      ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, q);
+      if (p.bnf_barrier)
+        ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false, 3>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, q);
+      else
+        ssb_launch_pro(conv_tn_kernel<BN, TN_STAGES, true, true, false>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, q);
     }
   } else if (p.red_sums) {
     if constexpr (!B_MN) {
@@ -1056,7 +1064,10 @@ int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const 
           return SSB_ERR_UNSUPPORTED;
         }
       }
-      ssb_launch_pro(conv_tn3_kernel<BN, true, true, false>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, q);
+      if (p.bnf_barrier)
+        ssb_launch_pro(conv_tn3_kernel<BN, true, true, false, 3>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, q);
+      else
+        ssb_launch_pro(conv_tn3_kernel<BN, true, true, false>, dim3(grid), dim3(TN_THREADS), smem, st, tmA, tmB, out, q);
     }
   } else if (p.red_sums) {
     if constexpr (!B_MN) {
@@ -1155,6 +1166,18 @@ int ssb_sm100_prepare() {
                              smem_bytes<BN_ * BK * 2, TN_STAGES>());
   SSB_TNR_ATTR(128, 1) SSB_TNR_ATTR(64, 1) SSB_TNR_ATTR(128, 2) SSB_TNR_ATTR(64, 2)
 #undef SSB_TNR_ATTR
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tn_kernel<128, TN_STAGES, true, true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes<128 * BK * 2, TN_STAGES>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tn_kernel<64, TN_STAGES, true, true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_bytes<64 * BK * 2, TN_STAGES>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tn3_kernel<64, true, true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3_bytes<64>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tn3_kernel<128, true, true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3_bytes<128>());
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(conv_tn3_kernel<256, true, true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3_bytes<256>());
 #define SSB_TN3_ATTR(BN_, ST_, MN_, EP_)                                                                               \
   if (e == cudaSuccess)                                                                                              \
     e = cudaFuncSetAttribute(conv_tn3_kernel<BN_, ST_, MN_, EP_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3_bytes<BN_>());
@@ -1267,11 +1290,11 @@ int ssb_conv1d_fwd_bnf_fits_sm100(ssb_geom gin, ssb_geom gout, int k, int stride
   }
   int occ = 0;
   if (N % 128 == 0) {
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<128, TN_STAGES, true, true, false>, TN_THREADS,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<128, TN_STAGES, true, true, false, 3>, TN_THREADS,
                                                       smem_bytes<128 * BK * 2, TN_STAGES>()) != cudaSuccess) return 0;
     return (long long)mt * (N / 128) <= (long long)occ * g_num_sms ? 1 : 0;
   }
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<64, TN_STAGES, true, true, false>, TN_THREADS,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tn_kernel<64, TN_STAGES, true, true, false, 3>, TN_THREADS,
                                                     smem_bytes<64 * BK * 2, TN_STAGES>()) != cudaSuccess) return 0;
   return (long long)mt * (N / 64) <= (long long)occ * g_num_sms ? 1 : 0;
 }

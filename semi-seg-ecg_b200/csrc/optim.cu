@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) syncbn_exchange_kernel(double* __restrict
       do {
         a = sbx_load(src);
         b = sbx_load(src + 1);
-        if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer is gone -- record it and go on rather than hang the GPU
+        if (clock64() - t0 > 40000000000LL) {   // ~20 s: a peer is gone -- record it and go on rather than hang the GPU
           *reinterpret_cast<unsigned int*>(mine + 64) = epoch;
           break;
         }

@@ -316,6 +316,10 @@ class StepEngine:
 
     def step(self, lr: float) -> None:
         """Run one optimizer step on the staged batch (asynchronous)."""
+        if self.it == 0 and getattr(self, "syncbn_p2p", False):
+            # the peer-memory exchange waits for its peers with a bounded spin: let the ranks enter their first step together
+            torch.cuda.synchronize()
+            torch.distributed.barrier(group=self.pg)
         self._write_step_params(lr)
         if self.use_graph:
             if self.graph is None:
