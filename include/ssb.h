@@ -227,12 +227,16 @@ int ssb_bn_bwd_apply(const void* g1, const void* g2, const void* y, const void* 
 /* both backward passes in ONE launch (reduce -> grid-wide barrier -> apply; g / y / x are read once).  Needs the
  * whole grid co-resident: returns SSB_ERR_UNSUPPORTED for tensors too large for that (callers then use the two
  * calls above).  barrier: a zeroed uint32 owned by this launch (the step engine keeps one per BN layer in the arena
- * it zeroes every step).  Not for SyncBN (the statistics exchange sits between the passes). */
+ * it zeroes every step).  rep / rep_res: zeroed scratch of 8 replicas of this layer's (and the residual BN's) [2C]
+ * sums, rep_stride doubles apart -- block b accumulates into replica b % 8, so that hundreds of blocks do not queue on
+ * the same 2C addresses; the totals are also left in bn->bwd_sums.  Not for SyncBN (the statistics exchange sits
+ * between the passes). */
 /* 1 if ssb_bn_bwd_fused can run this shape (res_mode: 0 none, 1 identity residual, 2 residual BN), else 0 */
 int ssb_bn_bwd_fused_fits(ssb_geom g, int res_mode, int has_y, int dtype);
 int ssb_bn_bwd_fused(const void* g1, const void* y, const void* x, const ssb_bn* bn, void* dx,
                      const void* x_res, const ssb_bn* bn_res, void* dx_res, void* g_ident, ssb_geom g,
-                     uint32_t* barrier, int dtype, ssb_stream_t stream);
+                     uint32_t* barrier, double* rep, double* rep_res, size_t rep_stride, int dtype,
+                     ssb_stream_t stream);
 /* stem tail backward (max-pool scatter + relu + bn), same two passes; gp: grad w.r.t. pooled output */
 int ssb_stem_bwd_reduce(const void* gp, const void* c0, const uint8_t* arg, const ssb_bn* bn, ssb_geom gin,
                         ssb_geom gout, int dtype, ssb_stream_t stream);

@@ -468,12 +468,25 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   __syncthreads();
 }
 
+#ifndef BWF_KEEP
+// Rows per thread whose (masked gradient, x[, x_res]) stay in registers across the barrier.  Measured on B200 at the
+// config-2 shapes: 0 is fastest -- keeping 1 / 2 rows costs 16 / 28 registers, the occupancy-capped grid shrinks
+// (444 -> 296 -> 148 blocks) and the step slows by 3 % / 5 %; forcing the register count with min-blocks spills.
+// The second read comes from L2 anyway.
+#define BWF_KEEP 0
+#endif
+#ifndef BWF_MINB
+#define BWF_MINB 1
+#endif
+#define BWF_REP 8      // replicated accumulators: block b adds into replica b % 8 (8x less same-address contention)
+
 template <typename T, bool HAS_Y, int RES>
-__global__ void __launch_bounds__(BN_THREADS) bn_bwd_fused_kernel(const T* __restrict__ g1, const T* __restrict__ y,
+__global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(const T* __restrict__ g1, const T* __restrict__ y,
                                                                   const T* __restrict__ x, const T* __restrict__ xr,
                                                                   T* __restrict__ dx, T* __restrict__ dxr, T* __restrict__ gid,
                                                                   ssb_bn bn, ssb_bn bnr, ssb_geom g, int cgpc, int rpb,
-                                                                  unsigned int* __restrict__ barrier) {
+                                                                  unsigned int* __restrict__ barrier, double* __restrict__ rep,
+                                                                  double* __restrict__ rep_r, long long rep_stride) {
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
@@ -491,6 +504,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_fused_kernel(const T* __res
   __shared__ float sC[RES == 2 ? BN_THREADS * V : 1];
   __shared__ float sCo[5][64];
   float mean[V], inv[V], meanr[V], invr[V];
+  Vec<T> kg[BWF_KEEP + 1], kx[BWF_KEEP + 1], kr[BWF_KEEP + 1];      // packed copies of the first rows (masked gradient, x, x_res)
   // ---- pass 1: reduce ----
   {
     float a[V], bq[V], cq[V];
@@ -507,35 +521,41 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_fused_kernel(const T* __res
           invr[i] = bnr.mean_invstd[C + c];
         }
       }
-      for (int row = r0 + rl; row < r1; row += rpp) {
-        if (!row_valid(row, g.pitch, g.len)) continue;     // halo / pad rows carry zero gradient
+      int k = 0;
+      for (int row = r0 + rl; row < r1; row += rpp, ++k) {
+        const bool valid = row_valid(row, g.pitch, g.len);
+        if (!valid && k >= BWF_KEEP) continue;     // halo / pad rows carry zero gradient
         const size_t off = (size_t)row * C + (size_t)cg * V;
-        Vec<T> vg, vx;
-        vg.load(g1 + off);
-        vx.load(x + off);
-        float fg[V], fx[V];
-        vg.get(fg);
-        vx.get(fx);
-        if (HAS_Y) {
-          Vec<T> vy;
-          vy.load(y + off);
-          float fy[V];
-          vy.get(fy);
+        Vec<T> vg, vx, vr;
+        float fg[V], fx[V], fr[V];
+        if (valid) {
+          vg.load(g1 + off);
+          vx.load(x + off);
+          vg.get(fg);
+          vx.get(fx);
+          if (HAS_Y) {
+            Vec<T> vy;
+            vy.load(y + off);
+            float fy[V];
+            vy.get(fy);
 #pragma unroll
-          for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
-        }
-        float fr[V];
-        if (RES == 2) {
-          Vec<T> vr;
-          vr.load(xr + off);
-          vr.get(fr);
+            for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
+            vg.set(fg);          // exact: masking keeps the stored values or zero
+          }
+          if (RES == 2) {
+            vr.load(xr + off);
+            vr.get(fr);
+          }
+#pragma unroll
+          for (int i = 0; i < V; ++i) {
+            a[i] += fg[i];
+            bq[i] += fg[i] * ((fx[i] - mean[i]) * inv[i]);
+            if (RES == 2) cq[i] += fg[i] * ((fr[i] - meanr[i]) * invr[i]);
+          }
         }
 #pragma unroll
-        for (int i = 0; i < V; ++i) {
-          a[i] += fg[i];
-          bq[i] += fg[i] * ((fx[i] - mean[i]) * inv[i]);
-          if (RES == 2) cq[i] += fg[i] * ((fr[i] - meanr[i]) * invr[i]);
-        }
+        for (int j = 0; j < BWF_KEEP; ++j)
+          if (j == k) { kg[j] = vg; kx[j] = vx; if (RES == 2) kr[j] = vr; }
       }
     }
 #pragma unroll
@@ -546,6 +566,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_fused_kernel(const T* __res
     }
   }
   __syncthreads();
+  const long long rsel = (long long)(blockIdx.x % BWF_REP) * rep_stride;
   for (int o = threadIdx.x; o < cgpc * V; o += BN_THREADS) {
     const int l = o / V, i = o % V;
     const int cgo = blockIdx.y * cgpc + l;
@@ -557,12 +578,9 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_fused_kernel(const T* __res
       if (RES == 2) dc += sC[(k * cgpc + l) * V + i];
     }
     const int c = cgo * V + i;
-    atomicAdd(&bn.bwd_sums[c], (double)da);
-    atomicAdd(&bn.bwd_sums[C + c], (double)db);
-    if (RES == 2) {
-      atomicAdd(&bnr.bwd_sums[c], (double)da);
-      atomicAdd(&bnr.bwd_sums[C + c], (double)dc);
-    }
+    atomicAdd(&rep[rsel + c], (double)da);
+    atomicAdd(&rep[rsel + C + c], (double)db);
+    if (RES == 2) atomicAdd(&rep_r[rsel + C + c], (double)dc);
     __threadfence();   // this thread's reductions are performed before the block signals the barrier
   }
   grid_barrier(barrier, gridDim.x * gridDim.y);
@@ -574,21 +592,30 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_fused_kernel(const T* __res
       const double inv_n = 1.0 / ((double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1));
       const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
       const bool writer = blockIdx.x == 0;
-      const double sg = __ldcg(&bn.bwd_sums[c]), sgx = __ldcg(&bn.bwd_sums[C + c]);
+      double sg = 0.0, sgx = 0.0, sgxr = 0.0;
+#pragma unroll
+      for (int k = 0; k < BWF_REP; ++k) {
+        sg += __ldcg(&rep[k * rep_stride + c]);
+        sgx += __ldcg(&rep[k * rep_stride + C + c]);
+        if (RES == 2) sgxr += __ldcg(&rep_r[k * rep_stride + C + c]);
+      }
       sCo[0][threadIdx.x] = bn.gamma[c] * bn.mean_invstd[C + c];
       sCo[1][threadIdx.x] = (float)(sg * inv_n);
       sCo[2][threadIdx.x] = (float)(sgx * inv_n);
       if (writer) {
         bn.dgamma[c] = (float)(sgx * gsc);
         bn.dbeta[c] = (float)(sg * gsc);
+        bn.bwd_sums[c] = sg;             // the totals, where the two-launch path leaves them
+        bn.bwd_sums[C + c] = sgx;
       }
       if (RES == 2) {
-        const double sgxr = __ldcg(&bnr.bwd_sums[C + c]);
         sCo[3][threadIdx.x] = bnr.gamma[c] * bnr.mean_invstd[C + c];
         sCo[4][threadIdx.x] = (float)(sgxr * inv_n);
         if (writer) {
           bnr.dgamma[c] = (float)(sgxr * gsc);
           bnr.dbeta[c] = (float)(sg * gsc);
+          bnr.bwd_sums[c] = sg;
+          bnr.bwd_sums[C + c] = sgxr;
         }
       }
     }
@@ -602,32 +629,40 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_fused_kernel(const T* __res
     k0[i] = sCo[0][j]; k1[i] = sCo[1][j]; k2[i] = sCo[2][j];
     if (RES == 2) { rk0[i] = sCo[3][j]; rk2[i] = sCo[4][j]; }
   }
-  for (int row = r0 + rl; row < r1; row += rpp) {     // the block's rows are still in L2 (and mostly in L1)
+  int k = 0;
+  for (int row = r0 + rl; row < r1; row += rpp, ++k) {
     const size_t off = (size_t)row * C + (size_t)cg * V;
     Vec<T> odx, odr, ogi;
     if (row_valid(row, g.pitch, g.len)) {
-      Vec<T> vg, vx;
-      vg.load(g1 + off);
-      vx.load(x + off);
-      float fg[V], fx[V];
-      vg.get(fg);
-      vx.get(fx);
-      if (HAS_Y) {
-        Vec<T> vy;
-        vy.load(y + off);
-        float fy[V];
-        vy.get(fy);
+      Vec<T> vg, vx, vr;
+      bool have = false;
 #pragma unroll
-        for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
+      for (int j = 0; j < BWF_KEEP; ++j)
+        if (j == k) { vg = kg[j]; vx = kx[j]; if (RES == 2) vr = kr[j]; have = true; }
+      float fg[V], fx[V];
+      if (!have) {                       // rows beyond the register-resident ones: second read (L2 / L1)
+        vg.load(g1 + off);
+        vx.load(x + off);
+        vg.get(fg);
+        if (HAS_Y) {
+          Vec<T> vy;
+          vy.load(y + off);
+          float fy[V];
+          vy.get(fy);
+#pragma unroll
+          for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
+        }
+        if (RES == 2) vr.load(xr + off);
+      } else {
+        vg.get(fg);
       }
+      vx.get(fx);
       float o[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = k0[i] * (fg[i] - k1[i] - ((fx[i] - mean[i]) * inv[i]) * k2[i]);
       odx.set(o);
       if (RES == 1) ogi.set(fg);
       if (RES == 2) {
-        Vec<T> vr;
-        vr.load(xr + off);
         float fr[V];
         vr.get(fr);
 #pragma unroll
@@ -877,7 +912,7 @@ static bool bwd_fused_plan(const ssb_geom& g, int mode, bool has_y, int* cgpc_o,
 
 #define SSB_BWF(Y, R)                                                                                                          \
   ssb_launch(bn_bwd_fused_kernel<T, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)y, (const T*)x,       \
-             (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, cgpc, rpb, barrier)
+             (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, cgpc, rpb, barrier, rep, rep_r, (long long)rep_stride)
 #define SSB_RED(G2, Y, R) \
   ssb_launch(bn_bwd_reduce_kernel<T, G2, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, *bn, br, rows, g.C, rpb)
 #define SSB_APP(G2, Y, R) \
@@ -1015,11 +1050,14 @@ int ssb_bn_bwd_fused_fits(ssb_geom g, int res_mode, int has_y, int dtype) {
 }
 
 int ssb_bn_bwd_fused(const void* g1, const void* y, const void* x, const ssb_bn* bn, void* dx, const void* x_res,
-                     const ssb_bn* bn_res, void* dx_res, void* g_ident, ssb_geom g, uint32_t* barrier, int dtype,
-                     ssb_stream_t stream) {
+                     const ssb_bn* bn_res, void* dx_res, void* g_ident, ssb_geom g, uint32_t* barrier, double* rep,
+                     double* rep_res, size_t rep_stride, int dtype, ssb_stream_t stream) {
   int rc = check_geom("ssb_bn_bwd_fused", g, 0);
   if (rc) return rc;
-  SSB_REQUIRE(g1 && x && bn && dx && barrier, "ssb_bn_bwd_fused: null pointer");
+  SSB_REQUIRE(g1 && x && bn && dx && barrier && rep, "ssb_bn_bwd_fused: null pointer");
+  SSB_REQUIRE(!bn_res || rep_res, "ssb_bn_bwd_fused: residual BN needs its replica scratch");
+  SSB_REQUIRE(rep_stride >= (size_t)2 * g.C, "ssb_bn_bwd_fused: replica stride %zu < 2C", rep_stride);
+  double* rep_r = rep_res;
   SSB_REQUIRE(!(bn_res && (!x_res || !dx_res)), "ssb_bn_bwd_fused: residual BN needs x_res and dx_res");
   SSB_REQUIRE(!(bn_res && g_ident), "ssb_bn_bwd_fused: g_ident and bn_res are exclusive");
   const int mode = bn_res ? 2 : (g_ident ? 1 : 0);

@@ -280,7 +280,7 @@ class TrainState:
         lay, dev = w.layout, w.device
         # everything a step zeroes before it starts lives in ONE arena (one memset node per step):
         # [gradients | BN forward sums | BN backward sums | loss sums] -- the tail is fp64
-        n_tail = 2 * lay.n_sums + 64 + len(lay.bns)
+        n_tail = 2 * lay.n_sums + 64 + len(lay.bns) + 8 * lay.n_sums
         self.zero_arena = torch.zeros(lay.n_params + 2 * n_tail, dtype=torch.float32, device=dev)
         self.grads = self.zero_arena[: lay.n_params]
         tail = self.zero_arena[lay.n_params:].view(torch.float64)
@@ -291,6 +291,9 @@ class TrainState:
         nb = (len(lay.bns) + 1) // 2
         self.barriers = tail[2 * lay.n_sums + 8: 2 * lay.n_sums + 8 + nb].view(torch.int32)
         self.fwd_barriers = tail[2 * lay.n_sums + 8 + nb: 2 * lay.n_sums + 8 + 2 * nb].view(torch.int32)
+        # 8 replicas of the BN backward sums (fused BN backward: block b accumulates into replica b % 8)
+        r0_ = 2 * lay.n_sums + 64 + len(lay.bns)
+        self.bwd_rep = tail[r0_: r0_ + 8 * lay.n_sums]
         self.exp_avg = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(lay.n_params, dtype=torch.float32, device=dev)
         self.step = 0
@@ -388,6 +391,7 @@ class NetPlan:
         # ---- BN statistic arenas ----
         self.barriers = state.barriers if state is not None else None
         self.fwd_barriers = state.fwd_barriers if state is not None else None
+        self.bwd_rep = state.bwd_rep if state is not None else None
         if state is not None:   # statistic arenas inside the step's zero arena (TrainState)
             self.sums, self.bwd_sums = state.sums, state.bwd_sums
         else:
@@ -555,6 +559,7 @@ class NetPlan:
             call("ssb_memset_zero", self.bwd_sums.data_ptr(), self.bwd_sums.numel() * 8, st)
             if self.barriers is not None:   # (the backward and forward barrier counters are adjacent)
                 call("ssb_memset_zero", self.barriers.data_ptr(), (self.barriers.numel() + self.fwd_barriers.numel()) * 4, st)
+                call("ssb_memset_zero", self.bwd_rep.data_ptr(), self.bwd_rep.numel() * 8, st)
 
     # ---- forward -------------------------------------------------------------------
     def forward(self, x: torch.Tensor, st: int, train_mode: Optional[bool] = None, zero: bool = True,
@@ -711,7 +716,8 @@ class NetPlan:
             if self._fused_ok[key]:
                 call("ssb_bn_bwd_fused", g1.data_ptr(), ptr(y), x.data_ptr(), self.bn(b), dx.data_ptr(), ptr(x_res),
                      self.bn(b_res) if b_res is not None else None, ptr(dx_res), ptr(g_ident), geom,
-                     self.barriers.data_ptr() + 4 * b.index, self.dtype, st)
+                     self.barriers.data_ptr() + 4 * b.index, self.bwd_rep.data_ptr() + 8 * b.soff,
+                     (self.bwd_rep.data_ptr() + 8 * b_res.soff) if b_res is not None else None, self.lay.n_sums, self.dtype, st)
                 return
         if not pre_reduced:
             call("ssb_bn_bwd_reduce", g1.data_ptr(), None, ptr(y), x.data_ptr(), self.bn(b), ptr(x_res),

@@ -349,8 +349,10 @@ def test_bn_bwd_fused(dtype, Cn, res_mode, L):
         a_res = (xr.data_ptr(), C.byref(bnr), dxr.data_ptr(), None) if res_mode == 2 else (None, None, None, gid.data_ptr() if res_mode == 1 else None)
         if fused:
             bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+            rep = torch.zeros(2, 8, 2 * Cn + 64, dtype=torch.float64, device=DEV)
             call("ssb_bn_bwd_fused", gr.data_ptr(), yy.data_ptr(), xx.data_ptr(), C.byref(bn), dx.data_ptr(), a_res[0], a_res[1],
-                 a_res[2], a_res[3], g, bar.data_ptr(), dtype, st())
+                 a_res[2], a_res[3], g, bar.data_ptr(), rep[0].data_ptr(), rep[1].data_ptr() if res_mode == 2 else None,
+                 2 * Cn + 64, dtype, st())
         else:
             call("ssb_bn_bwd_reduce", gr.data_ptr(), None, yy.data_ptr(), xx.data_ptr(), C.byref(bn), a_res[0], a_res[1], g, dtype, st())
             call("ssb_bn_bwd_apply", gr.data_ptr(), None, yy.data_ptr(), xx.data_ptr(), C.byref(bn), dx.data_ptr(), a_res[0], a_res[1],
