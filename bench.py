@@ -438,8 +438,61 @@ def run_b200(args):
         line["gpu_augmentation"] = aug
     if syncbn_on is not None:
         line["sync_bn_on"] = syncbn_on
+    if world == 1 and not args.no_aug and args.workload == DEFAULT_WORKLOAD:
+        line["other_algorithms"] = other_algorithm_rates(cfg, dev, dtype, C, L, Bl, Bu, host[0])
     print(json.dumps(line), flush=True)
     _finish(world)
+
+
+def other_algorithm_rates(cfg, dev, dtype, C, L, Bl, Bu, batch, steps=100):
+    """Supplementary: the same network and per-GPU batch through the other step modes of the engine (SURVEY.md 8f
+    rank 2) -- Mean-Teacher, ST++ (frozen hard teacher) and CPS (two models, two optimizer steps per step) --
+    device-resident inputs, CUDA events, samples/s counted as in the headline (B_l + B_u strips per step)."""
+    from algorithms.base import init_model_from_cfg
+    from algorithms.mean_teacher import init_teacher
+    from semiseg_b200.engine import CpsEngine
+    from semiseg_b200.trainer import get_engine
+    from utils.lr_sched import lr_at
+    tcfg = dict(cfg["train"], ema_decay=0.99)
+    x, y, uw, us = [t.to(dev) for t in batch]
+    out = {}
+
+    def rate(load, step):
+        for _ in range(5):
+            load()
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            load()
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"ms_per_step": round(ms, 4), "samples_per_s": round((Bl + Bu) / (ms / 1e3), 1)}
+
+    lr = lr_at(20.0, tcfg)
+    torch.manual_seed(1)
+    m = init_model_from_cfg(cfg).to(dev)
+    t = init_teacher(cfg, m, dev)
+    e = get_engine("mean_teacher", m, t, Bl, Bu, L, dtype, tcfg)
+    out["mean_teacher"] = dict(rate(lambda: e.load_batch(x, y, uw, us), lambda: e.step(lr)), launches_per_step=e.launches_per_step)
+    assert all(np.isfinite(s_["loss_total"]) for s_ in e.read_stats())
+    m = init_model_from_cfg(cfg).to(dev)
+    t = init_model_from_cfg(cfg).to(dev).eval()
+    e = get_engine("stpp", m, t, Bl, Bu, L, dtype, tcfg)
+    out["stpp"] = dict(rate(lambda: e.load_batch(x, y, uw), lambda: e.step(lr)), launches_per_step=e.launches_per_step)
+    assert all(np.isfinite(s_["loss_total"]) for s_ in e.read_stats())
+    m1, m2 = init_model_from_cfg(cfg).to(dev), init_model_from_cfg(cfg).to(dev)
+    e1 = get_engine("cps", m1, m2, Bl, Bu, L, dtype, tcfg, external_pseudo=True)
+    e2 = get_engine("cps", m2, m1, Bl, Bu, L, dtype, tcfg, external_pseudo=True)
+    cps = CpsEngine(e1, e2)
+    out["cps"] = dict(rate(lambda: cps.load_batch(x, y, uw), lambda: cps.step(lr)),
+                      launches_per_step=e1.launches_per_step + e2.launches_per_step,
+                      note="two models trained per step; the two training graphs run side by side")
+    assert all(np.isfinite(s_["loss_total"]) for s_ in cps.read_stats())
+    return out
 
 
 def large_batch_roofline(peaks, workload="fixmatch_resnet18w128_12x5000_b32+32"):

@@ -467,8 +467,46 @@ class OracleTrainer:
         return {"loss_total": float(loss.detach()), "loss_x": float(loss_x.detach()),
                 "loss_u_s": float(loss_u.detach())}
 
+    def hard_label_step(self, ecg_x: Tensor, mask_x: Tensor, ecg_u_w: Tensor, label_u: Tensor, lr: float,
+                        want_taps: bool = False) -> Dict[str, float]:
+        """The student half of cps.py:108-149 and stpp.py:154-197: train-mode forward of cat(ecg_x, ecg_u_w),
+        CE against the labels and against given hard pseudo-labels (mean over every position), /2, AdamW."""
+        sdg = self._leaf_params()
+        nb: Dict[str, Tensor] = {}
+        nl = ecg_x.shape[0]
+        self.taps = {} if want_taps else None
+        out = forward(sdg, torch.cat((ecg_x, ecg_u_w)).to(self.dtype), self.arch, True, None, nb, self.taps, quant=self.quant)
+        seg = out["seg_logits"]
+        loss_x = ce_hard(seg[:nl], mask_x)
+        loss_u = ce_hard(seg[nl:], label_u)
+        loss = (loss_x + loss_u) / 2.0
+        loss.backward()
+        self.sd.update(nb)
+        self._apply_grads(sdg, lr)
+        return {"loss_total": float(loss.detach()), "loss_x": float(loss_x.detach()), "loss_u_s": float(loss_u.detach())}
+
+    def hard_labels(self, ecg_u_w: Tensor, sd: Optional[Dict[str, Tensor]] = None) -> Tensor:
+        """cps.py:98-103 / stpp.py:150-152: eval-mode forward (running statistics), argmax over classes."""
+        with torch.no_grad():
+            return forward(sd if sd is not None else self.sd, ecg_u_w.to(self.dtype), self.arch, False,
+                           quant=self.quant)["seg_logits"].argmax(dim=1)
+
+    def stpp_step(self, ecg_x: Tensor, mask_x: Tensor, ecg_u_w: Tensor, teacher_sd: Dict[str, Tensor], lr: float) -> Dict[str, float]:
+        """stpp.py:140-197: hard pseudo-labels of a frozen teacher."""
+        return self.hard_label_step(ecg_x, mask_x, ecg_u_w, self.hard_labels(ecg_u_w, teacher_sd), lr)
+
     def teacher_state(self) -> Dict[str, Tensor]:
         return self._teacher_view()
+
+
+def cps_step(tr_1: "OracleTrainer", tr_2: "OracleTrainer", ecg_x: Tensor, mask_x: Tensor, ecg_u_w: Tensor,
+             lr: float) -> Dict[str, float]:
+    """cps.py:96-160: both models label the weak views BEFORE either is updated; each then trains against the other's
+    labels; the logged losses are the two models' means."""
+    lab_1, lab_2 = tr_1.hard_labels(ecg_u_w), tr_2.hard_labels(ecg_u_w)
+    s1 = tr_1.hard_label_step(ecg_x, mask_x, ecg_u_w, lab_2, lr)
+    s2 = tr_2.hard_label_step(ecg_x, mask_x, ecg_u_w, lab_1, lr)
+    return {k: (s1[k] + s2[k]) / 2.0 for k in s1}
 
 
 # --------------------------------------------------------------------------------------

@@ -27,7 +27,13 @@ from . import _lib
 from ._lib import StepParams, call
 from .net import NetPlan, ParamLayout, SegNetSpec, TrainState, WeightSet
 
-ALGOS = {"supervised": _lib.LOSS_SUP, "fixmatch": _lib.LOSS_FIXMATCH, "mean_teacher": _lib.LOSS_SOFT}
+# cps / stpp: hard pseudo-labels argmax(teacher(u_w)) from ANOTHER weight set (the peer
+# model of Cross Pseudo Supervision, cps.py:96-134; the frozen teacher of ST++, stpp.py:150-178), plain CE over every
+# position -- the FixMatch loss mode with threshold 0 (conf = max softmax >= 1/ncls > 0 keeps every position) -- and the
+# student sees the weak view itself (torch.cat((ecg_x, ecg_u_w))).
+ALGOS = {"supervised": _lib.LOSS_SUP, "fixmatch": _lib.LOSS_FIXMATCH, "mean_teacher": _lib.LOSS_SOFT,
+         "cps": _lib.LOSS_FIXMATCH, "stpp": _lib.LOSS_FIXMATCH}
+HARD_TEACHER = ("cps", "stpp")
 
 
 def _stream() -> int:
@@ -38,7 +44,7 @@ class StepEngine:
     def __init__(self, weights: WeightSet, state: TrainState, dtype: int, algorithm: str, Bl: int, Bu: int,
                  L: int, train_cfg: dict, teacher: Optional[WeightSet] = None, algo: Optional[int] = None,
                  use_graph: bool = True, process_group=None, sync_bn: bool = False, seed: int = 0,
-                 materialize: bool = False):
+                 materialize: bool = False, external_pseudo: bool = False):
         if algorithm not in ALGOS:
             raise ValueError(f"unknown algorithm {algorithm!r} (supported: {sorted(ALGOS)})")
         if weights.device.type != "cuda":
@@ -46,6 +52,12 @@ class StepEngine:
         _lib.check(_lib.load().ssb_device_check(), "ssb_device_check")
         self.w, self.state, self.algorithm = weights, state, algorithm
         self.mode = ALGOS[algorithm]
+        self.hard_teacher = algorithm in HARD_TEACHER
+        # external_pseudo: the pseudo-label forward is NOT part of step(); the owner calls pseudo() first (CpsEngine: both
+        # peers' pseudo-labels are taken before either model is updated, cps.py:96-103)
+        self.external_pseudo = external_pseudo
+        if external_pseudo and not self.hard_teacher:
+            raise ValueError("external_pseudo is for the hard-teacher algorithms (cps, stpp)")
         self.Bl, self.Bu, self.L = Bl, (Bu if algorithm != "supervised" else 0), L
         self.cfg = train_cfg
         self.spec: SegNetSpec = weights.layout.spec
@@ -92,8 +104,9 @@ class StepEngine:
         self.gnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         # teacher
         self.teacher = teacher
-        if algorithm == "mean_teacher" and teacher is None:
-            raise ValueError("mean_teacher needs a teacher WeightSet")
+        if (algorithm == "mean_teacher" or self.hard_teacher) and teacher is None:
+            raise ValueError(f"{algorithm} needs a teacher WeightSet")
+        self.uses_teacher_weights = algorithm == "mean_teacher" or self.hard_teacher
         self.ema_first = True
         # plans
         self.dtype = dtype
@@ -117,7 +130,7 @@ class StepEngine:
                               eval_rows=self.Bu if self.merged else 0, eval_bufs=self.bufs_snap)
         self.plan_t: Optional[NetPlan] = None
         if self.mode != _lib.LOSS_SUP and not self.merged:
-            tw = teacher if algorithm == "mean_teacher" else weights
+            tw = teacher if self.uses_teacher_weights else weights
             if algorithm == "fixmatch" and self.multi_stream:
                 # self-eval pass must see the running stats from BEFORE this step's update (fixmatch.py:87-93)
                 self.bufs_snap = torch.empty_like(weights.bufs)
@@ -128,6 +141,7 @@ class StepEngine:
                 s.count_mul = self.world
             self.plan_s.sync_hook = self._make_sync_hook()
         self.mat = None
+        self.pseudo_graph: Optional[torch.cuda.CUDAGraph] = None
         if materialize and self.mode == _lib.LOSS_FIXMATCH:
             self.mat = {"conf": torch.zeros(self.Bu, L, dtype=torch.float32, device=dev),
                         "label": torch.zeros(self.Bu, L, dtype=torch.int64, device=dev),
@@ -184,12 +198,18 @@ class StepEngine:
         """Stage one batch into the static input arena (H2D when given host tensors)."""
         self.x_s[: self.Bl].copy_(ecg_x, non_blocking=True)
         self.y_l.copy_(mask_x, non_blocking=True)
-        if self.mode != _lib.LOSS_SUP:
+        if self.hard_teacher:
+            # the student trains on the weak view itself (cps.py:113, stpp.py:158): one H2D, one device copy
+            self.x_uw.copy_(ecg_u_w, non_blocking=True)
+            self.x_s[self.Bl:].copy_(self.x_uw, non_blocking=True)
+        elif self.mode != _lib.LOSS_SUP:
             self.x_uw.copy_(ecg_u_w, non_blocking=True)
             self.x_s[self.Bl:].copy_(ecg_u_s, non_blocking=True)
 
     def h2d_bytes(self) -> int:
         n = self.x_s.numel() * 4 + self.y_l.numel() * 8 + 64
+        if self.hard_teacher:
+            return self.x_s[: self.Bl].numel() * 4 + self.x_uw.numel() * 4 + self.y_l.numel() * 8 + 64
         if self.mode != _lib.LOSS_SUP:
             n += self.x_uw.numel() * 4
         return n
@@ -211,7 +231,7 @@ class StepEngine:
         sp.rng_seed = self.seed & 0xFFFFFFFF
         sp.rng_step = self.it & 0xFFFFFFFF
         sp.grad_scale = 1.0 / self.world
-        sp.conf_thresh = float(self.cfg.get("conf_thresh", 0.0))
+        sp.conf_thresh = 0.0 if self.hard_teacher else float(self.cfg.get("conf_thresh", 0.0))
         C.memmove(self.sp_host[slot].data_ptr(), C.addressof(sp), 64)
         self.sp_dev.copy_(self.sp_host[slot], non_blocking=True)
         self.sp_events[slot].record()
@@ -231,21 +251,25 @@ class StepEngine:
             fork0.record()
             self.repack_stream.wait_event(fork0)
             self.plan_s.sh.refresh(self.repack_stream.cuda_stream)
-            if self.plan_t is not None and self.algorithm == "mean_teacher":
+            if self.plan_t is not None and self.uses_teacher_weights and not self.external_pseudo:
                 self.plan_t.sh.refresh(self.repack_stream.cuda_stream)
             repacked = torch.cuda.Event()
             repacked.record(self.repack_stream)
         else:
             self.plan_s.sh.refresh(st)
-            if self.plan_t is not None and self.algorithm == "mean_teacher":
+            if self.plan_t is not None and self.uses_teacher_weights and not self.external_pseudo:
                 self.plan_t.sh.refresh(st)
         self.plan_s.pre_block_event = repacked
         low_t = None
         if self.merged:
             self.bufs_snap.copy_(w.bufs, non_blocking=True)
             _, low_t = self.plan_s.forward_merged(self.x_all, st)
-        if self.plan_t is not None:
+        teacher_branch = False
+        if self.plan_t is not None and self.external_pseudo:
+            low_t = self.plan_t.low            # filled by pseudo(), which the owner ran before this step
+        elif self.plan_t is not None:
             self.plan_t.pre_block_event = repacked
+            teacher_branch = self.teacher_stream is not None
             if self.teacher_stream is not None:
                 if self.bufs_snap is not None:
                     self.bufs_snap.copy_(w.bufs, non_blocking=True)
@@ -258,7 +282,7 @@ class StepEngine:
                 low_t = self.plan_t.forward(self.x_uw, st, train_mode=False)
         if not self.merged:
             self.plan_s.forward(self.x_s, st, train_mode=True, zero=False, stream=cur)
-        if self.plan_t is not None and self.teacher_stream is not None:
+        if teacher_branch:
             torch.cuda.current_stream().wait_stream(self.teacher_stream)
         low_s = self.plan_s.low
         m = self.mat
@@ -314,6 +338,26 @@ class StepEngine:
             call("ssb_ema_i64", self.teacher.nbt.data_ptr(), w.nbt.data_ptr(), w.nbt.numel(), self.sp_dev.data_ptr(), st)
         self.launches_per_step = int(_lib.load().ssb_launch_count() - n0)
 
+    def pseudo(self) -> None:
+        """external_pseudo engines: storage-dtype copy of the teacher's weights + its eval-mode forward on the staged weak
+        views, into the logits buffer the next step() reads.  Its own small graph, replayed on the current stream."""
+        assert self.external_pseudo and self.plan_t is not None
+        if self.use_graph:
+            if self.pseudo_graph is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._enqueue_pseudo()
+                self.pseudo_graph = g
+            self.pseudo_graph.replay()
+        else:
+            self._enqueue_pseudo()
+
+    def _enqueue_pseudo(self) -> None:
+        st = _stream()
+        self.plan_t.sh.refresh(st)
+        self.plan_t.pre_block_event = None
+        self.plan_t.forward(self.x_uw, st, train_mode=False)
+
     def step(self, lr: float) -> None:
         """Run one optimizer step on the staged batch (asynchronous)."""
         if self.it == 0 and getattr(self, "syncbn_p2p", False):
@@ -354,7 +398,7 @@ class StepEngine:
         nu = float(self.Bu * self.L)
         loss_u = float(s[1]) / nu
         out = {"loss_total": (loss_x + loss_u) / 2.0, "loss_x": loss_x, "loss_u_s": loss_u}
-        if self.mode == _lib.LOSS_FIXMATCH:
+        if self.mode == _lib.LOSS_FIXMATCH and not self.hard_teacher:
             out["mask_ratio"] = float(s[2]) / nu
         return out
 
@@ -370,3 +414,49 @@ class StepEngine:
             self._retire(slot)
         out, self._done = self._done, []
         return out
+
+
+class CpsEngine:
+    """Cross Pseudo Supervision step (reference src/algorithms/cps.py:96-160): two models, each trained on
+    cat(ecg_x, ecg_u_w) against the labels and the OTHER model's hard pseudo-labels; both pseudo-label passes read the
+    weights and running statistics from before either update.  Two hard-teacher StepEngines over the two models'
+    arenas: pseudo(1<-2), pseudo(2<-1), then the two training graphs -- they touch disjoint state, so the second one
+    runs on its own stream beside the first."""
+
+    def __init__(self, eng_1: StepEngine, eng_2: StepEngine):
+        assert eng_1.algorithm == "cps" and eng_2.algorithm == "cps" and eng_1.external_pseudo and eng_2.external_pseudo
+        assert eng_1.teacher is eng_2.w and eng_2.teacher is eng_1.w, "each engine's teacher must be the other model"
+        self.engines = (eng_1, eng_2)
+        # (with collectives on, both engines issue NCCL all-reduces on one communicator: keep them in one stream order)
+        self.side = torch.cuda.Stream(device=eng_1.device) if (int(os.environ.get("SSB_CPS_CONCURRENT", "1")) and
+                                                                not eng_1.collectives) else None
+
+    def load_batch(self, ecg_x, mask_x, ecg_u_w) -> None:
+        a, b = self.engines
+        a.load_batch(ecg_x, mask_x, ecg_u_w)
+        # the second engine's arena is filled from the first one's (device copies): one H2D per step, not two
+        b.x_all.copy_(a.x_all, non_blocking=True)
+        b.y_l.copy_(a.y_l, non_blocking=True)
+
+    def h2d_bytes(self) -> int:
+        return self.engines[0].h2d_bytes()
+
+    def step(self, lr_1: float, lr_2: Optional[float] = None) -> None:
+        a, b = self.engines
+        a.pseudo()
+        b.pseudo()
+        if self.side is None:
+            a.step(lr_1)
+            b.step(lr_1 if lr_2 is None else lr_2)
+            return
+        cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)
+        a.step(lr_1)
+        with torch.cuda.stream(self.side):
+            b.step(lr_1 if lr_2 is None else lr_2)
+        cur.wait_stream(self.side)
+
+    def read_stats(self) -> List[Dict[str, float]]:
+        """Per step, the mean of the two models' losses (cps.py:153-160)."""
+        sa, sb = self.engines[0].read_stats(), self.engines[1].read_stats()
+        return [{k: (x[k] + y[k]) / 2.0 for k in x} for x, y in zip(sa, sb)]

@@ -30,6 +30,13 @@ def golden():
     return np.load(os.path.join(REPO, "tests", "golden", "reference_vectors.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_semi():
+    """cases F (CPS) and G (ST++), tests/golden/make_golden_semi.py"""
+    import numpy as np
+    return np.load(os.path.join(REPO, "tests", "golden", "semi_vectors.npz"))
+
+
 def golden_group(g, prefix):
     """{'name': array} for all keys under 'prefix/'."""
     pre = prefix + "/"

@@ -90,6 +90,49 @@ def test_mean_teacher_steps(golden):
             assert rel_err(teacher[name], refv) < 1e-4, name
 
 
+def _check_final(sd, g, prefix, tol=1e-4):
+    for name, refv in group(g, prefix).items():
+        if "num_batches_tracked" in name:
+            assert int(sd[name]) == int(refv), name
+        else:
+            assert rel_err(sd[name], refv) < tol, name
+
+
+def test_cps_steps(golden_semi):
+    """oracle cps_step vs the reference's cps.train_one_epoch (case F): both models' final states and the logged means"""
+    g = golden_semi
+    tr_1 = O.OracleTrainer(sd_from(g, "F/init_1"), TINY_ARCH, TRAIN_CFG, dtype=torch.float64)
+    tr_2 = O.OracleTrainer(sd_from(g, "F/init_2"), TINY_ARCH, TRAIN_CFG, dtype=torch.float64)
+    n, epoch = int(g["F/nsteps"]), int(g["F/epoch"])
+    stats = []
+    for it, (lab, unl) in enumerate(batches(int(g["F/data_seed"]), n, 3, 3, 2, 300)):
+        stats.append(O.cps_step(tr_1, tr_2, lab["ecg"], lab["target"], unl["ecg"], O.lr_at(it / n + epoch, TRAIN_CFG)))
+    ref = group(g, "F/stats")
+    for k in ("loss_total", "loss_x", "loss_u_s"):
+        assert abs(float(np.mean([s[k] for s in stats])) - float(ref[k])) < 2e-5, k
+    _check_final(tr_1.sd, g, "F/final_1")
+    _check_final(tr_2.sd, g, "F/final_2")
+    # the two models really differ (different init) and really moved
+    assert rel_err(tr_1.sd["backbone.layer1.0.conv1.weight"], g["F/final_2/backbone.layer1.0.conv1.weight"]) > 0.1
+
+
+def test_stpp_steps(golden_semi):
+    """oracle stpp_step vs the reference's stpp.train_one_epoch (case G): frozen teacher, hard labels"""
+    g = golden_semi
+    tr = O.OracleTrainer(sd_from(g, "G/init"), TINY_ARCH, TRAIN_CFG, dtype=torch.float64)
+    teacher = {k: (v.double() if v.is_floating_point() else v) for k, v in sd_from(g, "G/teacher").items()}
+    n, epoch = int(g["G/nsteps"]), int(g["G/epoch"])
+    stats = []
+    for it, (lab, unl) in enumerate(batches(int(g["G/data_seed"]), n, 3, 3, 2, 300)):
+        stats.append(tr.stpp_step(lab["ecg"], lab["target"], unl["ecg"], teacher, O.lr_at(it / n + epoch, TRAIN_CFG)))
+    ref = group(g, "G/stats")
+    for k in ("loss_total", "loss_x", "loss_u_s"):
+        assert abs(float(np.mean([s[k] for s in stats])) - float(ref[k])) < 2e-5, k
+    _check_final(tr.sd, g, "G/final")
+    for name, refv in group(g, "G/teacher_final").items():      # the teacher is untouched by the step
+        assert np.array_equal(g[f"G/teacher/{name}"], refv), name
+
+
 def test_full_size_step_scalars(golden):
     """resnet18 @ 1x2500, one FixMatch step: losses, mask ratio and all 65 gradient norms."""
     import models.backbones  # product constructors give the seeded init (checked bit-exact in test_surface)

@@ -157,6 +157,140 @@ def test_mean_teacher_steps_golden(golden):
     assert len(osd["state"]) == len(list(student.parameters()))
 
 
+def _check_final(sd, g, prefix, tol=2e-4):
+    for name, refv in group(g, prefix).items():
+        if "tracked" in name:
+            assert int(sd[name]) == int(refv), name
+        else:
+            assert rel_err(sd[name], refv) < tol, name
+
+
+def test_cps_epoch_golden(golden_semi):
+    """algorithms.cps.train_one_epoch (CpsEngine, fp32, graphs) vs the reference's cps.train_one_epoch (case F)."""
+    from algorithms.cps import train_one_epoch
+    from utils.optimizer import get_optimizer_from_config
+    g = golden_semi
+    m1, m2 = build(tiny_cfg(), sd_from(g, "F/init_1")), build(tiny_cfg(), sd_from(g, "F/init_2"))
+    n, epoch = int(g["F/nsteps"]), int(g["F/epoch"])
+    data = batches(int(g["F/data_seed"]), n, 3, 3, 2, 300)
+    o1, o2 = get_optimizer_from_config(TRAIN_CFG, m1.parameters()), get_optimizer_from_config(TRAIN_CFG, m2.parameters())
+    stats = train_one_epoch(m1, m2, [d[0] for d in data], [d[1] for d in data], o1, o2, torch.device(DEV), epoch, None,
+                            None, False, dict(TRAIN_CFG))
+    ref = group(g, "F/stats")
+    assert set(stats) == set(ref), (sorted(stats), sorted(ref))
+    for k in ("loss_total", "loss_x", "loss_u_s", "lr"):
+        assert abs(stats[k] - float(ref[k])) < 5e-5, (k, stats[k], float(ref[k]))
+    _check_final(m1.state_dict(), g, "F/final_1")
+    _check_final(m2.state_dict(), g, "F/final_2")
+
+
+@pytest.mark.parametrize("concurrent", ["0", "1"])
+def test_cps_engine_eager_matches_golden(golden_semi, concurrent, monkeypatch):
+    """CpsEngine without graphs, the two training steps serial or side by side: same result."""
+    from semiseg_b200.engine import CpsEngine
+    monkeypatch.setenv("SSB_CPS_CONCURRENT", concurrent)
+    g = golden_semi
+    m1, m2 = build(tiny_cfg(), sd_from(g, "F/init_1")), build(tiny_cfg(), sd_from(g, "F/init_2"))
+    n, epoch = int(g["F/nsteps"]), int(g["F/epoch"])
+    e1 = get_engine("cps", m1, m2, 3, 3, 300, _lib.F32, dict(TRAIN_CFG), use_graph=False, external_pseudo=True)
+    e2 = get_engine("cps", m2, m1, 3, 3, 300, _lib.F32, dict(TRAIN_CFG), use_graph=False, external_pseudo=True)
+    cps = CpsEngine(e1, e2)
+    assert (cps.side is not None) == (concurrent == "1")
+    for it, (lab, unl) in enumerate(batches(int(g["F/data_seed"]), n, 3, 3, 2, 300)):
+        cps.load_batch(lab["ecg"], lab["target"], unl["ecg"])
+        cps.step(O.lr_at(it / n + epoch, TRAIN_CFG))
+    stats = cps.read_stats()
+    ref = group(g, "F/stats")
+    for k in ("loss_total", "loss_x", "loss_u_s"):
+        assert abs(float(np.mean([s[k] for s in stats])) - float(ref[k])) < 5e-5, k
+    assert "mask_ratio" not in stats[0]
+    _check_final(m1.state_dict(), g, "F/final_1")
+    _check_final(m2.state_dict(), g, "F/final_2")
+
+
+def test_stpp_epoch_golden(golden_semi):
+    """algorithms.stpp.train_one_epoch (hard-teacher StepEngine, fp32) vs the reference's (case G); the teacher
+    stays untouched."""
+    from algorithms.stpp import train_one_epoch
+    from utils.optimizer import get_optimizer_from_config
+    g = golden_semi
+    student, teacher = build(tiny_cfg(), sd_from(g, "G/init")), build(tiny_cfg(), sd_from(g, "G/teacher"))
+    n, epoch = int(g["G/nsteps"]), int(g["G/epoch"])
+    data = batches(int(g["G/data_seed"]), n, 3, 3, 2, 300)
+    opt = get_optimizer_from_config(TRAIN_CFG, student.parameters())
+    stats = train_one_epoch(student, teacher, [d[0] for d in data], [{"ecg": d[1]["ecg"]} for d in data], opt,
+                            torch.device(DEV), epoch, None, None, False, dict(TRAIN_CFG))
+    ref = group(g, "G/stats")
+    assert set(stats) == set(ref), (sorted(stats), sorted(ref))
+    for k in ("loss_total", "loss_x", "loss_u_s", "lr"):
+        assert abs(stats[k] - float(ref[k])) < 5e-5, (k, stats[k], float(ref[k]))
+    _check_final(student.state_dict(), g, "G/final")
+    tsd = teacher.state_dict()
+    for name, refv in group(g, "G/teacher_final").items():
+        assert np.array_equal(tsd[name].cpu().numpy(), refv), name
+
+
+@pytest.mark.parametrize("dtype,tol", [(_lib.F32, 1e-5), (_lib.BF16, 2e-2)])
+def test_cps_full_size_vs_oracle(golden, dtype, tol):
+    """resnet18 @ 1x2500, one CPS step against the fp64 oracle.  FP32: the swapped pseudo-labels bit-equal wherever
+    the peer's top-2 logit gap is not at rounding level, losses within 1e-5, and each model's global gradient within
+    1e-5 when both sides took the same ReLU decisions.  Each pre-activation that sits within fp32 rounding of zero and
+    falls on the other side gates one unit's whole gradient contribution -- the gradient is a random-sign sum over
+    ~1e6 units, so one unit moves it by ~1e-3 relative (measured: 6.8e-4 .. 1.2e-3 per flip); with two networks a batch
+    without any such coincidence is rare, hence the per-flip allowance here.  The kernels are the ones
+    test_full_size_fp32_vs_oracle holds to 1e-5 on a coincidence-free batch.  BF16: losses 2e-2."""
+    from semiseg_b200.engine import CpsEngine
+    cfgm = model_cfg(1, 64, 64, 128, 0.0)
+    arch = O.Arch(num_leads=1, dropout_ratio=0.0)
+    lr = O.lr_at(3.0, TRAIN_CFG)
+    for seed in (410, 411, 412, 413, 414, 415):
+        m1, m2 = build(cfgm, None, seed=0), build(cfgm, None, seed=1)
+        init = [{k: v.detach().cpu().clone() for k, v in m.state_dict().items()} for m in (m1, m2)]
+        (lab, unl), = batches(seed, 1, 2, 2, 1, 2500)
+        tr = [O.OracleTrainer(sd, arch, TRAIN_CFG, dtype=torch.float64) for sd in init]
+        with torch.no_grad():
+            pw = [O.forward(t.sd, unl["ecg"].double(), arch, False)["seg_logits"] for t in tr]
+        e1 = get_engine("cps", m1, m2, 2, 2, 2500, dtype, dict(TRAIN_CFG), use_graph=True, external_pseudo=True)
+        e2 = get_engine("cps", m2, m1, 2, 2, 2500, dtype, dict(TRAIN_CFG), use_graph=True, external_pseudo=True)
+        for e in (e1, e2):
+            e.mat = {"conf": torch.zeros(2, 2500, device=DEV), "label": torch.zeros(2, 2500, dtype=torch.int64, device=DEV),
+                     "mask": torch.zeros(2, 2500, dtype=torch.uint8, device=DEV)}
+        cps = CpsEngine(e1, e2)
+        cps.load_batch(lab["ecg"], lab["target"], unl["ecg"])
+        cps.step(lr)
+        s, = cps.read_stats()
+        if dtype != _lib.F32:
+            ref = O.cps_step(tr[0], tr[1], lab["ecg"], lab["target"], unl["ecg"], lr)
+            break
+        # positions where the peer's top-2 logits tie at rounding level may legitimately resolve either way: the
+        # oracle's students are given the labels the kernels chose there (checked bit-equal everywhere else below)
+        l12 = [e.mat["label"].cpu() for e in (e1, e2)]
+        s1 = tr[0].hard_label_step(lab["ecg"], lab["target"], unl["ecg"], l12[0], lr, want_taps=True)
+        s2 = tr[1].hard_label_step(lab["ecg"], lab["target"], unl["ecg"], l12[1], lr, want_taps=True)
+        ref = {k: (s1[k] + s2[k]) / 2.0 for k in s1}
+        flips = [relu_mask_mismatches(e1.plan_s, tr[0].taps), relu_mask_mismatches(e2.plan_s, tr[1].taps)]
+        print(f"data seed {seed}: {flips} ReLU sign decisions differ from the fp64 oracle")
+        if sum(flips) <= 2:
+            break
+    for k in ("loss_total", "loss_x", "loss_u_s"):
+        assert abs(s[k] - ref[k]) < tol * max(1.0, abs(ref[k])), (k, s[k], ref[k])
+    if dtype == _lib.F32:
+        assert sum(flips) <= 2, "no candidate batch with at most two ReLU-kink coincidences"
+        for e, peer_logits in ((e1, pw[1]), (e2, pw[0])):          # engine i is labelled by the OTHER model
+            top2 = peer_logits.topk(2, dim=1).values
+            decided = (top2[:, 0] - top2[:, 1]) > 1e-5
+            assert decided.float().mean() > 0.99
+            assert torch.equal(e.mat["label"].cpu()[decided], peer_logits.argmax(1)[decided])
+            assert bool(e.mat["mask"].bool().all())              # threshold 0: every position counts
+        for i, (m, t) in enumerate(((m1, tr[0]), (m2, tr[1]))):
+            gv = m.runtime().weights.param_views(m.runtime().state.grads)
+            gflat = torch.cat([gv[n].flatten().cpu().double() for n in t.pnames])
+            rflat = torch.cat([t.grads[n].flatten() for n in t.pnames])
+            e = rel_err(gflat, rflat)
+            print(f"model {i + 1}: global gradient err {e:.2e} with {flips[i]} differing ReLU decisions")
+            assert e < 1e-5 + 2e-3 * flips[i], (e, flips[i])
+
+
 _ORACLE_CACHE = {}
 
 
