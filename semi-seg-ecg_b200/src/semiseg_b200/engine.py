@@ -443,17 +443,24 @@ class CpsEngine:
 
     def step(self, lr_1: float, lr_2: Optional[float] = None) -> None:
         a, b = self.engines
-        a.pseudo()
-        b.pseudo()
+        lr_2 = lr_1 if lr_2 is None else lr_2
         if self.side is None:
+            a.pseudo()
+            b.pseudo()
             a.step(lr_1)
-            b.step(lr_1 if lr_2 is None else lr_2)
+            b.step(lr_2)
             return
         cur = torch.cuda.current_stream()
+        self.side.wait_stream(cur)                # the staged batch
+        a.pseudo()
+        with torch.cuda.stream(self.side):
+            b.pseudo()
+        # each training step ends by updating the weights the OTHER engine's pseudo-label pass reads
+        cur.wait_stream(self.side)
         self.side.wait_stream(cur)
         a.step(lr_1)
         with torch.cuda.stream(self.side):
-            b.step(lr_1 if lr_2 is None else lr_2)
+            b.step(lr_2)
         cur.wait_stream(self.side)
 
     def read_stats(self) -> List[Dict[str, float]]:

@@ -233,17 +233,18 @@ def test_stpp_epoch_golden(golden_semi):
 @pytest.mark.parametrize("dtype,tol", [(_lib.F32, 1e-5), (_lib.BF16, 2e-2)])
 def test_cps_full_size_vs_oracle(golden, dtype, tol):
     """resnet18 @ 1x2500, one CPS step against the fp64 oracle.  FP32: the swapped pseudo-labels bit-equal wherever
-    the peer's top-2 logit gap is not at rounding level, losses within 1e-5, and each model's global gradient within
-    1e-5 when both sides took the same ReLU decisions.  Each pre-activation that sits within fp32 rounding of zero and
-    falls on the other side gates one unit's whole gradient contribution -- the gradient is a random-sign sum over
-    ~1e6 units, so one unit moves it by ~1e-3 relative (measured: 6.8e-4 .. 1.2e-3 per flip); with two networks a batch
-    without any such coincidence is rare, hence the per-flip allowance here.  The kernels are the ones
-    test_full_size_fp32_vs_oracle holds to 1e-5 on a coincidence-free batch.  BF16: losses 2e-2."""
+    the peer's top-2 logit gap is not at rounding level, losses within 1e-5 on every batch, and each model's global
+    gradient within 1e-5 on a batch where both sides took the same ReLU decisions for that model.  (A pre-activation
+    within fp32 rounding of zero that falls on the other side gates one unit's whole gradient contribution; the
+    gradient is a random-sign sum over ~1e6 units, so one such unit moves it by ~1e-3 relative -- measured 0.7e-3 to
+    2.5e-3 per flip.  With two networks a batch free of coincidences in both is rare, so batches are tried until each
+    model has had one.)  BF16: losses within 2e-2."""
     from semiseg_b200.engine import CpsEngine
     cfgm = model_cfg(1, 64, 64, 128, 0.0)
     arch = O.Arch(num_leads=1, dropout_ratio=0.0)
     lr = O.lr_at(3.0, TRAIN_CFG)
-    for seed in (410, 411, 412, 413, 414, 415):
+    verified = [False, False]
+    for seed in (420, 413, 411, 416, 417, 419, 410, 412, 414, 415, 418, 421, 422, 423):   # 420: none in either model
         m1, m2 = build(cfgm, None, seed=0), build(cfgm, None, seed=1)
         init = [{k: v.detach().cpu().clone() for k, v in m.state_dict().items()} for m in (m1, m2)]
         (lab, unl), = batches(seed, 1, 2, 2, 1, 2500)
@@ -261,34 +262,37 @@ def test_cps_full_size_vs_oracle(golden, dtype, tol):
         s, = cps.read_stats()
         if dtype != _lib.F32:
             ref = O.cps_step(tr[0], tr[1], lab["ecg"], lab["target"], unl["ecg"], lr)
-            break
+            for k in ("loss_total", "loss_x", "loss_u_s"):
+                assert abs(s[k] - ref[k]) < tol * max(1.0, abs(ref[k])), (k, s[k], ref[k])
+            return
         # positions where the peer's top-2 logits tie at rounding level may legitimately resolve either way: the
-        # oracle's students are given the labels the kernels chose there (checked bit-equal everywhere else below)
+        # oracle's students are given the labels the kernels chose there (checked bit-equal everywhere else)
         l12 = [e.mat["label"].cpu() for e in (e1, e2)]
-        s1 = tr[0].hard_label_step(lab["ecg"], lab["target"], unl["ecg"], l12[0], lr, want_taps=True)
-        s2 = tr[1].hard_label_step(lab["ecg"], lab["target"], unl["ecg"], l12[1], lr, want_taps=True)
-        ref = {k: (s1[k] + s2[k]) / 2.0 for k in s1}
-        flips = [relu_mask_mismatches(e1.plan_s, tr[0].taps), relu_mask_mismatches(e2.plan_s, tr[1].taps)]
-        print(f"data seed {seed}: {flips} ReLU sign decisions differ from the fp64 oracle")
-        if sum(flips) <= 2:
-            break
-    for k in ("loss_total", "loss_x", "loss_u_s"):
-        assert abs(s[k] - ref[k]) < tol * max(1.0, abs(ref[k])), (k, s[k], ref[k])
-    if dtype == _lib.F32:
-        assert sum(flips) <= 2, "no candidate batch with at most two ReLU-kink coincidences"
         for e, peer_logits in ((e1, pw[1]), (e2, pw[0])):          # engine i is labelled by the OTHER model
             top2 = peer_logits.topk(2, dim=1).values
             decided = (top2[:, 0] - top2[:, 1]) > 1e-5
             assert decided.float().mean() > 0.99
             assert torch.equal(e.mat["label"].cpu()[decided], peer_logits.argmax(1)[decided])
             assert bool(e.mat["mask"].bool().all())              # threshold 0: every position counts
+        s1 = tr[0].hard_label_step(lab["ecg"], lab["target"], unl["ecg"], l12[0], lr, want_taps=True)
+        s2 = tr[1].hard_label_step(lab["ecg"], lab["target"], unl["ecg"], l12[1], lr, want_taps=True)
+        ref = {k: (s1[k] + s2[k]) / 2.0 for k in s1}
+        for k in ("loss_total", "loss_x", "loss_u_s"):
+            assert abs(s[k] - ref[k]) < tol * max(1.0, abs(ref[k])), (k, s[k], ref[k])
+        flips = [relu_mask_mismatches(e1.plan_s, tr[0].taps), relu_mask_mismatches(e2.plan_s, tr[1].taps)]
+        errs = []
         for i, (m, t) in enumerate(((m1, tr[0]), (m2, tr[1]))):
             gv = m.runtime().weights.param_views(m.runtime().state.grads)
             gflat = torch.cat([gv[n].flatten().cpu().double() for n in t.pnames])
             rflat = torch.cat([t.grads[n].flatten() for n in t.pnames])
-            e = rel_err(gflat, rflat)
-            print(f"model {i + 1}: global gradient err {e:.2e} with {flips[i]} differing ReLU decisions")
-            assert e < 1e-5 + 2e-3 * flips[i], (e, flips[i])
+            errs.append(rel_err(gflat, rflat))
+            if flips[i] == 0:
+                assert errs[i] < 1e-5, (i, errs[i])
+                verified[i] = True
+        print(f"data seed {seed}: differing ReLU decisions {flips}, global gradient errors {errs[0]:.2e} {errs[1]:.2e}")
+        if all(verified):
+            break
+    assert all(verified), "no coincidence-free batch for one of the models"
 
 
 _ORACLE_CACHE = {}
