@@ -282,6 +282,17 @@ int ssb_semi_loss(const float* low_s, const int64_t* target, const float* low_t,
                   const ssb_step_params* sp, int align_corners, float* conf, int64_t* label,
                   uint8_t* mask, ssb_stream_t stream);
 
+/* ---- evaluation tail: upsample + softmax + argmax + CE + class counts  (base.py:198-221) -------------------------
+ * low: low-res logits [B, Lin, ncls] fp32 of an eval-mode forward; target int64 [B, L].
+ * sums (fp64[2], zeroed by the caller) += { sum of CE over the positions with a label in [0, ncls), their number }.
+ * counts (int32 [B, ncls, 3], zeroed by the caller) += per sample and class { |pred == c and target == c|,
+ * |pred == c|, |target == c| } -- the intersections and the two marginals every IoU / Dice style metric needs
+ * (the reference one-hot-encodes both and hands them to torchmetrics on the CPU).  pred = argmax over the soft-max
+ * outputs, first maximum.  Optional outputs (may be NULL): probs f32 [B, ncls, L] (the reference's returned
+ * `outputs`), pred i64 [B, L]. */
+int ssb_eval_metrics(const float* low, const int64_t* target, double* sums, int32_t* counts, float* probs,
+                     int64_t* pred, int B, int Lin, int L, int ncls, int align_corners, ssb_stream_t stream);
+
 /* ---- fused multi-tensor AdamW (+ EMA teacher)  (optimizer.py:22-34, mean_teacher.py:139-149) --- */
 /* flat arenas of n floats.  p_ema may be NULL.  Scalars come from sp (device). */
 int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, size_t n,

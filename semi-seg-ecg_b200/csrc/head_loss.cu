@@ -386,6 +386,80 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// evaluation tail (base.py:184-245): linear upsample + softmax + argmax + CE sum + per-sample class counts in one
+// pass over the low-res logits.  One block per (chunk of EV_CHUNK positions, sample).
+// ---------------------------------------------------------------------------------------
+#define EV_THREADS 256
+#define EV_CHUNK 1024
+
+__global__ void __launch_bounds__(EV_THREADS)
+eval_metrics_kernel(const float* __restrict__ low, const int64_t* __restrict__ target, double* __restrict__ sums,
+                    int* __restrict__ counts, float* __restrict__ probs, int64_t* __restrict__ pred, int B, int Lin, int L,
+                    int ncls, float scale, int align_corners) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ int sCnt[3][MAX_CLS];
+  __shared__ float sRed[2][EV_THREADS / 32];
+  const int b = blockIdx.y;
+  if (threadIdx.x < 3 * MAX_CLS) sCnt[threadIdx.x / MAX_CLS][threadIdx.x % MAX_CLS] = 0;
+  __syncthreads();
+  const int t0 = blockIdx.x * EV_CHUNK;
+  const int t1 = min(L, t0 + EV_CHUNK);
+  float acc = 0.f, nvalid = 0.f;
+  for (int t = t0 + threadIdx.x; t < t1; t += EV_THREADS) {
+    int i0, i1;
+    float w0, w1;
+    lerp_index(t, scale, Lin, align_corners, i0, i1, w0, w1);
+    const float* p0 = low + ((size_t)b * Lin + i0) * ncls;
+    const float* p1 = low + ((size_t)b * Lin + i1) * ncls;
+    float z[MAX_CLS], pr[MAX_CLS];
+    float m = -3.402823466e+38f;
+    for (int k = 0; k < ncls; ++k) {
+      z[k] = w0 * p0[k] + w1 * p1[k];
+      m = fmaxf(m, z[k]);
+    }
+    float sum = 0.f;
+    for (int k = 0; k < ncls; ++k) {
+      pr[k] = expf(z[k] - m);
+      sum += pr[k];
+    }
+    // prediction = argmax of the soft-max OUTPUTS (base.py:205-209), first maximum
+    int arg = 0;
+    float best = pr[0] / sum;
+    if (probs) probs[((size_t)b * ncls) * L + t] = best;
+    for (int k = 1; k < ncls; ++k) {
+      const float pk = pr[k] / sum;
+      if (probs) probs[((size_t)b * ncls + k) * L + t] = pk;
+      if (pk > best) { best = pk; arg = k; }
+    }
+    if (pred) pred[(size_t)b * L + t] = (int64_t)arg;
+    const int y = (int)target[(size_t)b * L + t];
+    atomicAdd(&sCnt[1][arg], 1);
+    if (y >= 0 && y < ncls) {
+      acc += m + logf(sum) - z[y];
+      nvalid += 1.f;
+      atomicAdd(&sCnt[2][y], 1);
+      if (y == arg) atomicAdd(&sCnt[0][y], 1);
+    }
+  }
+  acc = warp_sum(acc);
+  nvalid = warp_sum(nvalid);
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sRed[0][wid] = acc; sRed[1][wid] = nvalid; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float s_ = 0.f;
+    for (int i = 0; i < EV_THREADS / 32; ++i) s_ += sRed[threadIdx.x][i];
+    if (s_ != 0.f) atomicAdd(&sums[threadIdx.x], (double)s_);
+  }
+  if (threadIdx.x < 3 * ncls) {
+    const int q = threadIdx.x / ncls, c = threadIdx.x % ncls;
+    const int v = sCnt[q][c];
+    if (v) atomicAdd(&counts[((size_t)b * ncls + c) * 3 + q], v);
+  }
+}
+
 int ssb_loss_prepare() {
   cudaError_t e = cudaFuncSetAttribute(semi_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   if (e != cudaSuccess) {
@@ -463,6 +537,20 @@ int ssb_pseudo_label(const float* logits, float thr, float* conf, int64_t* label
   if (blocks > 148 * 8) blocks = 148 * 8;
   ssb_launch(pseudo_label_kernel, dim3(blocks), dim3(256), 0, to_stream(stream), logits, thr, conf, label, mask, U, ncls, L);
   SSB_LAUNCH_CHECK("ssb_pseudo_label");
+  return SSB_OK;
+}
+
+int ssb_eval_metrics(const float* low, const int64_t* target, double* sums, int32_t* counts, float* probs,
+                     int64_t* pred, int B, int Lin, int L, int ncls, int align_corners, ssb_stream_t stream) {
+  SSB_REQUIRE(low && target && sums && counts, "ssb_eval_metrics: null pointer");
+  SSB_REQUIRE(B > 0 && Lin > 0 && L > 0, "ssb_eval_metrics: bad sizes (B=%d Lin=%d L=%d)", B, Lin, L);
+  SSB_REQUIRE(ncls >= 1 && ncls <= MAX_CLS, "ssb_eval_metrics: num_classes %d out of range [1,%d]", ncls, MAX_CLS);
+  SSB_REQUIRE(B <= 65535, "ssb_eval_metrics: batch %d exceeds the grid limit", B);
+  const float scale = lerp_scale(Lin, L, align_corners);
+  dim3 grid((L + EV_CHUNK - 1) / EV_CHUNK, B);
+  ssb_launch(eval_metrics_kernel, grid, dim3(EV_THREADS), 0, to_stream(stream), low, target, sums, (int*)counts, probs, pred, B,
+             Lin, L, ncls, scale, align_corners);
+  SSB_LAUNCH_CHECK("ssb_eval_metrics");
   return SSB_OK;
 }
 

@@ -48,28 +48,24 @@ def train_one_epoch(model: torch.nn.Module, data_loader: Iterable, optimizer: to
 
 
 @torch.no_grad()
-def evaluate(model, data_loader, device, metric_fn=None, use_amp=True):
-    """Validation loss + mean IoU from a device-side confusion matrix (reference base.py:184-245
-    uses torchmetrics on CPU; eval is outside the accelerated training path)."""
-    model.eval()
-    ncls = model.decode_head.num_classes
-    conf = torch.zeros(ncls, ncls, dtype=torch.int64, device=device)
-    loss_sum, n = 0.0, 0
-    for samples in data_loader:
-        x = samples["ecg"].to(device, non_blocking=True)
-        y = samples["target"].to(device, non_blocking=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_amp):
-            out = model(x, y, return_loss=True)
-        loss_sum += float(out["loss"]) * x.shape[0]
-        n += x.shape[0]
-        pred = out["seg_logits"].argmax(dim=1)
-        conf += torch.bincount((y * ncls + pred).flatten(), minlength=ncls * ncls).view(ncls, ncls)
-    if misc.get_world_size() > 1:
-        torch.distributed.all_reduce(conf)
-    inter = conf.diag().double()
-    union = conf.sum(0).double() + conf.sum(1).double() - inter
-    miou = float((inter / union.clamp(min=1)).mean())
-    return {"loss": loss_sum / max(n, 1)}, {"MeanIoU": miou}, None, None
+def evaluate(model, data_loader, device, metric_fn=None, use_amp=True, return_outputs=False):
+    """Validation loss + MeanIoU (reference base.py:184-245): eval forward and the whole metric tail run as one CUDA
+    graph per batch, the metric (torchmetrics 1.5.2 MeanIoU semantics) is finalised on the device with a single
+    read-back (semiseg_b200.evaluate).  `metric_fn`: None, or a dict-like with the reference's MeanIoU options
+    (include_background, per_class).  The reference also returns every soft-max output and one-hot label on the
+    CPU; that is opt-in here (return_outputs=True -- `test` uses it)."""
+    from semiseg_b200.evaluate import evaluate_loader
+    opts = metric_fn if isinstance(metric_fn, dict) else {}
+    stats, metrics, outputs, labels = evaluate_loader(
+        _unwrap_model(model), data_loader, device, use_amp=use_amp,
+        include_background=bool(opts.get("include_background", True)), per_class=bool(opts.get("per_class", False)),
+        want_outputs=return_outputs)
+    print("* " + "  ".join(f"{k}: {v:.3f}" for k, v in metrics.items()) + f"  loss: {stats['loss']:.3f}")
+    return stats, metrics, outputs, labels
+
+
+def _unwrap_model(model):
+    return model.module if hasattr(model, "module") and not hasattr(model, "runtime") else model
 
 
 def _setup(config):
@@ -128,7 +124,9 @@ def train_loop(config, algorithm_epoch_fn, model, optimizer, loss_scaler, loader
             if hasattr(getattr(ld, "sampler", None), "set_epoch"):
                 ld.sampler.set_epoch(epoch)
         train_stats = algorithm_epoch_fn(epoch, log_writer, use_amp)
-        valid_stats, metrics, _, _ = evaluate(model, loaders["valid"], device, None, use_amp=use_amp)
+        valid_stats, metrics, _, _ = evaluate(model, loaders["valid"], device, config.get("metric"), use_amp=use_amp)
+        if "MeanIoU" not in metrics:          # per_class: true -> MeanIoU_<c>; the checkpoint criterion is their mean
+            metrics = {**metrics, "MeanIoU": float(np.mean(list(metrics.values())))}
         if output_dir and valid_stats["loss"] < best_loss:
             best_loss = valid_stats["loss"]
             misc.save_model(config, os.path.join(output_dir, "best-loss.pth"), epoch, model, optimizer, loss_scaler,
@@ -178,6 +176,6 @@ def test(config):
     model.to(device)
     if config.get("resume"):
         model.load_state_dict(torch.load(config["resume"], map_location="cpu", weights_only=False)["model"])
-    stats, metrics, _, _ = evaluate(model, ld, device, None, use_amp=config.get("use_amp", True))
+    stats, metrics, _, _ = evaluate(model, ld, device, config.get("metric"), use_amp=config.get("use_amp", True))
     print({**stats, **metrics})
     return stats, metrics

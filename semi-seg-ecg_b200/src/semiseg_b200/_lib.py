@@ -81,6 +81,7 @@ SIGNATURES = {
     "ssb_bn_bwd_reduce": [_P, _P, _P, _P, _BNP, _P, _BNP, Geom, _I, _P],
     "ssb_bn_bwd_apply": [_P, _P, _P, _P, _BNP, _P, _P, _BNP, _P, _P, Geom, _I, _P],
     "ssb_bn_bwd_fused_fits": [Geom, _I, _I, _I],
+    "ssb_eval_metrics": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
     "ssb_bn_bwd_fused": [_P, _P, _P, _BNP, _P, _P, _BNP, _P, _P, Geom, _P, _P, _P, _SZ, _I, _P],
     "ssb_stem_bwd_reduce": [_P, _P, _P, _BNP, Geom, Geom, _I, _P],
     "ssb_stem_bwd_apply": [_P, _P, _P, _BNP, _P, Geom, Geom, _I, _P],

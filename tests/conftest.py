@@ -37,6 +37,13 @@ def golden_semi():
     return np.load(os.path.join(REPO, "tests", "golden", "semi_vectors.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_eval():
+    """case H (evaluate), tests/golden/make_golden_eval.py"""
+    import numpy as np
+    return np.load(os.path.join(REPO, "tests", "golden", "eval_vectors.npz"))
+
+
 def golden_group(g, prefix):
     """{'name': array} for all keys under 'prefix/'."""
     pre = prefix + "/"

@@ -51,3 +51,12 @@ def model_cfg(num_leads, stem, base, head_ch, dropout):
                                     "concat_input": False, "dropout_ratio": dropout, "num_classes": 4,
                                     "align_corners": False}},
     }
+
+
+def eval_batches(g):
+    """the batches of golden case H (tests/golden/make_golden_eval.py): sizes 5, 5, 2"""
+    out = []
+    for i, n in enumerate(g["H/sizes"].tolist()):
+        lab, _ = synthetic.make_batch(int(g["H/data_seed"]) + i, int(n), 1, 2, 300)
+        out.append({k: torch.from_numpy(v) for k, v in lab.items()})
+    return out

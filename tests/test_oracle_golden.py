@@ -133,6 +133,33 @@ def test_stpp_steps(golden_semi):
         assert np.array_equal(g[f"G/teacher/{name}"], refv), name
 
 
+def test_evaluate_oracle_matches_reference(golden_eval):
+    """oracle/eval_oracle.evaluate vs the reference's base.evaluate (case H): loss, soft-max outputs, one-hot labels and
+    -- with the restated torchmetrics MeanIoU on both sides -- the metric in its three configurations."""
+    from helpers import eval_batches
+    from oracle import eval_oracle
+    g = golden_eval
+    sd = sd_from(g, "H/model")
+    bs = eval_batches(g)
+    for tag, kw in (("H", {}), ("Hnb", {"include_background": False}), ("Hpc", {"per_class": True})):
+        stats, metrics, outputs, preds = eval_oracle.evaluate(sd, TINY_ARCH, bs, **kw)
+        assert abs(stats["loss"] - float(g[f"{tag}/stats/loss"])) < 1e-5
+        ref = group(g, f"{tag}/metrics")
+        assert set(metrics) == set(ref)
+        for k in ref:
+            assert abs(metrics[k] - float(ref[k])) < 1e-9, (tag, k, metrics[k], float(ref[k]))
+    assert rel_err(outputs, g["H/outputs"]) < 1e-5
+    assert np.array_equal(preds.numpy(), g["H/outputs"].argmax(1))
+    onehot = torch.nn.functional.one_hot(torch.cat([b["target"] for b in bs]), 4).movedim(-1, 1).numpy()
+    assert np.array_equal(onehot, g["H/labels_onehot"])
+    # the aggregation really is a mean of per-batch means of per-sample IoUs: it differs from the pooled IoU
+    conf = np.zeros((4, 4))
+    for yt, yp in zip(torch.cat([b["target"] for b in bs]).numpy().ravel(), preds.numpy().ravel()):
+        conf[yt, yp] += 1
+    pooled = np.mean(np.diag(conf) / np.maximum(conf.sum(0) + conf.sum(1) - np.diag(conf), 1))
+    assert abs(pooled - float(g["H/metrics/MeanIoU"])) > 1e-3
+
+
 def test_full_size_step_scalars(golden):
     """resnet18 @ 1x2500, one FixMatch step: losses, mask ratio and all 65 gradient norms."""
     import models.backbones  # product constructors give the seeded init (checked bit-exact in test_surface)
