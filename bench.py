@@ -492,6 +492,13 @@ def other_algorithm_rates(cfg, dev, dtype, C, L, Bl, Bu, batch, steps=100):
                       launches_per_step=e1.launches_per_step + e2.launches_per_step,
                       note="two models trained per step; the two training graphs run side by side")
     assert all(np.isfinite(s_["loss_total"]) for s_ in cps.read_stats())
+    # evaluation path: eval forward + fused metric tail as one graph, batch = B_l + B_u strips
+    from semiseg_b200.evaluate import EvalEngine
+    xe, ye = torch.cat((x, uw)), torch.cat((y, y))
+    ev = EvalEngine(m1.runtime().weights, dtype, Bl + Bu, L)
+    ev.refresh_weights()
+    out["evaluate"] = dict(rate(lambda: None, lambda: ev.run(xe, ye)), launches_per_batch=ev.launches,
+                           note="eval-mode forward with BN folded into the conv epilogues + ssb_eval_metrics; device-resident batch")
     return out
 
 

@@ -76,11 +76,13 @@ class EvalEngine:
              self.spec.num_classes, 1 if self.spec.align_corners else 0, st)
         self.launches = int(_lib.load().ssb_launch_count() - n0)
 
-    def run(self, ecg: torch.Tensor, target: torch.Tensor) -> None:
+    def run(self, ecg: torch.Tensor, target: Optional[torch.Tensor] = None) -> None:
         """One batch (host or device tensors): afterwards self.sums / self.counts (/ probs / pred) hold its results
-        on the device, in stream order."""
+        on the device, in stream order.  target None (inference): the loss / count outputs refer to the stale labels
+        and are meaningless."""
         self.x.copy_(ecg, non_blocking=True)
-        self.y.copy_(target, non_blocking=True)
+        if target is not None:
+            self.y.copy_(target, non_blocking=True)
         if self.use_graph:
             if self.graph is None:
                 g = torch.cuda.CUDAGraph()
@@ -149,3 +151,46 @@ def evaluate_loader(model, data_loader, device, use_amp: bool = True, include_ba
     outputs = torch.cat(outs, dim=0) if want_outputs else None
     labels = torch.cat(labs, dim=0) if want_outputs else None
     return {"loss": loss}, metrics, outputs, labels
+
+
+@torch.no_grad()
+def predict_loader(model, data_loader, device, use_amp: bool = False) -> torch.Tensor:
+    """The loop of the reference's inference script (src/inference.py:108-119): soft-max outputs [N, ncls, L] of every
+    batch of the loader, on the CPU.  Same graph as evaluation (the probabilities are an output of ssb_eval_metrics);
+    device-to-host copies go through a pinned double buffer and overlap the next batch."""
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("inference: the B200 path needs device='cuda' (no CPU fallback)")
+    model.eval()
+    rt = model.runtime()
+    rt.ensure()
+    precision = getattr(model, "precision", None)
+    dtype = {"fp32": _lib.F32, "bf16": _lib.BF16}[precision] if precision else (_lib.BF16 if use_amp else _lib.F32)
+    engines = rt.__dict__.setdefault("eval_engines", {})
+    fresh = set()
+    outs: List[torch.Tensor] = []
+    pending: List[Tuple[torch.Tensor, torch.cuda.Event]] = []
+    for samples in data_loader:
+        ecg = samples["ecg"]
+        B, _, L = ecg.shape
+        key = (dtype, B, L, True)
+        if key not in engines:
+            engines[key] = EvalEngine(rt.weights, dtype, B, L, want_outputs=True)
+        eng = engines[key]
+        if key not in fresh:
+            eng.refresh_weights()
+            fresh.add(key)
+        eng.run(ecg, None)
+        host = torch.empty(eng.probs.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(eng.probs, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        pending.append((host, ev))
+        if len(pending) > 1:              # the previous batch's copy has had a whole batch of compute to finish
+            h, e = pending.pop(0)
+            e.synchronize()
+            outs.append(h)
+        # the next run() overwrites eng.probs: stream order keeps the copy above ahead of it
+    for h, e in pending:
+        e.synchronize()
+        outs.append(h)
+    return torch.cat(outs, dim=0) if outs else torch.empty(0)

@@ -115,6 +115,17 @@ def test_evaluate_bf16_and_after_training(golden_eval):
     assert stats2["loss"] != stats["loss"] and np.isfinite(stats2["loss"])
 
 
+def test_predict_loader_matches_reference_outputs(golden_eval):
+    """the inference loop (reference inference.py:108-119): soft-max outputs of every batch, on the CPU"""
+    from semiseg_b200.evaluate import predict_loader
+    g = golden_eval
+    out = predict_loader(_model(g), [{"ecg": b["ecg"]} for b in eval_batches(g)], torch.device(DEV), use_amp=False)
+    assert out.device.type == "cpu" and tuple(out.shape) == g["H/outputs"].shape
+    assert rel_err(out, g["H/outputs"]) < 1e-5
+    with pytest.raises(RuntimeError):
+        predict_loader(_model(g), [], torch.device("cpu"))
+
+
 def test_mean_iou_from_counts_semantics():
     """a class absent from prediction and target scores 0 (torchmetrics _safe_divide), not NaN and not skipped"""
     counts = torch.tensor([[[5, 10, 5], [0, 0, 0], [0, 3, 0]]], device=DEV)
