@@ -41,7 +41,7 @@ def build_seg_dataset(cfg: dict, split: str, mode: str = None, num_unlabeled: in
     if split == "train_labeled" and num_unlabeled:
         n = num_unlabeled  # labeled set tiled to the unlabeled length (semi_dataset.py:86-95)
     return SyntheticSemiSegDataset(n, int(syn.get("num_leads", 1)), int(cfg.get("signal_length", 2500)), labeled,
-                                   seed=hash(split) % 1000)
+                                   seed={"train_labeled": 11, "train_unlabeled": 23, "valid": 37, "test": 41}.get(split, 53))
 
 
 def get_dataloader(dataset, is_distributed: bool = False, mode: str = "train", **kwargs):

@@ -1,5 +1,5 @@
 """Emit the YAML configs of the drop-in surface (schema and values of the reference's
-configs/base/resnet18/{scratch,fixmatch,mean_teacher}.yaml and configs/bench/**; SURVEY.md
+configs/base/resnet18/{scratch,fixmatch,mean_teacher,cps,stpp}.yaml and configs/bench/**; SURVEY.md
 sections 5 and 8d).  Written from the schema description, not copied; run once, output committed."""
 import copy
 import os
@@ -24,7 +24,7 @@ def base(algorithm: str) -> dict:
                     "filter": [{"highpass_filter": {"fs": 250, "cutoff": 0.67}},
                                {"lowpass_filter": {"fs": 250, "cutoff": 40}}],
                     "augmentations": [{"random_resize_crop": {"target_length": 2500, "scale_min": 0.5, "scale_max": 2.0}}]})
-    if algorithm != "base":
+    if algorithm not in ("base", "cps"):      # CPS trains on the weak view only
         dataset["strong_augmentations"] = strong
     dataset["transforms"] = [{"standardize": {"axis": [-1, -2]}}, {"to_tensor": {"dtype": "float"}}]
     train = {"epochs": 100, "accum_iter": 1, "warmup_epochs": 10, "min_lr": 0.0001, "blr": None, "lr": 0.001,
@@ -32,7 +32,7 @@ def base(algorithm: str) -> dict:
              "optimizer_kwargs": {"betas": [0.9, 0.999]}, "auxiliary_loss_weight": [0.4]}
     if algorithm == "fixmatch":
         train["conf_thresh"] = 0.80
-    if algorithm == "mean_teacher":
+    if algorithm in ("mean_teacher", "stpp"):
         train["ema_decay"] = 0.99
     name = {"base": "scratch"}.get(algorithm, algorithm)
     return {
@@ -76,7 +76,8 @@ def dump(path: str, obj: dict):
 
 
 if __name__ == "__main__":
-    for algo, fname in (("base", "scratch"), ("fixmatch", "fixmatch"), ("mean_teacher", "mean_teacher")):
+    for algo, fname in (("base", "scratch"), ("fixmatch", "fixmatch"), ("mean_teacher", "mean_teacher"), ("cps", "cps"),
+                        ("stpp", "stpp")):
         cfg = base(algo)
         dump(os.path.join(ROOT, "base", "resnet18", f"{fname}.yaml"), cfg)
         dump(os.path.join(ROOT, "base", f"{fname}.yaml"), cfg)  # README-style alias path
