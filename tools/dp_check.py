@@ -59,9 +59,16 @@ if rank == 0:
     # one step: the sharded run IS the single-process run up to summation order.  More steps: Adam's early updates are
     # sign-like (m/sqrt(v) = +-1), so 1e-6 gradient differences move near-zero tensors (BN biases, |beta| ~ lr) by a
     # fraction of lr -- bound the ABSOLUTE drift by one learning-rate step instead
+    # fraction of lr -- and a gradient element at rounding level may take the other SIGN on the two sides (update differs by
+    # 2 lr in that one element): bound the absolute drift by the steps taken, and the number of elements beyond a tenth
+    # of a learning-rate step to 1e-4 of all elements after one step (measured: 7 of 4.05 M), 1 % after more (measured 0.4 %
+    # after three: the second and third updates divide by sqrt(v) of the same near-zero gradients)
     if nsteps == 1:
         assert worst < 1e-4, worst
-    assert errs[0][1] < 5e-4 and max(a for _, a, _ in errs) < 5e-4, errs[:3]
+    big = sum(int(((sd_dp[k].double() - sd_1[k].double()).abs() > 5e-5).sum()) for k in sd_1 if "tracked" not in k)
+    total = sum(sd_1[k].numel() for k in sd_1 if "tracked" not in k)
+    print(f"elements drifting by more than 5e-5: {big} of {total}; largest drift {max(a for _, a, _ in errs):.2e}")
+    assert max(a for _, a, _ in errs) < 2.5 * 5e-4 * nsteps and big < (1e-4 if nsteps == 1 else 1e-2) * total, (errs[:3], big, total)
     assert abs(float(t[0]) - st_1[-1]["loss_total"]) < 1e-4
     print("DP equivalence OK")
 torch.cuda.synchronize()
