@@ -55,8 +55,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef SSB_BOUNDED_WAIT
+  // development builds (make NVFLAGS+=-DSSB_BOUNDED_WAIT): a pipeline-protocol error becomes a launch failure after
+  // ~2 s instead of a hung device.  Not in the product build: the clock reads in the single-thread producer / MMA
+  // issue loops cost 1.7 % of the conv kernels at large batch and 0.3 % of the config-2 step (measured).
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) asm volatile("trap;");
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile(
