@@ -44,6 +44,13 @@ def golden_eval():
     return np.load(os.path.join(REPO, "tests", "golden", "eval_vectors.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_arch():
+    """case R (resnet34), tests/golden/make_golden_arch.py"""
+    import numpy as np
+    return np.load(os.path.join(REPO, "tests", "golden", "arch_vectors.npz"))
+
+
 def golden_group(g, prefix):
     """{'name': array} for all keys under 'prefix/'."""
     pre = prefix + "/"

@@ -160,6 +160,39 @@ def test_evaluate_oracle_matches_reference(golden_eval):
     assert abs(pooled - float(g["H/metrics/MeanIoU"])) > 1e-3
 
 
+R34_ARCH = dataclasses.replace(TINY_ARCH, stage_blocks=(3, 4, 6, 3))
+
+
+def test_resnet34_oracle_matches_reference(golden_arch):
+    """the oracle's BasicBlock stack at depth 3-4-6-3 vs the reference's resnet34 (case R): train forward + loss +
+    every gradient + running statistics, eval logits, two FixMatch steps"""
+    g = golden_arch
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in sd_from(g, "R/init").items()}
+    (lab, _), = batches(int(g["R/data_seed"]), 1, 4, 1, 2, 300)
+    tr = O.OracleTrainer(sd, R34_ARCH, TRAIN_CFG, dtype=torch.float64)
+    st = tr.supervised_step(lab["ecg"], lab["target"], 0.0)
+    assert abs(st["loss"] - float(g["R/loss"])) < 1e-5
+    for n, refv in group(g, "R/grad").items():
+        assert rel_err(tr.grads[n], refv) < 2e-5, n
+    for n, refv in group(g, "R/after_train_fwd").items():
+        if "tracked" in n:
+            assert int(tr.sd[n]) == int(refv)
+        else:
+            assert rel_err(tr.sd[n], refv) < 1e-5, n
+    with torch.no_grad():     # (lr 0: the step above left the parameters alone and updated the running statistics once)
+        ev = O.forward(tr.sd, lab["ecg"].double(), R34_ARCH, False)["seg_logits"]
+    assert rel_err(ev, g["R/seg_logits_eval"]) < 1e-5
+    cfg = dict(TRAIN_CFG, conf_thresh=float(g["R2/conf_thresh"]))
+    tr = O.OracleTrainer(sd_from(g, "R2/init"), R34_ARCH, cfg, dtype=torch.float64)
+    stats = []
+    for it, (lab, unl) in enumerate(batches(int(g["R2/data_seed"]), 2, 3, 3, 2, 300)):
+        stats.append(tr.fixmatch_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], O.lr_at(it / 2 + 3, cfg)))
+    ref = group(g, "R2/stats")
+    for k in ("loss_total", "loss_x", "loss_u_s", "mask_ratio"):
+        assert abs(float(np.mean([s[k] for s in stats])) - float(ref[k])) < 2e-5, k
+    _check_final(tr.sd, g, "R2/final")
+
+
 def test_full_size_step_scalars(golden):
     """resnet18 @ 1x2500, one FixMatch step: losses, mask ratio and all 65 gradient norms."""
     import models.backbones  # product constructors give the seeded init (checked bit-exact in test_surface)

@@ -295,6 +295,86 @@ def test_cps_full_size_vs_oracle(golden, dtype, tol):
     assert all(verified), "no coincidence-free batch for one of the models"
 
 
+def _cfg34(dropout=0.0):
+    c = tiny_cfg(dropout)
+    c["backbone"] = {"resnet34": c["backbone"]["resnet18"]}
+    return c
+
+
+def test_resnet34_module_and_steps_golden(golden_arch):
+    """Another member of the BasicBlock family behind the same registry: resnet34, 3-4-6-3
+    blocks, against the reference (case R): module-API train forward + loss + every gradient + running statistics,
+    eval logits, then two FixMatch steps of the engine."""
+    g = golden_arch
+    model = build(_cfg34(), sd_from(g, "R/init"))
+    assert len(model.runtime().ensure().layout.blocks) == 16
+    model.precision = "fp32"
+    (lab, _), = batches(int(g["R/data_seed"]), 1, 4, 1, 2, 300)
+    x, y = lab["ecg"].to(DEV), lab["target"].to(DEV)
+    model.train()
+    out = model(x, y, return_loss=True)
+    out["loss"].backward()
+    # yardstick: the fp64 oracle (pinned to case R by tests/test_oracle_golden.py); 1e-5, or 4x the error the
+    # reference's own fp32 run (the golden vectors) shows against it through these 34 layers
+    import dataclasses
+    arch34 = dataclasses.replace(TINY_ARCH, stage_blocks=(3, 4, 6, 3))
+    tr = O.OracleTrainer(sd_from(g, "R/init"), arch34, TRAIN_CFG, dtype=torch.float64)
+    with torch.no_grad():
+        truth = O.forward(tr.sd, lab["ecg"].double(), arch34, True, None, {}, None)["seg_logits"]
+    tr.supervised_step(lab["ecg"], lab["target"], 0.0)
+    e, e32 = rel_err(out["seg_logits"], truth), rel_err(g["R/seg_logits_train"], truth)
+    assert e < max(1e-5, 4 * e32), (e, e32)
+    assert abs(float(out["loss"].detach()) - float(g["R/loss"])) < 1e-5
+    grads = dict(model.named_parameters())
+    bad = []
+    for n, refv in group(g, "R/grad").items():
+        e, e32 = rel_err(grads[n].grad, tr.grads[n]), rel_err(refv, tr.grads[n])
+        if not e < max(1e-5, 4 * e32):
+            bad.append((n, e, e32))
+    assert not bad, bad
+    sd = model.state_dict()
+    for n, refv in group(g, "R/after_train_fwd").items():
+        if "tracked" in n:
+            assert int(sd[n]) == int(refv)
+        else:
+            assert rel_err(sd[n], refv) < 1e-5, n
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(model(x)["seg_logits"], g["R/seg_logits_eval"]) < 1e-5
+    # engine steps
+    cfg = dict(TRAIN_CFG, conf_thresh=float(g["R2/conf_thresh"]))
+    model = build(_cfg34(), sd_from(g, "R2/init"))
+    eng = get_engine("fixmatch", model, None, 3, 3, 300, _lib.F32, cfg)
+    for it, (lab, unl) in enumerate(batches(int(g["R2/data_seed"]), 2, 3, 3, 2, 300)):
+        eng.load_batch(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"])
+        eng.step(O.lr_at(it / 2 + 3, cfg))
+    stats = eng.read_stats()
+    ref = group(g, "R2/stats")
+    for k in ("loss_total", "loss_x", "loss_u_s", "mask_ratio"):
+        assert abs(float(np.mean([s_[k] for s_ in stats])) - float(ref[k])) < 5e-5 * max(1.0, abs(float(ref[k]))), k
+    _check_final(model.state_dict(), g, "R2/final")
+
+
+def test_resnet34_bf16_full_width_step_runs():
+    """resnet34 at the shipped widths through the tcgen05 path: finite losses, bf16 loss close to the fp32 path's."""
+    from algorithms.base import init_model_from_cfg
+    cfgm = model_cfg(1, 64, 64, 128, 0.0)
+    cfgm["backbone"] = {"resnet34": cfgm["backbone"]["resnet18"]}
+    (lab, unl), = batches(830, 1, 4, 4, 1, 2500)
+    losses = {}
+    for dtype in (_lib.F32, _lib.BF16):
+        torch.manual_seed(5)
+        model = init_model_from_cfg(cfgm).to(DEV)
+        eng = get_engine("fixmatch", model, None, 4, 4, 2500, dtype, dict(TRAIN_CFG, conf_thresh=0.3))
+        eng.load_batch(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"])
+        eng.step(1e-3)
+        s_, = eng.read_stats()
+        assert all(np.isfinite(v) for v in s_.values())
+        losses[dtype] = s_
+    for k in ("loss_total", "loss_x"):
+        assert abs(losses[_lib.BF16][k] - losses[_lib.F32][k]) < 2e-2 * max(1.0, abs(losses[_lib.F32][k])), (k, losses)
+
+
 _ORACLE_CACHE = {}
 
 
