@@ -18,7 +18,7 @@ def test_every_base_config_builds_a_model():
     from algorithms.base import init_model_from_cfg
     from utils.config import load_config
     files = sorted(glob.glob(os.path.join(CONFIGS, "base", "**", "*.yaml"), recursive=True))
-    assert len(files) >= 6
+    assert len(files) >= 10
     for f in files:
         cfg = load_config(f, os.path.join(CONFIGS, "bench", "ludb", "1over16.yaml"))
         assert cfg["exp_name"] == "ludb/1over16" and cfg["dataset"]["signal_length"] == 2500
@@ -30,9 +30,65 @@ def test_every_base_config_builds_a_model():
 
 def test_algorithm_registry():
     import algorithms
-    for name in ("base", "fixmatch", "mean_teacher"):
+    for name in ("base", "scratch", "fixmatch", "mean_teacher", "cps", "stpp"):
         mod = algorithms.__dict__[name]
         assert callable(mod.train) and callable(mod.test) and callable(mod.train_one_epoch)
+
+
+def test_entry_point_signatures_follow_the_reference():
+    """positional parameter names of the reference's entry points (base.py:83-93,184-191; fixmatch.py:28-39;
+    mean_teacher.py:28-40; cps.py:28-41; stpp.py:91-103; inference.py:75)"""
+    import inspect
+
+    import algorithms
+    import inference
+    common = ["device", "epoch", "loss_scaler", "log_writer", "use_amp", "config"]
+    expect = {
+        "base": ["model", "data_loader", "optimizer"] + common,
+        "fixmatch": ["model", "labeled_data_loader", "unlabeled_data_loader", "optimizer"] + common,
+        "mean_teacher": ["model_student", "model_teacher", "labeled_data_loader", "unlabeled_data_loader", "optimizer"] + common,
+        "cps": ["model_1", "model_2", "labeled_data_loader", "unlabeled_data_loader", "optimizer_1", "optimizer_2"] + common,
+        "stpp": ["model_student", "model_teacher", "labeled_data_loader", "unlabeled_data_loader", "optimizer"] + common,
+    }
+    for name, params in expect.items():
+        sig = inspect.signature(algorithms.__dict__[name].train_one_epoch)
+        assert list(sig.parameters) == params, name
+        assert sig.parameters["use_amp"].default is True and sig.parameters["log_writer"].default is None
+    ev = inspect.signature(algorithms.base.evaluate)
+    assert list(ev.parameters)[:5] == ["model", "data_loader", "device", "metric_fn", "use_amp"]
+    assert list(inspect.signature(algorithms.stpp.select_reliable).parameters) == ["models", "dataloader", "device"]
+    assert list(inspect.signature(algorithms.stpp.calculate_miou).parameters) == ["onehot_preds", "onehot_labels", "ignore_background"]
+    assert list(inspect.signature(inference.inference).parameters) == ["config"]
+
+
+def test_stpp_calculate_miou():
+    """reference stpp.py:32-43: mean over classes of intersection / union on one-hot arrays, 0 for an empty union"""
+    from algorithms.stpp import calculate_miou
+    p = np.zeros((1, 3, 6), dtype=np.int64)
+    t = np.zeros((1, 3, 6), dtype=np.int64)
+    p[0, 0, :4] = 1; p[0, 1, 4:] = 1
+    t[0, 0, :2] = 1; t[0, 1, 2:] = 1
+    assert abs(calculate_miou(p, t) - (2 / 4 + 2 / 4 + 0.0) / 3) < 1e-12
+    assert abs(calculate_miou(p, t, ignore_background=True) - (2 / 4 + 0.0) / 2) < 1e-12
+
+
+def test_mean_iou_restatement_follows_torchmetrics_semantics():
+    """oracle/eval_oracle.MeanIoU and semiseg_b200.evaluate.mean_iou_from_counts agree; per-sample IoU, empty union -> 0,
+    batch mean accumulated per update() and divided by the number of batches (torchmetrics 1.5.2)"""
+    from oracle.eval_oracle import MeanIoU
+    from semiseg_b200.evaluate import mean_iou_from_counts
+    rng = np.random.RandomState(0)
+    m = MeanIoU(4)
+    per_batch = []
+    for n in (3, 1):
+        pred, tgt = rng.randint(0, 3, (n, 50)), rng.randint(0, 3, (n, 50))     # class 3 never occurs
+        oh = lambda a: torch.nn.functional.one_hot(torch.from_numpy(a), 4).movedim(-1, 1)   # noqa: E731
+        m.update(oh(pred), oh(tgt))
+        counts = torch.tensor([[[int(((pred[i] == c) & (tgt[i] == c)).sum()), int((pred[i] == c).sum()), int((tgt[i] == c).sum())]
+                                for c in range(4)] for i in range(n)])
+        per_batch.append(float(mean_iou_from_counts(counts).mean()))
+    assert abs(float(m.compute()) - float(np.mean(per_batch))) < 1e-12
+    assert float(m.compute()) < 0.75        # the absent class contributes a 0 to every sample's class mean
 
 
 def test_state_dict_matches_reference_golden(golden):
