@@ -476,12 +476,12 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 #define BWF_KEEP 0
 #endif
 #ifndef BWF_MINB
-#define BWF_MINB 1
+#define BWF_MINB 1     // forcing 64 registers (4 blocks per SM, 324-block grids) was measured SLOWER: 0.710 vs 0.700 ms
 #endif
 #define BWF_REP 8      // replicated accumulators: block b adds into replica b % 8 (8x less same-address contention)
 
 template <typename T, bool HAS_Y, int RES>
-__global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(const T* __restrict__ g1, const T* __restrict__ y,
+__global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fused_kernel(const T* __restrict__ g1, const T* __restrict__ y,
                                                                   const T* __restrict__ x, const T* __restrict__ xr,
                                                                   T* __restrict__ dx, T* __restrict__ dxr, T* __restrict__ gid,
                                                                   ssb_bn bn, ssb_bn bnr, ssb_geom g, int cgpc, int rpb,
@@ -898,6 +898,8 @@ static bool bwd_fused_plan(const ssb_geom& g, int mode, bool has_y, int* cgpc_o,
                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 2>, BN_THREADS, 0);
   if (oe != cudaSuccess) occ = 0;
   // co-resident capacity with one block per SM left as slack; the rows are spread over at most that many blocks
+  // (measured at config 2: 216 blocks -- this cap at 3 blocks per SM -- 0.700 ms per step; 148 blocks 0.716; 324 blocks
+  // at a forced 64 registers 0.710)
   const long long cap = occ >= 2 ? 148LL * (occ - 1) : 0;
   int nx = cap / ny > 0 ? (int)(cap / ny) : 0;
   const int want = ceil_div(rows, rpp * BWF_ROWS);
