@@ -492,6 +492,19 @@ def other_algorithm_rates(cfg, dev, dtype, C, L, Bl, Bu, batch, steps=100):
                       launches_per_step=e1.launches_per_step + e2.launches_per_step,
                       note="two models trained per step; the two training graphs run side by side")
     assert all(np.isfinite(s_["loss_total"]) for s_ in cps.read_stats())
+    # other members of the backbone family behind the same registry: FixMatch step, same batch
+    import copy
+    for name, head_in in (("resnet34", 512), ("resnet50", 2048)):
+        c2 = copy.deepcopy(cfg)
+        c2["backbone"] = {name: c2["backbone"]["resnet18"]}
+        c2["decode_head"]["FCNHead"]["in_channels"] = head_in
+        mm = init_model_from_cfg(c2).to(dev)
+        ee = get_engine("fixmatch", mm, None, Bl, Bu, L, dtype, dict(cfg["train"]))
+        out[f"fixmatch_{name}"] = dict(rate(lambda: ee.load_batch(x, y, uw, us), lambda: ee.step(lr)),
+                                       launches_per_step=ee.launches_per_step,
+                                       params=int(sum(p_.numel() for p_ in mm.parameters())))
+        assert all(np.isfinite(s_["loss_total"]) for s_ in ee.read_stats())
+        del ee, mm
     # evaluation path: eval forward + fused metric tail as one graph, batch = B_l + B_u strips
     from semiseg_b200.evaluate import EvalEngine
     xe, ye = torch.cat((x, uw)), torch.cat((y, y))

@@ -47,13 +47,19 @@ class Arch:
     in_index: int = 3
     dropout_ratio: float = 0.1
     align_corners: bool = False
+    bottleneck: bool = False      # Bottleneck blocks (resnet.py:75-132): 1x1 - 3x3(stride) - 1x1(x4), expansion 4
+
+    @property
+    def expansion(self) -> int:
+        return 4 if self.bottleneck else 1
 
     @staticmethod
     def from_config(cfg: dict) -> "Arch":
         """YAML dict -> Arch (algorithms/base.py:32-43 reads the same two sub-dicts)."""
         bname, bkw = list(cfg["backbone"].items())[0]
         hname, hkw = list(cfg["decode_head"].items())[0]
-        blocks = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}[bname]
+        blocks = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3), "resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3),
+                  "resnet152": (3, 8, 36, 3)}[bname]
         ns = bkw.get("num_stages", 4)
         return Arch(
             num_leads=bkw["num_leads"],
@@ -66,6 +72,7 @@ class Arch:
             in_index=hkw.get("in_index", -1),
             dropout_ratio=hkw.get("dropout_ratio", 0.1),
             align_corners=hkw.get("align_corners", False),
+            bottleneck=bname in ("resnet50", "resnet101", "resnet152"),
         )
 
     def planes(self, i: int) -> int:
@@ -99,10 +106,12 @@ def param_names(arch: Arch) -> List[str]:
             pre = f"backbone.layer{i + 1}.{j}"
             names += [f"{pre}.conv1.weight", f"{pre}.bn1.weight", f"{pre}.bn1.bias",
                       f"{pre}.conv2.weight", f"{pre}.bn2.weight", f"{pre}.bn2.bias"]
-            if j == 0 and (arch.strides[i] != 1 or inpl != pl):
+            if arch.bottleneck:
+                names += [f"{pre}.conv3.weight", f"{pre}.bn3.weight", f"{pre}.bn3.bias"]
+            if j == 0 and (arch.strides[i] != 1 or inpl != pl * arch.expansion):
                 names += [f"{pre}.downsample.0.weight", f"{pre}.downsample.1.weight",
                           f"{pre}.downsample.1.bias"]
-        inpl = pl
+        inpl = pl * arch.expansion
     names += ["decode_head.convs.0.0.weight", "decode_head.convs.0.1.weight",
               "decode_head.convs.0.1.bias", "decode_head.cls_seg.weight", "decode_head.cls_seg.bias"]
     return names
@@ -203,7 +212,8 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
     """
     q = quant if quant is not None else (lambda t: t)
     if quant is not None:
-        sd = {k: (q(v) if (k.endswith("conv1.weight") or k.endswith("conv2.weight") or k.endswith("downsample.0.weight")
+        sd = {k: (q(v) if (k.endswith("conv1.weight") or k.endswith("conv2.weight") or k.endswith("conv3.weight")
+                           or k.endswith("downsample.0.weight")
                            or k == "decode_head.convs.0.0.weight") else v) for k, v in sd.items()}
     def tap(name, t):
         if taps is not None:
@@ -225,6 +235,25 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
             pre = f"backbone.layer{i + 1}.{j}"
             s = arch.strides[i] if j == 0 else 1
             ident = h
+            if arch.bottleneck:       # resnet.py:112-132: 1x1 - BN - ReLU - 3x3(stride) - BN - ReLU - 1x1 - BN (+ identity) - ReLU
+                o = q(F.conv1d(h, sd[pre + ".conv1.weight"], None))
+                tap(pre + ".conv1", o)
+                o = q(torch.relu(batchnorm(o, sd, pre + ".bn1", train, new_buffers)))
+                tap(pre + ".relu1", o)
+                o = q(F.conv1d(o, sd[pre + ".conv2.weight"], None, stride=s, padding=1))
+                tap(pre + ".conv2", o)
+                o = q(torch.relu(batchnorm(o, sd, pre + ".bn2", train, new_buffers)))
+                tap(pre + ".relu2", o)
+                o = q(F.conv1d(o, sd[pre + ".conv3.weight"], None))
+                tap(pre + ".conv3", o)
+                o = batchnorm(o, sd, pre + ".bn3", train, new_buffers)
+                if (pre + ".downsample.0.weight") in sd:
+                    ident = q(F.conv1d(h, sd[pre + ".downsample.0.weight"], None, stride=s, padding=0))
+                    tap(pre + ".downsample.0", ident)
+                    ident = batchnorm(ident, sd, pre + ".downsample.1", train, new_buffers)
+                h = q(torch.relu(o + ident))
+                tap(pre, h)
+                continue
             o = q(F.conv1d(h, sd[pre + ".conv1.weight"], None, stride=s, padding=1))
             tap(pre + ".conv1", o)
             o = q(torch.relu(batchnorm(o, sd, pre + ".bn1", train, new_buffers)))

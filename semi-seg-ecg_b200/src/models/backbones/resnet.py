@@ -15,6 +15,7 @@ import torch.nn as nn
 __all__ = ["ResNet", "resnet18", "resnet34", "resnet50", "resnet101", "resnet152"]
 
 _BASIC_LAYOUTS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+_BOTTLENECK_LAYOUTS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3), "resnet152": (3, 8, 36, 3)}
 
 
 class BasicBlock(nn.Module):
@@ -38,6 +39,29 @@ class BasicBlock(nn.Module):
         raise RuntimeError("BasicBlock is a parameter container; run the model through EncoderDecoder")
 
 
+class Bottleneck(nn.Module):
+    """1x1-BN-ReLU - conv3(s)-BN-ReLU - 1x1(x4)-BN (+ 1x1(s)-BN shortcut) -add-ReLU  (reference resnet.py:75-132)."""
+    expansion = 4
+
+    def __init__(self, inplanes: int, planes: int, stride: int, with_shortcut_conv: bool):
+        super().__init__()
+        self.conv1 = nn.Conv1d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm1d(planes)
+        self.conv2 = nn.Conv1d(planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm1d(planes)
+        self.conv3 = nn.Conv1d(planes, planes * self.expansion, 1, bias=False)
+        self.bn3 = nn.BatchNorm1d(planes * self.expansion)
+        self.relu = nn.ReLU(inplace=True)
+        self.downsample = None
+        if with_shortcut_conv:
+            self.downsample = nn.Sequential(nn.Conv1d(inplanes, planes * self.expansion, 1, stride=stride, bias=False),
+                                            nn.BatchNorm1d(planes * self.expansion))
+        self.stride = stride
+
+    def forward(self, x):
+        raise RuntimeError("Bottleneck is a parameter container; run the model through EncoderDecoder")
+
+
 class ResNet(nn.Module):
     def __init__(self, num_leads: int, stem_channels: int = 64, base_channels: int = 64, num_stages: int = 4,
                  strides: Sequence[int] = (1, 2, 2, 2), dilations: Sequence[int] = (1, 1, 1, 1),
@@ -56,8 +80,8 @@ class ResNet(nn.Module):
             unsupported.append("avg_down=True")
         if any(d != 1 for d in dilations) or multi_grid is not None:
             unsupported.append("dilation != 1 / multi_grid")
-        if block is not BasicBlock:
-            unsupported.append("Bottleneck blocks (resnet50/101/152)")
+        if block not in (BasicBlock, Bottleneck):
+            unsupported.append(f"block {block!r}")
         if norm_layer is not nn.BatchNorm1d:
             unsupported.append("norm_layer other than BatchNorm1d")
         if frozen_stages >= 0:
@@ -67,7 +91,7 @@ class ResNet(nn.Module):
         if unsupported:
             raise NotImplementedError(
                 "ResNet variant outside the accelerated hot path: " + ", ".join(unsupported) +
-                " (kernels cover k in {1,3,7}, stride in {1,2}, dilation 1, BasicBlock; SURVEY.md section 2)")
+                " (kernels cover k in {1,3,7}, stride in {1,2}, dilation 1, BasicBlock / Bottleneck; SURVEY.md section 2)")
         self.num_leads = num_leads
         self.stem_channels = stem_channels
         self.base_channels = base_channels
@@ -89,13 +113,16 @@ class ResNet(nn.Module):
             blocks = []
             for j in range(depth):
                 s = self.strides[i] if j == 0 else 1
-                cin = width_in if j == 0 else width
-                blocks.append(BasicBlock(cin, width, s, with_shortcut_conv=(j == 0 and (s != 1 or cin != width))))
+                cin = width_in if j == 0 else width * block.expansion
+                # (the shortcut module is created before the blocks of the stage, like the reference's _make_res_layer,
+                #  resnet.py:267-293 -- but registered under the first block, so the random-init stream is consumed in
+                #  module-traversal order either way: _init_weights walks self.modules())
+                blocks.append(block(cin, width, s, with_shortcut_conv=(j == 0 and (s != 1 or cin != width * block.expansion))))
             name = f"layer{i + 1}"
             self.add_module(name, nn.Sequential(*blocks))
             self.res_layers.append(name)
-            width_in = width
-        self.feat_dim = base_channels * 2 ** (len(self.stage_blocks) - 1)
+            width_in = width * block.expansion
+        self.feat_dim = block.expansion * base_channels * 2 ** (len(self.stage_blocks) - 1)
         self._init_weights()
 
     def _init_weights(self):
@@ -108,7 +135,9 @@ class ResNet(nn.Module):
                 m.bias.data.zero_()
         if self.zero_init_residual:
             for m in self.modules():
-                if isinstance(m, BasicBlock):
+                if isinstance(m, Bottleneck):
+                    nn.init.constant_(m.bn3.weight, 0)
+                elif isinstance(m, BasicBlock):
                     nn.init.constant_(m.bn2.weight, 0)
 
     def no_weight_decay(self):
@@ -120,9 +149,8 @@ class ResNet(nn.Module):
 
 
 def _make(name, num_leads, **kwargs):
-    if name not in _BASIC_LAYOUTS:
-        raise NotImplementedError(f"{name}: Bottleneck ResNets are outside the accelerated hot path "
-                                  "(SURVEY.md section 8f, rank 4)")
+    if name in _BOTTLENECK_LAYOUTS:
+        return ResNet(num_leads=num_leads, block=Bottleneck, stage_blocks=list(_BOTTLENECK_LAYOUTS[name]), **kwargs)
     return ResNet(num_leads=num_leads, block=BasicBlock, stage_blocks=list(_BASIC_LAYOUTS[name]), **kwargs)
 
 

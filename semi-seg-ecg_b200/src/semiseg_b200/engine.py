@@ -84,7 +84,7 @@ class StepEngine:
         # tail rows of the student's own conv launches (NetPlan.forward_merged)
         # (measured: with the multi-branch graph the separate pseudo-label branch overlaps the student forward and
         # wins, 0.76 vs 0.80 ms; in single-stream mode the merged launches win, 0.89 vs 1.00 ms)
-        self.merged = algorithm == "fixmatch" and bool(int(os.environ.get(
+        self.merged = algorithm == "fixmatch" and not weights.layout.spec.bottleneck and bool(int(os.environ.get(
             "SSB_MERGED_EVAL", "0" if int(os.environ.get("SSB_MULTI_STREAM", "1")) else "1")))
         self.x_all = torch.zeros(S + max(self.Bu, 1), Cl, L, dtype=torch.float32, device=dev)
         self.x_s = self.x_all[:S]

@@ -36,13 +36,21 @@ class SegNetSpec:
     num_classes: int = 4
     dropout_ratio: float = 0.1
     align_corners: bool = False
+    bottleneck: bool = False     # Bottleneck blocks (resnet50/101/152): 1x1 - 3x3(stride) - 1x1(x4)
 
     def planes(self, i: int) -> int:
         return self.base_channels * 2 ** i
 
     @property
+    def expansion(self) -> int:
+        return 4 if self.bottleneck else 1
+
+    def out_planes(self, i: int) -> int:
+        return self.planes(i) * self.expansion
+
+    @property
     def feat_dim(self) -> int:
-        return self.planes(len(self.stage_blocks) - 1)
+        return self.out_planes(len(self.stage_blocks) - 1)
 
 
 def conv_out_len(L: int, k: int, s: int, p: int) -> int:
@@ -81,6 +89,8 @@ class BlockDesc:
     convd: Optional[ConvDesc]
     bnd: Optional[BNDesc]
     stage: int
+    conv3: Optional[ConvDesc] = None     # Bottleneck only
+    bn3: Optional[BNDesc] = None
 
 
 ALIGN = 64  # floats; every tensor in an arena starts on a 256-byte boundary
@@ -109,6 +119,21 @@ class ParamLayout:
             for j in range(nb):
                 pre = f"backbone.layer{i + 1}.{j}"
                 s = spec.strides[i] if j == 0 else 1
+                if spec.bottleneck:
+                    po = pl * 4
+                    cin = inpl if j == 0 else po
+                    c1 = self._conv(pre + ".conv1.weight", pl, cin, 1, 1)
+                    b1 = self._bn(pre + ".bn1", pl)
+                    c2 = self._conv(pre + ".conv2.weight", pl, pl, 3, s)
+                    b2 = self._bn(pre + ".bn2", pl)
+                    c3 = self._conv(pre + ".conv3.weight", po, pl, 1, 1)
+                    b3 = self._bn(pre + ".bn3", po)
+                    cd = bd = None
+                    if j == 0 and (s != 1 or inpl != po):
+                        cd = self._conv(pre + ".downsample.0.weight", po, inpl, 1, s)
+                        bd = self._bn(pre + ".downsample.1", po)
+                    self.blocks.append(BlockDesc(pre, c1, b1, c2, b2, cd, bd, i, c3, b3))
+                    continue
                 cin = inpl if j == 0 else pl
                 c1 = self._conv(pre + ".conv1.weight", pl, cin, 3, s)
                 b1 = self._bn(pre + ".bn1", pl)
@@ -119,7 +144,7 @@ class ParamLayout:
                     cd = self._conv(pre + ".downsample.0.weight", pl, inpl, 1, s)
                     bd = self._bn(pre + ".downsample.1", pl)
                 self.blocks.append(BlockDesc(pre, c1, b1, c2, b2, cd, bd, i))
-            inpl = pl
+            inpl = pl * spec.expansion
         self.head_conv = self._conv("decode_head.convs.0.0.weight", spec.head_channels, spec.feat_dim, 3, 1)
         self.head_bn = self._bn("decode_head.convs.0.1", spec.head_channels)
         self.cls_w_off = self._param("decode_head.cls_seg.weight", (spec.num_classes, spec.head_channels, 1))
@@ -377,7 +402,9 @@ class NetPlan:
         assert p_stem >= L0 + 2
         self.g_stem = Geom(B, p_stem, L0, spec.stem_channels)
         self.g_pool = Geom(B, p_pool, Lp, spec.stem_channels)
-        self.g_stage = [Geom(B, pitches[i], lens[i], spec.planes(i)) for i in range(len(lens))]
+        self.g_stage = [Geom(B, pitches[i], lens[i], spec.out_planes(i)) for i in range(len(lens))]
+        # Bottleneck: conv2 / bn2 run at the stage's resolution with `planes` channels
+        self.g_mid = [Geom(B, pitches[i], lens[i], spec.planes(i)) for i in range(len(lens))]
         self.g_head = Geom(B, pitches[-1], lens[-1], spec.head_channels)
         self.Lh = lens[-1]
 
@@ -410,9 +437,17 @@ class NetPlan:
         self.pool_arg = torch.zeros(B * p_pool, spec.stem_channels, dtype=torch.uint8, device=self.device) if train else None
         self.blk_bufs: List[Dict[str, torch.Tensor]] = []
         gin = self.g_pool
+        self.blk_geoms: List[Dict[str, Geom]] = []     # Bottleneck blocks: geometry of conv1's output (block input resolution)
         for bd in self.lay.blocks:
             gout = self.g_stage[bd.stage]
-            bufs = {"c1": act(gout), "a1": act(gout), "c2": act(gout), "out": act(gout)}
+            if bd.conv3 is not None:
+                g1 = Geom(B, gin.pitch, gin.len, bd.conv1.cout)
+                gm = self.g_mid[bd.stage]
+                bufs = {"c1": act(g1), "a1": act(g1), "c2": act(gm), "a2": act(gm), "c3": act(gout), "out": act(gout)}
+                self.blk_geoms.append({"in": gin, "c1": g1, "mid": gm, "out": gout})
+            else:
+                bufs = {"c1": act(gout), "a1": act(gout), "c2": act(gout), "out": act(gout)}
+                self.blk_geoms.append({"in": gin, "out": gout})
             if bd.convd is not None:
                 bufs["cd"] = act(gout)
             self.blk_bufs.append(bufs)
@@ -434,7 +469,8 @@ class NetPlan:
         if train:
             self.dlow = torch.zeros(B, self.Lh, spec.num_classes, dtype=torch.float32, device=self.device)
             self.dc0 = act(self.g_stem)
-            for g in [self.g_pool, self.g_head] + self.g_stage:
+            extra = [g for bg_ in self.blk_geoms if "c1" in bg_ for g in (bg_["c1"], bg_["mid"])]
+            for g in [self.g_pool, self.g_head] + self.g_stage + extra:
                 key = (g.pitch, g.len, g.C)
                 if key not in self._scratch:
                     self._scratch[key] = {n: act(g) for n in ("gA", "gE", "gB", "gC", "gD")}
@@ -442,9 +478,12 @@ class NetPlan:
             # second stream: one buffer each per block, so that the main chain never waits for a wgrad to
             # release a buffer it wants to overwrite
             self.blk_grads: List[Dict[str, torch.Tensor]] = []
-            for bd in self.lay.blocks:
+            for bd, bgm in zip(self.lay.blocks, self.blk_geoms):
                 gout = self.g_stage[bd.stage]
-                bg = {"dc2": act(gout), "dc1": act(gout)}
+                if bd.conv3 is not None:
+                    bg = {"dc3": act(gout), "dc2": act(bgm["mid"]), "dc1": act(bgm["c1"])}
+                else:
+                    bg = {"dc2": act(gout), "dc1": act(gout)}
                 if bd.convd is not None:
                     bg["dcd"] = act(gout)
                 self.blk_grads.append(bg)
@@ -589,8 +628,18 @@ class NetPlan:
         if not tm:
             # eval mode: BatchNorm is a fixed affine map -> folded, with the residual add and the ReLU, into
             # the conv epilogue (one launch per conv, no pre-activation tensors)
-            for bd, bufs in zip(lay.blocks, self.blk_bufs):
+            for bd, bufs, bgm in zip(lay.blocks, self.blk_bufs, self.blk_geoms):
                 gout = self.g_stage[bd.stage]
+                if bd.conv3 is not None:     # Bottleneck (resnet.py:112-132)
+                    self._conv_bn_act(bd.conv1, bd.bn1, h, bufs["a1"], gin, bgm["c1"], None, 1, st)
+                    self._conv_bn_act(bd.conv2, bd.bn2, bufs["a1"], bufs["a2"], bgm["c1"], bgm["mid"], None, 1, st)
+                    res = h
+                    if bd.convd is not None:
+                        self._conv_bn_act(bd.convd, bd.bnd, h, bufs["cd"], gin, gout, None, 0, st)
+                        res = bufs["cd"]
+                    self._conv_bn_act(bd.conv3, bd.bn3, bufs["a2"], bufs["out"], bgm["mid"], gout, res, 1, st)
+                    h, gin = bufs["out"], gout
+                    continue
                 self._conv_bn_act(bd.conv1, bd.bn1, h, bufs["a1"], gin, gout, None, 1, st)
                 res = h
                 if bd.convd is not None:
@@ -602,8 +651,19 @@ class NetPlan:
             self._conv_bn_act(lay.head_conv, lay.head_bn, h, self.ah, gin, self.g_head, None, 1, st)
         else:
             aux = self.wgrad_stream if self.sync_hook is None else None   # idle during the forward
-            for bd, bufs in zip(lay.blocks, self.blk_bufs):
+            for bd, bufs, bgm in zip(lay.blocks, self.blk_bufs, self.blk_geoms):
                 gout = self.g_stage[bd.stage]
+                if bd.conv3 is not None:     # Bottleneck: three conv + BN stages, the residual joins the third
+                    self._conv_bn_train(bd.conv1, bd.bn1, h, bufs["c1"], bufs["a1"], gin, bgm["c1"], st)
+                    self._conv_bn_train(bd.conv2, bd.bn2, bufs["a1"], bufs["c2"], bufs["a2"], bgm["c1"], bgm["mid"], st)
+                    if bd.convd is not None:
+                        self._conv_fwd(bd.convd, h, bufs["cd"], gin, gout, st, bd.bnd)
+                        self._conv_bn_train(bd.conv3, bd.bn3, bufs["a2"], bufs["c3"], bufs["out"], bgm["mid"], gout, st,
+                                            res=bufs["cd"], b_res=bd.bnd)
+                    else:
+                        self._conv_bn_train(bd.conv3, bd.bn3, bufs["a2"], bufs["c3"], bufs["out"], bgm["mid"], gout, st, res=h)
+                    h, gin = bufs["out"], gout
+                    continue
                 side_done = None
                 if bd.convd is not None and aux is not None:
                     # the 1x1 shortcut conv only needs the block input: own branch, joined before the residual add
@@ -776,6 +836,13 @@ class NetPlan:
             else:
                 Gin = sci["gA"]
             bg = self.blk_grads[bi]
+            if bd.conv3 is not None:
+                self._backward_bottleneck(bi, G, Gin, xin, gin, st)
+                G = Gin
+                pre_reduced = False
+                if self.block_done_hook is not None:
+                    self.block_done_hook(bi)
+                continue
             dc2, dcd, da1 = bg["dc2"], bg.get("dcd"), sc["gD"]
             out, c2 = bufs["out"], bufs["c2"]
             self._before_write(dc2, dcd)
@@ -834,6 +901,42 @@ class NetPlan:
         call("ssb_stem_conv_wgrad", x.data_ptr(), self.dc0.data_ptr(), self._g(lay.stem_conv), spec.num_leads, self.L,
              self.g_stem, dt, st)
         self._join_wgrad()
+
+    def _backward_bottleneck(self, bi: int, G, Gin, xin, gin: Geom, st: int) -> None:
+        """Backward of one Bottleneck block (reference resnet.py:112-132): G = gradient w.r.t. the block output; leaves the
+        gradient w.r.t. the block input in Gin.  Same pieces as the BasicBlock path -- fused BN backward, dgrad on the
+        main chain, weight-gradient GEMMs forked onto the second stream -- in a plain serial order."""
+        bd, bufs, bgm, bg = self.lay.blocks[bi], self.blk_bufs[bi], self.blk_geoms[bi], self.blk_grads[bi]
+        dt = self.dtype
+        g1, gm, gout = bgm["c1"], bgm["mid"], bgm["out"]
+        dc3, dc2, dc1, dcd = bg["dc3"], bg["dc2"], bg["dc1"], bg.get("dcd")
+        da2 = self._scratch[(gm.pitch, gm.len, gm.C)]["gD"]
+        da1 = self._scratch[(g1.pitch, g1.len, g1.C)]["gD"]
+        self._before_write(dc3, dcd)
+        if bd.convd is not None:
+            self._bn_bwd(G, bufs["out"], bufs["c3"], bd.bn3, dc3, gout, st, x_res=bufs["cd"], b_res=bd.bnd, dx_res=dcd)
+        else:
+            self._bn_bwd(G, bufs["out"], bufs["c3"], bd.bn3, dc3, gout, st, g_ident=Gin)
+        if self.debug is not None:
+            self.debug[bd.prefix + ".conv3"] = self.to_ncl(dc3, gout)
+        self._wgrad(bd.conv3, bufs["a2"], dc3, gm, gout, st)
+        self._dgrad(bd.conv3, dc3, da2, gm, gout, 0, st)
+        self._before_write(dc2)
+        self._bn_bwd(da2, bufs["a2"], bufs["c2"], bd.bn2, dc2, gm, st)
+        if self.debug is not None:
+            self.debug[bd.prefix + ".conv2"] = self.to_ncl(dc2, gm)
+        self._wgrad(bd.conv2, bufs["a1"], dc2, g1, gm, st)
+        self._dgrad(bd.conv2, dc2, da1, g1, gm, 0, st)
+        self._before_write(dc1)
+        self._bn_bwd(da1, bufs["a1"], bufs["c1"], bd.bn1, dc1, g1, st)
+        if self.debug is not None:
+            self.debug[bd.prefix + ".conv1"] = self.to_ncl(dc1, g1)
+        self._wgrad(bd.conv1, xin, dc1, gin, g1, st)
+        if bd.convd is not None:
+            self._wgrad(bd.convd, xin, dcd, gin, gout, st)
+            call("ssb_conv1d_dgrad", dcd.data_ptr(), self.sh.ptr(bd.convd), Gin.data_ptr(), gin, gout,
+                 bd.convd.k, bd.convd.stride, 0, dt, self._algo_for(bd.convd), st)
+        self._dgrad(bd.conv1, dc1, Gin, gin, g1, 1, st)     # Gin already holds the identity / shortcut gradient
 
     # ---- test helpers: NCL fp32 copies of internal tensors ---------------------------
     def to_ncl(self, buf: torch.Tensor, g: Geom) -> torch.Tensor:

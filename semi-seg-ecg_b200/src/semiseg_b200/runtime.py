@@ -28,7 +28,8 @@ def spec_from_modules(backbone, head) -> SegNetSpec:
                       base_channels=backbone.base_channels, strides=tuple(backbone.strides),
                       stage_blocks=tuple(backbone.stage_blocks), head_channels=head.channels,
                       num_classes=head.num_classes, dropout_ratio=head.dropout_ratio,
-                      align_corners=bool(head.align_corners))
+                      align_corners=bool(head.align_corners),
+                      bottleneck=getattr(backbone.block, "expansion", 1) == 4)
 
 
 class ModelRuntime:

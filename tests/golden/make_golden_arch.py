@@ -6,6 +6,8 @@ UNMODIFIED reference (TEST INFRASTRUCTURE; build container only):
   case R: resnet34 (stage blocks 3-4-6-3, reference resnet.py:378-389) + FCNHead at tiny widths, two leads:
           train-mode forward + CE + backward (logits, loss, every parameter gradient, updated running statistics),
           eval-mode logits, and 2 steps of the reference's fixmatch.train_one_epoch.
+  case K: resnet50 (Bottleneck blocks 3-4-6-3, expansion 4, resnet.py:75-132, 391-402) + FCNHead at tiny widths:
+          train-mode forward + CE + backward, running statistics, eval logits, parameter registration order.
 Stores numbers only (tests/golden/arch_vectors.npz)."""
 import os
 import sys
@@ -75,6 +77,31 @@ def main():
     out["R2/conf_thresh"], out["R2/data_seed"] = np.float64(thresh), np.int64(810)
     mg.put(out, "R2/stats", {k: np.float64(v) for k, v in stats.items()})
     mg.put(out, "R2/final", mg.to_np(model.state_dict()))
+    # ---- case K: resnet50 (Bottleneck 3-4-6-3, reference resnet.py:75-132, 391-402) at tiny widths; head in = 8*8*4 ----
+    def cfg50():
+        c = mg.model_cfg(2, 8, 8, 16, 0.0)
+        c["backbone"] = {"resnet50": c["backbone"]["resnet18"]}
+        c["decode_head"]["FCNHead"]["in_channels"] = 8 * 8 * 4
+        return c
+    torch.manual_seed(int(os.environ.get("SEED_K", "41")))
+    model = R.base.init_model_from_cfg(cfg50())
+    assert sum(1 for k in model.state_dict() if k.endswith("conv3.weight")) == 16
+    mg.put(out, "K/init", mg.to_np(model.state_dict()))
+    lab, _ = mg.synthetic.make_batch(840, 4, 1, 2, 300)
+    x, y = torch.from_numpy(lab["ecg"]), torch.from_numpy(lab["target"])
+    out["K/data_seed"] = np.int64(840)
+    model.train()
+    res = model(x, y, return_loss=True)
+    res["loss"].backward()
+    out["K/seg_logits_train"] = res["seg_logits"].detach().numpy().copy()
+    out["K/loss"] = np.float64(res["loss"].item())
+    mg.put(out, "K/grad", {n: p.grad.detach().numpy().copy() for n, p in model.named_parameters()})
+    mg.put(out, "K/after_train_fwd", mg.to_np({k: v for k, v in model.state_dict().items() if "running" in k or "tracked" in k}))
+    model.eval()
+    with torch.no_grad():
+        out["K/seg_logits_eval"] = model(x)["seg_logits"].numpy()
+    out["K/param_order"] = np.array([n for n, _ in model.named_parameters()])
+
     path = os.path.join(HERE, "arch_vectors.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")

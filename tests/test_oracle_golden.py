@@ -193,6 +193,32 @@ def test_resnet34_oracle_matches_reference(golden_arch):
     _check_final(tr.sd, g, "R2/final")
 
 
+R50_ARCH = dataclasses.replace(TINY_ARCH, stage_blocks=(3, 4, 6, 3), bottleneck=True)
+
+
+def test_resnet50_oracle_matches_reference(golden_arch):
+    """the oracle's Bottleneck stack vs the reference's resnet50 (case K): parameter order, train forward + loss + every
+    gradient + running statistics, eval logits"""
+    g = golden_arch
+    assert O.param_names(R50_ARCH) == [str(n) for n in g["K/param_order"]]
+    sd = {k: (v.double() if v.is_floating_point() else v) for k, v in sd_from(g, "K/init").items()}
+    assert set(O.param_names(R50_ARCH) + O.buffer_names(R50_ARCH)) == set(sd)
+    (lab, _), = batches(int(g["K/data_seed"]), 1, 4, 1, 2, 300)
+    tr = O.OracleTrainer(sd, R50_ARCH, TRAIN_CFG, dtype=torch.float64)
+    st = tr.supervised_step(lab["ecg"], lab["target"], 0.0)
+    assert abs(st["loss"] - float(g["K/loss"])) < 1e-5
+    for n, refv in group(g, "K/grad").items():     # (the reference is fp32 through 53 layers: BN gradients are near-cancelling sums)
+        assert rel_err(tr.grads[n], refv) < (2e-4 if ".bn" in n or "downsample.1" in n else 5e-5), n
+    for n, refv in group(g, "K/after_train_fwd").items():
+        if "tracked" in n:
+            assert int(tr.sd[n]) == int(refv)
+        else:
+            assert rel_err(tr.sd[n], refv) < 1e-5, n
+    with torch.no_grad():
+        ev = O.forward(tr.sd, lab["ecg"].double(), R50_ARCH, False)["seg_logits"]
+    assert rel_err(ev, g["K/seg_logits_eval"]) < 1e-5
+
+
 def test_full_size_step_scalars(golden):
     """resnet18 @ 1x2500, one FixMatch step: losses, mask ratio and all 65 gradient norms."""
     import models.backbones  # product constructors give the seeded init (checked bit-exact in test_surface)

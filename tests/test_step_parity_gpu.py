@@ -361,6 +361,83 @@ def test_resnet34_module_and_steps_golden(golden_arch):
     _check_final(model.state_dict(), g, "R2/final")
 
 
+def test_resnet50_module_golden(golden_arch):
+    """Bottleneck family (resnet50, 3-4-6-3 blocks of 1x1 - 3x3(stride) - 1x1(x4)) against the reference (case K):
+    module-API train forward + loss + every gradient + running statistics, eval logits; yardstick as for resnet34."""
+    import dataclasses
+    g = golden_arch
+    cfg = tiny_cfg()
+    cfg["backbone"] = {"resnet50": cfg["backbone"]["resnet18"]}
+    cfg["decode_head"]["FCNHead"]["in_channels"] = 8 * 8 * 4
+    model = build(cfg, sd_from(g, "K/init"))
+    assert len(model.runtime().ensure().layout.blocks) == 16 and model.runtime().weights.layout.spec.bottleneck
+    model.precision = "fp32"
+    (lab, _), = batches(int(g["K/data_seed"]), 1, 4, 1, 2, 300)
+    x, y = lab["ecg"].to(DEV), lab["target"].to(DEV)
+    model.train()
+    out = model(x, y, return_loss=True)
+    out["loss"].backward()
+    arch50 = dataclasses.replace(TINY_ARCH, stage_blocks=(3, 4, 6, 3), bottleneck=True)
+    tr = O.OracleTrainer(sd_from(g, "K/init"), arch50, TRAIN_CFG, dtype=torch.float64)
+    with torch.no_grad():
+        truth = O.forward(tr.sd, lab["ecg"].double(), arch50, True, None, {}, None)["seg_logits"]
+    tr.supervised_step(lab["ecg"], lab["target"], 0.0, want_taps=True)
+    e, e32 = rel_err(out["seg_logits"], truth), rel_err(g["K/seg_logits_train"], truth)
+    assert e < max(1e-5, 4 * e32), (e, e32)
+    assert abs(float(out["loss"].detach()) - float(g["K/loss"])) < 1e-5
+    # ReLU decisions that differ from the fp64 oracle (pre-activations at rounding level): each gates one unit's whole
+    # gradient contribution, ~1e-3 of the gradient norm upstream of it in a network this small
+    plan = model.runtime().plan(_lib.F32, 4, 300, True)
+    flips = 0
+    for bd, bufs, bgm in zip(plan.lay.blocks, plan.blk_bufs, plan.blk_geoms):
+        for mine, gm_, name in ((bufs["a1"], bgm["c1"], bd.prefix + ".relu1"), (bufs["a2"], bgm["mid"], bd.prefix + ".relu2"),
+                                (bufs["out"], bgm["out"], bd.prefix)):
+            flips += int(((plan.to_ncl(mine, gm_).cpu() > 0) != (tr.taps[name].detach() > 0)).sum())
+    flips += int(((plan.to_ncl(plan.ah, plan.g_head).cpu() > 0) != (tr.taps["decode_head.convs.0"].detach() > 0)).sum())
+    flips += int(((plan.to_ncl(plan.p0, plan.g_pool).cpu() > 0) != (tr.taps["backbone.maxpool"].detach() > 0)).sum())
+    print(f"{flips} ReLU sign decisions differ from the fp64 oracle")
+    assert flips <= 3
+    grads = dict(model.named_parameters())
+    bad = []
+    for n, refv in group(g, "K/grad").items():
+        e, e32 = rel_err(grads[n].grad, tr.grads[n]), rel_err(refv, tr.grads[n])
+        print(f"  grad {n:44s} {e:.2e} (fp32 reference {e32:.2e})")
+        if not e < max(1e-5, 6 * e32) + 1e-3 * flips:
+            bad.append((n, e, e32))
+    assert not bad, bad
+    sd = model.state_dict()
+    for n, refv in group(g, "K/after_train_fwd").items():
+        if "tracked" in n:
+            assert int(sd[n]) == int(refv)
+        else:
+            assert rel_err(sd[n], refv) < 1e-5, n
+    model.eval()
+    with torch.no_grad():
+        assert rel_err(model(x)["seg_logits"], g["K/seg_logits_eval"]) < 2e-5
+
+
+def test_resnet50_bf16_full_width_step_runs():
+    """resnet50 at the shipped widths (stage outputs 256..2048 channels) through the tcgen05 path: one FixMatch step in
+    fp32 (CUDA-core path) and bf16; finite, and the bf16 losses within 2e-2 of the fp32 ones."""
+    from algorithms.base import init_model_from_cfg
+    cfgm = model_cfg(1, 64, 64, 128, 0.0)
+    cfgm["backbone"] = {"resnet50": cfgm["backbone"]["resnet18"]}
+    cfgm["decode_head"]["FCNHead"]["in_channels"] = 2048
+    (lab, unl), = batches(850, 1, 4, 4, 1, 2500)
+    losses = {}
+    for dtype in (_lib.F32, _lib.BF16):
+        torch.manual_seed(6)
+        model = init_model_from_cfg(cfgm).to(DEV)
+        eng = get_engine("fixmatch", model, None, 4, 4, 2500, dtype, dict(TRAIN_CFG, conf_thresh=0.3))
+        eng.load_batch(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"])
+        eng.step(1e-3)
+        s_, = eng.read_stats()
+        assert all(np.isfinite(v) for v in s_.values())
+        losses[dtype] = s_
+    for k in ("loss_total", "loss_x"):
+        assert abs(losses[_lib.BF16][k] - losses[_lib.F32][k]) < 2e-2 * max(1.0, abs(losses[_lib.F32][k])), (k, losses)
+
+
 def test_resnet34_bf16_full_width_step_runs():
     """resnet34 at the shipped widths through the tcgen05 path: finite losses, bf16 loss close to the fp32 path's."""
     from algorithms.base import init_model_from_cfg

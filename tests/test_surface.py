@@ -108,6 +108,32 @@ def test_state_dict_matches_reference_golden(golden):
     assert np.array_equal(cs, golden["E/init_checksum"])
 
 
+def test_resnet34_and_resnet50_init_match_reference(golden_arch):
+    """seeded init of the deeper family members is bit-identical to the reference's (cases R, K), and the parameter
+    arena follows the reference's registration order"""
+    import dataclasses
+
+    from algorithms.base import init_model_from_cfg
+    from semiseg_b200.net import ParamLayout
+    from semiseg_b200.runtime import spec_from_modules
+    for name, tag, seed, head_in in (("resnet34", "R", 31, 64), ("resnet50", "K", 41, 256)):
+        cfg = model_cfg(2, 8, 8, 16, 0.0)
+        cfg["backbone"] = {name: cfg["backbone"]["resnet18"]}
+        cfg["decode_head"]["FCNHead"]["in_channels"] = head_in
+        torch.manual_seed(seed)
+        m = init_model_from_cfg(cfg)
+        ref = group(golden_arch, f"{tag}/init")
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(ref.keys()), name
+        for k, v in sd.items():
+            assert np.array_equal(v.numpy(), ref[k]), f"{name}: seeded init differs from the reference for {k}"
+        lay = ParamLayout(spec_from_modules(m.backbone, m.decode_head))
+        assert lay.param_names() == [n for n, _ in m.named_parameters()]
+        arch = dataclasses.replace(O.Arch(num_leads=2, stem_channels=8, base_channels=8, head_channels=16, dropout_ratio=0.0),
+                                   stage_blocks=(3, 4, 6, 3), bottleneck=(name == "resnet50"))
+        assert lay.param_names() == O.param_names(arch) and lay.buffer_names() == O.buffer_names(arch)
+
+
 def test_layout_matches_oracle_names():
     from semiseg_b200.net import ParamLayout, SegNetSpec
     lay = ParamLayout(SegNetSpec())
@@ -139,8 +165,7 @@ def test_unsupported_variants_fail_loudly():
     import models.backbones as bb
     import models.decode_heads as dh
     from utils.optimizer import get_optimizer_from_config
-    with pytest.raises(NotImplementedError):
-        bb.resnet50(num_leads=1)
+    assert bb.resnet50(num_leads=1, stem_channels=8, base_channels=8).feat_dim == 8 * 8 * 4     # Bottleneck family is built
     with pytest.raises(NotImplementedError):
         bb.resnet18(num_leads=1, deep_stem=True)
     with pytest.raises(NotImplementedError):
