@@ -37,6 +37,37 @@ def mean_iou_from_counts(counts: torch.Tensor, include_background: bool = True, 
     return iou if per_class else iou.mean(dim=1)
 
 
+def aggregate_eval(per_batch: List[Tuple[torch.Tensor, torch.Tensor, int]], include_background: bool = True,
+                   per_class: bool = False, group=None) -> Tuple[Dict[str, float], Dict[str, float]]:
+    """Finalise an evaluation from its per-batch results [(sums fp64[2] = {CE sum, labelled positions}, counts
+    int32 [n, ncls, 3], n)], on whatever device they live, with ONE read-back.
+      loss    = sum_b loss_b * n_b / sum_b n_b                  (metric_logger.meters['loss'].update(loss, n), base.py:219,
+                                                                 then synchronize_between_processes: totals over ranks)
+      MeanIoU = mean over batches of the batch mean of the per-sample scores (torchmetrics update()/compute())
+    Under torch.distributed every rank holds its shard of each batch; the reference gathers the global batch before
+    each update (base.py:207-217), i.e. the batch mean runs over all ranks' samples: per-batch score sums and sample
+    counts are all-reduced (one collective for the whole evaluation), then divided."""
+    dev = per_batch[0][0].device
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    loss_w = torch.stack([s_[0] / s_[1].clamp(min=1.0) * n for s_, _, n in per_batch]).sum()        # sum_b loss_b * n_b
+    n_tot = torch.tensor(float(sum(n for _, _, n in per_batch)), dtype=torch.float64, device=dev)
+    score_sum = torch.stack([mean_iou_from_counts(c, include_background, per_class).sum(dim=0) for _, c, _ in per_batch])
+    n_b = torch.tensor([float(n) for _, _, n in per_batch], dtype=torch.float64, device=dev)
+    if world > 1:
+        pack = torch.cat([loss_w.reshape(1), n_tot.reshape(1), n_b, score_sum.reshape(-1)])
+        dist.all_reduce(pack, group=group)
+        nb = len(per_batch)
+        loss_w, n_tot, n_b = pack[0], pack[1], pack[2:2 + nb]
+        score_sum = pack[2 + nb:].reshape(score_sum.shape)
+    score = (score_sum / n_b.reshape(-1, *([1] * (score_sum.dim() - 1)))).mean(dim=0)              # mean over batches
+    loss = float(loss_w / n_tot)
+    if per_class:
+        metrics = {f"MeanIoU_{i}": float(v) for i, v in enumerate(score.tolist())}
+    else:
+        metrics = {"MeanIoU": float(score)}
+    return {"loss": loss}, metrics
+
+
 class EvalEngine:
     """Static buffers + one captured graph for batches of one shape."""
 
@@ -109,7 +140,6 @@ def evaluate_loader(model, data_loader, device, use_amp: bool = True, include_ba
     dtype = {"fp32": _lib.F32, "bf16": _lib.BF16}[precision] if precision else (_lib.BF16 if use_amp else _lib.F32)
     engines = rt.__dict__.setdefault("eval_engines", {})
     ncls = model.decode_head.num_classes
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     per_batch: List[Tuple[torch.Tensor, torch.Tensor, int]] = []
     outs, labs = [], []
     fresh = set()
@@ -130,27 +160,10 @@ def evaluate_loader(model, data_loader, device, use_amp: bool = True, include_ba
             labs.append(torch.nn.functional.one_hot(eng.y, num_classes=ncls).movedim(-1, 1).to("cpu"))
     if not per_batch:
         return {"loss": float("nan")}, {"MeanIoU": float("nan")}, None, None
-    # ---- finalise on the device: one read-back for the whole evaluation ----
-    loss_w = torch.stack([s[0] / s[1].clamp(min=1.0) * n for s, _, n in per_batch]).sum()        # sum_b loss_b * n_b
-    n_tot = torch.tensor(float(sum(n for _, _, n in per_batch)), dtype=torch.float64, device=device)
-    score_sum = torch.stack([mean_iou_from_counts(c, include_background, per_class).sum(dim=0) for _, c, _ in per_batch])
-    n_b = torch.tensor([float(n) for _, _, n in per_batch], dtype=torch.float64, device=device)
-    if world > 1:
-        # the reference gathers the global batch before each update(): per-batch sums over ranks, then the batch mean
-        pack = torch.cat([loss_w.reshape(1), n_tot.reshape(1), n_b, score_sum.reshape(-1)])
-        dist.all_reduce(pack)
-        nb = len(per_batch)
-        loss_w, n_tot, n_b = pack[0], pack[1], pack[2:2 + nb]
-        score_sum = pack[2 + nb:].reshape(score_sum.shape)
-    score = (score_sum / n_b.reshape(-1, *([1] * (score_sum.dim() - 1)))).mean(dim=0)              # mean over batches
-    loss = float(loss_w / n_tot)
-    if per_class:
-        metrics = {f"MeanIoU_{i}": float(v) for i, v in enumerate(score.tolist())}
-    else:
-        metrics = {"MeanIoU": float(score)}
+    stats, metrics = aggregate_eval(per_batch, include_background, per_class)
     outputs = torch.cat(outs, dim=0) if want_outputs else None
     labels = torch.cat(labs, dim=0) if want_outputs else None
-    return {"loss": loss}, metrics, outputs, labels
+    return stats, metrics, outputs, labels
 
 
 @torch.no_grad()

@@ -107,6 +107,52 @@ def test_dp_equivalence_world2():
     assert gerr < 1e-9 and lerr < 1e-12, (gerr, lerr)
 
 
+def _eval_worker(rank, world, port, q):
+    """semiseg_b200.evaluate.aggregate_eval on per-rank shards == the oracle's torchmetrics restatement fed the global
+    batches (the reference gathers the global batch before each metric update, base.py:207-217)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(REPO, "semi-seg-ecg_b200", "src"))
+    from oracle.eval_oracle import MeanIoU
+    from semiseg_b200.evaluate import aggregate_eval
+    rng = np.random.RandomState(3)
+    ncls, L = 4, 40
+    metric = MeanIoU(ncls)
+    per_batch, tot, cnt = [], 0.0, 0
+    for n_global in (6, 6, 2):                      # global batch sizes; every rank holds every second sample
+        pred = rng.randint(0, 3, (n_global, L))     # class 3 never predicted
+        tgt = rng.randint(0, ncls, (n_global, L))
+        ce = rng.rand(n_global, L)                  # per-position CE terms
+        oh = lambda a: torch.nn.functional.one_hot(torch.from_numpy(a), ncls).movedim(-1, 1)   # noqa: E731
+        metric.update(oh(pred), oh(tgt))
+        tot += float(ce.mean()) * n_global          # meters['loss'].update(batch mean, n)
+        cnt += n_global
+        mine = slice(rank, n_global, world)
+        counts = torch.tensor([[[int(((p_ == c) & (t_ == c)).sum()), int((p_ == c).sum()), int((t_ == c).sum())]
+                                for c in range(ncls)] for p_, t_ in zip(pred[mine], tgt[mine])], dtype=torch.int32)
+        sums = torch.tensor([float(ce[mine].sum()), float(ce[mine].size)], dtype=torch.float64)
+        per_batch.append((sums, counts, counts.shape[0]))
+    stats, metrics = aggregate_eval(per_batch)
+    q.put((rank, abs(stats["loss"] - tot / cnt), abs(metrics["MeanIoU"] - float(metric.compute()))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_eval_aggregation_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    for _ in range(2):
+        rank, lerr, merr = q.get(timeout=10)
+        assert lerr < 1e-12 and merr < 1e-12, (rank, lerr, merr)
+
+
 def test_bench_rank_sharding_is_disjoint():
     """bench.py gives every rank its own synthetic shard (seed + rank), like fixmatch.py:204-206."""
     sys.path.insert(0, REPO)
