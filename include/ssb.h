@@ -52,7 +52,12 @@ enum ssb_status {
 
 enum ssb_dtype { SSB_F32 = 0, SSB_BF16 = 1 };
 enum ssb_algo { SSB_ALGO_SIMT = 0, SSB_ALGO_TCGEN05 = 1 };
-enum ssb_loss_mode { SSB_LOSS_SUP = 0, SSB_LOSS_FIXMATCH = 1, SSB_LOSS_SOFT = 2 };
+enum ssb_loss_mode {
+  SSB_LOSS_SUP = 0,
+  SSB_LOSS_FIXMATCH = 1,     /* hard pseudo-labels, confidence mask (fixmatch.py:105-118; threshold 0: cps / stpp) */
+  SSB_LOSS_SOFT = 2,         /* soft targets (mean_teacher.py:115-117) */
+  SSB_LOSS_SOFT_MASKED = 3   /* soft targets, confidence mask: the consistency term of ReCo (reco.py:248-250) */
+};
 
 /* geometry of one flat padded NLC tensor */
 typedef struct ssb_geom {
@@ -273,7 +278,7 @@ int ssb_pseudo_label(const float* logits, float thr, float* conf, int64_t* label
  * low_s: student low-res logits [Bl+Bu, Lin, ncls]; target: int64 [Bl, L];
  * low_t: teacher / self-eval low-res logits [Bu, Lin, ncls] (NULL for SSB_LOSS_SUP).
  * dlow: gradient of the total loss w.r.t. low_s (written).  sums (fp64[4], zeroed by the
- * caller) += { sum CE_x, sum masked CE_u or soft CE_u, sum mask, 0 }.
+ * caller) += { sum CE_x, sum masked CE_u or soft CE_u, sum mask (the masked modes), 0 }.
  * Total loss = sum_x/(Bl*L) for SUP, else (sum_x/(Bl*L) + sum_u/(Bu*L))/2.
  * Optional materialised outputs (may be NULL): conf f32 [Bu,L], label i64 [Bu,L], mask u8 [Bu,L].
  * thr is read from sp->conf_thresh when sp != NULL, else from thr. */

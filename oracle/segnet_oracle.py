@@ -318,6 +318,13 @@ def ce_soft(z: Tensor, p: Tensor) -> Tensor:
     return -(p * log_softmax_c(z)).sum(dim=1).mean()
 
 
+def ce_soft_masked(z: Tensor, p: Tensor, mask: Tensor) -> Tensor:
+    """reco.py:248-250: F.cross_entropy(pred_u_s, prob_u_w, reduction='none') * (conf_u_w >= thr), mean over ALL
+    positions."""
+    per = -(p * log_softmax_c(z)).sum(dim=1)
+    return (per * mask.to(per.dtype)).mean()
+
+
 def lr_at(epoch: float, cfg: dict) -> float:
     """utils/lr_sched.py:6-18 -- linear warm-up then half-cosine to min_lr."""
     if epoch < cfg["warmup_epochs"]:

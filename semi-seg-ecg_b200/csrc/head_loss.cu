@@ -339,13 +339,26 @@ semi_loss_kernel(const float* __restrict__ low_s, const int64_t* __restrict__ ta
           float st = 0.f, q[MAX_CLS];
           for (int k = 0; k < ncls; ++k) { q[k] = expf(zt[k] - mt); st += q[k]; }
           const float it = 1.0f / st;
+          bool mk = true;
+          if (mode == SSB_LOSS_SOFT_MASKED) {   // loss_u * (conf_u_w >= conf_thresh), conf = softmax(1).max(1)[0] (reco.py:226,249)
+            float c;
+            int lab;
+            softmax_conf_label(zt, ncls, c, lab);
+            mk = c >= thr;
+            if (owner) {
+              if (mk) acc_m += 1.0f;
+              const size_t o = (size_t)u * L + t;
+              if (conf_out) conf_out[o] = c;
+              if (mask_out) mask_out[o] = mk ? 1 : 0;
+            }
+          }
           float l = 0.f;
           for (int k = 0; k < ncls; ++k) {
             q[k] *= it;
             l += q[k] * (lse - z[k]);
-            g[k] = (pr[k] * inv - q[k]) * cu;
+            g[k] = mk ? (pr[k] * inv - q[k]) * cu : 0.f;
           }
-          if (owner) acc_u += l;
+          if (owner && mk) acc_u += l;
         }
       }
     }
@@ -560,7 +573,8 @@ int ssb_semi_loss(const float* low_s, const int64_t* target, const float* low_t,
   SSB_REQUIRE(low_s && target && dlow && sums, "ssb_semi_loss: null pointer");
   SSB_REQUIRE(Bl > 0 && Bu >= 0 && Lin > 0 && L > 0, "ssb_semi_loss: bad sizes (Bl=%d Bu=%d Lin=%d L=%d)", Bl, Bu, Lin, L);
   SSB_REQUIRE(ncls >= 1 && ncls <= MAX_CLS, "ssb_semi_loss: num_classes %d out of range [1,%d]", ncls, MAX_CLS);
-  SSB_REQUIRE(mode == SSB_LOSS_SUP || mode == SSB_LOSS_FIXMATCH || mode == SSB_LOSS_SOFT, "ssb_semi_loss: bad mode %d", mode);
+  SSB_REQUIRE(mode == SSB_LOSS_SUP || mode == SSB_LOSS_FIXMATCH || mode == SSB_LOSS_SOFT || mode == SSB_LOSS_SOFT_MASKED,
+              "ssb_semi_loss: bad mode %d", mode);
   SSB_REQUIRE(mode == SSB_LOSS_SUP || (low_t && Bu > 0), "ssb_semi_loss: teacher logits required for mode %d", mode);
   const float scale = lerp_scale(Lin, L, align_corners);
   int tcap;

@@ -11,7 +11,7 @@ from typing import Optional
 
 F32, BF16 = 0, 1
 ALGO_SIMT, ALGO_TCGEN05 = 0, 1
-LOSS_SUP, LOSS_FIXMATCH, LOSS_SOFT = 0, 1, 2
+LOSS_SUP, LOSS_FIXMATCH, LOSS_SOFT, LOSS_SOFT_MASKED = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PKG_ROOT = os.path.abspath(os.path.join(_HERE, "..", ".."))          # semi-seg-ecg_b200/

@@ -599,7 +599,7 @@ def test_pseudo_label_bit_exact():
     assert torch.equal(torch.isnan(c2), torch.isnan(rc))
 
 
-@pytest.mark.parametrize("mode", [_lib.LOSS_SUP, _lib.LOSS_FIXMATCH, _lib.LOSS_SOFT])
+@pytest.mark.parametrize("mode", [_lib.LOSS_SUP, _lib.LOSS_FIXMATCH, _lib.LOSS_SOFT, _lib.LOSS_SOFT_MASKED])
 @pytest.mark.parametrize("Lin,L", [(79, 2500), (10, 300), (157, 5000)])
 def test_semi_loss(mode, Lin, L):
     torch.manual_seed(Lin + mode)
@@ -621,6 +621,10 @@ def test_semi_loss(mode, Lin, L):
             conf_r, lab_r, mask_r = O.pseudo_label(zt, thr)
             loss_u = O.ce_masked(zs[Bl:], lab_r, mask_r)
             mratio = float(mask_r.float().mean())
+        elif mode == _lib.LOSS_SOFT_MASKED:     # the consistency term of ReCo (reco.py:226, 248-250)
+            conf_r, lab_r, mask_r = O.pseudo_label(zt, thr)
+            loss_u = O.ce_soft_masked(zs[Bl:], zt.double().softmax(1), mask_r)
+            mratio = float(mask_r.float().mean())
         else:
             loss_u = O.ce_soft(zs[Bl:], zt.double().softmax(1))
         loss = (loss_x + loss_u) / 2
@@ -630,7 +634,7 @@ def test_semi_loss(mode, Lin, L):
     conf = torch.zeros(max(Bu, 1), L, device=DEV)
     label = torch.zeros(max(Bu, 1), L, dtype=torch.int64, device=DEV)
     mask = torch.zeros(max(Bu, 1), L, dtype=torch.uint8, device=DEV)
-    mat = mode == _lib.LOSS_FIXMATCH
+    mat = mode in (_lib.LOSS_FIXMATCH, _lib.LOSS_SOFT_MASKED)
     call("ssb_semi_loss", low_s.data_ptr(), y.data_ptr(), low_t.data_ptr() if Bu else None, dlow.data_ptr(), sums.data_ptr(),
          Bl, Bu, Lin, L, ncls, mode, thr, None, 0, conf.data_ptr() if mat else None, label.data_ptr() if mat else None,
          mask.data_ptr() if mat else None, st())
@@ -644,6 +648,9 @@ def test_semi_loss(mode, Lin, L):
         assert float((label != lab_r).float().mean()) < 1e-4
         assert float((mask.bool() != mask_r).float().mean()) < 1e-4
         assert float((conf - conf_r).abs().max()) < 5e-5
+    if mode == _lib.LOSS_SOFT_MASKED:
+        assert 0.1 < mratio < 0.9 and abs(float(s[2]) / (Bu * L) - mratio) < 1e-4
+        assert float((mask.bool() != mask_r).float().mean()) < 1e-4 and float((conf - conf_r).abs().max()) < 5e-5
     assert rel_err(dlow.permute(0, 2, 1), ls.grad) < 2e-5
 
 
