@@ -415,6 +415,88 @@ stem_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, fl
   }
 }
 
+// Stem weight gradient for a single lead (the shipped configs): no shared-memory staging of dy -- every thread streams
+// 16-byte dy vectors (V channels of one position) straight from L2, four positions in flight, and keeps its
+// [7 taps][V] products in registers; positions are spread over the block's lanes and over ~100 blocks.  Combine: warp
+// shuffles, then per-warp partials in shared memory summed by the block (NO shared-memory float atomics: they are
+// compare-and-swap loops, and 16- to 32-way contention on them was ~14 us of the tiled kernel's 21 us -- measured:
+// the time did not depend on the number of blocks, i.e. not on the global atomics), one global atomic per output
+// per block.
+#define SD_THREADS 256
+#define SD_POS_PER_LANE 12
+#define SD_UNROLL 4
+template <typename T, int CL>
+__global__ void __launch_bounds__(SD_THREADS)
+stem_conv_wgrad_direct_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int L, ssb_geom g,
+                              int chunk) {
+  pdl_trigger();
+  pdl_wait();
+  static_assert(CL == 1, "single lead");
+  constexpr int V = Vec<T>::N;
+  extern __shared__ float part[];           // [warps][7][Cs]
+  const int Cs = g.C;
+  const int ncg = Cs / V;                   // power of two, <= 32
+  const int plane = SD_THREADS / ncg;
+  const int cg = threadIdx.x % ncg, lane_p = threadIdx.x / ncg;
+  const int nout = 7 * Cs;
+  float acc[7][V];
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+#pragma unroll
+    for (int i = 0; i < V; ++i) acc[j][i] = 0.f;
+  const int P = g.B * g.len;                // (< 2^31: checked by the host)
+  const int p0 = blockIdx.x * chunk;
+  const int p1 = min(p0 + chunk, P);
+  for (int p = p0 + lane_p; p < p1; p += SD_UNROLL * plane) {
+    Vec<T> v[SD_UNROLL];
+    float xv[SD_UNROLL][7];
+#pragma unroll
+    for (int u = 0; u < SD_UNROLL; ++u) {     // issue every load of the batch before the first use
+      const int pp = p + u * plane;
+      if (pp < p1) {
+        const int b = pp / g.len, t = pp - b * g.len;
+        v[u].load(dy + ((size_t)b * g.pitch + 1 + t) * Cs + (size_t)cg * V);
+        const float* xr = x + (size_t)b * L;
+        const int l0 = 2 * t - 3;
+        const bool interior = l0 >= 0 && l0 + 6 < L;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) xv[u][j] = (interior || (l0 + j >= 0 && l0 + j < L)) ? xr[l0 + j] : 0.f;
+      } else {
+        v[u].zero();
+#pragma unroll
+        for (int j = 0; j < 7; ++j) xv[u][j] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SD_UNROLL; ++u) {
+      float d[V];
+      v[u].get(d);
+#pragma unroll
+      for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[j][i] = fmaf(d[i], xv[u][j], acc[j][i]);
+    }
+  }
+  // lanes of a warp with the same channel group: xor offsets ncg, 2 ncg, ... < 32; then one partial row per warp
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < 7; ++j)
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float a = acc[j][i];
+      for (int off = ncg; off < 32; off <<= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+      if (lane < ncg) part[(size_t)warp * nout + j * Cs + cg * V + i] = a;
+    }
+  __syncthreads();
+  for (int o = threadIdx.x; o < nout; o += SD_THREADS) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < SD_THREADS / 32; ++w) a += part[(size_t)w * nout + o];
+    const int co = o % Cs, cj = o / Cs;
+    if (a != 0.f) atomicAdd(&dw[(size_t)co * 7 + cj], a);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -713,6 +795,28 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
   int rc = check_stem("ssb_stem_conv_wgrad", Cl, L, g);
   if (rc) return rc;
   SSB_REQUIRE(x && dy && dw, "ssb_stem_conv_wgrad: null pointer");
+  {   // single lead: register-tile kernel streaming dy from L2 (two leads were measured slower than the tiled kernel)
+    const int V = dtype == SSB_BF16 ? 8 : 4;
+    const int ncg = g.C / V;
+    static const bool direct_on = !(getenv("SSB_STEM_WGRAD_DIRECT") && atoi(getenv("SSB_STEM_WGRAD_DIRECT")) == 0);
+    if (direct_on && Cl == 1 && (long long)g.B * g.len < (1ll << 30) && g.C % V == 0 && ncg >= 1 && ncg <= 32 && (ncg & (ncg - 1)) == 0 &&
+        (size_t)(SD_THREADS / 32) * 7 * g.C * sizeof(float) <= 48 * 1024) {
+      const int plane = SD_THREADS / ncg;
+      const long long P = (long long)g.B * g.len;
+      static const int ppl = getenv("SSB_STEM_WGRAD_PPL") ? atoi(getenv("SSB_STEM_WGRAD_PPL")) : SD_POS_PER_LANE;
+      long long nblk = ceil_div_ll(P, (long long)plane * (ppl > 0 ? ppl : SD_POS_PER_LANE));
+      if (nblk > 148) nblk = 148;
+      if (nblk < 1) nblk = 1;
+      const int chunk = (int)ceil_div_ll(P, nblk);
+      const size_t sm = (size_t)(SD_THREADS / 32) * 7 * g.C * sizeof(float);
+      SSB_DISPATCH_DTYPE(dtype, T, {
+        ssb_launch(stem_conv_wgrad_direct_kernel<T, 1>, dim3((unsigned)nblk), dim3(SD_THREADS), sm, to_stream(stream), x,
+                   (const T*)dy, dw, L, g, chunk);
+      })
+      SSB_LAUNCH_CHECK("ssb_stem_conv_wgrad");
+      return SSB_OK;
+    }
+  }
   const size_t smem = ((size_t)SW_TT * g.C + (size_t)Cl * (2 * SW_TT + 5) + (size_t)Cl * 7 * g.C) * sizeof(float);
   SSB_REQUIRE(smem <= 96 * 1024, "ssb_stem_conv_wgrad: num_leads x stem_channels too large (%zu B of shared memory)", smem);
   const int nown = (g.C / 4) * Cl;    // (4-channel group, lead) owners; the rest of the block slices the positions
