@@ -418,10 +418,8 @@ stem_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, fl
 // Stem weight gradient for a single lead (the shipped configs): no shared-memory staging of dy -- every thread streams
 // 16-byte dy vectors (V channels of one position) straight from L2, four positions in flight, and keeps its
 // [7 taps][V] products in registers; positions are spread over the block's lanes and over ~100 blocks.  Combine: warp
-// shuffles, then per-warp partials in shared memory summed by the block (NO shared-memory float atomics: they are
-// compare-and-swap loops, and 16- to 32-way contention on them was ~14 us of the tiled kernel's 21 us -- measured:
-// the time did not depend on the number of blocks, i.e. not on the global atomics), one global atomic per output
-// per block.
+// shuffles, per-warp partial rows in shared memory summed by the block, one global atomic per output per block.
+// Measured 15.9 us against 21.2 us for the tiled kernel above at the config-2 shape (tools/stem_wgrad_timing.py).
 #define SD_THREADS 256
 #define SD_POS_PER_LANE 12
 #define SD_UNROLL 4
