@@ -5,6 +5,8 @@
 //  * flat storage-dtype copy of the parameter arena (conv weights are kept tap-major, [k][Cin][Cout])
 // These are the exact-parity (fp32) path and the fallback for shapes the tcgen05 kernels
 // (conv_sm100.cu) do not cover.  Replaces cuDNN fprop/dgrad/wgrad (SURVEY.md 2.2 K1,K4).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -419,10 +421,13 @@ stem_conv_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ dy, fl
 // 16-byte dy vectors (V channels of one position) straight from L2, four positions in flight, and keeps its
 // [7 taps][V] products in registers; positions are spread over the block's lanes and over ~100 blocks.  Combine: warp
 // shuffles, per-warp partial rows in shared memory summed by the block, one global atomic per output per block.
-// Measured 15.9 us against 21.2 us for the tiled kernel above at the config-2 shape (tools/stem_wgrad_timing.py).
+// The blocks of a cluster of SD_CLUSTER are then summed through distributed shared memory, so that the global REDs are
+// one per output per cluster.  Measured 11.3 us against 21.2 us for the tiled kernel above at the config-2 shape
+// (tools/stem_wgrad_timing.py; 15.9 us before the cluster combine).
 #define SD_THREADS 256
 #define SD_POS_PER_LANE 12
 #define SD_UNROLL 4
+#define SD_CLUSTER 8
 template <typename T, int CL>
 __global__ void __launch_bounds__(SD_THREADS)
 stem_conv_wgrad_direct_kernel(const float* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int L, ssb_geom g,
@@ -486,13 +491,29 @@ stem_conv_wgrad_direct_kernel(const float* __restrict__ x, const T* __restrict__
       if (lane < ncg) part[(size_t)warp * nout + j * Cs + cg * V + i] = a;
     }
   __syncthreads();
+  // block totals, then the SD_CLUSTER blocks of a cluster are summed by its rank-0 block through distributed shared
+  // memory: the kernel's tail used to be ~47k global REDs onto 448 addresses (14 cache lines) -- ncu: SMs active
+  // 17.8k of 43.4k elapsed cycles, the rest the REDs draining at L2 -- now one RED per output per CLUSTER
+  float* tot = part + (size_t)(SD_THREADS / 32) * nout;
   for (int o = threadIdx.x; o < nout; o += SD_THREADS) {
     float a = 0.f;
 #pragma unroll
     for (int w = 0; w < SD_THREADS / 32; ++w) a += part[(size_t)w * nout + o];
-    const int co = o % Cs, cj = o / Cs;
-    if (a != 0.f) atomicAdd(&dw[(size_t)co * 7 + cj], a);
+    tot[o] = a;
   }
+  namespace cgs = cooperative_groups;
+  cgs::cluster_group cluster = cgs::this_cluster();
+  cluster.sync();
+  if (cluster.block_rank() == 0) {
+    const unsigned nr = cluster.num_blocks();
+    for (int o = threadIdx.x; o < nout; o += SD_THREADS) {
+      float a = 0.f;
+      for (unsigned r = 0; r < nr; ++r) a += cluster.map_shared_rank(tot, r)[o];
+      const int co = o % Cs, cj = o / Cs;
+      if (a != 0.f) atomicAdd(&dw[(size_t)co * 7 + cj], a);
+    }
+  }
+  cluster.sync();      // the peers' shared memory stays alive until rank 0 has read it
 }
 
 // ---------------------------------------------------------------------------------------
@@ -798,18 +819,30 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
     const int ncg = g.C / V;
     static const bool direct_on = !(getenv("SSB_STEM_WGRAD_DIRECT") && atoi(getenv("SSB_STEM_WGRAD_DIRECT")) == 0);
     if (direct_on && Cl == 1 && (long long)g.B * g.len < (1ll << 30) && g.C % V == 0 && ncg >= 1 && ncg <= 32 && (ncg & (ncg - 1)) == 0 &&
-        (size_t)(SD_THREADS / 32) * 7 * g.C * sizeof(float) <= 48 * 1024) {
+        (size_t)(SD_THREADS / 32 + 1) * 7 * g.C * sizeof(float) <= 48 * 1024) {
       const int plane = SD_THREADS / ncg;
       const long long P = (long long)g.B * g.len;
       static const int ppl = getenv("SSB_STEM_WGRAD_PPL") ? atoi(getenv("SSB_STEM_WGRAD_PPL")) : SD_POS_PER_LANE;
       long long nblk = ceil_div_ll(P, (long long)plane * (ppl > 0 ? ppl : SD_POS_PER_LANE));
-      if (nblk > 148) nblk = 148;
+      if (nblk > 144) nblk = 144;
       if (nblk < 1) nblk = 1;
+      nblk = ceil_div_ll(nblk, SD_CLUSTER) * SD_CLUSTER;          // whole clusters (blocks past the last position idle)
       const int chunk = (int)ceil_div_ll(P, nblk);
-      const size_t sm = (size_t)(SD_THREADS / 32) * 7 * g.C * sizeof(float);
+      const size_t sm = (size_t)(SD_THREADS / 32 + 1) * 7 * g.C * sizeof(float);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)nblk);
+      cfg.blockDim = dim3(SD_THREADS);
+      cfg.dynamicSmemBytes = sm;
+      cfg.stream = to_stream(stream);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = SD_CLUSTER;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
       SSB_DISPATCH_DTYPE(dtype, T, {
-        ssb_launch(stem_conv_wgrad_direct_kernel<T, 1>, dim3((unsigned)nblk), dim3(SD_THREADS), sm, to_stream(stream), x,
-                   (const T*)dy, dw, L, g, chunk);
+        cudaLaunchKernelEx(&cfg, stem_conv_wgrad_direct_kernel<T, 1>, x, (const T*)dy, dw, L, g, chunk);
       })
       SSB_LAUNCH_CHECK("ssb_stem_conv_wgrad");
       return SSB_OK;
