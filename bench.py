@@ -33,6 +33,13 @@ WORKLOADS = {
     "fixmatch_resnet18_ludb_1x2500_b16+16": ("fixmatch", 1, 2500, 16, 16, 64, 64),
     "mean_teacher_resnet18_qtdb_2x2500_b16+16": ("mean_teacher", 2, 2500, 16, 16, 64, 64),
     "fixmatch_resnet18w128_12x5000_b32+32": ("fixmatch", 12, 5000, 32, 32, 128, 128),
+    # BASELINE configs[3]: cross-domain merged index, labeled:unlabeled 1:7 -> B_l = 4, B_u = 28 per GPU (1 x 2500)
+    "fixmatch_resnet18_merged_1x2500_b4+28": ("fixmatch", 1, 2500, 4, 28, 64, 64),
+    # BASELINE configs[4]: widened network, 12 x 5000, global batch 256 ... 4096 on 8 GPUs = 16+16 ... 256+256 per GPU
+    "fixmatch_resnet18w128_12x5000_b16+16": ("fixmatch", 12, 5000, 16, 16, 128, 128),
+    "fixmatch_resnet18w128_12x5000_b64+64": ("fixmatch", 12, 5000, 64, 64, 128, 128),
+    "fixmatch_resnet18w128_12x5000_b128+128": ("fixmatch", 12, 5000, 128, 128, 128, 128),
+    "fixmatch_resnet18w128_12x5000_b256+256": ("fixmatch", 12, 5000, 256, 256, 128, 128),
 }
 DEFAULT_WORKLOAD = "fixmatch_resnet18_ludb_1x2500_b16+16"
 
@@ -56,6 +63,16 @@ def load_cfg(workload):
     cfg["dataset"]["signal_length"] = L
     cfg["dataloader"]["batch_size"] = Bl
     return cfg, algo, C, L, Bl, Bu
+
+
+def config_block(workload, world, sync_bn):
+    """The `config` object of the JSON line -- identical for the B200 arm and the reference arm of the same launch."""
+    algo, C, L, Bl, Bu, base, stem = WORKLOADS[workload]
+    return {"workload": workload, "algorithm": algo, "per_gpu_batch": f"{Bl}+{Bu}", "leads": C, "length": L,
+            "base_channels": base, "parallelism": f"dp{world}", "sync_bn": bool(sync_bn and world > 1),
+            "l2_policy": "no explicit flush: the per-step working set (activations + parameter / gradient / Adam arenas; "
+                         "164 MiB at 16+16 x 1 x 2500, reported as working_set_mib) exceeds the 126 MB L2 and the inputs "
+                         "rotate over 4 distinct batches"}
 
 
 class ClockSampler(threading.Thread):
@@ -106,7 +123,7 @@ def launch_cost(name, args, es):
     if geoms:
         g = geoms[-1]
         n = g.B * g.len * g.C
-        mult = {"ssb_bn_stats": 1, "ssb_bn_act_fwd": 2.5, "ssb_bn_bwd_reduce": 3, "ssb_bn_bwd_apply": 4,
+        mult = {"ssb_bn_stats": 1, "ssb_bn_act_fwd": 2.5, "ssb_bn_bwd_reduce": 3, "ssb_bn_bwd_apply": 4, "ssb_bn_bwd_fused": 4,
                 "ssb_stem_bn_relu_pool_fwd": 3, "ssb_stem_bwd_reduce": 3, "ssb_stem_bwd_apply": 3.5}.get(name, 2)
         return 0.0, n * es * mult, f"{name[4:]}[C{g.C},L{g.len}]"
     if name == "ssb_adamw_ema":
@@ -175,9 +192,10 @@ def steady_state_profile(eng_e, batch, lr, es, repeats=20):
     return out
 
 
-def roofline_from_profile(prof, peaks):
+def roofline_from_profile(prof, peaks, traffic=None):
     """Aggregate the steady-state launch times by kernel family; the dominant family (largest share of the
-    summed device time) gets the roofline entry: achieved = summed algorithmic FLOPs (or bytes) / summed time."""
+    summed device time) gets the roofline entry: achieved = summed algorithmic FLOPs (or bytes) / summed time.
+    These are kernels timed in isolation -> the BURST bf16 peak is the denominator (frac_of_sustained beside it)."""
     fam = {}
     tot = 0.0
     for label, n, us, fl, by in prof:
@@ -193,13 +211,22 @@ def roofline_from_profile(prof, peaks):
     if f["flops"] and f["bytes"] and f["flops"] / f["bytes"] > ridge:
         ach = f["flops"] / (f["us"] * 1e-6) / 1e12
         roof = {"bound": "tensor", "achieved": round(ach, 2), "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": round(ach / peaks["bf16_tflops"], 4), "traffic": None}
+                "frac": round(ach / peaks["bf16_tflops"], 4), "traffic": None,
+                "frac_of_sustained": round(ach / peaks["bf16_tflops_sustained"], 4)}
     else:
         ach = f["bytes"] / (f["us"] * 1e-6) / 1e9
         roof = {"bound": "hbm", "achieved": round(ach, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": round(ach / peaks["hbm_gbs"], 4), "traffic": None}
+    if traffic and name in traffic.get("families", {}):
+        tf = traffic["families"][name]
+        roof["traffic"] = round(tf["dram_bytes_per_step"] / max(tf["launches_per_step"], 1))
+        roof["traffic_detail"] = {"dram_mbyte_per_step": round(tf["dram_bytes_per_step"] / 1e6, 2),
+                                  "algorithmic_mbyte_per_step": round(f["bytes"] / 1e6, 2),
+                                  "dram_over_algorithmic": round(tf["dram_bytes_per_step"] / max(f["bytes"], 1), 3),
+                                  "launches_in_capture": tf["launches_per_step"], "source": traffic.get("source")}
     roof.update({"kernel": name, "launches_per_step": f["launches"], "us_per_launch": round(f["us"] / f["launches"], 2),
-                 "share_of_step": round(f["us"] / tot, 4), "peak_source": peaks["src"],
+                 "share_of_serial_sum": round(f["us"] / tot, 4), "peak_source": peaks["src"],
+                 "peak_kind": "burst (kernels timed in isolation)",
                  "algorithmic_per_step": {"gflop": round(f["flops"] / 1e9, 2), "mbyte": round(f["bytes"] / 1e6, 2)},
                  "timing": "CUDA events on the launch stream around each distinct launch replayed 20x5 times inside a "
                            "captured graph (steady state, warm L2), summed over the family's launches of one step"})
@@ -210,12 +237,26 @@ def roofline_from_profile(prof, peaks):
 
 
 def load_peaks():
-    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+    """bf16_tflops = the BURST figure (denominator for kernels timed in isolation); bf16_tflops_sustained for
+    anything timed inside the long step."""
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
     pf = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(pf):
         mp = json.load(open(pf))
-        peaks = {"hbm_gbs": mp["hbm_gbs"], "bf16_tflops": mp.get("bf16_tflops_sustained", mp["bf16_tflops"]), "src": "measured"}
+        peaks = {"hbm_gbs": mp["hbm_gbs"], "bf16_tflops": mp["bf16_tflops"],
+                 "bf16_tflops_sustained": mp.get("bf16_tflops_sustained", mp["bf16_tflops"]), "src": "measured (MEASURED_PEAKS.json)"}
     return peaks
+
+
+def load_traffic(workload):
+    """DRAM bytes per kernel family per step from the committed ncu pass (profiles/r2_traffic.json, written by
+    tools/profile_summary.py traffic from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,...` of
+    `bench.py --profile-mode`); None if there is no capture of this workload."""
+    pf = os.path.join(REPO, "profiles", "r2_traffic.json")
+    if not os.path.exists(pf):
+        return None
+    t = json.load(open(pf))
+    return t.get(workload)
 
 
 def _finish(world):
@@ -253,7 +294,9 @@ def run_b200(args):
     dtype = _lib.BF16 if args.dtype == "bf16" else _lib.F32
     torch.manual_seed(cfg["seed"])           # identical initial weights on every rank
     model = init_model_from_cfg(cfg).to(dev)
-    model.sync_bn = bool(args.sync_bn) and world > 1
+    # --sync-bn: default = the YAML's ddp.sync_bn (true in every shipped config, fixmatch.yaml:131 of the reference)
+    want_sync_bn = bool(cfg["ddp"].get("sync_bn", True)) if args.sync_bn is None else bool(args.sync_bn)
+    model.sync_bn = want_sync_bn and world > 1
     model.seed = cfg["seed"] + rank
     teacher = init_teacher(cfg, model, dev) if algo == "mean_teacher" else None
     eng = get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=not args.no_graph)
@@ -315,40 +358,100 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.3)
     ms_dev, stats_dev = timed(devb, args.steps, False)
-    ms_e2e, stats_e2e = timed(host, args.steps, True)
+
+    # ---- e2e: the call a user of the reference makes -- algorithms.<algo>.train_one_epoch(model, labeled_loader,
+    # unlabeled_loader, optimizer, device, epoch, loss_scaler, log_writer, use_amp, config['train']) -- over loaders that
+    # yield PINNED HOST batch dicts ({'ecg','target'} / {'ecg','ecg_aug'}, semi_dataset.py:235-244): every step's H2D
+    # copies, the per-step LR / param-group writes, the engine lookup and the read-back of the loss sums are inside.
+    import contextlib
+    import algorithms
+    from utils.misc import NativeScalerWithGradNormCount
+    from utils.optimizer import get_optimizer_from_config
+    optimizer = get_optimizer_from_config(tcfg, model.parameters())
+    scaler = NativeScalerWithGradNormCount()
+    toe = getattr(algorithms, algo).train_one_epoch
+
+    def epoch_call(n):
+        labs = [{"ecg": host[i % pool][0], "target": host[i % pool][1]} for i in range(n)]
+        unls = [{"ecg": host[i % pool][2], "ecg_aug": host[i % pool][3]} for i in range(n)]
+        with contextlib.redirect_stdout(sys.stderr):      # the epoch loop logs like the reference; stdout carries ONE line
+            if algo == "mean_teacher":
+                return toe(model, teacher, labs, unls, optimizer, dev, 20, scaler, None, args.dtype == "bf16", tcfg)
+            return toe(model, labs, unls, optimizer, dev, 20, scaler, None, args.dtype == "bf16", tcfg)
+    epoch_call(3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    stats_epoch = epoch_call(args.steps)
+    ev1.record()
+    sync_all()
+    ms_e2e = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t)
+    stats_e2e = [stats_epoch]
+    assert get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=not args.no_graph) is eng or args.no_graph, \
+        "train_one_epoch must run on the engine that was timed"
     sampler.stop_flag = True
     per_step = Bl + Bu
     value = per_step * world * args.steps / (ms_dev / 1e3)
     e2e = per_step * world * args.steps / (ms_e2e / 1e3)
     assert all(np.isfinite(s["loss_total"]) for s in stats_dev + stats_e2e), "non-finite loss in the timed region"
 
+    # ---- N>1: every rank must hold the same weights after the timed loops (replicated optimizer, averaged gradients) ----
+    replicas_equal = None
+    if world > 1:
+        w_ = model.runtime().weights.params
+        chk = torch.stack([w_.double().sum(), (w_.double() * w_.double()).sum()])
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        rel = float(((hi - lo).abs() / (hi.abs() + 1e-30)).max())
+        # SyncBN off: ranks see different BN statistics only through their own shard's forward; the averaged gradient and
+        # therefore the parameters are identical on every rank either way
+        replicas_equal = {"max_rel_spread_of_param_checksums": rel, "ok": bool(rel < 1e-9)}
+        assert replicas_equal["ok"], f"ranks hold different weights after the timed loop: {replicas_equal}"
+
     # ---- SyncBN on (the reference YAML's default, ddp.sync_bn: true): same timed loop, reported next to the headline ----
-    syncbn_on = None
-    if world > 1 and not model.sync_bn and args.syncbn_extra:
-        model.sync_bn = True
+    syncbn_other = None
+    if world > 1 and not args.no_syncbn_other:
+        main_sb = bool(model.sync_bn)
+        model.sync_bn = not main_sb
         eng_sb = get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=not args.no_graph)
-        model.sync_bn = False
+        model.sync_bn = main_sb
         eng_main, eng = eng, eng_sb
         for i in range(max(args.warmup, 3)):
             step_from(devb[i % pool])
         eng.read_stats()
         ms_sb, stats_sb = timed(devb, args.steps, False)
         eng = eng_main
-        syncbn_on = {"value": round(per_step * world * args.steps / (ms_sb / 1e3), 1), "unit": "samples/s",
-                     "ms_per_step": round(ms_sb / args.steps, 4),
-                     "exchange": "peer-memory kernel" if getattr(eng_sb, "syncbn_p2p", False) else "nccl",
-                     "finite": bool(all(np.isfinite(s_["loss_total"]) for s_ in stats_sb))}
+        syncbn_other = {"sync_bn": not main_sb, "value": round(per_step * world * args.steps / (ms_sb / 1e3), 1), "unit": "samples/s",
+                        "ms_per_step": round(ms_sb / args.steps, 4),
+                        "exchange": ("peer-memory kernel" if getattr(eng_sb, "syncbn_p2p", False) else "nccl") if not main_sb else None,
+                        "finite": bool(all(np.isfinite(s_["loss_total"]) for s_ in stats_sb))}
 
     # ---- per-kernel timing pass: every distinct launch of the step, steady state, on its launch stream ----
     roof, top, fams, large = None, [], [], None
     if rank == 0 or world > 1:   # (every rank takes part when the step contains collectives)
         es = 2 if dtype == _lib.BF16 else 4
         peaks = load_peaks()
+        main_sb = bool(model.sync_bn)
+        model.sync_bn = False    # (the peer-memory statistics exchange must not be replayed out of lockstep; same kernels otherwise)
         eng_e = get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=False)
+        model.sync_bn = main_sb
         eng_e.load_batch(*devb[0]); eng_e.step(lr_at(epoch_f[0], tcfg))
         torch.cuda.synchronize()
         prof = steady_state_profile(eng_e, devb[0], lr_at(epoch_f[0], tcfg), es)
-        roof, fams, tot = roofline_from_profile(prof, peaks)
+        roof, fams, tot = roofline_from_profile(prof, peaks, load_traffic(args.workload))
+        # step level: all algorithmic conv FLOPs of one step over the measured step time (kernels inside the long step ->
+        # the SUSTAINED peak is the denominator)
+        step_flops = sum(fl * n for _, n, _, fl, _ in prof)
+        ach_step = step_flops / (ms_dev / args.steps * 1e-3) / 1e12
+        roof["step_level"] = {"achieved": round(ach_step, 2), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                              "frac": round(ach_step / peaks["bf16_tflops_sustained"], 4), "peak_kind": "sustained",
+                              "gflop_per_step": round(step_flops / 1e9, 2),
+                              "serial_sum_us": round(tot, 1), "step_us": round(ms_dev / args.steps * 1e3, 1)}
         for label, n, us, fl, by in sorted(prof, key=lambda r: -r[1] * r[2])[:8]:
             top.append({"kernel": label, "share": round(n * us / tot, 4), "us_per_launch": round(us, 2), "launches_per_step": n,
                         "tflops": round(fl / (us * 1e-6) / 1e12, 2) if fl else None, "gbs": round(by / (us * 1e-6) / 1e9, 1) if by else None})
@@ -408,22 +511,29 @@ def run_b200(args):
     ws = sum(t.numel() * t.element_size() for bufs in plan.blk_bufs for t in bufs.values())
     ws += sum(t.numel() * t.element_size() for t in (plan.c0, plan.p0, plan.ch, plan.ah, plan.dc0))
     ws += 4 * model.runtime().weights.params.numel() * 4
-    cpu = None
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(args.workload, budget_s=15.0)
+        cpu, first = cpu_baseline(args.workload, budget_s=15.0)
+        parity = parity_at_bench_shape(args.workload, dtype, first)
+    lib_gpu = None
+    if world == 1 and not args.no_library:
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import library_baseline
+        base_, stem_ = WORKLOADS[args.workload][5:7]
+        lib_gpu = library_baseline.run(C, L, Bl, Bu, base_, stem_, steps=min(max(args.steps, 10), 50))
+        best = max(v["samples_per_s"] for k, v in lib_gpu.items() if isinstance(v, dict))
+        lib_gpu["this_repo_over_best_library_mode"] = {"value": round(value / best, 2), "e2e": round(e2e / best, 2)}
     line = {
         "metric": "train samples/sec FixMatch 1D U-Net (resnet18+FCNHead segmentor) step",
         "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic LUDB-shaped strips (z-scored Gaussian, 4-class piecewise labels), random-init weights",
-        "config": {"workload": args.workload, "algorithm": algo, "per_gpu_batch": f"{Bl}+{Bu}", "leads": C, "length": L,
-                   "parallelism": f"dp{world}", "sync_bn": bool(model.sync_bn),
-                   "sync_bn_exchange": ("peer-memory kernel" if getattr(eng, "syncbn_p2p", False) else "nccl") if model.sync_bn else None,
-                   "cuda_graph": not args.no_graph,
-                   "l2_policy": f"no explicit flush: per-step working set {ws / 2**20:.0f} MiB (activations + param/grad/Adam arenas) "
-                                "vs 126 MB L2; inputs rotate over 4 distinct batches"},
+        "config": config_block(args.workload, world, want_sync_bn),
+        "run": {"sync_bn_exchange": ("peer-memory kernel" if getattr(eng, "syncbn_p2p", False) else "nccl") if model.sync_bn else None,
+                "cuda_graph": not args.no_graph, "working_set_mib": round(ws / 2**20, 1)},
         "e2e": {"value": round(e2e, 1), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes(), "d2h_bytes_per_step": 32,
-                "ms_per_step": round(ms_e2e / args.steps, 4)},
+                "ms_per_step": round(ms_e2e / args.steps, 4),
+                "through": f"algorithms.{algo}.train_one_epoch over list loaders of pinned host batch dicts"},
         "gpu_launches": eng.launches_per_step * args.steps,
         "launches_per_step": eng.launches_per_step,
         "clocks": sampler.summary(),
@@ -432,12 +542,18 @@ def run_b200(args):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if parity is not None:
+        line["parity_at_bench_shape"] = parity
+    if lib_gpu is not None:
+        line["library_gpu_baseline"] = lib_gpu
     if large is not None:
         line["large_batch_roofline"] = large
     if aug is not None:
         line["gpu_augmentation"] = aug
-    if syncbn_on is not None:
-        line["sync_bn_on"] = syncbn_on
+    if syncbn_other is not None:
+        line["sync_bn_on" if syncbn_other["sync_bn"] else "sync_bn_off"] = syncbn_other
+    if replicas_equal is not None:
+        line["replicas_equal"] = replicas_equal
     if world == 1 and not args.no_aug and args.workload == DEFAULT_WORKLOAD:
         line["other_algorithms"] = other_algorithm_rates(cfg, dev, dtype, C, L, Bl, Bu, host[0])
     print(json.dumps(line), flush=True)
@@ -564,10 +680,16 @@ def cpu_augment_rate(C, L, budget_s=2.0):
     return round(n / (time.time() - t0), 1)
 
 
-def cpu_step_fn(workload):
-    """One FixMatch/Mean-Teacher step of the oracle port on the host CPU (fp32, all threads)."""
+PARITY_THRESH = 0.3    # at random init no position reaches the YAML's 0.8: the parity step uses a threshold near the median
+
+
+def cpu_step_fn(workload, dropout_off_first=False):
+    """One FixMatch/Mean-Teacher step of the oracle port on the host CPU (fp32, all threads).
+    dropout_off_first: the FIRST call runs without dropout at conf_thresh = PARITY_THRESH and returns the record that
+    parity_at_bench_shape compares the CUDA path with (losses, mask ratio, every parameter gradient)."""
     from algorithms.base import init_model_from_cfg
     from oracle import segnet_oracle as O
+    O.FAST_KERNELS = True    # BatchNorm / max-pool / upsample / CE through the ATen kernels the reference's modules call
     cfg, algo, C, L, Bl, Bu = load_cfg(workload)
     torch.manual_seed(cfg["seed"])
     model = init_model_from_cfg(cfg)
@@ -579,7 +701,17 @@ def cpu_step_fn(workload):
     g = torch.Generator().manual_seed(0)
     Lh = O.stage_lengths(arch, L)[-1]
 
+    calls = [0]
+
     def step():
+        calls[0] += 1
+        if dropout_off_first and calls[0] == 1:
+            thr0 = tr.cfg.get("conf_thresh")
+            tr.cfg = dict(tr.cfg, conf_thresh=PARITY_THRESH)
+            fn = tr.mean_teacher_step if algo == "mean_teacher" else tr.fixmatch_step
+            st_ = fn(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], 1e-3, dropout_mask=None)
+            tr.cfg = dict(tr.cfg, conf_thresh=thr0)
+            return {"stats": st_, "grads": {k: v.clone() for k, v in tr.grads.items()}, "pnames": list(tr.pnames)}
         dm = (torch.rand(Bl + Bu, arch.head_channels, Lh, generator=g) >= arch.dropout_ratio)
         if algo == "mean_teacher":
             return tr.mean_teacher_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], 1e-3, dropout_mask=dm)
@@ -587,20 +719,67 @@ def cpu_step_fn(workload):
     return step, Bl + Bu
 
 
+def parity_at_bench_shape(workload, dtype, first):
+    """Outside every timed region: ONE step of the CUDA path (captured graph, the benchmarked batch and network) from
+    the same seeded weights on the same batch as the CPU oracle's first step (no dropout, threshold PARITY_THRESH),
+    compared with it -- the oracle is the checker here, never the thing measured."""
+    import copy
+    from algorithms.base import init_model_from_cfg
+    from algorithms.mean_teacher import init_teacher
+    from semiseg_b200 import _lib
+    from semiseg_b200.trainer import get_engine
+    cfg, algo, C, L, Bl, Bu = load_cfg(workload)
+    cfg = copy.deepcopy(cfg)
+    cfg["decode_head"]["FCNHead"]["dropout_ratio"] = 0.0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(cfg["seed"])
+    model = init_model_from_cfg(cfg).to(dev)
+    teacher = init_teacher(cfg, model, dev) if algo == "mean_teacher" else None
+    tcfg = dict(cfg["train"], conf_thresh=PARITY_THRESH)
+    eng = get_engine(algo, model, teacher, Bl, Bu, L, dtype, tcfg, use_graph=True)
+    lab, unl = make_host_batch(cfg["seed"], 0, Bl, Bu, C, L)
+    eng.load_batch(torch.from_numpy(lab["ecg"]), torch.from_numpy(lab["target"]), torch.from_numpy(unl["ecg"]),
+                   torch.from_numpy(unl["ecg_aug"]))
+    eng.step(1e-3)
+    s, = eng.read_stats()
+    so = first["stats"]
+    tol = 2e-2 if dtype == _lib.BF16 else 1e-4
+    out = {"tolerance": tol, "threshold": PARITY_THRESH, "cuda": {k: round(float(v), 6) for k, v in s.items()},
+           "oracle_fp32_cpu": {k: round(float(v), 6) for k, v in so.items()}}
+    ok = all(abs(s[k] - so[k]) <= tol * max(1.0, abs(so[k])) for k in so)
+    grads = model.runtime().weights.param_views(model.runtime().state.grads)
+    g = torch.cat([grads[n].flatten().cpu().double() for n in first["pnames"]])
+    r = torch.cat([first["grads"][n].flatten().double() for n in first["pnames"]])
+    out["global_gradient_rel_err"] = float((g - r).norm() / (r.norm() + 1e-30))
+    head = ["decode_head.cls_seg.weight", "decode_head.cls_seg.bias"]
+    out["head_gradient_rel_err"] = max(float((grads[n].cpu().double() - first["grads"][n].double()).norm() /
+                                             (first["grads"][n].double().norm() + 1e-30)) for n in head)
+    ok = ok and out["head_gradient_rel_err"] <= tol
+    out["ok"] = bool(ok)
+    del eng, model
+    return out
+
+
 def cpu_baseline(workload, budget_s=15.0):
+    """(cpu_baseline dict, the oracle's first-step record for parity_at_bench_shape)"""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step, per = cpu_step_fn(workload)
-    step()
+    step, per = cpu_step_fn(workload, dropout_off_first=True)
+    first = step()
     t0 = time.time()
     n = 0
     while time.time() - t0 < budget_s and n < 100:
         step()
         n += 1
     dt = time.time() - t0
+    ratio = None
+    rf = os.path.join(REPO, "profiles", "r2_cpu_arm_vs_reference.json")
+    if os.path.exists(rf):
+        ratio = json.load(open(rf)).get("port_over_reference")
     return {"value": round(per * n / dt, 2), "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
             "sample": f"{n} steps of the same workload (oracle port of fixmatch.train_one_epoch body, torch CPU fp32, "
-                      f"{dt:.1f} s after 1 warm-up step)"}
+                      f"{dt:.1f} s after 1 warm-up step)",
+            "port_ms_over_reference_ms_in_build_container": ratio}, first
 
 
 def run_reference(args):
@@ -623,7 +802,7 @@ def run_reference(args):
         "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
         "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic LUDB-shaped strips, random-init weights",
-        "config": {"workload": args.workload, "algorithm": algo, "per_gpu_batch": f"{Bl}+{Bu}", "leads": C, "length": L},
+        "config": config_block(args.workload, args.gpus, bool(cfg["ddp"].get("sync_bn", True)) if args.sync_bn is None else bool(args.sync_bn)),
         "cpu_baseline": {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{args.steps} steps of the workload on the host CPU (oracle port of the reference step; the "
                                    "reference is Python and is not shipped to the GPU box)"},
@@ -638,12 +817,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--sync-bn", type=int, default=0, help="1: SyncBatchNorm statistic exchange (reference default); "
-                    "0: per-rank BN (ddp.sync_bn: false)")
+    ap.add_argument("--sync-bn", type=int, default=None, help="1: SyncBatchNorm statistic exchange; 0: per-rank BN "
+                    "(ddp.sync_bn: false); default: the YAML's ddp.sync_bn (true, like the reference)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--syncbn-extra", action="store_true", help="N>1: also time the step with SyncBN on (reference YAML "
-                    "default) after the headline measurement and report it as sync_bn_on")
+    ap.add_argument("--no-syncbn-other", action="store_true", help="N>1: skip timing the step with the OTHER SyncBN setting "
+                    "(reported as sync_bn_off / sync_bn_on next to the headline)")
+    ap.add_argument("--no-library", action="store_true", help="skip the torch.nn / cuDNN eager baseline of the same step")
     ap.add_argument("--no-aug", action="store_true", help="skip the supplementary GPU-augmentation measurement")
     ap.add_argument("--no-large", action="store_true", help="skip the supplementary large-batch roofline block")
     ap.add_argument("--profile-mode", action="store_true", help="warm-up + K plain steps only (for ncu)")

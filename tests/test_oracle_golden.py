@@ -66,6 +66,14 @@ def test_fixmatch_steps(golden, tag, dropout):
             assert rel_err(tr.sd[name], refv) < 1e-4, name
 
 
+@pytest.mark.parametrize("tag,dropout", [("B", 0.0), ("D", 0.1)])
+def test_fixmatch_steps_fast_kernels(golden, tag, dropout, monkeypatch):
+    """the timing arm's mode of the oracle (BatchNorm / max-pool / upsample / CE through the ATen kernels the reference's
+    modules call, bench.py cpu_baseline / --impl reference) is held to the same golden vectors"""
+    monkeypatch.setattr(O, "FAST_KERNELS", True)
+    test_fixmatch_steps(golden, tag, dropout)
+
+
 def test_mean_teacher_steps(golden):
     g = golden
     cfg = dict(TRAIN_CFG, ema_decay=0.99)

@@ -71,11 +71,67 @@ def full(src, dst, note):
     print(out.getvalue())
 
 
+# kernel function name (substring) -> index of bench.py's FAMILIES
+KERNEL_FAMILY = [("conv_tn", 0), ("zero_parity_rows", 0), ("tap_gemm", 0), ("conv_wgrad", 1), ("wgrad_kernel", 1),
+                 ("stem_conv", 3), ("bn_", 2), ("stem_bn", 2), ("stem_bwd", 2)]
+
+
+def traffic(src, dst, note, workload, steps):
+    """`ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --print-units base --csv` of
+    `bench.py --profile-mode --steps <steps>` -> DRAM bytes per kernel family per step, merged into the JSON file
+    `dst` under the workload's name (bench.py reads it for roofline.traffic)."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import FAMILIES
+    rows = list(csv.reader(open(src)))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, data = rows[hi], rows[hi + 1:]
+    ii, ki, mi, vi = hdr.index("ID"), hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    per = collections.OrderedDict()
+    for r in data:
+        if len(r) <= vi:
+            continue
+        d = per.setdefault(r[ii], {"name": r[ki].split("(")[0].replace("void ", "").replace("<unnamed>::", "")})
+        d[r[mi]] = float(r[vi].replace(",", ""))
+    fams = collections.defaultdict(lambda: {"dram_bytes_per_step": 0.0, "launches_per_step": 0.0, "time_us_per_step": 0.0})
+    kern = collections.defaultdict(lambda: {"dram_bytes": 0.0, "launches": 0, "time_us": 0.0})
+    for d in per.values():
+        fam = FAMILIES[-1][0]
+        for sub, idx in KERNEL_FAMILY:
+            if sub in d["name"]:
+                fam = FAMILIES[idx][0]
+                break
+        b = d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+        f = fams[fam]
+        f["dram_bytes_per_step"] += b / steps
+        f["launches_per_step"] += 1.0 / steps
+        f["time_us_per_step"] += d.get("gpu__time_duration.sum", 0.0) / 1e3 / steps
+        k = kern[d["name"]]
+        k["dram_bytes"] += b
+        k["launches"] += 1
+        k["time_us"] += d.get("gpu__time_duration.sum", 0.0) / 1e3
+    out = json.load(open(dst)) if os.path.exists(dst) else {}
+    out[workload] = {"source": f"{note} ({src}; {len(per)} launches = {steps} steps; cold-cache, serialised under ncu)",
+                     "families": {k: {kk: round(vv, 2) for kk, vv in v.items()} for k, v in fams.items()},
+                     "kernels": {k: {"launches": v["launches"], "dram_bytes_per_launch": round(v["dram_bytes"] / v["launches"]),
+                                     "us_per_launch": round(v["time_us"] / v["launches"], 2)} for k, v in
+                                 sorted(kern.items(), key=lambda kv: -kv[1]["time_us"])}}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out[workload]["families"], indent=1))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("mode", choices=["launches", "full"])
+    ap.add_argument("mode", choices=["launches", "full", "traffic"])
     ap.add_argument("src")
     ap.add_argument("dst")
     ap.add_argument("--note", default="")
+    ap.add_argument("--workload", default="fixmatch_resnet18_ludb_1x2500_b16+16")
+    ap.add_argument("--steps", type=int, default=2)
     a = ap.parse_args()
-    (launches if a.mode == "launches" else full)(a.src, a.dst, a.note)
+    if a.mode == "traffic":
+        traffic(a.src, a.dst, a.note, a.workload, a.steps)
+    else:
+        (launches if a.mode == "launches" else full)(a.src, a.dst, a.note)
