@@ -168,14 +168,39 @@ def train(config):
 
 
 def test(config):
-    """Evaluate `config['resume']` on the test split (reference base.py:442-499, minus csv/npy dumps)."""
-    device, seed = _setup(config)
+    """Evaluate a trained checkpoint on the test split (reference base.py:442-499): `test.model_path`, else
+    `<output_dir>/<exp_name>/best-<test.target_metric>.pth`; the checkpoint must exist (a freshly initialised model is
+    never scored); rank 0 only; writes test_metrics.csv, test_outputs.npy and test_labels.npy like the reference."""
+    if not misc.is_main_process():
+        return None
+    device = torch.device(config["device"])
+    output_dir = os.path.join(config["output_dir"], str(config.get("exp_name", "exp")))
+    os.makedirs(output_dir, exist_ok=True)
     ds = build_seg_dataset(config["dataset"], split="test")
     ld = get_dataloader(ds, is_distributed=False, mode="test", **config["dataloader"])
     model = init_model_from_cfg(config, train=False)
+    tcfg = config.get("test") or {}
+    if tcfg.get("model_path", None):
+        path = tcfg["model_path"]
+    else:
+        path = os.path.join(output_dir, f"best-{tcfg.get('target_metric', 'loss')}.pth")
+    assert os.path.exists(path), f"Checkpoint not found: {path}"
+    state_dict = torch.load(path, map_location="cpu", weights_only=False)["model"]
+    for k in list(state_dict.keys()):          # drop the auxiliary head
+        if k.startswith("auxiliary_head"):
+            del state_dict[k]
+    print(model.load_state_dict(state_dict))
     model.to(device)
-    if config.get("resume"):
-        model.load_state_dict(torch.load(config["resume"], map_location="cpu", weights_only=False)["model"])
-    stats, metrics, _, _ = evaluate(model, ld, device, config.get("metric"), use_amp=config.get("use_amp", True))
-    print({**stats, **metrics})
+    stats, metrics, outputs, labels = evaluate(model, ld, device, config.get("metric"), use_amp=config.get("use_amp", True),
+                                               return_outputs=True)
+    metrics = dict(metrics, loss=stats["loss"])
+    import csv
+    with open(os.path.join(output_dir, "test_metrics.csv"), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(list(metrics.keys()))
+        w.writerow([f"{float(v):.4f}" for v in metrics.values()])
+    if outputs is not None:
+        np.save(os.path.join(output_dir, "test_outputs.npy"), outputs.cpu().numpy())
+        np.save(os.path.join(output_dir, "test_labels.npy"), labels.cpu().numpy())
+    print("Done!")
     return stats, metrics

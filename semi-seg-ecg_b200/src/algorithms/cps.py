@@ -37,6 +37,7 @@ def train(config):
     # two models drawn one after the other from the same RNG stream (cps.py:271-272): different initialisations
     model_1, optimizer_1, scaler = build_model_and_optimizer(config, device, seed)
     model_2, optimizer_2, _ = build_model_and_optimizer(config, device, seed)
+    model_2.seed = seed + 1      # the two networks draw independent dropout masks (two nn.Dropout modules in the reference)
 
     def epoch_fn(epoch, log_writer, use_amp):
         return train_one_epoch(model_1, model_2, ld_l, ld_u, optimizer_1, optimizer_2, device, epoch, scaler,

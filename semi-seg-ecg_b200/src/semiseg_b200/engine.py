@@ -84,7 +84,15 @@ class StepEngine:
         # tail rows of the student's own conv launches (NetPlan.forward_merged)
         # (measured: with the multi-branch graph the separate pseudo-label branch overlaps the student forward and
         # wins, 0.76 vs 0.80 ms; in single-stream mode the merged launches win, 0.89 vs 1.00 ms)
-        self.merged = algorithm == "fixmatch" and not weights.layout.spec.bottleneck and bool(int(os.environ.get(
+        # train.pseudo_dtype: "fp32" runs the pseudo-label / teacher forward through the FP32 kernels even when the
+        # training step is bf16 -- what the reference does (that forward sits outside autocast: fixmatch.py:87-91,
+        # mean_teacher.py:89-91, cps.py:95-101).  Default: the training dtype (bf16 on the tcgen05 path; its decisions
+        # differ from the fp32 ones only within 2e-2 of the threshold / of a tie: tests/test_bench_shapes_gpu.py).
+        pd = str(train_cfg.get("pseudo_dtype", "") or "").lower()
+        if pd not in ("", "same", "fp32", "float32", "bf16"):
+            raise ValueError(f"train.pseudo_dtype={pd!r}: expected 'fp32' or 'bf16'")
+        self.dtype_t = _lib.F32 if pd in ("fp32", "float32") else dtype
+        self.merged = algorithm == "fixmatch" and not weights.layout.spec.bottleneck and self.dtype_t == dtype and bool(int(os.environ.get(
             "SSB_MERGED_EVAL", "0" if int(os.environ.get("SSB_MULTI_STREAM", "1")) else "1")))
         self.x_all = torch.zeros(S + max(self.Bu, 1), Cl, L, dtype=torch.float32, device=dev)
         self.x_s = self.x_all[:S]
@@ -134,7 +142,7 @@ class StepEngine:
             if algorithm == "fixmatch" and self.multi_stream:
                 # self-eval pass must see the running stats from BEFORE this step's update (fixmatch.py:87-93)
                 self.bufs_snap = torch.empty_like(weights.bufs)
-            self.plan_t = NetPlan(tw, dtype, self.Bu, L, False, algo, bufs=self.bufs_snap)
+            self.plan_t = NetPlan(tw, self.dtype_t, self.Bu, L, False, algo if self.dtype_t == dtype else None, bufs=self.bufs_snap)
         if self.sync_bn:
             # SyncBatchNorm (fixmatch.py:290-291): statistic arenas are exchanged layer by layer
             for s in self.plan_s._bn_structs.values():
@@ -229,7 +237,7 @@ class StepEngine:
         sp.ema_first = 1 if self.ema_first else 0
         sp.step = t
         sp.rng_seed = self.seed & 0xFFFFFFFF
-        sp.rng_step = self.it & 0xFFFFFFFF
+        sp.rng_step = st.step & 0xFFFFFFFF      # optimizer step count: survives a resume (the engine's own counter does not)
         sp.grad_scale = 1.0 / self.world
         sp.conf_thresh = 0.0 if self.hard_teacher else float(self.cfg.get("conf_thresh", 0.0))
         C.memmove(self.sp_host[slot].data_ptr(), C.addressof(sp), 64)
@@ -412,6 +420,13 @@ class StepEngine:
         outstanding asynchronous D2H copies only)."""
         for slot in list(self._pending):
             self._retire(slot)
+        if getattr(self, "syncbn_p2p", False):
+            # the peer-memory statistics exchange gives up on a silent peer after ~20 s and records the exchange
+            # number in its mailbox header instead of hanging the GPU: statistics summed after that are wrong
+            err = int(self._mailbox[64:68].view(torch.int32).item())
+            if err:
+                raise RuntimeError(f"SyncBN statistics exchange timed out waiting for a peer (exchange #{err}); "
+                                   "the BatchNorm statistics of this rank are no longer trustworthy")
         out, self._done = self._done, []
         return out
 

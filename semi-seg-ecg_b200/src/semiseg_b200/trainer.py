@@ -63,7 +63,9 @@ def get_engine(algorithm: str, model, teacher, Bl: int, Bu: int, L: int, dtype: 
                          process_group=pg, sync_bn=bool(getattr(model, "sync_bn", False)),
                          seed=int(getattr(model, "seed", 0)), external_pseudo=external_pseudo)
         if rt_t is not None and algorithm == "mean_teacher":
-            eng.ema_first = not rt_t.ema_started
+            # fresh run: the teacher's parameters alias the student's until the first EMA (mean_teacher.py:281-290);
+            # a teacher restored from a checkpoint (misc.load_model) or already averaged keeps its own history
+            eng.ema_first = not (rt_t.ema_started or getattr(teacher, "ema_restored", False))
         rt.engines[key] = eng
     return eng
 

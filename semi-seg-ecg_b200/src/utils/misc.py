@@ -165,7 +165,12 @@ def load_model(config, model_without_ddp, optimizer, loss_scaler, model_ema=None
     if model_ema is not None and "model_ema" in checkpoint:
         # NOTE: the reference loads model_ema into storage still aliased with the student and thereby
         # overwrites the student (SURVEY.md Appendix A, quirk ii); here the two models own separate arenas.
+        if hasattr(model_ema, "runtime") and next(model_ema.parameters()).is_cuda:
+            model_ema.runtime(nbt_float=True).ensure()   # float32 num_batches_tracked, as the reference's EMA leaves them
         model_ema.load_state_dict(checkpoint["model_ema"])
+        # the restored teacher carries EMA history: the first step after the resume must CONTINUE the average
+        # (trainer.get_engine: ema_first = False), not re-initialise the teacher from the student
+        model_ema.ema_restored = True
     print("Resume checkpoint %s" % config["resume"])
     if "optimizer" in checkpoint and "epoch" in checkpoint and not config.get("eval"):
         optimizer.load_state_dict(checkpoint["optimizer"])

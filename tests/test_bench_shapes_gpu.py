@@ -324,6 +324,21 @@ def test_fixmatch_bf16_w128_12x5000():
     _check_bf16_step(model_cfg(12, 128, 128, 128, 0.0), _arch(12, 128, 128), 4, 4, 5000, 932, 12, False)
 
 
+def test_pseudo_dtype_fp32_decisions_are_the_fp32_path():
+    """train.pseudo_dtype: fp32 -- a bf16 training step whose pseudo-label forward runs through the FP32 kernels (the
+    reference keeps that forward outside autocast, fixmatch.py:87-91): confidences, labels and mask are bit-identical to
+    the all-FP32 step's."""
+    cfgm = model_cfg(1, 64, 64, 128, 0.0)
+    (lab, unl), = batches(950, 1, 8, 8, 1, 2500)
+    cfg = dict(TRAIN_CFG, conf_thresh=0.3)
+    _, eng32, s32, _ = _cuda_fixmatch(cfgm, cfg, lab, unl, _lib.F32)
+    _, engbf, sbf, _ = _cuda_fixmatch(cfgm, dict(cfg, pseudo_dtype="fp32"), lab, unl, _lib.BF16)
+    for k in ("conf", "label", "mask"):
+        assert torch.equal(engbf.mat[k], eng32.mat[k]), k
+    assert sbf["mask_ratio"] == s32["mask_ratio"] and 0.2 < sbf["mask_ratio"] < 0.8
+    assert abs(sbf["loss_total"] - s32["loss_total"]) < 2e-2
+
+
 def test_mean_teacher_full_width_2x2500():
     """BASELINE config 3's network (2 leads x 2500, full width), three Mean-Teacher steps on the FP32 path against the
     fp64 oracle: losses per step, student and teacher state (parameters, running statistics, float num_batches_tracked)
