@@ -219,7 +219,8 @@ def bf16_round(t: Tensor) -> Tensor:
 def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
             dropout_mask: Optional[Tensor] = None,
             new_buffers: Optional[Dict[str, Tensor]] = None,
-            taps: Optional[Dict[str, Tensor]] = None, quant=None) -> Dict[str, Tensor]:
+            taps: Optional[Dict[str, Tensor]] = None, quant=None,
+            relu_masks: Optional[Dict[str, Tensor]] = None) -> Dict[str, Tensor]:
     """EncoderDecoder.forward (encoder_decoder.py:78-108) over resnet.py:353-363
     (stem -> maxpool -> BasicBlocks, resnet.py:55-72) and FCNHead.forward (fcn_head.py:89-97).
 
@@ -232,6 +233,12 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
     activation: it emulates the BF16 path's storage roundings on top of exact arithmetic, so that
     the BF16 kernels can be checked tightly (kernel correctness) separately from the precision
     loss that bf16 storage itself causes.
+    ``relu_masks`` {tap name of a ReLU output: bool tensor} INJECTS the sign decisions of those ReLUs (like a dropout
+    mask): relu(t) becomes t * mask.  ReLU'(0) is discontinuous, so two correct implementations whose pre-activations
+    differ by rounding (1e-7) can take different decisions on an element that is ~0, which moves the gradients by
+    O(1e-3); with the decisions injected, both sides differentiate the same piecewise-linear function.  (The stem's
+    max-pool(relu(x)) is evaluated as relu(max-pool(x)) -- the same function -- so that its decisions live on the pooled
+    tensor, the one the CUDA path materialises.)  Tests only.
     """
     q = quant if quant is not None else (lambda t: t)
     if quant is not None:
@@ -243,12 +250,22 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
             taps[name] = t
         return t
 
+    def act(name, t):
+        if relu_masks is not None and name in relu_masks:
+            if taps is not None:
+                taps[name + ".pre"] = t.detach()
+            return t * relu_masks[name].to(t.dtype)
+        return torch.relu(t)
+
     L = x.shape[2]
     h = q(F.conv1d(x, sd["backbone.stem.0.weight"], None, stride=2, padding=3))
     tap("backbone.stem.0", h)
-    h = torch.relu(batchnorm(h, sd, "backbone.stem.1", train, new_buffers))
-    tap("backbone.stem", h)
-    h = q(maxpool_k3s2p1(h))
+    if relu_masks is not None and "backbone.maxpool" in relu_masks:
+        h = q(act("backbone.maxpool", maxpool_k3s2p1(batchnorm(h, sd, "backbone.stem.1", train, new_buffers))))
+    else:
+        h = torch.relu(batchnorm(h, sd, "backbone.stem.1", train, new_buffers))
+        tap("backbone.stem", h)
+        h = q(maxpool_k3s2p1(h))
     tap("backbone.maxpool", h)
     feats = []
     inpl = arch.stem_channels
@@ -279,7 +296,7 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
                 continue
             o = q(F.conv1d(h, sd[pre + ".conv1.weight"], None, stride=s, padding=1))
             tap(pre + ".conv1", o)
-            o = q(torch.relu(batchnorm(o, sd, pre + ".bn1", train, new_buffers)))
+            o = q(act(pre + ".relu1", batchnorm(o, sd, pre + ".bn1", train, new_buffers)))
             tap(pre + ".relu1", o)
             o = q(F.conv1d(o, sd[pre + ".conv2.weight"], None, stride=1, padding=1))
             tap(pre + ".conv2", o)
@@ -288,14 +305,14 @@ def forward(sd: Dict[str, Tensor], x: Tensor, arch: Arch, train: bool,
                 ident = q(F.conv1d(h, sd[pre + ".downsample.0.weight"], None, stride=s, padding=0))
                 tap(pre + ".downsample.0", ident)
                 ident = batchnorm(ident, sd, pre + ".downsample.1", train, new_buffers)
-            h = q(torch.relu(o + ident))
+            h = q(act(pre, o + ident))
             tap(pre, h)
         inpl = pl
         feats.append(h)
     f = feats[arch.in_index]
     h = q(F.conv1d(f, sd["decode_head.convs.0.0.weight"], None, stride=1, padding=1))
     tap("decode_head.convs.0.0", h)
-    h = q(torch.relu(batchnorm(h, sd, "decode_head.convs.0.1", train, new_buffers)))
+    h = q(act("decode_head.convs.0", batchnorm(h, sd, "decode_head.convs.0.1", train, new_buffers)))
     tap("decode_head.convs.0", h)
     if train and dropout_mask is not None and arch.dropout_ratio > 0:
         h = h * dropout_mask.to(h.dtype) / (1.0 - arch.dropout_ratio)
@@ -405,6 +422,7 @@ class OracleTrainer:
         self.teacher_sd: Optional[Dict[str, Tensor]] = None
         self.teacher_aliased = True
         self.quant = None   # set to bf16_round to emulate the BF16 path's storage roundings
+        self.relu_masks = None   # tests: injected ReLU sign decisions of the student's TRAIN forward (see forward())
 
     # ---- helpers -------------------------------------------------------------------
     def _leaf_params(self) -> Dict[str, Tensor]:
@@ -459,7 +477,8 @@ class OracleTrainer:
         sdg = self._leaf_params()
         nb: Dict[str, Tensor] = {}
         self.taps = {} if want_taps else None
-        out = forward(sdg, ecg.to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant)
+        out = forward(sdg, ecg.to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant,
+                      relu_masks=self.relu_masks)
         if want_taps:
             for t_ in self.taps.values():
                 if t_.requires_grad:
@@ -487,7 +506,8 @@ class OracleTrainer:
         nb: Dict[str, Tensor] = {}
         self.taps = {} if want_taps else None
         nl = ecg_x.shape[0]
-        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant)
+        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant,
+                      relu_masks=self.relu_masks)
         if want_taps:
             for t_ in self.taps.values():
                 if t_.requires_grad:
@@ -518,7 +538,8 @@ class OracleTrainer:
         nb: Dict[str, Tensor] = {}
         self.taps = {} if want_taps else None
         nl = ecg_x.shape[0]
-        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant)
+        out = forward(sdg, torch.cat((ecg_x, ecg_u_s)).to(self.dtype), self.arch, True, dropout_mask, nb, self.taps, quant=self.quant,
+                      relu_masks=self.relu_masks)
         self.low_logits = out["low_logits"]
         self.low_logits.retain_grad()
         seg = out["seg_logits"]
@@ -540,7 +561,8 @@ class OracleTrainer:
         nb: Dict[str, Tensor] = {}
         nl = ecg_x.shape[0]
         self.taps = {} if want_taps else None
-        out = forward(sdg, torch.cat((ecg_x, ecg_u_w)).to(self.dtype), self.arch, True, None, nb, self.taps, quant=self.quant)
+        out = forward(sdg, torch.cat((ecg_x, ecg_u_w)).to(self.dtype), self.arch, True, None, nb, self.taps, quant=self.quant,
+                      relu_masks=self.relu_masks)
         seg = out["seg_logits"]
         loss_x = ce_hard(seg[:nl], mask_x)
         loss_u = ce_hard(seg[nl:], label_u)

@@ -322,3 +322,5 @@ int ssb_aug_strong_standardize(const float* x, float* y, const ssb_aug_op* ops, 
 }
 
 }  // extern "C"
+
+SSB_TRACE_DEFINE(augment)

@@ -1122,3 +1122,5 @@ int ssb_stem_bwd_apply(const void* gp, const void* c0, const uint8_t* arg, const
 }
 
 }  // extern "C"
+
+SSB_TRACE_DEFINE(bn)

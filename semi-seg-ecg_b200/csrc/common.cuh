@@ -54,7 +54,52 @@ extern std::atomic<long long> g_ssb_launches;
 extern int g_ssb_pdl;
 // The dependent grid is released only once this one is past its own wait (measured: releasing at kernel
 // entry lets a whole chain of parked grids pile up and is slower; profiles/r1b_pdl.md).
+#ifndef SSB_TRACE
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+// Development build (make TRACE=1 -> lib/libsemiseg_b200_trace.so, tools/trace_step.py): block (0,0,0) of every launch
+// records %globaltimer at kernel entry and when it gets past its dependency wait, with the source line of the wait --
+// the timeline of one step INSIDE the replayed graph (gaps between dependent kernels, overlap of the branches).
+struct SsbTraceRec { unsigned long long t_entry, t_start; unsigned int line, grid, block, pad; };
+#define SSB_TRACE_CAP 4096
+static __device__ SsbTraceRec ssb_trace_buf[SSB_TRACE_CAP];
+static __device__ unsigned int ssb_trace_n;
+__device__ __forceinline__ unsigned long long ssb_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void pdl_wait_line(unsigned int line) {
+  const bool rec = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0;
+  const unsigned long long t0 = rec ? ssb_gtime() : 0ull;
+  asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory");
+  if (rec) {
+    const unsigned int i = atomicAdd(&ssb_trace_n, 1u);
+    if (i < SSB_TRACE_CAP) {
+      SsbTraceRec r;
+      r.t_entry = t0; r.t_start = ssb_gtime(); r.line = line;
+      r.grid = gridDim.x * gridDim.y * gridDim.z; r.block = blockDim.x; r.pad = 0;
+      ssb_trace_buf[i] = r;
+    }
+  }
+}
+#define pdl_wait() pdl_wait_line(__LINE__)
+// one per translation unit: copies (and optionally resets) this unit's records
+#define SSB_TRACE_DEFINE(tu)                                                                         \
+  extern "C" int ssb_trace_dump_##tu(void* host, int cap, int reset) {                              \
+    unsigned int n = 0;                                                                              \
+    cudaDeviceSynchronize();                                                                         \
+    cudaMemcpyFromSymbol(&n, ssb_trace_n, sizeof(n));                                                \
+    if (n > SSB_TRACE_CAP) n = SSB_TRACE_CAP;                                                        \
+    if ((int)n > cap) n = cap;                                                                       \
+    if (host && n) cudaMemcpyFromSymbol(host, ssb_trace_buf, n * sizeof(SsbTraceRec));               \
+    if (reset) { unsigned int z = 0; cudaMemcpyToSymbol(ssb_trace_n, &z, sizeof(z)); }              \
+    return (int)n;                                                                                   \
+  }
+#endif
+#ifndef SSB_TRACE_DEFINE
+#define SSB_TRACE_DEFINE(tu)
+#endif
 __device__ __forceinline__ void pdl_trigger() {}
 
 // g_ssb_pdl (env SSB_PDL): 0 = plain launches, 1 = every launch carries the attribute, 2 = only the

@@ -865,3 +865,5 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
 }
 
 }  // extern "C"
+
+SSB_TRACE_DEFINE(conv_simt)

@@ -1442,3 +1442,5 @@ int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gi
   SSB_LAUNCH_CHECK("conv_wgrad_kernel");
   return SSB_OK;
 }
+
+SSB_TRACE_DEFINE(conv_sm100)

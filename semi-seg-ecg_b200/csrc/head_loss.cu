@@ -590,3 +590,5 @@ int ssb_semi_loss(const float* low_s, const int64_t* target, const float* low_t,
 }
 
 }  // extern "C"
+
+SSB_TRACE_DEFINE(head_loss)

@@ -227,3 +227,5 @@ int ssb_syncbn_exchange(double* slice, int n, const uint64_t* peers_dev, int wor
 }
 
 }  // extern "C"
+
+SSB_TRACE_DEFINE(optim)

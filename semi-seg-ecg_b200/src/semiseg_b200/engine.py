@@ -275,6 +275,8 @@ class StepEngine:
         teacher_branch = False
         if self.plan_t is not None and self.external_pseudo:
             low_t = self.plan_t.low            # filled by pseudo(), which the owner ran before this step
+        elif self.plan_t is not None and "teacher" in os.environ.get("SSB_DEBUG_SKIP", ""):
+            low_t = self.plan_t.low            # timing experiments only: the step without its pseudo-label forward
         elif self.plan_t is not None:
             self.plan_t.pre_block_event = repacked
             teacher_branch = self.teacher_stream is not None

@@ -566,6 +566,8 @@ class NetPlan:
     def _wgrad(self, c: ConvDesc, x, dy, gin: Geom, gout: Geom, st: int):
         """dW += x^T dy.  With a wgrad stream: fork after dy is produced, remember that dy is still
         being read so that the next writer of that scratch buffer waits (WAR)."""
+        if "wgrad" in os.environ.get("SSB_DEBUG_SKIP", ""):   # timing experiments only: the step without its weight-gradient GEMMs
+            return
         if self.wgrad_stream is None:
             call("ssb_conv1d_wgrad", x.data_ptr(), dy.data_ptr(), self._g(c), gin, gout, c.k, c.stride, self.dtype,
                  self._algo_for(c), st)

@@ -162,6 +162,8 @@ def load_model(config, model_without_ddp, optimizer, loss_scaler, model_ema=None
         return
     checkpoint = torch.load(config["resume"], map_location="cpu", weights_only=False)
     model_without_ddp.load_state_dict(checkpoint["model"])
+    if hasattr(model_without_ddp, "runtime") and next(model_without_ddp.parameters()).is_cuda:
+        model_without_ddp.runtime().ensure()    # the flat arenas the fused optimizer's state lives in
     if model_ema is not None and "model_ema" in checkpoint:
         # NOTE: the reference loads model_ema into storage still aliased with the student and thereby
         # overwrites the student (SURVEY.md Appendix A, quirk ii); here the two models own separate arenas.

@@ -191,8 +191,10 @@ def _oracle_fixmatch(init, arch, lab, unl, dtype, quant=None, thr=None):
     return tr, s, cfg
 
 
-def _cuda_fixmatch(cfgm, cfg, lab, unl, dtype, algo=None, use_graph=False):
+def _cuda_fixmatch(cfgm, cfg, lab, unl, dtype, algo=None, use_graph=False, sd=None):
     model, _ = _init(cfgm)
+    if sd is not None:
+        model.load_state_dict(sd)
     model.to(DEV)
     Bl, Bu, L = lab["ecg"].shape[0], unl["ecg"].shape[0], lab["ecg"].shape[2]
     eng = get_engine("fixmatch", model, None, Bl, Bu, L, dtype, cfg, use_graph=use_graph, algo=algo)
@@ -205,47 +207,77 @@ def _cuda_fixmatch(cfgm, cfg, lab, unl, dtype, algo=None, use_graph=False):
     return model, eng, s, grads
 
 
-def _relu_flips(plan, taps):
-    n = 0
+def _relu_masks(plan):
+    """the CUDA path's ReLU sign decisions, keyed by the oracle's tap names"""
+    m = {}
     for bd, bufs in zip(plan.lay.blocks, plan.blk_bufs):
         g = plan.g_stage[bd.stage]
-        for mine, ref in ((bufs["a1"], taps[bd.prefix + ".relu1"]), (bufs["out"], taps[bd.prefix])):
-            n += int(((plan.to_ncl(mine, g).cpu() > 0) != (ref.detach() > 0)).sum())
-    n += int(((plan.to_ncl(plan.ah, plan.g_head).cpu() > 0) != (taps["decode_head.convs.0"].detach() > 0)).sum())
-    n += int(((plan.to_ncl(plan.p0, plan.g_pool).cpu() > 0) != (taps["backbone.maxpool"].detach() > 0)).sum())
-    return n
+        m[bd.prefix + ".relu1"] = plan.to_ncl(bufs["a1"], g).cpu() > 0
+        m[bd.prefix] = plan.to_ncl(bufs["out"], g).cpu() > 0
+    m["decode_head.convs.0"] = plan.to_ncl(plan.ah, plan.g_head).cpu() > 0
+    m["backbone.maxpool"] = plan.to_ncl(plan.p0, plan.g_pool).cpu() > 0
+    return m
+
+
+def _relu_flips(masks, taps):
+    return sum(int((m != (taps[n].detach() > 0)).sum()) for n, m in masks.items())
 
 
 def _check_fp32_step(cfgm, arch, Bl, Bu, L, seeds, leads):
-    """FP32 path vs the fp64 oracle on a batch where both take the same ReLU / pseudo-label decisions (walk `seeds`)."""
+    """FP32 path vs the fp64 oracle.  ReLU'(0) and the threshold comparison are discontinuous: at these sizes (1e8
+    ReLU decisions per step) a handful of pre-activations sit within fp32 rounding of zero and legitimately fall on
+    either side, each moving the gradients by O(1e-3).  So (1) the batch is walked until the pseudo-label decisions
+    agree, (2) the CUDA path's ReLU decisions are shown to differ from the free-running fp64 oracle's only on elements
+    that are ~0 there (|pre-activation| < 1e-5 of the tensor's RMS; a few per 1e8), and (3) the oracle is re-run with
+    those decisions INJECTED (like a dropout mask): the same piecewise-linear function on both sides, gradients to 1e-5."""
     _, init = _init(cfgm)
-    flips = -1
+    same_mask = False
     for seed in seeds:
         (lab, unl), = batches(seed, 1, Bl, Bu, leads, L)
         t64, s64, cfg = _oracle_fixmatch(init, arch, lab, unl, torch.float64)
         model, eng, s, grads = _cuda_fixmatch(cfgm, cfg, lab, unl, _lib.F32, _lib.ALGO_SIMT)
-        flips = _relu_flips(eng.plan_s, t64.taps)
         same_mask = torch.equal(eng.mat["mask"].cpu().bool(), t64.pseudo["mask"]) and torch.equal(eng.mat["label"].cpu(), t64.pseudo["label"])
-        print(f"data seed {seed}: {flips} ReLU sign decisions differ, pseudo-label decisions equal: {same_mask}")
-        if flips == 0 and same_mask:
+        if same_mask:
             break
-    assert flips == 0 and same_mask, "no candidate batch without a rounding-level ReLU / threshold coincidence"
-    t32, s32, _ = _oracle_fixmatch(init, arch, lab, unl, torch.float32, thr=cfg["conf_thresh"])
+    assert same_mask, "no candidate batch with equal pseudo-label decisions"
+    masks = _relu_masks(eng.plan_s)
+    flips = _relu_flips(masks, t64.taps)
+    total = sum(m.numel() for m in masks.values())
+    runs = {}
+    for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        tr = O.OracleTrainer(init, arch, cfg, dtype=dt)
+        tr.relu_masks = masks
+        runs[name] = (tr, tr.fixmatch_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], O.lr_at(3.0, cfg), want_taps=True))
+    (m64, ms64), (m32, _) = runs["f64"], runs["f32"]
+    worst_pre = 0.0
+    for n, m in masks.items():        # the injected decisions differ from the free ones only on elements that are ~0
+        diff = m != (t64.taps[n].detach() > 0)
+        if diff.any():
+            pre = m64.taps[n + ".pre"]
+            worst_pre = max(worst_pre, float(pre[diff].abs().max() / pre.pow(2).mean().sqrt()))
+    print(f"data seed {seed}: {flips} of {total} ReLU decisions differ from the free-running fp64 oracle; largest such "
+          f"|pre-activation| / RMS = {worst_pre:.1e}")
+    assert flips <= 1e-6 * total + 2 and worst_pre < 1e-5
     for k in ("loss_total", "loss_x", "loss_u_s", "mask_ratio"):
-        assert abs(s[k] - s64[k]) < 1e-5 * max(1.0, abs(s64[k])), (k, s[k], s64[k])
+        assert abs(s[k] - s64[k]) < 1e-5 * max(1.0, abs(s64[k])), (k, s[k], s64[k])          # free-running oracle
+        assert abs(s[k] - ms64[k]) < 1e-5 * max(1.0, abs(ms64[k])), (k, s[k], ms64[k])
     bad, worst = [], 0.0
-    for n in t64.pnames:
-        e, e32 = rel_err(grads[n], t64.grads[n]), rel_err(t32.grads[n], t64.grads[n])
+    for n in m64.pnames:
+        e, e32 = rel_err(grads[n], m64.grads[n]), rel_err(m32.grads[n], m64.grads[n])
         worst = max(worst, e)
         if not e < max(1e-5, 4 * e32):
             bad.append((n, e, e32))
-    gflat = torch.cat([grads[n].flatten().cpu().double() for n in t64.pnames])
-    rflat = torch.cat([t64.grads[n].flatten() for n in t64.pnames])
-    print(f"fp32 {Bl}+{Bu} x {leads}x{L}: worst per-tensor grad err {worst:.2e}, global {rel_err(gflat, rflat):.2e}, "
-          f"mask_ratio {s['mask_ratio']:.3f}")
+    gflat = torch.cat([grads[n].flatten().cpu().double() for n in m64.pnames])
+    rflat = torch.cat([m64.grads[n].flatten() for n in m64.pnames])
+    fflat = torch.cat([t64.grads[n].flatten() for n in m64.pnames])
+    print(f"fp32 {Bl}+{Bu} x {leads}x{L}: worst per-tensor grad err {worst:.2e}, global {rel_err(gflat, rflat):.2e} "
+          f"(vs the free-running oracle: {rel_err(gflat, fflat):.2e}), mask_ratio {s['mask_ratio']:.3f}")
     assert not bad, bad
     assert rel_err(gflat, rflat) < 1e-5
     assert 0.2 < s["mask_ratio"] < 0.8      # the masked branch is exercised
+    sd = model.state_dict()
+    for n in m64.pnames:                     # updated weights (first Adam step = lr * g / (|g| + eps), see test_step_parity_gpu)
+        assert rel_err(sd[n], m64.sd[n]) < 5e-5, n
 
 
 def test_fixmatch_fp32_b16_16():
@@ -263,17 +295,19 @@ def test_fixmatch_fp32_w128_12x5000():
     _check_fp32_step(model_cfg(12, 128, 128, 128, 0.0), _arch(12, 128, 128), 2, 2, 5000, (920, 921, 922, 923), 12)
 
 
-def _check_bf16_step(cfgm, arch, Bl, Bu, L, seed, leads, graph):
+def _check_bf16_step(cfgm, arch, Bl, Bu, L, seed, leads, graph, init=None, data=None, grad_tol=None):
     """BF16 tcgen05 path, whole FixMatch step.  (1) losses within 2e-2 of the exact fp64 oracle; (2) pseudo-label
     decisions differ from the exact oracle's only where the oracle's own confidence is within 2e-2 of the threshold
     (labels: only where the top-2 probabilities are within 2e-2); (3) gradients: global and per tensor against the exact
     oracle, 2e-2 or what bf16 storage alone causes (oracle with the same roundings emulated) -- the printed table says
     which tensors meet the plain 2e-2."""
-    _, init = _init(cfgm)
-    (lab, unl), = batches(seed, 1, Bl, Bu, leads, L)
+    sd0 = init
+    if init is None:
+        _, init = _init(cfgm)
+    (lab, unl), = batches(seed, 1, Bl, Bu, leads, L) if data is None else (data,)
     t64, s64, cfg = _oracle_fixmatch(init, arch, lab, unl, torch.float64)
     temu, semu, _ = _oracle_fixmatch(init, arch, lab, unl, torch.float64, quant=O.bf16_round, thr=cfg["conf_thresh"])
-    model, eng, s, grads = _cuda_fixmatch(cfgm, cfg, lab, unl, _lib.BF16, None, use_graph=graph)
+    model, eng, s, grads = _cuda_fixmatch(cfgm, cfg, lab, unl, _lib.BF16, None, use_graph=graph, sd=sd0)
     thr = cfg["conf_thresh"]
     conf64, mask64, lab64 = t64.pseudo["conf"], t64.pseudo["mask"], t64.pseudo["label"]
     mask = eng.mat["mask"].cpu().bool()
@@ -285,6 +319,10 @@ def _check_bf16_step(cfgm, arch, Bl, Bu, L, seed, leads, graph):
     assert float((top2[:, 0] - top2[:, 1])[ldiff].max()) <= 2e-2 if ldiff.any() else True, "labels differ away from a tie"
     mism, lmism = float(diff.float().mean()), float(ldiff.float().mean())
     near = float(((conf64 - thr).abs() <= 2e-2).float().mean())
+    dconf = float((eng.mat["conf"].cpu().double() - conf64).abs().max())
+    print(f"  largest |conf_bf16 - conf_fp64| = {dconf:.2e}; fp64 confidences: 5th/50th/95th percentile "
+          f"{float(conf64.flatten().kthvalue(max(1, int(0.05 * conf64.numel()))).values):.3f} / {float(conf64.median()):.3f} / "
+          f"{float(conf64.flatten().kthvalue(int(0.95 * conf64.numel())).values):.3f}, threshold {thr:.4f}")
     assert mism <= near
     assert rel_err(eng.mat["conf"], conf64) < 2e-2
     for k in ("loss_total", "loss_x", "loss_u_s"):
@@ -296,7 +334,7 @@ def _check_bf16_step(cfgm, arch, Bl, Bu, L, seed, leads, graph):
         worst = max(worst, e)
         ok2 += e < 2e-2
         print(f"  grad {n:40s} {e:.2e} (bf16 storage alone {ee:.2e})")
-        assert e < max(2e-2, 1.5 * ee), (n, e, ee)
+        assert e < max(grad_tol or 2e-2, 1.5 * ee), (n, e, ee)
     gflat = torch.cat([grads[n].flatten().cpu().double() for n in t64.pnames])
     rflat = torch.cat([t64.grads[n].flatten() for n in t64.pnames])
     eflat = torch.cat([temu.grads[n].flatten() for n in t64.pnames])
@@ -308,6 +346,46 @@ def _check_bf16_step(cfgm, arch, Bl, Bu, L, seed, leads, graph):
     for n in ("decode_head.cls_seg.weight", "decode_head.cls_seg.bias"):     # well-conditioned: plain 2e-2
         assert rel_err(grads[n], t64.grads[n]) < 2e-2, n
     return ge, gee
+
+
+def _structured_batch(seed, Bl, Bu, leads, L):
+    """strips whose samples carry their label (class-dependent offset + noise, z-scored): something a network can
+    actually fit, unlike the benchmark's pure-noise strips"""
+    from semiseg_b200 import synthetic
+    rng = np.random.default_rng(seed)
+    level = np.array([0.0, 1.0, -1.5, 0.6], dtype=np.float32)
+    yl, yu = synthetic.make_labels(rng, Bl, L), synthetic.make_labels(rng, Bu, L)
+    xl = synthetic.zscore(level[yl][:, None, :] + 0.5 * rng.standard_normal((Bl, leads, L)).astype(np.float32))
+    xw = synthetic.zscore(level[yu][:, None, :] + 0.5 * rng.standard_normal((Bu, leads, L)).astype(np.float32))
+    xs = synthetic.zscore(xw + 0.5 * rng.standard_normal(xw.shape).astype(np.float32))
+    t = torch.from_numpy
+    return {"ecg": t(xl), "target": t(yl)}, {"ecg": t(xw), "ecg_aug": t(xs)}
+
+
+def test_fixmatch_bf16_b16_16_trained_state():
+    """Where do the tens-of-percent bf16 gradient errors at random init come from?  At random init the logits barely
+    depend on the position (83 % of the confidences lie within 2e-2 of their median), the loss gradient is almost
+    entirely a per-channel constant, and train-mode BatchNorm's backward projects exactly that component out -- what is
+    left is a small difference of large numbers, so ANY 2^-9 storage rounding moves it by tens of percent (the oracle
+    with emulated bf16 storage shows the same figures).  Here the same network is first fitted for 150 steps to strips
+    that carry their labels; from that state the same comparison is made and the errors are reported (and bounded by
+    what bf16 storage alone causes)."""
+    cfgm, arch = model_cfg(1, 64, 64, 128, 0.0), _arch(1, 64, 64)
+    model, _ = _init(cfgm)
+    model.to(DEV)
+    cfg = dict(TRAIN_CFG, conf_thresh=0.95)
+    eng = get_engine("fixmatch", model, None, 16, 16, 2500, _lib.BF16, cfg, use_graph=True)
+    pool = [_structured_batch(7000 + i, 16, 16, 1, 2500) for i in range(8)]
+    for i in range(150):
+        lab, unl = pool[i % 8]
+        eng.load_batch(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"])
+        eng.step(1e-3)
+    st = eng.read_stats()
+    print(f"fitted: loss_x {st[0]['loss_x']:.3f} -> {st[-1]['loss_x']:.3f}, mask_ratio {st[-1]['mask_ratio']:.3f}")
+    assert st[-1]["loss_x"] < 0.5 * st[0]["loss_x"]
+    init = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    ge, gee = _check_bf16_step(cfgm, arch, 16, 16, 2500, 0, 1, True, init=init, data=_structured_batch(7100, 16, 16, 1, 2500))
+    print(f"trained state: global gradient error {ge:.2e} (bf16 storage alone {gee:.2e})")
 
 
 def test_fixmatch_bf16_b16_16():

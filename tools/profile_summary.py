@@ -72,8 +72,8 @@ def full(src, dst, note):
 
 
 # kernel function name (substring) -> index of bench.py's FAMILIES
-KERNEL_FAMILY = [("conv_tn", 0), ("zero_parity_rows", 0), ("tap_gemm", 0), ("conv_wgrad", 1), ("wgrad_kernel", 1),
-                 ("stem_conv", 3), ("bn_", 2), ("stem_bn", 2), ("stem_bwd", 2)]
+KERNEL_FAMILY = [("stem_conv", 3), ("conv_tn", 0), ("zero_parity_rows", 0), ("tap_gemm", 0), ("conv_wgrad", 1), ("wgrad_kernel", 1),
+                 ("bn_", 2), ("stem_bn", 2), ("stem_bwd", 2)]
 
 
 def traffic(src, dst, note, workload, steps):
