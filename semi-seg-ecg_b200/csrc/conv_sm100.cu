@@ -1094,6 +1094,29 @@ int launch_tn3(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const 
   return SSB_OK;
 }
 
+// Split count of a weight-gradient launch: `tiles` independent output tiles, each reducing over `nblk` row blocks, one
+// (BN=128) or two (BN=64) CTAs per SM.  ceil(#SMs / tiles) splits -- the round-1 rule -- often lands just above a
+// whole number of waves (16 tiles x 3 taps x 4 splits = 192 CTAs on 148 SMs = two waves of 11 blocks instead of one wave
+// of 14: ncu, profiles/r2_conv_w128_launches.md).  Pick the count that minimises waves x (blocks per CTA + fixed cost),
+// the fixed cost (pipeline fill + the RED epilogue of the partial tile) expressed in reduction blocks.
+int pick_splits(int tiles, int nblk, int ctas_per_sm, int fixed_blocks) {
+  const int cap = g_num_sms * ctas_per_sm;
+  int max_ns = nblk / 4;
+  if (max_ns < 1) max_ns = 1;
+  int best = 1;
+  long long best_cost = -1;
+  for (int ns = 1; ns <= max_ns; ++ns) {
+    const long long ctas = (long long)tiles * ns;
+    if (ctas > 4LL * cap && ns > 1) break;
+    const long long waves = (ctas + cap - 1) / cap;
+    const long long cost = waves * (ceil_div(nblk, ns) + fixed_blocks);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ns; }
+  }
+  return best;
+}
+int g_wg_split_rule = 1;   // env SSB_WG_SPLIT=0: the round-1 rule (A/B comparison)
+int g_wg_fixed = 4, g_wg3_fixed = 8;   // env SSB_WG_FIXED / SSB_WG3_FIXED: fixed per-CTA cost in reduction blocks
+
 int g_tn3 = 1;   // env SSB_TN3=0 disables the tap-reuse kernel (A/B comparison)
 int g_wg3 = 1;   // env SSB_WG3=0 disables the tap-fused wgrad kernel
 
@@ -1220,6 +1243,9 @@ int ssb_sm100_prepare() {
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_wgrad3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_wg3_bytes<64>());
   if (const char* w3 = getenv("SSB_WG3")) g_wg3 = atoi(w3);
+  if (const char* ws = getenv("SSB_WG_SPLIT")) g_wg_split_rule = atoi(ws);
+  if (const char* wf = getenv("SSB_WG_FIXED")) g_wg_fixed = atoi(wf);
+  if (const char* wf = getenv("SSB_WG3_FIXED")) g_wg3_fixed = atoi(wf);
   if (e != cudaSuccess) {
     ssb_set_error("ssb_sm100_prepare: %s", cudaGetErrorString(e));
     return SSB_ERR_CUDA;
@@ -1405,6 +1431,7 @@ int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gi
     int ns = ceil_div(g_num_sms, tiles3);
     if (ns > nblk / 4) ns = nblk / 4;
     if (ns < 1) ns = 1;
+    if (g_wg_split_rule) ns = pick_splits(tiles3, nblk, 1, g_wg3_fixed);
     p.blocks_per_split = ceil_div(nblk, ns);
     p.nsplit = ceil_div(nblk, p.blocks_per_split);
     CUtensorMap tmX3, tmDY3;
@@ -1421,9 +1448,10 @@ int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gi
     return SSB_OK;
   }
   const int tiles = p.n_ci_tiles * (gout.C / BN) * k;
-  int nsplit = ceil_div(148, tiles);
+  int nsplit = ceil_div(g_num_sms, tiles);
   if (nsplit > nblk / 4) nsplit = nblk / 4;
   if (nsplit < 1) nsplit = 1;
+  if (g_wg_split_rule) nsplit = pick_splits(tiles, nblk, BN == 64 ? 2 : 1, g_wg_fixed);
   p.blocks_per_split = ceil_div(nblk, nsplit);
   p.nsplit = ceil_div(nblk, p.blocks_per_split);
   CUtensorMap tmX, tmDY;
