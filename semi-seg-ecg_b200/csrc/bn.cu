@@ -2,6 +2,11 @@
 // Replaces cuDNN/ATen native_batch_norm + relu_ + add_ + max_pool (+ their backward
 // kernels) at resnet.py:41-70,254-257,354-355 and fcn_head.py:48-49.  HBM-bound: every
 // kernel moves 16-byte vectors, channels fastest (coalesced), one pass per tensor.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include <utility>
+
 #include "common.cuh"
 
 #define BN_THREADS 256
@@ -583,7 +588,9 @@ __global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fu
     if (RES == 2) atomicAdd(&rep_r[rsel + C + c], (double)dc);
     __threadfence();   // this thread's reductions are performed before the block signals the barrier
   }
+  if (threadIdx.x == 0) SSB_MARK();                 // pass 1 + atomics done
   grid_barrier(barrier, gridDim.x * gridDim.y);
+  if (threadIdx.x == 0) SSB_MARK();                 // past the grid barrier
   // ---- pass 2: apply; per-channel constants from the now complete sums (one thread per channel) ----
   const int nch = cgpc * V;
   if (threadIdx.x < nch) {
@@ -678,6 +685,211 @@ __global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fu
     if (RES == 1) ogi.store(gid + off);
     if (RES == 2) odr.store(dxr + off);
   }
+}
+
+// ---------------------------------------------------------------------------------------
+// backward, both passes in ONE launch and ONE read of the operands: thread-block CLUSTERS + distributed shared memory.
+// The in-kernel timeline of the config-2 step (profiles/r2_trace_config2.md) shows the grid-barrier kernel above at
+// 10-14 us per BatchNorm layer on the critical path of the backward (17 layers): load -> shared reduce -> fp64 atomics
+// -> fence -> grid barrier -> reload of the sums -> second read of the operands -> store, every arrow a round trip to
+// L2.  Here a cluster of CL blocks owns ALL rows of a chunk of <= 64 channels: every thread keeps its <= NR rows of
+// (masked gradient, x[, x_res]) in REGISTERS, the block partials meet in shared memory, the CL blocks read one another's
+// partials through DSMEM after one hardware cluster barrier (no global atomics, no fence, no spin), and the apply pass
+// runs from the registers.  Summation order is fixed (warp tree -> 8 warps -> CL ranks in rank order): deterministic.
+// Fits when rows <= CL * NR * (256 / vector groups per chunk); larger tensors keep the kernels above.
+// RES: 0 none; 1 identity residual -> g_ident = g; 2 residual BN -> dx_res
+// ---------------------------------------------------------------------------------------
+template <typename T, bool HAS_Y, int RES, int NR>
+__global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_cluster_kernel(const T* __restrict__ g1, const T* __restrict__ y,
+                                                                      const T* __restrict__ x, const T* __restrict__ xr,
+                                                                      T* __restrict__ dx, T* __restrict__ dxr, T* __restrict__ gid,
+                                                                      ssb_bn bn, ssb_bn bnr, ssb_geom g, int cgpc, int rows_per_cta) {
+  namespace cgs = cooperative_groups;
+  pdl_trigger();
+  pdl_wait();
+  constexpr int V = Vec<T>::N;
+  constexpr int NQ = RES == 2 ? 3 : 2;
+  cgs::cluster_group cluster = cgs::this_cluster();
+  const unsigned CL = cluster.num_blocks(), rank = cluster.block_rank();
+  const int C = g.C;
+  const int chunk = blockIdx.x / CL;
+  const int cpc = cgpc * V;                       // channels of this chunk (<= 64)
+  const int rpp = BN_THREADS / cgpc;              // row lanes
+  const int cgl = threadIdx.x % cgpc, rl = threadIdx.x / cgpc;
+  const int cg = chunk * cgpc + cgl;              // 16-byte channel group
+  const int rows = g.B * g.pitch;
+  const int r0 = (int)rank * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  __shared__ float s_warp[BN_THREADS / 32][NQ][64];
+  __shared__ float s_part[NQ][64];                // this block's partial sums: read by the whole cluster
+  __shared__ float s_co[5][64];
+  float mean[V], inv[V], meanr[V], invr[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = cg * V + i;
+    mean[i] = bn.mean_invstd[c];
+    inv[i] = bn.mean_invstd[C + c];
+    if (RES == 2) {
+      meanr[i] = bnr.mean_invstd[c];
+      invr[i] = bnr.mean_invstd[C + c];
+    }
+  }
+  // ---- one read of the operands: all loads of a thread's rows are issued before the first use ----
+  Vec<T> kg[NR], kx[NR], kr[RES == 2 ? NR : 1], ky[HAS_Y ? NR : 1];
+  bool ok[NR];
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    const int row = r0 + rl + k * rpp;
+    ok[k] = row < r1 && row_valid(row, g.pitch, g.len);
+    if (ok[k]) {
+      const size_t off = (size_t)row * C + (size_t)cg * V;
+      kg[k].load(g1 + off);
+      kx[k].load(x + off);
+      if (HAS_Y) ky[k].load(y + off);
+      if (RES == 2) kr[k].load(xr + off);
+    }
+  }
+  float a[V], bq[V], cq[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) a[i] = bq[i] = cq[i] = 0.f;
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    if (!ok[k]) continue;
+    float fg[V], fx[V];
+    kg[k].get(fg);
+    kx[k].get(fx);
+    if (HAS_Y) {
+      float fy[V];
+      ky[k].get(fy);
+#pragma unroll
+      for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
+      kg[k].set(fg);            // exact: masking keeps the stored values or zero
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      a[i] += fg[i];
+      bq[i] += fg[i] * ((fx[i] - mean[i]) * inv[i]);
+    }
+    if (RES == 2) {
+      float fr[V];
+      kr[k].get(fr);
+#pragma unroll
+      for (int i = 0; i < V; ++i) cq[i] += fg[i] * ((fr[i] - meanr[i]) * invr[i]);
+    }
+  }
+  // ---- block partials: lanes of a warp that share a channel group (lane % cgpc) are summed by xor shuffles ----
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    if (o >= cgpc) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+        bq[i] += __shfl_xor_sync(0xffffffffu, bq[i], o);
+        if (RES == 2) cq[i] += __shfl_xor_sync(0xffffffffu, cq[i], o);
+      }
+    }
+  }
+  if (lane < cgpc) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      s_warp[warp][0][lane * V + i] = a[i];
+      s_warp[warp][1][lane * V + i] = bq[i];
+      if (RES == 2) s_warp[warp][2][lane * V + i] = cq[i];
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NQ * cpc) {
+    const int q = threadIdx.x / cpc, ch = threadIdx.x - q * cpc;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < BN_THREADS / 32; ++w) t += s_warp[w][q][ch];
+    s_part[q][ch] = t;
+  }
+  if (threadIdx.x == 0) SSB_MARK();                 // operands read, block partials done
+  cluster.sync();                                   // every block's partials are in its shared memory
+  if (threadIdx.x == 0) SSB_MARK();                 // past the cluster barrier
+  // ---- totals over the cluster (rank order, fp64), per-channel constants; rank 0 publishes the parameter gradients ----
+  double tot = 0.0;
+  if ((int)threadIdx.x < NQ * cpc) {
+    const int q = threadIdx.x / cpc, ch = threadIdx.x - q * cpc;
+    for (unsigned r = 0; r < CL; ++r) tot += (double)cluster.map_shared_rank(&s_part[0][0], r)[q * 64 + ch];
+  }
+  cgs::cluster_group::arrival_token token = cluster.barrier_arrive();   // done reading the peers' shared memory
+  {
+    const double inv_n = 1.0 / ((double)g.B * (double)g.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1));
+    const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
+    if ((int)threadIdx.x < NQ * cpc) {
+      const int q = threadIdx.x / cpc, ch = threadIdx.x - q * cpc;
+      const int c = chunk * cpc + ch;
+      if (q == 0) {
+        s_co[0][ch] = bn.gamma[c] * bn.mean_invstd[C + c];
+        s_co[1][ch] = (float)(tot * inv_n);
+        if (RES == 2) s_co[3][ch] = bnr.gamma[c] * bnr.mean_invstd[C + c];
+        if (rank == 0) {
+          bn.dbeta[c] = (float)(tot * gsc);
+          bn.bwd_sums[c] = tot;
+          if (RES == 2) {
+            bnr.dbeta[c] = (float)(tot * gsc);
+            bnr.bwd_sums[c] = tot;
+          }
+        }
+      } else if (q == 1) {
+        s_co[2][ch] = (float)(tot * inv_n);
+        if (rank == 0) {
+          bn.dgamma[c] = (float)(tot * gsc);
+          bn.bwd_sums[C + c] = tot;
+        }
+      } else {
+        s_co[4][ch] = (float)(tot * inv_n);
+        if (rank == 0) {
+          bnr.dgamma[c] = (float)(tot * gsc);
+          bnr.bwd_sums[C + c] = tot;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  float k0[V], k1[V], k2[V], rk0[V], rk2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int j = cgl * V + i;
+    k0[i] = s_co[0][j]; k1[i] = s_co[1][j]; k2[i] = s_co[2][j];
+    if (RES == 2) { rk0[i] = s_co[3][j]; rk2[i] = s_co[4][j]; }
+  }
+  // ---- apply from the registers ----
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    const int row = r0 + rl + k * rpp;
+    if (row >= r1) continue;
+    const size_t off = (size_t)row * C + (size_t)cg * V;
+    Vec<T> odx, odr, ogi;
+    if (ok[k]) {
+      float fg[V], fx[V], o[V];
+      kg[k].get(fg);
+      kx[k].get(fx);
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[i] = k0[i] * (fg[i] - k1[i] - ((fx[i] - mean[i]) * inv[i]) * k2[i]);
+      odx.set(o);
+      if (RES == 1) ogi = kg[k];
+      if (RES == 2) {
+        float fr[V];
+        kr[k].get(fr);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = rk0[i] * (fg[i] - k1[i] - ((fr[i] - meanr[i]) * invr[i]) * rk2[i]);
+        odr.set(o);
+      }
+    } else {
+      odx.zero();
+      odr.zero();
+      ogi.zero();
+    }
+    odx.store(dx + off);
+    if (RES == 1) ogi.store(gid + off);
+    if (RES == 2) odr.store(dxr + off);
+  }
+  if (threadIdx.x == 0) SSB_MARK();                 // applied and stored
+  cluster.barrier_wait(std::move(token));           // no block leaves while a peer may still read its partials
 }
 
 // ---------------------------------------------------------------------------------------
@@ -912,6 +1124,69 @@ static bool bwd_fused_plan(const ssb_geom& g, int mode, bool has_y, int* cgpc_o,
   return nx > 0 && (long long)nx * ny <= cap;
 }
 
+// ---- cluster / DSMEM backward (bn_bwd_cluster_kernel) ----
+// largest cluster size to use: 16 (non-portable, opt-in), 8, or 0 = off; env SSB_BN_CLUSTER (read per call: launches are
+// captured once, and the tests switch it)
+static int bn_cluster_max() {
+  const char* e = getenv("SSB_BN_CLUSTER");
+  const int v = e ? atoi(e) : 16;
+  return (v == 0 || v == 8 || v == 16) ? v : 16;
+}
+struct ClusterPlan {
+  int cgpc, rows_per_cta, cl, nr, nchunks;
+};
+template <typename T>
+static bool bwd_cluster_plan(const ssb_geom& g, int mode, ClusterPlan* p) {
+  constexpr int V = Vec<T>::N;
+  const int cmax = bn_cluster_max();
+  if (cmax == 0) return false;
+  const int ncg = g.C / V;
+  int cgpc = 1;
+  while (cgpc * 2 <= ncg / 8 && cgpc * 2 <= 64 / V) cgpc *= 2;      // aim at >= 8 channel chunks, <= 64 channels each
+  while (ncg % cgpc) cgpc >>= 1;
+  const int rpp = BN_THREADS / cgpc;
+  const int rows = g.B * g.pitch;
+  for (int cl = cmax; cl >= 8; cl >>= 1) {
+    const int rpc = ceil_div(rows, cl);
+    const int need = ceil_div(rpc, rpp);
+    // (12 register-resident rows of three bf16 operands -- the residual-BN mode -- do not fit 255 registers: ptxas spills)
+    if (need <= 6 || (need <= 12 && !(mode == 2 && V == 8))) {
+      p->cgpc = cgpc; p->rows_per_cta = rpc; p->cl = cl; p->nr = need <= 6 ? 6 : 12; p->nchunks = ncg / cgpc;
+      return true;
+    }
+  }
+  return false;
+}
+template <typename Kern, typename... Args>
+static cudaError_t launch_cluster(Kern kern, int nblocks, int cl, cudaStream_t st, Args... args) {
+  // (one-time opt-in per instantiation for clusters of 16)
+  static bool opted = false;
+  if (cl > 8 && !opted) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    opted = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)nblocks);
+  cfg.blockDim = dim3(BN_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_ssb_pdl == 1 ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#define SSB_BWC(Y, R, N)                                                                                                   \
+  launch_cluster(bn_bwd_cluster_kernel<T, Y, R, N>, cp.nchunks * cp.cl, cp.cl, st, (const T*)g1, (const T*)y, (const T*)x, \
+                 (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, cp.cgpc, cp.rows_per_cta)
+#define SSB_BWC_NR(Y, R) (cp.nr == 6 ? SSB_BWC(Y, R, 6) : SSB_BWC(Y, R, 12))
+
 #define SSB_BWF(Y, R)                                                                                                          \
   ssb_launch(bn_bwd_fused_kernel<T, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)y, (const T*)x,       \
              (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, cgpc, rpb, barrier, rep, rep_r, (long long)rep_stride)
@@ -1046,8 +1321,9 @@ int ssb_bn_bwd_fused_fits(ssb_geom g, int res_mode, int has_y, int dtype) {
   if (check_geom("ssb_bn_bwd_fused_fits", g, 0)) return 0;
   int cgpc, rpb;
   dim3 grid;
-  if (dtype == SSB_F32) return bwd_fused_plan<float>(g, res_mode, has_y != 0, &cgpc, &rpb, &grid) ? 1 : 0;
-  if (dtype == SSB_BF16) return bwd_fused_plan<bf16>(g, res_mode, has_y != 0, &cgpc, &rpb, &grid) ? 1 : 0;
+  ClusterPlan cp;
+  if (dtype == SSB_F32) return (bwd_cluster_plan<float>(g, res_mode, &cp) || bwd_fused_plan<float>(g, res_mode, has_y != 0, &cgpc, &rpb, &grid)) ? 1 : 0;
+  if (dtype == SSB_BF16) return (bwd_cluster_plan<bf16>(g, res_mode, &cp) || bwd_fused_plan<bf16>(g, res_mode, has_y != 0, &cgpc, &rpb, &grid)) ? 1 : 0;
   return 0;
 }
 
@@ -1066,6 +1342,21 @@ int ssb_bn_bwd_fused(const void* g1, const void* y, const void* x, const ssb_bn*
   SSB_DISPATCH_DTYPE(dtype, T, {
     int cgpc, rpb;
     dim3 grid;
+    ClusterPlan cp;
+    if (bwd_cluster_plan<T>(g, mode, &cp)) {     // clusters + DSMEM: one read of the operands, no grid barrier
+      cudaStream_t st = to_stream(stream);
+      const ssb_bn br = bn_res ? *bn_res : kNoBn;
+      cudaError_t ce;
+      if (mode == 0) ce = y ? SSB_BWC_NR(true, 0) : SSB_BWC_NR(false, 0);
+      else if (mode == 1) ce = y ? SSB_BWC_NR(true, 1) : SSB_BWC_NR(false, 1);
+      else ce = y ? SSB_BWC_NR(true, 2) : SSB_BWC_NR(false, 2);
+      if (ce != cudaSuccess) {
+        ssb_set_error("ssb_bn_bwd_fused: cluster launch failed: %s", cudaGetErrorString(ce));
+        return SSB_ERR_CUDA;
+      }
+      SSB_LAUNCH_CHECK("ssb_bn_bwd_fused");
+      return SSB_OK;
+    }
     if (!bwd_fused_plan<T>(g, mode, y != nullptr, &cgpc, &rpb, &grid)) {
       ssb_set_error("ssb_bn_bwd_fused: %u x %u blocks exceed the co-resident capacity; use ssb_bn_bwd_reduce + ssb_bn_bwd_apply",
                     grid.x, grid.y);

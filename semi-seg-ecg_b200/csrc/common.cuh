@@ -84,6 +84,17 @@ __device__ __forceinline__ void pdl_wait_line(unsigned int line) {
   }
 }
 #define pdl_wait() pdl_wait_line(__LINE__)
+// phase marks inside a kernel (block (0,0,0) only; any one thread may call it): pad = 1, t_start = time of the mark
+__device__ __forceinline__ void ssb_mark_line(unsigned int line) {
+  if ((blockIdx.x | blockIdx.y | blockIdx.z) != 0) return;
+  const unsigned int i = atomicAdd(&ssb_trace_n, 1u);
+  if (i < SSB_TRACE_CAP) {
+    SsbTraceRec r;
+    r.t_entry = 0; r.t_start = ssb_gtime(); r.line = line; r.grid = 0; r.block = threadIdx.x; r.pad = 1;
+    ssb_trace_buf[i] = r;
+  }
+}
+#define SSB_MARK() ssb_mark_line(__LINE__)
 // one per translation unit: copies (and optionally resets) this unit's records
 #define SSB_TRACE_DEFINE(tu)                                                                         \
   extern "C" int ssb_trace_dump_##tu(void* host, int cap, int reset) {                              \
@@ -99,6 +110,7 @@ __device__ __forceinline__ void pdl_wait_line(unsigned int line) {
 #endif
 #ifndef SSB_TRACE_DEFINE
 #define SSB_TRACE_DEFINE(tu)
+#define SSB_MARK()
 #endif
 __device__ __forceinline__ void pdl_trigger() {}
 

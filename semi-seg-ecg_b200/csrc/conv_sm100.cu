@@ -264,6 +264,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
     asm volatile("bar.sync 1, 256;" ::: "memory");
   }
   mbar_wait(done, done_parity);
+  if (threadIdx.x == 64) SSB_MARK();   // accumulator complete (MMAs retired)
   tc_fence_after();
   const int row = q * 32 + lane;
   const int m = m0 + row;
@@ -413,6 +414,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
     tc_fence_before();
     mbar_arrive(release);
   }
+  if (threadIdx.x == 64) SSB_MARK();     // tile stored
   if (STATS) {
     asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
     for (int col = e; col < BN; col += EPI_THREADS) {
@@ -557,6 +559,7 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int st = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         mbar_wait(&s.full[st], ph);
+        if (it == 0) SSB_MARK();   // first operands landed
         tc_fence_after();
         const uint32_t a0 = smem_u32(s.a + st * A_BYTES), b0 = smem_u32(s.b + st * B_BYTES);
 #pragma unroll
@@ -569,10 +572,12 @@ conv_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&s.empty[st]);   // frees the smem stage when these MMAs retire
       }
       umma_commit(s.done);           // accumulator complete
+      SSB_MARK();                    // last MMA issued
     }
   } else {
     tn_epilogue<BN, STATS, EPI, RED>(p, out, tmem_base, s.done, 0u, nullptr, reinterpret_cast<float*>(s.tmem_slot + 4),
                                 reinterpret_cast<float*>(s.a), m0, n0, warp, lane);
+    if (threadIdx.x == 64) SSB_MARK();   // epilogue done
   }
   tc_fence_before();
   __syncthreads();
@@ -678,6 +683,7 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int tap = 0; tap < 3; ++tap, ++bi) {
             const int bs = bi % NB;
             mbar_wait(&b_full[bs], ((uint32_t)(bi / NB)) & 1u);
+            if (bi == 0) SSB_MARK();   // first operands landed
             tc_fence_after();
             const uint32_t b0 = smem_u32(sb + bs * B_BYTES);
             const uint32_t at = a0 + (uint32_t)(p.a_row_off[tap] + 1) * 128u;   // tap's row shift inside the haloed tile
@@ -691,6 +697,7 @@ conv_tn3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           umma_commit(&a_empty[sl]);
         }
         umma_commit(&t_full[buf]);
+        SSB_MARK();                    // last MMA of a tile issued
       }
     }
   } else {

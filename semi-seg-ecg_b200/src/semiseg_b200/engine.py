@@ -126,8 +126,7 @@ class StepEngine:
         self.repack_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         # gradient all-reduce in buckets: the ranges of the last stages (+ head) are exchanged on their own stream as
         # soon as those gradients exist, under the backward of the earlier stages (SSB_BUCKETS = how many, 0 = off)
-        self.comm_stream = torch.cuda.Stream(device=dev) if (self.multi_stream and self.collectives and
-                                                              int(os.environ.get("SSB_BUCKETS", "2"))) else None
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.multi_stream and int(os.environ.get("SSB_BUCKETS", "2"))) else None
         self.dgrad_stream = torch.cuda.Stream(device=dev) if self.multi_stream else None
         self.bufs_snap: Optional[torch.Tensor] = None
         if self.merged:
@@ -344,11 +343,22 @@ class StepEngine:
              self.spec.num_classes, self.mode, 0.0, self.sp_dev.data_ptr(), 1 if self.spec.align_corners else 0,
              m["conf"].data_ptr() if m else None, m["label"].data_ptr() if m else None,
              m["mask"].data_ptr() if m else None, st)
+        # ---- backward, gradient exchange and optimizer, pipelined by parameter range ----
+        # The arena is in forward order, the backward produces gradients from its END: the ranges of the last stages
+        # (+ head; ~97 % of the parameters) are complete when the backward reaches the first block of those stages.
+        # Each such range is handed to the update stream at once -- [all-reduce over the ranks,] fused AdamW(+EMA) on the
+        # range -- under the backward of the earlier stages; only the early layers' small range is exchanged and updated
+        # after the backward (a 17 us optimizer pass over the whole arena used to sit at the end of the critical path).
+        pe_base = self.teacher.params.data_ptr() if self.algorithm == "mean_teacher" else None
+
+        def adamw(lo, hi, stream_ptr):
+            call("ssb_adamw_ema", w.params.data_ptr() + 4 * lo, state.grads.data_ptr() + 4 * lo, state.exp_avg.data_ptr() + 4 * lo,
+                 state.exp_avg_sq.data_ptr() + 4 * lo, (pe_base + 4 * lo) if pe_base else None, hi - lo, self.beta1, self.beta2,
+                 self.eps, self.wd, self.sp_dev.data_ptr(), stream_ptr)
+
         split = None
+        want_norm = bool(self.cfg.get("grad_norm", False))
         if self.comm_stream is not None:
-            # buckets = the parameter ranges of the last stages (arena order = forward order): each is all-reduced
-            # on the communication stream as soon as its gradients exist; only the early layers' small range is
-            # exchanged after the backward has finished
             lay = self.plan_s.lay
             nst = len(self.spec.stage_blocks)
             firsts = {}
@@ -367,25 +377,32 @@ class StepEngine:
                 self.comm_stream.wait_stream(cur_)                       # BN / head gradients of the range (main stream)
                 if self.wgrad_stream is not None:
                     self.comm_stream.wait_stream(self.wgrad_stream)      # conv weight gradients of the range
+                if self.dgrad_stream is not None:
+                    self.comm_stream.wait_stream(self.dgrad_stream)      # (the shortcut dgrads read the range's weights)
                 with torch.cuda.stream(self.comm_stream):
-                    torch.distributed.all_reduce(state.grads[lo:hi], group=self.pg)
+                    if self.collectives:
+                        torch.distributed.all_reduce(state.grads[lo:hi], group=self.pg)
+                    if not want_norm:      # (the global norm reads every gradient first; the update then waits for it)
+                        adamw(lo, hi, self.comm_stream.cuda_stream)
             self.plan_s.block_done_hook = bucket
         self.plan_s.backward(self.plan_s.dlow, st)
         self.plan_s.block_done_hook = None
         if self.collectives:
             if split is not None:
                 torch.distributed.all_reduce(state.grads[:split], group=self.pg)
-                torch.cuda.current_stream().wait_stream(self.comm_stream)
             else:
                 torch.distributed.all_reduce(state.grads, group=self.pg)
-        if self.cfg.get("grad_norm", False):
+        if split is not None and want_norm:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        if want_norm:
             call("ssb_memset_zero", self.gnorm_ws.data_ptr(), 8, st)
             call("ssb_grad_norm", state.grads.data_ptr(), state.grads.numel(), self.gnorm_ws.data_ptr(),
                  self.gnorm.data_ptr(), st)
-        pe = self.teacher.params.data_ptr() if self.algorithm == "mean_teacher" else None
-        call("ssb_adamw_ema", w.params.data_ptr(), state.grads.data_ptr(), state.exp_avg.data_ptr(),
-             state.exp_avg_sq.data_ptr(), pe, w.params.numel(), self.beta1, self.beta2, self.eps, self.wd,
-             self.sp_dev.data_ptr(), st)
+        if split is not None and not want_norm:
+            adamw(0, split, st)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            adamw(0, w.params.numel(), st)
         if self.algorithm == "mean_teacher":
             call("ssb_ema", self.teacher.bufs.data_ptr(), w.bufs.data_ptr(), w.bufs.numel(), self.sp_dev.data_ptr(), st)
             call("ssb_ema_i64", self.teacher.nbt.data_ptr(), w.nbt.data_ptr(), w.nbt.numel(), self.sp_dev.data_ptr(), st)
@@ -460,10 +477,13 @@ class StepEngine:
         self._done.append(self._to_stats(self.stats_host[slot].clone()))
         self._pending.remove(slot)
 
-    def read_stats(self) -> List[Dict[str, float]]:
+    def read_stats(self, block: bool = True) -> List[Dict[str, float]]:
         """Stats of all steps issued since the last call, in order (synchronises on the
-        outstanding asynchronous D2H copies only)."""
+        outstanding asynchronous D2H copies only).  block=False: only the steps whose read-back has already
+        arrived (no host wait, no bubble in the GPU's queue) -- the rest come with a later call."""
         for slot in list(self._pending):
+            if not block and not self.stats_events[slot].query():
+                break
             self._retire(slot)
         if getattr(self, "syncbn_p2p", False):
             # the peer-memory statistics exchange gives up on a silent peer after ~20 s and records the exchange

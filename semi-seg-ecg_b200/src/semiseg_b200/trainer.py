@@ -120,9 +120,9 @@ def run_epoch(algorithm: str, model, teacher, labeled_loader: Iterable, unlabele
     eng = None
     pairs = zip(labeled_loader, unlabeled_loader) if unlabeled_loader is not None else ((b, None) for b in labeled_loader)
 
-    def drain(step_idx):
+    def drain(step_idx, block=True):
         nonlocal count
-        for s in eng.read_stats():
+        for s in eng.read_stats(block=block):
             total = s.get("loss_total", s.get("loss"))
             if not math.isfinite(total):
                 print(f"Loss is {total}, stopping training")
@@ -158,7 +158,9 @@ def run_epoch(algorithm: str, model, teacher, labeled_loader: Iterable, unlabele
         if teacher is not None and algorithm == "mean_teacher":
             teacher.runtime().ema_started = True
         if (it + 1) % PRINT_FREQ == 0 or it + 1 == num_steps:
-            drain(it)
+            # mid-epoch log lines use the steps whose loss sums have ALREADY arrived (the reference blocks on .item() every
+            # step; blocking here every PRINT_FREQ steps would still drain the GPU's queue once per line)
+            drain(it, block=it + 1 == num_steps)
             dt = time.time() - t0
             print(f"Epoch: [{epoch}]  [{it + 1}/{num_steps}]  lr: {lr:.6f}  " +
                   "  ".join(f"{k}: {v / max(count, 1):.4f}" for k, v in sums.items()) +

@@ -325,11 +325,17 @@ def test_conv_fwd_bn_train(cin, cout, k, stride, L, res_mode):
 
 
 @pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
-@pytest.mark.parametrize("Cn,res_mode,L", [(64, 0, 625), (128, 1, 313), (512, 2, 79), (24, 1, 50), (8, 2, 33)])
-def test_bn_bwd_fused(dtype, Cn, res_mode, L):
-    """reduce + grid barrier + apply in one launch == ssb_bn_bwd_reduce followed by ssb_bn_bwd_apply"""
+@pytest.mark.parametrize("cluster", ["16", "8", "0"])
+@pytest.mark.parametrize("Cn,res_mode,L,B", [(64, 0, 625, 16), (128, 1, 313, 16), (512, 2, 79, 16), (24, 1, 50, 16), (8, 2, 33, 16),
+                                             (64, 1, 625, 32), (128, 2, 313, 32), (256, 0, 157, 32), (512, 1, 79, 32), (1024, 2, 157, 32),
+                                             (128, 0, 1250, 64)])
+def test_bn_bwd_fused(dtype, Cn, res_mode, L, B, cluster, monkeypatch):
+    """both BatchNorm-backward passes in one launch == ssb_bn_bwd_reduce followed by ssb_bn_bwd_apply.  cluster 16 / 8: the
+    thread-block-cluster kernel (register-resident rows, partial sums exchanged through distributed shared memory) where
+    the tensor fits it; 0: the grid-barrier kernel.  B = 32: the benchmark's batch (config 2 / config 5 at 16+16)."""
+    monkeypatch.setenv("SSB_BN_CLUSTER", cluster)
     torch.manual_seed(Cn + L)
-    B, pitch = 16, L + 3
+    pitch = L + 3
     g = Geom(B, pitch, L, Cn)
     gr = to_flat(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64), pitch, dtype)
     yy = to_flat(torch.relu(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64)), pitch, dtype)

@@ -56,7 +56,7 @@ def dump(lib, reset):
         n = fn(C.cast(buf, C.c_void_p), 4096, 1 if reset else 0)
         for i in range(n):
             r = buf[i]
-            out.append((r.t_start, r.t_entry, tu, r.line, r.grid, r.block))
+            out.append((r.t_start, r.t_entry, tu, r.line, r.grid, r.block, r.pad))
     return sorted(out)
 
 
@@ -94,7 +94,9 @@ def main():
     eng.step(1e-3)
     e1.record()
     torch.cuda.synchronize()
-    recs = dump(lib, True)
+    allrecs = dump(lib, True)
+    recs = [r[:6] for r in allrecs if r[6] == 0]
+    marks = [r for r in allrecs if r[6] == 1]
     t0 = recs[0][0]
     lines = [f"# in-kernel timeline of one replayed step: {a.workload}", "",
              f"{len(recs)} launches recorded; step {e0.elapsed_time(e1) * 1e3:.1f} us by CUDA events (one replay, trace build); "
@@ -105,7 +107,13 @@ def main():
              "| # | start us | waited us | to next us | kernel | grid | block |", "|---:|---:|---:|---:|---|---:|---:|"]
     for i, (ts, te, tu, line, grid, block) in enumerate(recs):
         nxt = (recs[i + 1][0] - ts) / 1e3 if i + 1 < len(recs) else 0.0
-        lines.append(f"| {i} | {(ts - t0) / 1e3:.1f} | {(ts - te) / 1e3:.1f} | {nxt:.1f} | `{kernel_at(tu, line)}` ({tu}.cu:{line}) | {grid} | {block} |")
+        name = kernel_at(tu, line)
+        # phase marks of this launch: same kernel function, after this start and before the next start of the same function
+        later = [r[0] for r in recs[i + 1:] if r[2] == tu and kernel_at(r[2], r[3]) == name]
+        lim = later[0] if later else ts + 10**9
+        mk = sorted((m[0], m[3]) for m in marks if m[2] == tu and ts <= m[0] < lim and (kernel_at(tu, m[3]) == name or name.startswith("conv_tn")))
+        ms = " ".join(f"+{(mt - ts) / 1e3:.1f}@{ml}" for mt, ml in mk)
+        lines.append(f"| {i} | {(ts - t0) / 1e3:.1f} | {(ts - te) / 1e3:.1f} | {nxt:.1f} | `{name}` ({tu}.cu:{line}) {ms} | {grid} | {block} |")
     txt = "\n".join(lines) + "\n"
     if a.out:
         open(a.out, "w").write(txt)
