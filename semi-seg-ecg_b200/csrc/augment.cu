@@ -12,6 +12,8 @@
 // The Fourier resize is evaluated directly (two dense DFT passes with exact integer phase indices into a
 // shared-memory twiddle table): sizes are arbitrary integers in [L/2, 2L] (no FFT-friendly factorisation),
 // only the L cropped output positions are needed, and at L = 2500 the whole batch is ~1 GFLOP.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 #define AUG_THREADS 256
@@ -150,6 +152,182 @@ aug_resize_crop_kernel(const float2* __restrict__ spec, const int64_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// The same two transforms as FFTs (round 2): one block per (strip, lead), everything in shared memory.
+// Both are chirp-z transforms -- pass 1 wants the first kmax+1 <= L/2+1 bins of a length-L DFT (L = 2500 = 2^2 5^4 is not
+// a power of two), pass 2 evaluates a trigonometric polynomial of <= L/2+1 terms at L consecutive points of a grid of
+// ARBITRARY length `size` (int(L * ratio), possibly prime) -- so both go through Bluestein's identity
+//     n k = (n^2 + k^2 - (k - n)^2) / 2 :   X[k] = w[k] * sum_n (x[n] w[n]) * conj(w)[k - n],   w[n] = exp(-+ i pi n^2 / den)
+// i.e. a linear convolution of length <= L + L/2 + 1 with a chirp, done as a cyclic convolution of P = 4096 (L = 2500)
+// or 8192 (L = 5000) points: forward radix-2 DIF (natural in, bit-reversed out) of both sequences, pointwise product,
+// inverse DIT (bit-reversed in, natural out) -- no bit-reversal pass.  Chirp phases are reduced exactly in integers
+// (n^2 mod 2 den) before sincospi.  ~0.5 MFLOP per strip instead of ~25 MFLOP for the dense evaluation above, which stays
+// as the fallback for L > 5460 (P would exceed 8192 points = 160 KB of shared memory) and as the A/B reference
+// (SSB_AUG_FFT=0).
+// ---------------------------------------------------------------------------------------------
+#define AFFT_THREADS 512
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// exp(sign * i * pi * n^2 / den), n < 65536
+__device__ __forceinline__ float2 chirp(unsigned int n, unsigned int den, float sign) {
+  const unsigned int r = (n * n) % (2u * den);
+  float s, c;
+  sincospif((float)r / (float)den, &s, &c);
+  return make_float2(c, sign * s);
+}
+__device__ __forceinline__ void fft_twiddles(float2* T, int P) {      // T[t] = exp(-2 pi i t / P), t < P/2
+  for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+    float s, c;
+    sincospif(2.0f * (float)t / (float)P, &s, &c);
+    T[t] = make_float2(c, -s);
+  }
+}
+__device__ __forceinline__ void fft_dif_fwd(float2* a, const float2* T, int P) {
+  for (int half = P >> 1, tstep = 1; half >= 1; half >>= 1, tstep <<= 1) {
+    for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+      const int j = t & (half - 1);
+      const int i = ((t - j) << 1) + j;
+      const float2 u = a[i], v = a[i + half];
+      a[i] = make_float2(u.x + v.x, u.y + v.y);
+      a[i + half] = cmul(make_float2(u.x - v.x, u.y - v.y), T[j * tstep]);
+    }
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ void fft_dit_inv(float2* a, const float2* T, int P) {      // unscaled
+  for (int half = 1, tstep = P >> 1; half < P; half <<= 1, tstep >>= 1) {
+    for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
+      const int j = t & (half - 1);
+      const int i = ((t - j) << 1) + j;
+      const float2 w = T[j * tstep];
+      const float2 u = a[i], v = cmul(a[i + half], make_float2(w.x, -w.y));
+      a[i] = make_float2(u.x + v.x, u.y + v.y);
+      a[i + half] = make_float2(u.x - v.x, u.y - v.y);
+    }
+    __syncthreads();
+  }
+}
+// a <- cyclic convolution of a and h (both length P, in shared memory); h is destroyed
+__device__ __forceinline__ void fft_convolve(float2* a, float2* h, const float2* T, int P) {
+  __syncthreads();
+  fft_dif_fwd(a, T, P);
+  fft_dif_fwd(h, T, P);
+  for (int i = threadIdx.x; i < P; i += blockDim.x) a[i] = cmul(a[i], h[i]);
+  __syncthreads();
+  fft_dit_inv(a, T, P);
+}
+
+__global__ void __launch_bounds__(AFFT_THREADS)
+aug_spectrum_fft_kernel(const float* __restrict__ x, float2* __restrict__ spec, const int32_t* __restrict__ size, int C, int L,
+                        int K1, int P) {
+  pdl_wait();
+  extern __shared__ float sm[];
+  float2* a = reinterpret_cast<float2*>(sm);
+  float2* h = a + P;
+  float2* T = h + P;
+  const int bc = blockIdx.x;
+  const int b = bc / C;
+  const int kmax = min(size[b], L) / 2;
+  const int M = kmax + 1;
+  fft_twiddles(T, P);
+  for (int n = threadIdx.x; n < P; n += AFFT_THREADS) {
+    float2 av = make_float2(0.f, 0.f), hv = make_float2(0.f, 0.f);
+    if (n < L) {
+      const float2 w = chirp((unsigned)n, (unsigned)L, -1.f);
+      const float xv = x[(size_t)bc * L + n];
+      av = make_float2(xv * w.x, xv * w.y);
+    }
+    if (n < M) hv = chirp((unsigned)n, (unsigned)L, 1.f);
+    else if (n > P - L) hv = chirp((unsigned)(P - n), (unsigned)L, 1.f);       // lags -(L-1) .. -1
+    a[n] = av;
+    h[n] = hv;
+  }
+  fft_convolve(a, h, T, P);
+  const float invP = 1.0f / (float)P;
+  for (int k = threadIdx.x; k <= kmax; k += AFFT_THREADS) {
+    const float2 v = cmul(a[k], chirp((unsigned)k, (unsigned)L, -1.f));
+    spec[(size_t)bc * K1 + k] = make_float2(v.x * invP, v.y * invP);
+  }
+}
+
+__global__ void __launch_bounds__(AFFT_THREADS)
+aug_resize_crop_fft_kernel(const float2* __restrict__ spec, const int64_t* __restrict__ lab_in, float* __restrict__ y,
+                           int64_t* __restrict__ lab_out, const int32_t* __restrict__ size_arr,
+                           const int32_t* __restrict__ start_arr, int C, int L, int K1, int P) {
+  pdl_wait();
+  extern __shared__ float sm[];
+  float2* a = reinterpret_cast<float2*>(sm);
+  float2* h = a + P;
+  float2* T = h + P;
+  const int bc = blockIdx.x;
+  const int b = bc / C, c = bc - b * C;
+  const int size = size_arr[b], start = start_arr[b];
+  const int N = min(size, L);
+  const int kmax = N / 2;
+  const int pad = L - size;
+  const int left = pad > 0 ? pad / 2 : 0;
+  const int p0 = start - left;                            // position in the resized strip of output sample 0
+  fft_twiddles(T, P);
+  for (int n = threadIdx.x; n < P; n += AFFT_THREADS) {
+    float2 av = make_float2(0.f, 0.f), hv = make_float2(0.f, 0.f);
+    if (n <= kmax) {
+      float2 v = spec[(size_t)bc * K1 + n];
+      // irfft weights: 1 for DC, 2 for interior bins; the shared Nyquist bin of an even N keeps
+      // scipy.signal.resample's fix-up (x2 when shrinking, x0.5 when growing, untouched when equal)
+      float w = (n == 0) ? 1.f : 2.f;
+      if ((N & 1) == 0 && n == kmax) w = (size < L) ? 2.f : 1.f;
+      long long r = ((long long)n * (long long)p0) % (long long)size;      // exp(2 pi i n p0 / size), exact phase
+      if (r < 0) r += size;
+      float sn, cs;
+      sincospif(2.0f * (float)r / (float)size, &sn, &cs);
+      v = cmul(make_float2(v.x * w, v.y * w), make_float2(cs, sn));
+      av = cmul(v, chirp((unsigned)n, (unsigned)size, 1.f));
+    }
+    if (n < L) hv = chirp((unsigned)n, (unsigned)size, -1.f);
+    else if (n >= P - kmax) hv = chirp((unsigned)(P - n), (unsigned)size, -1.f);      // lags -kmax .. -1
+    a[n] = av;
+    h[n] = hv;
+  }
+  fft_convolve(a, h, T, P);
+  const float scale = 1.0f / ((float)P * (float)L);
+  for (int j = threadIdx.x; j < L; j += AFFT_THREADS) {
+    const int p = p0 + j;
+    const bool inside = p >= 0 && p < size;
+    float out = 0.f;
+    if (inside) {
+      const float2 w = chirp((unsigned)j, (unsigned)size, 1.f);
+      out = (a[j].x * w.x - a[j].y * w.y) * scale;
+    }
+    y[(size_t)bc * L + j] = out;
+    if (lab_in && c == 0) {
+      int64_t lab = 0;
+      if (inside) {
+        // np.linspace(0, L-1, size)[p] in float64, then interp1d(kind='nearest'): half-way points round DOWN
+        int src;
+        if (size == 1) src = 0;
+        else if (p == size - 1) src = L - 1;
+        else {
+          const double step = (double)(L - 1) / (double)(size - 1);
+          const double pos = (double)p * step;
+          src = (int)ceil(pos - 0.5);
+          src = src < 0 ? 0 : (src > L - 1 ? L - 1 : src);
+        }
+        lab = lab_in[(size_t)b * L + src];
+      }
+      lab_out[(size_t)b * L + j] = lab;
+    }
+  }
+}
+
+// FFT length of the chirp convolutions (0: use the dense kernels)
+static int aug_fft_points(int L) {
+  const char* e = getenv("SSB_AUG_FFT");
+  if (e && atoi(e) == 0) return 0;
+  int P = 64;
+  while (P < L + L / 2 + 2) P <<= 1;
+  return P <= 8192 ? P : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // strong augmentation + standardise, one block per strip
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float aug_uniform(uint32_t seed, uint32_t stream, uint32_t idx) {
@@ -272,6 +450,8 @@ int ssb_aug_prepare() {
   if (e == cudaSuccess) e = cudaFuncSetAttribute(aug_resize_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(aug_strong_standardize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(aug_spectrum_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(aug_resize_crop_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) {
     ssb_set_error("ssb_aug_prepare: %s", cudaGetErrorString(e));
     return SSB_ERR_CUDA;
@@ -285,6 +465,12 @@ int ssb_aug_spectrum(const float* x, float* spec, const int32_t* size, int B, in
   SSB_REQUIRE(x && spec && size, "ssb_aug_spectrum: null pointer");
   SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_spectrum: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
   const int K1 = L / 2 + 1;
+  if (const int P = aug_fft_points(L)) {
+    ssb_launch(aug_spectrum_fft_kernel, dim3(B * C), dim3(AFFT_THREADS), (size_t)(2 * P + P / 2) * sizeof(float2), to_stream(stream), x,
+               reinterpret_cast<float2*>(spec), size, C, L, K1, P);
+    SSB_LAUNCH_CHECK("ssb_aug_spectrum");
+    return SSB_OK;
+  }
   const size_t smem = ((size_t)((L + 3) & ~3) + 2 * 4 * AUG_FPB) * sizeof(float);
   ssb_launch(aug_spectrum_kernel, dim3(ceil_div(K1, AUG_FPB), B * C), dim3(AUG_THREADS), smem, to_stream(stream), x,
              reinterpret_cast<float2*>(spec), size, C, L, K1);
@@ -299,6 +485,12 @@ int ssb_aug_resize_crop(const float* spec, const int64_t* lab_in, float* y, int6
   SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_resize_crop: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
   SSB_REQUIRE(max_size >= 1 && max_size <= 2 * L, "ssb_aug_resize_crop: max_size %d out of [1, 2L]", max_size);
   const int K1 = L / 2 + 1;
+  if (const int P = aug_fft_points(L)) {
+    ssb_launch(aug_resize_crop_fft_kernel, dim3(B * C), dim3(AFFT_THREADS), (size_t)(2 * P + P / 2) * sizeof(float2), to_stream(stream),
+               reinterpret_cast<const float2*>(spec), lab_in, y, lab_out, size, start, C, L, K1, P);
+    SSB_LAUNCH_CHECK("ssb_aug_resize_crop");
+    return SSB_OK;
+  }
   const size_t smem = (2 * (size_t)(K1 + 1) + 4 * AUG_FPB) * sizeof(float);
   ssb_launch(aug_resize_crop_kernel, dim3(ceil_div(L, AUG_FPB), B * C), dim3(AUG_THREADS), smem, to_stream(stream),
              reinterpret_cast<const float2*>(spec), lab_in, y, lab_out, size, start, C, L, K1);

@@ -799,12 +799,16 @@ __global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_cluster_kernel(const T* 
     }
   }
   __syncthreads();
+  float pre_gi = 0.f;       // gamma * invstd of the channel this thread finalises (loaded before the barrier)
   if ((int)threadIdx.x < NQ * cpc) {
     const int q = threadIdx.x / cpc, ch = threadIdx.x - q * cpc;
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < BN_THREADS / 32; ++w) t += s_warp[w][q][ch];
     s_part[q][ch] = t;
+    const int c = chunk * cpc + ch;
+    if (q == 0) pre_gi = bn.gamma[c] * bn.mean_invstd[C + c];
+    if (RES == 2 && q == 2) pre_gi = bnr.gamma[c] * bnr.mean_invstd[C + c];
   }
   if (threadIdx.x == 0) SSB_MARK();                 // operands read, block partials done
   cluster.sync();                                   // every block's partials are in its shared memory
@@ -813,7 +817,11 @@ __global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_cluster_kernel(const T* 
   double tot = 0.0;
   if ((int)threadIdx.x < NQ * cpc) {
     const int q = threadIdx.x / cpc, ch = threadIdx.x - q * cpc;
-    for (unsigned r = 0; r < CL; ++r) tot += (double)cluster.map_shared_rank(&s_part[0][0], r)[q * 64 + ch];
+    float pv[16];
+#pragma unroll
+    for (unsigned r = 0; r < 16; ++r) pv[r] = r < CL ? cluster.map_shared_rank(&s_part[0][0], r)[q * 64 + ch] : 0.f;   // loads in flight together
+#pragma unroll
+    for (unsigned r = 0; r < 16; ++r) tot += (double)pv[r];
   }
   cgs::cluster_group::arrival_token token = cluster.barrier_arrive();   // done reading the peers' shared memory
   {
@@ -823,9 +831,8 @@ __global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_cluster_kernel(const T* 
       const int q = threadIdx.x / cpc, ch = threadIdx.x - q * cpc;
       const int c = chunk * cpc + ch;
       if (q == 0) {
-        s_co[0][ch] = bn.gamma[c] * bn.mean_invstd[C + c];
+        s_co[0][ch] = pre_gi;
         s_co[1][ch] = (float)(tot * inv_n);
-        if (RES == 2) s_co[3][ch] = bnr.gamma[c] * bnr.mean_invstd[C + c];
         if (rank == 0) {
           bn.dbeta[c] = (float)(tot * gsc);
           bn.bwd_sums[c] = tot;
@@ -841,6 +848,7 @@ __global__ void __launch_bounds__(BN_THREADS, 1) bn_bwd_cluster_kernel(const T* 
           bn.bwd_sums[C + c] = tot;
         }
       } else {
+        s_co[3][ch] = pre_gi;
         s_co[4][ch] = (float)(tot * inv_n);
         if (rank == 0) {
           bnr.dgamma[c] = (float)(tot * gsc);
@@ -1159,12 +1167,11 @@ static bool bwd_cluster_plan(const ssb_geom& g, int mode, ClusterPlan* p) {
 }
 template <typename Kern, typename... Args>
 static cudaError_t launch_cluster(Kern kern, int nblocks, int cl, cudaStream_t st, Args... args) {
-  // (one-time opt-in per instantiation for clusters of 16)
-  static bool opted = false;
-  if (cl > 8 && !opted) {
+  // clusters of 16 are a per-kernel opt-in.  (All instantiations share one function-pointer TYPE, so a flag that is
+  // static in this template would be shared by them: set the attribute on every launch -- launches are captured once.)
+  if (cl > 8) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
-    opted = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)nblocks);
