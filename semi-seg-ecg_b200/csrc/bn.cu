@@ -481,12 +481,14 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 #define BWF_KEEP 0
 #endif
 #ifndef BWF_MINB
-#define BWF_MINB 1     // forcing 64 registers (4 blocks per SM, 324-block grids) was measured SLOWER: 0.710 vs 0.700 ms
+#define BWF_MINB 2     // <= 128 registers: two blocks per SM with the batched loads (forcing 64 registers -- 4 blocks per SM,
+                       // 324-block grids -- was measured SLOWER in round 1: 0.710 vs 0.700 ms)
 #endif
+#define BWF_UR 4       // rows per trip of the row loops (all loads of a trip are in flight together)
 #define BWF_REP 8      // replicated accumulators: block b adds into replica b % 8 (8x less same-address contention)
 
 template <typename T, bool HAS_Y, int RES>
-__global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fused_kernel(const T* __restrict__ g1, const T* __restrict__ y,
+__global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(const T* __restrict__ g1, const T* __restrict__ y,
                                                                   const T* __restrict__ x, const T* __restrict__ xr,
                                                                   T* __restrict__ dx, T* __restrict__ dxr, T* __restrict__ gid,
                                                                   ssb_bn bn, ssb_bn bnr, ssb_geom g, int cgpc, int rpb,
@@ -495,6 +497,7 @@ __global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fu
   pdl_trigger();
   pdl_wait();
   constexpr int V = Vec<T>::N;
+  constexpr int UR = RES == 2 ? 2 : BWF_UR;     // (three operand tensors x 4 rows do not fit 128 registers: ptxas spills)
   const int C = g.C;
   const int ncg = C / V;
   const int rpp = BN_THREADS / cgpc;
@@ -509,7 +512,6 @@ __global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fu
   __shared__ float sC[RES == 2 ? BN_THREADS * V : 1];
   __shared__ float sCo[5][64];
   float mean[V], inv[V], meanr[V], invr[V];
-  Vec<T> kg[BWF_KEEP + 1], kx[BWF_KEEP + 1], kr[BWF_KEEP + 1];      // packed copies of the first rows (masked gradient, x, x_res)
   // ---- pass 1: reduce ----
   {
     float a[V], bq[V], cq[V];
@@ -526,31 +528,36 @@ __global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fu
           invr[i] = bnr.mean_invstd[C + c];
         }
       }
-      int k = 0;
-      for (int row = r0 + rl; row < r1; row += rpp, ++k) {
-        const bool valid = row_valid(row, g.pitch, g.len);
-        if (!valid && k >= BWF_KEEP) continue;     // halo / pad rows carry zero gradient
-        const size_t off = (size_t)row * C + (size_t)cg * V;
-        Vec<T> vg, vx, vr;
-        float fg[V], fx[V], fr[V];
-        if (valid) {
-          vg.load(g1 + off);
-          vx.load(x + off);
-          vg.get(fg);
-          vx.get(fx);
+      // UR rows per trip, every load of the trip issued before the first use: the trace marks showed this pass at
+      // ~5 us for 3 rows per thread -- one DRAM/L2 round trip per row, back to back (profiles/r2b_trace_config2.md)
+      for (int base = r0 + rl; base < r1; base += UR * rpp) {
+        Vec<T> vg[UR], vx[UR], vy[HAS_Y ? UR : 1], vr[RES == 2 ? UR : 1];
+        bool ok[UR];
+#pragma unroll
+        for (int u = 0; u < UR; ++u) {
+          const int row = base + u * rpp;
+          ok[u] = row < r1 && row_valid(row, g.pitch, g.len);       // halo / pad rows carry zero gradient
+          if (ok[u]) {
+            const size_t off = (size_t)row * C + (size_t)cg * V;
+            vg[u].load(g1 + off);
+            vx[u].load(x + off);
+            if (HAS_Y) vy[u].load(y + off);
+            if (RES == 2) vr[u].load(xr + off);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UR; ++u) {
+          if (!ok[u]) continue;
+          float fg[V], fx[V], fr[V];
+          vg[u].get(fg);
+          vx[u].get(fx);
           if (HAS_Y) {
-            Vec<T> vy;
-            vy.load(y + off);
             float fy[V];
-            vy.get(fy);
+            vy[u].get(fy);
 #pragma unroll
             for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
-            vg.set(fg);          // exact: masking keeps the stored values or zero
           }
-          if (RES == 2) {
-            vr.load(xr + off);
-            vr.get(fr);
-          }
+          if (RES == 2) vr[u].get(fr);
 #pragma unroll
           for (int i = 0; i < V; ++i) {
             a[i] += fg[i];
@@ -558,9 +565,6 @@ __global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fu
             if (RES == 2) cq[i] += fg[i] * ((fr[i] - meanr[i]) * invr[i]);
           }
         }
-#pragma unroll
-        for (int j = 0; j < BWF_KEEP; ++j)
-          if (j == k) { kg[j] = vg; kx[j] = vx; if (RES == 2) kr[j] = vr; }
       }
     }
 #pragma unroll
@@ -636,54 +640,57 @@ __global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fu
     k0[i] = sCo[0][j]; k1[i] = sCo[1][j]; k2[i] = sCo[2][j];
     if (RES == 2) { rk0[i] = sCo[3][j]; rk2[i] = sCo[4][j]; }
   }
-  int k = 0;
-  for (int row = r0 + rl; row < r1; row += rpp, ++k) {
-    const size_t off = (size_t)row * C + (size_t)cg * V;
-    Vec<T> odx, odr, ogi;
-    if (row_valid(row, g.pitch, g.len)) {
-      Vec<T> vg, vx, vr;
-      bool have = false;
+  for (int base = r0 + rl; base < r1; base += UR * rpp) {
+    Vec<T> vg[UR], vx[UR], vy[HAS_Y ? UR : 1], vr[RES == 2 ? UR : 1];
+    bool ok[UR];
 #pragma unroll
-      for (int j = 0; j < BWF_KEEP; ++j)
-        if (j == k) { vg = kg[j]; vx = kx[j]; if (RES == 2) vr = kr[j]; have = true; }
-      float fg[V], fx[V];
-      if (!have) {                       // rows beyond the register-resident ones: second read (L2 / L1)
-        vg.load(g1 + off);
-        vx.load(x + off);
-        vg.get(fg);
+    for (int u = 0; u < UR; ++u) {          // second read (L2 / L1): again all loads of the trip first
+      const int row = base + u * rpp;
+      ok[u] = row < r1 && row_valid(row, g.pitch, g.len);
+      if (ok[u]) {
+        const size_t off = (size_t)row * C + (size_t)cg * V;
+        vg[u].load(g1 + off);
+        vx[u].load(x + off);
+        if (HAS_Y) vy[u].load(y + off);
+        if (RES == 2) vr[u].load(xr + off);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const int row = base + u * rpp;
+      if (row >= r1) continue;
+      const size_t off = (size_t)row * C + (size_t)cg * V;
+      Vec<T> odx, odr, ogi;
+      if (ok[u]) {
+        float fg[V], fx[V], o[V];
+        vg[u].get(fg);
+        vx[u].get(fx);
         if (HAS_Y) {
-          Vec<T> vy;
-          vy.load(y + off);
           float fy[V];
-          vy.get(fy);
+          vy[u].get(fy);
 #pragma unroll
           for (int i = 0; i < V; ++i) fg[i] = fy[i] > 0.f ? fg[i] : 0.f;
         }
-        if (RES == 2) vr.load(xr + off);
+#pragma unroll
+        for (int i = 0; i < V; ++i) o[i] = k0[i] * (fg[i] - k1[i] - ((fx[i] - mean[i]) * inv[i]) * k2[i]);
+        odx.set(o);
+        if (RES == 1) ogi.set(fg);
+        if (RES == 2) {
+          float fr[V];
+          vr[u].get(fr);
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[i] = rk0[i] * (fg[i] - k1[i] - ((fr[i] - meanr[i]) * invr[i]) * rk2[i]);
+          odr.set(o);
+        }
       } else {
-        vg.get(fg);
+        odx.zero();
+        odr.zero();
+        ogi.zero();
       }
-      vx.get(fx);
-      float o[V];
-#pragma unroll
-      for (int i = 0; i < V; ++i) o[i] = k0[i] * (fg[i] - k1[i] - ((fx[i] - mean[i]) * inv[i]) * k2[i]);
-      odx.set(o);
-      if (RES == 1) ogi.set(fg);
-      if (RES == 2) {
-        float fr[V];
-        vr.get(fr);
-#pragma unroll
-        for (int i = 0; i < V; ++i) o[i] = rk0[i] * (fg[i] - k1[i] - ((fr[i] - meanr[i]) * invr[i]) * rk2[i]);
-        odr.set(o);
-      }
-    } else {
-      odx.zero();
-      odr.zero();
-      ogi.zero();
+      odx.store(dx + off);
+      if (RES == 1) ogi.store(gid + off);
+      if (RES == 2) odr.store(dxr + off);
     }
-    odx.store(dx + off);
-    if (RES == 1) ogi.store(gid + off);
-    if (RES == 2) odr.store(dxr + off);
   }
 }
 
@@ -697,6 +704,10 @@ __global__ void __launch_bounds__(BN_THREADS, RES == 2 ? 1 : BWF_MINB) bn_bwd_fu
 // partials through DSMEM after one hardware cluster barrier (no global atomics, no fence, no spin), and the apply pass
 // runs from the registers.  Summation order is fixed (warp tree -> 8 warps -> CL ranks in rank order): deterministic.
 // Fits when rows <= CL * NR * (256 / vector groups per chunk); larger tensors keep the kernels above.
+// MEASURED (round 2, config-2 step, B200): 0.689 ms per step with the grid-barrier kernel, 0.739 with clusters of 8,
+// 0.772 with clusters of 16 -- in-kernel marks: 2-4 us until a block has its operands and partials, ~0.9 us cluster
+// barrier, ~3 us DSMEM gather + finalise + stores.  The chain of dependent memory round trips is as long as before and
+// cluster launches schedule later.  Kept behind SSB_BN_CLUSTER=8|16 (tested), OFF by default.
 // RES: 0 none; 1 identity residual -> g_ident = g; 2 residual BN -> dx_res
 // ---------------------------------------------------------------------------------------
 template <typename T, bool HAS_Y, int RES, int NR>
@@ -1120,7 +1131,8 @@ static bool bwd_fused_plan(const ssb_geom& g, int mode, bool has_y, int* cgpc_o,
   // co-resident capacity with one block per SM left as slack; the rows are spread over at most that many blocks
   // (measured at config 2: 216 blocks -- this cap at 3 blocks per SM -- 0.700 ms per step; 148 blocks 0.716; 324 blocks
   // at a forced 64 registers 0.710)
-  const long long cap = occ >= 2 ? 148LL * (occ - 1) : 0;
+  static const int slack = getenv("SSB_BWF_SLACK") ? atoi(getenv("SSB_BWF_SLACK")) : 1;
+  const long long cap = occ - slack >= 1 ? 148LL * (occ - slack) : 0;
   int nx = cap / ny > 0 ? (int)(cap / ny) : 0;
   const int want = ceil_div(rows, rpp * BWF_ROWS);
   if (nx > want) nx = want;
@@ -1137,8 +1149,8 @@ static bool bwd_fused_plan(const ssb_geom& g, int mode, bool has_y, int* cgpc_o,
 // captured once, and the tests switch it)
 static int bn_cluster_max() {
   const char* e = getenv("SSB_BN_CLUSTER");
-  const int v = e ? atoi(e) : 16;
-  return (v == 0 || v == 8 || v == 16) ? v : 16;
+  const int v = e ? atoi(e) : 0;      // measured SLOWER than the grid-barrier kernel: off by default
+  return (v == 0 || v == 8 || v == 16) ? v : 0;
 }
 struct ClusterPlan {
   int cgpc, rows_per_cta, cl, nr, nchunks;

@@ -462,14 +462,21 @@ def test_mean_teacher_full_width_2x2500():
         if dtype != _lib.F32:
             continue
         sd, tsd, tref = model.state_dict(), teacher.state_dict(), t64.teacher_state()
-        worst = 0.0
+        worst, lr = 0.0, cfg["lr"]
         for n in t64.pnames + [b_ for b_ in t64.bnames if "tracked" not in b_]:
-            for mine, ref, ref32 in ((sd[n], t64.sd[n], t32.sd[n]), (tsd[n], tref[n], t32.teacher_state()[n])):
+            for mine, ref, ref32, ema in ((sd[n], t64.sd[n], t32.sd[n], 1.0), (tsd[n], tref[n], t32.teacher_state()[n], 0.03)):
                 e, e32 = rel_err(mine, ref), rel_err(ref32, ref)
                 worst = max(worst, e)
-                # three AdamW steps: an element whose first gradients are rounding-level noise moves by +-lr either way
-                # (the fp32 ORACLE itself is ~2e-4 off the fp64 one on such tensors: 8x its deviation)
-                assert e < max(1e-4, 8 * e32), (n, e, e32)
+                if e < max(1e-4, 8 * e32):
+                    continue
+                # AdamW's early steps are sign-like (lr * m / (sqrt(v) + eps)): an element whose gradients are rounding-level
+                # noise steps by +-lr per step on either side (the fp32 ORACLE differs from the fp64 one in the same way).
+                # Parameters only: bound the drift by the steps taken (x the EMA weight for the teacher) and the number
+                # of such elements
+                assert n in t64.pnames, (n, e, e32)
+                d = (mine.cpu().double() - ref).abs()
+                assert float(d.max()) <= 2.0 * lr * 3 * ema * 1.01 and int((d > 0.1 * lr * ema).sum()) <= 2 + 2e-3 * d.numel(), \
+                    (n, e, e32, float(d.max()), int((d > 0.1 * lr * ema).sum()))
         for n in t64.bnames:
             if "tracked" in n:
                 assert int(sd[n]) == 3 and abs(float(tsd[n]) - float(tref[n])) < 1e-6, n
