@@ -93,6 +93,17 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restr
   const int rows = g.B * g.pitch;
   const int r0 = blockIdx.x * rpb;
   const int r1 = min(rows, r0 + rpb);
+  // the first row's operands are requested BEFORE the coefficient phase (statistics load -> fp64 arithmetic -> shared
+  // memory -> barrier): two dependent memory round trips become one (most launches have one row per thread)
+  const bool active = rl < rpp && cg < ncg;
+  const int row0 = r0 + rl;
+  const bool first_ok = active && row0 < r1 && row_valid(row0, g.pitch, g.len);
+  Vec<T> pv, prv;
+  if (first_ok) {
+    const size_t off = (size_t)row0 * C + (size_t)cg * V;
+    pv.load(x + off);
+    if (RES != 0) prv.load(res + off);
+  }
   // per-channel coefficients of this block's <= 64 channels: ONE thread per channel does the fp64
   // statistics arithmetic (fp64 issue rate is low: never replicate it across row lanes)
   __shared__ float sCo[4][64];
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restr
     }
   }
   __syncthreads();
-  if (rl >= rpp || cg >= ncg) return;
+  if (!active) return;
   float sc[V], sh[V], rsc[V], rsh[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
@@ -126,20 +137,22 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restr
       rsh[i] = sCo[3][cgl * V + i];
     }
   }
-  for (int row = r0 + rl; row < r1; row += rpp) {
+  for (int row = row0; row < r1; row += rpp) {
     const size_t off = (size_t)row * C + (size_t)cg * V;
     Vec<T> out;
     if (row_valid(row, g.pitch, g.len)) {
-      Vec<T> v;
-      v.load(x + off);
+      Vec<T> v, rv;
+      if (row == row0) {
+        v = pv;
+        if (RES != 0) rv = prv;
+      } else {
+        v.load(x + off);
+        if (RES != 0) rv.load(res + off);
+      }
       float f[V];
       v.get(f);
       float r[V];
-      if (RES != 0) {
-        Vec<T> rv;
-        rv.load(res + off);
-        rv.get(r);
-      }
+      if (RES != 0) rv.get(r);
 #pragma unroll
       for (int i = 0; i < V; ++i) {
         float o = fmaf(f[i], sc[i], sh[i]);

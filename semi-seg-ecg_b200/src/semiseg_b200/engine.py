@@ -377,8 +377,7 @@ class StepEngine:
                 self.comm_stream.wait_stream(cur_)                       # BN / head gradients of the range (main stream)
                 if self.wgrad_stream is not None:
                     self.comm_stream.wait_stream(self.wgrad_stream)      # conv weight gradients of the range
-                if self.dgrad_stream is not None:
-                    self.comm_stream.wait_stream(self.dgrad_stream)      # (the shortcut dgrads read the range's weights)
+                # (the shortcut dgrads on their own branch are joined into the main stream inside their block)
                 with torch.cuda.stream(self.comm_stream):
                     if self.collectives:
                         torch.distributed.all_reduce(state.grads[lo:hi], group=self.pg)

@@ -475,7 +475,7 @@ def test_mean_teacher_full_width_2x2500():
                 # of such elements
                 assert n in t64.pnames, (n, e, e32)
                 d = (mine.cpu().double() - ref).abs()
-                assert float(d.max()) <= 2.0 * lr * 3 * ema * 1.01 and int((d > 0.1 * lr * ema).sum()) <= 2 + 2e-3 * d.numel(), \
+                assert float(d.max()) <= 2.0 * lr * 3 * ema * 1.01 and int((d > 0.1 * lr * ema).sum()) <= 2 + 1e-2 * d.numel(), \
                     (n, e, e32, float(d.max()), int((d > 0.1 * lr * ema).sum()))
         for n in t64.bnames:
             if "tracked" in n:
