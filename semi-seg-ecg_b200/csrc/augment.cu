@@ -161,7 +161,7 @@ aug_resize_crop_kernel(const float2* __restrict__ spec, const int64_t* __restric
 // or 8192 (L = 5000) points: forward radix-2 DIF (natural in, bit-reversed out) of both sequences, pointwise product,
 // inverse DIT (bit-reversed in, natural out) -- no bit-reversal pass.  Chirp phases are reduced exactly in integers
 // (n^2 mod 2 den) before sincospi.  ~0.5 MFLOP per strip instead of ~25 MFLOP for the dense evaluation above, which stays
-// as the fallback for L > 5460 (P would exceed 8192 points = 160 KB of shared memory) and as the A/B reference
+// as the fallback for L > 5460 (P would exceed 8192 points = 128 KB of shared memory) and as the A/B reference
 // (SSB_AUG_FFT=0).
 // ---------------------------------------------------------------------------------------------
 #define AFFT_THREADS 512
@@ -174,31 +174,32 @@ __device__ __forceinline__ float2 chirp(unsigned int n, unsigned int den, float 
   sincospif((float)r / (float)den, &s, &c);
   return make_float2(c, sign * s);
 }
-__device__ __forceinline__ void fft_twiddles(float2* T, int P) {      // T[t] = exp(-2 pi i t / P), t < P/2
-  for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
-    float s, c;
-    sincospif(2.0f * (float)t / (float)P, &s, &c);
-    T[t] = make_float2(c, -s);
-  }
+// Twiddles are evaluated on the fly (sincospi of an exact dyadic fraction): a shared-memory table read at T[j * P/len]
+// is a 16..32-way bank conflict in every stage with len <= P/8 (stride of 128 B or more) -- measured 44 us per launch
+// with the table against the dense kernels' 33 us.
+__device__ __forceinline__ float2 twiddle(int j, int len) {            // exp(-2 pi i j / len), len a power of two
+  float s, c;
+  sincospif(2.0f * (float)j / (float)len, &s, &c);
+  return make_float2(c, -s);
 }
-__device__ __forceinline__ void fft_dif_fwd(float2* a, const float2* T, int P) {
-  for (int half = P >> 1, tstep = 1; half >= 1; half >>= 1, tstep <<= 1) {
+__device__ __forceinline__ void fft_dif_fwd(float2* a, int P) {
+  for (int half = P >> 1; half >= 1; half >>= 1) {
     for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
       const int j = t & (half - 1);
       const int i = ((t - j) << 1) + j;
       const float2 u = a[i], v = a[i + half];
       a[i] = make_float2(u.x + v.x, u.y + v.y);
-      a[i + half] = cmul(make_float2(u.x - v.x, u.y - v.y), T[j * tstep]);
+      a[i + half] = cmul(make_float2(u.x - v.x, u.y - v.y), twiddle(j, 2 * half));
     }
     __syncthreads();
   }
 }
-__device__ __forceinline__ void fft_dit_inv(float2* a, const float2* T, int P) {      // unscaled
-  for (int half = 1, tstep = P >> 1; half < P; half <<= 1, tstep >>= 1) {
+__device__ __forceinline__ void fft_dit_inv(float2* a, int P) {      // unscaled
+  for (int half = 1; half < P; half <<= 1) {
     for (int t = threadIdx.x; t < P / 2; t += blockDim.x) {
       const int j = t & (half - 1);
       const int i = ((t - j) << 1) + j;
-      const float2 w = T[j * tstep];
+      const float2 w = twiddle(j, 2 * half);
       const float2 u = a[i], v = cmul(a[i + half], make_float2(w.x, -w.y));
       a[i] = make_float2(u.x + v.x, u.y + v.y);
       a[i + half] = make_float2(u.x - v.x, u.y - v.y);
@@ -207,13 +208,13 @@ __device__ __forceinline__ void fft_dit_inv(float2* a, const float2* T, int P) {
   }
 }
 // a <- cyclic convolution of a and h (both length P, in shared memory); h is destroyed
-__device__ __forceinline__ void fft_convolve(float2* a, float2* h, const float2* T, int P) {
+__device__ __forceinline__ void fft_convolve(float2* a, float2* h, int P) {
   __syncthreads();
-  fft_dif_fwd(a, T, P);
-  fft_dif_fwd(h, T, P);
+  fft_dif_fwd(a, P);
+  fft_dif_fwd(h, P);
   for (int i = threadIdx.x; i < P; i += blockDim.x) a[i] = cmul(a[i], h[i]);
   __syncthreads();
-  fft_dit_inv(a, T, P);
+  fft_dit_inv(a, P);
 }
 
 __global__ void __launch_bounds__(AFFT_THREADS)
@@ -223,12 +224,10 @@ aug_spectrum_fft_kernel(const float* __restrict__ x, float2* __restrict__ spec, 
   extern __shared__ float sm[];
   float2* a = reinterpret_cast<float2*>(sm);
   float2* h = a + P;
-  float2* T = h + P;
   const int bc = blockIdx.x;
   const int b = bc / C;
   const int kmax = min(size[b], L) / 2;
   const int M = kmax + 1;
-  fft_twiddles(T, P);
   for (int n = threadIdx.x; n < P; n += AFFT_THREADS) {
     float2 av = make_float2(0.f, 0.f), hv = make_float2(0.f, 0.f);
     if (n < L) {
@@ -241,7 +240,7 @@ aug_spectrum_fft_kernel(const float* __restrict__ x, float2* __restrict__ spec, 
     a[n] = av;
     h[n] = hv;
   }
-  fft_convolve(a, h, T, P);
+  fft_convolve(a, h, P);
   const float invP = 1.0f / (float)P;
   for (int k = threadIdx.x; k <= kmax; k += AFFT_THREADS) {
     const float2 v = cmul(a[k], chirp((unsigned)k, (unsigned)L, -1.f));
@@ -257,7 +256,6 @@ aug_resize_crop_fft_kernel(const float2* __restrict__ spec, const int64_t* __res
   extern __shared__ float sm[];
   float2* a = reinterpret_cast<float2*>(sm);
   float2* h = a + P;
-  float2* T = h + P;
   const int bc = blockIdx.x;
   const int b = bc / C, c = bc - b * C;
   const int size = size_arr[b], start = start_arr[b];
@@ -266,7 +264,6 @@ aug_resize_crop_fft_kernel(const float2* __restrict__ spec, const int64_t* __res
   const int pad = L - size;
   const int left = pad > 0 ? pad / 2 : 0;
   const int p0 = start - left;                            // position in the resized strip of output sample 0
-  fft_twiddles(T, P);
   for (int n = threadIdx.x; n < P; n += AFFT_THREADS) {
     float2 av = make_float2(0.f, 0.f), hv = make_float2(0.f, 0.f);
     if (n <= kmax) {
@@ -287,7 +284,7 @@ aug_resize_crop_fft_kernel(const float2* __restrict__ spec, const int64_t* __res
     a[n] = av;
     h[n] = hv;
   }
-  fft_convolve(a, h, T, P);
+  fft_convolve(a, h, P);
   const float scale = 1.0f / ((float)P * (float)L);
   for (int j = threadIdx.x; j < L; j += AFFT_THREADS) {
     const int p = p0 + j;
@@ -350,13 +347,89 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-// numpy.percentile(..., method='linear') on an ascending array
-__device__ __forceinline__ float percentile_sorted(const float* s, int n, double q) {
+// ---- exact order statistics without sorting (numpy.percentile needs two adjacent ones per percentile) ----
+// Round 1 sorted every lead with a block-wide bitonic sort (78 compare-exchange stages with a barrier each: ~26 us per
+// 2500-sample lead, 130 us per launch -- the largest item of the augmentation).  The k-th smallest value is found by a
+// radix select instead: four passes over the samples, 8 key bits per pass, a 256-bin shared-memory histogram and a
+// warp scan per pass; the (k+1)-th comes from one more pass (count of values <= the k-th, smallest value above it).
+__device__ __forceinline__ unsigned int aug_key(float f) {            // order-preserving float -> uint
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float aug_unkey(unsigned int k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// k-th smallest (0-based) of row[0..n); all threads of the block call it, all get the result.  hist: 256 + 2 words.
+__device__ float block_kth(const float* row, int n, int k, unsigned int* hist) {
+  unsigned int prefix = 0u, mask = 0u;
+  int kk = k;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += AUG_THREADS) hist[i] = 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += AUG_THREADS) {
+      const unsigned int key = aug_key(row[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                       // warp 0: lane l owns bins 8l .. 8l+7
+      const int lane = threadIdx.x;
+      unsigned int c[8], mine = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; mine += c[j]; }
+      unsigned int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const unsigned int excl = incl - mine;
+      if ((unsigned int)kk >= excl && (unsigned int)kk < incl) {     // exactly one lane
+        unsigned int cum = excl;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if ((unsigned int)kk >= cum && (unsigned int)kk < cum + c[j]) { hist[256] = (unsigned int)(lane * 8 + j); hist[257] = (unsigned int)kk - cum; }
+          cum += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= hist[256] << shift;
+    mask |= 0xFFu << shift;
+    kk = (int)hist[257];
+    __syncthreads();
+  }
+  return aug_unkey(prefix);
+}
+// (k+1)-th smallest given the k-th (value vk): vk again if at least k+2 values are <= vk, else the smallest value above vk
+__device__ float block_next(const float* row, int n, int k, float vk, float* red) {
+  int cnt = 0;
+  float mn = INFINITY;
+  for (int i = threadIdx.x; i < n; i += AUG_THREADS) {
+    const float v = row[i];
+    if (v <= vk) ++cnt;
+    else mn = fminf(mn, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) { red[wid] = (float)cnt; red[AUG_THREADS / 32 + wid] = mn; }
+  __syncthreads();
+  float tc = 0.f, tm = INFINITY;
+  for (int i = 0; i < AUG_THREADS / 32; ++i) { tc += red[i]; tm = fminf(tm, red[AUG_THREADS / 32 + i]); }
+  __syncthreads();
+  return (int)tc >= k + 2 ? vk : tm;
+}
+// numpy.percentile(row, q, method='linear')
+__device__ float block_percentile(const float* row, int n, double q, unsigned int* hist, float* red) {
   const double h = (double)(n - 1) * q / 100.0;
   const int lo = (int)floor(h);
-  const int hi = lo + 1 < n ? lo + 1 : n - 1;
   const float t = (float)(h - (double)lo);
-  const float a = s[lo], b = s[hi];
+  const float a = block_kth(row, n, lo, hist);
+  const float b = lo + 1 < n ? block_next(row, n, lo, a, red) : a;
   return t >= 0.5f ? b - (b - a) * (1.0f - t) : a + (b - a) * t;
 }
 
@@ -367,8 +440,11 @@ aug_strong_standardize_kernel(const float* __restrict__ x, float* __restrict__ y
   pdl_wait();
   if (seed_dev) seed += *seed_dev;   // per-replay seed of a captured launch
   extern __shared__ float sm[];
-  float* sortbuf = sm;                 // [npow2] (only used by the powerline op)
+  (void)sm;
+  (void)npow2;
   __shared__ float red[AUG_THREADS / 32];
+  __shared__ float red2[2 * (AUG_THREADS / 32)];
+  __shared__ unsigned int hist[258];
   __shared__ float s_amp;
   const int b = blockIdx.x;
   const size_t base = (size_t)b * C * L;
@@ -388,22 +464,9 @@ aug_strong_standardize_kernel(const float* __restrict__ x, float* __restrict__ y
     } else if (op.kind == SSB_AUG_POWERLINE) {
       for (int c = 0; c < C; ++c) {
         float* row = yb + (size_t)c * L;
-        for (int i = threadIdx.x; i < npow2; i += AUG_THREADS) sortbuf[i] = i < L ? row[i] : INFINITY;
-        __syncthreads();
-        for (int k = 2; k <= npow2; k <<= 1) {          // bitonic sort, ascending
-          for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < npow2; i += AUG_THREADS) {
-              const int ixj = i ^ j;
-              if (ixj > i) {
-                const float a = sortbuf[i], bb = sortbuf[ixj];
-                const bool up = (i & k) == 0;
-                if ((a > bb) == up) { sortbuf[i] = bb; sortbuf[ixj] = a; }
-              }
-            }
-            __syncthreads();
-          }
-        }
-        if (threadIdx.x == 0) s_amp = (percentile_sorted(sortbuf, L, 95.0) - percentile_sorted(sortbuf, L, 5.0)) * 0.5f;
+        const float p95 = block_percentile(row, L, 95.0, hist, red2);
+        const float p05 = block_percentile(row, L, 5.0, hist, red2);
+        if (threadIdx.x == 0) s_amp = (p95 - p05) * 0.5f;
         __syncthreads();
         const float amp = s_amp;
         const int f2 = 2 * op.a;                          // phase in half-turns: 2*f*t/fs, reduced exactly
@@ -466,7 +529,7 @@ int ssb_aug_spectrum(const float* x, float* spec, const int32_t* size, int B, in
   SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_spectrum: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
   const int K1 = L / 2 + 1;
   if (const int P = aug_fft_points(L)) {
-    ssb_launch(aug_spectrum_fft_kernel, dim3(B * C), dim3(AFFT_THREADS), (size_t)(2 * P + P / 2) * sizeof(float2), to_stream(stream), x,
+    ssb_launch(aug_spectrum_fft_kernel, dim3(B * C), dim3(AFFT_THREADS), (size_t)(2 * P) * sizeof(float2), to_stream(stream), x,
                reinterpret_cast<float2*>(spec), size, C, L, K1, P);
     SSB_LAUNCH_CHECK("ssb_aug_spectrum");
     return SSB_OK;
@@ -486,7 +549,7 @@ int ssb_aug_resize_crop(const float* spec, const int64_t* lab_in, float* y, int6
   SSB_REQUIRE(max_size >= 1 && max_size <= 2 * L, "ssb_aug_resize_crop: max_size %d out of [1, 2L]", max_size);
   const int K1 = L / 2 + 1;
   if (const int P = aug_fft_points(L)) {
-    ssb_launch(aug_resize_crop_fft_kernel, dim3(B * C), dim3(AFFT_THREADS), (size_t)(2 * P + P / 2) * sizeof(float2), to_stream(stream),
+    ssb_launch(aug_resize_crop_fft_kernel, dim3(B * C), dim3(AFFT_THREADS), (size_t)(2 * P) * sizeof(float2), to_stream(stream),
                reinterpret_cast<const float2*>(spec), lab_in, y, lab_out, size, start, C, L, K1, P);
     SSB_LAUNCH_CHECK("ssb_aug_resize_crop");
     return SSB_OK;
@@ -507,7 +570,7 @@ int ssb_aug_strong_standardize(const float* x, float* y, const ssb_aug_op* ops, 
               "ssb_aug_strong_standardize: bad arguments (B=%d C=%d L=%d fs=%d n_ops=%d)", B, C, L, fs, n_ops);
   int npow2 = 1;
   while (npow2 < L) npow2 <<= 1;
-  ssb_launch(aug_strong_standardize_kernel, dim3(B), dim3(AUG_THREADS), (size_t)npow2 * sizeof(float), to_stream(stream), x, y,
+  ssb_launch(aug_strong_standardize_kernel, dim3(B), dim3(AUG_THREADS), 0, to_stream(stream), x, y,
              ops, n_ops, scales, white, seed, seed_dev, C, L, fs, level, npow2);
   SSB_LAUNCH_CHECK("ssb_aug_strong_standardize");
   return SSB_OK;
