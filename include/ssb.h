@@ -82,6 +82,19 @@ typedef struct ssb_bn {
   float* dbeta;            /* [C] gradient of bias */
   int32_t count_mul;       /* SyncBN: world size (sums hold the all-reduced totals); 0/1 = local */
   int32_t pad;
+  /* SyncBN statistics exchange INSIDE the consuming kernels (torch SyncBatchNorm's all_gather / all_reduce,
+   * fixmatch.py:290-291): when sync_peers != NULL the kernels that turn `sums` / `bwd_sums` into coefficients
+   * (ssb_bn_act_fwd, ssb_stem_bn_relu_pool_fwd, ssb_bn_bwd_fused, ssb_bn_bwd_apply, ssb_stem_bwd_apply) publish this
+   * rank's local sums into every peer's mailbox over NVLink and sum the ranks' values, in rank order, from their own
+   * mailbox -- no separate exchange launch.  Mailbox of a rank: ssb_syncbn_fused_mailbox_bytes(slot, world) bytes of
+   * peer-mapped memory, zeroed once; every BN layer owns [sync_fwd_off, +2C) and [sync_bwd_off, +2C) doubles of each
+   * rank's region; words are tagged with sync_sp->step (one use of a slice per step). */
+  const uint64_t* sync_peers;          /* DEVICE array [sync_world] of the ranks' mailbox base addresses, or NULL */
+  const struct ssb_step_params* sync_sp;
+  int32_t sync_world, sync_rank;
+  uint32_t sync_slot;                  /* doubles per rank region */
+  uint32_t sync_fwd_off, sync_bwd_off; /* first double of this layer's forward / backward slice */
+  uint32_t pad2;
 } ssb_bn;
 
 /* per-step scalars that change between replays of a captured step graph; lives in
@@ -125,6 +138,9 @@ int64_t ssb_launch_count(void);
 /* one-time per-device setup (opt-in shared-memory sizes of the large kernels); call once before
  * the first launch / before capturing a CUDA graph */
 int ssb_prepare(void);
+
+/* bytes of one rank's mailbox for the in-kernel SyncBN exchange (see ssb_bn.sync_peers) */
+size_t ssb_syncbn_fused_mailbox_bytes(int slot_doubles, int world);
 
 int ssb_memset_zero(void* p, size_t bytes, ssb_stream_t stream);
 

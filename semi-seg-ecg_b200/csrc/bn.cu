@@ -376,7 +376,12 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
       const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
       const bool writer = blockIdx.x == 0;
       const float mean_ = bn.mean_invstd[c], inv_ = bn.mean_invstd[C + c];
-      const double sg = bn.bwd_sums[c], sgx = bn.bwd_sums[C + c];
+      double sb[2] = {bn.bwd_sums[c], bn.bwd_sums[C + c]};
+      if (bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here
+        const unsigned int ix[2] = {bn.sync_bwd_off + (unsigned int)c, bn.sync_bwd_off + (unsigned int)(C + c)};
+        sbx_allsum<2>(bn, ix, sb, writer);
+      }
+      const double sg = sb[0], sgx = sb[1];
       sCo[0][threadIdx.x] = mean_;
       sCo[1][threadIdx.x] = inv_;
       sCo[2][threadIdx.x] = bn.gamma[c] * inv_;
@@ -388,7 +393,12 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
       }
       if (RES == 2) {
         const float meanr = bnr.mean_invstd[c], invr = bnr.mean_invstd[C + c];
-        const double sgxr = bnr.bwd_sums[C + c];
+        double sr[1] = {bnr.bwd_sums[C + c]};
+        if (bnr.sync_peers) {
+          const unsigned int ix[1] = {bnr.sync_bwd_off + (unsigned int)(C + c)};
+          sbx_allsum<1>(bnr, ix, sr, writer);
+        }
+        const double sgxr = sr[0];
         sCo[5][threadIdx.x] = meanr;
         sCo[6][threadIdx.x] = invr;
         sCo[7][threadIdx.x] = bnr.gamma[c] * invr;
@@ -622,6 +632,19 @@ __global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(cons
         sg += __ldcg(&rep[k * rep_stride + c]);
         sgx += __ldcg(&rep[k * rep_stride + C + c]);
         if (RES == 2) sgxr += __ldcg(&rep_r[k * rep_stride + C + c]);
+      }
+      if (bn.sync_peers) {      // SyncBN: this rank's sums are complete (grid barrier above) -- totals over the ranks
+        double sb[2] = {sg, sgx};
+        const unsigned int ix[2] = {bn.sync_bwd_off + (unsigned int)c, bn.sync_bwd_off + (unsigned int)(C + c)};
+        sbx_allsum<2>(bn, ix, sb, writer);
+        sg = sb[0];
+        sgx = sb[1];
+        if (RES == 2) {
+          double sr[1] = {sgxr};
+          const unsigned int ixr[1] = {bnr.sync_bwd_off + (unsigned int)(C + c)};
+          sbx_allsum<1>(bnr, ixr, sr, writer);
+          sgxr = sr[0];
+        }
       }
       sCo[0][threadIdx.x] = bn.gamma[c] * bn.mean_invstd[C + c];
       sCo[1][threadIdx.x] = (float)(sg * inv_n);
@@ -1041,12 +1064,17 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bwd_apply_kernel(const T* __r
     sMean[c] = mean;
     sInv[c] = inv;
     sScale[c] = bn.gamma[c] * inv;
-    sK1[c] = (float)(bn.bwd_sums[c] * inv_n);
-    sK2[c] = (float)(bn.bwd_sums[C + c] * inv_n);
+    double sb[2] = {bn.bwd_sums[c], bn.bwd_sums[C + c]};
+    if (bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here
+      const unsigned int ix[2] = {bn.sync_bwd_off + (unsigned int)c, bn.sync_bwd_off + (unsigned int)(C + c)};
+      sbx_allsum<2>(bn, ix, sb, blockIdx.x == 0);
+    }
+    sK1[c] = (float)(sb[0] * inv_n);
+    sK2[c] = (float)(sb[1] * inv_n);
     if (blockIdx.x == 0) {
       const double gsc = 1.0 / (double)(bn.count_mul > 1 ? bn.count_mul : 1);
-      bn.dgamma[c] = (float)(bn.bwd_sums[C + c] * gsc);
-      bn.dbeta[c] = (float)(bn.bwd_sums[c] * gsc);
+      bn.dgamma[c] = (float)(sb[1] * gsc);
+      bn.dbeta[c] = (float)(sb[0] * gsc);
     }
   }
   __syncthreads();

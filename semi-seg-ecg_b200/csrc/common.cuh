@@ -214,13 +214,94 @@ struct ssb_bnf_args {
 #define BN_EPS 1e-5
 #define BN_MOMENTUM 0.1f
 
+// ---- SyncBN exchange inside the consuming kernels (ssb_bn.sync_*; protocol of optim.cu's exchange kernel) ----
+// Self-validating 8-byte words {32 payload bits, tag}: a value has arrived when both of its words carry this step's
+// tag -- no fence, no flag round trip: one NVLink hop.  A slice is used once per step, so the tag is the step count.
+#define SBX_HDR_BYTES 4096          // [0] (legacy exchange counter), [64] error word
+#define SBX_MAX_WORLD 16
+__device__ __forceinline__ void sbx_store(uint2* p, uint32_t payload, uint32_t epoch) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ uint2 sbx_load(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// Sum over the ranks (in rank order: bitwise identical everywhere) of NV doubles whose local values are mine[0..NV) and
+// whose region indices are idx[0..NV).  push: this thread also publishes the local values (exactly one thread per
+// value and launch must).  All peer loads of a polling round are in flight together.
+template <int NV>
+__device__ __forceinline__ void sbx_allsum(const ssb_bn& bn, const unsigned int (&idx)[NV], double (&val)[NV], bool push) {
+  const unsigned int epoch = (unsigned int)bn.sync_sp->step;
+  const int world = bn.sync_world, rank = bn.sync_rank;
+  const unsigned long long* peers = reinterpret_cast<const unsigned long long*>(bn.sync_peers);
+  if (push) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const uint32_t lo = (uint32_t)__double2loint(val[v]), hi = (uint32_t)__double2hiint(val[v]);
+      for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<char*>(peers[r]) + SBX_HDR_BYTES) +
+                     ((size_t)rank * bn.sync_slot + idx[v]) * 2;
+        sbx_store(dst, lo, epoch);
+        sbx_store(dst + 1, hi, epoch);
+      }
+    }
+  }
+  char* mine = reinterpret_cast<char*>(peers[rank]);
+  const uint2* mail = reinterpret_cast<const uint2*>(mine + SBX_HDR_BYTES);
+  const long long t0 = clock64();
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    double t = 0.0;
+    for (int r0 = 0; r0 < world; r0 += 4) {          // four ranks per round: their loads are in flight together
+      double got[4] = {0.0, 0.0, 0.0, 0.0};
+      unsigned int pending = 0u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r0 + j < world && r0 + j != rank) pending |= 1u << j;
+      while (pending) {
+        uint2 a[4], b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (pending & (1u << j)) {
+            const uint2* src = mail + ((size_t)(r0 + j) * bn.sync_slot + idx[v]) * 2;
+            a[j] = sbx_load(src);
+            b[j] = sbx_load(src + 1);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((pending & (1u << j)) && a[j].y == epoch && b[j].y == epoch) {
+            got[j] = __hiloint2double((int)b[j].x, (int)a[j].x);
+            pending &= ~(1u << j);
+          }
+        }
+        if (pending && clock64() - t0 > 40000000000LL) {   // ~20 s: a peer is gone -- record it (the host raises) and go on
+          *reinterpret_cast<unsigned int*>(mine + 64) = epoch;
+          pending = 0u;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r0 + j < world) t += (r0 + j == rank) ? val[v] : got[j];
+    }
+    val[v] = t;
+  }
+}
+
 // per-channel affine coefficients: y = x*scale + shift
 __device__ __forceinline__ void bn_coeffs(const ssb_bn& bn, int c, int C, int train, double inv_n, double n,
                                           bool writer, float& scale, float& shift) {
   float mean, invstd;
   if (train) {
-    double m = __ldcg(&bn.sums[c]) * inv_n;   // (L2 read: the sums may have been completed by other blocks of this launch)
-    double var = __ldcg(&bn.sums[C + c]) * inv_n - m * m;
+    double st[2] = {__ldcg(&bn.sums[c]), __ldcg(&bn.sums[C + c])};   // (L2 read: the sums may have been completed by other blocks of this launch)
+    if (bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here (the writer block publishes this rank's sums)
+      const unsigned int ix[2] = {bn.sync_fwd_off + (unsigned int)c, bn.sync_fwd_off + (unsigned int)(C + c)};
+      sbx_allsum<2>(bn, ix, st, writer);
+    }
+    double m = st[0] * inv_n;
+    double var = st[1] * inv_n - m * m;
     if (var < 0.0) var = 0.0;
     mean = (float)m;
     invstd = rsqrtf((float)var + (float)BN_EPS);

@@ -152,17 +152,7 @@ int ssb_grad_norm(const float* g, size_t n, double* ws, float* out, ssb_stream_t
 // Two parities: a rank can be at most one exchange ahead of a peer (it cannot finish exchange k+1 before the peer
 // has sent k+1, which the peer does only after it has finished reading k), so slot reuse never races.
 // ---------------------------------------------------------------------------------------
-#define SBX_MAX_WORLD 16
-#define SBX_HDR_BYTES 4096          // [0] exchange counter, [64] error word
-
-__device__ __forceinline__ void sbx_store(uint2* p, uint32_t payload, uint32_t epoch) {
-  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(payload), "r"(epoch) : "memory");
-}
-__device__ __forceinline__ uint2 sbx_load(const uint2* p) {
-  uint2 v;
-  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
-}
+// (SBX_MAX_WORLD, SBX_HDR_BYTES, sbx_store / sbx_load: common.cuh -- shared with the in-kernel exchange of bn.cu)
 
 __global__ void __launch_bounds__(256) syncbn_exchange_kernel(double* __restrict__ slice, int n, const unsigned long long* __restrict__ peers,
                                                               int world, int rank, int slot_doubles) {
@@ -213,6 +203,10 @@ extern "C" {
 
 size_t ssb_syncbn_mailbox_bytes(int slot_doubles) {
   return (size_t)SBX_HDR_BYTES + (size_t)2 * SBX_MAX_WORLD * (size_t)slot_doubles * 16;   // two {payload, number} words per double
+}
+
+size_t ssb_syncbn_fused_mailbox_bytes(int slot_doubles, int world) {
+  return (size_t)SBX_HDR_BYTES + (size_t)world * (size_t)slot_doubles * 16;   // two {payload, tag} words per double
 }
 
 int ssb_syncbn_exchange(double* slice, int n, const uint64_t* peers_dev, int world, int rank, int slot_doubles,

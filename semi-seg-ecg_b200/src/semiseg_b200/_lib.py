@@ -33,7 +33,10 @@ class BN(C.Structure):
     _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("running_mean", C.c_void_p),
                 ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p), ("sums", C.c_void_p),
                 ("mean_invstd", C.c_void_p), ("bwd_sums", C.c_void_p), ("dgamma", C.c_void_p),
-                ("dbeta", C.c_void_p), ("count_mul", C.c_int32), ("pad", C.c_int32)]
+                ("dbeta", C.c_void_p), ("count_mul", C.c_int32), ("pad", C.c_int32),
+                # SyncBN exchange inside the consuming kernels (include/ssb.h: ssb_bn.sync_*); all zero = off
+                ("sync_peers", C.c_void_p), ("sync_sp", C.c_void_p), ("sync_world", C.c_int32), ("sync_rank", C.c_int32),
+                ("sync_slot", C.c_uint32), ("sync_fwd_off", C.c_uint32), ("sync_bwd_off", C.c_uint32), ("pad2", C.c_uint32)]
 
 
 class StepParams(C.Structure):
@@ -49,7 +52,7 @@ class AugOp(C.Structure):
 
 AUG_AMPLITUDE, AUG_POWERLINE, AUG_PARTIAL_WHITE, AUG_PARTIAL_SINE = 0, 1, 2, 3
 
-assert C.sizeof(StepParams) == 64 and C.sizeof(Geom) == 16 and C.sizeof(AugOp) == 16
+assert C.sizeof(StepParams) == 64 and C.sizeof(Geom) == 16 and C.sizeof(AugOp) == 16 and C.sizeof(BN) == 128
 
 _P, _I, _F, _SZ, _D = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_double
 _BNP = C.POINTER(BN)
@@ -96,12 +99,14 @@ SIGNATURES = {
     "ssb_ema_i64": [_P, _P, _SZ, _P, _P],
     "ssb_grad_norm": [_P, _SZ, _P, _P, _P],
     "ssb_syncbn_mailbox_bytes": [_I],
+    "ssb_syncbn_fused_mailbox_bytes": [_I, _I],
     "ssb_syncbn_exchange": [_P, _I, _P, _I, _I, _I, _P],
     "ssb_aug_spectrum": [_P, _P, _P, _I, _I, _I, _P],
     "ssb_aug_resize_crop": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "ssb_aug_strong_standardize": [_P, _P, _P, _I, _P, _P, C.c_uint32, _P, _I, _I, _I, _I, _F, _P],
 }
-_RESTYPES = {"ssb_last_error": C.c_char_p, "ssb_launch_count": C.c_int64, "ssb_syncbn_mailbox_bytes": C.c_size_t}
+_RESTYPES = {"ssb_last_error": C.c_char_p, "ssb_launch_count": C.c_int64, "ssb_syncbn_mailbox_bytes": C.c_size_t,
+             "ssb_syncbn_fused_mailbox_bytes": C.c_size_t}
 
 _lib: Optional[C.CDLL] = None
 

@@ -143,10 +143,11 @@ class StepEngine:
                 self.bufs_snap = torch.empty_like(weights.bufs)
             self.plan_t = NetPlan(tw, self.dtype_t, self.Bu, L, False, algo if self.dtype_t == dtype else None, bufs=self.bufs_snap)
         if self.sync_bn:
-            # SyncBatchNorm (fixmatch.py:290-291): statistic arenas are exchanged layer by layer
+            # SyncBatchNorm (fixmatch.py:290-291): the statistics of every BN layer are summed over the ranks
             for s in self.plan_s._bn_structs.values():
                 s.count_mul = self.world
-            self.plan_s.sync_hook = self._make_sync_hook()
+            if not self._setup_fused_sync():          # exchange inside the consuming kernels (NVLink peer mailboxes)
+                self.plan_s.sync_hook = self._make_sync_hook()   # else: one exchange launch (or NCCL call) per BN layer
         self._stage = None
         self.stage_h2d = bool(int(os.environ.get("SSB_STAGE_H2D", "1")))
         self.mat = None
@@ -165,6 +166,47 @@ class StepEngine:
         self.wd = float(train_cfg.get("weight_decay", 0.0))
         if train_cfg.get("optimizer", "adamw") != "adamw":
             raise NotImplementedError("the fused optimizer kernel implements AdamW (all shipped configs)")
+
+    def _setup_fused_sync(self) -> bool:
+        """SyncBN without exchange launches: every BN struct of the training plan gets the peers' mailbox addresses and
+        its own slices (ssb_bn.sync_*); the kernels that consume the statistics publish this rank's sums to the peers and
+        sum the ranks' values from their own mailbox.  A slice is used once per step and tagged with the step count, so
+        the BN layers' exchanges need no common order: the shortcut convs may stay on their side branch.  False if the
+        peer mapping cannot be set up (or SSB_SYNCBN_FUSED=0): the caller falls back to the per-layer exchange."""
+        self.syncbn_p2p = False
+        self.syncbn_fused = False
+        if not int(os.environ.get("SSB_SYNCBN_FUSED", "1")) or not int(os.environ.get("SSB_SYNCBN_P2P", "1")) or \
+                self.world < 2 or self.world > 16 or self.merged:
+            return False
+        lay = self.plan_s.lay
+        slot = 2 * lay.n_sums                      # forward sums | backward sums of every layer
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = int(_lib.load().ssb_syncbn_fused_mailbox_bytes(slot, self.world))
+            box = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            box.zero_()
+            hdl = symm_mem.rendezvous(box, self.pg if self.pg is not None else torch.distributed.group.WORLD)
+            ptrs = [int(p_) for p_ in hdl.buffer_ptrs]
+            assert len(ptrs) == self.world and ptrs[hdl.rank] == box.data_ptr()
+            torch.cuda.synchronize()
+            torch.distributed.barrier(group=self.pg)
+        except Exception as e:   # no peer access / allocator not available
+            import warnings
+            warnings.warn(f"SyncBN in-kernel exchange unavailable ({type(e).__name__}: {e}); using one exchange per layer")
+            return False
+        self._mailbox, self._mail_hdl = box, hdl
+        self._peers_dev = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+        for b in lay.bns:
+            s = self.plan_s._bn_structs[b.prefix]
+            s.sync_peers = self._peers_dev.data_ptr()
+            s.sync_sp = self.sp_dev.data_ptr()
+            s.sync_world, s.sync_rank = self.world, hdl.rank
+            s.sync_slot = slot
+            s.sync_fwd_off, s.sync_bwd_off = b.soff, lay.n_sums + b.soff
+        self.plan_s.sync_fused = True
+        self.syncbn_p2p = True
+        self.syncbn_fused = True
+        return True
 
     def _make_sync_hook(self):
         """Statistics exchange of one SyncBN slice.  Preferred: our own kernel over NVLink peer memory (a symmetric

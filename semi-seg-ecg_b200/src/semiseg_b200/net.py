@@ -358,6 +358,7 @@ class NetPlan:
         self.drop_mask_ptr = 0   # tests may inject an explicit keep-mask (u8 [B, Lh, Ch])
         self.debug = None        # tests: dict that receives clones of the block-output gradients
         self.sync_hook = None    # SyncBN: callable(tensor) all-reducing a statistics slice in place
+        self.sync_fused = False  # SyncBN: the kernels that consume the statistics exchange them (ssb_bn.sync_*), no hook
         self.pre_block_event = None   # event the stream waits on after the stem (storage-dtype weight copy ready)
         # BN-backward reduce in the dgrad epilogue (ssb_conv1d_dgrad_bnred): 13 launches fewer per step, but measured
         # SLOWER (0.779 vs 0.765 ms at 16+16 x 2500; conv family +37 % at width 128): the extra loads, transposes and
@@ -531,7 +532,7 @@ class NetPlan:
         else conv(+statistics) followed by the BatchNorm pass."""
         key = (c.name, gout.B)
         if key not in self._bnf_ok:
-            self._bnf_ok[key] = bool(self.fuse_bn_fwd and self.sync_hook is None and self.barriers is not None and
+            self._bnf_ok[key] = bool(self.fuse_bn_fwd and self.sync_hook is None and not self.sync_fused and self.barriers is not None and
                                      _lib.load().ssb_conv1d_fwd_bn_train_fits(gin, gout, c.k, c.stride, self.dtype, self._algo_for(c)))
         if self._bnf_ok[key]:
             call("ssb_conv1d_fwd_bn_train", x.data_ptr(), self.sh.ptr(c), y_raw.data_ptr(), y_act.data_ptr(), gin, gout, c.k,

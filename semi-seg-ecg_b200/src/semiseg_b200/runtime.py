@@ -47,6 +47,7 @@ class ModelRuntime:
         self._sp_dev: Optional[torch.Tensor] = None
         self._rng_calls = 0
         self.seed = 0
+        self._first_last = None
 
     # ---- arena adoption ------------------------------------------------------------
     def _named(self):
@@ -107,6 +108,18 @@ class ModelRuntime:
         if not self.adopted():
             self.adopt()
         return self.weights
+
+    def quick_ok(self) -> bool:
+        """O(1) version of adopted() for the per-step path: the first and the last parameter still alias the arena."""
+        if self.weights is None:
+            return False
+        ps = self._first_last
+        if ps is None:
+            plist = list(self.model.parameters())
+            ps = self._first_last = (plist[0], plist[-1])
+        lay = self.layout.params
+        base = self.weights.params.data_ptr()
+        return ps[0].data_ptr() == base + 4 * lay[0][2] and ps[1].data_ptr() == base + 4 * lay[-1][2]
 
     # ---- plans ---------------------------------------------------------------------
     def plan(self, dtype: int, B: int, L: int, train: bool) -> NetPlan:

@@ -39,14 +39,17 @@ def get_engine(algorithm: str, model, teacher, Bl: int, Bu: int, L: int, dtype: 
                external_pseudo: bool = False) -> StepEngine:
     """Engine cache keyed by shapes; engines share the model's arenas."""
     rt = model.runtime()
-    rt.ensure()
+    if not rt.quick_ok():        # (per-step path: an O(1) check; the full parameter walk only when something moved)
+        rt.ensure()
     rt_t = None
     if algorithm == "mean_teacher":
         rt_t = teacher.runtime(nbt_float=True)
-        rt_t.ensure()
+        if not rt_t.quick_ok():
+            rt_t.ensure()
     elif algorithm in ("cps", "stpp"):      # the peer model / the frozen teacher: a plain second weight set
         rt_t = teacher.runtime()
-        rt_t.ensure()
+        if not rt_t.quick_ok():
+            rt_t.ensure()
     key = (algorithm, Bl, Bu, L, dtype, use_graph, algo, id(rt_t), bool(getattr(model, "sync_bn", False)), external_pseudo)
     eng = rt.engines.get(key)
     if eng is None:
@@ -76,6 +79,9 @@ def bind_optimizer_state(optimizer, model) -> None:
     rt = model.runtime()
     rt.ensure()
     st = rt.state
+    bound = getattr(optimizer, "_ssb_bound", None)
+    if bound is not None and bound[0] is st and len(optimizer.state) == bound[1]:
+        return      # this optimizer's state already aliases these arenas (every epoch after the first)
     mv, vv = rt.weights.param_views(st.exp_avg), rt.weights.param_views(st.exp_avg_sq)
     with torch.no_grad():
         for n, p in model.named_parameters():
@@ -85,6 +91,7 @@ def bind_optimizer_state(optimizer, model) -> None:
                 vv[n].copy_(s["exp_avg_sq"])
                 st.step = max(st.step, int(s["step"]))
             optimizer.state[p] = {"step": torch.tensor(float(st.step)), "exp_avg": mv[n], "exp_avg_sq": vv[n]}
+    optimizer._ssb_bound = (st, len(optimizer.state))
 
 
 def run_epoch(algorithm: str, model, teacher, labeled_loader: Iterable, unlabeled_loader: Optional[Iterable],
@@ -167,9 +174,10 @@ def run_epoch(algorithm: str, model, teacher, labeled_loader: Iterable, unlabele
                   f"  time: {dt / (it + 1):.4f}  max mem: {torch.cuda.max_memory_allocated() / 2 ** 20:.0f}")
     if eng is not None:
         drain(num_steps - 1)
+    step_t = torch.tensor(float(model.runtime().state.step))
     for p in optimizer.state.values():
         if isinstance(p, dict) and "step" in p:
-            p["step"] = torch.tensor(float(model.runtime().state.step))
+            p["step"] = step_t
     stats = {k: v / max(count, 1) for k, v in sums.items()}
     stats["lr"] = lr_sum / max(num_steps, 1)      # the reference returns each meter's global average (fixmatch.py:188-192)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -735,6 +735,114 @@ def test_syncbn_exchange_single_gpu():
     assert int(box[0][:4].view(torch.int32)[0]) == 1 and int(box[0][64:68].view(torch.int32)[0]) == 0   # counter, no timeout
 
 
+def _fused_sync_setup(bn, t, Cn, world, step, fwd_vals=None, bwd_vals=None, n_sums=None):
+    """Two mailboxes on ONE GPU for the in-kernel SyncBN exchange (ssb_bn.sync_*): this process is rank 0, the values
+    rank 1 'sent' are pre-filled in rank 0's mailbox in the wire format, tagged with `step`.  Returns what must stay alive."""
+    lib = _lib.load()
+    n_sums = n_sums or 2 * Cn + 64
+    slot = 2 * n_sums
+    nbytes = int(lib.ssb_syncbn_fused_mailbox_bytes(slot, world))
+    box = [torch.zeros(nbytes, dtype=torch.uint8, device=DEV) for _ in range(world)]
+    peers = torch.tensor([b.data_ptr() for b in box], dtype=torch.int64, device=DEV)
+    sp = StepParams()
+    sp.step = step
+    sp_dev = torch.frombuffer(bytearray(bytes(sp)), dtype=torch.uint8).to(DEV)
+    bn.sync_peers, bn.sync_sp = peers.data_ptr(), sp_dev.data_ptr()
+    bn.sync_world, bn.sync_rank, bn.sync_slot = world, 0, slot
+    bn.sync_fwd_off, bn.sync_bwd_off = 8, n_sums + 8
+    for vals, off in ((fwd_vals, 8), (bwd_vals, n_sums + 8)):
+        if vals is None:
+            continue
+        n = vals.numel()
+        words = torch.zeros(n, 4, dtype=torch.int32, device=DEV)
+        raw = vals.contiguous().view(torch.int32).view(n, 2)
+        words[:, 0], words[:, 1], words[:, 2], words[:, 3] = raw[:, 0], step, raw[:, 1], step
+        o = 4096 + (1 * slot + off) * 16                     # rank 0's mailbox, region of rank 1
+        box[0][o: o + n * 16] = words.view(torch.uint8).flatten()
+    return box, peers, sp_dev, slot
+
+
+def _pushed(box, slot, off, n, step):
+    """what rank 0 deposited in rank 1's mailbox (region of rank 0): values, and whether every word carries the tag"""
+    o = 4096 + (0 * slot + off) * 16
+    got = box[1][o: o + n * 16].view(torch.int32).view(n, 4)
+    return got[:, [0, 2]].contiguous().view(torch.float64).flatten(), bool((got[:, [1, 3]] == step).all())
+
+
+@pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
+def test_syncbn_in_kernel_exchange_forward(dtype):
+    """ssb_bn_act_fwd (train) with ssb_bn.sync_* set: this rank's statistics go to the peer's mailbox, the peer's
+    (pre-filled) are added in rank order, and the output / saved mean, invstd / running statistics are those of the
+    layer run on the TOTAL statistics with count_mul = 2."""
+    torch.manual_seed(11)
+    B, Cn, L, pitch = 6, 128, 157, 160
+    g = Geom(B, pitch, L, Cn)
+    xx = to_flat(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64) * 1.3 + 0.2, pitch, dtype)
+    theirs = torch.cat((torch.randn(Cn, dtype=torch.float64, device=DEV) * 30, torch.rand(Cn, dtype=torch.float64, device=DEV) * 2000 + 1500))
+    outs = []
+    for sync in (False, True):
+        bn, t = make_bn(Cn, train_count_mul=2)
+        call("ssb_bn_stats", xx.data_ptr(), g, t["sums"].data_ptr(), dtype, st())
+        local = t["sums"].clone()
+        keep = None
+        if sync:
+            keep = _fused_sync_setup(bn, t, Cn, 2, 7, fwd_vals=theirs)
+        else:
+            t["sums"] += theirs
+        y = torch.full((B * pitch, Cn), 5.0, dtype=TDT[dtype], device=DEV)
+        call("ssb_bn_act_fwd", xx.data_ptr(), C.byref(bn), None, None, y.data_ptr(), g, 1, 1, dtype, st())
+        torch.cuda.synchronize()
+        outs.append((y.clone(), t["mi"].clone(), t["rm"].clone(), t["rv"].clone()))
+        if sync:
+            box, _, _, slot = keep
+            vals, tagged = _pushed(box, slot, 8, 2 * Cn, 7)
+            assert tagged and torch.equal(vals, local)
+            assert int(box[0][64:68].view(torch.int32)[0]) == 0      # no timeout recorded
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("dtype", [_lib.F32, _lib.BF16])
+@pytest.mark.parametrize("fused", [True, False])
+def test_syncbn_in_kernel_exchange_backward(dtype, fused):
+    """ssb_bn_bwd_fused / ssb_bn_bwd_apply with ssb_bn.sync_* set == the two-launch path with the peer's sums added by hand."""
+    torch.manual_seed(12)
+    B, Cn, L, pitch = 16, 128, 313, 316
+    g = Geom(B, pitch, L, Cn)
+    gr = to_flat(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64), pitch, dtype)
+    yy = to_flat(torch.relu(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64)), pitch, dtype)
+    xx = to_flat(torch.randn(B, Cn, L, device=DEV, dtype=torch.float64) + 0.3, pitch, dtype)
+    theirs = torch.randn(2 * Cn, dtype=torch.float64, device=DEV) * 40
+    res = []
+    for sync in (False, True):
+        torch.manual_seed(99)
+        bn, t = make_bn(Cn, train_count_mul=2)
+        t["mi"][:Cn] = 0.1
+        t["mi"][Cn:] = 0.9
+        dx = torch.full((B * pitch, Cn), 3.0, dtype=TDT[dtype], device=DEV)
+        keep = _fused_sync_setup(bn, t, Cn, 2, 3, bwd_vals=theirs) if sync else None
+        if sync and fused:
+            bar = torch.zeros(1, dtype=torch.int32, device=DEV)
+            rep = torch.zeros(8, 2 * Cn + 64, dtype=torch.float64, device=DEV)
+            call("ssb_bn_bwd_fused", gr.data_ptr(), yy.data_ptr(), xx.data_ptr(), C.byref(bn), dx.data_ptr(), None, None, None, None, g,
+                 bar.data_ptr(), rep.data_ptr(), None, 2 * Cn + 64, dtype, st())
+        else:
+            call("ssb_bn_bwd_reduce", gr.data_ptr(), None, yy.data_ptr(), xx.data_ptr(), C.byref(bn), None, None, g, dtype, st())
+            if not sync:
+                t["bsums"] += theirs
+            call("ssb_bn_bwd_apply", gr.data_ptr(), None, yy.data_ptr(), xx.data_ptr(), C.byref(bn), dx.data_ptr(), None, None,
+                 None, None, g, dtype, st())
+        torch.cuda.synchronize()
+        res.append((dx.float(), t["dgamma"].clone(), t["dbeta"].clone()))
+        if sync:
+            box, _, _, slot = keep
+            vals, tagged = _pushed(box, slot, (2 * Cn + 64) + 8, 2 * Cn, 3)
+            assert tagged and int(box[0][64:68].view(torch.int32)[0]) == 0
+    tol = 1e-5 if dtype == _lib.F32 else 1e-2
+    assert rel_err(res[1][0], res[0][0]) < tol and halo_is_zero(res[1][0], B, pitch, L)
+    assert rel_err(res[1][1], res[0][1]) < 1e-5 and rel_err(res[1][2], res[0][2]) < 1e-5
+
+
 def test_errors_are_reported():
     lib = _lib.load()
     g = Geom(1, 4, 8, 8)   # pitch < len + 2
