@@ -315,10 +315,15 @@ aug_resize_crop_fft_kernel(const float2* __restrict__ spec, const int64_t* __res
   }
 }
 
-// FFT length of the chirp convolutions (0: use the dense kernels)
-static int aug_fft_points(int L) {
+// FFT length of the chirp convolutions (0: use the dense kernels).  One block per (strip, lead) does ~36 radix-2 stage
+// passes: ~50 us for a 4096-point problem however few strips there are, while the dense kernels spread a strip over
+// 20-40 blocks.  Measured at 16 strips x 1 lead x 2500: dense 33 + 28 us, FFT 52 + 55 us; the dense cost grows with
+// strips x leads x L^2 (config 5: 768 strip-leads x 5000 samples = 154 GFLOP), the FFT cost with strips x leads / #SMs.
+// SSB_AUG_FFT = 0 | 1 forces a path; default: FFT from 96 strip-leads on (every SM has a block).
+static int aug_fft_points(int L, int strips) {
   const char* e = getenv("SSB_AUG_FFT");
   if (e && atoi(e) == 0) return 0;
+  if (!(e && atoi(e) == 1) && strips < 96) return 0;
   int P = 64;
   while (P < L + L / 2 + 2) P <<= 1;
   return P <= 8192 ? P : 0;
@@ -528,7 +533,7 @@ int ssb_aug_spectrum(const float* x, float* spec, const int32_t* size, int B, in
   SSB_REQUIRE(x && spec && size, "ssb_aug_spectrum: null pointer");
   SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_spectrum: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
   const int K1 = L / 2 + 1;
-  if (const int P = aug_fft_points(L)) {
+  if (const int P = aug_fft_points(L, B * C)) {
     ssb_launch(aug_spectrum_fft_kernel, dim3(B * C), dim3(AFFT_THREADS), (size_t)(2 * P) * sizeof(float2), to_stream(stream), x,
                reinterpret_cast<float2*>(spec), size, C, L, K1, P);
     SSB_LAUNCH_CHECK("ssb_aug_spectrum");
@@ -548,7 +553,7 @@ int ssb_aug_resize_crop(const float* spec, const int64_t* lab_in, float* y, int6
   SSB_REQUIRE(B > 0 && C > 0 && L >= 4 && L <= 8192, "ssb_aug_resize_crop: bad shape (B=%d C=%d L=%d; L in [4, 8192])", B, C, L);
   SSB_REQUIRE(max_size >= 1 && max_size <= 2 * L, "ssb_aug_resize_crop: max_size %d out of [1, 2L]", max_size);
   const int K1 = L / 2 + 1;
-  if (const int P = aug_fft_points(L)) {
+  if (const int P = aug_fft_points(L, B * C)) {
     ssb_launch(aug_resize_crop_fft_kernel, dim3(B * C), dim3(AFFT_THREADS), (size_t)(2 * P) * sizeof(float2), to_stream(stream),
                reinterpret_cast<const float2*>(spec), lab_in, y, lab_out, size, start, C, L, K1, P);
     SSB_LAUNCH_CHECK("ssb_aug_resize_crop");

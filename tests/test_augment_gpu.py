@@ -45,8 +45,12 @@ def strips(seed, B, C, L):
     return xs, ys
 
 
-@pytest.mark.parametrize("C,L,B", [(1, 2500, 6), (2, 1000, 4), (3, 601, 3), (12, 500, 2), (1, 128, 5)])
-def test_weak_resize_crop(C, L, B):
+@pytest.mark.parametrize("fft", ["0", "1"])
+@pytest.mark.parametrize("C,L,B", [(1, 2500, 6), (2, 1000, 4), (3, 601, 3), (12, 500, 2), (1, 128, 5), (12, 5000, 2)])
+def test_weak_resize_crop(C, L, B, fft, monkeypatch):
+    """both evaluations of the Fourier resize: the dense DFT kernels (fft = 0) and the Bluestein / FFT kernels (fft = 1;
+    the library picks by problem size when SSB_AUG_FFT is unset)"""
+    monkeypatch.setenv("SSB_AUG_FFT", fft)
     np.random.seed(C * 1000 + L)
     xs, ys = strips(C + L, B, C, L)
     cfg = G.AugConfig(target_length=L)
