@@ -619,6 +619,24 @@ __global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(cons
   grid_barrier(barrier, gridDim.x * gridDim.y);
   if (threadIdx.x == 0) SSB_MARK();                 // past the grid barrier
   // ---- pass 2: apply; per-channel constants from the now complete sums (one thread per channel) ----
+  // The operands of the first trip are requested BEFORE the constants are worked out: the second read (L2) then runs
+  // under the reload of the sums, the fp64 arithmetic and -- with SyncBN -- the exchange of the sums with the peers.
+  constexpr int PU = RES == 2 ? 0 : (HAS_Y ? 1 : 2);   // rows requested early (more does not fit 128 registers next to the exchange)
+  constexpr int PA = PU > 0 ? PU : 1;
+  Vec<T> pg[PA], px[PA], py[PA], pr[PA];
+  bool pok[PA];
+#pragma unroll
+  for (int u = 0; u < PU; ++u) {
+    const int row = r0 + rl + u * rpp;
+    pok[u] = owner && row < r1 && row_valid(row, g.pitch, g.len);
+    if (pok[u]) {
+      const size_t off = (size_t)row * C + (size_t)cg * V;
+      pg[u].load(g1 + off);
+      px[u].load(x + off);
+      if (HAS_Y) py[u].load(y + off);
+      if (RES == 2) pr[u].load(xr + off);
+    }
+  }
   const int nch = cgpc * V;
   if (threadIdx.x < nch) {
     const int c = blockIdx.y * nch + threadIdx.x;
@@ -679,8 +697,17 @@ __global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(cons
   for (int base = r0 + rl; base < r1; base += UR * rpp) {
     Vec<T> vg[UR], vx[UR], vy[HAS_Y ? UR : 1], vr[RES == 2 ? UR : 1];
     bool ok[UR];
+    const bool first = base == r0 + rl;       // the trip whose first PU rows were requested before the constants
 #pragma unroll
-    for (int u = 0; u < UR; ++u) {          // second read (L2 / L1): again all loads of the trip first
+    for (int u = 0; u < UR; ++u) {            // second read (L2 / L1): again all loads of the trip first
+      if (first && u < PU) {
+        ok[u] = pok[u < PA ? u : 0];
+        vg[u] = pg[u < PA ? u : 0];
+        vx[u] = px[u < PA ? u : 0];
+        if (HAS_Y) vy[u] = py[u < PA ? u : 0];
+        if (RES == 2) vr[u] = pr[u < PA ? u : 0];
+        continue;
+      }
       const int row = base + u * rpp;
       ok[u] = row < r1 && row_valid(row, g.pitch, g.len);
       if (ok[u]) {

@@ -559,6 +559,7 @@ int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gi
                            cudaStream_t st);
 
 int ssb_conv1d_fwd_bnf_fits_sm100(ssb_geom gin, ssb_geom gout, int k, int stride);
+int ssb_stem_conv_fwd_sm100(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g, double* stats, cudaStream_t st);
 
 int ssb_simt_prepare() {
   const int big = 96 * 1024;
@@ -794,6 +795,10 @@ int ssb_stem_conv_fwd(const float* x, const float* w, void* y, int Cl, int L, ss
   int rc = check_stem("ssb_stem_conv_fwd", Cl, L, g);
   if (rc) return rc;
   SSB_REQUIRE(x && w && y, "ssb_stem_conv_fwd: null pointer");
+  if (dtype == SSB_BF16) {   // multi-lead stems: implicit GEMM on the tensor cores (conv_sm100.cu: stem_tn_kernel)
+    const int tc = ssb_stem_conv_fwd_sm100(x, w, y, Cl, L, g, nullptr, to_stream(stream));
+    if (tc <= 0) return tc;
+  }
   // tile of positions per block: every thread owns ST_PT positions x 4 channels
   const int cog = g.C / 4;
   int tt = (ST_THREADS / cog) * ST_PT;

@@ -972,6 +972,113 @@ conv_wgrad3_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stem conv (k7, s2, p3) of MULTI-LEAD inputs as an implicit GEMM on the tensor cores (round 2).
+//   D[rows, Cs] = A[rows, K] * W[K, Cs],  K = 7 * leads (84 at 12 leads, padded to a multiple of 16)
+// The CUDA-core direct conv is FMA-bound there: 94-177 us per launch at 12 x 5000 (ncu: tensor pipe 0 %, 7 % of the HBM
+// roofline, 9 % of the width-128 step), against ~10 us of memory time.  The input is fp32 NCL -- the reference's layout,
+// not TMA-tileable as an im2col operand -- so the A tile is BUILT in shared memory by the threads: row r of a 128-row
+// tile is one output position, its 7 * leads samples x[b][lead][2t-3 .. 2t+3] are converted to bf16 and stored in the
+// 128-byte-swizzled K-major layout the UMMA descriptors of the other kernels read (byte offset r*128 + ((k/8) ^ (r%8))*16
+// + (k%8)*2 inside a 64-column chunk; the swizzle follows the absolute address, tiles are 1024-byte aligned), then made
+// visible to the async proxy (fence.proxy.async) before ONE thread issues K/16 MMAs.  Weights: converted from the fp32
+// master [Cs][leads][7] = K-major rows once per CTA.  Persistent over the row tiles; two CTAs per SM overlap one CTA's
+// tile build with the other's MMAs / epilogue.  Epilogue = tn_epilogue (halo rows zeroed, optional BN statistics).
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool STATS>
+__global__ void __launch_bounds__(TN_THREADS, 1)
+stem_tn_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ out, const TnParams p, int Cl, int L,
+               int KP) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* sa = smem_raw + (((base + 1023u) & ~1023u) - base);
+  const int nchunk = (KP + 63) / 64;
+  uint8_t* sb = sa + nchunk * A_BYTES;
+  uint64_t* done = reinterpret_cast<uint64_t*>(sb + nchunk * BN * 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  float* ep_scale = reinterpret_cast<float*>(tmem_slot + 4);   // [4 * BN] (unused by this epilogue mode)
+  float* red = ep_scale + 4 * BN;                               // [8 * BN] statistics scratch
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int K = 7 * Cl;
+  // weights -> bf16, swizzled K-major rows (row n = output channel); pad columns of A zeroed once
+  for (int i = threadIdx.x; i < BN * KP; i += TN_THREADS) {
+    const int n = i / KP, k = i - n * KP;
+    const float v = k < K ? w[(size_t)n * K + k] : 0.f;
+    const int kk = k & 63;
+    *reinterpret_cast<bf16*>(sb + (k >> 6) * (BN * 128) + n * 128 + ((((kk >> 3) ^ (n & 7))) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(v);
+  }
+  for (int i = threadIdx.x; i < BM * (KP - K); i += TN_THREADS) {
+    const int r = i % BM, k = K + i / BM;
+    const int kk = k & 63;
+    *reinterpret_cast<bf16*>(sa + (k >> 6) * A_BYTES + r * 128 + ((((kk >> 3) ^ (r & 7))) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(0.f);
+  }
+  const int MT = (p.M + BM - 1) / BM;
+  constexpr uint32_t idesc = make_idesc(BN, false, false);
+  int it = 0;
+  for (int t = blockIdx.x; t < MT; t += gridDim.x, ++it) {
+    const int m0 = t * BM;
+    // ---- build the im2col tile: (row, lead) pairs, rows fastest (neighbouring threads read neighbouring samples) ----
+    for (int i = threadIdx.x; i < BM * Cl; i += TN_THREADS) {
+      const int r = i % BM, lead = i / BM;
+      const int m = m0 + r;
+      float v[7];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) v[j] = 0.f;
+      if (m < p.M) {
+        const int b = m / p.o_pitch, pos = m - b * p.o_pitch;
+        if (pos >= 1 && pos <= p.o_len) {
+          const float* src = x + ((size_t)b * Cl + lead) * L;
+          const int s0 = 2 * (pos - 1) - 3;
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {
+            const int sidx = s0 + j;
+            if (sidx >= 0 && sidx < L) v[j] = __ldg(src + sidx);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        const int k = lead * 7 + j, kk = k & 63;
+        *reinterpret_cast<bf16*>(sa + (k >> 6) * A_BYTES + r * 128 + ((((kk >> 3) ^ (r & 7))) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(v[j]);
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+    __syncthreads();
+    if (warp == 1) {
+      if (lane == 0) {
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+        for (int kc = 0; kc < KP / 16; ++kc) {
+          const int ch = kc >> 2, k4 = kc & 3;
+          umma_bf16(tmem_base, make_smem_desc(a0 + ch * A_BYTES + k4 * 32, 0, 1024),
+                    make_smem_desc(b0 + ch * (BN * 128) + k4 * 32, 0, 1024), idesc, (uint32_t)(kc != 0));
+        }
+        umma_commit(done);
+      }
+    } else if (warp >= 2) {
+      tn_epilogue<BN, STATS, false, 0>(p, out, tmem_base, done, (uint32_t)(it & 1), nullptr, ep_scale, red, m0, 0, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();     // accumulator drained, operand tile free
+    tc_fence_after();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+template <int BN> constexpr int smem_stem_bytes(int nchunk) { return nchunk * (A_BYTES + BN * 128) + 8 + 16 + 12 * BN * 4 + 1024 + 64; }
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1257,6 +1364,44 @@ int ssb_sm100_prepare() {
     ssb_set_error("ssb_sm100_prepare: %s", cudaGetErrorString(e));
     return SSB_ERR_CUDA;
   }
+  return SSB_OK;
+}
+
+// stem conv on the tensor cores (bf16 output); 0 = launched, 1 = shape not covered (caller keeps the direct kernel)
+int ssb_stem_conv_fwd_sm100(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g, double* stats, cudaStream_t st) {
+  static const bool on = !(getenv("SSB_STEM_TC") && atoi(getenv("SSB_STEM_TC")) == 0);
+  if (!on || Cl < 2 || (g.C != 64 && g.C != 128)) return 1;
+  const int KP = (7 * Cl + 15) / 16 * 16;
+  const int nchunk = (KP + 63) / 64;
+  TnParams p = {};
+  p.M = g.B * g.pitch;
+  p.N = g.C;
+  p.K = KP;
+  p.o_mul = 1;
+  p.o_off = 0;
+  p.o_rows = p.M;
+  p.o_pitch = g.pitch;
+  p.o_len = g.len;
+  p.accumulate = 0;
+  p.stats = stats;
+  const int mt = ceil_div(p.M, BM);
+  cudaError_t e = cudaSuccess;
+#define SSB_STEM_TC_LAUNCH(BN_, ST_)                                                                                          \
+  {                                                                                                                           \
+    const int smem = smem_stem_bytes<BN_>(nchunk);                                                                            \
+    e = cudaFuncSetAttribute(stem_tn_kernel<BN_, ST_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                    \
+    dim3 grid(mt < 2 * g_num_sms ? mt : 2 * g_num_sms);                                                                       \
+    if (e == cudaSuccess)                                                                                                     \
+      ssb_launch_pro(stem_tn_kernel<BN_, ST_>, dim3(grid), dim3(TN_THREADS), smem, st, x, w, (bf16*)y, p, Cl, L, KP);         \
+  }
+  if (g.C == 128) { if (stats) SSB_STEM_TC_LAUNCH(128, true) else SSB_STEM_TC_LAUNCH(128, false) }
+  else { if (stats) SSB_STEM_TC_LAUNCH(64, true) else SSB_STEM_TC_LAUNCH(64, false) }
+#undef SSB_STEM_TC_LAUNCH
+  if (e != cudaSuccess) {
+    ssb_set_error("ssb_stem_conv_fwd: %s", cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+  }
+  SSB_LAUNCH_CHECK("stem_tn_kernel");
   return SSB_OK;
 }
 
