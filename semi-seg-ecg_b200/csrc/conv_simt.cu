@@ -560,6 +560,7 @@ int ssb_conv1d_wgrad_sm100(const void* x, const void* dy, float* dw, ssb_geom gi
 
 int ssb_conv1d_fwd_bnf_fits_sm100(ssb_geom gin, ssb_geom gout, int k, int stride);
 int ssb_stem_conv_fwd_sm100(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g, double* stats, cudaStream_t st);
+int ssb_stem_conv_wgrad_sm100(const float* x, const void* dy, float* dw, int Cl, int L, ssb_geom g, cudaStream_t st);
 
 int ssb_simt_prepare() {
   const int big = 96 * 1024;
@@ -819,6 +820,10 @@ int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L
   int rc = check_stem("ssb_stem_conv_wgrad", Cl, L, g);
   if (rc) return rc;
   SSB_REQUIRE(x && dy && dw, "ssb_stem_conv_wgrad: null pointer");
+  if (dtype == SSB_BF16) {   // multi-lead stems: tensor cores (conv_sm100.cu: stem_wgrad_tn_kernel)
+    const int tc = ssb_stem_conv_wgrad_sm100(x, dy, dw, Cl, L, g, to_stream(stream));
+    if (tc <= 0) return tc;
+  }
   {   // single lead: register-tile kernel streaming dy from L2 (two leads were measured slower than the tiled kernel)
     const int V = dtype == SSB_BF16 ? 8 : 4;
     const int ncg = g.C / V;

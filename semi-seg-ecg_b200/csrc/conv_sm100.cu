@@ -1076,6 +1076,140 @@ stem_tn_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* _
   if (warp == 1) tmem_dealloc<BN>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem weight gradient of multi-lead inputs on the tensor cores:  dW[co][k] += sum_rows dY[row][co] * A[row][k],
+// k = lead * 7 + tap.  Same operand roles as conv_wgrad_kernel (both MN-major, reduction over rows, split over rows across
+// CTAs): the accumulator has the 7*leads <= 112 im2col columns on its lanes and the stem channels on its columns; dY
+// tiles come by TMA, the im2col tile [64 rows][128 columns] is built in shared memory from the fp32 NCL input like in
+// stem_tn_kernel.  Epilogue: the accumulator is transposed through shared memory so that each output channel's 7*leads
+// contiguous gradients go out as 16-byte vector REDs (scalar REDs when 7*leads is not a multiple of 4).
+// The CUDA-core kernel took 173 us at 32+32 x 12 x 5000 (ncu), ~51 % of the remaining stem time.
+// ---------------------------------------------------------------------------------------------
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+stem_wgrad_tn_kernel(const float* __restrict__ x, const __grid_constant__ CUtensorMap tmDY, float* __restrict__ dw, int Cl, int L,
+                     int M, int pitch, int len, int blocks_per_split) {
+  constexpr int B_BYTES = BN * BK * 2;
+  constexpr int X_BYTES = 2 * BK * 128;           // [2 atoms of 64 columns][64 rows][128 B]
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);
+  uint8_t* sa = smem_raw + (((base + 1023u) & ~1023u) - base);
+  uint8_t* sb = sa + X_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sb + B_BYTES);
+  uint64_t* mma_done = full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_done + 1);
+  float* stage = reinterpret_cast<float*>(tmem_slot + 4);     // [32 channels][132] transposed accumulator chunk
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = 7 * Cl;
+  const int nblk_total = (M + BK - 1) / BK;
+  const int blk0 = blockIdx.x * blocks_per_split;
+  const int blk1 = min(nblk_total, blk0 + blocks_per_split);
+  const int iters = blk1 - blk0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    mbar_init(full, 1);
+    mbar_init(mma_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<BN>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  if (iters > 0) {
+    // pad columns K .. 127 of the im2col tile: zero, once
+    for (int i = threadIdx.x; i < BK * (128 - K); i += NTHREADS) {
+      const int r = i % BK, k = K + i / BK;
+      const int kk = k & 63;
+      *reinterpret_cast<bf16*>(sa + (k >> 6) * (BK * 128) + r * 128 + ((((kk >> 3) ^ (r & 7))) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(0.f);
+    }
+    constexpr uint32_t idesc = make_idesc(BN, true, true);
+    for (int it = 0; it < iters; ++it) {
+      const int r0 = (blk0 + it) * BK;
+      if (warp == 0 && lane == 0) {
+        mbar_expect_tx(full, B_BYTES);
+#pragma unroll
+        for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * (BK * 128), &tmDY, full, b * 64, r0);
+      }
+      for (int i = threadIdx.x; i < BK * Cl; i += NTHREADS) {
+        const int r = i % BK, lead = i / BK;
+        const int m = r0 + r;
+        float v[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) v[j] = 0.f;
+        if (m < M) {
+          const int b = m / pitch, pos = m - b * pitch;
+          if (pos >= 1 && pos <= len) {
+            const float* src = x + ((size_t)b * Cl + lead) * L;
+            const int s0 = 2 * (pos - 1) - 3;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+              const int sidx = s0 + j;
+              if (sidx >= 0 && sidx < L) v[j] = __ldg(src + sidx);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          const int k = lead * 7 + j, kk = k & 63;
+          *reinterpret_cast<bf16*>(sa + (k >> 6) * (BK * 128) + r * 128 + ((((kk >> 3) ^ (r & 7))) << 4) + (kk & 7) * 2) = __float2bfloat16_rn(v[j]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (warp == 1 && lane == 0) {
+        mbar_wait(full, (uint32_t)(it & 1));
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sb);
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 16; ++k4)
+          umma_bf16(tmem_base, make_smem_desc(a0 + k4 * 2048, BK * 128, 1024), make_smem_desc(b0 + k4 * 2048, BK * 128, 1024), idesc,
+                    (uint32_t)((it | k4) != 0));
+        umma_commit(mma_done);
+      }
+      mbar_wait(mma_done, (uint32_t)(it & 1));     // the MMAs have read both tiles: they may be overwritten
+    }
+    // ---- epilogue: lanes = im2col columns k, TMEM columns = channels; transposed through shared memory ----
+    tc_fence_after();
+    const bool vec = (K & 3) == 0;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (warp >= 2) {
+        const int q = warp & 3;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        tmem_ld_wait();
+        const int k = q * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[j * 132 + k] = __uint_as_float(r[j]);
+      }
+      __syncthreads();
+      if (vec) {
+        const int nv = K / 4;
+        for (int i = threadIdx.x; i < 32 * nv; i += NTHREADS) {
+          const int j = i / nv, v4 = i - j * nv;
+          const float* sp_ = stage + j * 132 + v4 * 4;
+          float* dst = dw + (size_t)(c + j) * K + v4 * 4;
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sp_[0]), "f"(sp_[1]), "f"(sp_[2]),
+                       "f"(sp_[3]) : "memory");
+        }
+      } else {
+        for (int i = threadIdx.x; i < 32 * K; i += NTHREADS) {
+          const int j = i / K, k = i - j * K;
+          atomicAdd(dw + (size_t)(c + j) * K + k, stage[j * 132 + k]);
+        }
+      }
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN>(tmem_base);
+}
+
+template <int BN> constexpr int smem_stem_wgrad_bytes() { return 2 * BK * 128 + BN * BK * 2 + 16 + 16 + 32 * 132 * 4 + 1024 + 64; }
+
 template <int BN> constexpr int smem_stem_bytes(int nchunk) { return nchunk * (A_BYTES + BN * 128) + 8 + 16 + 12 * BN * 4 + 1024 + 64; }
 
 // ---------------------------------------------------------------------------------------------
@@ -1402,6 +1536,36 @@ int ssb_stem_conv_fwd_sm100(const float* x, const float* w, void* y, int Cl, int
     return SSB_ERR_CUDA;
   }
   SSB_LAUNCH_CHECK("stem_tn_kernel");
+  return SSB_OK;
+}
+
+// stem weight gradient on the tensor cores; 0 = launched, 1 = shape not covered (caller keeps the CUDA-core kernel)
+int ssb_stem_conv_wgrad_sm100(const float* x, const void* dy, float* dw, int Cl, int L, ssb_geom g, cudaStream_t st) {
+  static const bool on = !(getenv("SSB_STEM_TC") && atoi(getenv("SSB_STEM_TC")) == 0);
+  if (!on || Cl < 2 || (g.C != 64 && g.C != 128)) return 1;
+  const int M = g.B * g.pitch;
+  const int nblk = ceil_div(M, BK);
+  int ns = pick_splits(1, nblk, 1, 12);
+  const int bps = ceil_div(nblk, ns);
+  ns = ceil_div(nblk, bps);
+  CUtensorMap tmDY;
+  int rc = make_map(&tmDY, dy, g.C, M, g.C, 64, BK);
+  if (rc) return rc;
+  cudaError_t e;
+  if (g.C == 128) {
+    e = cudaFuncSetAttribute(stem_wgrad_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_stem_wgrad_bytes<128>());
+    if (e == cudaSuccess)
+      ssb_launch_pro(stem_wgrad_tn_kernel<128>, dim3(ns), dim3(NTHREADS), smem_stem_wgrad_bytes<128>(), st, x, tmDY, dw, Cl, L, M, g.pitch, g.len, bps);
+  } else {
+    e = cudaFuncSetAttribute(stem_wgrad_tn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_stem_wgrad_bytes<64>());
+    if (e == cudaSuccess)
+      ssb_launch_pro(stem_wgrad_tn_kernel<64>, dim3(ns), dim3(NTHREADS), smem_stem_wgrad_bytes<64>(), st, x, tmDY, dw, Cl, L, M, g.pitch, g.len, bps);
+  }
+  if (e != cudaSuccess) {
+    ssb_set_error("ssb_stem_conv_wgrad: %s", cudaGetErrorString(e));
+    return SSB_ERR_CUDA;
+  }
+  SSB_LAUNCH_CHECK("stem_wgrad_tn_kernel");
   return SSB_OK;
 }
 
