@@ -325,15 +325,20 @@ def run_b200(args):
 
     def timed(batches, steps, read_each_step):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per = [torch.cuda.Event(enable_timing=True) for _ in range(steps)] if os.environ.get("SSB_BENCH_PERSTEP") else None
         sync_all()
         ev0.record()
         for i in range(steps):
             step_from(batches[i % pool])
-            if read_each_step:
-                pass  # eng.step() already enqueues the asynchronous D2H copy of the loss sums
+            if per is not None:
+                per[i].record()
         ev1.record()
         sync_all()
         ms = ev0.elapsed_time(ev1)
+        if per is not None and rank == 0:      # development: where a short timed region spends its time
+            ts = [ev0.elapsed_time(e_) for e_ in per]
+            print("per-step end times (ms):", " ".join(f"{t:.3f}" for t in ts[:24]), "| deltas:",
+                  " ".join(f"{b - a:.3f}" for a, b in zip([0.0] + ts[:23], ts[:24])), file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

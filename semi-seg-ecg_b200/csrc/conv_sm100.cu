@@ -263,9 +263,6 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
   }
-  mbar_wait(done, done_parity);
-  if (threadIdx.x == 64) SSB_MARK();   // accumulator complete (MMAs retired)
-  tc_fence_after();
   const int row = q * 32 + lane;
   const int m = m0 + row;
   const long long orow = (long long)p.o_mul * m + p.o_off;
@@ -274,6 +271,27 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
   constexpr bool DUAL = STATS && EPI;
   const bool eval_row = !DUAL || m >= p.split_row;    // this thread's row takes the EPI transform
   bf16* optr = ((DUAL && eval_row) ? p.out2 : out) + (size_t)(in_range ? orow : 0) * p.N + n0;
+  // RED: the operands of the BatchNorm-backward reduce (y for the ReLU mask, x for xhat[, x_res]) are requested NOW, while
+  // the main loop still runs -- as first written they were loaded chunk by chunk after the accumulator, two dependent L2
+  // round trips per 32 columns on the critical tail of the kernel (measured slower than a separate reduce launch)
+  constexpr int NCHK = CH / 32;                          // 32-column chunks of this warp's column half
+  constexpr int PF = REDC ? (NCHK <= 2 ? NCHK : 2) : 0;  // chunks whose operands are held in registers
+  uint4 pf_y[PF > 0 ? PF : 1][4], pf_x[PF > 0 ? PF : 1][4], pf_r[(PF > 0 && RED == 2) ? PF : 1][4];
+  if (REDC && valid) {
+#pragma unroll
+    for (int ch = 0; ch < PF; ++ch) {
+      const size_t roff = (size_t)orow * p.N + n0 + cbeg + ch * 32;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        pf_y[ch][v] = *reinterpret_cast<const uint4*>(p.red_y + roff + v * 8);
+        pf_x[ch][v] = *reinterpret_cast<const uint4*>(p.red_x + roff + v * 8);
+        if (RED == 2) pf_r[ch][v] = *reinterpret_cast<const uint4*>(p.red_xr + roff + v * 8);
+      }
+    }
+  }
+  mbar_wait(done, done_parity);
+  if (threadIdx.x == 64) SSB_MARK();   // accumulator complete (MMAs retired)
+  tc_fence_after();
   // all MMAs have retired: the operand stages are free, stage 0 of A is reused as reduction scratch
   float* red = scratch;   // [4 warps][2][BN]
 #pragma unroll 1
@@ -330,16 +348,18 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
       for (int i = 0; i < 32; ++i) sv[i] = 0.f;
     }
     if (REDC) {
-      // g = dx * (y > 0); per-column sums of g and g * xhat over this tile's rows, 32 columns at a time:
-      // warp transpose-reduce -> 4 warps combined through a small scratch -> fp64 atomics
+      // g = dx * (y > 0); per-column sums of g and g * xhat over this tile's rows, 32 columns at a time: warp
+      // transpose-reduce into the scratch (one warp per (lane quadrant, column)); combined and added after the loop
+      const int ci = (c - cbeg) >> 5;
       const size_t roff = (size_t)(in_range ? orow : 0) * p.N + n0 + c;
+      constexpr int NQR = RED == 2 ? 3 : 2;
       float t[32];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         float fy[8];
         if (valid) {
           Vec<bf16> vy;
-          vy.raw = *reinterpret_cast<const uint4*>(p.red_y + roff + v * 8);
+          vy.raw = ci < PF ? pf_y[ci < PF ? ci : 0][v] : *reinterpret_cast<const uint4*>(p.red_y + roff + v * 8);
           vy.get(fy);
         }
 #pragma unroll
@@ -349,13 +369,13 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
         }
       }
       warp_transpose_sum(t, lane);
-      red[half * 384 + (q * 3 + 0) * 32 + lane] = t[0];
+      red[(q * NQR + 0) * BN + c + lane] = t[0];
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         float fx[8];
         if (valid) {
           Vec<bf16> vx;
-          vx.raw = *reinterpret_cast<const uint4*>(p.red_x + roff + v * 8);
+          vx.raw = ci < PF ? pf_x[ci < PF ? ci : 0][v] : *reinterpret_cast<const uint4*>(p.red_x + roff + v * 8);
           vx.get(fx);
         }
 #pragma unroll
@@ -363,14 +383,14 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
           t[v * 8 + i] = valid ? sv[v * 8 + i] * ((fx[i] - ep_scale[c + v * 8 + i]) * ep_scale[BN + c + v * 8 + i]) : 0.f;
       }
       warp_transpose_sum(t, lane);
-      red[half * 384 + (q * 3 + 1) * 32 + lane] = t[0];
+      red[(q * NQR + 1) * BN + c + lane] = t[0];
       if (RED == 2) {
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           float fx[8];
           if (valid) {
             Vec<bf16> vx;
-            vx.raw = *reinterpret_cast<const uint4*>(p.red_xr + roff + v * 8);
+            vx.raw = ci < PF ? pf_r[(ci < PF && RED == 2) ? ci : 0][v] : *reinterpret_cast<const uint4*>(p.red_xr + roff + v * 8);
             vx.get(fx);
           }
 #pragma unroll
@@ -378,26 +398,8 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
             t[v * 8 + i] = valid ? sv[v * 8 + i] * ((fx[i] - ep_scale[2 * BN + c + v * 8 + i]) * ep_scale[3 * BN + c + v * 8 + i]) : 0.f;
         }
         warp_transpose_sum(t, lane);
-        red[half * 384 + (q * 3 + 2) * 32 + lane] = t[0];
+        red[(q * NQR + 2) * BN + c + lane] = t[0];
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const int eh = q * 32 + lane;   // 0..127 inside this column half
-      if (eh < 32 * (RED == 2 ? 3 : 2)) {
-        const int which = eh >> 5, col = eh & 31;
-        const float* rh = red + half * 384;
-        const float a = (rh[(0 * 3 + which) * 32 + col] + rh[(1 * 3 + which) * 32 + col]) +
-                        (rh[(2 * 3 + which) * 32 + col] + rh[(3 * 3 + which) * 32 + col]);
-        const int gc = n0 + c + col;
-        if (which == 0) {
-          atomicAdd(&p.red_sums[gc], (double)a);
-          if (RED == 2) atomicAdd(&p.red_sums_r[gc], (double)a);
-        } else if (which == 1) {
-          atomicAdd(&p.red_sums[p.N + gc], (double)a);
-        } else {
-          atomicAdd(&p.red_sums_r[p.N + gc], (double)a);
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     if (STATS) {
       float sq[32];
@@ -415,6 +417,23 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
     mbar_arrive(release);
   }
   if (threadIdx.x == 64) SSB_MARK();     // tile stored
+  if (REDC) {
+    constexpr int NQR = RED == 2 ? 3 : 2;
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
+    for (int col = e; col < BN; col += EPI_THREADS) {
+      float a[NQR];
+#pragma unroll
+      for (int wh = 0; wh < NQR; ++wh) a[wh] = (red[(0 * NQR + wh) * BN + col] + red[(1 * NQR + wh) * BN + col]) +
+                                               (red[(2 * NQR + wh) * BN + col] + red[(3 * NQR + wh) * BN + col]);
+      const int gc = n0 + col;
+      atomicAdd(&p.red_sums[gc], (double)a[0]);
+      atomicAdd(&p.red_sums[p.N + gc], (double)a[1]);
+      if (RED == 2) {
+        atomicAdd(&p.red_sums_r[gc], (double)a[0]);
+        atomicAdd(&p.red_sums_r[p.N + gc], (double)a[2]);
+      }
+    }
+  }
   if (STATS) {
     asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps only
     for (int col = e; col < BN; col += EPI_THREADS) {
@@ -597,7 +616,7 @@ constexpr int A3_SLOTS = 3;
 template <int BN> __host__ __device__ constexpr int b3_slots() { return BN == 256 ? 5 : (BN == 128 ? 8 : 9); }
 template <int BN> constexpr int smem3_bytes() {
   return A3_SLOTS * A3_BYTES + b3_slots<BN>() * BN * 128 + (2 * A3_SLOTS + 2 * b3_slots<BN>() + 4) * 8 + 16 + 4 * BN * 4 +
-         (8 * BN < 768 ? 768 : 8 * BN) * 4 + 1024;
+         (12 * BN < 768 ? 768 : 12 * BN) * 4 + 1024;
 }
 
 // PERSISTENT: gridDim.x CTAs walk the tile list (m fastest, so that CTAs running together share the weight
