@@ -648,10 +648,10 @@ def other_algorithm_rates(cfg, dev, dtype, C, L, Bl, Bu, batch, steps=100):
     return out
 
 
-def large_batch_roofline(peaks, workload="fixmatch_resnet18w128_12x5000_b32+32"):
+def large_batch_roofline(peaks, workload="fixmatch_resnet18w128_12x5000_b64+64"):
     """Supplementary evidence (not the bench value): the same kernels on BASELINE.json configs[4]'s shapes
-    (12 x 5000, base width 128, 32+32 strips on this GPU), where the convs are tensor-bound instead of
-    latency-bound.  Same steady-state per-launch timing as the main roofline entry."""
+    (12 x 5000, base width 128, 64+64 strips on this GPU = global batch 1024 on 8 GPUs), where the convs are
+    tensor-bound instead of latency-bound.  Same steady-state per-launch timing as the main roofline entry."""
     from algorithms.base import init_model_from_cfg
     from semiseg_b200 import _lib
     from semiseg_b200.trainer import get_engine
@@ -676,6 +676,7 @@ def large_batch_roofline(peaks, workload="fixmatch_resnet18w128_12x5000_b32+32")
     if tb:
         out["tensor_bound_convs"] = {"launches_per_step": sum(n for _, n, _, _, _ in tb), "tflops": round(tfl / (tus * 1e-6) / 1e12, 1),
                                      "frac_of_peak": round(tfl / (tus * 1e-6) / 1e12 / peaks["bf16_tflops"], 4),
+                                     "frac_of_sustained_peak": round(tfl / (tus * 1e-6) / 1e12 / peaks["bf16_tflops_sustained"], 4),
                                      "best": {"kernel": best[0], "tflops": round(best[3] / (best[2] * 1e-6) / 1e12, 1)}}
     del eng, model
     torch.cuda.empty_cache()

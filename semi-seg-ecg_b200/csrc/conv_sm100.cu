@@ -616,7 +616,8 @@ constexpr int A3_SLOTS = 3;
 template <int BN> __host__ __device__ constexpr int b3_slots() { return BN == 256 ? 5 : (BN == 128 ? 8 : 9); }
 template <int BN> constexpr int smem3_bytes() {
   return A3_SLOTS * A3_BYTES + b3_slots<BN>() * BN * 128 + (2 * A3_SLOTS + 2 * b3_slots<BN>() + 4) * 8 + 16 + 4 * BN * 4 +
-         (12 * BN < 768 ? 768 : 12 * BN) * 4 + 1024;
+         ((BN == 256 ? 8 : 12) * BN < 768 ? 768 : (BN == 256 ? 8 : 12) * BN) * 4 + 1024;   // scratch: [4][2 | 3][BN] floats (three quantities:
+                                                                                       // RED == 2, never launched with 256-wide tiles)
 }
 
 // PERSISTENT: gridDim.x CTAs walk the tile list (m fastest, so that CTAs running together share the weight
@@ -1277,6 +1278,13 @@ int make_map(CUtensorMap* map, const void* base, long long inner, long long oute
 constexpr int TN_STAGES = 4;
 constexpr int WG_STAGES = 4;
 
+// every opt-in shared-memory size must fit the 227 KB a CTA can have (cudaFuncSetAttribute fails at ssb_prepare otherwise --
+// which no CPU-side build step notices)
+constexpr int SMEM_MAX = 227 * 1024;
+static_assert(smem3_bytes<64>() <= SMEM_MAX && smem3_bytes<128>() <= SMEM_MAX && smem3_bytes<256>() <= SMEM_MAX, "conv_tn3 smem");
+static_assert(smem_bytes<128 * BK * 2, TN_STAGES>() <= SMEM_MAX && smem_bytes<128 * BK * 2, WG_STAGES>() <= SMEM_MAX, "conv_tn / wgrad smem");
+static_assert(smem_wg3_bytes<128>() <= SMEM_MAX && smem_stem_bytes<128>(2) <= SMEM_MAX && smem_stem_wgrad_bytes<128>() <= SMEM_MAX, "wgrad3 / stem smem");
+
 int g_num_sms = 148;
 
 template <int BN, bool B_MN>
@@ -1398,7 +1406,7 @@ int run_tn(const void* a_base, long long a_inner, long long a_outer, long long a
     // widest tile that still gives every SM a CTA
     const int mt = ceil_div(p.M, BM);
     int BN = 64;
-    if (p.N % 256 == 0 && (long long)mt * (p.N / 256) >= 148) BN = 256;
+    if (p.N % 256 == 0 && (long long)mt * (p.N / 256) >= g_num_sms && !p.red_xr) BN = 256;   // (RED == 2 needs 12 x BN floats of scratch)
     else if (p.N % 128 == 0) BN = 128;
     rc = make_map(&tmA, a_base, a_inner, a_outer, a_pitch, BK, A3_ROWS);
     if (rc) return rc;
@@ -1656,7 +1664,7 @@ int ssb_conv1d_fwd_bnf_fits_sm100(ssb_geom gin, ssb_geom gout, int k, int stride
   const int mt = ceil_div(M, BM);
   if (stride == 1 && k == 3 && g_tn3 && K >= 128) {
     int BN = 64;
-    if (N % 256 == 0 && (long long)mt * (N / 256) >= 148) BN = 256;
+    if (N % 256 == 0 && (long long)mt * (N / 256) >= g_num_sms) BN = 256;
     else if (N % 128 == 0) BN = 128;
     return mt * (N / BN) <= g_num_sms ? 1 : 0;
   }
