@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restric
 // group for all its rows, so the per-channel coefficients live in registers: no shared memory,
 // no barrier, and the data loads are in flight while the coefficients are being computed.
 // ---------------------------------------------------------------------------------------
-template <typename T, int RES>
+template <typename T, int RES, bool SYNC>
 __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
                                                                 T* __restrict__ y, ssb_bn bn, ssb_bn bnr,
                                                                 ssb_geom g, int relu, int train, int cgpc, int rpb) {
@@ -115,11 +115,11 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restr
       const double inv_n = 1.0 / n;
       const bool writer = blockIdx.x == 0;
       float a, b;
-      bn_coeffs(bn, c, C, train, inv_n, n, writer, a, b);
+      bn_coeffs<SYNC>(bn, c, C, train, inv_n, n, writer, a, b);
       sCo[0][threadIdx.x] = a;
       sCo[1][threadIdx.x] = b;
       if (RES == 2) {
-        bn_coeffs(bnr, c, C, train, inv_n, n, writer, a, b);
+        bn_coeffs<SYNC>(bnr, c, C, train, inv_n, n, writer, a, b);
         sCo[2][threadIdx.x] = a;
         sCo[3][threadIdx.x] = b;
       }
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_act_fwd_kernel(const T* __restr
 // max-pool tie rule), or 3 when the maximum is <= 0 (the ReLU kills the gradient there), so the
 // backward pass routes gradients without recomputing the windows.
 // ---------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool SYNC>
 __global__ void __launch_bounds__(BN_THREADS) stem_bn_relu_pool_kernel(const T* __restrict__ c0, T* __restrict__ y,
                                                                        uint8_t* __restrict__ arg, ssb_bn bn,
                                                                        ssb_geom gi, ssb_geom go, int train) {
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bn_relu_pool_kernel(const T* 
   const double n = (double)gi.B * (double)gi.len * (double)(bn.count_mul > 1 ? bn.count_mul : 1);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float sc, sh;
-    bn_coeffs(bn, c, C, train, 1.0 / n, n, blockIdx.x == 0, sc, sh);
+    bn_coeffs<SYNC>(bn, c, C, train, 1.0 / n, n, blockIdx.x == 0, sc, sh);
     sScale[c] = sc;
     sShift[c] = sh;
   }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_reduce_kernel(const T* __re
 // RES: 0 none; 1 identity residual -> g_ident = g; 2 residual BN -> dx_res
 // same decomposition as bn_act_fwd_kernel: per-channel constants in registers.
 // ---------------------------------------------------------------------------------------
-template <typename T, bool HAS_G2, bool HAS_Y, int RES>
+template <typename T, bool HAS_G2, bool HAS_Y, int RES, bool SYNC>
 __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __restrict__ g1, const T* __restrict__ g2,
                                                                   const T* __restrict__ y, const T* __restrict__ x,
                                                                   const T* __restrict__ xr, T* __restrict__ dx,
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
       const bool writer = blockIdx.x == 0;
       const float mean_ = bn.mean_invstd[c], inv_ = bn.mean_invstd[C + c];
       double sb[2] = {bn.bwd_sums[c], bn.bwd_sums[C + c]};
-      if (bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here
+      if (SYNC && bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here
         const unsigned int ix[2] = {bn.sync_bwd_off + (unsigned int)c, bn.sync_bwd_off + (unsigned int)(C + c)};
         sbx_allsum<2>(bn, ix, sb, writer);
       }
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_apply_kernel(const T* __res
       if (RES == 2) {
         const float meanr = bnr.mean_invstd[c], invr = bnr.mean_invstd[C + c];
         double sr[1] = {bnr.bwd_sums[C + c]};
-        if (bnr.sync_peers) {
+        if (SYNC && bnr.sync_peers) {
           const unsigned int ix[1] = {bnr.sync_bwd_off + (unsigned int)(C + c)};
           sbx_allsum<1>(bnr, ix, sr, writer);
         }
@@ -510,7 +510,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 #define BWF_UR 4       // rows per trip of the row loops (all loads of a trip are in flight together)
 #define BWF_REP 8      // replicated accumulators: block b adds into replica b % 8 (8x less same-address contention)
 
-template <typename T, bool HAS_Y, int RES>
+template <typename T, bool HAS_Y, int RES, bool SYNC>
 __global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(const T* __restrict__ g1, const T* __restrict__ y,
                                                                   const T* __restrict__ x, const T* __restrict__ xr,
                                                                   T* __restrict__ dx, T* __restrict__ dxr, T* __restrict__ gid,
@@ -621,7 +621,8 @@ __global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(cons
   // ---- pass 2: apply; per-channel constants from the now complete sums (one thread per channel) ----
   // The operands of the first trip are requested BEFORE the constants are worked out: the second read (L2) then runs
   // under the reload of the sums, the fp64 arithmetic and -- with SyncBN -- the exchange of the sums with the peers.
-  constexpr int PU = RES == 2 ? 0 : (HAS_Y ? 1 : 2);   // rows requested early (more does not fit 128 registers next to the exchange)
+  // (only where an exchange follows: at N = 1 the early requests made the kernel SLOWER, 8.05 -> 8.4 us in isolation)
+  constexpr int PU = !SYNC ? 0 : (RES == 2 ? 0 : (HAS_Y ? 1 : 2));   // rows requested early (more does not fit 128 registers next to the exchange)
   constexpr int PA = PU > 0 ? PU : 1;
   Vec<T> pg[PA], px[PA], py[PA], pr[PA];
   bool pok[PA];
@@ -651,7 +652,7 @@ __global__ void __launch_bounds__(BN_THREADS, BWF_MINB) bn_bwd_fused_kernel(cons
         sgx += __ldcg(&rep[k * rep_stride + C + c]);
         if (RES == 2) sgxr += __ldcg(&rep_r[k * rep_stride + C + c]);
       }
-      if (bn.sync_peers) {      // SyncBN: this rank's sums are complete (grid barrier above) -- totals over the ranks
+      if (SYNC && bn.sync_peers) {      // SyncBN: this rank's sums are complete (grid barrier above) -- totals over the ranks
         double sb[2] = {sg, sgx};
         const unsigned int ix[2] = {bn.sync_bwd_off + (unsigned int)c, bn.sync_bwd_off + (unsigned int)(C + c)};
         sbx_allsum<2>(bn, ix, sb, writer);
@@ -1071,7 +1072,7 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bwd_reduce_kernel(const T* __
   }
 }
 
-template <typename T>
+template <typename T, bool SYNC>
 __global__ void __launch_bounds__(BN_THREADS) stem_bwd_apply_kernel(const T* __restrict__ gp, const T* __restrict__ c0,
                                                                     const uint8_t* __restrict__ arg, T* __restrict__ dc0,
                                                                     ssb_bn bn, ssb_geom gi, ssb_geom go) {
@@ -1092,7 +1093,7 @@ __global__ void __launch_bounds__(BN_THREADS) stem_bwd_apply_kernel(const T* __r
     sInv[c] = inv;
     sScale[c] = bn.gamma[c] * inv;
     double sb[2] = {bn.bwd_sums[c], bn.bwd_sums[C + c]};
-    if (bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here
+    if (SYNC && bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here
       const unsigned int ix[2] = {bn.sync_bwd_off + (unsigned int)c, bn.sync_bwd_off + (unsigned int)(C + c)};
       sbx_allsum<2>(bn, ix, sb, blockIdx.x == 0);
     }
@@ -1189,12 +1190,12 @@ static bool bwd_fused_plan(const ssb_geom& g, int mode, bool has_y, int* cgpc_o,
   const int rpp = BN_THREADS / cgpc;
   int occ = 0;
   cudaError_t oe = cudaSuccess;
-  if (mode == 0) oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 0>, BN_THREADS, 0)
-                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 0>, BN_THREADS, 0);
-  else if (mode == 1) oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 1>, BN_THREADS, 0)
-                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 1>, BN_THREADS, 0);
-  else oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 2>, BN_THREADS, 0)
-                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 2>, BN_THREADS, 0);
+  if (mode == 0) oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 0, false>, BN_THREADS, 0)
+                            : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 0, false>, BN_THREADS, 0);
+  else if (mode == 1) oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 1, false>, BN_THREADS, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 1, false>, BN_THREADS, 0);
+  else oe = has_y ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, true, 2, false>, BN_THREADS, 0)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_fused_kernel<T, false, 2, false>, BN_THREADS, 0);
   if (oe != cudaSuccess) occ = 0;
   // co-resident capacity with one block per SM left as slack; the rows are spread over at most that many blocks
   // (measured at config 2: 216 blocks -- this cap at 3 blocks per SM -- 0.700 ms per step; 148 blocks 0.716; 324 blocks
@@ -1274,13 +1275,23 @@ static cudaError_t launch_cluster(Kern kern, int nblocks, int cl, cudaStream_t s
                  (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, cp.cgpc, cp.rows_per_cta)
 #define SSB_BWC_NR(Y, R) (cp.nr == 6 ? SSB_BWC(Y, R, 6) : SSB_BWC(Y, R, 12))
 
-#define SSB_BWF(Y, R)                                                                                                          \
-  ssb_launch(bn_bwd_fused_kernel<T, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)y, (const T*)x,       \
+#define SSB_BWF_S(Y, R, S)                                                                                                     \
+  ssb_launch(bn_bwd_fused_kernel<T, Y, R, S>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)y, (const T*)x,    \
              (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, cgpc, rpb, barrier, rep, rep_r, (long long)rep_stride)
+#define SSB_BWF(Y, R)                                    \
+  do {                                                   \
+    if (bn->sync_peers) SSB_BWF_S(Y, R, true);           \
+    else SSB_BWF_S(Y, R, false);                         \
+  } while (0)
 #define SSB_RED(G2, Y, R) \
   ssb_launch(bn_bwd_reduce_kernel<T, G2, Y, R>, dim3(grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, *bn, br, rows, g.C, rpb)
-#define SSB_APP(G2, Y, R) \
-  ssb_launch(bn_bwd_apply_kernel<T, G2, Y, R>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, eg.cgpc, eg.rpb)
+#define SSB_APP_S(G2, Y, R, S) \
+  ssb_launch(bn_bwd_apply_kernel<T, G2, Y, R, S>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)g1, (const T*)g2, (const T*)y, (const T*)x, (const T*)x_res, (T*)dx, (T*)dx_res, (T*)g_ident, *bn, br, g, eg.cgpc, eg.rpb)
+#define SSB_APP(G2, Y, R)                                  \
+  do {                                                     \
+    if (bn->sync_peers) SSB_APP_S(G2, Y, R, true);         \
+    else SSB_APP_S(G2, Y, R, false);                       \
+  } while (0)
 
 extern "C" {
 
@@ -1314,11 +1325,14 @@ int ssb_bn_act_fwd(const void* x, const ssb_bn* bn, const void* res, const ssb_b
     const EwGeom eg = ew_geom(g.B * g.pitch, g.C / Vec<T>::N, Vec<T>::N);
     cudaStream_t st = to_stream(stream);
     if (mode == 0)
-      ssb_launch(bn_act_fwd_kernel<T, 0>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, nullptr, (T*)y, *bn, kNoBn, g, relu, train, eg.cgpc, eg.rpb);
+      if (bn->sync_peers) ssb_launch(bn_act_fwd_kernel<T, 0, true>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, nullptr, (T*)y, *bn, kNoBn, g, relu, train, eg.cgpc, eg.rpb);
+      else ssb_launch(bn_act_fwd_kernel<T, 0, false>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, nullptr, (T*)y, *bn, kNoBn, g, relu, train, eg.cgpc, eg.rpb);
     else if (mode == 1)
-      ssb_launch(bn_act_fwd_kernel<T, 1>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, (const T*)res, (T*)y, *bn, kNoBn, g, relu, train, eg.cgpc, eg.rpb);
+      if (bn->sync_peers) ssb_launch(bn_act_fwd_kernel<T, 1, true>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, (const T*)res, (T*)y, *bn, kNoBn, g, relu, train, eg.cgpc, eg.rpb);
+      else ssb_launch(bn_act_fwd_kernel<T, 1, false>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, (const T*)res, (T*)y, *bn, kNoBn, g, relu, train, eg.cgpc, eg.rpb);
     else
-      ssb_launch(bn_act_fwd_kernel<T, 2>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, (const T*)res, (T*)y, *bn, *bn_res, g, relu, train, eg.cgpc, eg.rpb);
+      if (bn->sync_peers) ssb_launch(bn_act_fwd_kernel<T, 2, true>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, (const T*)res, (T*)y, *bn, *bn_res, g, relu, train, eg.cgpc, eg.rpb);
+      else ssb_launch(bn_act_fwd_kernel<T, 2, false>, dim3(eg.grid), dim3(BN_THREADS), 0, st, (const T*)x, (const T*)res, (T*)y, *bn, *bn_res, g, relu, train, eg.cgpc, eg.rpb);
   })
   SSB_LAUNCH_CHECK("ssb_bn_act_fwd");
   return SSB_OK;
@@ -1336,7 +1350,8 @@ int ssb_stem_bn_relu_pool_fwd(const void* c0, const ssb_bn* bn, void* y, uint8_t
   const size_t smem = (size_t)2 * gin.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
     const long long total = (long long)gout.B * gout.pitch * (gout.C / Vec<T>::N);
-    ssb_launch(stem_bn_relu_pool_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)c0, (T*)y, arg, *bn, gin, gout, train);
+    if (bn->sync_peers) ssb_launch(stem_bn_relu_pool_kernel<T, true>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)c0, (T*)y, arg, *bn, gin, gout, train);
+    else ssb_launch(stem_bn_relu_pool_kernel<T, false>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)c0, (T*)y, arg, *bn, gin, gout, train);
   })
   SSB_LAUNCH_CHECK("ssb_stem_bn_relu_pool_fwd");
   return SSB_OK;
@@ -1493,7 +1508,8 @@ int ssb_stem_bwd_apply(const void* gp, const void* c0, const uint8_t* arg, const
   const size_t smem = (size_t)6 * gin.C * sizeof(float);
   SSB_DISPATCH_DTYPE(dtype, T, {
     const long long total = (long long)gin.B * gin.pitch * (gin.C / Vec<T>::N);
-    ssb_launch(stem_bwd_apply_kernel<T>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)gp, (const T*)c0, arg, (T*)dc0, *bn, gin, gout);
+    if (bn->sync_peers) ssb_launch(stem_bwd_apply_kernel<T, true>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)gp, (const T*)c0, arg, (T*)dc0, *bn, gin, gout);
+    else ssb_launch(stem_bwd_apply_kernel<T, false>, dim3(ew_blocks(total)), dim3(BN_THREADS), smem, to_stream(stream), (const T*)gp, (const T*)c0, arg, (T*)dc0, *bn, gin, gout);
   })
   SSB_LAUNCH_CHECK("ssb_stem_bwd_apply");
   return SSB_OK;

@@ -291,12 +291,15 @@ __device__ __forceinline__ void sbx_allsum(const ssb_bn& bn, const unsigned int 
 }
 
 // per-channel affine coefficients: y = x*scale + shift
+// SYNC: compiled into the SyncBN instantiations only -- the exchange costs registers, and the elementwise kernels around
+// it lose occupancy if every instantiation carries it (measured: +15 us per step at N = 1)
+template <bool SYNC = false>
 __device__ __forceinline__ void bn_coeffs(const ssb_bn& bn, int c, int C, int train, double inv_n, double n,
                                           bool writer, float& scale, float& shift) {
   float mean, invstd;
   if (train) {
     double st[2] = {__ldcg(&bn.sums[c]), __ldcg(&bn.sums[C + c])};   // (L2 read: the sums may have been completed by other blocks of this launch)
-    if (bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here (the writer block publishes this rank's sums)
+    if (SYNC && bn.sync_peers) {      // SyncBN: totals over the ranks, exchanged here (the writer block publishes this rank's sums)
       const unsigned int ix[2] = {bn.sync_fwd_off + (unsigned int)c, bn.sync_fwd_off + (unsigned int)(C + c)};
       sbx_allsum<2>(bn, ix, st, writer);
     }

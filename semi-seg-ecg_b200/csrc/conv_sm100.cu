@@ -294,11 +294,15 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
   tc_fence_after();
   // all MMAs have retired: the operand stages are free, stage 0 of A is reused as reduction scratch
   float* red = scratch;   // [4 warps][2][BN]
-#pragma unroll 1
-  for (int c = cbeg; c < cend; c += 32) {
+  // (RED: fully unrolled, so that the prefetched operand arrays are indexed by constants and stay in registers)
+  constexpr int UNR = REDC ? NCHK : 1;
+#pragma unroll UNR
+  for (int ci = 0; ci < NCHK; ++ci) {
+    const int c = cbeg + ci * 32;
     uint32_t r[32];
     tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
     tmem_ld_wait();
+    if (REDC && threadIdx.x == 64) SSB_MARK();   // chunk in registers
     float sv[32];
     if (in_range && !(!valid && p.accumulate)) {
       uint4* dst = reinterpret_cast<uint4*>(optr + c);
@@ -347,10 +351,10 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
 #pragma unroll
       for (int i = 0; i < 32; ++i) sv[i] = 0.f;
     }
+    if (REDC && threadIdx.x == 64) SSB_MARK();     // chunk stored
     if (REDC) {
       // g = dx * (y > 0); per-column sums of g and g * xhat over this tile's rows, 32 columns at a time: warp
       // transpose-reduce into the scratch (one warp per (lane quadrant, column)); combined and added after the loop
-      const int ci = (c - cbeg) >> 5;
       const size_t roff = (size_t)(in_range ? orow : 0) * p.N + n0 + c;
       constexpr int NQR = RED == 2 ? 3 : 2;
       float t[32];
@@ -400,6 +404,7 @@ __device__ __forceinline__ void tn_epilogue(const TnParams& p, bf16* __restrict_
         warp_transpose_sum(t, lane);
         red[(q * NQR + 2) * BN + c + lane] = t[0];
       }
+      if (threadIdx.x == 64) SSB_MARK();           // chunk reduced
     }
     if (STATS) {
       float sq[32];
