@@ -172,12 +172,13 @@ def run_epoch(algorithm: str, model, teacher, labeled_loader: Iterable, unlabele
             print(f"Epoch: [{epoch}]  [{it + 1}/{num_steps}]  lr: {lr:.6f}  " +
                   "  ".join(f"{k}: {v / max(count, 1):.4f}" for k, v in sums.items()) +
                   f"  time: {dt / (it + 1):.4f}  max mem: {torch.cuda.max_memory_allocated() / 2 ** 20:.0f}")
-    if eng is not None:
-        drain(num_steps - 1)
+    # (host-side bookkeeping first, the blocking read of the last steps' loss sums after it: the GPU is still working)
     step_t = torch.tensor(float(model.runtime().state.step))
     for p in optimizer.state.values():
         if isinstance(p, dict) and "step" in p:
             p["step"] = step_t
+    if eng is not None:
+        drain(num_steps - 1)
     stats = {k: v / max(count, 1) for k, v in sums.items()}
     stats["lr"] = lr_sum / max(num_steps, 1)      # the reference returns each meter's global average (fixmatch.py:188-192)
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
