@@ -259,9 +259,11 @@ def load_traffic(workload):
     return t.get(workload)
 
 
-def _finish(world):
-    """Multi-rank teardown: destroying an NCCL communicator while CUDA graphs that captured collectives
-    on it are still alive can hang, so synchronise, barrier and leave without the destructor."""
+def _finish(world, engines=()):
+    """Multi-rank teardown.  Round 1 left with os._exit(0) because destroying the NCCL communicator while CUDA graphs that
+    captured collectives on it were alive could hang.  Now: synchronise, barrier, RESET the captured graphs (they hold the
+    communicator's work), then destroy the process group -- with a 15 s watchdog that falls back to os._exit(0), so a
+    teardown problem can never turn into a hung benchmark."""
     if world > 1:
         import torch.distributed as dist
         torch.cuda.synchronize()
@@ -269,7 +271,20 @@ def _finish(world):
         torch.cuda.synchronize()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        guard = threading.Timer(15.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
+        try:
+            for e in engines:
+                for name in ("graph", "pseudo_graph"):
+                    g = getattr(e, name, None)
+                    if g is not None:
+                        g.reset()
+                        setattr(e, name, None)
+            torch.cuda.synchronize()
+            dist.destroy_process_group()
+        finally:
+            guard.cancel()
 
 
 def run_b200(args):
@@ -368,7 +383,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         if rank == 0:
             print(json.dumps({"profile_mode": True, "steps": args.steps, "launches_per_step": eng.launches_per_step}), flush=True)
-        _finish(world)
+        _finish(world, [eng])
         return
     sampler = ClockSampler(local)
     if rank == 0:
@@ -521,7 +536,7 @@ def run_b200(args):
                "what": "FixMatchBatcher.load (weak Fourier resize-crop + labels, RandAugment 3 of 4 ops, standardise x3) from raw "
                        "strips resident in HBM into the engine's input arena; host makes only the scalar draws"}
     if rank != 0:
-        _finish(world)
+        _finish(world, list(model.runtime().engines.values()))
         return
     # working set, to justify the L2 policy
     plan = eng.plan_s
@@ -574,7 +589,7 @@ def run_b200(args):
     if world == 1 and not args.no_aug and args.workload == DEFAULT_WORKLOAD:
         line["other_algorithms"] = other_algorithm_rates(cfg, dev, dtype, C, L, Bl, Bu, host[0])
     print(json.dumps(line), flush=True)
-    _finish(world)
+    _finish(world, list(model.runtime().engines.values()))
 
 
 def other_algorithm_rates(cfg, dev, dtype, C, L, Bl, Bu, batch, steps=100):

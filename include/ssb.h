@@ -149,6 +149,11 @@ int ssb_memset_zero(void* p, size_t bytes, ssb_stream_t stream);
  * weight; y: flat padded NLC, geometry g (g.len = floor((L-1)/2)+1, g.C = Cs). */
 int ssb_stem_conv_fwd(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g,
                       int dtype, ssb_stream_t stream);
+/* the same conv with the train-mode BatchNorm statistics of its output (sums[2*Cs] += sum y, sum y^2 of the stored
+ * values: what ssb_bn_stats computes) out of the same launch where the tensor-core kernel covers the shape (bf16, Cs in
+ * {64, 128}); otherwise the conv followed by the statistics pass */
+int ssb_stem_conv_fwd_stats(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g, double* sums,
+                            int dtype, ssb_stream_t stream);
 /* dw[Cs][Cl][7] (fp32) += sum_{b,t} dy * x   (conv backward w.r.t. weight; the stem has no dgrad) */
 int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L, ssb_geom g,
                         int dtype, ssb_stream_t stream);

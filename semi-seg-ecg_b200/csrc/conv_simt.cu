@@ -815,6 +815,22 @@ int ssb_stem_conv_fwd(const float* x, const float* w, void* y, int Cl, int L, ss
   return SSB_OK;
 }
 
+int ssb_bn_stats(const void* x, ssb_geom g, double* sums, int dtype, ssb_stream_t stream);
+
+int ssb_stem_conv_fwd_stats(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g, double* sums, int dtype,
+                            ssb_stream_t stream) {
+  int rc = check_stem("ssb_stem_conv_fwd_stats", Cl, L, g);
+  if (rc) return rc;
+  SSB_REQUIRE(x && w && y && sums, "ssb_stem_conv_fwd_stats: null pointer");
+  if (dtype == SSB_BF16) {   // tensor-core kernel: statistics in its epilogue (also at one lead: one launch instead of two)
+    const int tc = ssb_stem_conv_fwd_sm100(x, w, y, Cl, L, g, sums, to_stream(stream));
+    if (tc <= 0) return tc;
+  }
+  rc = ssb_stem_conv_fwd(x, w, y, Cl, L, g, dtype, stream);
+  if (rc) return rc;
+  return ssb_bn_stats(y, g, sums, dtype, stream);
+}
+
 int ssb_stem_conv_wgrad(const float* x, const void* dy, float* dw, int Cl, int L, ssb_geom g, int dtype,
                         ssb_stream_t stream) {
   int rc = check_stem("ssb_stem_conv_wgrad", Cl, L, g);

@@ -1536,7 +1536,9 @@ int ssb_sm100_prepare() {
 // stem conv on the tensor cores (bf16 output); 0 = launched, 1 = shape not covered (caller keeps the direct kernel)
 int ssb_stem_conv_fwd_sm100(const float* x, const float* w, void* y, int Cl, int L, ssb_geom g, double* stats, cudaStream_t st) {
   static const bool on = !(getenv("SSB_STEM_TC") && atoi(getenv("SSB_STEM_TC")) == 0);
-  if (!on || Cl < 2 || (g.C != 64 && g.C != 128)) return 1;
+  // (one lead: the CUDA-core kernel is at the launch floor already -- the tensor-core kernel only pays when it also
+  //  delivers the statistics, i.e. replaces two launches)
+  if (!on || (Cl < 2 && !stats) || (g.C != 64 && g.C != 128)) return 1;
   const int KP = (7 * Cl + 15) / 16 * 16;
   const int nchunk = (KP + 63) / 64;
   TnParams p = {};

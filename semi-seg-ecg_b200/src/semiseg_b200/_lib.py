@@ -67,6 +67,7 @@ SIGNATURES = {
     "ssb_prepare": [],
     "ssb_memset_zero": [_P, _SZ, _P],
     "ssb_stem_conv_fwd": [_P, _P, _P, _I, _I, Geom, _I, _P],
+    "ssb_stem_conv_fwd_stats": [_P, _P, _P, _I, _I, Geom, _P, _I, _P],
     "ssb_stem_conv_wgrad": [_P, _P, _P, _I, _I, Geom, _I, _P],
     "ssb_conv1d_fwd": [_P, _P, _P, Geom, Geom, _I, _I, _I, _I, _P],
     "ssb_conv1d_fwd_stats": [_P, _P, _P, Geom, Geom, _I, _I, _P, _I, _I, _P],

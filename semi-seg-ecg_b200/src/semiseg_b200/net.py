@@ -619,10 +619,14 @@ class NetPlan:
         t = 1 if tm else 0
         if tm and zero:
             self.zero_stats(st)
-        call("ssb_stem_conv_fwd", x.data_ptr(), self.w.w_ptr(lay.stem_conv), self.c0.data_ptr(), spec.num_leads,
-             self.L, self.g_stem, dt, st)
-        if tm:
-            self._stats(self.c0, self.g_stem, lay.stem_bn, st)
+        if tm:      # conv + the BatchNorm statistics of its output (one launch on the tensor-core path)
+            call("ssb_stem_conv_fwd_stats", x.data_ptr(), self.w.w_ptr(lay.stem_conv), self.c0.data_ptr(), spec.num_leads,
+                 self.L, self.g_stem, self._bn_structs[lay.stem_bn.prefix].sums, dt, st)
+            if self.sync_hook is not None:
+                self.sync_hook(self.sums[lay.stem_bn.soff: lay.stem_bn.soff + 2 * lay.stem_bn.C])
+        else:
+            call("ssb_stem_conv_fwd", x.data_ptr(), self.w.w_ptr(lay.stem_conv), self.c0.data_ptr(), spec.num_leads,
+                 self.L, self.g_stem, dt, st)
         call("ssb_stem_bn_relu_pool_fwd", self.c0.data_ptr(), self.bn(lay.stem_bn), self.p0.data_ptr(),
              self.pool_arg.data_ptr() if tm else None, self.g_stem, self.g_pool, t, dt, st)
         h, gin = self.p0, self.g_pool

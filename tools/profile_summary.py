@@ -31,10 +31,11 @@ def launches(src, dst, note):
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, data = rows[hi], rows[hi + 1:]
     ki, vi, gi, bi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+    mi = hdr.index("Metric Name")
     d = collections.defaultdict(list)
     grids = collections.defaultdict(set)
     for r in data:
-        if len(r) <= vi:
+        if len(r) <= vi or r[mi] != "gpu__time_duration.sum":      # (a pass may carry more metrics per launch)
             continue
         name = r[ki].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
         d[name].append(float(r[vi].replace(",", "")))
