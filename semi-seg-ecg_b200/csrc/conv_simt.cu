@@ -822,7 +822,7 @@ int ssb_stem_conv_fwd_stats(const float* x, const float* w, void* y, int Cl, int
   int rc = check_stem("ssb_stem_conv_fwd_stats", Cl, L, g);
   if (rc) return rc;
   SSB_REQUIRE(x && w && y && sums, "ssb_stem_conv_fwd_stats: null pointer");
-  if (dtype == SSB_BF16) {   // tensor-core kernel: statistics in its epilogue (also at one lead: one launch instead of two)
+  if (dtype == SSB_BF16) {   // multi-lead stems: tensor-core kernel with the statistics in its epilogue
     const int tc = ssb_stem_conv_fwd_sm100(x, w, y, Cl, L, g, sums, to_stream(stream));
     if (tc <= 0) return tc;
   }

@@ -150,7 +150,7 @@ def test_stem_bench_shapes(leads, L, cs, B, dtype):
     call("ssb_stem_conv_fwd", x.data_ptr(), w.data_ptr(), yb.data_ptr(), leads, L, g, dtype, st())
     assert rel_err(from_flat(yb, B, po, Lo), yr.detach()) < tol
     assert halo_is_zero(yb, B, po, Lo)
-    # the same conv with the BatchNorm statistics of its output (one launch on the tensor-core path, also at one lead)
+    # the same conv with the BatchNorm statistics of its output (one launch on the multi-lead tensor-core path, two at one lead)
     yb2 = torch.full((B * po, cs), 3.0, dtype=tdt, device=DEV)
     sums = torch.zeros(2 * cs, dtype=torch.float64, device=DEV)
     call("ssb_stem_conv_fwd_stats", x.data_ptr(), w.data_ptr(), yb2.data_ptr(), leads, L, g, sums.data_ptr(), dtype, st())
