@@ -324,6 +324,13 @@ int ssb_eval_metrics(const float* low, const int64_t* target, double* sums, int3
 int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, size_t n,
                   double beta1, double beta2, double eps, double weight_decay,
                   const ssb_step_params* sp, ssb_stream_t stream);
+/* the same update with gradient clipping (loss_scaler(..., clip_grad=max_norm), misc.py:242-250 ->
+ * torch.nn.utils.clip_grad_norm_): gradients are multiplied by min(1, max_norm / (norm + 1e-6)), norm = gnorm[0] *
+ * sp->grad_scale with gnorm (DEVICE, from ssb_grad_norm over the WHOLE arena) the norm of the stored gradients.
+ * gnorm == NULL: no clipping. */
+int ssb_adamw_ema_clip(float* p, const float* g, float* m, float* v, float* p_ema, size_t n,
+                       double beta1, double beta2, double eps, double weight_decay,
+                       const ssb_step_params* sp, const float* gnorm, double max_norm, ssb_stream_t stream);
 /* dst = dst*d + src*(1-d) (teacher BN buffers); d from sp->ema_decay */
 int ssb_ema(float* dst, const float* src, size_t n, const ssb_step_params* sp, ssb_stream_t stream);
 /* teacher num_batches_tracked quirk: dst_f32[i] = dst_f32[i]*d + (float)src_i64[i]*(1-d) */

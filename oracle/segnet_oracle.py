@@ -436,9 +436,18 @@ class OracleTrainer:
         kw = self.cfg.get("optimizer_kwargs", {}) or {}
         betas = tuple(kw.get("betas", (0.9, 0.999)))
         eps = kw.get("eps", 1e-8)
+        # clip_grad=max_norm (fixmatch.py:129-136 -> misc.py:248-250, torch.nn.utils.clip_grad_norm_): every gradient times
+        # min(1, max_norm / (global L2 norm + 1e-6)); self.grads keeps the UNCLIPPED gradients (the returned norm is theirs)
+        max_norm = self.cfg.get("max_norm", None)
+        coef = 1.0
+        if max_norm is not None:
+            total = math.sqrt(sum(float((sdg[k].grad.double() ** 2).sum()) for k in self.pnames))
+            coef = min(1.0, float(max_norm) / (total + 1e-6))
         for k in self.pnames:
             g = sdg[k].grad
             self.grads[k] = g.detach().clone()
+            if max_norm is not None:
+                g = g * coef
             adamw_update(self.sd[k], g, self.m[k], self.v[k], self.t, lr, betas, eps,
                          self.cfg["weight_decay"])
 

@@ -8,14 +8,17 @@
 __global__ void __launch_bounds__(256)
 adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  float* __restrict__ pe, size_t n4, float beta1, float omb1, float beta2, float omb2, float eps,
-                 float wd, const ssb_step_params* __restrict__ sp) {
+                 float wd, const ssb_step_params* __restrict__ sp, const float* __restrict__ gnorm, float max_norm) {
   pdl_trigger();
   pdl_wait();
   const float lr = sp->lr;
   const float step_size = lr * sp->inv_bias1;
   const float isb2 = sp->inv_sqrt_bias2;
   const float decay = 1.0f - lr * wd;
-  const float gs = sp->grad_scale;
+  float gs = sp->grad_scale;
+  // torch.nn.utils.clip_grad_norm_ (misc.py:248-250): gradients times min(1, max_norm / (total_norm + 1e-6)); gnorm holds
+  // the norm of the arena as stored, i.e. before grad_scale
+  if (gnorm) gs *= fminf(1.0f, max_norm / (gnorm[0] * gs + 1e-6f));
   const float d = sp->ema_decay;
   const int first = sp->ema_first;
   float4* p4 = reinterpret_cast<float4*>(p);
@@ -101,13 +104,20 @@ extern "C" {
 
 int ssb_adamw_ema(float* p, const float* g, float* m, float* v, float* p_ema, size_t n, double beta1, double beta2,
                   double eps, double weight_decay, const ssb_step_params* sp, ssb_stream_t stream) {
+  return ssb_adamw_ema_clip(p, g, m, v, p_ema, n, beta1, beta2, eps, weight_decay, sp, nullptr, 0.0, stream);
+}
+
+int ssb_adamw_ema_clip(float* p, const float* g, float* m, float* v, float* p_ema, size_t n, double beta1, double beta2,
+                       double eps, double weight_decay, const ssb_step_params* sp, const float* gnorm, double max_norm,
+                       ssb_stream_t stream) {
   SSB_REQUIRE(p && g && m && v && sp, "ssb_adamw_ema: null pointer");
+  SSB_REQUIRE(!gnorm || max_norm > 0.0, "ssb_adamw_ema_clip: max_norm must be positive (got %g)", max_norm);
   SSB_REQUIRE(n > 0 && n % 4 == 0, "ssb_adamw_ema: arena length %zu must be a positive multiple of 4", n);
   const size_t n4 = n / 4;
   long long blocks = ceil_div_ll((long long)n4, 256 * 2);
   if (blocks > 148 * 8) blocks = 148 * 8;
   ssb_launch(adamw_ema_kernel, dim3((int)blocks), dim3(256), 0, to_stream(stream), p, g, m, v, p_ema, n4, (float)beta1, (float)(1.0 - beta1), (float)beta2,
-                                                                (float)(1.0 - beta2), (float)eps, (float)weight_decay, sp);
+                                                                (float)(1.0 - beta2), (float)eps, (float)weight_decay, sp, gnorm, (float)max_norm);
   SSB_LAUNCH_CHECK("ssb_adamw_ema");
   return SSB_OK;
 }

@@ -96,6 +96,7 @@ SIGNATURES = {
     "ssb_pseudo_label": [_P, _F, _P, _P, _P, _I, _I, _I, _P],
     "ssb_semi_loss": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P, _P, _P],
     "ssb_adamw_ema": [_P, _P, _P, _P, _P, _SZ, _D, _D, _D, _D, _P, _P],
+    "ssb_adamw_ema_clip": [_P, _P, _P, _P, _P, _SZ, _D, _D, _D, _D, _P, _P, _D, _P],
     "ssb_ema": [_P, _P, _SZ, _P, _P],
     "ssb_ema_i64": [_P, _P, _SZ, _P, _P],
     "ssb_grad_norm": [_P, _SZ, _P, _P, _P],

@@ -393,13 +393,21 @@ class StepEngine:
         # after the backward (a 17 us optimizer pass over the whole arena used to sit at the end of the critical path).
         pe_base = self.teacher.params.data_ptr() if self.algorithm == "mean_teacher" else None
 
+        # max_norm (loss_scaler(..., clip_grad=max_norm), fixmatch.py:129-136 -> clip_grad_norm_, misc.py:248-250): the
+        # global norm of the exchanged gradients first, then every range's update scales by min(1, max_norm/(norm+1e-6))
+        max_norm = self.cfg.get("max_norm", None)
+
         def adamw(lo, hi, stream_ptr):
-            call("ssb_adamw_ema", w.params.data_ptr() + 4 * lo, state.grads.data_ptr() + 4 * lo, state.exp_avg.data_ptr() + 4 * lo,
-                 state.exp_avg_sq.data_ptr() + 4 * lo, (pe_base + 4 * lo) if pe_base else None, hi - lo, self.beta1, self.beta2,
-                 self.eps, self.wd, self.sp_dev.data_ptr(), stream_ptr)
+            args = (w.params.data_ptr() + 4 * lo, state.grads.data_ptr() + 4 * lo, state.exp_avg.data_ptr() + 4 * lo,
+                    state.exp_avg_sq.data_ptr() + 4 * lo, (pe_base + 4 * lo) if pe_base else None, hi - lo, self.beta1,
+                    self.beta2, self.eps, self.wd, self.sp_dev.data_ptr())
+            if max_norm is not None:
+                call("ssb_adamw_ema_clip", *args, self.gnorm.data_ptr(), float(max_norm), stream_ptr)
+            else:
+                call("ssb_adamw_ema", *args, stream_ptr)
 
         split = None
-        want_norm = bool(self.cfg.get("grad_norm", False))
+        want_norm = bool(self.cfg.get("grad_norm", False)) or max_norm is not None
         if self.comm_stream is not None:
             lay = self.plan_s.lay
             nst = len(self.spec.stage_blocks)

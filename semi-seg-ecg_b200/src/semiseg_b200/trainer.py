@@ -50,7 +50,8 @@ def get_engine(algorithm: str, model, teacher, Bl: int, Bu: int, L: int, dtype: 
         rt_t = teacher.runtime()
         if not rt_t.quick_ok():
             rt_t.ensure()
-    key = (algorithm, Bl, Bu, L, dtype, use_graph, algo, id(rt_t), bool(getattr(model, "sync_bn", False)), external_pseudo)
+    key = (algorithm, Bl, Bu, L, dtype, use_graph, algo, id(rt_t), bool(getattr(model, "sync_bn", False)), external_pseudo,
+           config.get("max_norm", None))
     eng = rt.engines.get(key)
     if eng is None:
         pg = dist.group.WORLD if (dist.is_available() and dist.is_initialized() and
@@ -102,9 +103,6 @@ def run_epoch(algorithm: str, model, teacher, labeled_loader: Iterable, unlabele
     config = config or {}
     if config.get("accum_iter", 1) != 1:
         raise NotImplementedError("accum_iter > 1 is not supported by the fused step (all shipped configs use 1)")
-    if config.get("max_norm", None) is not None:
-        raise NotImplementedError("gradient clipping (max_norm) is not supported by the fused step "
-                                  "(max_norm is null in every shipped config)")
     if torch.device(device).type != "cuda":
         raise RuntimeError("train_one_epoch: the B200 hot path needs device='cuda' (no CPU fallback)")
     model.train()
@@ -201,8 +199,6 @@ def run_epoch_cps(model_1, model_2, labeled_loader: Iterable, unlabeled_loader: 
     config = config or {}
     if config.get("accum_iter", 1) != 1:
         raise NotImplementedError("accum_iter > 1 is not supported by the fused step (all shipped configs use 1)")
-    if config.get("max_norm", None) is not None:
-        raise NotImplementedError("gradient clipping (max_norm) is not supported by the fused step")
     if torch.device(device).type != "cuda":
         raise RuntimeError("train_one_epoch: the B200 hot path needs device='cuda' (no CPU fallback)")
     model_1.train()

@@ -51,6 +51,13 @@ def golden_arch():
     return np.load(os.path.join(REPO, "tests", "golden", "arch_vectors.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_clip():
+    """case K (FixMatch with max_norm clipping), tests/golden/make_golden_clip.py"""
+    import numpy as np
+    return np.load(os.path.join(REPO, "tests", "golden", "clip_vectors.npz"))
+
+
 def golden_group(g, prefix):
     """{'name': array} for all keys under 'prefix/'."""
     pre = prefix + "/"

@@ -91,6 +91,40 @@ def test_mean_iou_restatement_follows_torchmetrics_semantics():
     assert float(m.compute()) < 0.75        # the absent class contributes a 0 to every sample's class mean
 
 
+def test_mean_iou_known_answers_by_hand():
+    """torchmetrics itself is not installable here, so the aggregation is held to answers worked out BY HAND from the
+    published algorithm (the fractions below are the arithmetic, not output of any code): per sample and class
+    intersection / union with 0 for an empty union, class mean per sample, batch mean per update(), mean of the batch
+    means at compute() -- in the three configurations perf_metrics.py:14-20 can build."""
+    from oracle.eval_oracle import MeanIoU
+    from semiseg_b200.evaluate import aggregate_eval
+    oh = lambda a: torch.nn.functional.one_hot(torch.tensor(a), 3).movedim(-1, 1)   # noqa: E731
+    # batch 1, sample 0: pred 0 0 1 2 / target 0 1 1 2 -> class 0: 1/2, class 1: 1/2, class 2: 1/1
+    #          sample 1: pred 1 1 1 1 / target 1 1 0 0 -> class 0: 0/2, class 1: 2/4, class 2: empty union -> 0
+    # batch 2, sample 0: pred 2 2 0 0 / target 2 0 0 0 -> class 0: 2/3, class 1: empty -> 0, class 2: 1/2
+    b1 = ([[0, 0, 1, 2], [1, 1, 1, 1]], [[0, 1, 1, 2], [1, 1, 0, 0]])
+    b2 = ([[2, 2, 0, 0]], [[2, 0, 0, 0]])
+    want = {
+        (True, False): ((2 / 3 + 1 / 6) / 2 + (2 / 3 + 0 + 1 / 2) / 3) / 2,
+        (False, False): ((3 / 4 + 1 / 4) / 2 + (0 + 1 / 2) / 2) / 2,
+        (True, True): [((1 / 2 + 0) / 2 + 2 / 3) / 2, ((1 / 2 + 1 / 2) / 2 + 0) / 2, ((1 + 0) / 2 + 1 / 2) / 2],
+    }
+    for (bg, pc), w in want.items():
+        m = MeanIoU(3, include_background=bg, per_class=pc)
+        per_batch = []
+        for p, t in (b1, b2):
+            m.update(oh(p), oh(t))
+            P, T = np.array(p), np.array(t)
+            counts = torch.tensor([[[int(((P[i] == c) & (T[i] == c)).sum()), int((P[i] == c).sum()), int((T[i] == c).sum())]
+                                    for c in range(3)] for i in range(len(p))], dtype=torch.int32)
+            per_batch.append((torch.tensor([1.0, 1.0], dtype=torch.float64), counts, len(p)))
+        got = m.compute()
+        assert np.allclose(np.asarray(got, dtype=np.float64), np.asarray(w), atol=1e-12), (bg, pc, got, w)
+        _, md = aggregate_eval(per_batch, include_background=bg, per_class=pc)      # the product's aggregation
+        prod = [md[f"MeanIoU_{i}"] for i in range(3)] if pc else md["MeanIoU"]
+        assert np.allclose(np.asarray(prod), np.asarray(w), atol=1e-12), (bg, pc, prod, w)
+
+
 def test_state_dict_matches_reference_golden(golden):
     from algorithms.base import init_model_from_cfg
     ref = group(golden, "A/init")
