@@ -363,10 +363,18 @@ def run_b200(args):
 
     # pre-roll: bring the GPU out of its idle clocks before the W warm-up steps (a 20-step timed region is 14 ms long; measured
     # 0.726 ms per step over 20 steps right after start-up against 0.694 over 200) -- untimed, stated in config.l2_policy
+    # Every rank must run the SAME number of steps (each step holds collectives: the gradient all-reduce and the SyncBN
+    # exchange, whose mailbox words are tagged with the step count).  N = 1: steps until preroll_s of wall time have passed;
+    # N > 1: a FIXED count (about the same time) -- a per-rank wall-clock loop let the ranks stop at different counts, after
+    # which their collectives were off by one step: the N = 4 run of call c18 hung in exactly that way.
     if not args.profile_mode:
         t_pre = time.time()
         n_pre = 0
-        while time.time() - t_pre < args.preroll_s:
+        # (~1 ms per step at the default workload; scaled by the workload's size -- a function of the config alone, hence
+        #  the same on every rank)
+        rel_work = (Bl + Bu) * L * (WORKLOADS[args.workload][5] / 64.0) ** 2 / (32 * 2500.0)
+        n_fixed = int(min(max(args.preroll_s * 1000.0 / max(rel_work, 1.0), 20), 1000)) if world > 1 else None
+        while (n_pre < n_fixed) if n_fixed is not None else (time.time() - t_pre < args.preroll_s):
             step_from(devb[n_pre % pool])
             n_pre += 1
             if n_pre % 50 == 0:

@@ -175,8 +175,13 @@ class StepEngine:
         peer mapping cannot be set up (or SSB_SYNCBN_FUSED=0): the caller falls back to the per-layer exchange."""
         self.syncbn_p2p = False
         self.syncbn_fused = False
-        if not int(os.environ.get("SSB_SYNCBN_FUSED", "1")) or not int(os.environ.get("SSB_SYNCBN_P2P", "1")) or \
-                self.world < 2 or self.world > 16 or self.merged:
+        # Default: on at world size 2 -- the configuration this path was run and checked on (tools/dp_check.py on two
+        # B200s, bench at N = 2).  At N = 4 / 8 the per-layer exchange launches below are the path with hardware runs
+        # behind them (profiles/r2b_multi_gpu.md); the sweep that was to cover the in-kernel exchange there did not
+        # complete (profiles/r2e_multi_gpu.md), so larger worlds need SSB_SYNCBN_FUSED=1 to opt in.
+        want = os.environ.get("SSB_SYNCBN_FUSED")
+        on = (self.world == 2) if want is None else bool(int(want))
+        if not on or not int(os.environ.get("SSB_SYNCBN_P2P", "1")) or self.world < 2 or self.world > 16 or self.merged:
             return False
         lay = self.plan_s.lay
         slot = 2 * lay.n_sums                      # forward sums | backward sums of every layer
