@@ -53,7 +53,7 @@ def golden_arch():
 
 @pytest.fixture(scope="session")
 def golden_clip():
-    """case K (FixMatch with max_norm clipping), tests/golden/make_golden_clip.py"""
+    """case M (FixMatch with max_norm clipping), tests/golden/make_golden_clip.py"""
     import numpy as np
     return np.load(os.path.join(REPO, "tests", "golden", "clip_vectors.npz"))
 

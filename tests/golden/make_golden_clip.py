@@ -25,7 +25,7 @@ def main():
     seed, nsteps = 7, 3
     torch.manual_seed(seed)
     model = R.base.init_model_from_cfg(G.model_cfg(T["num_leads"], T["stem_channels"], T["base_channels"], T["head_channels"], 0.0))
-    G.put(out, "K/init", G.to_np(model.state_dict()))
+    G.put(out, "M/init", G.to_np(model.state_dict()))
     labl, unll = G.batches(200 + seed, nsteps, T["Bl"], T["Bu"], T["num_leads"], T["L"])
     model.eval()
     with torch.no_grad():
@@ -48,11 +48,11 @@ def main():
 
     stats = R.fixmatch.train_one_epoch(model, labl, unll, opt, torch.device("cpu"), 3, Spy(), None, False, tc)
     assert len(norms) == nsteps and min(norms) > max_norm, norms     # clipping active at every step
-    out["K/conf_thresh"], out["K/max_norm"] = np.float64(thresh), np.float64(max_norm)
-    out["K/epoch"], out["K/nsteps"], out["K/data_seed"] = np.int64(3), np.int64(nsteps), np.int64(200 + seed)
-    out["K/grad_norms"] = np.array(norms)
-    G.put(out, "K/stats", {k: np.float64(v) for k, v in stats.items()})
-    G.put(out, "K/final", G.to_np(model.state_dict()))
+    out["M/conf_thresh"], out["M/max_norm"] = np.float64(thresh), np.float64(max_norm)
+    out["M/epoch"], out["M/nsteps"], out["M/data_seed"] = np.int64(3), np.int64(nsteps), np.int64(200 + seed)
+    out["M/grad_norms"] = np.array(norms)
+    G.put(out, "M/stats", {k: np.float64(v) for k, v in stats.items()})
+    G.put(out, "M/final", G.to_np(model.state_dict()))
     path = os.path.join(HERE, "clip_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; grad norms", norms)

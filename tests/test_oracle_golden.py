@@ -75,25 +75,25 @@ def test_fixmatch_steps_fast_kernels(golden, tag, dropout, monkeypatch):
 
 
 def test_fixmatch_steps_with_gradient_clipping(golden_clip):
-    """case K: the reference's train_one_epoch with max_norm below the run's gradient norms (clip_grad_norm_ active at every
+    """case M: the reference's train_one_epoch with max_norm below the run's gradient norms (clip_grad_norm_ active at every
     step): the oracle's clipped update reproduces the final weights and the norms the reference's scaler returned; the
     unclipped oracle does not (Adam is nearly scale-invariant, so the difference is small but well above the tolerance)."""
     g = golden_clip
-    n, epoch = int(g["K/nsteps"]), int(g["K/epoch"])
-    data = batches(int(g["K/data_seed"]), n, 3, 3, 2, 300)
+    n, epoch = int(g["M/nsteps"]), int(g["M/epoch"])
+    data = batches(int(g["M/data_seed"]), n, 3, 3, 2, 300)
     drift = {}
     for clip in (True, False):
-        cfg = dict(TRAIN_CFG, conf_thresh=float(g["K/conf_thresh"]), max_norm=float(g["K/max_norm"]) if clip else None)
-        tr = O.OracleTrainer(sd_from(g, "K/init"), TINY_ARCH, cfg, dtype=torch.float64)
+        cfg = dict(TRAIN_CFG, conf_thresh=float(g["M/conf_thresh"]), max_norm=float(g["M/max_norm"]) if clip else None)
+        tr = O.OracleTrainer(sd_from(g, "M/init"), TINY_ARCH, cfg, dtype=torch.float64)
         norms = []
         for it, (lab, unl) in enumerate(data):
             tr.fixmatch_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], O.lr_at(it / n + epoch, cfg))
             norms.append(tr.grad_norm())
-        drift[clip] = max(rel_err(tr.sd[name], refv) for name, refv in group(g, "K/final").items()
+        drift[clip] = max(rel_err(tr.sd[name], refv) for name, refv in group(g, "M/final").items()
                           if "num_batches_tracked" not in name)
         if clip:
-            assert np.allclose(norms, g["K/grad_norms"], rtol=2e-4), (norms, g["K/grad_norms"])
-            assert min(norms) > float(g["K/max_norm"])
+            assert np.allclose(norms, g["M/grad_norms"], rtol=2e-4), (norms, g["M/grad_norms"])
+            assert min(norms) > float(g["M/max_norm"])
     assert drift[True] < 1e-4, drift
     assert drift[False] > 10 * drift[True], drift
 
