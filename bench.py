@@ -44,6 +44,14 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "fixmatch_resnet18_ludb_1x2500_b16+16"
 
 
+def preroll_steps(workload, preroll_s):
+    """Untimed steps before the warm-up at N > 1: a function of the CONFIG alone, so every rank runs the same number
+    (each step holds collectives).  ~1 ms per step at the default workload, scaled by the workload's size."""
+    _, _, L, Bl, Bu, base, _ = WORKLOADS[workload]
+    rel_work = (Bl + Bu) * L * (base / 64.0) ** 2 / (32 * 2500.0)
+    return int(min(max(preroll_s * 1000.0 / max(rel_work, 1.0), 20), 1000))
+
+
 def make_host_batch(seed, rank, Bl, Bu, C, L):
     from semiseg_b200 import synthetic
     return synthetic.make_batch(seed * 1000 + rank, Bl, Bu, C, L)
@@ -370,10 +378,7 @@ def run_b200(args):
     if not args.profile_mode:
         t_pre = time.time()
         n_pre = 0
-        # (~1 ms per step at the default workload; scaled by the workload's size -- a function of the config alone, hence
-        #  the same on every rank)
-        rel_work = (Bl + Bu) * L * (WORKLOADS[args.workload][5] / 64.0) ** 2 / (32 * 2500.0)
-        n_fixed = int(min(max(args.preroll_s * 1000.0 / max(rel_work, 1.0), 20), 1000)) if world > 1 else None
+        n_fixed = preroll_steps(args.workload, args.preroll_s) if world > 1 else None
         while (n_pre < n_fixed) if n_fixed is not None else (time.time() - t_pre < args.preroll_s):
             step_from(devb[n_pre % pool])
             n_pre += 1

@@ -161,3 +161,26 @@ def test_bench_rank_sharding_is_disjoint():
     b = bench.make_host_batch(0, 1, 4, 4, 1, 256)
     assert not np.array_equal(a[0]["ecg"], b[0]["ecg"])
     assert np.array_equal(a[0]["ecg"], bench.make_host_batch(0, 0, 4, 4, 1, 256)[0]["ecg"])
+
+
+def test_bench_untimed_steps_do_not_depend_on_the_rank():
+    """Every rank must run the same number of steps around the timed region (each step holds the gradient all-reduce and the
+    SyncBN exchange): bench.py's pre-roll count at N > 1 comes from the workload alone -- no clock, no rank, no environment --
+    and the source has no other wall-clock-bounded loop around engine steps (the N = 4 hang of profiles/r2e_multi_gpu.md)."""
+    import ast
+    import inspect
+    import bench
+    for w in bench.WORKLOADS:
+        n = bench.preroll_steps(w, 0.4)
+        assert 20 <= n <= 1000 and n == bench.preroll_steps(w, 0.4)
+    assert bench.preroll_steps(bench.DEFAULT_WORKLOAD, 0.4) == 400
+    assert set(inspect.signature(bench.preroll_steps).parameters) == {"workload", "preroll_s"}
+    body = ast.parse(inspect.getsource(bench.preroll_steps)).body[0]
+    names = {n.id for n in ast.walk(body) if isinstance(n, ast.Name)} | {n.attr for n in ast.walk(body) if isinstance(n, ast.Attribute)}
+    assert not names & {"time", "rank", "environ", "os", "dist", "torch"}, names
+    # while-loops of bench.main that call the step: the only clock-bounded one is guarded by `n_fixed is not None`
+    tree = ast.parse(inspect.getsource(bench))
+    for node in ast.walk(tree):
+        if isinstance(node, ast.While) and "step_from" in ast.unparse(node):
+            assert "n_fixed" in ast.unparse(node.test), ast.unparse(node.test)
+
