@@ -7,6 +7,7 @@
 
 std::atomic<long long> g_ssb_launches{0};
 int g_ssb_pdl = 2;   // env SSB_PDL: see common.cuh
+int g_ssb_num_sms = 148;
 static thread_local char g_err[512] = "";
 
 void ssb_set_error(const char* fmt, ...) {
@@ -28,6 +29,11 @@ int ssb_prepare(void) {
   if (pdl) g_ssb_pdl = atoi(pdl);
   int rc = ssb_device_check();
   if (rc) return rc;
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      g_ssb_num_sms = sms;
+  }
   if ((rc = ssb_simt_prepare())) return rc;
   if ((rc = ssb_loss_prepare())) return rc;
   if ((rc = ssb_aug_prepare())) return rc;

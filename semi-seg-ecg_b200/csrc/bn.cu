@@ -1201,7 +1201,7 @@ static bool bwd_fused_plan(const ssb_geom& g, int mode, bool has_y, int* cgpc_o,
   // (measured at config 2: 216 blocks -- this cap at 3 blocks per SM -- 0.700 ms per step; 148 blocks 0.716; 324 blocks
   // at a forced 64 registers 0.710)
   static const int slack = getenv("SSB_BWF_SLACK") ? atoi(getenv("SSB_BWF_SLACK")) : 1;
-  const long long cap = occ - slack >= 1 ? 148LL * (occ - slack) : 0;
+  const long long cap = occ - slack >= 1 ? (long long)g_ssb_num_sms * (occ - slack) : 0;
   int nx = cap / ny > 0 ? (int)(cap / ny) : 0;
   const int want = ceil_div(rows, rpp * BWF_ROWS);
   if (nx > want) nx = want;

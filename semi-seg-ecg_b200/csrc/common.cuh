@@ -52,6 +52,9 @@ extern std::atomic<long long> g_ssb_launches;
 // global-memory access, so launch latency / CTA scheduling / on-chip prologues (barrier init,
 // TMEM allocation, tensor-map prefetch) overlap with the predecessor's tail.
 extern int g_ssb_pdl;
+// SM count of the device (ssb_prepare(); 148 = B200 until then): every co-residency bound (grid-barrier kernels, persistent
+// grids) uses it; the plain `148 * k` caps elsewhere are tuning constants of grid-stride loops, correct for any SM count
+extern int g_ssb_num_sms;
 // The dependent grid is released only once this one is past its own wait (measured: releasing at kernel
 // entry lets a whole chain of parked grids pile up and is slower; profiles/r1b_pdl.md).
 #ifndef SSB_TRACE

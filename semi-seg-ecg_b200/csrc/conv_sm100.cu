@@ -1290,7 +1290,7 @@ static_assert(smem3_bytes<64>() <= SMEM_MAX && smem3_bytes<128>() <= SMEM_MAX &&
 static_assert(smem_bytes<128 * BK * 2, TN_STAGES>() <= SMEM_MAX && smem_bytes<128 * BK * 2, WG_STAGES>() <= SMEM_MAX, "conv_tn / wgrad smem");
 static_assert(smem_wg3_bytes<128>() <= SMEM_MAX && smem_stem_bytes<128>(2) <= SMEM_MAX && smem_stem_wgrad_bytes<128>() <= SMEM_MAX, "wgrad3 / stem smem");
 
-int g_num_sms = 148;
+#define g_num_sms g_ssb_num_sms      // (set by ssb_prepare, api.cu)
 
 template <int BN, bool B_MN>
 int launch_tn(const CUtensorMap& tmA, const CUtensorMap& tmB, bf16* out, const TnParams& p, cudaStream_t st) {
@@ -1507,11 +1507,6 @@ int ssb_sm100_prepare() {
   SSB_TN3R_ATTR(64, 1) SSB_TN3R_ATTR(128, 1) SSB_TN3R_ATTR(256, 1) SSB_TN3R_ATTR(64, 2) SSB_TN3R_ATTR(128, 2) SSB_TN3R_ATTR(256, 2)
 #undef SSB_TN3R_ATTR
   if (const char* t3 = getenv("SSB_TN3")) g_tn3 = atoi(t3);
-  {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
-      g_num_sms = sms;
-  }
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(conv_wgrad_kernel<128, WG_STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_bytes<128 * BK * 2, WG_STAGES>());
