@@ -80,7 +80,7 @@ def config_block(workload, world, sync_bn):
             "base_channels": base, "parallelism": f"dp{world}", "sync_bn": bool(sync_bn and world > 1),
             "l2_policy": "no explicit flush: the per-step working set (activations + parameter / gradient / Adam arenas; "
                          "164 MiB at 16+16 x 1 x 2500, reported as working_set_mib) exceeds the 126 MB L2 and the inputs "
-                         "rotate over 4 distinct batches; 0.4 s of untimed steps precede the W warm-up steps (clocks out of idle)"}
+                         "rotate over 4 distinct batches; 0.4 s of untimed steps (N > 1: the same fixed count on every rank) precede the W warm-up steps (clocks out of idle)"}
 
 
 class ClockSampler(threading.Thread):
