@@ -17,29 +17,31 @@ sys.path.insert(0, HERE)
 import make_golden as G  # noqa: E402
 
 
-def main():
-    R = G.import_reference()
-    torch.set_num_threads(4)
-    torch.use_deterministic_algorithms(True)
+def run_case(R, G, seed, nsteps, max_norm):
+    """One clipped FixMatch run of the reference from `seed`; returns (vectors, min |confidence - threshold| over the steps)."""
+    from oracle import segnet_oracle as O
+    sys.path.insert(0, os.path.join(G.REPO, "tests"))
+    from helpers import TINY_ARCH, TRAIN_CFG            # the oracle-side twins of model_cfg / train_cfg below
     out, T = {}, G.TINY
-    seed, nsteps = 7, 3
     torch.manual_seed(seed)
     model = R.base.init_model_from_cfg(G.model_cfg(T["num_leads"], T["stem_channels"], T["base_channels"], T["head_channels"], 0.0))
     G.put(out, "M/init", G.to_np(model.state_dict()))
+    init_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
     labl, unll = G.batches(200 + seed, nsteps, T["Bl"], T["Bu"], T["num_leads"], T["L"])
     model.eval()
     with torch.no_grad():
-        conf = model(unll[0]["ecg"])["seg_logits"].softmax(1).max(1)[0]
-    thresh = float(np.round(conf.median().item(), 3))
-    max_norm = 0.25
+        conf = np.sort(model(unll[0]["ecg"])["seg_logits"].softmax(1).max(1)[0].flatten().double().numpy())
+    a, b = int(0.35 * len(conf)), int(0.65 * len(conf))          # threshold = middle of the widest gap around the median
+    j = int(np.argmax(conf[a + 1:b] - conf[a:b - 1])) + a
+    thresh = float(np.round(0.5 * (conf[j] + conf[j + 1]), 6))
     tc = G.train_cfg(conf_thresh=thresh, max_norm=max_norm)
     opt = R.optimizer.get_optimizer_from_config(tc, model.parameters())
     scaler = R.misc.NativeScalerWithGradNormCount()
     norms = []
 
     class Spy:                      # records the norm the reference's scaler returns (the norm BEFORE clipping)
-        def __call__(self, *a, **k):
-            n = scaler(*a, **k)
+        def __call__(self, *a_, **k):
+            n = scaler(*a_, **k)
             norms.append(float(n))
             return n
 
@@ -47,15 +49,41 @@ def main():
             return getattr(scaler, k)
 
     stats = R.fixmatch.train_one_epoch(model, labl, unll, opt, torch.device("cpu"), 3, Spy(), None, False, tc)
-    assert len(norms) == nsteps and min(norms) > max_norm, norms     # clipping active at every step
     out["M/conf_thresh"], out["M/max_norm"] = np.float64(thresh), np.float64(max_norm)
     out["M/epoch"], out["M/nsteps"], out["M/data_seed"] = np.int64(3), np.int64(nsteps), np.int64(200 + seed)
     out["M/grad_norms"] = np.array(norms)
     G.put(out, "M/stats", {k: np.float64(v) for k, v in stats.items()})
     G.put(out, "M/final", G.to_np(model.state_dict()))
+    # how far is the nearest confidence from the threshold at each step?  (fp64 replay by the oracle: a pseudo-label
+    # decision within rounding of the threshold would make the fixture a coin toss for any fp32 implementation)
+    cfg = dict(TRAIN_CFG, conf_thresh=thresh, max_norm=max_norm)
+    tr = O.OracleTrainer(init_sd, TINY_ARCH, cfg, dtype=torch.float64)
+    margin = 1.0
+    for it in range(nsteps):
+        lab, unl = labl[it], unll[it]
+        with torch.no_grad():
+            z = O.forward(tr.sd, unl["ecg"].double(), TINY_ARCH, False)["seg_logits"]
+            margin = min(margin, float((z.softmax(1).max(1)[0] - np.float32(thresh).astype(np.float64)).abs().min()))
+        tr.fixmatch_step(lab["ecg"], lab["target"], unl["ecg"], unl["ecg_aug"], O.lr_at(it / nsteps + 3, cfg))
+    return out, norms, margin
+
+
+def main():
+    R = G.import_reference()
+    torch.set_num_threads(4)
+    torch.use_deterministic_algorithms(True)
+    nsteps, max_norm = 3, 0.25
+    for seed in range(7, 60):       # first seed whose every pseudo-label decision is >= 2e-4 away from the threshold
+        out, norms, margin = run_case(R, G, seed, nsteps, max_norm)
+        print(f"seed {seed}: grad norms {norms}, min |conf - thresh| {margin:.2e}")
+        if margin >= 2e-4 and len(norms) == nsteps and min(norms) > max_norm:      # clipping active at every step
+            break
+    else:
+        raise SystemExit("no seed with a comfortable margin")
+    out["M/model_seed"], out["M/min_margin"] = np.int64(seed), np.float64(margin)
     path = os.path.join(HERE, "clip_vectors.npz")
     np.savez_compressed(path, **out)
-    print("wrote", path, os.path.getsize(path), "bytes; grad norms", norms)
+    print("wrote", path, os.path.getsize(path), "bytes; seed", seed)
 
 
 if __name__ == "__main__":
